@@ -1,0 +1,265 @@
+// TEST INFRASTRUCTURE -- NOT PRODUCT CODE.  C ABI over oracle/sofa_oracle.hpp for ctypes
+// (tests/, __graft_entry__.smoke(), bench.py cpu_baseline / --impl reference only).
+// `real`: 0 = float (Vec3f build of the reference), 1 = double (Vec3d).  State arrays are
+// AoS Vec3 of that Real; indices are uint32 (sofa::Index).
+#include "sofa_oracle.hpp"
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <thread>
+
+using namespace orc;
+
+namespace {
+template <class R> std::vector<Vec3<R>> toVec(const void* p, size_t n) {
+    std::vector<Vec3<R>> v(n);
+    if (p && n) std::memcpy(v.data(), p, n * sizeof(Vec3<R>));
+    return v;
+}
+template <class R> void fromVec(const std::vector<Vec3<R>>& v, void* p) { if (!v.empty()) std::memcpy(p, v.data(), v.size() * sizeof(Vec3<R>)); }
+
+struct SceneAny {
+    int real;
+    Scene<float> f;
+    Scene<double> d;
+    int threads = 1;  // >1: MultiThreading-plugin style parallel addDForce for the CPU baseline
+};
+template <class R> Scene<R>& S(SceneAny* s);
+template <> Scene<float>& S<float>(SceneAny* s) { return s->f; }
+template <> Scene<double>& S<double>(SceneAny* s) { return s->d; }
+
+#define DISPATCH(h, ...)                         \
+    do {                                         \
+        SceneAny* s_ = static_cast<SceneAny*>(h);\
+        if (s_->real == 0) { typedef float R; Scene<R>& sc = s_->f; (void)sc; __VA_ARGS__; } \
+        else { typedef double R; Scene<R>& sc = s_->d; (void)sc; __VA_ARGS__; }            \
+    } while (0)
+
+void fillReal(std::vector<float>& dst, const double* src, int n) { dst.resize(n); for (int i = 0; i < n; ++i) dst[i] = float(src[i]); }
+void fillReal(std::vector<double>& dst, const double* src, int n) { dst.assign(src, src + n); }
+
+template <class R> void copyOut(const std::vector<R>& v, void* out) { if (!v.empty()) std::memcpy(out, v.data(), v.size() * sizeof(R)); }
+template <class R> void copyMats(const std::vector<Mat3<R>>& v, void* out) { if (!v.empty()) std::memcpy(out, v.data(), v.size() * sizeof(Mat3<R>)); }
+
+// ParallelTetrahedronFEMForceField::addDForce restated for the CPU baseline:
+// applications/plugins/MultiThreading/src/MultiThreading/component/solidmechanics/fem/elastic/ParallelTetrahedronFEMForceField.inl:67-99
+// (element ranges over threads, thread-local df, merged under a mutex).  Summation order differs from the
+// sequential loop exactly as it does in the reference plugin, so this is a TIMING variant, not a parity one.
+template <class R> void parallelTetAddDForce(TetFEM<R>& ff, VecDeriv<R>& df, const VecDeriv<R>& dx, double kf, int nthreads) {
+    const size_t T = ff.nbTets();
+    std::mutex mtx;
+    std::vector<std::thread> pool;
+    const R kFactor = R(kf);
+    for (int t = 0; t < nthreads; ++t) {
+        pool.emplace_back([&, t]() {
+            const size_t lo = T * t / nthreads, hi = T * (t + 1) / nthreads;
+            VecDeriv<R> local(dx.size());
+            if (ff.method == SMALL) for (size_t i = lo; i < hi; ++i) ff.applyStiffnessSmall(local, dx, i, kFactor);
+            else for (size_t i = lo; i < hi; ++i) ff.applyStiffnessCorotational(local, dx, i, kFactor);
+            std::lock_guard<std::mutex> g(mtx);
+            for (size_t i = 0; i < df.size(); ++i) df[i] += local[i];
+        });
+    }
+    for (auto& th : pool) th.join();
+}
+}  // namespace
+
+extern "C" {
+
+// ---- mesh generation ------------------------------------------------------------------------------------------
+void orc_grid(int nx, int ny, int nz, const double* mn, const double* mx, double* pos_out, uint32_t* hex_out) {
+    GridMesh g = regularGrid(nx, ny, nz, mn, mx);
+    std::memcpy(pos_out, g.pos.data(), g.pos.size() * sizeof(double));
+    if (hex_out && !g.hexas.empty()) std::memcpy(hex_out, g.hexas.data(), g.hexas.size() * sizeof(uint32_t));
+}
+void orc_hexas_to_tetras(int nx, int ny, int nz, int mode, uint32_t* tets_out) {
+    const double z[3] = {0, 0, 0}, o[3] = {1, 1, 1};
+    GridMesh g = regularGrid(nx, ny, nz, z, o);
+    std::vector<uint32_t> t = hexasToTetras(g, mode);
+    std::memcpy(tets_out, t.data(), t.size() * sizeof(uint32_t));
+}
+
+// ---- restated sofa::type / helper::Decompose math, for bit-for-bit comparison with oracle/_ref ----------------
+#define MATH(SFX, R)                                                                                                  \
+    R orc_polar_##SFX(const R* M, R* Q) { Mat3<R> m, q; std::memcpy(m.m, M, sizeof(m.m)); R det = Decompose<R>::polarDecomposition(m, q); std::memcpy(Q, q.m, sizeof(q.m)); return det; } \
+    int orc_polar_stable_##SFX(const R* M, R* Q) { Mat3<R> m, q; std::memcpy(m.m, M, sizeof(m.m)); bool d = Decompose<R>::polarDecomposition_stable(m, q); std::memcpy(Q, q.m, sizeof(q.m)); return d; } \
+    int orc_svd_stable_##SFX(const R* F, R* U, R* Sd, R* V) { Mat3<R> f, u, v; Vec3<R> s; std::memcpy(f.m, F, sizeof(f.m)); bool d = Decompose<R>::SVD_stable(f, u, s, v); std::memcpy(U, u.m, sizeof(u.m)); std::memcpy(V, v.m, sizeof(v.m)); std::memcpy(Sd, s.v, sizeof(s.v)); return d; } \
+    int orc_mat3_invert_##SFX(const R* A, R* Ai) { Mat3<R> a, i; std::memcpy(a.m, A, sizeof(a.m)); bool ok = invertMatrix(i, a); std::memcpy(Ai, i.m, sizeof(i.m)); return ok; } \
+    R orc_mat3_det_##SFX(const R* A) { Mat3<R> a; std::memcpy(a.m, A, sizeof(a.m)); return determinant(a); }           \
+    void orc_mat3_mul_##SFX(const R* A, const R* B, R* C) { Mat3<R> a, b; std::memcpy(a.m, A, sizeof(a.m)); std::memcpy(b.m, B, sizeof(b.m)); Mat3<R> c = a * b; std::memcpy(C, c.m, sizeof(c.m)); } \
+    void orc_mat3_mul_transposed_##SFX(const R* A, const R* B, R* C) { Mat3<R> a, b; std::memcpy(a.m, A, sizeof(a.m)); std::memcpy(b.m, B, sizeof(b.m)); Mat3<R> c = a.multTransposed(b); std::memcpy(C, c.m, sizeof(c.m)); } \
+    void orc_mat3_vec_##SFX(const R* A, const R* v, R* r) { Mat3<R> a; std::memcpy(a.m, A, sizeof(a.m)); Vec3<R> x(v[0], v[1], v[2]); Vec3<R> y = a * x; std::memcpy(r, y.v, sizeof(y.v)); } \
+    void orc_mat3_tvec_##SFX(const R* A, const R* v, R* r) { Mat3<R> a; std::memcpy(a.m, A, sizeof(a.m)); Vec3<R> x(v[0], v[1], v[2]); Vec3<R> y = a.multTranspose(x); std::memcpy(r, y.v, sizeof(y.v)); } \
+    void orc_frame_large_##SFX(const R* a, const R* b, const R* c, R* Ro) { std::vector<Vec3<R>> p = {Vec3<R>(a[0], a[1], a[2]), Vec3<R>(b[0], b[1], b[2]), Vec3<R>(c[0], c[1], c[2])}; Mat3<R> r; TetFEM<R>::computeRotationLarge(r, p, 0, 1, 2); std::memcpy(Ro, r.m, sizeof(r.m)); } \
+    R orc_tet_volume_##SFX(const R* a, const R* b, const R* c, const R* d) { return DiagonalMass<R>::tetVol(Vec3<R>(a[0], a[1], a[2]), Vec3<R>(b[0], b[1], b[2]), Vec3<R>(c[0], c[1], c[2]), Vec3<R>(d[0], d[1], d[2])); }
+MATH(f, float)
+MATH(d, double)
+
+// ---- MechanicalObject vector ops on raw arrays (aliasing by pointer identity, null = no operand) ---------------
+void orc_vop(int real, size_t n, void* r, const void* a, const void* b, double k) {
+    auto run = [&](auto tag) {
+        typedef decltype(tag) R;
+        VecDeriv<R> vr = toVec<R>(r, n), va, vb;
+        const VecDeriv<R>* pa = nullptr; const VecDeriv<R>* pb = nullptr;
+        if (a) { if (a == r) pa = &vr; else { va = toVec<R>(a, n); pa = &va; } }
+        if (b) { if (b == r) pb = &vr; else if (b == a && pa != &vr) pb = pa; else { vb = toVec<R>(b, n); pb = &vb; } }
+        VOps<R>::vOp(&vr, pa, pb, k);
+        fromVec(vr, r);
+    };
+    if (real == 0) run(float()); else run(double());
+}
+double orc_vdot(int real, size_t n, const void* a, const void* b) {
+    if (real == 0) return VOps<float>::dot(toVec<float>(a, n), toVec<float>(b, n));
+    return VOps<double>::dot(toVec<double>(a, n), toVec<double>(b, n));
+}
+
+// ---- scene ------------------------------------------------------------------------------------------------------
+void* orc_scene_create(int real) { SceneAny* s = new SceneAny(); s->real = real; return s; }
+void orc_scene_destroy(void* h) { delete static_cast<SceneAny*>(h); }
+void orc_scene_set_threads(void* h, int n) { static_cast<SceneAny*>(h)->threads = n < 1 ? 1 : n; }
+
+// positions (also the rest positions) and velocities
+void orc_scene_set_state(void* h, size_t n, const void* x, const void* v) {
+    DISPATCH(h, { sc.x = toVec<R>(x, n); sc.x0 = sc.x; sc.v = toVec<R>(v, n); if (!v) sc.v.assign(n, Vec3<R>()); sc.f.assign(n, Vec3<R>()); sc.dx.assign(n, Vec3<R>()); });
+}
+void orc_scene_set_x(void* h, const void* x) { DISPATCH(h, { sc.x = toVec<R>(x, sc.x.size()); }); }
+void orc_scene_set_v(void* h, const void* v) { DISPATCH(h, { sc.v = toVec<R>(v, sc.v.size()); }); }
+
+
+// TetrahedronFEMForceField: method 0 small, 1 large, 2 polar, 3 svd; reinit() on the rest positions
+void orc_scene_set_tets(void* h, size_t T, const uint32_t* tets, int method, int ny, const double* young, int np, const double* poisson,
+                        int nlsf, const double* lsf) {
+    DISPATCH(h, {
+        sc.hasTet = true; sc.tet.method = method; sc.tet.tets.assign(tets, tets + 4 * T);
+        fillReal(sc.tet.young, young, ny); fillReal(sc.tet.poisson, poisson, np);
+        if (nlsf > 0) fillReal(sc.tet.localStiffnessFactor, lsf, nlsf); else sc.tet.localStiffnessFactor.clear();
+        sc.tet.reinit(sc.x0);
+    });
+}
+// HexahedronFEMForceField: method 0 large, 1 polar, 2 small
+void orc_scene_set_hexas(void* h, size_t H, const uint32_t* hexas, int method, int ny, const double* young, int np, const double* poisson) {
+    DISPATCH(h, {
+        sc.hasHex = true; sc.hex.method = method; sc.hex.hexas.assign(hexas, hexas + 8 * H);
+        fillReal(sc.hex.young, young, ny); fillReal(sc.hex.poisson, poisson, np);
+        sc.hex.reinit(sc.x0);
+    });
+}
+// DiagonalMass: kind 0 = massDensity, 1 = totalMass, lumped over `elems` (elemSize 4 or 8); kind 2 = explicit vertexMass array
+void orc_scene_set_mass(void* h, int kind, double value, size_t nelems, const uint32_t* elems, int elemSize, const void* vertexMass) {
+    DISPATCH(h, {
+        sc.hasMass = true;
+        if (kind == 2) { sc.mass.vertexMass.resize(sc.x.size()); std::memcpy(sc.mass.vertexMass.data(), vertexMass, sc.x.size() * sizeof(R)); }
+        else {
+            std::vector<uint32_t> e(elems, elems + nelems * elemSize);
+            if (kind == 0) sc.mass.initFromMassDensity(R(value), sc.x0, e, elemSize);
+            else sc.mass.initFromTotalMass(R(value), sc.x0, e, elemSize);
+        }
+    });
+}
+void orc_scene_set_fixed(void* h, size_t n, const uint32_t* idx, int fixAll) {
+    DISPATCH(h, { sc.fixed.assign(idx, idx + n); sc.fixAll = fixAll != 0; });
+}
+// params: [0..2] gravity, 3 dt, 4 rayleighStiffness, 5 rayleighMass, 6 vdamping, 7 firstOrder, 8 trapezoidal,
+//         9 iterations, 10 tolerance, 11 threshold, 12 warmStart, 13 massFirst, 14 ff.rayleighStiffness, 15 mass.rayleighMass
+void orc_scene_set_params(void* h, const double* p) {
+    DISPATCH(h, {
+        sc.gravity[0] = p[0]; sc.gravity[1] = p[1]; sc.gravity[2] = p[2];
+        sc.dt = p[3]; sc.rayleighStiffness = p[4]; sc.rayleighMass = p[5]; sc.vdamping = p[6];
+        sc.firstOrder = p[7] != 0; sc.trapezoidal = p[8] != 0;
+        sc.maxIter = unsigned(p[9]); sc.tolerance = p[10]; sc.threshold = p[11]; sc.warmStart = p[12] != 0;
+        sc.massFirst = p[13] != 0; sc.ffRayleighStiffness = p[14]; sc.massRayleighMass = p[15];
+    });
+}
+// One EulerImplicitSolver::solve.  Returns the "CG iterations" value (nb_iter).
+int orc_scene_step(void* h) {
+    SceneAny* s = static_cast<SceneAny*>(h);
+    int it = 0;
+    DISPATCH(h, { sc.step(); it = int(sc.lastIter); });
+    (void)s;
+    return it;
+}
+int orc_scene_end_condition(void* h) { int e = 0; DISPATCH(h, { e = sc.endCond; }); return e; }
+void orc_scene_reset_timestep_count(void* h) { DISPATCH(h, { sc.timeStepCount = 0; }); }
+
+// f += addForce(x) for the FEM force field alone (f in/out)
+void orc_scene_fem_add_force(void* h, void* f_inout, const void* x) {
+    DISPATCH(h, {
+        const size_t n = sc.x.size();
+        std::vector<Vec3<R>> saved = sc.x; sc.x = toVec<R>(x, n);
+        VecDeriv<R> F = toVec<R>(f_inout, n);
+        sc.femAddForce(F);
+        fromVec(F, f_inout); sc.x = saved;
+    });
+}
+// df += addDForce(dx) with kFactorIncludingRayleighDamping = kFactor (df in/out)
+void orc_scene_fem_add_dforce(void* h, void* df_inout, const void* dx, double kFactor) {
+    SceneAny* sa = static_cast<SceneAny*>(h);
+    DISPATCH(h, {
+        const size_t n = sc.x.size();
+        VecDeriv<R> df = toVec<R>(df_inout, n), d = toVec<R>(dx, n);
+        if (sa->threads > 1 && sc.hasTet) parallelTetAddDForce(sc.tet, df, d, kFactor, sa->threads);
+        else sc.femAddDForce(df, d, kFactor);
+        fromVec(df, df_inout);
+    });
+}
+// mop.computeForce: f = sum of addForce of the node's force fields at the scene's current x
+void orc_scene_compute_force(void* h, void* f_out) { DISPATCH(h, { VecDeriv<R> F; sc.computeForce(F); fromVec(F, f_out); }); }
+// q = project( (m M + b B + k K) p )  -- GraphScatteredMatrix::apply
+void orc_scene_apply(void* h, void* q_out, const void* p, double m, double b, double k) {
+    DISPATCH(h, {
+        const size_t n = sc.x.size();
+        sc.mFact = m; sc.bFact = b; sc.kFact = k;
+        VecDeriv<R> q, pp = toVec<R>(p, n);
+        sc.applyA(q, pp);
+        fromVec(q, q_out);
+    });
+}
+// CG on the system with factors (m,b,k); returns nb_iter.  x_inout is the initial guess when warmStart.
+int orc_scene_cg(void* h, void* x_inout, const void* b, double m, double bf, double k) {
+    int it = 0;
+    DISPATCH(h, {
+        const size_t n = sc.x.size();
+        sc.mFact = m; sc.bFact = bf; sc.kFact = k;
+        VecDeriv<R> X = toVec<R>(x_inout, n), B = toVec<R>(b, n);
+        sc.cgSolve(X, B);
+        fromVec(X, x_inout); it = int(sc.lastIter);
+    });
+    return it;
+}
+size_t orc_scene_graph(void* h, int which, double* out, size_t cap) {
+    size_t n = 0;
+    DISPATCH(h, { const std::vector<double>& g = which == 0 ? sc.graphError : sc.graphDen; n = g.size(); for (size_t i = 0; i < n && i < cap; ++i) out[i] = g[i]; });
+    return n;
+}
+// Named array getter.  Returns the number of Real (or uint32) scalars written; call with out = nullptr for the count.
+size_t orc_scene_get(void* h, const char* what, void* out) {
+    const std::string w(what);
+    size_t cnt = 0;
+    DISPATCH(h, {
+        auto vec3 = [&](const std::vector<Vec3<R>>& v) { cnt = 3 * v.size(); if (out) fromVec(v, out); };
+        auto mats = [&](const std::vector<Mat3<R>>& v) { cnt = 9 * v.size(); if (out) copyMats(v, out); };
+        auto reals = [&](const std::vector<R>& v) { cnt = v.size(); if (out) copyOut(v, out); };
+        if (w == "x") vec3(sc.x); else if (w == "v") vec3(sc.v); else if (w == "f") vec3(sc.lastForce);
+        else if (w == "b") vec3(sc.lastB); else if (w == "sol") vec3(sc.lastSol); else if (w == "x0") vec3(sc.x0);
+        else if (w == "vertexMass") reals(sc.mass.vertexMass);
+        else if (w == "tet.rotations") mats(sc.tet.rotations); else if (w == "tet.initialRotations") mats(sc.tet.initialRotations);
+        else if (w == "tet.initialTransformation") mats(sc.tet.initialTransformation);
+        else if (w == "tet.J") reals(sc.tet.J); else if (w == "tet.K") reals(sc.tet.K); else if (w == "tet.X0") vec3(sc.tet.X0);
+        else if (w == "hex.rotations") mats(sc.hex.rotations); else if (w == "hex.initialRotations") mats(sc.hex.initialRotations);
+        else if (w == "hex.Ke") reals(sc.hex.Ke); else if (w == "hex.X0") vec3(sc.hex.X0); else if (w == "hex.Kmat") reals(sc.hex.Kmat);
+    });
+    return cnt;
+}
+// full reference-shaped matrices of one tetrahedron (for the golden vectors): J 12x6, K 6x6, row-major, as double
+void orc_scene_tet_matrices(void* h, size_t e, double* J72, double* K36) {
+    DISPATCH(h, {
+        R j[72], k[36];
+        sc.tet.strainDisplacementMatrix(e, j); sc.tet.materialStiffnessMatrix(e, k);
+        for (int i = 0; i < 72; ++i) J72[i] = j[i];
+        for (int i = 0; i < 36; ++i) K36[i] = k[i];
+    });
+}
+double orc_scene_hex_potential_energy(void* h) { double e = 0; DISPATCH(h, { e = sc.hex.potentialEnergy; }); return e; }
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+"""Pin the oracle against the golden vectors of the reference's own tests.
+Sources (relative to /root/reference/Sofa/Component/SolidMechanics/FEM/Elastic/tests):
+  BaseTetrahedronFEMForceField_test.h:286-315   single tetra `2 3 1 0`, E=1000 nu=0.3, method=large
+  BaseTetrahedronFEMForceField_test.h:379-431   4x10x4 grid beam, 100 EulerImplicit+CG steps, element 100
+  TetrahedronFEMForceField_stepTest.cpp:53-83   regular tetra stretched in z, method=small, E=40 nu=0
+  HexahedronFEMForceField_test.cpp:55-91        unit cube stretched to z=1.1, method=small, E=10 nu=0
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+TOL = 1e-4  # EXPECT_NEAR(..., 1e-4) in the reference tests
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_single_tetra_large_init(dtype):
+    x = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype)
+    s = O.OracleScene(dtype, x)
+    s.set_tets(np.array([[2, 3, 1, 0]], np.uint32), "large", 1000.0, 0.3)
+    exp_initRot = np.array([[0, 0.816497, 0.57735], [-0.707107, -0.408248, 0.57735], [0.707107, -0.408248, 0.57735]])
+    exp_initPos = np.array([[0, 0, 0], [1.41421, 0, 0], [0.707107, 1.22474, 0], [0.707107, 0.408248, -0.57735]])
+    exp_K = np.zeros((6, 6)); exp_K[:3, :3] = 96.1538; exp_K[[0, 1, 2], [0, 1, 2]] = 224.359; exp_K[[3, 4, 5], [3, 4, 5]] = 64.1026
+    exp_J = np.array([[0.707107, 0, 0, 0.408248, 0, -0.57735], [0, 0.408248, 0, 0.707107, -0.57735, 0], [0, 0, -0.57735, 0, 0.408248, 0.707107],
+                      [-0.707107, 0, 0, 0.408248, 0, -0.57735], [0, 0.408248, 0, -0.707107, -0.57735, 0], [0, 0, -0.57735, 0, 0.408248, -0.707107],
+                      [-0, 0, 0, -0.816497, 0, -0.57735], [0, -0.816497, 0, -0, -0.57735, 0], [0, 0, -0.57735, 0, -0.816497, 0],
+                      [0, 0, 0, -0, 0, 1.73205], [0, 0, 0, 0, 1.73205, 0], [0, 0, 1.73205, 0, 0, 0]])
+    # getInitialTetraRotation = _initialRotations, getActualTetraRotation = rotations (both R^T)
+    assert np.abs(s.get("tet.initialRotations")[0] - exp_initRot).max() < TOL
+    assert np.abs(s.get("tet.rotations")[0] - exp_initRot).max() < TOL
+    assert np.abs(s.get("tet.X0")[0] - exp_initPos).max() < TOL
+    J, K = s.tet_matrices(0)
+    assert np.abs(K - exp_K).max() < 1e-3  # 6 significant digits printed: 224.359
+    assert np.abs(J - exp_J).max() < TOL
+
+
+def _grid_beam(dtype):
+    pos, hexas = O.regular_grid((4, 10, 4), (0, 0, 20), (10, 40, 30))
+    tets = O.hexas_to_tetras((4, 10, 4), 0)  # Hexa2TetraTopologicalMapping, swapping default false
+    s = O.OracleScene(dtype, pos)
+    s.set_params(gravity=(0, 10, 0), dt=0.01, iterations=20, tolerance=1e-5, threshold=1e-6)
+    s.set_mass_density(1.0, tets)
+    s.set_tets(tets, "large", 600.0, 0.3)
+    s.set_fixed(O.box_roi(pos, (-1, -1, 0, 10, 1, 50)))
+    return s, pos
+
+
+def test_grid_beam_100_steps_double():
+    s, pos = _grid_beam(np.float64)
+    assert pos.shape[0] == 160
+    assert np.abs(pos[159] - [10, 40, 30]).max() < TOL
+    for _ in range(100):
+        s.step()
+    x = s.get("x")
+    assert np.abs(x[159] - [9.99985, 45.0487, 30.0011]).max() < TOL
+    exp_initRot = np.array([[-1, 0, 0], [0, -0.8, -0.6], [0, -0.6, 0.8]])
+    exp_initPos = np.array([[0, 0, 0], [3.33333, 0, 0], [3.33333, 5.55556, 0], [0, 3.55556, 2.66667]])
+    exp_curRot = np.array([[-1, 8.01488e-06, 0.000541687], [-0.000320764, -0.814541, -0.580106], [0.000436576, -0.580106, 0.814541]])
+    exp_K = np.zeros((6, 6)); exp_K[:3, :3] = 1.16827; exp_K[[0, 1, 2], [0, 1, 2]] = 2.72596; exp_K[[3, 4, 5], [3, 4, 5]] = 0.778846
+    exp_J = np.array([[-14.8148, 0, 0, 1.18424e-14, 0, -18.5185], [0, 1.18424e-14, 0, -14.8148, -18.5185, 0], [0, 0, -18.5185, 0, 1.18424e-14, -14.8148],
+                      [14.8148, 0, 0, -8.88889, 0, 11.8519], [0, -8.88889, 0, 14.8148, 11.8519, 0], [0, 0, 11.8519, 0, -8.88889, 14.8148],
+                      [-0, 0, 0, 8.88889, 0, -11.8519], [0, 8.88889, 0, -0, -11.8519, 0], [0, 0, -11.8519, 0, 8.88889, -0],
+                      [0, 0, 0, -1.18424e-14, 0, 18.5185], [0, -1.18424e-14, 0, 0, 18.5185, 0], [0, 0, 18.5185, 0, -1.18424e-14, 0]])
+    e = 100
+    assert np.abs(s.get("tet.initialRotations")[e] - exp_initRot).max() < TOL
+    assert np.abs(s.get("tet.X0")[e] - exp_initPos).max() < TOL
+    assert np.abs(s.get("tet.rotations")[e] - exp_curRot).max() < TOL
+    J, K = s.tet_matrices(e)
+    assert np.abs(K - exp_K).max() < TOL
+    assert np.abs(J - exp_J).max() < TOL
+
+
+def test_grid_beam_float_tracks_double():
+    """Vec3f build of the same scene stays within the reference test's own 1e-4 band for a few steps."""
+    sd, _ = _grid_beam(np.float64)
+    sf, _ = _grid_beam(np.float32)
+    for _ in range(10):
+        sd.step(); sf.step()
+    assert np.abs(sd.get("x") - sf.get("x")).max() < 1e-3
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_tetra_small_force_kat(dtype):
+    x0 = np.array([[0, 0, 0], [1, 0, 0], [0.5, 0.86602540378443864676, 0], [0.5, 0.288675134594812882254, 1]], dtype)
+    s = O.OracleScene(dtype, x0)
+    s.set_tets(np.array([[0, 1, 2, 3]], np.uint32), "small", 40.0, 0.0)
+    x = np.array([[0, 0, 0], [1, 0, 0], [0.5, 0.8660254037, 0], [0.5, 0.28867513, 2]], dtype)
+    f = s.fem_add_force(np.zeros((4, 3), dtype), x)
+    fdown, fup = np.sqrt(3.0) * 10.0 / 9.0, np.sqrt(3.0) * 10.0 / 3.0
+    exp = np.array([[0, 0, fdown]] * 3 + [[0, 0, -fup]])
+    assert np.abs(f - exp).max() < (1e-6 if dtype == np.float64 else 1e-5)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_hexa_small_force_kat(dtype):
+    x0 = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], dtype)
+    s = O.OracleScene(dtype, x0)
+    s.set_hexas(np.arange(8, dtype=np.uint32)[None, :], "small", 10.0, 0.0)
+    x = x0.copy(); x[4:, 2] = 1.1
+    f = s.fem_add_force(np.zeros((8, 3), dtype), x)
+    exp = np.array([[0, 0, 0.25]] * 4 + [[0, 0, -0.25]] * 4)
+    assert np.abs(f - exp).max() < (1e-9 if dtype == np.float64 else 1e-6)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("method", ["small", "large", "polar", "svd"])
+def test_tetra_dforce_is_force_derivative(dtype, method):
+    """ForceField_test::checkComputeDf (SolidMechanics/Testing ForceFieldTestCreation.h:197-213):
+    addDForce(dx) ~ f(x+dx) - f(x) for a small perturbation."""
+    rng = np.random.default_rng(5)
+    pos, _ = O.regular_grid((3, 3, 4), (0, 0, 0), (1, 1, 2))
+    tets = O.hexas_to_tetras((3, 3, 4), 1)
+    s = O.OracleScene(dtype, pos)
+    s.set_tets(tets, method, 1000.0, 0.3)
+    x = (pos + 0.02 * rng.standard_normal(pos.shape)).astype(dtype)
+    eps = 1e-6 if dtype == np.float64 else 1e-3
+    dx = (eps * rng.standard_normal(pos.shape)).astype(dtype)
+    z = np.zeros_like(x)
+    f0 = s.fem_add_force(z, x)            # also caches rotations at x
+    df = s.fem_add_dforce(z, dx, 1.0)
+    f1 = s.fem_add_force(z, (x + dx).astype(dtype))
+    num = f1.astype(np.float64) - f0
+    # corotational addDForce ignores dR/dx, so this is first-order only: compare at 5%
+    rel = np.linalg.norm(df - num) / np.linalg.norm(num)
+    assert rel < (0.06 if method != "small" else (1e-6 if dtype == np.float64 else 2e-2)), rel
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_vop_semantics(dtype):
+    """Cases pinned by StateContainer/tests/MechanicalObjectVOp_test.cpp:770-979."""
+    rng = np.random.default_rng(7)
+    a = rng.standard_normal((50, 3)).astype(dtype); b = rng.standard_normal((50, 3)).astype(dtype)
+    k = 0.37
+    kr = dtype(k)
+    r = a.copy(); O.vop(dtype, r, None, None, k); assert not r.any()                       # r = 0
+    r = a.copy(); O.vop(dtype, r, None, r, k); assert np.array_equal(r, a * kr)            # r *= k
+    r = a.copy(); O.vop(dtype, r, None, b, k); assert np.array_equal(r, b * kr)            # r = b*k
+    r = a.copy(); O.vop(dtype, r, b, None, k); assert np.array_equal(r, b)                 # r = a
+    r = a.copy(); O.vop(dtype, r, r, b, 1.0); assert np.array_equal(r, a + b)              # r += b
+    r = a.copy(); O.vop(dtype, r, r, b, k); assert np.array_equal(r, a + b * kr)           # r += b*k
+    r = a.copy(); O.vop(dtype, r, b, r, k); assert np.array_equal(r, a * kr + b)           # r = a + r*k
+    r = np.zeros_like(a); O.vop(dtype, r, a, b, 1.0); assert np.array_equal(r, a + b)      # r = a + b
+    r = np.zeros_like(a); O.vop(dtype, r, a, b, k); assert np.array_equal(r, a + b * kr)   # r = a + b*k
+    d = O.vdot(dtype, a, b)
+    assert abs(d - float(np.sum(a.astype(np.float64) * b))) < (1e-12 if dtype == np.float64 else 1e-4)
