@@ -1,0 +1,222 @@
+/*
+ * sofa_b200.h -- C ABI of the B200-native implicit-dynamics FEM hot path for SOFA.
+ *
+ * This is the drop-in boundary: plain C, opaque handles, raw pointers and sizes, int status
+ * returns.  A SOFA plugin (sofa_b200/plugin/) specialises the reference's
+ * component templates for a device DataTypes and forwards each virtual to one entry point below;
+ * the Python/ctypes host layer used by tests/ and bench.py binds exactly the same symbols.
+ *
+ * Conventions
+ *   - `real`: SOFAB200_F32 = Vec3f build of the reference, SOFAB200_F64 = Vec3d.  State vectors are
+ *     AoS Vec3 of that Real (x0 y0 z0 x1 ...), the memory layout of sofa::type::vector<Vec<3,Real>>.
+ *   - pointers named *_dev are CUDA device pointers valid on the context's device; *_host are host
+ *     pointers.  Indices are uint32_t (sofa::Index).
+ *   - every call enqueues on the context's stream and returns without synchronising unless the
+ *     comment says "(sync)".  No entry point ever falls back to a CPU computation.
+ *   - return value: SOFAB200_OK or a negative error; sofab200_last_error() gives the text
+ *     (the plugin maps non-zero to msg_error() + ComponentState::Invalid, the reference's own
+ *     failure convention: TetrahedronFEMForceField.inl:1299-1311).
+ *
+ * Reference interfaces replaced (paths relative to the SOFA tree):
+ *   [TFF]  Sofa/Component/SolidMechanics/FEM/Elastic/src/sofa/component/solidmechanics/fem/elastic/TetrahedronFEMForceField.{h,inl}
+ *   [HFF]  .../elastic/HexahedronFEMForceField.{h,inl}
+ *   [MO]   Sofa/Component/StateContainer/src/sofa/component/statecontainer/MechanicalObject.inl
+ *   [DM]   Sofa/Component/Mass/src/sofa/component/mass/DiagonalMass.inl
+ *   [FPC]  Sofa/Component/Constraint/Projective/src/sofa/component/constraint/projective/FixedProjectiveConstraint.inl
+ *   [CG]   Sofa/Component/LinearSolver/Iterative/src/sofa/component/linearsolver/iterative/CGLinearSolver.inl
+ *   [GS]   .../iterative/GraphScatteredTypes.cpp
+ *   [EI]   Sofa/Component/ODESolver/Backward/src/sofa/component/odesolver/backward/EulerImplicitSolver.cpp
+ *   [CUDA] applications/plugins/SofaCUDA/Component/src/SofaCUDA/component/solidmechanics/fem/elastic/CudaTetrahedronFEMForceField.inl:31-55
+ *          (the extern "C" kernel-launcher layer of the incumbent GPU plugin, whose role this header takes)
+ */
+#ifndef SOFA_B200_H
+#define SOFA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOFAB200_OK 0
+#define SOFAB200_ERR_INVALID (-1)  /* bad argument / inconsistent sizes                        */
+#define SOFAB200_ERR_CUDA (-2)     /* a CUDA runtime call failed (text in sofab200_last_error) */
+#define SOFAB200_ERR_NO_DEVICE (-3)/* no CUDA device: this library never computes on the CPU   */
+#define SOFAB200_ERR_UNSUPPORTED (-4)
+
+typedef enum { SOFAB200_F32 = 0, SOFAB200_F64 = 1 } sofab200_real;
+
+/* TetrahedronFEMForceField `method` Data ([TFF].h:75-77, setMethod .inl) */
+typedef enum { SOFAB200_TET_SMALL = 0, SOFAB200_TET_LARGE = 1, SOFAB200_TET_POLAR = 2, SOFAB200_TET_SVD = 3 } sofab200_tet_method;
+/* HexahedronFEMForceField method numbering ([HFF].h setMethod: 0 large, 1 polar, 2 small) */
+typedef enum { SOFAB200_HEX_LARGE = 0, SOFAB200_HEX_POLAR = 1, SOFAB200_HEX_SMALL = 2 } sofab200_hex_method;
+
+typedef struct sofab200_ctx sofab200_ctx;       /* one device + one stream; one per force-field owner thread */
+typedef struct sofab200_tetfem sofab200_tetfem; /* TetrahedronFEMForceFieldInternalData<B200Types>            */
+typedef struct sofab200_hexfem sofab200_hexfem; /* HexahedronFEMForceFieldInternalData<B200Types>             */
+typedef struct sofab200_node sofab200_node;     /* one solver node kept resident on the device                */
+
+/* ------------------------------------------------------------------------------------------------ */
+/* library / context                                                                                */
+/* ------------------------------------------------------------------------------------------------ */
+const char* sofab200_version(void);
+/* Text of the last error raised on the calling thread ("" when none). */
+const char* sofab200_last_error(void);
+/* device: CUDA ordinal.  cuda_stream: a cudaStream_t to enqueue on, or NULL to create an own
+ * non-blocking stream.  Replaces mycudaInit() (SofaCUDA/Core/src/sofa/gpu/cuda/mycuda.cu:142-155). */
+int sofab200_ctx_create(int device, void* cuda_stream, sofab200_ctx** out);
+int sofab200_ctx_destroy(sofab200_ctx* ctx);
+int sofab200_ctx_set_stream(sofab200_ctx* ctx, void* cuda_stream);
+int sofab200_ctx_synchronize(sofab200_ctx* ctx); /* (sync) */
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t sofab200_ctx_launch_count(const sofab200_ctx* ctx);
+/* Per-kernel-class device timing with CUDA events recorded on the context's stream around every launch
+ * (replaces SofaCUDA's CUDA_TIMER_SYNC env switch, mycuda.cpp:146).  Classes:
+ *   0 element pass of addDForce / A*p   1 boundary gather   2 element pass of addForce   3 CG / vector kernels
+ * profile_begin enables recording; profile_end (sync) disables it and returns, per class, the summed
+ * milliseconds and the number of launches.  total_ms / count: arrays of SOFAB200_PROFILE_CLASSES. */
+#define SOFAB200_PROFILE_CLASSES 4
+int sofab200_ctx_profile_begin(sofab200_ctx* ctx);
+int sofab200_ctx_profile_end(sofab200_ctx* ctx, double* total_ms, uint64_t* count);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* MechanicalObject<B200Vec3Types> vector operations  -- [MO]                                       */
+/* ------------------------------------------------------------------------------------------------ */
+/* MechanicalObject::vOp(r, a, b, k) [MO]:2075-2203.  a_dev / b_dev NULL == null VecId:
+ *   a,b null: r = 0 | a null, b==r: r *= k | a null: r = b*k | b null: r = a | r==a: r += b*k
+ *   | r==b: r = a + r*k | else r = a + b*k   (k == 1 takes the reference's multiplication-free forms). */
+int sofab200_mo_vop(sofab200_ctx* ctx, sofab200_real real, size_t n, void* r_dev, const void* a_dev, const void* b_dev, double k);
+/* MechanicalObject::vDot [MO]:2333-2356.  Accumulated in double with a fixed-order tree (run-to-run
+ * reproducible); the reference's serial Real accumulation order cannot be kept in parallel. (sync) */
+int sofab200_mo_vdot(sofab200_ctx* ctx, sofab200_real real, size_t n, const void* a_dev, const void* b_dev, double* result_host);
+/* MechanicalObject::vMultiOp integration fast path [MO]:2208-2241: v += a*f_v_a ; x += v*f_x_v. */
+int sofab200_mo_vmultiop_integrate(sofab200_ctx* ctx, sofab200_real real, size_t n, void* v_dev, void* x_dev, const void* a_dev, double f_v_a, double f_x_v);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* DiagonalMass / FixedProjectiveConstraint pieces of A*p and of the right-hand side                  */
+/* ------------------------------------------------------------------------------------------------ */
+/* DiagonalMass::addMDx [DM]:535-559: res[i] += (dx[i]*m[i])*factor  (factor==1: res[i] += dx[i]*m[i]). */
+int sofab200_mass_add_mdx(sofab200_ctx* ctx, sofab200_real real, size_t n, void* res_dev, const void* dx_dev, const void* vertex_mass_dev, double factor);
+/* DiagonalMass::addForce [DM]:1392-1413: f[i] += gravity*m[i]. */
+int sofab200_mass_add_force(sofab200_ctx* ctx, sofab200_real real, size_t n, void* f_dev, const void* vertex_mass_dev, const double gravity[3]);
+/* DiagonalMass::accFromF [DM]:563-575: a[i] = f[i]/m[i]. */
+int sofab200_mass_acc_from_f(sofab200_ctx* ctx, sofab200_real real, size_t n, void* a_dev, const void* f_dev, const void* vertex_mass_dev);
+/* FixedProjectiveConstraint::projectResponse / projectVelocity [FPC]:183-206,236-258. */
+int sofab200_fixed_project_response(sofab200_ctx* ctx, sofab200_real real, size_t n, void* res_dev, size_t n_indices, const uint32_t* indices_dev, int fix_all);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* TetrahedronFEMForceField<B200Vec3Types>  -- [TFF]                                                 */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct sofab200_tetfem_desc {
+    int method;                 /* sofab200_tet_method  (Data `method`)                                    */
+    size_t n_young;             /* Data `youngModulus`: one value, or one per element                      */
+    const double* young;
+    size_t n_poisson;           /* Data `poissonRatio`: idem                                               */
+    const double* poisson;
+    size_t n_local_stiffness;   /* Data `localStiffnessFactor` (may be 0)                                  */
+    const double* local_stiffness;
+    int tile_elems;             /* elements per CTA tile of the device layout; 0 = library default         */
+} sofab200_tetfem_desc;
+
+/* init()+reinit() [TFF].inl:1257-1545: per-element material stiffness, rest rotation, rotated rest
+ * shape and strain-displacement terms are computed in the reference's arithmetic, then laid out in
+ * HBM as CTA tiles with a deterministic gather plan.  rest_position_host: n_nodes Vec3 of `real`
+ * (the MechanicalObject's restPosition); tets_host: n_tets x 4 indices in topology order. (sync) */
+int sofab200_tetfem_create(sofab200_ctx* ctx, sofab200_real real, size_t n_nodes, const void* rest_position_host,
+                           size_t n_tets, const uint32_t* tets_host, const sofab200_tetfem_desc* desc, sofab200_tetfem** out);
+int sofab200_tetfem_destroy(sofab200_tetfem* ff);
+/* addForce(mparams, f, x, v) [TFF].inl:1548-1604: f += elastic forces at x; caches rotations[e]. */
+int sofab200_tetfem_add_force(sofab200_tetfem* ff, void* f_dev, const void* x_dev);
+/* addDForce(mparams, df, dx) [TFF].inl:1606-1636 with k_factor = kFactorIncludingRayleighDamping
+ * (MechanicalParams.h:62): df -= R K_e R^T dx * k_factor using the cached rotations. */
+int sofab200_tetfem_add_dforce(sofab200_tetfem* ff, void* df_dev, const void* dx_dev, double k_factor);
+/* Element-ordered copies for inspection / parity (sync).  what:
+ *   "rotations" (T x 9, rotations[e] = R^T, [TFF].inl:880), "initialRotations" (T x 9),
+ *   "strainDisplacements" (T x 12: the 12 distinct cofactors), "materialsStiffnesses" (T x 3: K00,K01,K33),
+ *   "rotatedInitialElements" (T x 12), "initialTransformation" (T x 9, svd only). */
+int sofab200_tetfem_get(sofab200_tetfem* ff, const char* what, void* out_host);
+/* Layout statistics: out[0]=tiles, [1]=elements per tile, [2]=interior nodes, [3]=shared nodes,
+ * [4]=staged (HBM) corner contributions, [5]=dynamic shared memory bytes, [6]=max valence, [7]=n_tets */
+int sofab200_tetfem_stats(const sofab200_tetfem* ff, uint64_t out[8]);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* HexahedronFEMForceField<B200Vec3Types>  -- [HFF]                                                  */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct sofab200_hexfem_desc {
+    int method;                 /* sofab200_hex_method */
+    size_t n_young;
+    const double* young;
+    size_t n_poisson;
+    const double* poisson;
+    int tile_elems;
+} sofab200_hexfem_desc;
+int sofab200_hexfem_create(sofab200_ctx* ctx, sofab200_real real, size_t n_nodes, const void* rest_position_host,
+                           size_t n_hexas, const uint32_t* hexas_host, const sofab200_hexfem_desc* desc, sofab200_hexfem** out);
+int sofab200_hexfem_destroy(sofab200_hexfem* ff);
+/* addForce [HFF].inl:194-246 / addDForce [HFF].inl:248-286 */
+int sofab200_hexfem_add_force(sofab200_hexfem* ff, void* f_dev, const void* x_dev);
+int sofab200_hexfem_add_dforce(sofab200_hexfem* ff, void* df_dev, const void* dx_dev, double k_factor);
+/* what: "rotations" (H x 9, _rotations[e] = R), "elementStiffnesses" (H x 576), "rotatedInitialElements" (H x 24) */
+int sofab200_hexfem_get(sofab200_hexfem* ff, const char* what, void* out_host);
+int sofab200_hexfem_stats(const sofab200_hexfem* ff, uint64_t out[8]);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* One solver node resident on the device: EulerImplicitSolver + CGLinearSolver<GraphScattered> over  */
+/* {MechanicalObject, DiagonalMass, one FEM force field, FixedProjectiveConstraint}  -- [EI][CG][GS]  */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct sofab200_node_desc {
+    sofab200_tetfem* tetfem;        /* exactly one of tetfem / hexfem                                     */
+    sofab200_hexfem* hexfem;
+    const void* vertex_mass_host;   /* DiagonalMass `vertexMass` (n Reals) or NULL for no mass            */
+    size_t n_fixed;                 /* FixedProjectiveConstraint `indices`                                */
+    const uint32_t* fixed_host;
+    int fix_all;                    /* Data `fixAll`                                                      */
+    int mass_first;                 /* 1: the mass precedes the force field in the scene (all reference scenes) */
+} sofab200_node_desc;
+
+typedef struct sofab200_solver_params {
+    double gravity[3];              /* context gravity                                                    */
+    double dt;
+    double rayleigh_stiffness;      /* EulerImplicitSolver Data [EI]:40-50                                */
+    double rayleigh_mass;
+    double vdamping;
+    int first_order;
+    int trapezoidal;
+    unsigned iterations;            /* CGLinearSolver Data [CG]:35-45                                     */
+    double tolerance;
+    double threshold;
+    int warm_start;
+    double ff_rayleigh_stiffness;   /* BaseForceField::rayleighStiffness of the FEM component             */
+    double mass_rayleigh_mass;      /* Mass::rayleighMass of the mass component                           */
+} sofab200_solver_params;
+
+int sofab200_node_create(sofab200_ctx* ctx, sofab200_real real, size_t n_nodes, const sofab200_node_desc* desc, sofab200_node** out);
+int sofab200_node_destroy(sofab200_node* node);
+int sofab200_node_set_params(sofab200_node* node, const sofab200_solver_params* p);
+/* mop.computeForce: f = sum of addForce over the node's force fields in scene order
+ * (MappingGraphMechanicalOperations.cpp:41-93): one fused pass, gravity term + element forces. */
+int sofab200_node_compute_force(sofab200_node* node, void* f_dev, const void* x_dev);
+/* GraphScatteredMatrix::apply [GS]:33-46: q = project((m M + b B + k K) p), fused in one pass. */
+int sofab200_node_apply(sofab200_node* node, void* q_dev, const void* p_dev, double m_factor, double b_factor, double k_factor);
+/* CGLinearSolver::solve [CG]:73-315 for the matrix-free system (m M + b B + k K), entirely on the
+ * device: no host round trip per iteration.  x_dev: solution (initial guess when warm_start).
+ * nb_iter_host: NULL = leave the result on the device (async); else (sync) receives "CG iterations". */
+int sofab200_node_cg_solve(sofab200_node* node, void* x_dev, const void* b_dev, double m_factor, double b_factor, double k_factor, int* nb_iter_host);
+/* EulerImplicitSolver::solve [EI]:83-341 on device-resident x, v (async). */
+int sofab200_node_step(sofab200_node* node, void* x_dev, void* v_dev);
+/* The same step for HOST state vectors (pinned or pageable): H2D of x,v, step, D2H of x,v. (sync) */
+int sofab200_node_step_host(sofab200_node* node, void* x_host, void* v_host);
+/* Results of the last solve (sync): nb_iter ("CG iterations" as the reference reports it), end condition
+ * (0 iterations exhausted, 1 tolerance, 2 threshold, 3 den==0, 4 b==0), and the `graph` Data
+ * (Error / Denominator histories, [CG]:109-116,148,213).  Any pointer may be NULL. */
+int sofab200_node_last_solve(sofab200_node* node, int* nb_iter, int* end_cond, double* graph_error, size_t* n_error, double* graph_den, size_t* n_den, size_t cap);
+/* Device vectors of the last step for parity checks (sync): "f" (force), "b" (right-hand side), "dx" (solution) */
+int sofab200_node_get(sofab200_node* node, const char* what, void* out_host);
+/* CGLinearSolver keeps `timeStepCount` to silence first-step warnings ([CG]:161-176); reset() restores 0. */
+int sofab200_node_reset(sofab200_node* node);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOFA_B200_H */

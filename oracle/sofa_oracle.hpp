@@ -25,6 +25,8 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 namespace orc {
@@ -1013,6 +1015,16 @@ template <class R> struct Scene {
     // CGLinearSolver Data (CGLinearSolver.inl:35-45)
     unsigned maxIter = 25; double tolerance = 1e-5, threshold = 1e-5; bool warmStart = false;
     unsigned timeStepCount = 0;
+    // TEST KNOB (not a reference Data): accumulate the CG dot products in double instead of the reference's serial
+    // Real accumulation (MechanicalObject.inl:2333-2356).  Used to separate "the dot product is summed in another
+    // order / precision" (inherent to any parallel implementation) from every other source of difference.
+    bool dotDouble = false;
+    SReal sdot(const VecDeriv<R>& a, const VecDeriv<R>& b) const {
+        if (!dotDouble) return VOps<R>::dot(a, b);
+        double r = 0.0;
+        for (size_t i = 0; i < a.size(); ++i) r += double(a[i][0]) * double(b[i][0]) + double(a[i][1]) * double(b[i][1]) + double(a[i][2]) * double(b[i][2]);
+        return r;
+    }
     // outputs of the last solve
     unsigned lastIter = 0; int endCond = 0;  // 0 iterations, 1 tolerance, 2 threshold, 3 den==0, 4 b==0
     std::vector<double> graphError, graphDen;
@@ -1021,7 +1033,33 @@ template <class R> struct Scene {
     double mFact = 0, bFact = 0, kFact = 0;
 
     void femAddForce(VecDeriv<R>& F) { if (hasTet) tet.addForce(F, x); if (hasHex) hex.addForce(F, x); }
-    void femAddDForce(VecDeriv<R>& df, const VecDeriv<R>& d, double kf) { if (hasTet) tet.addDForce(df, d, kf); if (hasHex) hex.addDForce(df, d, kf); }
+    // threads > 1: the MultiThreading plugin's ParallelTetrahedronFEMForceField::addDForce
+    // (applications/plugins/MultiThreading/src/MultiThreading/component/solidmechanics/fem/elastic/ParallelTetrahedronFEMForceField.inl:67-99):
+    // element ranges over threads, thread-local df, merged under a mutex.  A TIMING variant for the CPU baseline
+    // (its summation order differs from the sequential loop exactly as it does in the reference plugin).
+    int threads = 1;
+    void parallelTetAddDForce(VecDeriv<R>& df, const VecDeriv<R>& d, double kf) {
+        df.resize(d.size());
+        const size_t T = tet.nbTets();
+        const R kFactor = R(kf);
+        std::mutex mtx;
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; ++t) {
+            pool.emplace_back([&, t]() {
+                const size_t lo = T * t / threads, hi = T * (t + 1) / threads;
+                VecDeriv<R> local(d.size());
+                if (tet.method == SMALL) for (size_t i = lo; i < hi; ++i) tet.applyStiffnessSmall(local, d, i, kFactor);
+                else for (size_t i = lo; i < hi; ++i) tet.applyStiffnessCorotational(local, d, i, kFactor);
+                std::lock_guard<std::mutex> g(mtx);
+                for (size_t i = 0; i < df.size(); ++i) df[i] += local[i];
+            });
+        }
+        for (auto& th : pool) th.join();
+    }
+    void femAddDForce(VecDeriv<R>& df, const VecDeriv<R>& d, double kf) {
+        if (hasTet) { if (threads > 1) parallelTetAddDForce(df, d, kf); else tet.addDForce(df, d, kf); }
+        if (hasHex) hex.addDForce(df, d, kf);
+    }
     // mop.computeForce: resetForce, accumulateForce (no external force), every force field's addForce in scene order
     // Sofa/framework/Simulation/Core/src/sofa/simulation/MappingGraphMechanicalOperations.cpp:41-93
     void computeForce(VecDeriv<R>& F) {
@@ -1056,12 +1094,12 @@ template <class R> struct Scene {
         SReal rho, rho_1 = 0, alpha, beta;
         if (warmStart) { applyA(r, X); VOps<R>::avf(r, b, -1.0); /* r = b + r*(-1): eq(b,r,-1) -> vOp(r,b,r,-1) */ }
         else { VOps<R>::clear(X); r = b; }
-        const SReal normb = std::sqrt(VOps<R>::dot(b, b));
+        const SReal normb = std::sqrt(sdot(b, b));
         graphError.clear(); graphError.push_back(1); graphDen.clear();
         unsigned nb_iter = 0; endCond = 0;
         if (normb != 0.0) {
             for (nb_iter = 1; nb_iter <= maxIter; nb_iter++) {
-                rho = VOps<R>::dot(r, r);
+                rho = sdot(r, r);
                 const SReal normr = std::sqrt(rho);
                 const SReal err = normr / normb;
                 graphError.push_back(err);
@@ -1072,7 +1110,7 @@ template <class R> struct Scene {
                 if (nb_iter == 1) p = r;
                 else { beta = rho / rho_1; VOps<R>::avf(p, r, beta); }
                 applyA(q, p);
-                const SReal den = VOps<R>::dot(p, q);
+                const SReal den = sdot(p, q);
                 graphDen.push_back(den);
                 if (den != 0.0) {
                     if (std::fabs(den) <= threshold) {

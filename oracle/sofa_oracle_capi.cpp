@@ -23,7 +23,6 @@ struct SceneAny {
     int real;
     Scene<float> f;
     Scene<double> d;
-    int threads = 1;  // >1: MultiThreading-plugin style parallel addDForce for the CPU baseline
 };
 template <class R> Scene<R>& S(SceneAny* s);
 template <> Scene<float>& S<float>(SceneAny* s) { return s->f; }
@@ -42,27 +41,6 @@ void fillReal(std::vector<double>& dst, const double* src, int n) { dst.assign(s
 template <class R> void copyOut(const std::vector<R>& v, void* out) { if (!v.empty()) std::memcpy(out, v.data(), v.size() * sizeof(R)); }
 template <class R> void copyMats(const std::vector<Mat3<R>>& v, void* out) { if (!v.empty()) std::memcpy(out, v.data(), v.size() * sizeof(Mat3<R>)); }
 
-// ParallelTetrahedronFEMForceField::addDForce restated for the CPU baseline:
-// applications/plugins/MultiThreading/src/MultiThreading/component/solidmechanics/fem/elastic/ParallelTetrahedronFEMForceField.inl:67-99
-// (element ranges over threads, thread-local df, merged under a mutex).  Summation order differs from the
-// sequential loop exactly as it does in the reference plugin, so this is a TIMING variant, not a parity one.
-template <class R> void parallelTetAddDForce(TetFEM<R>& ff, VecDeriv<R>& df, const VecDeriv<R>& dx, double kf, int nthreads) {
-    const size_t T = ff.nbTets();
-    std::mutex mtx;
-    std::vector<std::thread> pool;
-    const R kFactor = R(kf);
-    for (int t = 0; t < nthreads; ++t) {
-        pool.emplace_back([&, t]() {
-            const size_t lo = T * t / nthreads, hi = T * (t + 1) / nthreads;
-            VecDeriv<R> local(dx.size());
-            if (ff.method == SMALL) for (size_t i = lo; i < hi; ++i) ff.applyStiffnessSmall(local, dx, i, kFactor);
-            else for (size_t i = lo; i < hi; ++i) ff.applyStiffnessCorotational(local, dx, i, kFactor);
-            std::lock_guard<std::mutex> g(mtx);
-            for (size_t i = 0; i < df.size(); ++i) df[i] += local[i];
-        });
-    }
-    for (auto& th : pool) th.join();
-}
 }  // namespace
 
 extern "C" {
@@ -117,7 +95,8 @@ double orc_vdot(int real, size_t n, const void* a, const void* b) {
 // ---- scene ------------------------------------------------------------------------------------------------------
 void* orc_scene_create(int real) { SceneAny* s = new SceneAny(); s->real = real; return s; }
 void orc_scene_destroy(void* h) { delete static_cast<SceneAny*>(h); }
-void orc_scene_set_threads(void* h, int n) { static_cast<SceneAny*>(h)->threads = n < 1 ? 1 : n; }
+void orc_scene_set_dot_double(void* h, int on) { DISPATCH(h, { sc.dotDouble = on != 0; }); }
+void orc_scene_set_threads(void* h, int n) { DISPATCH(h, { sc.threads = n < 1 ? 1 : n; }); }
 
 // positions (also the rest positions) and velocities
 void orc_scene_set_state(void* h, size_t n, const void* x, const void* v) {
@@ -194,12 +173,10 @@ void orc_scene_fem_add_force(void* h, void* f_inout, const void* x) {
 }
 // df += addDForce(dx) with kFactorIncludingRayleighDamping = kFactor (df in/out)
 void orc_scene_fem_add_dforce(void* h, void* df_inout, const void* dx, double kFactor) {
-    SceneAny* sa = static_cast<SceneAny*>(h);
     DISPATCH(h, {
         const size_t n = sc.x.size();
         VecDeriv<R> df = toVec<R>(df_inout, n), d = toVec<R>(dx, n);
-        if (sa->threads > 1 && sc.hasTet) parallelTetAddDForce(sc.tet, df, d, kFactor, sa->threads);
-        else sc.femAddDForce(df, d, kFactor);
+        sc.femAddDForce(df, d, kFactor);
         fromVec(df, df_inout);
     });
 }

@@ -1,0 +1,327 @@
+"""Host-side mirror of the reference components on the hot path (names, Data fields and call
+signatures follow the reference; every method forwards to one C-ABI entry point of libsofa_b200.so).
+
+  MechanicalObject            Sofa/Component/StateContainer/src/sofa/component/statecontainer/MechanicalObject.inl
+  TetrahedronFEMForceField    Sofa/Component/SolidMechanics/FEM/Elastic/src/.../TetrahedronFEMForceField.{h,inl}
+  HexahedronFEMForceField     .../HexahedronFEMForceField.{h,inl}
+  DiagonalMass                Sofa/Component/Mass/src/sofa/component/mass/DiagonalMass.inl
+  FixedProjectiveConstraint   Sofa/Component/Constraint/Projective/src/.../FixedProjectiveConstraint.inl
+  SolverNode                  EulerImplicitSolver.cpp:83-341 + CGLinearSolver.inl:73-315 + GraphScatteredTypes.cpp:33-46
+
+Vectors are torch CUDA tensors of shape [N,3] (float32 for template "B200Vec3f", float64 for "B200Vec3d"):
+PyTorch only owns the memory and the stream.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import F32, F64, check
+
+TEMPLATES = {"B200Vec3f": (F32, torch.float32, np.float32), "B200Vec3d": (F64, torch.float64, np.float64),
+             "Vec3f": (F32, torch.float32, np.float32), "Vec3d": (F64, torch.float64, np.float64), "Vec3": (F64, torch.float64, np.float64)}
+TET_METHODS = {"small": 0, "large": 1, "polar": 2, "svd": 3}
+HEX_METHODS = {"large": 0, "polar": 1, "small": 2}
+_P = C.c_void_p
+
+
+def _dptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _darr(a):
+    a = np.ascontiguousarray(np.atleast_1d(np.asarray(a, np.float64)))
+    return a, a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Context:
+    """One device + one stream (sofab200_ctx).  Uses torch's current stream of that device."""
+
+    def __init__(self, device=0, stream=None):
+        self.L = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.Sofab200Error("no CUDA device: sofa_b200 has no CPU path")
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self.stream = stream if stream is not None else torch.cuda.current_stream(self.device)
+        self.h = _P()
+        check(self.L.sofab200_ctx_create(device, C.c_void_p(self.stream.cuda_stream), C.byref(self.h)))
+
+    def synchronize(self):
+        check(self.L.sofab200_ctx_synchronize(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.L.sofab200_ctx_launch_count(self.h))
+
+    PROFILE_CLASSES = ("element_pass_dforce", "boundary_gather", "element_pass_force", "cg_vector_kernels")
+
+    def profile_begin(self):
+        check(self.L.sofab200_ctx_profile_begin(self.h))
+
+    def profile_end(self):
+        ms = (C.c_double * 4)(); cnt = (C.c_uint64 * 4)()
+        check(self.L.sofab200_ctx_profile_end(self.h, ms, cnt))
+        return {k: dict(ms=ms[i], launches=int(cnt[i])) for i, k in enumerate(self.PROFILE_CLASSES)}
+
+    def __del__(self):
+        try:
+            self.L.sofab200_ctx_destroy(self.h)
+        except Exception:
+            pass
+
+
+class MechanicalObject:
+    """MechanicalObject<B200Vec3Types>: state vectors + vOp / vMultiOp / vDot."""
+
+    def __init__(self, ctx, template="B200Vec3f", position=None, velocity=None, rest_position=None):
+        self.ctx = ctx
+        self.real, self.tdtype, self.ndtype = TEMPLATES[template]
+        self.template = template
+        pos = np.ascontiguousarray(position, self.ndtype).reshape(-1, 3)
+        self.size = pos.shape[0]
+        self.rest_position_host = pos.copy() if rest_position is None else np.ascontiguousarray(rest_position, self.ndtype).reshape(-1, 3)
+        self.x = torch.from_numpy(pos).to(ctx.device)
+        self.v = torch.zeros_like(self.x) if velocity is None else torch.from_numpy(np.ascontiguousarray(velocity, self.ndtype)).to(ctx.device)
+        self.f = torch.zeros_like(self.x)
+        self.dx = torch.zeros_like(self.x)
+
+    def new_vector(self):
+        return torch.zeros_like(self.x)
+
+    def vOp(self, r, a=None, b=None, k=1.0):
+        check(self.ctx.L.sofab200_mo_vop(self.ctx.h, self.real, self.size, _dptr(r), _dptr(a), _dptr(b), float(k)))
+        return r
+
+    def vDot(self, a, b):
+        out = C.c_double()
+        check(self.ctx.L.sofab200_mo_vdot(self.ctx.h, self.real, self.size, _dptr(a), _dptr(b), C.byref(out)))
+        return out.value
+
+    def vMultiOp_integrate(self, v, x, a, f_v_a=1.0, f_x_v=1.0):
+        check(self.ctx.L.sofab200_mo_vmultiop_integrate(self.ctx.h, self.real, self.size, _dptr(v), _dptr(x), _dptr(a), float(f_v_a), float(f_x_v)))
+
+    def resetForce(self, f=None):
+        return self.vOp(self.f if f is None else f)
+
+
+class TetrahedronFEMForceField:
+    """TetrahedronFEMForceField<B200Vec3Types>.  Data: youngModulus, poissonRatio, method, localStiffnessFactor,
+    rayleighStiffness (BaseForceField)."""
+
+    def __init__(self, mstate, tetrahedra, youngModulus=5000.0, poissonRatio=0.45, method="large", localStiffnessFactor=None,
+                 rayleighStiffness=0.0, tileElems=0):
+        if method not in TET_METHODS:
+            raise ValueError(f"method must be one of {list(TET_METHODS)}")
+        self.mstate, self.ctx = mstate, mstate.ctx
+        self.method, self.rayleighStiffness = method, float(rayleighStiffness)
+        self.tetrahedra = np.ascontiguousarray(tetrahedra, np.uint32).reshape(-1, 4)
+        y, yp = _darr(youngModulus); p, pp = _darr(poissonRatio)
+        d = _lib.TetFemDesc(); d.method = TET_METHODS[method]
+        d.n_young, d.young, d.n_poisson, d.poisson = len(y), yp, len(p), pp
+        if localStiffnessFactor is not None:
+            l, lp = _darr(localStiffnessFactor); d.n_local_stiffness, d.local_stiffness = len(l), lp
+        d.tile_elems = int(tileElems)
+        self.h = _P()
+        rest = mstate.rest_position_host
+        check(self.ctx.L.sofab200_tetfem_create(self.ctx.h, mstate.real, mstate.size, rest.ctypes.data_as(_P), self.tetrahedra.shape[0],
+                                                self.tetrahedra.ctypes.data_as(_P), C.byref(d), C.byref(self.h)))
+
+    def addForce(self, f, x, v=None):
+        check(self.ctx.L.sofab200_tetfem_add_force(self.h, _dptr(f), _dptr(x)))
+
+    def addDForce(self, df, dx, kFactor=1.0, bFactor=0.0):
+        """kFactor/bFactor as in MechanicalParams; the effective factor is kFactor + bFactor*rayleighStiffness."""
+        check(self.ctx.L.sofab200_tetfem_add_dforce(self.h, _dptr(df), _dptr(dx), float(kFactor) + float(bFactor) * self.rayleighStiffness))
+
+    def get(self, what):
+        T = self.tetrahedra.shape[0]
+        shape = {"rotations": (T, 3, 3), "initialRotations": (T, 3, 3), "strainDisplacements": (T, 4, 3), "materialsStiffnesses": (T, 3),
+                 "rotatedInitialElements": (T, 4, 3), "initialTransformation": (T, 3, 3)}[what]
+        out = np.empty(shape, self.mstate.ndtype)
+        check(self.ctx.L.sofab200_tetfem_get(self.h, what.encode(), out.ctypes.data_as(_P)))
+        return out
+
+    def stats(self):
+        out = (C.c_uint64 * 8)()
+        check(self.ctx.L.sofab200_tetfem_stats(self.h, out))
+        return dict(zip(["tiles", "tile_elems", "interior_nodes", "shared_nodes", "staged_corners", "smem_bytes", "max_valence", "n_elems"], list(out)))
+
+    def __del__(self):
+        try:
+            self.ctx.L.sofab200_tetfem_destroy(self.h)
+        except Exception:
+            pass
+
+
+class HexahedronFEMForceField:
+    """HexahedronFEMForceField<B200Vec3Types>.  Data: youngModulus, poissonRatio, method (large | polar | small)."""
+
+    def __init__(self, mstate, hexahedra, youngModulus=5000.0, poissonRatio=0.45, method="large", rayleighStiffness=0.0, tileElems=0):
+        if method not in HEX_METHODS:
+            raise ValueError(f"method must be one of {list(HEX_METHODS)}")
+        self.mstate, self.ctx = mstate, mstate.ctx
+        self.method, self.rayleighStiffness = method, float(rayleighStiffness)
+        self.hexahedra = np.ascontiguousarray(hexahedra, np.uint32).reshape(-1, 8)
+        y, yp = _darr(youngModulus); p, pp = _darr(poissonRatio)
+        d = _lib.HexFemDesc(); d.method = HEX_METHODS[method]
+        d.n_young, d.young, d.n_poisson, d.poisson = len(y), yp, len(p), pp
+        d.tile_elems = int(tileElems)
+        self.h = _P()
+        rest = mstate.rest_position_host
+        check(self.ctx.L.sofab200_hexfem_create(self.ctx.h, mstate.real, mstate.size, rest.ctypes.data_as(_P), self.hexahedra.shape[0],
+                                                self.hexahedra.ctypes.data_as(_P), C.byref(d), C.byref(self.h)))
+
+    def addForce(self, f, x, v=None):
+        check(self.ctx.L.sofab200_hexfem_add_force(self.h, _dptr(f), _dptr(x)))
+
+    def addDForce(self, df, dx, kFactor=1.0, bFactor=0.0):
+        check(self.ctx.L.sofab200_hexfem_add_dforce(self.h, _dptr(df), _dptr(dx), float(kFactor) + float(bFactor) * self.rayleighStiffness))
+
+    def get(self, what):
+        H = self.hexahedra.shape[0]
+        shape = {"rotations": (H, 3, 3), "elementStiffnesses": (H, 24, 24), "rotatedInitialElements": (H, 8, 3)}[what]
+        out = np.empty(shape, self.mstate.ndtype)
+        check(self.ctx.L.sofab200_hexfem_get(self.h, what.encode(), out.ctypes.data_as(_P)))
+        return out
+
+    def stats(self):
+        out = (C.c_uint64 * 8)()
+        check(self.ctx.L.sofab200_hexfem_stats(self.h, out))
+        return dict(zip(["tiles", "tile_elems", "interior_nodes", "shared_nodes", "staged_corners", "smem_bytes", "max_valence", "n_elems"], list(out)))
+
+    def __del__(self):
+        try:
+            self.ctx.L.sofab200_hexfem_destroy(self.h)
+        except Exception:
+            pass
+
+
+class DiagonalMass:
+    """DiagonalMass<B200Vec3Types>: Data vertexMass | massDensity | totalMass (+ rayleighMass of Mass)."""
+
+    def __init__(self, mstate, elements=None, vertexMass=None, massDensity=None, totalMass=None, rayleighMass=0.0):
+        from .topology import diagonal_mass
+        self.mstate, self.ctx = mstate, mstate.ctx
+        self.rayleighMass = float(rayleighMass)
+        if vertexMass is not None:
+            self.vertexMass_host = np.ascontiguousarray(vertexMass, mstate.ndtype)
+        else:
+            self.vertexMass_host = diagonal_mass(mstate.rest_position_host, elements, mstate.ndtype, massDensity, totalMass)
+        self.vertexMass = torch.from_numpy(self.vertexMass_host).to(self.ctx.device)
+
+    def addMDx(self, res, dx, factor=1.0):
+        check(self.ctx.L.sofab200_mass_add_mdx(self.ctx.h, self.mstate.real, self.mstate.size, _dptr(res), _dptr(dx), _dptr(self.vertexMass), float(factor)))
+
+    def addForce(self, f, gravity):
+        g = (C.c_double * 3)(*[float(v) for v in gravity])
+        check(self.ctx.L.sofab200_mass_add_force(self.ctx.h, self.mstate.real, self.mstate.size, _dptr(f), _dptr(self.vertexMass), g))
+
+    def accFromF(self, a, f):
+        check(self.ctx.L.sofab200_mass_acc_from_f(self.ctx.h, self.mstate.real, self.mstate.size, _dptr(a), _dptr(f), _dptr(self.vertexMass)))
+
+
+class FixedProjectiveConstraint:
+    """FixedProjectiveConstraint<B200Vec3Types>: Data indices, fixAll."""
+
+    def __init__(self, mstate, indices=(), fixAll=False):
+        self.mstate, self.ctx = mstate, mstate.ctx
+        self.indices_host = np.ascontiguousarray(indices, np.uint32)
+        self.fixAll = bool(fixAll)
+        self.indices = torch.from_numpy(self.indices_host.astype(np.int32)).to(self.ctx.device)
+
+    def projectResponse(self, res):
+        check(self.ctx.L.sofab200_fixed_project_response(self.ctx.h, self.mstate.real, self.mstate.size, _dptr(res), len(self.indices_host),
+                                                         _dptr(self.indices) if len(self.indices_host) else None, int(self.fixAll)))
+
+
+class SolverNode:
+    """EulerImplicitSolver + CGLinearSolver<GraphScattered> over one MechanicalObject, resident on the device.
+
+    Data (EulerImplicitSolver): rayleighStiffness, rayleighMass, vdamping, firstOrder, trapezoidalScheme;
+    Data (CGLinearSolver): iterations, tolerance, threshold, warmStart; context: dt, gravity."""
+
+    def __init__(self, mstate, forcefield, mass=None, constraint=None, massFirst=True, dt=0.01, gravity=(0.0, -9.81, 0.0), rayleighStiffness=0.0,
+                 rayleighMass=0.0, vdamping=0.0, firstOrder=False, trapezoidalScheme=False, iterations=25, tolerance=1e-5, threshold=1e-5,
+                 warmStart=False):
+        self.mstate, self.ctx, self.forcefield, self.mass, self.constraint = mstate, mstate.ctx, forcefield, mass, constraint
+        d = _lib.NodeDesc()
+        if isinstance(forcefield, TetrahedronFEMForceField):
+            d.tetfem = forcefield.h
+        else:
+            d.hexfem = forcefield.h
+        if mass is not None:
+            d.vertex_mass_host = mass.vertexMass_host.ctypes.data_as(_P)
+        if constraint is not None:
+            d.n_fixed = len(constraint.indices_host)
+            d.fixed_host = constraint.indices_host.ctypes.data_as(C.POINTER(C.c_uint32))
+            d.fix_all = int(constraint.fixAll)
+        d.mass_first = int(massFirst)
+        self.h = _P()
+        check(self.ctx.L.sofab200_node_create(self.ctx.h, mstate.real, mstate.size, C.byref(d), C.byref(self.h)))
+        self.params = dict(dt=dt, gravity=tuple(gravity), rayleighStiffness=rayleighStiffness, rayleighMass=rayleighMass, vdamping=vdamping,
+                           firstOrder=firstOrder, trapezoidalScheme=trapezoidalScheme, iterations=iterations, tolerance=tolerance,
+                           threshold=threshold, warmStart=warmStart)
+        self._push()
+
+    def _push(self):
+        p, s = self.params, _lib.SolverParams()
+        s.gravity = (C.c_double * 3)(*p["gravity"]); s.dt = p["dt"]
+        s.rayleigh_stiffness, s.rayleigh_mass, s.vdamping = p["rayleighStiffness"], p["rayleighMass"], p["vdamping"]
+        s.first_order, s.trapezoidal = int(p["firstOrder"]), int(p["trapezoidalScheme"])
+        s.iterations, s.tolerance, s.threshold, s.warm_start = int(p["iterations"]), p["tolerance"], p["threshold"], int(p["warmStart"])
+        s.ff_rayleigh_stiffness = self.forcefield.rayleighStiffness
+        s.mass_rayleigh_mass = self.mass.rayleighMass if self.mass is not None else 0.0
+        check(self.ctx.L.sofab200_node_set_params(self.h, C.byref(s)))
+
+    def set_params(self, **kw):
+        for k in kw:
+            if k not in self.params:
+                raise KeyError(k)
+        self.params.update(kw)
+        self._push()
+
+    def computeForce(self, f, x):
+        check(self.ctx.L.sofab200_node_compute_force(self.h, _dptr(f), _dptr(x)))
+
+    def apply(self, q, p, mFactor, bFactor, kFactor):
+        """GraphScatteredMatrix::apply: q = project((m M + b B + k K) p)."""
+        check(self.ctx.L.sofab200_node_apply(self.h, _dptr(q), _dptr(p), float(mFactor), float(bFactor), float(kFactor)))
+
+    def cg_solve(self, x, b, mFactor, bFactor, kFactor, sync=True):
+        it = C.c_int()
+        check(self.ctx.L.sofab200_node_cg_solve(self.h, _dptr(x), _dptr(b), float(mFactor), float(bFactor), float(kFactor), C.byref(it) if sync else None))
+        return it.value if sync else None
+
+    def step(self, x=None, v=None):
+        """EulerImplicitSolver::solve on the MechanicalObject's device-resident x, v (asynchronous)."""
+        check(self.ctx.L.sofab200_node_step(self.h, _dptr(self.mstate.x if x is None else x), _dptr(self.mstate.v if v is None else v)))
+
+    def step_host(self, x_host, v_host):
+        """The same step for host arrays (numpy or pinned torch CPU tensors): H2D, step, D2H."""
+        xp = x_host.ctypes.data_as(_P) if isinstance(x_host, np.ndarray) else C.c_void_p(x_host.data_ptr())
+        vp = v_host.ctypes.data_as(_P) if isinstance(v_host, np.ndarray) else C.c_void_p(v_host.data_ptr())
+        check(self.ctx.L.sofab200_node_step_host(self.h, xp, vp))
+
+    def last_solve(self):
+        it, ec = C.c_int(), C.c_int()
+        ne, nd = C.c_size_t(), C.c_size_t()
+        cap = 1100
+        ge, gd = (C.c_double * cap)(), (C.c_double * cap)()
+        check(self.ctx.L.sofab200_node_last_solve(self.h, C.byref(it), C.byref(ec), ge, C.byref(ne), gd, C.byref(nd), cap))
+        return dict(iterations=it.value, end_condition=ec.value, graph_error=np.array(ge[:ne.value]), graph_den=np.array(gd[:nd.value]))
+
+    def get(self, what):
+        out = np.empty((self.mstate.size, 3), self.mstate.ndtype)
+        check(self.ctx.L.sofab200_node_get(self.h, what.encode(), out.ctypes.data_as(_P)))
+        return out
+
+    def reset(self):
+        check(self.ctx.L.sofab200_node_reset(self.h))
+
+    def __del__(self):
+        try:
+            self.ctx.L.sofab200_node_destroy(self.h)
+        except Exception:
+            pass

@@ -1,0 +1,87 @@
+// Context, error reporting.
+#include "common.cuh"
+
+namespace sb {
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+const char* sofab200_version(void) { return "sofa_b200 0.1 (sm_100a)"; }
+const char* sofab200_last_error(void) { return g_last_error.c_str(); }
+
+int sofab200_ctx_create(int device, void* cuda_stream, sofab200_ctx** out) {
+    SB_CHECK(out != nullptr, "out is null");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(SOFAB200_ERR_NO_DEVICE, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); sofa_b200 has no CPU path");
+    SB_CHECK(device >= 0 && device < count, "device ordinal out of range");
+    SB_CUDA(cudaSetDevice(device));
+    sofab200_ctx* c = new sofab200_ctx();
+    c->device = device;
+    if (cuda_stream) { c->stream = static_cast<cudaStream_t>(cuda_stream); c->own_stream = false; }
+    else {
+        cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e2 != cudaSuccess) { delete c; return fail(SOFAB200_ERR_CUDA, cudaGetErrorString(e2)); }
+        c->own_stream = true;
+    }
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    int rc = c->red_partials.alloc(4096);
+    if (rc == SOFAB200_OK) rc = c->red_result.alloc(4);
+    if (rc == SOFAB200_OK) rc = c->red_counter.alloc(4);
+    if (rc == SOFAB200_OK) rc = c->red_counter.zero(c->stream);
+    if (rc != SOFAB200_OK) { delete c; return rc; }
+    *out = c;
+    return SOFAB200_OK;
+}
+int sofab200_ctx_destroy(sofab200_ctx* ctx) {
+    if (!ctx) return SOFAB200_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return SOFAB200_OK;
+}
+int sofab200_ctx_set_stream(sofab200_ctx* ctx, void* cuda_stream) {
+    SB_CHECK(ctx != nullptr, "ctx is null");
+    if (ctx->own_stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
+    if (cuda_stream) ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    else { SB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    return SOFAB200_OK;
+}
+int sofab200_ctx_synchronize(sofab200_ctx* ctx) {
+    SB_CHECK(ctx != nullptr, "ctx is null");
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SOFAB200_OK;
+}
+uint64_t sofab200_ctx_launch_count(const sofab200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int sofab200_ctx_profile_begin(sofab200_ctx* ctx) {
+    SB_CHECK(ctx != nullptr, "ctx is null");
+    for (auto& v : ctx->prof) { for (auto& e : v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } v.clear(); }
+    ctx->profiling = true;
+    return SOFAB200_OK;
+}
+int sofab200_ctx_profile_end(sofab200_ctx* ctx, double* total_ms, uint64_t* count) {
+    SB_CHECK(ctx && total_ms && count, "null argument");
+    ctx->profiling = false;
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int c = 0; c < SOFAB200_PROFILE_CLASSES; ++c) {
+        double tot = 0.0;
+        for (auto& e : ctx->prof[c]) {
+            float ms = 0.f;
+            SB_CUDA(cudaEventElapsedTime(&ms, e.first, e.second));
+            tot += ms;
+            cudaEventDestroy(e.first); cudaEventDestroy(e.second);
+        }
+        total_ms[c] = tot; count[c] = ctx->prof[c].size();
+        ctx->prof[c].clear();
+    }
+    return SOFAB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,212 @@
+// Device data layout shared by the tetra / hexa force fields: CTA tiles of elements, a deterministic
+// gather plan, and the fused per-node epilogue (mass, projection, dot) of the solver node.
+//
+// Layout (see DESIGN.md "Data layout in HBM"):
+//   * elements are sorted along a Morton curve of their rest centroid and cut into tiles of `tile_e`;
+//     one CTA processes one tile.
+//   * a node whose incident elements all lie in one tile is INTERIOR to it: its corner contributions
+//     are staged in shared memory and summed in-kernel.  Every other node is SHARED: its contributions
+//     are staged in HBM (`stage`) and summed by the boundary kernel.
+//   * in both cases the contributions of one node are added one by one in ascending ORIGINAL element
+//     index, starting from the incoming value -- the exact order of the reference's sequential
+//     `f[index[k]] += ...` loop (TetrahedronFEMForceField.inl:928-929,1220-1235).  No atomics:
+//     results are bit-reproducible run to run and independent of the tiling.
+//   * slots are laid out as jagged diagonals: nodes of a tile (or of a 256-node chunk of shared nodes)
+//     are ranked by descending valence and contribution j of rank k lives at jds[j] + k, so that the
+//     per-node sequential sums are conflict-free in shared memory and coalesced in HBM.
+#pragma once
+#include "common.cuh"
+
+namespace sb {
+
+constexpr int kGatherChunk = 256;      // shared nodes per CTA of the boundary kernel
+constexpr unsigned kStageFlag = 0x80000000u;
+
+// epilogue selection for the per-node gather
+enum PreKind { PRE_NONE = 0, PRE_GRAVITY = 1, PRE_MDX = 2 };
+enum DotKind { DOT_NONE = 0, DOT_STORE = 1, DOT_CG_DEN = 2 };
+
+// Device-resident CG scalars (CGLinearSolver.inl:73-315 keeps these on the host; here the whole
+// solve runs without a host round trip, so they live in HBM).
+constexpr int kMaxGraph = 1026;
+struct CGDev {
+    int done;               // set once a break condition is met; later kernels of the solve become no-ops
+    int nb_iter;            // "CG iterations" as the reference reports it
+    int end_cond;           // 0 iterations, 1 tolerance, 2 threshold, 3 den==0, 4 b==0
+    int it;                 // current iteration (1-based)
+    unsigned time_step_count;
+    unsigned max_iter;
+    double tolerance, threshold;
+    double normb, rho, rho_1, den, alpha;
+    int n_err, n_den;
+    double graph_error[kMaxGraph];
+    double graph_den[kMaxGraph];
+};
+
+template <class R> struct NodeEpilogue {
+    const R* init_src;      // acc starts from init_src[node] (may alias out), or 0 when null
+    int sign;               // +1: acc += c_i ; -1: acc -= c_i  (per contribution, in order)
+    int pre_kind;           // mass term applied BEFORE the element contributions (mass first in the scene)
+    int post_kind;          // ... or AFTER them
+    const R* mass;          // DiagonalMass vertexMass
+    const R* mdx_src;       // dx of addMDx (== the kernel's input vector p / v)
+    R mass_factor;          // addMDx factor (narrowed to Real as the reference does)
+    int mass_factor_is_one; // reference takes `res += dx*m` when factor == 1.0
+    R gx, gy, gz;           // gravity (narrowed)
+    int has_scale;          // b.teq(h)
+    R scale;
+    const unsigned char* fixed;  // projectResponse mask (1 = fixed), may be null
+    R* out;
+    // dot(out, dot_with) accumulated in double, per-CTA partials, fixed-order final sum by the last CTA
+    int dot_kind;
+    const R* dot_with;
+    double* partials;       // [partial_base + blockIdx.x]
+    int partial_base;
+    int partial_total;      // number of partials to sum when finishing (tile CTAs + boundary CTAs)
+    unsigned* counter;      // last-CTA detection (boundary kernel only)
+    double* dot_result;
+    CGDev* cg;
+};
+
+template <class R> struct TileDev {
+    int n_nodes, n_elems, n_tiles, tile_e, maxval;
+    // per tile
+    const uint32_t* tile_node_off;   // [n_tiles+1] into tile_nodes
+    const uint32_t* tile_nodes;      // global node ids: interior (ranked by valence desc) then shared
+    const uint32_t* tile_nint;       // [n_tiles]
+    const uint16_t* tile_val;        // valence of each interior node, aligned with tile_nodes (shared entries unused)
+    const uint16_t* tile_jds;        // [n_tiles][maxval+1]
+    // shared nodes
+    int n_shared, n_chunks;
+    const uint32_t* sh_nodes;        // [n_chunks*kGatherChunk] (padded with 0xFFFFFFFF)
+    const uint16_t* sh_val;
+    const uint32_t* sh_jds;          // [n_chunks][maxval+1]
+    const uint32_t* sh_base;         // [n_chunks]
+    R* stage;                        // 3 planes of stage_n
+    size_t stage_n;
+};
+
+// acc (op)= contribution, in the reference's order; then mass/scale/projection/dot.
+template <class R> HD void node_pre(const NodeEpilogue<R>& ep, uint32_t g, R& ax, R& ay, R& az) {
+    if (ep.init_src) { ax = ep.init_src[3 * size_t(g)]; ay = ep.init_src[3 * size_t(g) + 1]; az = ep.init_src[3 * size_t(g) + 2]; }
+    else { ax = R(0); ay = R(0); az = R(0); }
+}
+template <class R> HD void node_mass(const NodeEpilogue<R>& ep, int kind, uint32_t g, R& ax, R& ay, R& az) {
+    if (kind == PRE_GRAVITY) {  // DiagonalMass::addForce: f[i] += theGravity*masses[i]
+        const R m = ep.mass[g];
+        ax += ep.gx * m; ay += ep.gy * m; az += ep.gz * m;
+    } else if (kind == PRE_MDX) {  // DiagonalMass::addMDx
+        const R m = ep.mass[g];
+        const R dx = ep.mdx_src[3 * size_t(g)], dy = ep.mdx_src[3 * size_t(g) + 1], dz = ep.mdx_src[3 * size_t(g) + 2];
+        if (ep.mass_factor_is_one) { ax += dx * m; ay += dy * m; az += dz * m; }
+        else { ax += (dx * m) * ep.mass_factor; ay += (dy * m) * ep.mass_factor; az += (dz * m) * ep.mass_factor; }
+    }
+}
+// returns this node's contribution to the dot product
+template <class R> HD double node_post(const NodeEpilogue<R>& ep, uint32_t g, R ax, R ay, R az) {
+    node_mass(ep, ep.post_kind, g, ax, ay, az);
+    if (ep.has_scale) { ax *= ep.scale; ay *= ep.scale; az *= ep.scale; }
+    if (ep.fixed && ep.fixed[g]) { ax = R(0); ay = R(0); az = R(0); }
+    ep.out[3 * size_t(g)] = ax; ep.out[3 * size_t(g) + 1] = ay; ep.out[3 * size_t(g) + 2] = az;
+    if (ep.dot_kind != DOT_NONE) {
+        const R* w = ep.dot_with + 3 * size_t(g);
+        return double(ax) * double(w[0]) + double(ay) * double(w[1]) + double(az) * double(w[2]);
+    }
+    return 0.0;
+}
+
+// block-wide sum in a fixed order: warp shuffles, then warp 0 over the per-warp partials
+__device__ __forceinline__ double block_sum(double v, double* warp_scratch /* >= 32 doubles of smem */) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) warp_scratch[w] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? warp_scratch[threadIdx.x] : 0.0;
+    if (w == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    }
+    return v;  // valid in thread 0
+}
+
+// CG bookkeeping executed by one thread once den = p.q is known (CGLinearSolver.inl:211-265)
+__host__ __device__ inline void cg_after_den(CGDev* cg, double den) {
+    if (cg->n_den < kMaxGraph) cg->graph_den[cg->n_den++] = den;
+    cg->den = den;
+    if (den != 0.0) {
+        if (fabs(den) <= cg->threshold) {
+            if (cg->it == 1 && cg->time_step_count == 0) { /* reference only warns on the very first step */ }
+            else { cg->done = 1; cg->nb_iter = cg->it; cg->end_cond = 2; return; }
+        }
+        cg->alpha = cg->rho / den;
+    } else { cg->done = 1; cg->nb_iter = cg->it; cg->end_cond = 3; }
+}
+// ... and once the next rho = r.r is known (CGLinearSolver.inl:130-180,268)
+__host__ __device__ inline void cg_after_rho(CGDev* cg, double rho_new) {
+    cg->rho_1 = cg->rho;
+    cg->rho = rho_new;
+    const int it = cg->it + 1;
+    if (unsigned(it) > cg->max_iter) { cg->done = 1; cg->nb_iter = it; cg->end_cond = 0; return; }
+    cg->it = it;
+    const double err = sqrt(rho_new) / cg->normb;
+    if (cg->n_err < kMaxGraph) cg->graph_error[cg->n_err++] = err;
+    if (err <= cg->tolerance) {
+        if (it == 1 && cg->time_step_count == 0) { /* warning only */ }
+        else { cg->done = 1; cg->nb_iter = it; cg->end_cond = 1; }
+    }
+}
+
+// Finish a dot product whose per-CTA partials are complete: the LAST CTA to arrive sums them in index order.
+template <class R> __device__ __forceinline__ void finish_dot(const NodeEpilogue<R>& ep, double block_total, double* scratch, bool count_blocks) {
+    if (ep.dot_kind == DOT_NONE) return;
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+        ep.partials[ep.partial_base + blockIdx.x] = block_total;
+        is_last = false;
+        if (count_blocks) {
+            __threadfence();
+            const unsigned ticket = atomicInc(ep.counter, gridDim.x - 1);  // wraps to 0 for the next launch
+            is_last = (ticket == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    if (!count_blocks || !is_last) return;
+    __threadfence();
+    double s = 0.0;
+    for (int i = threadIdx.x; i < ep.partial_total; i += blockDim.x) s += __ldcg(ep.partials + i);
+    __syncthreads();
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) {
+        if (ep.dot_result) *ep.dot_result = s;
+        if (ep.dot_kind == DOT_CG_DEN) cg_after_den(ep.cg, s);
+    }
+}
+
+// ---- boundary kernel: sums the HBM-staged contributions of the shared nodes -------------------------------
+template <class R> __global__ void __launch_bounds__(kGatherChunk) gather_shared_kernel(TileDev<R> d, NodeEpilogue<R> ep) {
+    __shared__ double red[32];
+    if (ep.cg && ep.cg->done) return;
+    const int chunk = blockIdx.x, k = threadIdx.x;
+    const uint32_t g = d.sh_nodes[size_t(chunk) * kGatherChunk + k];
+    double part = 0.0;
+    if (g != 0xFFFFFFFFu) {
+        const int val = d.sh_val[size_t(chunk) * kGatherChunk + k];
+        const uint32_t* jds = d.sh_jds + size_t(chunk) * (d.maxval + 1);
+        const size_t base = d.sh_base[chunk];
+        const R* sx = d.stage; const R* sy = d.stage + d.stage_n; const R* sz = d.stage + 2 * d.stage_n;
+        R ax, ay, az;
+        node_pre(ep, g, ax, ay, az);
+        node_mass(ep, ep.pre_kind, g, ax, ay, az);
+        if (ep.sign > 0) for (int j = 0; j < val; ++j) { const size_t p = base + jds[j] + k; ax += __ldcg(sx + p); ay += __ldcg(sy + p); az += __ldcg(sz + p); }
+        else             for (int j = 0; j < val; ++j) { const size_t p = base + jds[j] + k; ax -= __ldcg(sx + p); ay -= __ldcg(sy + p); az -= __ldcg(sz + p); }
+        part = node_post(ep, g, ax, ay, az);
+    }
+    if (ep.dot_kind != DOT_NONE) {
+        const double tot = block_sum(part, red);
+        finish_dot(ep, tot, red, true);
+    }
+}
+
+}  // namespace sb

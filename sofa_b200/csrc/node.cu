@@ -1,0 +1,362 @@
+// MechanicalObject vector ops, DiagonalMass / FixedProjectiveConstraint kernels, and the device-resident
+// solver node (EulerImplicitSolver + CGLinearSolver<GraphScattered>).
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+#include "vec_ops.cuh"
+
+using namespace sb;
+
+namespace sb {
+// implemented in tet_fem.cu / hex_fem.cu
+template <class R> int tet_run(sofab200_tetfem* ff, bool dforce, const R* in, R k_factor, NodeEpilogue<R> ep);
+int tet_partial_count(sofab200_tetfem* ff);
+template <class R> int hex_run(sofab200_hexfem* ff, bool dforce, const R* in, R k_factor, NodeEpilogue<R> ep);
+int hex_partial_count(sofab200_hexfem* ff);
+int tet_real(sofab200_tetfem* ff); size_t tet_nodes(sofab200_tetfem* ff);
+int hex_real(sofab200_hexfem* ff); size_t hex_nodes(sofab200_hexfem* ff);
+}  // namespace sb
+
+#define LAUNCH(ctx, kernel, grid, block, ...)                              \
+    do {                                                                   \
+        (ctx)->prof_start(3);                                              \
+        kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);        \
+        (ctx)->prof_stop(3);                                               \
+        (ctx)->launches++;                                                 \
+        SB_CUDA(cudaGetLastError());                                       \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// MechanicalObject::vOp dispatch (MechanicalObject.inl:2075-2203)
+// ---------------------------------------------------------------------------------------------------
+template <class R> static int vop_impl(sofab200_ctx* ctx, size_t n, R* r, const R* a, const R* b, double k) {
+    const size_t n3 = 3 * n;
+    if (n3 == 0) return SOFAB200_OK;
+    const int g = vec_grid(n3, ctx->sm_count);
+    const R kr = R(k);
+    if (!a) {
+        if (!b) LAUNCH(ctx, (vop_kernel<R, VOP_CLEAR>), g, kVecBlock, n3, r, a, b, kr);
+        else if (r == b) LAUNCH(ctx, (vop_kernel<R, VOP_SCALE>), g, kVecBlock, n3, r, a, b, kr);
+        else LAUNCH(ctx, (vop_kernel<R, VOP_EQ_BF>), g, kVecBlock, n3, r, a, b, kr);
+    } else if (!b) {
+        if (r != a) LAUNCH(ctx, (vop_kernel<R, VOP_COPY>), g, kVecBlock, n3, r, a, b, kr);
+    } else if (r == a) {
+        if (k == 1.0) LAUNCH(ctx, (vop_kernel<R, VOP_PEQ>), g, kVecBlock, n3, r, a, b, kr);
+        else LAUNCH(ctx, (vop_kernel<R, VOP_PEQ_BF>), g, kVecBlock, n3, r, a, b, kr);
+    } else if (r == b) {
+        if (k == 1.0) LAUNCH(ctx, (vop_kernel<R, VOP_PEQ>), g, kVecBlock, n3, r, b, a, kr);  // r += a
+        else LAUNCH(ctx, (vop_kernel<R, VOP_AVF>), g, kVecBlock, n3, r, a, b, kr);
+    } else {
+        if (k == 1.0) LAUNCH(ctx, (vop_kernel<R, VOP_EQ_AB>), g, kVecBlock, n3, r, a, b, kr);
+        else LAUNCH(ctx, (vop_kernel<R, VOP_EQ_ABF>), g, kVecBlock, n3, r, a, b, kr);
+    }
+    return SOFAB200_OK;
+}
+
+template <class R> static int vdot_impl(sofab200_ctx* ctx, size_t n, const R* a, const R* b, double* result_host) {
+    const size_t n3 = 3 * n;
+    int g = vec_grid(n3, ctx->sm_count);
+    if (g > 4096) g = 4096;
+    LAUNCH(ctx, (vdot_kernel<R>), g, kVecBlock, n3, a, b, ctx->red_partials.p, ctx->red_counter.p, int(DF_STORE), ctx->red_result.p, (CGDev*)nullptr);
+    SB_CUDA(cudaMemcpyAsync(result_host, ctx->red_result.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SOFAB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// solver node
+// ---------------------------------------------------------------------------------------------------
+struct sofab200_node {
+    virtual ~sofab200_node() {}
+    sofab200_ctx* ctx = nullptr;
+    int real = 0;
+    size_t n = 0;
+    sofab200_solver_params prm;
+};
+
+namespace sb {
+template <class R> struct Node : sofab200_node {
+    sofab200_tetfem* tet = nullptr;
+    sofab200_hexfem* hex = nullptr;
+    bool has_mass = false, mass_first = true;
+    DevBuf<R> mass;
+    DevBuf<unsigned char> fixed;
+    bool has_fixed = false;
+    DevBuf<R> f, b, dx, p, q, r;
+    DevBuf<R> hx, hv;           // device copies of host state for step_host
+    DevBuf<CGDev> cg;
+    DevBuf<double> partials;
+    DevBuf<unsigned> counters;  // [0] boundary kernel, [1] vector kernels
+    int n_fem_partials = 0;
+    double mF = 0, bF = 0, kF = 0;
+
+    int fem_run(bool dforce, const R* in, R k_factor, const NodeEpilogue<R>& ep) {
+        if (tet) return tet_run<R>(tet, dforce, in, k_factor, ep);
+        return hex_run<R>(hex, dforce, in, k_factor, ep);
+    }
+    NodeEpilogue<R> base_ep() {
+        NodeEpilogue<R> ep{};
+        ep.mass = mass.p; ep.partials = partials.p; ep.counter = counters.p; ep.cg = nullptr;
+        return ep;
+    }
+    void set_mass_term(NodeEpilogue<R>& ep, int kind, const R* src, double factor) {
+        if (!has_mass) return;
+        if (kind == PRE_MDX && factor == 0.0) return;  // Mass::addMBKdx skips a null factor (Mass.inl:96-99)
+        if (mass_first) ep.pre_kind = kind; else ep.post_kind = kind;
+        ep.mdx_src = src; ep.mass_factor = R(factor); ep.mass_factor_is_one = (factor == 1.0);
+        ep.gx = R(prm.gravity[0]); ep.gy = R(prm.gravity[1]); ep.gz = R(prm.gravity[2]);
+    }
+    // mop.computeForce
+    int compute_force(R* f_out, const R* x) {
+        NodeEpilogue<R> ep = base_ep();
+        ep.init_src = nullptr; ep.sign = +1; ep.out = f_out;
+        set_mass_term(ep, PRE_GRAVITY, nullptr, 1.0);
+        return fem_run(false, x, R(0), ep);
+    }
+    // df = init + (m M + b B + k K) d, optionally scaled and projected; dot(out, dot_with) optional
+    int add_mbk(R* out, const R* init, const R* d, double m, double bfac, double k, bool scale, double s, bool project, int dot_kind, CGDev* cgp) {
+        NodeEpilogue<R> ep = base_ep();
+        ep.init_src = init; ep.sign = -1; ep.out = out;
+        const double mf = m - bfac * prm.mass_rayleigh_mass;          // MechanicalParams.h:64
+        const double kf = k + bfac * prm.ff_rayleigh_stiffness;       // MechanicalParams.h:62
+        set_mass_term(ep, PRE_MDX, d, mf);
+        ep.has_scale = scale; ep.scale = R(s);
+        ep.fixed = (project && has_fixed) ? fixed.p : nullptr;
+        ep.dot_kind = dot_kind; ep.dot_with = d; ep.cg = cgp;
+        if (kf != 0.0 || bfac != 0.0) return fem_run(true, d, R(kf), ep);   // BaseForceField::addMBKdx, BaseForceField.cpp:38-47
+        if (dot_kind != DOT_NONE) return fail(SOFAB200_ERR_UNSUPPORTED, "system without a stiffness term is not supported in the CG loop");
+        LAUNCH(ctx, (node_only_kernel<R>), vec_grid(n, ctx->sm_count), kVecBlock, n, ep);
+        return SOFAB200_OK;
+    }
+    int apply(R* q_out, const R* p_in, double m, double bfac, double k) {
+        return add_mbk(q_out, nullptr, p_in, m, bfac, k, false, 1.0, true, DOT_NONE, nullptr);
+    }
+    // CGLinearSolver::solve, device resident
+    int cg_solve(R* x, const R* bvec, double m, double bfac, double k) {
+        const size_t n3 = 3 * n;
+        const int g = vec_grid(n3, ctx->sm_count);
+        CGBegin cb{prm.iterations, prm.tolerance, prm.threshold};
+        LAUNCH(ctx, cg_begin_kernel, 1, 1, cg.p, cb);
+        if (prm.warm_start) {
+            SB_TRY(apply(r.p, x, m, bfac, k));                                             // r = A x
+            LAUNCH(ctx, (vop_kernel<R, VOP_AVF>), g, kVecBlock, n3, r.p, bvec, (const R*)nullptr, R(-1.0));  // r = b + r*(-1)
+        } else {
+            LAUNCH(ctx, (vop_kernel<R, VOP_CLEAR>), g, kVecBlock, n3, x, (const R*)nullptr, (const R*)nullptr, R(0));
+            SB_CUDA(cudaMemcpyAsync(r.p, bvec, n3 * sizeof(R), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        int gd = g > 2048 ? 2048 : g;
+        LAUNCH(ctx, (vdot_kernel<R>), gd, kVecBlock, n3, bvec, bvec, partials.p, counters.p + 1, int(DF_CG_NORMB), (double*)nullptr, cg.p);
+        LAUNCH(ctx, (vdot_kernel<R>), gd, kVecBlock, n3, (const R*)r.p, (const R*)r.p, partials.p, counters.p + 1, int(DF_CG_RHO), (double*)nullptr, cg.p);
+        for (unsigned it = 1; it <= prm.iterations; ++it) {
+            LAUNCH(ctx, (cg_p_update_kernel<R>), g, kVecBlock, n3, p.p, (const R*)r.p, (const CGDev*)cg.p);
+            SB_TRY(add_mbk(q.p, nullptr, p.p, m, bfac, k, false, 1.0, true, DOT_CG_DEN, cg.p));  // q = A p ; den = p.q
+            LAUNCH(ctx, (cg_xr_update_kernel<R>), gd, kVecBlock, n3, x, r.p, (const R*)p.p, (const R*)q.p, cg.p, partials.p, counters.p + 1);
+        }
+        LAUNCH(ctx, cg_end_kernel, 1, 1, cg.p);
+        return SOFAB200_OK;
+    }
+    // EulerImplicitSolver::solve
+    int step(R* x, R* v) {
+        const double h = prm.dt, tr = prm.trapezoidal ? 0.5 : 1.0;
+        const bool fo = prm.first_order != 0;
+        SB_TRY(compute_force(f.p, x));
+        if (!fo) {
+            // b = (f + (-rM M + (h tr + rK) K) v) * h, projected          EulerImplicitSolver.cpp:147-162
+            SB_TRY(add_mbk(b.p, f.p, v, -prm.rayleigh_mass, 0.0, h * tr + prm.rayleigh_stiffness, true, h, true, DOT_NONE, nullptr));
+        } else {
+            NodeEpilogue<R> ep = base_ep();
+            ep.init_src = f.p; ep.out = b.p; ep.sign = -1; ep.fixed = has_fixed ? fixed.p : nullptr;
+            LAUNCH(ctx, (node_only_kernel<R>), vec_grid(n, ctx->sm_count), kVecBlock, n, ep);
+        }
+        mF = fo ? 1 : 1 + tr * h * prm.rayleigh_mass;
+        bF = fo ? 0 : -tr * h;
+        kF = fo ? -h * tr : -tr * h * (tr * h + prm.rayleigh_stiffness);
+        SB_TRY(cg_solve(dx.p, b.p, mF, bF, kF));
+        const size_t n3 = 3 * n;
+        const int g = vec_grid(n3, ctx->sm_count);
+        if (fo) {
+            SB_CUDA(cudaMemcpyAsync(v, dx.p, n3 * sizeof(R), cudaMemcpyDeviceToDevice, ctx->stream));   // newVel.eq(x)
+            LAUNCH(ctx, (vop_kernel<R, VOP_PEQ_BF>), g, kVecBlock, n3, x, (const R*)x, (const R*)v, R(h));  // newPos.eq(pos,newVel,h)
+        } else {
+            LAUNCH(ctx, (integrate_kernel<R>), g, kVecBlock, n3, v, x, (const R*)dx.p, R(1), 1, R(h));
+        }
+        if (prm.vdamping != 0.0) LAUNCH(ctx, (vop_kernel<R, VOP_SCALE>), g, kVecBlock, n3, v, (const R*)nullptr, (const R*)v, R(std::exp(-h * prm.vdamping)));
+        return SOFAB200_OK;
+    }
+};
+
+template <class R> static int node_create(sofab200_ctx* ctx, size_t n, const sofab200_node_desc* d, sofab200_node** out) {
+    std::unique_ptr<Node<R>> nd(new Node<R>());
+    nd->ctx = ctx; nd->real = sizeof(R) == 4 ? SOFAB200_F32 : SOFAB200_F64; nd->n = n;
+    nd->tet = d->tetfem; nd->hex = d->hexfem; nd->mass_first = d->mass_first != 0;
+    std::memset(&nd->prm, 0, sizeof(nd->prm));
+    nd->prm.gravity[1] = -9.81; nd->prm.dt = 0.01; nd->prm.iterations = 25; nd->prm.tolerance = 1e-5; nd->prm.threshold = 1e-5;
+    cudaStream_t s = ctx->stream;
+    if (d->vertex_mass_host) {
+        nd->has_mass = true;
+        SB_TRY(nd->mass.alloc(n));
+        SB_CUDA(cudaMemcpyAsync(nd->mass.p, d->vertex_mass_host, n * sizeof(R), cudaMemcpyHostToDevice, s));
+    }
+    if (d->fix_all || d->n_fixed > 0) {
+        std::vector<unsigned char> mask(n, d->fix_all ? 1 : 0);
+        for (size_t i = 0; i < d->n_fixed; ++i) { SB_CHECK(d->fixed_host[i] < n, "fixed index out of range"); mask[d->fixed_host[i]] = 1; }
+        nd->has_fixed = true;
+        SB_TRY(nd->fixed.upload(mask, s));
+    }
+    for (DevBuf<R>* v : {&nd->f, &nd->b, &nd->dx, &nd->p, &nd->q, &nd->r}) { SB_TRY(v->alloc(3 * n)); SB_TRY(v->zero(s)); }
+    SB_TRY(nd->cg.alloc(1)); SB_TRY(nd->cg.zero(s));
+    nd->n_fem_partials = d->tetfem ? tet_partial_count(d->tetfem) : hex_partial_count(d->hexfem);
+    SB_TRY(nd->partials.alloc(size_t(std::max(nd->n_fem_partials, 4096)) + 16)); SB_TRY(nd->partials.zero(s));
+    SB_TRY(nd->counters.alloc(4)); SB_TRY(nd->counters.zero(s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    *out = nd.release();
+    return SOFAB200_OK;
+}
+}  // namespace sb
+
+#define NODE_DISPATCH(node, EXPR_F, EXPR_D) ((node)->real == SOFAB200_F32 ? (EXPR_F) : (EXPR_D))
+#define NF(node) (static_cast<Node<float>*>(node))
+#define ND(node) (static_cast<Node<double>*>(node))
+
+extern "C" {
+
+int sofab200_mo_vop(sofab200_ctx* ctx, sofab200_real real, size_t n, void* r_dev, const void* a_dev, const void* b_dev, double k) {
+    SB_CHECK(ctx && r_dev, "null argument");
+    if (real == SOFAB200_F32) return vop_impl<float>(ctx, n, (float*)r_dev, (const float*)a_dev, (const float*)b_dev, k);
+    return vop_impl<double>(ctx, n, (double*)r_dev, (const double*)a_dev, (const double*)b_dev, k);
+}
+int sofab200_mo_vdot(sofab200_ctx* ctx, sofab200_real real, size_t n, const void* a_dev, const void* b_dev, double* result_host) {
+    SB_CHECK(ctx && a_dev && b_dev && result_host, "null argument");
+    if (n == 0) { *result_host = 0.0; return SOFAB200_OK; }
+    if (real == SOFAB200_F32) return vdot_impl<float>(ctx, n, (const float*)a_dev, (const float*)b_dev, result_host);
+    return vdot_impl<double>(ctx, n, (const double*)a_dev, (const double*)b_dev, result_host);
+}
+int sofab200_mo_vmultiop_integrate(sofab200_ctx* ctx, sofab200_real real, size_t n, void* v_dev, void* x_dev, const void* a_dev, double f_v_a, double f_x_v) {
+    SB_CHECK(ctx && v_dev && x_dev && a_dev, "null argument");
+    const size_t n3 = 3 * n;
+    if (n3 == 0) return SOFAB200_OK;
+    const int g = vec_grid(n3, ctx->sm_count);
+    if (real == SOFAB200_F32) LAUNCH(ctx, (integrate_kernel<float>), g, kVecBlock, n3, (float*)v_dev, (float*)x_dev, (const float*)a_dev, float(f_v_a), int(float(f_v_a) == 1.0f), float(f_x_v));
+    else LAUNCH(ctx, (integrate_kernel<double>), g, kVecBlock, n3, (double*)v_dev, (double*)x_dev, (const double*)a_dev, f_v_a, int(f_v_a == 1.0), f_x_v);
+    return SOFAB200_OK;
+}
+int sofab200_mass_add_mdx(sofab200_ctx* ctx, sofab200_real real, size_t n, void* res_dev, const void* dx_dev, const void* m_dev, double factor) {
+    SB_CHECK(ctx && res_dev && dx_dev && m_dev, "null argument");
+    if (n == 0) return SOFAB200_OK;
+    const int g = vec_grid(3 * n, ctx->sm_count);
+    if (real == SOFAB200_F32) LAUNCH(ctx, (mass_mdx_kernel<float>), g, kVecBlock, n, (float*)res_dev, (const float*)dx_dev, (const float*)m_dev, float(factor), int(factor == 1.0));
+    else LAUNCH(ctx, (mass_mdx_kernel<double>), g, kVecBlock, n, (double*)res_dev, (const double*)dx_dev, (const double*)m_dev, factor, int(factor == 1.0));
+    return SOFAB200_OK;
+}
+int sofab200_mass_add_force(sofab200_ctx* ctx, sofab200_real real, size_t n, void* f_dev, const void* m_dev, const double gravity[3]) {
+    SB_CHECK(ctx && f_dev && m_dev && gravity, "null argument");
+    if (n == 0) return SOFAB200_OK;
+    const int g = vec_grid(3 * n, ctx->sm_count);
+    if (real == SOFAB200_F32) LAUNCH(ctx, (mass_gravity_kernel<float>), g, kVecBlock, n, (float*)f_dev, (const float*)m_dev, float(gravity[0]), float(gravity[1]), float(gravity[2]));
+    else LAUNCH(ctx, (mass_gravity_kernel<double>), g, kVecBlock, n, (double*)f_dev, (const double*)m_dev, gravity[0], gravity[1], gravity[2]);
+    return SOFAB200_OK;
+}
+int sofab200_mass_acc_from_f(sofab200_ctx* ctx, sofab200_real real, size_t n, void* a_dev, const void* f_dev, const void* m_dev) {
+    SB_CHECK(ctx && a_dev && f_dev && m_dev, "null argument");
+    if (n == 0) return SOFAB200_OK;
+    const int g = vec_grid(3 * n, ctx->sm_count);
+    if (real == SOFAB200_F32) LAUNCH(ctx, (mass_acc_kernel<float>), g, kVecBlock, n, (float*)a_dev, (const float*)f_dev, (const float*)m_dev);
+    else LAUNCH(ctx, (mass_acc_kernel<double>), g, kVecBlock, n, (double*)a_dev, (const double*)f_dev, (const double*)m_dev);
+    return SOFAB200_OK;
+}
+int sofab200_fixed_project_response(sofab200_ctx* ctx, sofab200_real real, size_t n, void* res_dev, size_t n_idx, const uint32_t* idx_dev, int fix_all) {
+    SB_CHECK(ctx && res_dev, "null argument");
+    if (fix_all) return sofab200_mo_vop(ctx, real, n, res_dev, nullptr, nullptr, 0.0);
+    if (n_idx == 0) return SOFAB200_OK;
+    SB_CHECK(idx_dev != nullptr, "indices are null");
+    const int g = vec_grid(n_idx, ctx->sm_count);
+    if (real == SOFAB200_F32) LAUNCH(ctx, (fixed_project_kernel<float>), g, kVecBlock, n_idx, idx_dev, (float*)res_dev);
+    else LAUNCH(ctx, (fixed_project_kernel<double>), g, kVecBlock, n_idx, idx_dev, (double*)res_dev);
+    return SOFAB200_OK;
+}
+
+int sofab200_node_create(sofab200_ctx* ctx, sofab200_real real, size_t n_nodes, const sofab200_node_desc* desc, sofab200_node** out) {
+    SB_CHECK(ctx && desc && out, "null argument");
+    SB_CHECK((desc->tetfem != nullptr) != (desc->hexfem != nullptr), "exactly one of tetfem / hexfem must be given");
+    if (desc->tetfem) SB_CHECK(tet_real(desc->tetfem) == int(real) && tet_nodes(desc->tetfem) == n_nodes, "force field and node disagree on Real or size");
+    if (desc->hexfem) SB_CHECK(hex_real(desc->hexfem) == int(real) && hex_nodes(desc->hexfem) == n_nodes, "force field and node disagree on Real or size");
+    SB_CHECK(desc->n_fixed == 0 || desc->fixed_host, "fixed indices are null");
+    SB_CUDA(cudaSetDevice(ctx->device));
+    if (real == SOFAB200_F32) return node_create<float>(ctx, n_nodes, desc, out);
+    return node_create<double>(ctx, n_nodes, desc, out);
+}
+int sofab200_node_destroy(sofab200_node* node) { delete node; return SOFAB200_OK; }
+int sofab200_node_set_params(sofab200_node* node, const sofab200_solver_params* p) {
+    SB_CHECK(node && p, "null argument");
+    SB_CHECK(p->iterations + 2 < unsigned(kMaxGraph), "iterations too large");
+    node->prm = *p;
+    return SOFAB200_OK;
+}
+int sofab200_node_compute_force(sofab200_node* node, void* f_dev, const void* x_dev) {
+    SB_CHECK(node && f_dev && x_dev, "null argument");
+    return NODE_DISPATCH(node, NF(node)->compute_force((float*)f_dev, (const float*)x_dev), ND(node)->compute_force((double*)f_dev, (const double*)x_dev));
+}
+int sofab200_node_apply(sofab200_node* node, void* q_dev, const void* p_dev, double m, double b, double k) {
+    SB_CHECK(node && q_dev && p_dev && q_dev != p_dev, "null or aliased argument");
+    return NODE_DISPATCH(node, NF(node)->apply((float*)q_dev, (const float*)p_dev, m, b, k), ND(node)->apply((double*)q_dev, (const double*)p_dev, m, b, k));
+}
+int sofab200_node_cg_solve(sofab200_node* node, void* x_dev, const void* b_dev, double m, double b, double k, int* nb_iter_host) {
+    SB_CHECK(node && x_dev && b_dev, "null argument");
+    SB_TRY(NODE_DISPATCH(node, NF(node)->cg_solve((float*)x_dev, (const float*)b_dev, m, b, k), ND(node)->cg_solve((double*)x_dev, (const double*)b_dev, m, b, k)));
+    if (nb_iter_host) return sofab200_node_last_solve(node, nb_iter_host, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+    return SOFAB200_OK;
+}
+int sofab200_node_step(sofab200_node* node, void* x_dev, void* v_dev) {
+    SB_CHECK(node && x_dev && v_dev, "null argument");
+    return NODE_DISPATCH(node, NF(node)->step((float*)x_dev, (float*)v_dev), ND(node)->step((double*)x_dev, (double*)v_dev));
+}
+int sofab200_node_step_host(sofab200_node* node, void* x_host, void* v_host) {
+    SB_CHECK(node && x_host && v_host, "null argument");
+    const size_t bytes = 3 * node->n * (node->real == SOFAB200_F32 ? 4 : 8);
+    cudaStream_t s = node->ctx->stream;
+    void* dx; void* dv;
+    if (node->real == SOFAB200_F32) { auto* n = NF(node); if (!n->hx.p) { SB_TRY(n->hx.alloc(3 * n->n)); SB_TRY(n->hv.alloc(3 * n->n)); } dx = n->hx.p; dv = n->hv.p; }
+    else { auto* n = ND(node); if (!n->hx.p) { SB_TRY(n->hx.alloc(3 * n->n)); SB_TRY(n->hv.alloc(3 * n->n)); } dx = n->hx.p; dv = n->hv.p; }
+    SB_CUDA(cudaMemcpyAsync(dx, x_host, bytes, cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(dv, v_host, bytes, cudaMemcpyHostToDevice, s));
+    SB_TRY(sofab200_node_step(node, dx, dv));
+    SB_CUDA(cudaMemcpyAsync(x_host, dx, bytes, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaMemcpyAsync(v_host, dv, bytes, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    return SOFAB200_OK;
+}
+int sofab200_node_last_solve(sofab200_node* node, int* nb_iter, int* end_cond, double* graph_error, size_t* n_error, double* graph_den, size_t* n_den, size_t cap) {
+    SB_CHECK(node != nullptr, "null argument");
+    CGDev* dev = node->real == SOFAB200_F32 ? NF(node)->cg.p : ND(node)->cg.p;
+    static thread_local CGDev h;
+    SB_CUDA(cudaMemcpyAsync(&h, dev, sizeof(CGDev), cudaMemcpyDeviceToHost, node->ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(node->ctx->stream));
+    if (nb_iter) *nb_iter = h.nb_iter;
+    if (end_cond) *end_cond = h.end_cond;
+    if (n_error) *n_error = size_t(h.n_err);
+    if (n_den) *n_den = size_t(h.n_den);
+    if (graph_error) for (size_t i = 0; i < cap && i < size_t(h.n_err); ++i) graph_error[i] = h.graph_error[i];
+    if (graph_den) for (size_t i = 0; i < cap && i < size_t(h.n_den); ++i) graph_den[i] = h.graph_den[i];
+    return SOFAB200_OK;
+}
+int sofab200_node_get(sofab200_node* node, const char* what, void* out_host) {
+    SB_CHECK(node && what && out_host, "null argument");
+    const std::string w(what);
+    const void* src = nullptr;
+    const size_t es = node->real == SOFAB200_F32 ? 4 : 8;
+    if (node->real == SOFAB200_F32) { auto* n = NF(node); src = w == "f" ? n->f.p : w == "b" ? n->b.p : w == "dx" ? n->dx.p : nullptr; }
+    else { auto* n = ND(node); src = w == "f" ? n->f.p : w == "b" ? n->b.p : w == "dx" ? n->dx.p : nullptr; }
+    SB_CHECK(src != nullptr, "unknown vector name");
+    SB_CUDA(cudaMemcpyAsync(out_host, src, 3 * node->n * es, cudaMemcpyDeviceToHost, node->ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(node->ctx->stream));
+    return SOFAB200_OK;
+}
+int sofab200_node_reset(sofab200_node* node) {
+    SB_CHECK(node != nullptr, "null argument");
+    CGDev* dev = node->real == SOFAB200_F32 ? NF(node)->cg.p : ND(node)->cg.p;
+    SB_CUDA(cudaMemsetAsync(dev, 0, sizeof(CGDev), node->ctx->stream));
+    return SOFAB200_OK;
+}
+
+}  // extern "C"

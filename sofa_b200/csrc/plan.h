@@ -1,0 +1,203 @@
+// Host-side construction of the tile / gather plan (init-time; see fem_layout.cuh for the layout).
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace sb {
+
+struct HostPlan {
+    int n_nodes = 0, n_elems = 0, npe = 0, tile_e = 0, n_tiles = 0, maxval = 0;
+    std::vector<uint32_t> order;          // [n_tiles*tile_e] element slot -> original element (0xFFFFFFFF = padding)
+    std::vector<uint32_t> tile_node_off;  // [n_tiles+1]
+    std::vector<uint32_t> tile_nodes;
+    std::vector<uint32_t> tile_nint;
+    std::vector<uint16_t> tile_val;
+    std::vector<uint16_t> tile_jds;       // [n_tiles][maxval+1]
+    std::vector<uint16_t> lnode;          // [n_tiles*tile_e*npe]
+    std::vector<uint32_t> slot;           // [n_tiles*tile_e*npe]
+    int n_shared = 0, n_chunks = 0;
+    std::vector<uint32_t> sh_nodes;       // [n_chunks*chunk]
+    std::vector<uint16_t> sh_val;
+    std::vector<uint32_t> sh_jds;         // [n_chunks][maxval+1]
+    std::vector<uint32_t> sh_base;        // [n_chunks]
+    size_t stage_n = 0;
+    int max_touched = 0, max_slots = 0;
+    size_t n_interior = 0, n_staged_corners = 0;
+};
+
+inline uint64_t morton_spread(uint64_t v) {  // 21 bits -> every third bit
+    v &= 0x1fffffULL;
+    v = (v | v << 32) & 0x1f00000000ffffULL;
+    v = (v | v << 16) & 0x1f0000ff0000ffULL;
+    v = (v | v << 8) & 0x100f00f00f00f00fULL;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
+    v = (v | v << 2) & 0x1249249249249249ULL;
+    return v;
+}
+
+// elems: n_elems x npe node indices (original topology order); pos: 3*n_nodes doubles (rest positions).
+// Returns "" or an error text.
+inline std::string build_plan(HostPlan& P, int n_nodes, int n_elems, int npe, const uint32_t* elems, const double* pos,
+                              int tile_e, int chunk, uint32_t stage_flag) {
+    P = HostPlan();
+    P.n_nodes = n_nodes; P.n_elems = n_elems; P.npe = npe; P.tile_e = tile_e;
+    P.n_tiles = std::max(1, (n_elems + tile_e - 1) / tile_e);
+    for (size_t i = 0; i < size_t(n_elems) * npe; ++i)
+        if (elems[i] >= uint32_t(n_nodes)) return "element refers to a node index out of range";
+
+    // ---- spatial order of the elements (Morton code of the rest centroid)
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int i = 0; i < n_nodes; ++i) for (int c = 0; c < 3; ++c) { lo[c] = std::min(lo[c], pos[3 * size_t(i) + c]); hi[c] = std::max(hi[c], pos[3 * size_t(i) + c]); }
+    double ext = 0; for (int c = 0; c < 3; ++c) ext = std::max(ext, hi[c] - lo[c]);
+    if (!(ext > 0)) ext = 1;
+    std::vector<uint64_t> key(n_elems);
+    for (int e = 0; e < n_elems; ++e) {
+        uint64_t k = 0;
+        for (int c = 0; c < 3; ++c) {
+            double s = 0; for (int a = 0; a < npe; ++a) s += pos[3 * size_t(elems[size_t(e) * npe + a]) + c];
+            double u = (s / npe - lo[c]) / ext; u = std::min(std::max(u, 0.0), 1.0);
+            k |= morton_spread(uint64_t(u * 2097151.0)) << c;
+        }
+        key[e] = k;
+    }
+    std::vector<uint32_t> sorted(n_elems);
+    std::iota(sorted.begin(), sorted.end(), 0u);
+    std::stable_sort(sorted.begin(), sorted.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+    const size_t n_slots = size_t(P.n_tiles) * tile_e;
+    P.order.assign(n_slots, 0xFFFFFFFFu);
+    std::vector<uint32_t> tile_of(n_elems), slot_of_elem(n_elems);
+    for (int i = 0; i < n_elems; ++i) { P.order[i] = sorted[i]; tile_of[sorted[i]] = uint32_t(i / tile_e); slot_of_elem[sorted[i]] = uint32_t(i); }
+
+    // ---- node -> incident (element, corner) in ascending original element order
+    std::vector<uint32_t> inc_off(size_t(n_nodes) + 1, 0);
+    for (size_t i = 0; i < size_t(n_elems) * npe; ++i) inc_off[elems[i] + 1]++;
+    for (int i = 0; i < n_nodes; ++i) inc_off[i + 1] += inc_off[i];
+    std::vector<uint32_t> inc(size_t(n_elems) * npe), fill(inc_off.begin(), inc_off.end() - 1);
+    for (int e = 0; e < n_elems; ++e) for (int c = 0; c < npe; ++c) inc[fill[elems[size_t(e) * npe + c]]++] = uint32_t(e) * npe + c;
+    int maxval = 1;
+    for (int i = 0; i < n_nodes; ++i) maxval = std::max<int>(maxval, inc_off[i + 1] - inc_off[i]);
+    if (maxval > 1023) return "node valence above 1023 is not supported";
+    P.maxval = maxval;
+
+    // ---- interior / shared classification
+    std::vector<int32_t> interior_tile(n_nodes, -1);
+    for (int i = 0; i < n_nodes; ++i) {
+        const uint32_t b = inc_off[i], e = inc_off[i + 1];
+        if (b == e) continue;
+        const uint32_t t0 = tile_of[inc[b] / npe];
+        bool same = true;
+        for (uint32_t k = b + 1; k < e && same; ++k) same = tile_of[inc[k] / npe] == t0;
+        if (same) interior_tile[i] = int32_t(t0);
+    }
+    std::vector<std::vector<uint32_t>> tile_int(P.n_tiles);
+    for (int i = 0; i < n_nodes; ++i) if (interior_tile[i] >= 0) tile_int[interior_tile[i]].push_back(uint32_t(i));
+
+    std::vector<uint32_t> corner_slot(size_t(n_elems) * npe, 0);
+    std::vector<int32_t> local_idx(n_nodes, -1);
+    P.tile_node_off.assign(P.n_tiles + 1, 0);
+    P.tile_nint.assign(P.n_tiles, 0);
+    P.tile_jds.assign(size_t(P.n_tiles) * (maxval + 1), 0);
+    P.lnode.assign(n_slots * npe, 0xFFFFu);
+    for (int t = 0; t < P.n_tiles; ++t) {
+        std::vector<uint32_t>& in = tile_int[t];
+        auto val = [&](uint32_t n) { return inc_off[n + 1] - inc_off[n]; };
+        std::stable_sort(in.begin(), in.end(), [&](uint32_t a, uint32_t b) { return val(a) > val(b); });
+        // jagged-diagonal offsets
+        std::vector<uint32_t> jds(maxval + 1, 0);
+        for (int j = 0; j < maxval; ++j) {
+            uint32_t cnt = 0;  // nodes with valence > j: a prefix of the ranked list
+            while (cnt < in.size() && val(in[cnt]) > uint32_t(j)) ++cnt;
+            jds[j + 1] = jds[j] + cnt;
+        }
+        if (jds[maxval] > 65535u) return "tile needs more than 65535 shared-memory slots; use a smaller tile";
+        for (int j = 0; j <= maxval; ++j) P.tile_jds[size_t(t) * (maxval + 1) + j] = uint16_t(jds[j]);
+        P.max_slots = std::max<int>(P.max_slots, jds[maxval]);
+        const uint32_t base = uint32_t(P.tile_nodes.size());
+        P.tile_node_off[t] = base;
+        P.tile_nint[t] = uint32_t(in.size());
+        for (size_t k = 0; k < in.size(); ++k) {
+            const uint32_t n = in[k];
+            local_idx[n] = int32_t(k);
+            P.tile_nodes.push_back(n);
+            P.tile_val.push_back(uint16_t(val(n)));
+            for (uint32_t j = 0; j < val(n); ++j) corner_slot[inc[inc_off[n] + j]] = jds[j] + uint32_t(k);
+        }
+        P.n_interior += in.size();
+        // shared nodes touched by this tile, ascending id
+        std::vector<uint32_t> sh;
+        const size_t s0 = size_t(t) * tile_e, s1 = std::min(n_slots, s0 + tile_e);
+        for (size_t s = s0; s < s1; ++s) {
+            const uint32_t e = P.order[s];
+            if (e == 0xFFFFFFFFu) continue;
+            for (int c = 0; c < npe; ++c) { const uint32_t n = elems[size_t(e) * npe + c]; if (local_idx[n] < 0) { sh.push_back(n); local_idx[n] = 0x40000000; } }
+        }
+        std::sort(sh.begin(), sh.end());
+        for (size_t k = 0; k < sh.size(); ++k) { local_idx[sh[k]] = int32_t(in.size() + k); P.tile_nodes.push_back(sh[k]); P.tile_val.push_back(0); }
+        const size_t touched = in.size() + sh.size();
+        if (touched >= 65535) return "tile touches more than 65534 nodes; use a smaller tile";
+        P.max_touched = std::max<int>(P.max_touched, int(touched));
+        for (size_t s = s0; s < s1; ++s) {
+            const uint32_t e = P.order[s];
+            if (e == 0xFFFFFFFFu) continue;
+            for (int c = 0; c < npe; ++c) P.lnode[s * npe + c] = uint16_t(local_idx[elems[size_t(e) * npe + c]]);
+        }
+        for (uint32_t n : in) local_idx[n] = -1;
+        for (uint32_t n : sh) local_idx[n] = -1;
+    }
+    P.tile_node_off[P.n_tiles] = uint32_t(P.tile_nodes.size());
+    if (P.max_touched < 1) P.max_touched = 1;
+    if (P.max_slots < 1) P.max_slots = 1;
+
+    // ---- shared nodes: chunks of `chunk`, ranked by valence inside a chunk, HBM staging positions
+    std::vector<uint32_t> shared;
+    for (int i = 0; i < n_nodes; ++i) if (interior_tile[i] < 0) shared.push_back(uint32_t(i));
+    P.n_shared = int(shared.size());
+    P.n_chunks = std::max(1, (P.n_shared + chunk - 1) / chunk);
+    P.sh_nodes.assign(size_t(P.n_chunks) * chunk, 0xFFFFFFFFu);
+    P.sh_val.assign(size_t(P.n_chunks) * chunk, 0);
+    P.sh_jds.assign(size_t(P.n_chunks) * (maxval + 1), 0);
+    P.sh_base.assign(P.n_chunks, 0);
+    size_t stage = 0;
+    for (int c = 0; c < P.n_chunks; ++c) {
+        const size_t b = size_t(c) * chunk, e = std::min(shared.size(), b + chunk);
+        std::vector<uint32_t> ns(shared.begin() + std::min(b, shared.size()), shared.begin() + e);
+        auto val = [&](uint32_t n) { return inc_off[n + 1] - inc_off[n]; };
+        std::stable_sort(ns.begin(), ns.end(), [&](uint32_t a, uint32_t b2) { return val(a) > val(b2); });
+        std::vector<uint32_t> jds(maxval + 1, 0);
+        for (int j = 0; j < maxval; ++j) {
+            uint32_t cnt = 0;
+            while (cnt < ns.size() && val(ns[cnt]) > uint32_t(j)) ++cnt;
+            jds[j + 1] = jds[j] + cnt;
+        }
+        for (int j = 0; j <= maxval; ++j) P.sh_jds[size_t(c) * (maxval + 1) + j] = jds[j];
+        P.sh_base[c] = uint32_t(stage);
+        for (size_t k = 0; k < ns.size(); ++k) {
+            const uint32_t n = ns[k];
+            P.sh_nodes[b + k] = n;
+            P.sh_val[b + k] = uint16_t(val(n));
+            for (uint32_t j = 0; j < val(n); ++j) {
+                const size_t p = stage + jds[j] + k;
+                if (p >= 0x7fffffffu) return "staging buffer exceeds 2^31 entries";
+                corner_slot[inc[inc_off[n] + j]] = stage_flag | uint32_t(p);
+            }
+        }
+        stage += jds[maxval];
+        P.n_staged_corners += jds[maxval];
+    }
+    P.stage_n = std::max<size_t>(stage, 1);
+
+    // ---- per element-slot destination table
+    P.slot.assign(n_slots * npe, 0);
+    for (size_t s = 0; s < n_slots; ++s) {
+        const uint32_t e = P.order[s];
+        if (e == 0xFFFFFFFFu) continue;
+        for (int c = 0; c < npe; ++c) P.slot[s * npe + c] = corner_slot[size_t(e) * npe + c];
+    }
+    (void)slot_of_elem;
+    return "";
+}
+
+}  // namespace sb

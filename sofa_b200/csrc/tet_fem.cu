@@ -1,0 +1,201 @@
+// TetrahedronFEMForceField<B200Vec3Types>: device upload + launches + C ABI.
+#include <cstring>
+#include <memory>
+
+#include "tet_host.h"
+
+using namespace sb;
+
+struct sofab200_tetfem {
+    virtual ~sofab200_tetfem() {}
+    sofab200_ctx* ctx = nullptr;
+    int real = 0, method = 1;
+    size_t n_nodes = 0, n_tets = 0;
+};
+
+namespace sb {
+
+template <class R> struct TetFF : sofab200_tetfem {
+    HostTet<R> h;
+    DevBuf<ushort4> lnode; DevBuf<uint4> slot; DevBuf<uint32_t> orig;
+    DevBuf<Quad<R>> rk0, rk1, rk2, j0, j1, j2, x0a, x0b, x0c, sv0, sv1, sv2, sv3, sv4;
+    DevBuf<uint32_t> tile_node_off, tile_nodes, tile_nint, sh_nodes, sh_jds, sh_base;
+    DevBuf<uint16_t> tile_val, tile_jds, sh_val;
+    DevBuf<R> stage;
+    DevBuf<R> rot_export;
+    TetDev<R> dev() {
+        const HostPlan& plan = h.plan;
+        TetDev<R> d;
+        d.t.n_nodes = int(n_nodes); d.t.n_elems = int(n_tets); d.t.n_tiles = plan.n_tiles; d.t.tile_e = plan.tile_e; d.t.maxval = plan.maxval;
+        d.t.tile_node_off = tile_node_off.p; d.t.tile_nodes = tile_nodes.p; d.t.tile_nint = tile_nint.p; d.t.tile_val = tile_val.p; d.t.tile_jds = tile_jds.p;
+        d.t.n_shared = plan.n_shared; d.t.n_chunks = plan.n_chunks; d.t.sh_nodes = sh_nodes.p; d.t.sh_val = sh_val.p; d.t.sh_jds = sh_jds.p; d.t.sh_base = sh_base.p;
+        d.t.stage = stage.p; d.t.stage_n = plan.stage_n;
+        d.lnode = lnode.p; d.slot = slot.p;
+        d.rk0 = rk0.p; d.rk1 = rk1.p; d.rk2 = rk2.p; d.j0 = j0.p; d.j1 = j1.p; d.j2 = j2.p;
+        d.x0a = x0a.p; d.x0b = x0b.p; d.x0c = x0c.p; d.sv0 = sv0.p; d.sv1 = sv1.p; d.sv2 = sv2.p; d.sv3 = sv3.p; d.sv4 = sv4.p;
+        d.k_factor = R(0);
+        return d;
+    }
+};
+
+template <class R> static int tet_upload(TetFF<R>& ff) {
+    HostTet<R>& H = ff.h;
+    const HostPlan& P = H.plan;
+    cudaStream_t s = ff.ctx->stream;
+    SB_TRY(ff.lnode.upload(H.lnode, s)); SB_TRY(ff.slot.upload(H.slot, s)); SB_TRY(ff.orig.upload(P.order, s));
+    SB_TRY(ff.rk0.upload(H.rk0, s)); SB_TRY(ff.rk1.upload(H.rk1, s)); SB_TRY(ff.rk2.upload(H.rk2, s));
+    SB_TRY(ff.j0.upload(H.j0, s)); SB_TRY(ff.j1.upload(H.j1, s)); SB_TRY(ff.j2.upload(H.j2, s));
+    SB_TRY(ff.x0a.upload(H.x0a, s)); SB_TRY(ff.x0b.upload(H.x0b, s)); SB_TRY(ff.x0c.upload(H.x0c, s));
+    if (H.method == SOFAB200_TET_SVD) {
+        SB_TRY(ff.sv0.upload(H.sv[0], s)); SB_TRY(ff.sv1.upload(H.sv[1], s)); SB_TRY(ff.sv2.upload(H.sv[2], s));
+        SB_TRY(ff.sv3.upload(H.sv[3], s)); SB_TRY(ff.sv4.upload(H.sv[4], s));
+    }
+    SB_TRY(ff.tile_node_off.upload(P.tile_node_off, s)); SB_TRY(ff.tile_nodes.upload(P.tile_nodes, s)); SB_TRY(ff.tile_nint.upload(P.tile_nint, s));
+    SB_TRY(ff.tile_val.upload(P.tile_val, s)); SB_TRY(ff.tile_jds.upload(P.tile_jds, s));
+    SB_TRY(ff.sh_nodes.upload(P.sh_nodes, s)); SB_TRY(ff.sh_val.upload(P.sh_val, s)); SB_TRY(ff.sh_jds.upload(P.sh_jds, s)); SB_TRY(ff.sh_base.upload(P.sh_base, s));
+    SB_TRY(ff.stage.alloc(3 * P.stage_n)); SB_TRY(ff.stage.zero(s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    // the tile-ordered host planes are no longer needed once they are resident in HBM
+    for (auto* v : {&H.rk0, &H.rk1, &H.rk2, &H.j0, &H.j1, &H.j2, &H.x0a, &H.x0b, &H.x0c}) { v->clear(); v->shrink_to_fit(); }
+    for (auto& v : H.sv) { v.clear(); v.shrink_to_fit(); }
+    H.lnode.clear(); H.lnode.shrink_to_fit(); H.slot.clear(); H.slot.shrink_to_fit();
+    return SOFAB200_OK;
+}
+
+template <class R, int MODE> static int tet_launch_mode(TetFF<R>& ff, const TetDev<R>& d, const R* in, const NodeEpilogue<R>& ep) {
+    auto kern = tet_tile_kernel<R, MODE>;
+    static thread_local size_t configured = 0;
+    if (ff.h.smem_bytes > 48 * 1024 && configured < ff.h.smem_bytes) {
+        SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ff.h.smem_bytes)));
+        configured = ff.h.smem_bytes;
+    }
+    const int cls = (MODE == TM_DF_COROT || MODE == TM_DF_SMALL) ? 0 : 2;
+    ff.ctx->prof_start(cls);
+    kern<<<ff.h.plan.n_tiles, 256, ff.h.smem_bytes, ff.ctx->stream>>>(d, in, ep, ff.h.plan.max_touched, ff.h.plan.max_slots);
+    ff.ctx->prof_stop(cls);
+    ff.ctx->launches++;
+    SB_CUDA(cudaGetLastError());
+    return SOFAB200_OK;
+}
+
+// Element pass + boundary gather with a caller-provided epilogue (also used by the solver node).
+template <class R> int tet_run(sofab200_tetfem* base, bool dforce, const R* in, R k_factor, NodeEpilogue<R> ep) {
+    TetFF<R>& ff = *static_cast<TetFF<R>*>(base);
+    const HostPlan& plan = ff.h.plan;
+    TetDev<R> d = ff.dev();
+    d.k_factor = k_factor;
+    ep.partial_base = 0;
+    ep.partial_total = plan.n_tiles + plan.n_chunks;
+    if (dforce) {
+        if (ff.method == SOFAB200_TET_SMALL) SB_TRY((tet_launch_mode<R, TM_DF_SMALL>(ff, d, in, ep)));
+        else SB_TRY((tet_launch_mode<R, TM_DF_COROT>(ff, d, in, ep)));
+    } else {
+        switch (ff.method) {
+        case SOFAB200_TET_SMALL: SB_TRY((tet_launch_mode<R, TM_F_SMALL>(ff, d, in, ep))); break;
+        case SOFAB200_TET_LARGE: SB_TRY((tet_launch_mode<R, TM_F_LARGE>(ff, d, in, ep))); break;
+        case SOFAB200_TET_POLAR: SB_TRY((tet_launch_mode<R, TM_F_POLAR>(ff, d, in, ep))); break;
+        default: SB_TRY((tet_launch_mode<R, TM_F_SVD>(ff, d, in, ep))); break;
+        }
+    }
+    ep.partial_base = plan.n_tiles;
+    ff.ctx->prof_start(1);
+    gather_shared_kernel<R><<<plan.n_chunks, kGatherChunk, 0, ff.ctx->stream>>>(d.t, ep);
+    ff.ctx->prof_stop(1);
+    ff.ctx->launches++;
+    SB_CUDA(cudaGetLastError());
+    return SOFAB200_OK;
+}
+template int tet_run<float>(sofab200_tetfem*, bool, const float*, float, NodeEpilogue<float>);
+template int tet_run<double>(sofab200_tetfem*, bool, const double*, double, NodeEpilogue<double>);
+
+int tet_real(sofab200_tetfem* ff) { return ff->real; }
+size_t tet_nodes(sofab200_tetfem* ff) { return ff->n_nodes; }
+int tet_partial_count(sofab200_tetfem* base) {
+    if (base->real == SOFAB200_F32) { auto& ff = *static_cast<TetFF<float>*>(base); return ff.h.plan.n_tiles + ff.h.plan.n_chunks; }
+    auto& ff = *static_cast<TetFF<double>*>(base); return ff.h.plan.n_tiles + ff.h.plan.n_chunks;
+}
+
+template <class R> static int tet_create(sofab200_ctx* ctx, size_t n_nodes, const void* rest, size_t n_tets, const uint32_t* tets,
+                                         const sofab200_tetfem_desc* desc, sofab200_tetfem** out) {
+    std::unique_ptr<TetFF<R>> ff(new TetFF<R>());
+    ff->ctx = ctx; ff->real = sizeof(R) == 4 ? SOFAB200_F32 : SOFAB200_F64; ff->method = desc->method;
+    ff->n_nodes = n_nodes; ff->n_tets = n_tets;
+    const std::string err = tet_host_build(ff->h, n_nodes, static_cast<const R*>(rest), n_tets, tets, desc, kGatherChunk);
+    if (!err.empty()) return fail(SOFAB200_ERR_INVALID, err);
+    SB_TRY(tet_upload(*ff));
+    *out = ff.release();
+    return SOFAB200_OK;
+}
+
+template <class R> static int tet_get(TetFF<R>& ff, const std::string& what, void* out) {
+    auto cp = [&](const std::vector<R>& v) { std::memcpy(out, v.data(), v.size() * sizeof(R)); return SOFAB200_OK; };
+    if (what == "initialRotations") return cp(ff.h.h_R0t);
+    if (what == "strainDisplacements") return cp(ff.h.h_J);
+    if (what == "materialsStiffnesses") return cp(ff.h.h_K);
+    if (what == "rotatedInitialElements") return cp(ff.h.h_X0);
+    if (what == "initialTransformation") return cp(ff.h.h_A0inv);
+    if (what == "rotations") {
+        if (ff.method == SOFAB200_TET_SMALL) return fail(SOFAB200_ERR_UNSUPPORTED, "method small keeps no rotations");
+        SB_TRY(ff.rot_export.alloc(9 * ff.n_tets));
+        const size_t NS = size_t(ff.h.plan.n_tiles) * ff.h.plan.tile_e;
+        tet_export_rotations_kernel<R><<<unsigned((NS + 255) / 256), 256, 0, ff.ctx->stream>>>(ff.dev(), ff.orig.p, ff.rot_export.p);
+        ff.ctx->launches++;
+        SB_CUDA(cudaGetLastError());
+        SB_CUDA(cudaMemcpyAsync(out, ff.rot_export.p, 9 * ff.n_tets * sizeof(R), cudaMemcpyDeviceToHost, ff.ctx->stream));
+        SB_CUDA(cudaStreamSynchronize(ff.ctx->stream));
+        return SOFAB200_OK;
+    }
+    return fail(SOFAB200_ERR_INVALID, "unknown array name: " + what);
+}
+
+}  // namespace sb
+
+extern "C" {
+
+int sofab200_tetfem_create(sofab200_ctx* ctx, sofab200_real real, size_t n_nodes, const void* rest_position_host, size_t n_tets,
+                           const uint32_t* tets_host, const sofab200_tetfem_desc* desc, sofab200_tetfem** out) {
+    SB_CHECK(ctx && out && desc && rest_position_host && (tets_host || n_tets == 0), "null argument");
+    SB_CHECK(desc->method >= 0 && desc->method <= 3, "method must be small, large, polar or svd");
+    SB_CHECK(desc->n_young > 0 && desc->young && desc->n_poisson > 0 && desc->poisson, "youngModulus / poissonRatio are required");
+    SB_CHECK(n_nodes < 0xFFFFFFFFull && n_tets < 0x3FFFFFFFull, "mesh too large for 32-bit indices");
+    SB_CUDA(cudaSetDevice(ctx->device));
+    if (real == SOFAB200_F32) return tet_create<float>(ctx, n_nodes, rest_position_host, n_tets, tets_host, desc, out);
+    return tet_create<double>(ctx, n_nodes, rest_position_host, n_tets, tets_host, desc, out);
+}
+int sofab200_tetfem_destroy(sofab200_tetfem* ff) { delete ff; return SOFAB200_OK; }
+
+int sofab200_tetfem_add_force(sofab200_tetfem* ff, void* f_dev, const void* x_dev) {
+    SB_CHECK(ff && f_dev && x_dev, "null argument");
+    if (ff->real == SOFAB200_F32) {
+        NodeEpilogue<float> ep{}; ep.init_src = static_cast<float*>(f_dev); ep.out = static_cast<float*>(f_dev); ep.sign = +1;
+        return tet_run<float>(ff, false, static_cast<const float*>(x_dev), 0.f, ep);
+    }
+    NodeEpilogue<double> ep{}; ep.init_src = static_cast<double*>(f_dev); ep.out = static_cast<double*>(f_dev); ep.sign = +1;
+    return tet_run<double>(ff, false, static_cast<const double*>(x_dev), 0.0, ep);
+}
+int sofab200_tetfem_add_dforce(sofab200_tetfem* ff, void* df_dev, const void* dx_dev, double k_factor) {
+    SB_CHECK(ff && df_dev && dx_dev, "null argument");
+    SB_CHECK(df_dev != dx_dev, "df and dx must be distinct vectors");
+    if (ff->real == SOFAB200_F32) {
+        NodeEpilogue<float> ep{}; ep.init_src = static_cast<float*>(df_dev); ep.out = static_cast<float*>(df_dev); ep.sign = -1;
+        return tet_run<float>(ff, true, static_cast<const float*>(dx_dev), float(k_factor), ep);
+    }
+    NodeEpilogue<double> ep{}; ep.init_src = static_cast<double*>(df_dev); ep.out = static_cast<double*>(df_dev); ep.sign = -1;
+    return tet_run<double>(ff, true, static_cast<const double*>(dx_dev), k_factor, ep);
+}
+int sofab200_tetfem_get(sofab200_tetfem* ff, const char* what, void* out_host) {
+    SB_CHECK(ff && what && out_host, "null argument");
+    if (ff->real == SOFAB200_F32) return tet_get(*static_cast<TetFF<float>*>(ff), what, out_host);
+    return tet_get(*static_cast<TetFF<double>*>(ff), what, out_host);
+}
+int sofab200_tetfem_stats(const sofab200_tetfem* ff, uint64_t out[8]) {
+    SB_CHECK(ff && out, "null argument");
+    const HostPlan* P; size_t smem;
+    if (ff->real == SOFAB200_F32) { auto* f = static_cast<const TetFF<float>*>(ff); P = &f->h.plan; smem = f->h.smem_bytes; }
+    else { auto* f = static_cast<const TetFF<double>*>(ff); P = &f->h.plan; smem = f->h.smem_bytes; }
+    out[0] = P->n_tiles; out[1] = P->tile_e; out[2] = P->n_interior; out[3] = P->n_shared; out[4] = P->n_staged_corners;
+    out[5] = smem; out[6] = P->maxval; out[7] = ff->n_tets;
+    return SOFAB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,154 @@
+// Host-side init of TetrahedronFEMForceField<B200Vec3Types>: the reference's reinit() arithmetic, the tile /
+// gather plan, and the element planes in tile order.  Pure host code (also used by tests/emu).
+#pragma once
+#include <cstring>
+
+#include "math3.cuh"
+#include "plan.h"
+#include "tet_kernels.cuh"
+
+namespace sb {
+
+template <class R> struct HostTet {
+    int method = 1;
+    size_t n_nodes = 0, n_tets = 0;
+    HostPlan plan;
+    // element-ordered values, as the reference class keeps them
+    std::vector<R> h_K, h_J, h_X0, h_R0t, h_A0inv;
+    // element planes in tile order
+    std::vector<ushort4> lnode; std::vector<uint4> slot;
+    std::vector<Quad<R>> rk0, rk1, rk2, j0, j1, j2, x0a, x0b, x0c, sv[5];
+    size_t smem_bytes = 0;
+};
+
+// peudo_determinant_for_coef, TetrahedronFEMForceField.inl:204-208
+template <class R> static inline R pdet(R m00, R m01, R m02, R m10, R m11, R m12) {
+    return m01 * m12 - m11 * m02 - m00 * m12 + m10 * m02 + m00 * m11 - m10 * m01;
+}
+// computeStrainDisplacement, :134-202 -- the 12 distinct cofactors
+template <class R> static void strain_displacement(R* j, const V3<R>& a, const V3<R>& b, const V3<R>& c, const V3<R>& d) {
+    j[0] = -pdet(b.y, c.y, d.y, b.z, c.z, d.z);
+    j[1] = pdet(b.x, c.x, d.x, b.z, c.z, d.z);
+    j[2] = -pdet(b.x, c.x, d.x, b.y, c.y, d.y);
+    j[3] = pdet(c.y, d.y, a.y, c.z, d.z, a.z);
+    j[4] = -pdet(c.x, d.x, a.x, c.z, d.z, a.z);
+    j[5] = pdet(c.x, d.x, a.x, c.y, d.y, a.y);
+    j[6] = -pdet(d.y, a.y, b.y, d.z, a.z, b.z);
+    j[7] = pdet(d.x, a.x, b.x, d.z, a.z, b.z);
+    j[8] = -pdet(d.x, a.x, b.x, d.y, a.y, b.y);
+    j[9] = pdet(a.y, b.y, c.y, a.z, b.z, c.z);
+    j[10] = -pdet(a.x, b.x, c.x, a.z, b.z, c.z);
+    j[11] = pdet(a.x, b.x, c.x, a.y, b.y, c.y);
+}
+
+// reinit(): TetrahedronFEMForceField.inl:1390-1505 with computeMaterialStiffness :255-291,
+// initSmall :526-532, initLarge :834-868, initPolar :992-1023, initSVD :1086-1117
+template <class R> static int tet_init_elements(HostTet<R>& ff, const R* x0, const uint32_t* tets, const sofab200_tetfem_desc* desc) {
+    const size_t T = ff.n_tets;
+    std::vector<R> young(desc->n_young), poisson(desc->n_poisson), lsf(desc->n_local_stiffness);
+    for (size_t i = 0; i < young.size(); ++i) young[i] = R(desc->young[i]);
+    for (size_t i = 0; i < poisson.size(); ++i) poisson[i] = R(desc->poisson[i]);
+    for (size_t i = 0; i < lsf.size(); ++i) lsf[i] = R(desc->local_stiffness[i]);
+    ff.h_K.assign(3 * T, 0); ff.h_J.assign(12 * T, 0); ff.h_X0.assign(12 * T, 0); ff.h_R0t.assign(9 * T, 0);
+    if (ff.method == SOFAB200_TET_SVD) ff.h_A0inv.assign(9 * T, 0);
+    auto P = [&](uint32_t n) { return mk3<R>(x0[3 * size_t(n)], x0[3 * size_t(n) + 1], x0[3 * size_t(n) + 2]); };
+    for (size_t i = 0; i < T; ++i) {
+        const uint32_t ia = tets[4 * i], ib = tets[4 * i + 1], ic = tets[4 * i + 2], id = tets[4 * i + 3];
+        const V3<R> a = P(ia), b = P(ib), c = P(ic), d = P(id);
+        // material stiffness
+        const R E_el = young.size() > i ? young[i] : young[0];
+        const R E = (lsf.empty() ? 1.0f : lsf[i * lsf.size() / T]) * E_el;
+        const R nu = poisson.size() > i ? poisson[i] : poisson[0];
+        R k00 = 1, k01 = nu / (1 - nu), k33 = (1 - 2 * nu) / (2 * (1 - nu));
+        const R s = (E * (1 - nu)) / ((1 + nu) * (1 - 2 * nu));
+        k00 *= s; k01 *= s; k33 *= s;
+        const R vol = std::abs(dot3(cross3(b - a, c - a), d - a) / R(6));  // geometry::Tetrahedron::volume
+        const R div = vol * 36;
+        ff.h_K[3 * i] = k00 / div; ff.h_K[3 * i + 1] = k01 / div; ff.h_K[3 * i + 2] = k33 / div;
+        R* X0 = &ff.h_X0[12 * i];
+        R* R0t = &ff.h_R0t[9 * i];
+        if (ff.method == SOFAB200_TET_SMALL) {
+            strain_displacement(&ff.h_J[12 * i], a, b, c, d);
+            const V3<R> q[4] = {a, b, c, d};
+            for (int n = 0; n < 4; ++n) { X0[3 * n] = q[n].x; X0[3 * n + 1] = q[n].y; X0[3 * n + 2] = q[n].z; }
+            R0t[0] = R0t[4] = R0t[8] = 1;
+            continue;
+        }
+        M3<R> R01;
+        if (ff.method == SOFAB200_TET_LARGE) {
+            V3<R> ex = b - a; normalize3(ex);
+            V3<R> ey = c - a;
+            V3<R> ez = cross3(ex, ey); normalize3(ez);
+            ey = cross3(ez, ex);
+            set_row(R01, 0, ex); set_row(R01, 1, ey); set_row(R01, 2, ez);
+        } else {
+            M3<R> A;
+            set_row(A, 0, b - a); set_row(A, 1, c - a); set_row(A, 2, d - a);
+            if (ff.method == SOFAB200_TET_SVD) {
+                M3<R> Ai;
+                std::memset(&Ai, 0, sizeof(Ai));
+                invert3(Ai, A);
+                for (int r = 0; r < 3; ++r) for (int cc = 0; cc < 3; ++cc) ff.h_A0inv[9 * i + 3 * r + cc] = Ai.m[r][cc];
+            }
+            polar_decomposition(A, R01);
+        }
+        for (int r = 0; r < 3; ++r) for (int cc = 0; cc < 3; ++cc) R0t[3 * r + cc] = R01.m[cc][r];
+        V3<R> q[4] = {mul(R01, a), mul(R01, b), mul(R01, c), mul(R01, d)};
+        if (ff.method == SOFAB200_TET_LARGE) {
+            q[1] = q[1] - q[0]; q[2] = q[2] - q[0]; q[3] = q[3] - q[0];
+            q[0] = mk3<R>(0, 0, 0);
+        }
+        for (int n = 0; n < 4; ++n) { X0[3 * n] = q[n].x; X0[3 * n + 1] = q[n].y; X0[3 * n + 2] = q[n].z; }
+        strain_displacement(&ff.h_J[12 * i], q[0], q[1], q[2], q[3]);
+    }
+    return SOFAB200_OK;
+}
+
+
+// element planes in tile order
+template <class R> static void tet_fill_planes(HostTet<R>& ff) {
+    const HostPlan& P = ff.plan;
+    const size_t NS = size_t(P.n_tiles) * P.tile_e;
+    const Quad<R> z{0, 0, 0, 0};
+    ff.lnode.resize(NS); ff.slot.resize(NS);
+    for (auto* v : {&ff.rk0, &ff.rk1, &ff.rk2, &ff.j0, &ff.j1, &ff.j2, &ff.x0a, &ff.x0b, &ff.x0c}) v->assign(NS, z);
+    const bool svd = ff.method == SOFAB200_TET_SVD;
+    if (svd) for (auto& v : ff.sv) v.assign(NS, z);
+    for (size_t es = 0; es < NS; ++es) {
+        const uint32_t e = P.order[es];
+        ff.lnode[es] = make_ushort4(P.lnode[4 * es], P.lnode[4 * es + 1], P.lnode[4 * es + 2], P.lnode[4 * es + 3]);
+        ff.slot[es] = make_uint4(P.slot[4 * es], P.slot[4 * es + 1], P.slot[4 * es + 2], P.slot[4 * es + 3]);
+        if (e == 0xFFFFFFFFu) continue;
+        const R* r = &ff.h_R0t[9 * size_t(e)]; const R* k = &ff.h_K[3 * size_t(e)];
+        const R* j = &ff.h_J[12 * size_t(e)]; const R* x = &ff.h_X0[12 * size_t(e)];
+        ff.rk0[es] = Quad<R>{r[0], r[1], r[2], r[3]}; ff.rk1[es] = Quad<R>{r[4], r[5], r[6], r[7]}; ff.rk2[es] = Quad<R>{r[8], k[0], k[1], k[2]};
+        ff.j0[es] = Quad<R>{j[0], j[1], j[2], j[3]}; ff.j1[es] = Quad<R>{j[4], j[5], j[6], j[7]}; ff.j2[es] = Quad<R>{j[8], j[9], j[10], j[11]};
+        ff.x0a[es] = Quad<R>{x[0], x[1], x[2], x[3]}; ff.x0b[es] = Quad<R>{x[4], x[5], x[6], x[7]}; ff.x0c[es] = Quad<R>{x[8], x[9], x[10], x[11]};
+        if (svd) {
+            const R* a = &ff.h_A0inv[9 * size_t(e)];
+            ff.sv[0][es] = Quad<R>{a[0], a[1], a[2], a[3]}; ff.sv[1][es] = Quad<R>{a[4], a[5], a[6], a[7]};
+            ff.sv[2][es] = Quad<R>{a[8], r[0], r[1], r[2]}; ff.sv[3][es] = Quad<R>{r[3], r[4], r[5], r[6]}; ff.sv[4][es] = Quad<R>{r[7], r[8], 0, 0};
+        }
+    }
+}
+
+// init()+reinit()+layout.  Returns "" or an error text.
+template <class R> static std::string tet_host_build(HostTet<R>& ff, size_t n_nodes, const R* x0, size_t n_tets, const uint32_t* tets,
+                                                     const sofab200_tetfem_desc* desc, int chunk) {
+    ff.method = desc->method; ff.n_nodes = n_nodes; ff.n_tets = n_tets;
+    for (size_t i = 0; i < 4 * n_tets; ++i) if (tets[i] >= n_nodes) return "tetrahedron refers to a node index out of range";
+    tet_init_elements(ff, x0, tets, desc);
+    std::vector<double> pos(3 * n_nodes);
+    for (size_t i = 0; i < 3 * n_nodes; ++i) pos[i] = double(x0[i]);
+    int tile_e = desc->tile_elems > 0 ? desc->tile_elems : 1024;
+    if (const char* env = getenv("SOFAB200_TILE_ELEMS")) { const int v = atoi(env); if (v > 0) tile_e = v; }
+    tile_e = (tile_e + 255) / 256 * 256;
+    const std::string err = build_plan(ff.plan, int(n_nodes), int(n_tets), 4, tets, pos.data(), tile_e, chunk, kStageFlag);
+    if (!err.empty()) return err;
+    ff.smem_bytes = tet_smem_bytes<R>(ff.plan.max_touched, ff.plan.max_slots);
+    if (ff.smem_bytes > 200 * 1024) return "tile does not fit in shared memory; use a smaller tile_elems";
+    tet_fill_planes(ff);
+    return "";
+}
+
+}  // namespace sb

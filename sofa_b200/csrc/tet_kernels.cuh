@@ -1,0 +1,252 @@
+// TetrahedronFEMForceField on the device: one CTA per tile of elements.
+//   phase 1  stage the tile's nodal input vectors (x or dx) in shared memory
+//   phase 2  one thread per element: rotation (addForce) or cached rotation (addDForce), F = J (K (J^T D)),
+//            rotate back; scatter the 4 corner contributions to their slot (shared memory for interior
+//            nodes, HBM staging for shared nodes)
+//   phase 3  one thread per interior node: sequential sum of its slots in element order + fused epilogue
+// Arithmetic follows the reference statement by statement (file:line cited per function); compiled with
+// -fmad=false so no multiply-add is contracted.
+#pragma once
+#include "fem_layout.cuh"
+#include "math3.cuh"
+
+namespace sb {
+
+enum TetMode { TM_DF_COROT = 0, TM_DF_SMALL = 1, TM_F_SMALL = 2, TM_F_LARGE = 3, TM_F_POLAR = 4, TM_F_SVD = 5 };
+
+template <class R> struct TetDev {
+    TileDev<R> t;
+    const ushort4* lnode;      // [n_tiles*tile_e] local node index of the 4 corners (0xFFFF = padding element)
+    const uint4* slot;         // destination slot of each corner's contribution
+    Quad<R>* rk0; Quad<R>* rk1; Quad<R>* rk2;            // rotations[e] (9, row-major) + {K00, K01, K33}
+    const Quad<R>* j0; const Quad<R>* j1; const Quad<R>* j2;     // 12 strain-displacement cofactors
+    const Quad<R>* x0a; const Quad<R>* x0b; const Quad<R>* x0c;  // _rotatedInitialElements (small: rest positions)
+    const Quad<R>* sv0; const Quad<R>* sv1; const Quad<R>* sv2; const Quad<R>* sv3; const Quad<R>* sv4;  // svd: A0^-1 (9) + R0^T (9)
+    R k_factor;                // addDForce: (Real)kFactorIncludingRayleighDamping
+};
+
+// computeForce (TetrahedronFEMForceField.inl:293-415 without plasticity, :417-521 with `fact`).
+// j[3n..3n+2] = (jx,jy,jz) of node n: J(3n,0)=J(3n+1,3)=J(3n+2,5)=jx, J(3n,3)=J(3n+1,1)=J(3n+2,4)=jy,
+// J(3n,5)=J(3n+1,4)=J(3n+2,2)=jz; K has three distinct values k0=K(i,i) i<3, k1=K(i,j) i!=j<3, k2=K(i,i) i>=3.
+template <class R, bool USE_FACT> HD void tet_compute_force(R F[12], const R D[12], const R j[12], R k0, R k1, R k2, R fact) {
+    R s0 = j[0] * D[0] + j[3] * D[3] + j[6] * D[6] + j[9] * D[9];
+    R s1 = j[1] * D[1] + j[4] * D[4] + j[7] * D[7] + j[10] * D[10];
+    R s2 = j[2] * D[2] + j[5] * D[5] + j[8] * D[8] + j[11] * D[11];
+    R s3 = j[1] * D[0] + j[0] * D[1] + j[4] * D[3] + j[3] * D[4] + j[7] * D[6] + j[6] * D[7] + j[10] * D[9] + j[9] * D[10];
+    R s4 = j[2] * D[1] + j[1] * D[2] + j[5] * D[4] + j[4] * D[5] + j[8] * D[7] + j[7] * D[8] + j[11] * D[10] + j[10] * D[11];
+    R s5 = j[2] * D[0] + j[0] * D[2] + j[5] * D[3] + j[3] * D[5] + j[8] * D[6] + j[6] * D[8] + j[11] * D[9] + j[9] * D[11];
+    R t0 = k0 * s0 + k1 * s1 + k1 * s2;
+    R t1 = k1 * s0 + k0 * s1 + k1 * s2;
+    R t2 = k1 * s0 + k1 * s1 + k0 * s2;
+    R t3 = k2 * s3, t4 = k2 * s4, t5 = k2 * s5;
+    if (USE_FACT) { t0 *= fact; t1 *= fact; t2 *= fact; t3 *= fact; t4 *= fact; t5 *= fact; }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+        const R jx = j[3 * n], jy = j[3 * n + 1], jz = j[3 * n + 2];
+        F[3 * n + 0] = jx * t0 + jy * t3 + jz * t5;
+        F[3 * n + 1] = jy * t1 + jx * t3 + jz * t4;
+        F[3 * n + 2] = jz * t2 + jy * t4 + jx * t5;
+    }
+}
+
+// One element: inputs are the 4 nodal vectors P (positions for addForce, dx for addDForce); outputs the 4 corner
+// contributions C in the form the reference adds (addForce) or subtracts (addDForce) them.  addForce modes also
+// store rotations[e].  Host-callable so that tests/emu can execute the very same statements on the CPU.
+template <class R, int MODE> HD void tet_element(const TetDev<R>& d, size_t es, const V3<R> P[4], V3<R> C[4]) {
+    const Quad<R> q0 = d.rk0[es], q1 = d.rk1[es], q2 = d.rk2[es];
+    const Quad<R> ja = d.j0[es], jb = d.j1[es], jc = d.j2[es];
+    const R j[12] = {ja.a, ja.b, ja.c, ja.d, jb.a, jb.b, jb.c, jb.d, jc.a, jc.b, jc.c, jc.d};
+    const R k0 = q2.b, k1 = q2.c, k2 = q2.d;
+    R F[12];
+    if (MODE == TM_DF_COROT) {
+        // applyStiffnessCorotational, TetrahedronFEMForceField.inl:1192-1237 (rot = rotations[e])
+        const R r00 = q0.a, r01 = q0.b, r02 = q0.c, r10 = q0.d, r11 = q1.a, r12 = q1.b, r20 = q1.c, r21 = q1.d, r22 = q2.a;
+        R X[12];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            X[3 * n + 0] = r00 * P[n].x + r10 * P[n].y + r20 * P[n].z;
+            X[3 * n + 1] = r01 * P[n].x + r11 * P[n].y + r21 * P[n].z;
+            X[3 * n + 2] = r02 * P[n].x + r12 * P[n].y + r22 * P[n].z;
+        }
+        tet_compute_force<R, true>(F, X, j, k0, k1, k2, d.k_factor);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            C[n].x = r00 * F[3 * n] + r01 * F[3 * n + 1] + r02 * F[3 * n + 2];
+            C[n].y = r10 * F[3 * n] + r11 * F[3 * n + 1] + r12 * F[3 * n + 2];
+            C[n].z = r20 * F[3 * n] + r21 * F[3 * n + 1] + r22 * F[3 * n + 2];
+        }
+    } else if (MODE == TM_DF_SMALL) {
+        // applyStiffnessSmall, :724-748
+        R X[12];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) { X[3 * n] = P[n].x; X[3 * n + 1] = P[n].y; X[3 * n + 2] = P[n].z; }
+        tet_compute_force<R, true>(F, X, j, k0, k1, k2, d.k_factor);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) C[n] = mk3<R>(F[3 * n], F[3 * n + 1], F[3 * n + 2]);
+    } else {
+        const Quad<R> xa = d.x0a[es], xb = d.x0b[es], xc = d.x0c[es];
+        const R X0[12] = {xa.a, xa.b, xa.c, xa.d, xb.a, xb.b, xb.c, xb.d, xc.a, xc.b, xc.c, xc.d};
+        R D[12];
+        if (MODE == TM_F_SMALL) {
+            // accumulateForceSmall, :534-556 (X0 planes hold the rest positions of the 4 nodes)
+            D[0] = 0; D[1] = 0; D[2] = 0;
+#pragma unroll
+            for (int n = 1; n < 4; ++n) {
+                D[3 * n + 0] = X0[3 * n + 0] - X0[0] - P[n].x + P[0].x;
+                D[3 * n + 1] = X0[3 * n + 1] - X0[1] - P[n].y + P[0].y;
+                D[3 * n + 2] = X0[3 * n + 2] - X0[2] - P[n].z + P[0].z;
+            }
+            tet_compute_force<R, false>(F, D, j, k0, k1, k2, R(0));
+#pragma unroll
+            for (int n = 0; n < 4; ++n) C[n] = mk3<R>(F[3 * n], F[3 * n + 1], F[3 * n + 2]);
+        } else {
+            M3<R> R02;  // R_0_2: rows = element frame axes
+            if (MODE == TM_F_LARGE) {
+                // computeRotationLarge, :754-778
+                V3<R> ex = P[1] - P[0];
+                normalize3(ex);
+                V3<R> ey = P[2] - P[0];
+                V3<R> ez = cross3(ex, ey);
+                normalize3(ez);
+                ey = cross3(ez, ex);
+                set_row(R02, 0, ex); set_row(R02, 1, ey); set_row(R02, 2, ez);
+            } else {
+                M3<R> A;
+                set_row(A, 0, P[1] - P[0]); set_row(A, 1, P[2] - P[0]); set_row(A, 2, P[3] - P[0]);
+                if (MODE == TM_F_SVD) {
+                    // accumulateForceSVD, :1122-1152
+                    const Quad<R> v0 = d.sv0[es], v1 = d.sv1[es], v2 = d.sv2[es], v3 = d.sv3[es], v4 = d.sv4[es];
+                    M3<R> A0i, R0t;
+                    A0i.m[0][0] = v0.a; A0i.m[0][1] = v0.b; A0i.m[0][2] = v0.c; A0i.m[1][0] = v0.d;
+                    A0i.m[1][1] = v1.a; A0i.m[1][2] = v1.b; A0i.m[2][0] = v1.c; A0i.m[2][1] = v1.d; A0i.m[2][2] = v2.a;
+                    R0t.m[0][0] = v2.b; R0t.m[0][1] = v2.c; R0t.m[0][2] = v2.d; R0t.m[1][0] = v3.a;
+                    R0t.m[1][1] = v3.b; R0t.m[1][2] = v3.c; R0t.m[2][0] = v3.d; R0t.m[2][1] = v4.a; R0t.m[2][2] = v4.b;
+                    const M3<R> Fm = mul(A, A0i);
+                    if (double(det3(Fm)) < 1e-6) {
+                        polar_decomposition_stable(Fm, R02);
+                        R02 = mul_abt(R02, R0t);  // R_0_2.multTransposed(_initialRotations[e])
+                    } else polar_decomposition(A, R02);
+                } else polar_decomposition(A, R02);  // accumulateForcePolar, :1025-1038
+            }
+            const M3<R> rot = transpose(R02);  // rotations[e] = R_0_2^T
+            d.rk0[es] = Quad<R>{rot.m[0][0], rot.m[0][1], rot.m[0][2], rot.m[1][0]};
+            d.rk1[es] = Quad<R>{rot.m[1][1], rot.m[1][2], rot.m[2][0], rot.m[2][1]};
+            d.rk2[es] = Quad<R>{rot.m[2][2], k0, k1, k2};
+            V3<R> def[4];
+#pragma unroll
+            for (int n = 0; n < 4; ++n) def[n] = mul(R02, P[n]);
+            if (MODE == TM_F_LARGE) {
+                // accumulateForceLarge, :870-905
+                def[1].x -= def[0].x;
+                def[2].x -= def[0].x;
+                def[2].y -= def[0].y;
+                def[3].x -= def[0].x; def[3].y -= def[0].y; def[3].z -= def[0].z;
+                D[0] = 0; D[1] = 0; D[2] = 0;
+                D[3] = X0[3] - def[1].x; D[4] = 0; D[5] = 0;
+                D[6] = X0[6] - def[2].x; D[7] = X0[7] - def[2].y; D[8] = 0;
+                D[9] = X0[9] - def[3].x; D[10] = X0[10] - def[3].y; D[11] = X0[11] - def[3].z;
+            } else {
+                // :1047-1058 / :1160-1171
+#pragma unroll
+                for (int n = 0; n < 4; ++n) { D[3 * n] = X0[3 * n] - def[n].x; D[3 * n + 1] = X0[3 * n + 1] - def[n].y; D[3 * n + 2] = X0[3 * n + 2] - def[n].z; }
+            }
+            tet_compute_force<R, false>(F, D, j, k0, k1, k2, R(0));
+            // f[index[i/3]] += rotations[e] * Deriv(F[i],F[i+1],F[i+2]), :928-929
+#pragma unroll
+            for (int n = 0; n < 4; ++n) C[n] = mul(rot, mk3<R>(F[3 * n], F[3 * n + 1], F[3 * n + 2]));
+        }
+    }
+}
+
+// shared-memory staging of nodal vectors: float -> float4 (one LDS.128), double -> 3 doubles
+template <class R> struct SVec;
+template <> struct SVec<float> { typedef float4 T; static __device__ __forceinline__ T make(float x, float y, float z) { return make_float4(x, y, z, 0.f); } };
+template <> struct SVec<double> { struct T { double x, y, z; }; static __device__ __forceinline__ T make(double x, double y, double z) { T t; t.x = x; t.y = y; t.z = z; return t; } };
+
+template <class R> __host__ __device__ inline size_t tet_smem_bytes(int max_touched, int max_slots) {
+    size_t a = sizeof(typename SVec<R>::T) * size_t(max_touched);
+    a = (a + 15) & ~size_t(15);
+    return a + sizeof(R) * 3 * size_t(max_slots);
+}
+
+template <class R, int MODE>
+__global__ void __launch_bounds__(256) tet_tile_kernel(TetDev<R> d, const R* __restrict__ in, NodeEpilogue<R> ep, int max_touched, int max_slots) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[32];
+    __shared__ uint16_t s_jds[1024];
+    typedef typename SVec<R>::T SV;
+    if (ep.cg && ep.cg->done) return;
+    SV* s_in = reinterpret_cast<SV*>(smem_raw);
+    size_t off = (sizeof(SV) * size_t(max_touched) + 15) & ~size_t(15);
+    R* s_slot = reinterpret_cast<R*>(smem_raw + off);  // 3 planes of max_slots
+
+    const TileDev<R>& t = d.t;
+    const int tile = blockIdx.x;
+    const uint32_t node_off = t.tile_node_off[tile];
+    const int n_touched = int(t.tile_node_off[tile + 1] - node_off);
+    const int n_int = int(t.tile_nint[tile]);
+
+    // ---- phase 1: stage input vectors of the touched nodes
+    for (int k = threadIdx.x; k < n_touched; k += blockDim.x) {
+        const uint32_t g = t.tile_nodes[node_off + k];
+        const R* p = in + 3 * size_t(g);
+        s_in[k] = SVec<R>::make(p[0], p[1], p[2]);
+    }
+    for (int j = threadIdx.x; j <= t.maxval; j += blockDim.x) s_jds[j] = t.tile_jds[size_t(tile) * (t.maxval + 1) + j];
+    __syncthreads();
+
+    // ---- phase 2: elements
+    R* stx = t.stage; R* sty = t.stage + t.stage_n; R* stz = t.stage + 2 * t.stage_n;
+    for (int le = threadIdx.x; le < t.tile_e; le += blockDim.x) {
+        const size_t es = size_t(tile) * t.tile_e + le;
+        const ushort4 ln = d.lnode[es];
+        if (ln.x == 0xFFFFu) continue;
+        const uint4 sl = d.slot[es];
+        const SV pa = s_in[ln.x], pb = s_in[ln.y], pc = s_in[ln.z], pd = s_in[ln.w];
+        const V3<R> P[4] = {mk3<R>(pa.x, pa.y, pa.z), mk3<R>(pb.x, pb.y, pb.z), mk3<R>(pc.x, pc.y, pc.z), mk3<R>(pd.x, pd.y, pd.z)};
+        V3<R> C[4];
+        tet_element<R, MODE>(d, es, P, C);
+        const unsigned s4[4] = {sl.x, sl.y, sl.z, sl.w};
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            const unsigned s = s4[n];
+            if (s & kStageFlag) {
+                const size_t p = s & ~kStageFlag;
+                __stcg(stx + p, C[n].x); __stcg(sty + p, C[n].y); __stcg(stz + p, C[n].z);
+            } else {
+                s_slot[s] = C[n].x; s_slot[max_slots + s] = C[n].y; s_slot[2 * max_slots + s] = C[n].z;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: interior nodes, sequential sum in element order
+    double part = 0.0;
+    for (int k = threadIdx.x; k < n_int; k += blockDim.x) {
+        const uint32_t g = t.tile_nodes[node_off + k];
+        const int val = t.tile_val[node_off + k];
+        R ax, ay, az;
+        node_pre(ep, g, ax, ay, az);
+        node_mass(ep, ep.pre_kind, g, ax, ay, az);
+        if (ep.sign > 0) for (int jj = 0; jj < val; ++jj) { const int s = s_jds[jj] + k; ax += s_slot[s]; ay += s_slot[max_slots + s]; az += s_slot[2 * max_slots + s]; }
+        else             for (int jj = 0; jj < val; ++jj) { const int s = s_jds[jj] + k; ax -= s_slot[s]; ay -= s_slot[max_slots + s]; az -= s_slot[2 * max_slots + s]; }
+        part += node_post(ep, g, ax, ay, az);
+    }
+    if (ep.dot_kind != DOT_NONE) {
+        const double tot = block_sum(part, red);
+        finish_dot(ep, tot, red, false);
+    }
+}
+
+// rotations[e] back in ORIGINAL element order (getRotations-style accessors, parity checks)
+template <class R> __global__ void tet_export_rotations_kernel(TetDev<R> d, const uint32_t* __restrict__ orig, R* __restrict__ out) {
+    const size_t es = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (es >= size_t(d.t.n_tiles) * d.t.tile_e) return;
+    const uint32_t e = orig[es];
+    if (e == 0xFFFFFFFFu) return;
+    const Quad<R> q0 = d.rk0[es], q1 = d.rk1[es], q2 = d.rk2[es];
+    R* o = out + 9 * size_t(e);
+    o[0] = q0.a; o[1] = q0.b; o[2] = q0.c; o[3] = q0.d; o[4] = q1.a; o[5] = q1.b; o[6] = q1.c; o[7] = q1.d; o[8] = q2.a;
+}
+
+}  // namespace sb

@@ -1,0 +1,154 @@
+// MechanicalObject vector operations and the CG vector updates (streaming kernels).
+// Vec3 operations of the reference are componentwise, so the kernels run on the flat 3n array.
+#pragma once
+#include "fem_layout.cuh"
+
+namespace sb {
+
+enum VOpKind { VOP_CLEAR = 0, VOP_SCALE, VOP_EQ_BF, VOP_COPY, VOP_PEQ, VOP_PEQ_BF, VOP_AVF, VOP_EQ_AB, VOP_EQ_ABF };
+
+constexpr int kVecBlock = 256;
+inline int vec_grid(size_t n, int sm_count) {
+    size_t b = (n + kVecBlock - 1) / kVecBlock;
+    const size_t cap = size_t(sm_count) * 8;  // a few CTAs per SM, grid-stride beyond that
+    if (b > cap) b = cap;
+    return int(b < 1 ? 1 : b);
+}
+
+// MechanicalObject.inl:1930-2072 helper forms
+template <class R, int KIND> __global__ void __launch_bounds__(kVecBlock) vop_kernel(size_t n3, R* __restrict__ r, const R* a, const R* b, R k) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n3; i += size_t(gridDim.x) * blockDim.x) {
+        if (KIND == VOP_CLEAR) r[i] = R(0);
+        else if (KIND == VOP_SCALE) r[i] *= k;                       // vOp_vf
+        else if (KIND == VOP_EQ_BF) r[i] = b[i] * k;                 // vOp_vbf
+        else if (KIND == VOP_COPY) r[i] = a[i];                      // vOp_va
+        else if (KIND == VOP_PEQ) r[i] += b[i];                      // vOp_vb
+        else if (KIND == VOP_PEQ_BF) r[i] += b[i] * k;               // vOp_v_inc_bf
+        else if (KIND == VOP_AVF) { R t = r[i]; t *= k; t += a[i]; r[i] = t; }  // vOp_avf
+        else if (KIND == VOP_EQ_AB) r[i] = a[i] + b[i];              // vOp_vab
+        else if (KIND == VOP_EQ_ABF) r[i] = a[i] + b[i] * k;         // vOp_vabf
+    }
+}
+
+// what the last CTA does with a finished dot product
+enum DotFinish { DF_STORE = 0, DF_CG_NORMB = 1, DF_CG_RHO = 2 };
+
+__device__ inline void dot_finish_action(int action, double s, double* result, CGDev* cg) {
+    if (result) *result = s;
+    if (action == DF_CG_NORMB) {
+        cg->normb = sqrt(s);
+        if (cg->normb == 0.0) { cg->done = 1; cg->nb_iter = 0; cg->end_cond = 4; }
+    } else if (action == DF_CG_RHO) cg_after_rho(cg, s);
+}
+
+template <class R> __device__ __forceinline__ void dot_epilogue(double part, double* partials, unsigned* counter, int action, double* result, CGDev* cg) {
+    __shared__ double red[32];
+    __shared__ bool is_last;
+    const double tot = block_sum(part, red);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = tot;
+        __threadfence();
+        const unsigned ticket = atomicInc(counter, gridDim.x - 1);
+        is_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double s = 0.0;
+    for (int i = threadIdx.x; i < int(gridDim.x); i += blockDim.x) s += __ldcg(partials + i);
+    __syncthreads();
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) dot_finish_action(action, s, result, cg);
+}
+
+// MechanicalObject::vDot in double with a fixed summation tree
+template <class R> __global__ void __launch_bounds__(kVecBlock) vdot_kernel(size_t n3, const R* __restrict__ a, const R* __restrict__ b, double* partials,
+                                                                             unsigned* counter, int action, double* result, CGDev* cg) {
+    if (cg && cg->done) return;
+    double part = 0.0;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n3; i += size_t(gridDim.x) * blockDim.x) part += double(a[i]) * double(b[i]);
+    dot_epilogue<R>(part, partials, counter, action, result, cg);
+}
+
+// vMultiOp integration fast path, MechanicalObject.inl:2208-2241
+template <class R> __global__ void __launch_bounds__(kVecBlock) integrate_kernel(size_t n3, R* __restrict__ v, R* __restrict__ x, const R* __restrict__ a, R f_v_a, int f_v_a_is_one, R f_x_v) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n3; i += size_t(gridDim.x) * blockDim.x) {
+        R vv = v[i];
+        if (f_v_a_is_one) vv += a[i]; else vv += a[i] * f_v_a;
+        v[i] = vv;
+        x[i] += vv * f_x_v;
+    }
+}
+
+// DiagonalMass pieces (DiagonalMass.inl:535-575,1392-1413)
+template <class R> __global__ void __launch_bounds__(kVecBlock) mass_mdx_kernel(size_t n, R* __restrict__ res, const R* __restrict__ dx, const R* __restrict__ m, R factor, int is_one) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < 3 * n; i += size_t(gridDim.x) * blockDim.x) {
+        const R mm = m[i / 3];
+        if (is_one) res[i] += dx[i] * mm; else res[i] += (dx[i] * mm) * factor;
+    }
+}
+template <class R> __global__ void __launch_bounds__(kVecBlock) mass_gravity_kernel(size_t n, R* __restrict__ f, const R* __restrict__ m, R gx, R gy, R gz) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < 3 * n; i += size_t(gridDim.x) * blockDim.x) {
+        const int c = int(i % 3);
+        const R g = c == 0 ? gx : (c == 1 ? gy : gz);
+        f[i] += g * m[i / 3];
+    }
+}
+template <class R> __global__ void __launch_bounds__(kVecBlock) mass_acc_kernel(size_t n, R* __restrict__ a, const R* __restrict__ f, const R* __restrict__ m) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < 3 * n; i += size_t(gridDim.x) * blockDim.x) a[i] = f[i] / m[i / 3];
+}
+// FixedProjectiveConstraint::projectResponse, indexed form
+template <class R> __global__ void __launch_bounds__(kVecBlock) fixed_project_kernel(size_t n_idx, const uint32_t* __restrict__ idx, R* __restrict__ res) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_idx; i += size_t(gridDim.x) * blockDim.x) {
+        const size_t g = idx[i];
+        res[3 * g] = R(0); res[3 * g + 1] = R(0); res[3 * g + 2] = R(0);
+    }
+}
+// generic per-node epilogue without element contributions (right-hand side when the stiffness term is absent)
+template <class R> __global__ void __launch_bounds__(kVecBlock) node_only_kernel(size_t n, NodeEpilogue<R> ep) {
+    for (size_t g = size_t(blockIdx.x) * blockDim.x + threadIdx.x; g < n; g += size_t(gridDim.x) * blockDim.x) {
+        R ax, ay, az;
+        node_pre(ep, uint32_t(g), ax, ay, az);
+        node_mass(ep, ep.pre_kind, uint32_t(g), ax, ay, az);
+        node_post(ep, uint32_t(g), ax, ay, az);
+    }
+}
+
+// ---- CG vector steps -------------------------------------------------------------------------------
+// p = r (first iteration) or p = p*beta + r  (cgstep_beta -> vOp_avf), CGLinearSolver.inl:184-197
+template <class R> __global__ void __launch_bounds__(kVecBlock) cg_p_update_kernel(size_t n3, R* __restrict__ p, const R* __restrict__ r, const CGDev* cg) {
+    if (cg->done) return;
+    const bool first = cg->it == 1;
+    const R beta = R(cg->rho / cg->rho_1);
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n3; i += size_t(gridDim.x) * blockDim.x) {
+        if (first) p[i] = r[i];
+        else { R t = p[i]; t *= beta; t += r[i]; p[i] = t; }
+    }
+}
+// x += p*alpha ; r += q*(-alpha)  (cgstep_alpha -> two vOp_v_inc_bf), then rho' = r.r for the next iteration
+template <class R> __global__ void __launch_bounds__(kVecBlock) cg_xr_update_kernel(size_t n3, R* __restrict__ x, R* __restrict__ r, const R* __restrict__ p, const R* __restrict__ q,
+                                                                                     CGDev* cg, double* partials, unsigned* counter) {
+    if (cg->done) return;
+    const double alpha_d = cg->alpha;
+    const R alpha = R(alpha_d), malpha = R(-alpha_d);
+    const bool a_one = (alpha_d == 1.0), ma_one = (-alpha_d == 1.0);  // vOp takes r += b when k == 1
+    double part = 0.0;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n3; i += size_t(gridDim.x) * blockDim.x) {
+        if (a_one) x[i] += p[i]; else x[i] += p[i] * alpha;
+        R rr = r[i];
+        if (ma_one) rr += q[i]; else rr += q[i] * malpha;
+        r[i] = rr;
+        part += double(rr) * double(rr);
+    }
+    dot_epilogue<R>(part, partials, counter, DF_CG_RHO, nullptr, cg);
+}
+struct CGBegin { unsigned max_iter; double tolerance, threshold; };
+__global__ void cg_begin_kernel(CGDev* cg, CGBegin b) {
+    cg->done = 0; cg->nb_iter = 0; cg->end_cond = 0; cg->it = 0;
+    cg->max_iter = b.max_iter; cg->tolerance = b.tolerance; cg->threshold = b.threshold;
+    cg->rho = 0; cg->rho_1 = 0; cg->den = 0; cg->alpha = 0; cg->normb = 0;
+    cg->n_err = 1; cg->graph_error[0] = 1.0; cg->n_den = 0;
+}
+__global__ void cg_end_kernel(CGDev* cg) { cg->time_step_count++; }
+
+}  // namespace sb

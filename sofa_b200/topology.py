@@ -1,0 +1,139 @@
+"""Init-time inputs of the path, generated host-side with numpy exactly as the reference's topology
+components produce them (ordering matters for parity: the gather sums follow element order).
+
+  RegularGridTopology   Sofa/Component/Topology/Container/Grid/src/sofa/component/topology/container/grid/
+                        RegularGridTopology.cpp:124-168, GridTopology.cpp:352-398
+  Hexa2TetraTopologicalMapping   Sofa/Component/Topology/Mapping/src/sofa/component/topology/mapping/
+                        Hexa2TetraTopologicalMapping.cpp:104-196
+  TetrahedronFEMForceField::init's own tessellation   .../fem/elastic/TetrahedronFEMForceField.inl:1317-1371
+  BoxROI                Sofa/Component/Engine/Select/src/sofa/component/engine/select/BoxROI.inl:189-201
+  DiagonalMass lumping  Sofa/Component/Mass/src/sofa/component/mass/DiagonalMass.inl:1061-1110,1218-1258
+  Gmsh v1 reader        Sofa/Component/IO/Mesh/src/sofa/component/io/mesh/MeshGmshLoader.cpp
+"""
+import numpy as np
+
+# Sofa/framework/Geometry/src/sofa/geometry/Hexahedron.h:67-88
+_X_EDGES = ((0, 1), (4, 5), (3, 2), (7, 6))
+_Y_EDGES = ((4, 7), (5, 6), (1, 2), (0, 3))
+_Z_EDGES = ((4, 0), (5, 1), (6, 2), (7, 3))
+_NON_SWAPPED = np.array([[0, 5, 1, 6], [0, 1, 3, 6], [1, 3, 6, 2], [6, 3, 0, 7], [6, 7, 0, 5], [7, 5, 4, 0]])
+_SWAPPED = np.array([[0, 5, 6, 1], [0, 1, 6, 3], [1, 3, 2, 6], [6, 3, 7, 0], [6, 7, 5, 0], [7, 5, 0, 4]])
+
+
+def regular_grid(n, mn, mx):
+    """RegularGridTopology(n, min, max) -> (positions float64 [N,3], hexahedra uint32 [H,8])."""
+    nx, ny, nz = (int(v) for v in n)
+    mn = np.asarray(mn, np.float64); mx = np.asarray(mx, np.float64)
+    p0 = mn.copy(); d = np.empty(3)
+    for c, m in enumerate((nx - 1, ny - 1, nz - 1)):
+        if m > 0:
+            d[c] = (mx[c] - mn[c]) / m
+        else:
+            d[c] = mx[c] - mn[c]
+            if c < 2:
+                p0[c] = (mx[c] + mn[c]) / 2
+    i = np.arange(nx, dtype=np.float64); j = np.arange(ny, dtype=np.float64); k = np.arange(nz, dtype=np.float64)
+    pos = np.empty((nz, ny, nx, 3), np.float64)
+    pos[..., 0] = (p0[0] + d[0] * i)[None, None, :]
+    pos[..., 1] = (p0[1] + d[1] * j)[None, :, None]
+    pos[..., 2] = (p0[2] + d[2] * k)[:, None, None]
+    pos = pos.reshape(-1, 3)
+    if min(nx, ny, nz) < 2:
+        return pos, np.zeros((0, 8), np.uint32)
+    z, y, x = np.meshgrid(np.arange(nz - 1), np.arange(ny - 1), np.arange(nx - 1), indexing="ij")
+    x = x.ravel(); y = y.ravel(); z = z.ravel()
+
+    def P(a, b, c):
+        return nx * (ny * c + b) + a
+    hexas = np.stack([P(x, y, z), P(x + 1, y, z), P(x + 1, y + 1, z), P(x, y + 1, z),
+                      P(x, y, z + 1), P(x + 1, y, z + 1), P(x + 1, y + 1, z + 1), P(x, y + 1, z + 1)], axis=1).astype(np.uint32)
+    return pos, hexas
+
+
+def hexas_to_tetras(hexas, n, mode="mapping"):
+    """6 tetrahedra per hexahedron of a grid with n=(nx,ny,nz) points.
+    mode: "mapping" (Hexa2TetraTopologicalMapping swapping=false), "mapping_swapping" (swapping=true),
+          "forcefield" (the tessellation TetrahedronFEMForceField::init builds for a hexahedral topology)."""
+    H = hexas.shape[0]
+    nx, ny = int(n[0]) - 1, int(n[1]) - 1
+    c = hexas.astype(np.uint32).copy()
+    swapped = np.zeros(H, bool)
+    if mode != "mapping":
+        i = np.arange(H)
+        for cond, edges in ((((i % nx) & 1) == 0, _X_EDGES), ((((i // nx) % ny) & 1) == 1, _Y_EDGES), (((i // (nx * ny)) & 1) == 1, _Z_EDGES)):
+            for a, b in edges:
+                tmp = c[cond, a].copy(); c[cond, a] = c[cond, b]; c[cond, b] = tmp
+            swapped ^= cond
+    tets = np.empty((H, 6, 4), np.uint32)
+    use_sw = swapped if mode == "mapping_swapping" else np.zeros(H, bool)
+    for t in range(6):
+        for k in range(4):
+            tets[:, t, k] = np.where(use_sw, c[np.arange(H), _SWAPPED[t, k]], c[np.arange(H), _NON_SWAPPED[t, k]])
+    return tets.reshape(-1, 4)
+
+
+def box_roi(positions, box):
+    b = np.asarray(box, np.float64)
+    return np.nonzero(np.all((positions >= b[:3]) & (positions <= b[3:]), axis=1))[0].astype(np.uint32)
+
+
+def _tet_volume(p, t):
+    a = p[t[:, 1]] - p[t[:, 0]]; b = p[t[:, 2]] - p[t[:, 0]]; c = p[t[:, 3]] - p[t[:, 0]]
+    cx = a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1]
+    cy = a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2]
+    cz = a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]
+    r = cx * c[:, 0]; r = r + cy * c[:, 1]; r = r + cz * c[:, 2]
+    return np.abs(r / p.dtype.type(6))
+
+
+def diagonal_mass(positions, elems, dtype, mass_density=None, total_mass=None):
+    """DiagonalMass vertexMass lumped from tetrahedra ([T,4]) or hexahedra ([H,8]) in the reference's Real arithmetic."""
+    dt = np.dtype(dtype).type
+    p = np.ascontiguousarray(positions, dtype)
+    e = np.asarray(elems, np.int64)
+    density = dt(1.0) if mass_density is None else dt(mass_density)
+    if e.shape[1] == 4:
+        vol = _tet_volume(p, e); share = dt(4.0)
+    else:
+        idx = ((0, 5, 1, 6), (0, 1, 3, 6), (1, 3, 6, 2), (6, 3, 0, 7), (6, 7, 0, 5), (7, 5, 4, 0))
+        vol = None
+        for q in idx:
+            v = _tet_volume(p, e[:, q])
+            vol = v if vol is None else vol + v
+        share = dt(8.0)
+    m_el = (density * vol) / share
+    masses = np.zeros(p.shape[0], dtype)
+    np.add.at(masses, e.ravel(), np.repeat(m_el, e.shape[1]))  # sequential, element order then corner order
+    if total_mass is not None:
+        # initFromTotalMass: density = totalMass / sum (sum accumulated in the same order, in Real)
+        flat = np.repeat(m_el, e.shape[1]).astype(dtype)
+        s = np.cumsum(flat, dtype=dtype)[-1] if flat.size else dt(0)  # cumsum == strictly sequential `total_mass += mass` in Real
+        dens = dt(1.0) if s < np.finfo(dtype).eps else dt(dt(total_mass) / s)
+        masses = masses * dens
+    return masses
+
+
+def read_gmsh_v1(path):
+    """Gmsh file format 1.0 ($NOD / $ELM) -> (positions float64 [N,3], tetrahedra uint32 [T,4], hexahedra uint32 [H,8])."""
+    with open(path) as fh:
+        tok = fh.read().split()
+    i = tok.index("$NOD") + 1
+    n = int(tok[i]); i += 1
+    ids = {}
+    pos = np.empty((n, 3), np.float64)
+    for k in range(n):
+        ids[int(tok[i])] = k
+        pos[k] = [float(tok[i + 1]), float(tok[i + 2]), float(tok[i + 3])]
+        i += 4
+    i = tok.index("$ELM") + 1
+    ne = int(tok[i]); i += 1
+    tets, hexas = [], []
+    for _ in range(ne):
+        etype, nnodes = int(tok[i + 1]), int(tok[i + 4])
+        nodes = [ids[int(v)] for v in tok[i + 5:i + 5 + nnodes]]
+        if etype == 4:
+            tets.append(nodes)
+        elif etype == 5:
+            hexas.append(nodes)
+        i += 5 + nnodes
+    return pos, np.array(tets, np.uint32).reshape(-1, 4), np.array(hexas, np.uint32).reshape(-1, 8)

@@ -170,6 +170,10 @@ class OracleScene:
     def set_v(self, v):
         self.L.orc_scene_set_v(self.h, _ptr(np.ascontiguousarray(v, self.dtype)))
 
+    def set_dot_double(self, on=True):
+        """Test knob: accumulate CG dot products in double (see Scene::dotDouble in oracle/sofa_oracle.hpp)."""
+        self.L.orc_scene_set_dot_double(self.h, int(on))
+
     def set_threads(self, n):
         self.L.orc_scene_set_threads(self.h, int(n))
 

@@ -1,0 +1,74 @@
+"""BASELINE.json config C2 at full size (33x33x161 grid, 983 040 tetrahedra): bit-exact against the oracle for the
+element passes, plus size-independent properties of the operator."""
+import numpy as np
+import pytest
+
+from gpu_common import dev, gpu_scene, oracle_scene, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c2():
+    g = gpu_scene("C2", np.float32)
+    s = oracle_scene("C2", np.float32)
+    return g, s
+
+
+def test_c2_sizes(c2):
+    g, _ = c2
+    assert g["tets"].shape[0] == 983040 and g["pos"].shape[0] == 175329 and len(g["fixed"]) == 1089
+    st = g["ff"].stats()
+    assert st["interior_nodes"] + st["shared_nodes"] == 175329
+
+
+def test_c2_force_and_dforce_bit_exact(c2):
+    g, s = c2
+    rng = np.random.default_rng(0)
+    z = g["pos"][:, 2:3]
+    x = (g["pos"] + np.hstack([0.02 * np.sin(z / 3.0), 0.05 * (z / 20.0) ** 2, 0 * z]) + 1e-3 * rng.standard_normal(g["pos"].shape)).astype(np.float32)
+    zero = np.zeros_like(x)
+    f_d = dev(g["mo"], zero); g["ff"].addForce(f_d, dev(g["mo"], x))
+    f_ref = s.fem_add_force(zero, x)
+    assert f_d.cpu().numpy().tobytes() == f_ref.tobytes()
+    dx = (1e-3 * rng.standard_normal(x.shape)).astype(np.float32)
+    df_d = dev(g["mo"], zero); g["ff"].addDForce(df_d, dev(g["mo"], dx), -0.0011)
+    assert df_d.cpu().numpy().tobytes() == s.fem_add_dforce(zero, dx, -0.0011).tobytes()
+
+
+def test_c2_operator_properties(c2):
+    g, _ = c2
+    mo, node = g["mo"], g["node"]
+    rng = np.random.default_rng(1)
+    p = dev(mo, rng.standard_normal((mo.size, 3))); q = dev(mo, rng.standard_normal((mo.size, 3)))
+    p[g["fixed"].astype(np.int64)] = 0; q[g["fixed"].astype(np.int64)] = 0
+    Ap, Aq = mo.new_vector(), mo.new_vector()
+    m, b, k = 1.001, -0.01, -0.0011
+    node.apply(Ap, p, m, b, k); node.apply(Aq, q, m, b, k)
+    # symmetry and positive definiteness of the projected system, fixed rows zero, idempotent projection, determinism
+    pAq, qAp, pAp = mo.vDot(p, Aq), mo.vDot(q, Ap), mo.vDot(p, Ap)
+    assert abs(pAq - qAp) <= 1e-4 * abs(pAp)
+    assert pAp > 0
+    assert not Ap.cpu().numpy()[g["fixed"]].any()
+    Ap2 = mo.new_vector(); node.apply(Ap2, p, m, b, k)
+    assert Ap2.cpu().numpy().tobytes() == Ap.cpu().numpy().tobytes()
+    # linearity in p (float32: to rounding)
+    pq = mo.new_vector(); mo.vOp(pq, p, q, 2.0)
+    Apq = mo.new_vector(); node.apply(Apq, pq, m, b, k)
+    lin = mo.new_vector(); mo.vOp(lin, Ap, Aq, 2.0)
+    assert rel_err(Apq.cpu().numpy(), lin.cpu().numpy()) <= 1e-5
+
+
+def test_c2_steps_match_oracle(c2):
+    """Whole EulerImplicit steps at full size.  Oracle dots accumulated in double (see test_euler_implicit_steps_match_oracle)."""
+    g, s = c2
+    s.set_dot_double(True)
+    node = g["node"]
+    for step in range(2):
+        node.step()
+        it = node.last_solve()["iterations"]
+        it_ref = s.step()
+        assert abs(it - it_ref) <= 1
+        assert rel_err(node.get("f"), s.get("f")) <= 1e-5
+        assert rel_err(node.get("dx"), s.get("sol")) <= 1e-4
+    assert np.abs(g["mo"].x.cpu().numpy().astype(np.float64) - s.get("x")).max() <= 1e-5
