@@ -63,7 +63,8 @@ typedef struct sofab200_node sofab200_node;     /* one solver node kept resident
 const char* sofab200_version(void);
 /* Text of the last error raised on the calling thread ("" when none). */
 const char* sofab200_last_error(void);
-/* device: CUDA ordinal.  cuda_stream: a cudaStream_t to enqueue on, or NULL to create an own
+/* device: CUDA ordinal.  cuda_stream: a cudaStream_t to enqueue on (pass cudaStreamLegacy / cudaStreamPerThread
+ * explicitly for the default streams), or NULL to create an own
  * non-blocking stream.  Replaces mycudaInit() (SofaCUDA/Core/src/sofa/gpu/cuda/mycuda.cu:142-155). */
 int sofab200_ctx_create(int device, void* cuda_stream, sofab200_ctx** out);
 int sofab200_ctx_destroy(sofab200_ctx* ctx);

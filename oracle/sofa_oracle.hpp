@@ -1018,11 +1018,17 @@ template <class R> struct Scene {
     // TEST KNOB (not a reference Data): accumulate the CG dot products in double instead of the reference's serial
     // Real accumulation (MechanicalObject.inl:2333-2356).  Used to separate "the dot product is summed in another
     // order / precision" (inherent to any parallel implementation) from every other source of difference.
-    bool dotDouble = false;
+    // dotReverse additionally walks the vector backwards: the same numbers summed in another order, to measure how
+    // strongly the trajectory of the reference itself depends on the (unspecified) summation order of vDot.
+    bool dotDouble = false, dotReverse = false;
     SReal sdot(const VecDeriv<R>& a, const VecDeriv<R>& b) const {
-        if (!dotDouble) return VOps<R>::dot(a, b);
+        if (!dotDouble && !dotReverse) return VOps<R>::dot(a, b);
         double r = 0.0;
-        for (size_t i = 0; i < a.size(); ++i) r += double(a[i][0]) * double(b[i][0]) + double(a[i][1]) * double(b[i][1]) + double(a[i][2]) * double(b[i][2]);
+        const size_t n = a.size();
+        for (size_t k = 0; k < n; ++k) {
+            const size_t i = dotReverse ? n - 1 - k : k;
+            r += double(a[i][0]) * double(b[i][0]) + double(a[i][1]) * double(b[i][1]) + double(a[i][2]) * double(b[i][2]);
+        }
         return r;
     }
     // outputs of the last solve

@@ -95,7 +95,7 @@ double orc_vdot(int real, size_t n, const void* a, const void* b) {
 // ---- scene ------------------------------------------------------------------------------------------------------
 void* orc_scene_create(int real) { SceneAny* s = new SceneAny(); s->real = real; return s; }
 void orc_scene_destroy(void* h) { delete static_cast<SceneAny*>(h); }
-void orc_scene_set_dot_double(void* h, int on) { DISPATCH(h, { sc.dotDouble = on != 0; }); }
+void orc_scene_set_dot_double(void* h, int on) { DISPATCH(h, { sc.dotDouble = (on & 1) != 0; sc.dotReverse = (on & 2) != 0; }); }
 void orc_scene_set_threads(void* h, int n) { DISPATCH(h, { sc.threads = n < 1 ? 1 : n; }); }
 
 // positions (also the rest positions) and velocities

@@ -46,7 +46,10 @@ class Context:
         torch.cuda.set_device(self.device)
         self.stream = stream if stream is not None else torch.cuda.current_stream(self.device)
         self.h = _P()
-        check(self.L.sofab200_ctx_create(device, C.c_void_p(self.stream.cuda_stream), C.byref(self.h)))
+        # torch's default stream is the legacy NULL stream: hand the library the explicit cudaStreamLegacy handle (0x1) so that
+        # it enqueues on the SAME stream as torch's copies instead of creating its own (a NULL handle means "create one").
+        handle = self.stream.cuda_stream or 1
+        check(self.L.sofab200_ctx_create(device, C.c_void_p(handle), C.byref(self.h)))
 
     def synchronize(self):
         check(self.L.sofab200_ctx_synchronize(self.h))

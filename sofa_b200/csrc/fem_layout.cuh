@@ -19,7 +19,7 @@
 
 namespace sb {
 
-constexpr int kGatherChunk = 256;      // shared nodes per CTA of the boundary kernel
+constexpr int kGatherChunk = 128;      // shared nodes per CTA of the boundary kernel
 constexpr unsigned kStageFlag = 0x80000000u;
 
 // epilogue selection for the per-node gather
@@ -82,37 +82,127 @@ template <class R> struct TileDev {
     const uint16_t* sh_val;
     const uint32_t* sh_jds;          // [n_chunks][maxval+1]
     const uint32_t* sh_base;         // [n_chunks]
-    R* stage;                        // 3 planes of stage_n
+    Quad<R>* stage;                  // one (x,y,z,-) quad per staged contribution: a single 16-byte store / load
     size_t stage_n;
 };
+
+// L2 residency control (sm_80+ createpolicy / cache_hint).  The staged corner contributions are written by the element
+// pass and read once by the boundary kernel a few microseconds later: they are stored evict_last so that they are still in
+// the 126 MB L2 when read (no HBM round trip), while the element records, which stream through exactly once per pass, are
+// loaded evict_first so that they do not push the staged data out.
+HD uint64_t l2_policy_evict_last() {
+    uint64_t p = 0;
+#ifdef __CUDA_ARCH__
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+#endif
+    return p;
+}
+HD uint64_t l2_policy_evict_first() {
+    uint64_t p = 0;
+#ifdef __CUDA_ARCH__
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+#endif
+    return p;
+}
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ float4 ldg_hint(const float4* a, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double2 ldg_hint(const double2* a, uint64_t pol) {
+    double2 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg_hint(const uint4* a, uint64_t pol) {
+    uint4 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint2 ldg_hint(const uint2* a, uint64_t pol) {
+    uint2 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void stg_hint(float4* a, float4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" :: "l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stg_hint(double2* a, double2 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" :: "l"(a), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+#endif
+// pol: an L2 cache policy on the device; ignored on the host (tests/emu executes the same functions on the CPU)
+HD void stage_store(Quad<float>* p, float x, float y, float z, uint64_t pol) {
+#ifdef __CUDA_ARCH__
+    stg_hint(reinterpret_cast<float4*>(p), make_float4(x, y, z, 0.f), pol);
+#else
+    (void)pol; *p = Quad<float>{x, y, z, 0.f};
+#endif
+}
+HD void stage_store(Quad<double>* p, double x, double y, double z, uint64_t pol) {
+#ifdef __CUDA_ARCH__
+    stg_hint(reinterpret_cast<double2*>(p), make_double2(x, y), pol);
+    stg_hint(reinterpret_cast<double2*>(p) + 1, make_double2(z, 0.0), pol);
+#else
+    (void)pol; *p = Quad<double>{x, y, z, 0.0};
+#endif
+}
+HD Quad<float> stage_load(const Quad<float>* p, uint64_t pol) {
+#ifdef __CUDA_ARCH__
+    const float4 v = ldg_hint(reinterpret_cast<const float4*>(p), pol);
+    return Quad<float>{v.x, v.y, v.z, v.w};
+#else
+    (void)pol; return *p;
+#endif
+}
+HD Quad<double> stage_load(const Quad<double>* p, uint64_t pol) {
+#ifdef __CUDA_ARCH__
+    const double2 a = ldg_hint(reinterpret_cast<const double2*>(p), pol), b = ldg_hint(reinterpret_cast<const double2*>(p) + 1, pol);
+    return Quad<double>{a.x, a.y, b.x, b.y};
+#else
+    (void)pol; return *p;
+#endif
+}
+// element records: streamed once per pass
+HD Quad<float> rec_load(const Quad<float>* p, uint64_t pol) { return stage_load(p, pol); }
+HD Quad<double> rec_load(const Quad<double>* p, uint64_t pol) { return stage_load(p, pol); }
 
 // acc (op)= contribution, in the reference's order; then mass/scale/projection/dot.
 template <class R> HD void node_pre(const NodeEpilogue<R>& ep, uint32_t g, R& ax, R& ay, R& az) {
     if (ep.init_src) { ax = ep.init_src[3 * size_t(g)]; ay = ep.init_src[3 * size_t(g) + 1]; az = ep.init_src[3 * size_t(g) + 2]; }
     else { ax = R(0); ay = R(0); az = R(0); }
 }
-template <class R> HD void node_mass(const NodeEpilogue<R>& ep, int kind, uint32_t g, R& ax, R& ay, R& az) {
+// (vx,vy,vz): the node's entry of mdx_src / dot_with when the caller already holds it (shared-memory copy of the input vector)
+template <class R> HD void node_mass_v(const NodeEpilogue<R>& ep, int kind, uint32_t g, R vx, R vy, R vz, R& ax, R& ay, R& az) {
     if (kind == PRE_GRAVITY) {  // DiagonalMass::addForce: f[i] += theGravity*masses[i]
         const R m = ep.mass[g];
         ax += ep.gx * m; ay += ep.gy * m; az += ep.gz * m;
     } else if (kind == PRE_MDX) {  // DiagonalMass::addMDx
         const R m = ep.mass[g];
-        const R dx = ep.mdx_src[3 * size_t(g)], dy = ep.mdx_src[3 * size_t(g) + 1], dz = ep.mdx_src[3 * size_t(g) + 2];
-        if (ep.mass_factor_is_one) { ax += dx * m; ay += dy * m; az += dz * m; }
-        else { ax += (dx * m) * ep.mass_factor; ay += (dy * m) * ep.mass_factor; az += (dz * m) * ep.mass_factor; }
+        if (ep.mass_factor_is_one) { ax += vx * m; ay += vy * m; az += vz * m; }
+        else { ax += (vx * m) * ep.mass_factor; ay += (vy * m) * ep.mass_factor; az += (vz * m) * ep.mass_factor; }
     }
 }
+template <class R> HD void node_mass(const NodeEpilogue<R>& ep, int kind, uint32_t g, R& ax, R& ay, R& az) {
+    R vx = 0, vy = 0, vz = 0;
+    if (kind == PRE_MDX) { vx = ep.mdx_src[3 * size_t(g)]; vy = ep.mdx_src[3 * size_t(g) + 1]; vz = ep.mdx_src[3 * size_t(g) + 2]; }
+    node_mass_v(ep, kind, g, vx, vy, vz, ax, ay, az);
+}
 // returns this node's contribution to the dot product
-template <class R> HD double node_post(const NodeEpilogue<R>& ep, uint32_t g, R ax, R ay, R az) {
-    node_mass(ep, ep.post_kind, g, ax, ay, az);
+template <class R> HD double node_post_v(const NodeEpilogue<R>& ep, uint32_t g, R vx, R vy, R vz, R ax, R ay, R az) {
+    node_mass_v(ep, ep.post_kind, g, vx, vy, vz, ax, ay, az);
     if (ep.has_scale) { ax *= ep.scale; ay *= ep.scale; az *= ep.scale; }
     if (ep.fixed && ep.fixed[g]) { ax = R(0); ay = R(0); az = R(0); }
     ep.out[3 * size_t(g)] = ax; ep.out[3 * size_t(g) + 1] = ay; ep.out[3 * size_t(g) + 2] = az;
-    if (ep.dot_kind != DOT_NONE) {
-        const R* w = ep.dot_with + 3 * size_t(g);
-        return double(ax) * double(w[0]) + double(ay) * double(w[1]) + double(az) * double(w[2]);
-    }
+    if (ep.dot_kind != DOT_NONE) return double(ax) * double(vx) + double(ay) * double(vy) + double(az) * double(vz);
     return 0.0;
+}
+template <class R> HD double node_post(const NodeEpilogue<R>& ep, uint32_t g, R ax, R ay, R az) {
+    R vx = 0, vy = 0, vz = 0;
+    const R* src = ep.dot_kind != DOT_NONE ? ep.dot_with : (ep.post_kind == PRE_MDX ? ep.mdx_src : nullptr);
+    if (src) { vx = src[3 * size_t(g)]; vy = src[3 * size_t(g) + 1]; vz = src[3 * size_t(g) + 2]; }
+    return node_post_v(ep, g, vx, vy, vz, ax, ay, az);
 }
 
 // block-wide sum in a fixed order: warp shuffles, then warp 0 over the per-warp partials
@@ -185,22 +275,45 @@ template <class R> __device__ __forceinline__ void finish_dot(const NodeEpilogue
 }
 
 // ---- boundary kernel: sums the HBM-staged contributions of the shared nodes -------------------------------
+// One thread per node.  The node's contributions are fetched in batches of kGatherBatch independent 16-byte loads, two
+// batches ahead of the one being consumed, and added ONE BY ONE IN ELEMENT ORDER.  The chunk's jagged-diagonal table
+// sits in shared memory so that the only dependent global loads are node id -> contributions.
+constexpr int kGatherBatch = 8;
 template <class R> __global__ void __launch_bounds__(kGatherChunk) gather_shared_kernel(TileDev<R> d, NodeEpilogue<R> ep) {
     __shared__ double red[32];
+    __shared__ uint32_t s_jds[1024 + 3 * kGatherBatch];
     if (ep.cg && ep.cg->done) return;
     const int chunk = blockIdx.x, k = threadIdx.x;
+    for (int j = k; j <= d.maxval + 3 * kGatherBatch - 1; j += blockDim.x) s_jds[j] = j <= d.maxval ? d.sh_jds[size_t(chunk) * (d.maxval + 1) + j] : 0u;
     const uint32_t g = d.sh_nodes[size_t(chunk) * kGatherChunk + k];
+    const int val = g != 0xFFFFFFFFu ? int(d.sh_val[size_t(chunk) * kGatherChunk + k]) : 0;
+    const Quad<R>* st = d.stage + d.sh_base[chunk] + k;
+    const uint64_t pol = l2_policy_evict_first();
+    __syncthreads();
     double part = 0.0;
     if (g != 0xFFFFFFFFu) {
-        const int val = d.sh_val[size_t(chunk) * kGatherChunk + k];
-        const uint32_t* jds = d.sh_jds + size_t(chunk) * (d.maxval + 1);
-        const size_t base = d.sh_base[chunk];
-        const R* sx = d.stage; const R* sy = d.stage + d.stage_n; const R* sz = d.stage + 2 * d.stage_n;
+        const Quad<R> zero{R(0), R(0), R(0), R(0)};
+        Quad<R> b0[kGatherBatch], b1[kGatherBatch], b2[kGatherBatch];
+#pragma unroll
+        for (int u = 0; u < kGatherBatch; ++u) b0[u] = (u < val) ? stage_load(st + s_jds[u], pol) : zero;
+#pragma unroll
+        for (int u = 0; u < kGatherBatch; ++u) b1[u] = (kGatherBatch + u < val) ? stage_load(st + s_jds[kGatherBatch + u], pol) : zero;
         R ax, ay, az;
         node_pre(ep, g, ax, ay, az);
         node_mass(ep, ep.pre_kind, g, ax, ay, az);
-        if (ep.sign > 0) for (int j = 0; j < val; ++j) { const size_t p = base + jds[j] + k; ax += __ldcg(sx + p); ay += __ldcg(sy + p); az += __ldcg(sz + p); }
-        else             for (int j = 0; j < val; ++j) { const size_t p = base + jds[j] + k; ax -= __ldcg(sx + p); ay -= __ldcg(sy + p); az -= __ldcg(sz + p); }
+        const bool plus = ep.sign > 0;
+        for (int j0 = 0; j0 < val; j0 += kGatherBatch) {
+#pragma unroll
+            for (int u = 0; u < kGatherBatch; ++u) { const int j = j0 + 2 * kGatherBatch + u; b2[u] = (j < val) ? stage_load(st + s_jds[j], pol) : zero; }
+#pragma unroll
+            for (int u = 0; u < kGatherBatch; ++u) {
+                if (j0 + u < val) {
+                    if (plus) { ax += b0[u].a; ay += b0[u].b; az += b0[u].c; } else { ax -= b0[u].a; ay -= b0[u].b; az -= b0[u].c; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kGatherBatch; ++u) { b0[u] = b1[u]; b1[u] = b2[u]; }
+        }
         part = node_post(ep, g, ax, ay, az);
     }
     if (ep.dot_kind != DOT_NONE) {

@@ -1,6 +1,7 @@
 // Host-side construction of the tile / gather plan (init-time; see fem_layout.cuh for the layout).
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <numeric>
 #include <string>
@@ -48,18 +49,24 @@ inline std::string build_plan(HostPlan& P, int n_nodes, int n_elems, int npe, co
     for (size_t i = 0; i < size_t(n_elems) * npe; ++i)
         if (elems[i] >= uint32_t(n_nodes)) return "element refers to a node index out of range";
 
-    // ---- spatial order of the elements (Morton code of the rest centroid)
+    // ---- spatial order of the elements: Morton code of the integer cell that holds the rest centroid.  The cell size is
+    // the edge of the average hexahedron-equivalent element, so that on a regular grid the 6 tetrahedra of one cube share
+    // a cell and power-of-8 tiles are exact cubes of cells (minimal tile surface => fewest shared nodes).
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     for (int i = 0; i < n_nodes; ++i) for (int c = 0; c < 3; ++c) { lo[c] = std::min(lo[c], pos[3 * size_t(i) + c]); hi[c] = std::max(hi[c], pos[3 * size_t(i) + c]); }
-    double ext = 0; for (int c = 0; c < 3; ++c) ext = std::max(ext, hi[c] - lo[c]);
+    double ext = 0, vol = 1; int flat = 0;
+    for (int c = 0; c < 3; ++c) { const double e = hi[c] - lo[c]; ext = std::max(ext, e); if (e > 0) vol *= e; else flat++; }
     if (!(ext > 0)) ext = 1;
+    const double cells = std::max(1.0, npe == 4 ? n_elems / 6.0 : double(n_elems));
+    double h = flat == 0 ? std::cbrt(vol / cells) : (flat == 1 ? std::sqrt(vol / cells) : (flat == 2 ? vol / cells : 1.0));
+    if (!(h > 0) || ext / h > 2000000.0) h = ext / 2000000.0;
     std::vector<uint64_t> key(n_elems);
     for (int e = 0; e < n_elems; ++e) {
         uint64_t k = 0;
         for (int c = 0; c < 3; ++c) {
             double s = 0; for (int a = 0; a < npe; ++a) s += pos[3 * size_t(elems[size_t(e) * npe + a]) + c];
-            double u = (s / npe - lo[c]) / ext; u = std::min(std::max(u, 0.0), 1.0);
-            k |= morton_spread(uint64_t(u * 2097151.0)) << c;
+            double u = std::floor((s / npe - lo[c]) / h); u = std::min(std::max(u, 0.0), 2097151.0);
+            k |= morton_spread(uint64_t(u)) << c;
         }
         key[e] = k;
     }

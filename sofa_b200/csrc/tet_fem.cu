@@ -21,8 +21,10 @@ template <class R> struct TetFF : sofab200_tetfem {
     DevBuf<Quad<R>> rk0, rk1, rk2, j0, j1, j2, x0a, x0b, x0c, sv0, sv1, sv2, sv3, sv4;
     DevBuf<uint32_t> tile_node_off, tile_nodes, tile_nint, sh_nodes, sh_jds, sh_base;
     DevBuf<uint16_t> tile_val, tile_jds, sh_val;
-    DevBuf<R> stage;
+    DevBuf<Quad<R>> stage;
     DevBuf<R> rot_export;
+    int threads = 256;   // CTA size of the addDForce tile kernel
+    bool prefetch = true;
     TetDev<R> dev() {
         const HostPlan& plan = h.plan;
         TetDev<R> d;
@@ -53,7 +55,7 @@ template <class R> static int tet_upload(TetFF<R>& ff) {
     SB_TRY(ff.tile_node_off.upload(P.tile_node_off, s)); SB_TRY(ff.tile_nodes.upload(P.tile_nodes, s)); SB_TRY(ff.tile_nint.upload(P.tile_nint, s));
     SB_TRY(ff.tile_val.upload(P.tile_val, s)); SB_TRY(ff.tile_jds.upload(P.tile_jds, s));
     SB_TRY(ff.sh_nodes.upload(P.sh_nodes, s)); SB_TRY(ff.sh_val.upload(P.sh_val, s)); SB_TRY(ff.sh_jds.upload(P.sh_jds, s)); SB_TRY(ff.sh_base.upload(P.sh_base, s));
-    SB_TRY(ff.stage.alloc(3 * P.stage_n)); SB_TRY(ff.stage.zero(s));
+    SB_TRY(ff.stage.alloc(P.stage_n)); SB_TRY(ff.stage.zero(s));
     SB_CUDA(cudaStreamSynchronize(s));
     // the tile-ordered host planes are no longer needed once they are resident in HBM
     for (auto* v : {&H.rk0, &H.rk1, &H.rk2, &H.j0, &H.j1, &H.j2, &H.x0a, &H.x0b, &H.x0c}) { v->clear(); v->shrink_to_fit(); }
@@ -62,8 +64,8 @@ template <class R> static int tet_upload(TetFF<R>& ff) {
     return SOFAB200_OK;
 }
 
-template <class R, int MODE> static int tet_launch_mode(TetFF<R>& ff, const TetDev<R>& d, const R* in, const NodeEpilogue<R>& ep) {
-    auto kern = tet_tile_kernel<R, MODE>;
+template <class R, int MODE, int MAXT, bool PF> static int tet_launch_variant(TetFF<R>& ff, const TetDev<R>& d, const R* in, const NodeEpilogue<R>& ep) {
+    auto kern = tet_tile_kernel<R, MODE, MAXT, PF>;
     static thread_local size_t configured = 0;
     if (ff.h.smem_bytes > 48 * 1024 && configured < ff.h.smem_bytes) {
         SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ff.h.smem_bytes)));
@@ -71,17 +73,26 @@ template <class R, int MODE> static int tet_launch_mode(TetFF<R>& ff, const TetD
     }
     const int cls = (MODE == TM_DF_COROT || MODE == TM_DF_SMALL) ? 0 : 2;
     ff.ctx->prof_start(cls);
-    kern<<<ff.h.plan.n_tiles, 256, ff.h.smem_bytes, ff.ctx->stream>>>(d, in, ep, ff.h.plan.max_touched, ff.h.plan.max_slots);
+    kern<<<ff.h.plan.n_tiles, (MODE == TM_DF_COROT && sizeof(R) == 4) ? ff.threads : 256, ff.h.smem_bytes, ff.ctx->stream>>>(d, in, ep, ff.h.plan.max_touched, ff.h.plan.max_slots);
     ff.ctx->prof_stop(cls);
     ff.ctx->launches++;
     SB_CUDA(cudaGetLastError());
     return SOFAB200_OK;
+}
+template <class R, int MODE> static int tet_launch_mode(TetFF<R>& ff, const TetDev<R>& d, const R* in, const NodeEpilogue<R>& ep) {
+    // the addForce passes run once per step: one conservative variant; the addDForce pass (26x per step) is tuned
+    if (MODE != TM_DF_COROT) return tet_launch_variant<R, MODE, 256, false>(ff, d, in, ep);
+    if (sizeof(R) == 8) return tet_launch_variant<R, MODE, 256, false>(ff, d, in, ep);
+    if (ff.threads > 512) return tet_launch_variant<R, MODE, 1024, false>(ff, d, in, ep);
+    if (ff.threads > 256) return ff.prefetch ? tet_launch_variant<R, MODE, 512, true>(ff, d, in, ep) : tet_launch_variant<R, MODE, 512, false>(ff, d, in, ep);
+    return ff.prefetch ? tet_launch_variant<R, MODE, 256, true>(ff, d, in, ep) : tet_launch_variant<R, MODE, 256, false>(ff, d, in, ep);
 }
 
 // Element pass + boundary gather with a caller-provided epilogue (also used by the solver node).
 template <class R> int tet_run(sofab200_tetfem* base, bool dforce, const R* in, R k_factor, NodeEpilogue<R> ep) {
     TetFF<R>& ff = *static_cast<TetFF<R>*>(base);
     const HostPlan& plan = ff.h.plan;
+    SB_CHECK((!ep.mdx_src || ep.mdx_src == in) && (!ep.dot_with || ep.dot_with == in), "mass / dot operands must be the pass's input vector");
     TetDev<R> d = ff.dev();
     d.k_factor = k_factor;
     ep.partial_base = 0;
@@ -120,8 +131,11 @@ template <class R> static int tet_create(sofab200_ctx* ctx, size_t n_nodes, cons
     std::unique_ptr<TetFF<R>> ff(new TetFF<R>());
     ff->ctx = ctx; ff->real = sizeof(R) == 4 ? SOFAB200_F32 : SOFAB200_F64; ff->method = desc->method;
     ff->n_nodes = n_nodes; ff->n_tets = n_tets;
-    const std::string err = tet_host_build(ff->h, n_nodes, static_cast<const R*>(rest), n_tets, tets, desc, kGatherChunk);
+    const std::string err = tet_host_build(ff->h, n_nodes, static_cast<const R*>(rest), n_tets, tets, desc, kGatherChunk, ctx->sm_count);
     if (!err.empty()) return fail(SOFAB200_ERR_INVALID, err);
+    ff->threads = (ff->h.plan.tile_e >= 2048 && sizeof(R) == 4) ? 512 : 256;
+    if (const char* env = getenv("SOFAB200_TILE_THREADS")) { const int v = atoi(env); if (v >= 64 && v <= 1024 && v % 32 == 0) ff->threads = v; }
+    if (const char* env = getenv("SOFAB200_PREFETCH")) ff->prefetch = atoi(env) != 0;
     SB_TRY(tet_upload(*ff));
     *out = ff.release();
     return SOFAB200_OK;

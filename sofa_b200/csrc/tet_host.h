@@ -134,19 +134,35 @@ template <class R> static void tet_fill_planes(HostTet<R>& ff) {
 
 // init()+reinit()+layout.  Returns "" or an error text.
 template <class R> static std::string tet_host_build(HostTet<R>& ff, size_t n_nodes, const R* x0, size_t n_tets, const uint32_t* tets,
-                                                     const sofab200_tetfem_desc* desc, int chunk) {
+                                                     const sofab200_tetfem_desc* desc, int chunk, int sm_count = 148) {
     ff.method = desc->method; ff.n_nodes = n_nodes; ff.n_tets = n_tets;
     for (size_t i = 0; i < 4 * n_tets; ++i) if (tets[i] >= n_nodes) return "tetrahedron refers to a node index out of range";
     tet_init_elements(ff, x0, tets, desc);
     std::vector<double> pos(3 * n_nodes);
     for (size_t i = 0; i < 3 * n_nodes; ++i) pos[i] = double(x0[i]);
-    int tile_e = desc->tile_elems > 0 ? desc->tile_elems : 1024;
+    // Tile size.  One CTA streams one tile, so the number of tiles should be a whole multiple of the CTAs the GPU holds at
+    // once (no partial last wave), and a tile must fit in shared memory.  Default: the largest tile <= 3584 (Vec3f) / 1536
+    // (Vec3d) elements that cuts the mesh into k * sm_count equal parts.  desc->tile_elems or SOFAB200_TILE_ELEMS override.
+    const bool fixed_tile = desc->tile_elems > 0 || getenv("SOFAB200_TILE_ELEMS");
+    int tile_e = desc->tile_elems;
     if (const char* env = getenv("SOFAB200_TILE_ELEMS")) { const int v = atoi(env); if (v > 0) tile_e = v; }
-    tile_e = (tile_e + 255) / 256 * 256;
-    const std::string err = build_plan(ff.plan, int(n_nodes), int(n_tets), 4, tets, pos.data(), tile_e, chunk, kStageFlag);
-    if (!err.empty()) return err;
-    ff.smem_bytes = tet_smem_bytes<R>(ff.plan.max_touched, ff.plan.max_slots);
-    if (ff.smem_bytes > 200 * 1024) return "tile does not fit in shared memory; use a smaller tile_elems";
+    const int cap = sizeof(R) == 4 ? 3584 : 1536;
+    int k_waves = std::max<int>(1, int((n_tets + size_t(sm_count) * cap - 1) / (size_t(sm_count) * cap)));
+    if (tile_e <= 0) tile_e = int((n_tets + size_t(sm_count) * k_waves - 1) / (size_t(sm_count) * k_waves));
+    tile_e = std::max(32, (tile_e + 31) / 32 * 32);
+    for (;;) {
+        const std::string err = build_plan(ff.plan, int(n_nodes), int(n_tets), 4, tets, pos.data(), tile_e, chunk, kStageFlag);
+        ff.smem_bytes = tet_smem_bytes<R>(ff.plan.max_touched, ff.plan.max_slots);
+        const bool too_big = ff.smem_bytes > 200 * 1024 || err.find("use a smaller tile") != std::string::npos;
+        if (too_big && !fixed_tile && tile_e > 32) {
+            ++k_waves;
+            tile_e = std::max(32, (int((n_tets + size_t(sm_count) * k_waves - 1) / (size_t(sm_count) * k_waves)) + 31) / 32 * 32);
+            continue;
+        }
+        if (!err.empty()) return err;
+        if (too_big) return "tile does not fit in shared memory; use a smaller tile_elems";
+        break;
+    }
     tet_fill_planes(ff);
     return "";
 }

@@ -16,7 +16,7 @@ enum TetMode { TM_DF_COROT = 0, TM_DF_SMALL = 1, TM_F_SMALL = 2, TM_F_LARGE = 3,
 
 template <class R> struct TetDev {
     TileDev<R> t;
-    const ushort4* lnode;      // [n_tiles*tile_e] local node index of the 4 corners (0xFFFF = padding element)
+    const ushort4* lnode;      // [n_tiles*tile_e] local node index of the 4 corners (0xFFFF = padding element); read as one 64-bit word
     const uint4* slot;         // destination slot of each corner's contribution
     Quad<R>* rk0; Quad<R>* rk1; Quad<R>* rk2;            // rotations[e] (9, row-major) + {K00, K01, K33}
     const Quad<R>* j0; const Quad<R>* j1; const Quad<R>* j2;     // 12 strain-displacement cofactors
@@ -52,9 +52,30 @@ template <class R, bool USE_FACT> HD void tet_compute_force(R F[12], const R D[1
 // One element: inputs are the 4 nodal vectors P (positions for addForce, dx for addDForce); outputs the 4 corner
 // contributions C in the form the reference adds (addForce) or subtracts (addDForce) them.  addForce modes also
 // store rotations[e].  Host-callable so that tests/emu can execute the very same statements on the CPU.
-template <class R, int MODE> HD void tet_element(const TetDev<R>& d, size_t es, const V3<R> P[4], V3<R> C[4]) {
-    const Quad<R> q0 = d.rk0[es], q1 = d.rk1[es], q2 = d.rk2[es];
-    const Quad<R> ja = d.j0[es], jb = d.j1[es], jc = d.j2[es];
+template <class R> struct TetRec { Quad<R> q0, q1, q2, ja, jb, jc; };   // rotations[e]+K and the 12 cofactors of one element
+template <class R> HD TetRec<R> tet_load_rec(const TetDev<R>& d, size_t es, uint64_t pol = 0) {
+    TetRec<R> r;
+    r.q0 = rec_load(d.rk0 + es, pol); r.q1 = rec_load(d.rk1 + es, pol); r.q2 = rec_load(d.rk2 + es, pol);
+    r.ja = rec_load(d.j0 + es, pol); r.jb = rec_load(d.j1 + es, pol); r.jc = rec_load(d.j2 + es, pol);
+    return r;
+}
+HD uint2 idx_load(const uint2* p, uint64_t pol) {
+#ifdef __CUDA_ARCH__
+    return ldg_hint(p, pol);
+#else
+    (void)pol; return *p;
+#endif
+}
+HD uint4 idx_load(const uint4* p, uint64_t pol) {
+#ifdef __CUDA_ARCH__
+    return ldg_hint(p, pol);
+#else
+    (void)pol; return *p;
+#endif
+}
+template <class R, int MODE> HD void tet_element(const TetDev<R>& d, size_t es, const TetRec<R>& rec, const V3<R> P[4], V3<R> C[4]) {
+    const Quad<R> q0 = rec.q0, q1 = rec.q1, q2 = rec.q2;
+    const Quad<R> ja = rec.ja, jb = rec.jb, jc = rec.jc;
     const R j[12] = {ja.a, ja.b, ja.c, ja.d, jb.a, jb.b, jb.c, jb.d, jc.a, jc.b, jc.c, jc.d};
     const R k0 = q2.b, k1 = q2.c, k2 = q2.d;
     R F[12];
@@ -169,8 +190,9 @@ template <class R> __host__ __device__ inline size_t tet_smem_bytes(int max_touc
     return a + sizeof(R) * 3 * size_t(max_slots);
 }
 
-template <class R, int MODE>
-__global__ void __launch_bounds__(256) tet_tile_kernel(TetDev<R> d, const R* __restrict__ in, NodeEpilogue<R> ep, int max_touched, int max_slots) {
+// MAXT: CTA size the kernel is compiled for (register budget 65536/MAXT); PF: software-prefetch the next element record
+template <class R, int MODE, int MAXT, bool PF>
+__global__ void __launch_bounds__(MAXT) tet_tile_kernel(TetDev<R> d, const R* __restrict__ in, NodeEpilogue<R> ep, int max_touched, int max_slots) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[32];
     __shared__ uint16_t s_jds[1024];
@@ -196,26 +218,46 @@ __global__ void __launch_bounds__(256) tet_tile_kernel(TetDev<R> d, const R* __r
     __syncthreads();
 
     // ---- phase 2: elements
-    R* stx = t.stage; R* sty = t.stage + t.stage_n; R* stz = t.stage + 2 * t.stage_n;
-    for (int le = threadIdx.x; le < t.tile_e; le += blockDim.x) {
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    // Software pipeline: the record of the thread's NEXT element is requested before the current one is processed,
+    // so one element's worth of HBM latency is always overlapped with ~500 instructions of arithmetic.
+    int le = threadIdx.x;
+    uint2 lnw = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); uint4 sl = make_uint4(0, 0, 0, 0);
+    TetRec<R> rec;
+    if (le < t.tile_e) {
         const size_t es = size_t(tile) * t.tile_e + le;
-        const ushort4 ln = d.lnode[es];
-        if (ln.x == 0xFFFFu) continue;
-        const uint4 sl = d.slot[es];
-        const SV pa = s_in[ln.x], pb = s_in[ln.y], pc = s_in[ln.z], pd = s_in[ln.w];
-        const V3<R> P[4] = {mk3<R>(pa.x, pa.y, pa.z), mk3<R>(pb.x, pb.y, pb.z), mk3<R>(pc.x, pc.y, pc.z), mk3<R>(pd.x, pd.y, pd.z)};
-        V3<R> C[4];
-        tet_element<R, MODE>(d, es, P, C);
-        const unsigned s4[4] = {sl.x, sl.y, sl.z, sl.w};
+        lnw = idx_load(reinterpret_cast<const uint2*>(d.lnode + es), pol_stream); sl = idx_load(d.slot + es, pol_stream); rec = tet_load_rec(d, es, pol_stream);
+    }
+    while (le < t.tile_e) {
+        const size_t es = size_t(tile) * t.tile_e + le;
+        const int nle = le + blockDim.x;
+        uint2 n_lnw = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); uint4 n_sl = make_uint4(0, 0, 0, 0);
+        TetRec<R> n_rec;
+        if (PF && nle < t.tile_e) {
+            const size_t nes = size_t(tile) * t.tile_e + nle;
+            n_lnw = idx_load(reinterpret_cast<const uint2*>(d.lnode + nes), pol_stream); n_sl = idx_load(d.slot + nes, pol_stream); n_rec = tet_load_rec(d, nes, pol_stream);
+        }
+        if ((lnw.x & 0xFFFFu) != 0xFFFFu) {
+            const SV pa = s_in[lnw.x & 0xFFFFu], pb = s_in[lnw.x >> 16], pc = s_in[lnw.y & 0xFFFFu], pd = s_in[lnw.y >> 16];
+            const V3<R> P[4] = {mk3<R>(pa.x, pa.y, pa.z), mk3<R>(pb.x, pb.y, pb.z), mk3<R>(pc.x, pc.y, pc.z), mk3<R>(pd.x, pd.y, pd.z)};
+            V3<R> C[4];
+            tet_element<R, MODE>(d, es, rec, P, C);
+            const unsigned s4[4] = {sl.x, sl.y, sl.z, sl.w};
 #pragma unroll
-        for (int n = 0; n < 4; ++n) {
-            const unsigned s = s4[n];
-            if (s & kStageFlag) {
-                const size_t p = s & ~kStageFlag;
-                __stcg(stx + p, C[n].x); __stcg(sty + p, C[n].y); __stcg(stz + p, C[n].z);
-            } else {
-                s_slot[s] = C[n].x; s_slot[max_slots + s] = C[n].y; s_slot[2 * max_slots + s] = C[n].z;
+            for (int n = 0; n < 4; ++n) {
+                const unsigned s = s4[n];
+                if (s & kStageFlag) {
+                    stage_store(t.stage + (s & ~kStageFlag), C[n].x, C[n].y, C[n].z, pol_keep);
+                } else {
+                    s_slot[s] = C[n].x; s_slot[max_slots + s] = C[n].y; s_slot[2 * max_slots + s] = C[n].z;
+                }
             }
+        }
+        le = nle;
+        if (PF) { lnw = n_lnw; sl = n_sl; rec = n_rec; }
+        else if (le < t.tile_e) {
+            const size_t nes = size_t(tile) * t.tile_e + le;
+            lnw = idx_load(reinterpret_cast<const uint2*>(d.lnode + nes), pol_stream); sl = idx_load(d.slot + nes, pol_stream); rec = tet_load_rec(d, nes, pol_stream);
         }
     }
     __syncthreads();
@@ -225,12 +267,15 @@ __global__ void __launch_bounds__(256) tet_tile_kernel(TetDev<R> d, const R* __r
     for (int k = threadIdx.x; k < n_int; k += blockDim.x) {
         const uint32_t g = t.tile_nodes[node_off + k];
         const int val = t.tile_val[node_off + k];
+        // mdx_src / dot_with are the kernel's own input vector whenever they are used (A*p: both are p), so the
+        // shared-memory copy staged in phase 1 serves them
+        const SV pv = s_in[k];
         R ax, ay, az;
         node_pre(ep, g, ax, ay, az);
-        node_mass(ep, ep.pre_kind, g, ax, ay, az);
+        node_mass_v(ep, ep.pre_kind, g, R(pv.x), R(pv.y), R(pv.z), ax, ay, az);
         if (ep.sign > 0) for (int jj = 0; jj < val; ++jj) { const int s = s_jds[jj] + k; ax += s_slot[s]; ay += s_slot[max_slots + s]; az += s_slot[2 * max_slots + s]; }
         else             for (int jj = 0; jj < val; ++jj) { const int s = s_jds[jj] + k; ax -= s_slot[s]; ay -= s_slot[max_slots + s]; az -= s_slot[2 * max_slots + s]; }
-        part += node_post(ep, g, ax, ay, az);
+        part += node_post_v(ep, g, R(pv.x), R(pv.y), R(pv.z), ax, ay, az);
     }
     if (ep.dot_kind != DOT_NONE) {
         const double tot = block_sum(part, red);

@@ -11,7 +11,7 @@ using namespace sb;
 namespace {
 template <class R> struct Emu {
     HostTet<R> h;
-    std::vector<R> stage;
+    std::vector<Quad<R>> stage;
     TetDev<R> dev() {
         const HostPlan& P = h.plan;
         TetDev<R> d{};
@@ -36,7 +36,6 @@ template <class R, int MODE> double run_mode(Emu<R>& E, const R* in, R kf, NodeE
     double dot = 0.0;
     std::vector<V3<R>> s_in(P.max_touched);
     std::vector<R> s_slot(3 * size_t(P.max_slots));
-    R* stx = t.stage; R* sty = t.stage + t.stage_n; R* stz = t.stage + 2 * t.stage_n;
     for (int tile = 0; tile < t.n_tiles; ++tile) {
         const uint32_t node_off = t.tile_node_off[tile];
         const int n_touched = int(t.tile_node_off[tile + 1] - node_off), n_int = int(t.tile_nint[tile]);
@@ -50,11 +49,11 @@ template <class R, int MODE> double run_mode(Emu<R>& E, const R* in, R kf, NodeE
             const uint4 sl = d.slot[es];
             const V3<R> Pn[4] = {s_in[ln.x], s_in[ln.y], s_in[ln.z], s_in[ln.w]};
             V3<R> C[4];
-            tet_element<R, MODE>(d, es, Pn, C);
+            tet_element<R, MODE>(d, es, tet_load_rec(d, es), Pn, C);
             const unsigned s4[4] = {sl.x, sl.y, sl.z, sl.w};
             for (int n = 0; n < 4; ++n) {
                 const unsigned s = s4[n];
-                if (s & kStageFlag) { const size_t p = s & ~kStageFlag; stx[p] = C[n].x; sty[p] = C[n].y; stz[p] = C[n].z; }
+                if (s & kStageFlag) stage_store(t.stage + (s & ~kStageFlag), C[n].x, C[n].y, C[n].z, 0);
                 else { s_slot[s] = C[n].x; s_slot[P.max_slots + s] = C[n].y; s_slot[2 * size_t(P.max_slots) + s] = C[n].z; }
             }
         }
@@ -83,8 +82,8 @@ template <class R, int MODE> double run_mode(Emu<R>& E, const R* in, R kf, NodeE
             node_pre(ep, g, ax, ay, az);
             node_mass(ep, ep.pre_kind, g, ax, ay, az);
             for (int j = 0; j < val; ++j) {
-                const size_t p = base + jds[j] + k;
-                if (ep.sign > 0) { ax += stx[p]; ay += sty[p]; az += stz[p]; } else { ax -= stx[p]; ay -= sty[p]; az -= stz[p]; }
+                const Quad<R> v = stage_load(t.stage + (base + jds[j] + k), 0);
+                if (ep.sign > 0) { ax += v.a; ay += v.b; az += v.c; } else { ax -= v.a; ay -= v.b; az -= v.c; }
             }
             dot += node_post(ep, g, ax, ay, az);
         }
@@ -115,8 +114,8 @@ void* emu_tet_create(int real, size_t n_nodes, const void* rest, size_t n_tets, 
                      size_t np, const double* poisson, int tile_e) {
     EmuAny* e = new EmuAny(); e->real = real;
     sofab200_tetfem_desc d{}; d.method = method; d.n_young = ny; d.young = young; d.n_poisson = np; d.poisson = poisson; d.tile_elems = tile_e;
-    if (real == 0) { e->err = tet_host_build(e->f.h, n_nodes, (const float*)rest, n_tets, tets, &d, kGatherChunk); e->f.stage.assign(3 * e->f.h.plan.stage_n, 777.f); }
-    else { e->err = tet_host_build(e->d.h, n_nodes, (const double*)rest, n_tets, tets, &d, kGatherChunk); e->d.stage.assign(3 * e->d.h.plan.stage_n, 777.0); }
+    if (real == 0) { e->err = tet_host_build(e->f.h, n_nodes, (const float*)rest, n_tets, tets, &d, kGatherChunk); e->f.stage.assign(e->f.h.plan.stage_n, Quad<float>{777.f, 777.f, 777.f, 0.f}); }
+    else { e->err = tet_host_build(e->d.h, n_nodes, (const double*)rest, n_tets, tets, &d, kGatherChunk); e->d.stage.assign(e->d.h.plan.stage_n, Quad<double>{777.0, 777.0, 777.0, 0.0}); }
     return e;
 }
 const char* emu_tet_error(void* h) { return static_cast<EmuAny*>(h)->err.c_str(); }

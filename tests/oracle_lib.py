@@ -170,9 +170,9 @@ class OracleScene:
     def set_v(self, v):
         self.L.orc_scene_set_v(self.h, _ptr(np.ascontiguousarray(v, self.dtype)))
 
-    def set_dot_double(self, on=True):
-        """Test knob: accumulate CG dot products in double (see Scene::dotDouble in oracle/sofa_oracle.hpp)."""
-        self.L.orc_scene_set_dot_double(self.h, int(on))
+    def set_dot_double(self, on=True, reverse=False):
+        """Test knobs: accumulate CG dot products in double / in reverse order (Scene::dotDouble, dotReverse)."""
+        self.L.orc_scene_set_dot_double(self.h, int(bool(on)) | (2 if reverse else 0))
 
     def set_threads(self, n):
         self.L.orc_scene_set_threads(self.h, int(n))

