@@ -69,6 +69,7 @@ struct sofab200_ctx {
     bool own_stream = false;
     int sm_count = 148;
     uint64_t launches = 0;
+    cudaStream_t capture_stream = nullptr;   // stream captures run here (the legacy default stream cannot be captured)
     // optional per-class event timing (sofab200_ctx_profile_begin/end)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[SOFAB200_PROFILE_CLASSES];

@@ -44,6 +44,7 @@ int sofab200_ctx_destroy(sofab200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->capture_stream) cudaStreamDestroy(ctx->capture_stream);
     delete ctx;
     return SOFAB200_OK;
 }

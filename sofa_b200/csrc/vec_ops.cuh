@@ -115,30 +115,61 @@ template <class R> __global__ void __launch_bounds__(kVecBlock) node_only_kernel
 }
 
 // ---- CG vector steps -------------------------------------------------------------------------------
+// 16-byte vector accesses on the flat 3n array (cudaMalloc'ed vectors are 256-byte aligned); the last n3 % 4 scalars
+// are handled by the first threads of CTA 0.
+template <class R> struct Vec4T;
+template <> struct Vec4T<float> { typedef float4 T; static constexpr int N = 4; };
+template <> struct Vec4T<double> { typedef double2 T; static constexpr int N = 2; };
+__device__ __forceinline__ void v4_avf(float4& p, const float4& r, float b) { p.x *= b; p.x += r.x; p.y *= b; p.y += r.y; p.z *= b; p.z += r.z; p.w *= b; p.w += r.w; }
+__device__ __forceinline__ void v4_avf(double2& p, const double2& r, double b) { p.x *= b; p.x += r.x; p.y *= b; p.y += r.y; }
+
 // p = r (first iteration) or p = p*beta + r  (cgstep_beta -> vOp_avf), CGLinearSolver.inl:184-197
 template <class R> __global__ void __launch_bounds__(kVecBlock) cg_p_update_kernel(size_t n3, R* __restrict__ p, const R* __restrict__ r, const CGDev* cg) {
     if (cg->done) return;
+    typedef typename Vec4T<R>::T V;
+    constexpr int N = Vec4T<R>::N;
     const bool first = cg->it == 1;
     const R beta = R(cg->rho / cg->rho_1);
-    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n3; i += size_t(gridDim.x) * blockDim.x) {
+    const size_t nv = n3 / N, stride = size_t(gridDim.x) * blockDim.x, t0 = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    V* pv = reinterpret_cast<V*>(p); const V* rv = reinterpret_cast<const V*>(r);
+    for (size_t i = t0; i < nv; i += stride) {
+        if (first) pv[i] = rv[i];
+        else { V a = pv[i]; v4_avf(a, rv[i], beta); pv[i] = a; }
+    }
+    for (size_t i = nv * N + t0; i < n3; i += stride) {
         if (first) p[i] = r[i];
         else { R t = p[i]; t *= beta; t += r[i]; p[i] = t; }
     }
 }
 // x += p*alpha ; r += q*(-alpha)  (cgstep_alpha -> two vOp_v_inc_bf), then rho' = r.r for the next iteration
+template <class R> __device__ __forceinline__ double xr_one(R& x, R& r, R p, R q, R alpha, R malpha, bool a_one, bool ma_one) {
+    if (a_one) x += p; else x += p * alpha;      // vOp takes `r += b` when k == 1
+    if (ma_one) r += q; else r += q * malpha;
+    return double(r) * double(r);
+}
 template <class R> __global__ void __launch_bounds__(kVecBlock) cg_xr_update_kernel(size_t n3, R* __restrict__ x, R* __restrict__ r, const R* __restrict__ p, const R* __restrict__ q,
                                                                                      CGDev* cg, double* partials, unsigned* counter) {
     if (cg->done) return;
     const double alpha_d = cg->alpha;
     const R alpha = R(alpha_d), malpha = R(-alpha_d);
-    const bool a_one = (alpha_d == 1.0), ma_one = (-alpha_d == 1.0);  // vOp takes r += b when k == 1
+    const bool a_one = (alpha_d == 1.0), ma_one = (-alpha_d == 1.0);
+    const size_t stride = size_t(gridDim.x) * blockDim.x, t0 = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     double part = 0.0;
-    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n3; i += size_t(gridDim.x) * blockDim.x) {
-        if (a_one) x[i] += p[i]; else x[i] += p[i] * alpha;
-        R rr = r[i];
-        if (ma_one) rr += q[i]; else rr += q[i] * malpha;
-        r[i] = rr;
-        part += double(rr) * double(rr);
+    if (sizeof(R) == 4) {
+        const size_t nv = n3 / 4;
+        float4* xv = reinterpret_cast<float4*>(x); float4* rv = reinterpret_cast<float4*>(r);
+        const float4* pv = reinterpret_cast<const float4*>(p); const float4* qv = reinterpret_cast<const float4*>(q);
+        for (size_t i = t0; i < nv; i += stride) {
+            float4 xx = xv[i], rr = rv[i]; const float4 pp = pv[i], qq = qv[i];
+            part += xr_one<float>(xx.x, rr.x, pp.x, qq.x, alpha, malpha, a_one, ma_one);
+            part += xr_one<float>(xx.y, rr.y, pp.y, qq.y, alpha, malpha, a_one, ma_one);
+            part += xr_one<float>(xx.z, rr.z, pp.z, qq.z, alpha, malpha, a_one, ma_one);
+            part += xr_one<float>(xx.w, rr.w, pp.w, qq.w, alpha, malpha, a_one, ma_one);
+            xv[i] = xx; rv[i] = rr;
+        }
+        for (size_t i = nv * 4 + t0; i < n3; i += stride) part += xr_one<R>(x[i], r[i], p[i], q[i], alpha, malpha, a_one, ma_one);
+    } else {
+        for (size_t i = t0; i < n3; i += stride) part += xr_one<R>(x[i], r[i], p[i], q[i], alpha, malpha, a_one, ma_one);
     }
     dot_epilogue<R>(part, partials, counter, DF_CG_RHO, nullptr, cg);
 }
