@@ -192,7 +192,7 @@ class HexahedronFEMForceField:
     def stats(self):
         out = (C.c_uint64 * 8)()
         check(self.ctx.L.sofab200_hexfem_stats(self.h, out))
-        return dict(zip(["tiles", "tile_elems", "interior_nodes", "shared_nodes", "staged_corners", "smem_bytes", "max_valence", "n_elems"], list(out)))
+        return dict(zip(["tiles", "tile_elems", "interior_nodes", "shared_nodes", "staged_corners", "smem_bytes", "unique_stiffness_matrices", "n_elems"], list(out)))
 
     def __del__(self):
         try:

@@ -164,6 +164,21 @@ HD Quad<double> stage_load(const Quad<double>* p, uint64_t pol) {
     (void)pol; return *p;
 #endif
 }
+// index words of the element records
+HD uint2 idx_load(const uint2* p, uint64_t pol) {
+#ifdef __CUDA_ARCH__
+    return ldg_hint(p, pol);
+#else
+    (void)pol; return *p;
+#endif
+}
+HD uint4 idx_load(const uint4* p, uint64_t pol) {
+#ifdef __CUDA_ARCH__
+    return ldg_hint(p, pol);
+#else
+    (void)pol; return *p;
+#endif
+}
 // element records: streamed once per pass
 HD Quad<float> rec_load(const Quad<float>* p, uint64_t pol) { return stage_load(p, pol); }
 HD Quad<double> rec_load(const Quad<double>* p, uint64_t pol) { return stage_load(p, pol); }
@@ -272,6 +287,56 @@ template <class R> __device__ __forceinline__ void finish_dot(const NodeEpilogue
         if (ep.dot_result) *ep.dot_result = s;
         if (ep.dot_kind == DOT_CG_DEN) cg_after_den(ep.cg, s);
     }
+}
+
+// ---- pieces of the tile kernels shared by the tetra and hexa force fields -------------------------------------------
+// shared-memory staging of nodal vectors: float -> float4 (one LDS.128), double -> 3 doubles
+template <class R> struct SVec;
+template <> struct SVec<float> { typedef float4 T; static __device__ __forceinline__ T make(float x, float y, float z) { return make_float4(x, y, z, 0.f); } };
+template <> struct SVec<double> { struct T { double x, y, z; }; static __device__ __forceinline__ T make(double x, double y, double z) { T t; t.x = x; t.y = y; t.z = z; return t; } };
+
+template <class R> __host__ __device__ inline size_t tile_smem_bytes(int max_touched, int max_slots) {
+    size_t a = sizeof(typename SVec<R>::T) * size_t(max_touched);
+    a = (a + 15) & ~size_t(15);
+    return a + sizeof(R) * 3 * size_t(max_slots);
+}
+// phase 1: stage the input vector of the tile's touched nodes (and the tile's jagged-diagonal table) in shared memory
+template <class R> __device__ __forceinline__ void tile_phase1(const TileDev<R>& t, int tile, const R* __restrict__ in, typename SVec<R>::T* s_in, uint16_t* s_jds) {
+    const uint32_t node_off = t.tile_node_off[tile];
+    const int n_touched = int(t.tile_node_off[tile + 1] - node_off);
+    for (int k = threadIdx.x; k < n_touched; k += blockDim.x) {
+        const uint32_t g = t.tile_nodes[node_off + k];
+        const R* p = in + 3 * size_t(g);
+        s_in[k] = SVec<R>::make(p[0], p[1], p[2]);
+    }
+    for (int j = threadIdx.x; j <= t.maxval; j += blockDim.x) s_jds[j] = t.tile_jds[size_t(tile) * (t.maxval + 1) + j];
+    __syncthreads();
+}
+// phase 2 tail: one corner contribution to its slot (shared memory for interior nodes, L2-resident HBM stage for shared ones)
+template <class R> __device__ __forceinline__ void tile_scatter(const TileDev<R>& t, unsigned s, R cx, R cy, R cz, R* s_slot, int max_slots, uint64_t pol_keep) {
+    if (s & kStageFlag) stage_store(t.stage + (s & ~kStageFlag), cx, cy, cz, pol_keep);
+    else { s_slot[s] = cx; s_slot[max_slots + s] = cy; s_slot[2 * max_slots + s] = cz; }
+}
+// phase 3: interior nodes, sequential sum in element order + fused epilogue; returns the thread's share of the dot product.
+// mdx_src / dot_with are the kernel's own input vector whenever they are used (A*p: both are p), so the shared-memory
+// copy staged in phase 1 serves them.
+template <class R> __device__ __forceinline__ double tile_phase3(const TileDev<R>& t, int tile, const NodeEpilogue<R>& ep, const typename SVec<R>::T* s_in,
+                                                                 const R* s_slot, int max_slots, const uint16_t* s_jds) {
+    const uint32_t node_off = t.tile_node_off[tile];
+    const int n_int = int(t.tile_nint[tile]);
+    double part = 0.0;
+    for (int k = threadIdx.x; k < n_int; k += blockDim.x) {
+        const uint32_t g = t.tile_nodes[node_off + k];
+        const int val = t.tile_val[node_off + k];
+        const typename SVec<R>::T pv = s_in[k];
+        R ax, ay, az;
+        node_pre(ep, g, ax, ay, az);
+        node_mass_v(ep, ep.pre_kind, g, R(pv.x), R(pv.y), R(pv.z), ax, ay, az);
+        if (ep.sign > 0) for (int jj = 0; jj < val; ++jj) { const int s = s_jds[jj] + k; ax += s_slot[s]; ay += s_slot[max_slots + s]; az += s_slot[2 * max_slots + s]; }
+        else             for (int jj = 0; jj < val; ++jj) { const int s = s_jds[jj] + k; ax -= s_slot[s]; ay -= s_slot[max_slots + s]; az -= s_slot[2 * max_slots + s]; }
+        part += node_post_v(ep, g, R(pv.x), R(pv.y), R(pv.z), ax, ay, az);
+    }
+    return part;
 }
 
 // ---- boundary kernel: sums the HBM-staged contributions of the shared nodes -------------------------------

@@ -1,20 +1,188 @@
-// HexahedronFEMForceField<B200Vec3Types> (placeholder until the hexa kernels land)
-#include "fem_layout.cuh"
+// HexahedronFEMForceField<B200Vec3Types>: device upload + launches + C ABI.
+#include <cstring>
+#include <memory>
+
+#include "hex_host.h"
+
 using namespace sb;
-struct sofab200_hexfem { int real; size_t n_nodes; };
+
+struct sofab200_hexfem {
+    virtual ~sofab200_hexfem() {}
+    sofab200_ctx* ctx = nullptr;
+    int real = 0, method = 0;
+    size_t n_nodes = 0, n_hexas = 0;
+};
+
 namespace sb {
-template <class R> int hex_run(sofab200_hexfem*, bool, const R*, R, NodeEpilogue<R>) { return fail(SOFAB200_ERR_UNSUPPORTED, "hexa not built"); }
+
+template <class R> struct HexFF : sofab200_hexfem {
+    HostHex<R> h;
+    DevBuf<uint4> lnode, slot_a, slot_b;
+    DevBuf<uint32_t> orig, kidx, tile_kuniq;
+    DevBuf<Quad<R>> r0, r1, r2, x0;
+    DevBuf<R> ktab;
+    DevBuf<uint32_t> tile_node_off, tile_nodes, tile_nint, sh_nodes, sh_jds, sh_base;
+    DevBuf<uint16_t> tile_val, tile_jds, sh_val;
+    DevBuf<Quad<R>> stage;
+    DevBuf<R> rot_export;
+    size_t n_unique = 0;
+    HexDev<R> dev() {
+        const HostPlan& plan = h.plan;
+        HexDev<R> d;
+        d.t.n_nodes = int(n_nodes); d.t.n_elems = int(n_hexas); d.t.n_tiles = plan.n_tiles; d.t.tile_e = plan.tile_e; d.t.maxval = plan.maxval;
+        d.t.tile_node_off = tile_node_off.p; d.t.tile_nodes = tile_nodes.p; d.t.tile_nint = tile_nint.p; d.t.tile_val = tile_val.p; d.t.tile_jds = tile_jds.p;
+        d.t.n_shared = plan.n_shared; d.t.n_chunks = plan.n_chunks; d.t.sh_nodes = sh_nodes.p; d.t.sh_val = sh_val.p; d.t.sh_jds = sh_jds.p; d.t.sh_base = sh_base.p;
+        d.t.stage = stage.p; d.t.stage_n = plan.stage_n;
+        d.lnode = lnode.p; d.slot_a = slot_a.p; d.slot_b = slot_b.p; d.r0 = r0.p; d.r1 = r1.p; d.r2 = r2.p;
+        d.kidx = kidx.p; d.ktab = ktab.p; d.tile_kuniq = tile_kuniq.p; d.x0 = x0.p; d.n_slots = size_t(plan.n_tiles) * plan.tile_e;
+        d.k_factor = R(0);
+        return d;
+    }
+};
+
+template <class R> static int hex_upload(HexFF<R>& ff) {
+    HostHex<R>& H = ff.h;
+    const HostPlan& P = H.plan;
+    cudaStream_t s = ff.ctx->stream;
+    SB_TRY(ff.lnode.upload(H.lnode, s)); SB_TRY(ff.slot_a.upload(H.slot_a, s)); SB_TRY(ff.slot_b.upload(H.slot_b, s)); SB_TRY(ff.orig.upload(P.order, s));
+    SB_TRY(ff.r0.upload(H.r0, s)); SB_TRY(ff.r1.upload(H.r1, s)); SB_TRY(ff.r2.upload(H.r2, s)); SB_TRY(ff.x0.upload(H.x0, s));
+    SB_TRY(ff.kidx.upload(H.kidx, s)); SB_TRY(ff.tile_kuniq.upload(H.tile_kuniq, s)); SB_TRY(ff.ktab.upload(H.ktab, s));
+    SB_TRY(ff.tile_node_off.upload(P.tile_node_off, s)); SB_TRY(ff.tile_nodes.upload(P.tile_nodes, s)); SB_TRY(ff.tile_nint.upload(P.tile_nint, s));
+    SB_TRY(ff.tile_val.upload(P.tile_val, s)); SB_TRY(ff.tile_jds.upload(P.tile_jds, s));
+    SB_TRY(ff.sh_nodes.upload(P.sh_nodes, s)); SB_TRY(ff.sh_val.upload(P.sh_val, s)); SB_TRY(ff.sh_jds.upload(P.sh_jds, s)); SB_TRY(ff.sh_base.upload(P.sh_base, s));
+    SB_TRY(ff.stage.alloc(P.stage_n)); SB_TRY(ff.stage.zero(s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    ff.n_unique = H.ktab.size() / 576;
+    for (auto* v : {&H.r0, &H.r1, &H.r2, &H.x0}) { v->clear(); v->shrink_to_fit(); }
+    H.lnode.clear(); H.slot_a.clear(); H.slot_b.clear(); H.kidx.clear();
+    return SOFAB200_OK;
+}
+
+template <class R, int MODE> static int hex_launch_mode(HexFF<R>& ff, const HexDev<R>& d, const R* in, const NodeEpilogue<R>& ep) {
+    auto kern = hex_tile_kernel<R, MODE>;
+    static thread_local size_t configured = 0;
+    if (ff.h.smem_bytes > 48 * 1024 && configured < ff.h.smem_bytes) {
+        SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ff.h.smem_bytes)));
+        configured = ff.h.smem_bytes;
+    }
+    const int cls = MODE == HM_DF ? 0 : 2;
+    ff.ctx->prof_start(cls);
+    kern<<<ff.h.plan.n_tiles, 256, ff.h.smem_bytes, ff.ctx->stream>>>(d, in, ep, ff.h.plan.max_touched, ff.h.plan.max_slots);
+    ff.ctx->prof_stop(cls);
+    ff.ctx->launches++;
+    SB_CUDA(cudaGetLastError());
+    return SOFAB200_OK;
+}
+
+template <class R> int hex_run(sofab200_hexfem* base, bool dforce, const R* in, R k_factor, NodeEpilogue<R> ep) {
+    HexFF<R>& ff = *static_cast<HexFF<R>*>(base);
+    const HostPlan& plan = ff.h.plan;
+    SB_CHECK((!ep.mdx_src || ep.mdx_src == in) && (!ep.dot_with || ep.dot_with == in), "mass / dot operands must be the pass's input vector");
+    HexDev<R> d = ff.dev();
+    d.k_factor = k_factor;
+    ep.partial_base = 0;
+    ep.partial_total = plan.n_tiles + plan.n_chunks;
+    if (dforce) SB_TRY((hex_launch_mode<R, HM_DF>(ff, d, in, ep)));
+    else if (ff.method == SOFAB200_HEX_SMALL) SB_TRY((hex_launch_mode<R, HM_F_SMALL>(ff, d, in, ep)));
+    else if (ff.method == SOFAB200_HEX_LARGE) SB_TRY((hex_launch_mode<R, HM_F_LARGE>(ff, d, in, ep)));
+    else SB_TRY((hex_launch_mode<R, HM_F_POLAR>(ff, d, in, ep)));
+    ep.partial_base = plan.n_tiles;
+    ff.ctx->prof_start(1);
+    gather_shared_kernel<R><<<plan.n_chunks, kGatherChunk, 0, ff.ctx->stream>>>(d.t, ep);
+    ff.ctx->prof_stop(1);
+    ff.ctx->launches++;
+    SB_CUDA(cudaGetLastError());
+    return SOFAB200_OK;
+}
 template int hex_run<float>(sofab200_hexfem*, bool, const float*, float, NodeEpilogue<float>);
 template int hex_run<double>(sofab200_hexfem*, bool, const double*, double, NodeEpilogue<double>);
-int hex_partial_count(sofab200_hexfem*) { return 0; }
+
 int hex_real(sofab200_hexfem* ff) { return ff->real; }
 size_t hex_nodes(sofab200_hexfem* ff) { return ff->n_nodes; }
+int hex_partial_count(sofab200_hexfem* base) {
+    if (base->real == SOFAB200_F32) { auto& ff = *static_cast<HexFF<float>*>(base); return ff.h.plan.n_tiles + ff.h.plan.n_chunks; }
+    auto& ff = *static_cast<HexFF<double>*>(base); return ff.h.plan.n_tiles + ff.h.plan.n_chunks;
 }
+
+template <class R> static int hex_create(sofab200_ctx* ctx, size_t n_nodes, const void* rest, size_t n_hexas, const uint32_t* hexas,
+                                         const sofab200_hexfem_desc* desc, sofab200_hexfem** out) {
+    std::unique_ptr<HexFF<R>> ff(new HexFF<R>());
+    ff->ctx = ctx; ff->real = sizeof(R) == 4 ? SOFAB200_F32 : SOFAB200_F64; ff->method = desc->method;
+    ff->n_nodes = n_nodes; ff->n_hexas = n_hexas;
+    const std::string err = hex_host_build(ff->h, n_nodes, static_cast<const R*>(rest), n_hexas, hexas, desc, kGatherChunk, ctx->sm_count);
+    if (!err.empty()) return fail(SOFAB200_ERR_INVALID, err);
+    SB_TRY(hex_upload(*ff));
+    *out = ff.release();
+    return SOFAB200_OK;
+}
+
+template <class R> static int hex_get(HexFF<R>& ff, const std::string& what, void* out) {
+    if (what == "rotatedInitialElements") { std::memcpy(out, ff.h.h_X0.data(), ff.h.h_X0.size() * sizeof(R)); return SOFAB200_OK; }
+    if (what == "elementStiffnesses") {
+        R* o = static_cast<R*>(out);
+        for (size_t e = 0; e < ff.n_hexas; ++e) std::memcpy(o + 576 * e, ff.h.ktab.data() + 576 * size_t(ff.h.h_kidx[e]), 576 * sizeof(R));
+        return SOFAB200_OK;
+    }
+    if (what == "rotations") {
+        SB_TRY(ff.rot_export.alloc(9 * ff.n_hexas));
+        const HexDev<R> d = ff.dev();
+        hex_export_rotations_kernel<R><<<unsigned((d.n_slots + 255) / 256), 256, 0, ff.ctx->stream>>>(d, ff.orig.p, ff.rot_export.p);
+        ff.ctx->launches++;
+        SB_CUDA(cudaGetLastError());
+        SB_CUDA(cudaMemcpyAsync(out, ff.rot_export.p, 9 * ff.n_hexas * sizeof(R), cudaMemcpyDeviceToHost, ff.ctx->stream));
+        SB_CUDA(cudaStreamSynchronize(ff.ctx->stream));
+        return SOFAB200_OK;
+    }
+    return fail(SOFAB200_ERR_INVALID, "unknown array name: " + what);
+}
+
+}  // namespace sb
+
 extern "C" {
-int sofab200_hexfem_create(sofab200_ctx*, sofab200_real, size_t, const void*, size_t, const uint32_t*, const sofab200_hexfem_desc*, sofab200_hexfem**) { return fail(SOFAB200_ERR_UNSUPPORTED, "hexa not built"); }
-int sofab200_hexfem_destroy(sofab200_hexfem*) { return SOFAB200_OK; }
-int sofab200_hexfem_add_force(sofab200_hexfem*, void*, const void*) { return fail(SOFAB200_ERR_UNSUPPORTED, "hexa not built"); }
-int sofab200_hexfem_add_dforce(sofab200_hexfem*, void*, const void*, double) { return fail(SOFAB200_ERR_UNSUPPORTED, "hexa not built"); }
-int sofab200_hexfem_get(sofab200_hexfem*, const char*, void*) { return fail(SOFAB200_ERR_UNSUPPORTED, "hexa not built"); }
-int sofab200_hexfem_stats(const sofab200_hexfem*, uint64_t*) { return fail(SOFAB200_ERR_UNSUPPORTED, "hexa not built"); }
+
+int sofab200_hexfem_create(sofab200_ctx* ctx, sofab200_real real, size_t n_nodes, const void* rest_position_host, size_t n_hexas,
+                           const uint32_t* hexas_host, const sofab200_hexfem_desc* desc, sofab200_hexfem** out) {
+    SB_CHECK(ctx && out && desc && rest_position_host && (hexas_host || n_hexas == 0), "null argument");
+    SB_CHECK(desc->method >= 0 && desc->method <= 2, "method must be large, polar or small");
+    SB_CHECK(desc->n_young > 0 && desc->young && desc->n_poisson > 0 && desc->poisson, "youngModulus / poissonRatio are required");
+    SB_CHECK(n_nodes < 0xFFFFFFFFull && n_hexas < 0x1FFFFFFFull, "mesh too large for 32-bit indices");
+    SB_CUDA(cudaSetDevice(ctx->device));
+    if (real == SOFAB200_F32) return hex_create<float>(ctx, n_nodes, rest_position_host, n_hexas, hexas_host, desc, out);
+    return hex_create<double>(ctx, n_nodes, rest_position_host, n_hexas, hexas_host, desc, out);
 }
+int sofab200_hexfem_destroy(sofab200_hexfem* ff) { delete ff; return SOFAB200_OK; }
+int sofab200_hexfem_add_force(sofab200_hexfem* ff, void* f_dev, const void* x_dev) {
+    SB_CHECK(ff && f_dev && x_dev, "null argument");
+    if (ff->real == SOFAB200_F32) {
+        NodeEpilogue<float> ep{}; ep.init_src = static_cast<float*>(f_dev); ep.out = static_cast<float*>(f_dev); ep.sign = +1;
+        return hex_run<float>(ff, false, static_cast<const float*>(x_dev), 0.f, ep);
+    }
+    NodeEpilogue<double> ep{}; ep.init_src = static_cast<double*>(f_dev); ep.out = static_cast<double*>(f_dev); ep.sign = +1;
+    return hex_run<double>(ff, false, static_cast<const double*>(x_dev), 0.0, ep);
+}
+int sofab200_hexfem_add_dforce(sofab200_hexfem* ff, void* df_dev, const void* dx_dev, double k_factor) {
+    SB_CHECK(ff && df_dev && dx_dev, "null argument");
+    SB_CHECK(df_dev != dx_dev, "df and dx must be distinct vectors");
+    if (ff->real == SOFAB200_F32) {
+        NodeEpilogue<float> ep{}; ep.init_src = static_cast<float*>(df_dev); ep.out = static_cast<float*>(df_dev); ep.sign = -1;
+        return hex_run<float>(ff, true, static_cast<const float*>(dx_dev), float(k_factor), ep);
+    }
+    NodeEpilogue<double> ep{}; ep.init_src = static_cast<double*>(df_dev); ep.out = static_cast<double*>(df_dev); ep.sign = -1;
+    return hex_run<double>(ff, true, static_cast<const double*>(dx_dev), k_factor, ep);
+}
+int sofab200_hexfem_get(sofab200_hexfem* ff, const char* what, void* out_host) {
+    SB_CHECK(ff && what && out_host, "null argument");
+    if (ff->real == SOFAB200_F32) return hex_get(*static_cast<HexFF<float>*>(ff), what, out_host);
+    return hex_get(*static_cast<HexFF<double>*>(ff), what, out_host);
+}
+int sofab200_hexfem_stats(const sofab200_hexfem* ff, uint64_t out[8]) {
+    SB_CHECK(ff && out, "null argument");
+    const HostPlan* P; size_t smem, uniq;
+    if (ff->real == SOFAB200_F32) { auto* f = static_cast<const HexFF<float>*>(ff); P = &f->h.plan; smem = f->h.smem_bytes; uniq = f->n_unique; }
+    else { auto* f = static_cast<const HexFF<double>*>(ff); P = &f->h.plan; smem = f->h.smem_bytes; uniq = f->n_unique; }
+    out[0] = P->n_tiles; out[1] = P->tile_e; out[2] = P->n_interior; out[3] = P->n_shared; out[4] = P->n_staged_corners;
+    out[5] = smem; out[6] = uniq; out[7] = ff->n_hexas;
+    return SOFAB200_OK;
+}
+
+}  // extern "C"

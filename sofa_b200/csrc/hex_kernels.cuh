@@ -1,0 +1,164 @@
+// HexahedronFEMForceField on the device (same tile / gather structure as the tetra force field).
+//   addForce  : HexahedronFEMForceField.inl:194-246  (accumulateForceSmall :740-786, Large :836-884, Polar :1027-1076)
+//   addDForce : HexahedronFEMForceField.inl:248-286
+// The element stiffness K_e (24x24) is a per-element Data of the reference (`stiffnessMatrices`).  Matrices that are
+// bit-identical (all elements of a grid whose spacing is exactly representable) are stored once: the element record keeps
+// an index into a table of unique matrices, and a CTA whose tile refers to few matrices serves them from shared memory.
+#pragma once
+#include "fem_layout.cuh"
+#include "math3.cuh"
+
+namespace sb {
+
+enum HexMode { HM_DF = 0, HM_F_SMALL = 1, HM_F_LARGE = 2, HM_F_POLAR = 3 };
+constexpr int kHexSmemMatrices = 4;   // unique K_e cached per CTA in shared memory
+
+template <class R> struct HexDev {
+    TileDev<R> t;
+    const uint4* lnode;            // 8 x u16 local node ids (0xFFFF first = padding element)
+    const uint4* slot_a; const uint4* slot_b;   // 8 contribution destinations
+    Quad<R>* r0; Quad<R>* r1; Quad<R>* r2;      // _rotations[e] (9, row-major; R, not transposed) ; r2.d unused
+    const uint32_t* kidx;          // index of the element's K_e in ktab
+    const R* ktab;                 // [n_unique][576] row-major
+    const uint32_t* tile_kuniq;    // [n_tiles][kHexSmemMatrices+1]: count (0 = too many: read K_e from global) then indices
+    const Quad<R>* x0;             // 6 planes of n_slots: _rotatedInitialElements (24 Reals)
+    size_t n_slots;
+    R k_factor;
+};
+
+// F = K*Depl : Mat<24,24>*Vec<24>, row by row, left to right (HexahedronFEMForceField.inl:711-715, Mat.h:577-587)
+template <class R> HD void hex_matvec(R F[24], const R* __restrict__ K, const R D[24]) {
+#pragma unroll
+    for (int i = 0; i < 24; ++i) {
+        const R* row = K + 24 * i;
+        R s = row[0] * D[0];
+#pragma unroll
+        for (int j = 1; j < 24; ++j) s += row[j] * D[j];
+        F[i] = s;
+    }
+}
+
+// mean edges of the 8 nodes (HexahedronFEMForceField.inl:797-801, 920-931)
+template <class R> HD void hex_mean_edges(const V3<R> n[8], V3<R>& ex, V3<R>& ey, V3<R>& ez) {
+    ex = (n[1] - n[0] + n[2] - n[3] + n[5] - n[4] + n[6] - n[7]) * R(.25);
+    ey = (n[3] - n[0] + n[2] - n[1] + n[7] - n[4] + n[6] - n[5]) * R(.25);
+    ez = (n[4] - n[0] + n[5] - n[1] + n[7] - n[3] + n[6] - n[2]) * R(.25);
+}
+// computeRotationLarge :816-834 / computeRotationPolar :918-943
+template <class R> HD void hex_rotation(M3<R>& r, const V3<R> n[8], bool polar) {
+    V3<R> ex, ey, ez;
+    hex_mean_edges(n, ex, ey, ez);
+    if (!polar) {
+        normalize3(ex);
+        V3<R> z = cross3(ex, ey);
+        normalize3(z);
+        ey = cross3(z, ex);
+        set_row(r, 0, ex); set_row(r, 1, ey); set_row(r, 2, z);
+    } else {
+        M3<R> A;
+        set_row(A, 0, ex); set_row(A, 1, ey); set_row(A, 2, ez);
+        polar_decomposition(A, r);
+    }
+}
+
+// One element.  P: the 8 nodal vectors (positions or dx); C: the 8 corner contributions as the reference adds/subtracts them.
+template <class R, int MODE> HD void hex_element(const HexDev<R>& d, size_t es, const R* __restrict__ K, const V3<R> P[8], V3<R> C[8]) {
+    R D[24], F[24];
+    if (MODE == HM_DF) {
+        const Quad<R> q0 = d.r0[es], q1 = d.r1[es], q2 = d.r2[es];
+        M3<R> rot;
+        rot.m[0][0] = q0.a; rot.m[0][1] = q0.b; rot.m[0][2] = q0.c; rot.m[1][0] = q0.d; rot.m[1][1] = q1.a; rot.m[1][2] = q1.b;
+        rot.m[2][0] = q1.c; rot.m[2][1] = q1.d; rot.m[2][2] = q2.a;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const V3<R> x2 = mul(rot, P[w]); D[3 * w] = x2.x; D[3 * w + 1] = x2.y; D[3 * w + 2] = x2.z; }
+        hex_matvec(F, K, D);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) C[w] = mul_t(rot, mk3<R>(F[3 * w], F[3 * w + 1], F[3 * w + 2])) * d.k_factor;   // _rotations[i].multTranspose(F_w) * kFactor
+    } else {
+        R X0[24];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) { const Quad<R> v = d.x0[size_t(q) * d.n_slots + es]; X0[4 * q] = v.a; X0[4 * q + 1] = v.b; X0[4 * q + 2] = v.c; X0[4 * q + 3] = v.d; }
+        if (MODE == HM_F_SMALL) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { D[3 * w] = X0[3 * w] - P[w].x; D[3 * w + 1] = X0[3 * w + 1] - P[w].y; D[3 * w + 2] = X0[3 * w + 2] - P[w].z; }
+            hex_matvec(F, K, D);
+#pragma unroll
+            for (int w = 0; w < 8; ++w) C[w] = mk3<R>(F[3 * w], F[3 * w + 1], F[3 * w + 2]);
+        } else {
+            M3<R> rot;
+            hex_rotation(rot, P, MODE == HM_F_POLAR);
+            d.r0[es] = Quad<R>{rot.m[0][0], rot.m[0][1], rot.m[0][2], rot.m[1][0]};
+            d.r1[es] = Quad<R>{rot.m[1][1], rot.m[1][2], rot.m[2][0], rot.m[2][1]};
+            d.r2[es] = Quad<R>{rot.m[2][2], R(0), R(0), R(0)};
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { const V3<R> def = mul(rot, P[w]); D[3 * w] = X0[3 * w] - def.x; D[3 * w + 1] = X0[3 * w + 1] - def.y; D[3 * w + 2] = X0[3 * w + 2] - def.z; }
+            hex_matvec(F, K, D);
+#pragma unroll
+            for (int w = 0; w < 8; ++w) C[w] = mul_t(rot, mk3<R>(F[3 * w], F[3 * w + 1], F[3 * w + 2]));
+        }
+    }
+}
+
+template <class R> __host__ __device__ inline size_t hex_smem_bytes(int max_touched, int max_slots) {
+    size_t a = tile_smem_bytes<R>(max_touched, max_slots);
+    a = (a + 15) & ~size_t(15);
+    return a + sizeof(R) * 576 * kHexSmemMatrices;
+}
+
+template <class R, int MODE>
+__global__ void __launch_bounds__(256) hex_tile_kernel(HexDev<R> d, const R* __restrict__ in, NodeEpilogue<R> ep, int max_touched, int max_slots) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[32];
+    __shared__ uint16_t s_jds[1024];
+    typedef typename SVec<R>::T SV;
+    if (ep.cg && ep.cg->done) return;
+    SV* s_in = reinterpret_cast<SV*>(smem_raw);
+    size_t off = (sizeof(SV) * size_t(max_touched) + 15) & ~size_t(15);
+    R* s_slot = reinterpret_cast<R*>(smem_raw + off);
+    off = (off + sizeof(R) * 3 * size_t(max_slots) + 15) & ~size_t(15);
+    R* s_k = reinterpret_cast<R*>(smem_raw + off);   // kHexSmemMatrices x 576
+
+    const TileDev<R>& t = d.t;
+    const int tile = blockIdx.x;
+    const uint32_t* ku = d.tile_kuniq + size_t(tile) * (kHexSmemMatrices + 1);
+    const int n_ku = int(ku[0]);
+    for (int i = threadIdx.x; i < n_ku * 576; i += blockDim.x) s_k[i] = d.ktab[size_t(ku[1 + i / 576]) * 576 + i % 576];
+    tile_phase1<R>(t, tile, in, s_in, s_jds);   // ends with __syncthreads()
+
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    for (int le = threadIdx.x; le < t.tile_e; le += blockDim.x) {
+        const size_t es = size_t(tile) * t.tile_e + le;
+        const uint4 ln = idx_load(d.lnode + es, pol_stream);
+        if ((ln.x & 0xFFFFu) == 0xFFFFu) continue;
+        const uint4 sa = idx_load(d.slot_a + es, pol_stream), sb2 = idx_load(d.slot_b + es, pol_stream);
+        const unsigned lid[8] = {ln.x & 0xFFFFu, ln.x >> 16, ln.y & 0xFFFFu, ln.y >> 16, ln.z & 0xFFFFu, ln.z >> 16, ln.w & 0xFFFFu, ln.w >> 16};
+        V3<R> P[8], C[8];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const SV pv = s_in[lid[w]]; P[w] = mk3<R>(pv.x, pv.y, pv.z); }
+        const uint32_t ki = d.kidx[es];
+        const R* K = d.ktab + size_t(ki) * 576;
+        for (int u = 0; u < n_ku; ++u) if (ku[1 + u] == ki) K = s_k + 576 * u;
+        hex_element<R, MODE>(d, es, K, P, C);
+        const unsigned s8[8] = {sa.x, sa.y, sa.z, sa.w, sb2.x, sb2.y, sb2.z, sb2.w};
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tile_scatter<R>(t, s8[w], C[w].x, C[w].y, C[w].z, s_slot, max_slots, pol_keep);
+    }
+    __syncthreads();
+    const double part = tile_phase3<R>(t, tile, ep, s_in, s_slot, max_slots, s_jds);
+    if (ep.dot_kind != DOT_NONE) {
+        const double tot = block_sum(part, red);
+        finish_dot(ep, tot, red, false);
+    }
+}
+
+template <class R> __global__ void hex_export_rotations_kernel(HexDev<R> d, const uint32_t* __restrict__ orig, R* __restrict__ out) {
+    const size_t es = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (es >= d.n_slots) return;
+    const uint32_t e = orig[es];
+    if (e == 0xFFFFFFFFu) return;
+    const Quad<R> q0 = d.r0[es], q1 = d.r1[es], q2 = d.r2[es];
+    R* o = out + 9 * size_t(e);
+    o[0] = q0.a; o[1] = q0.b; o[2] = q0.c; o[3] = q0.d; o[4] = q1.a; o[5] = q1.b; o[6] = q1.c; o[7] = q1.d; o[8] = q2.a;
+}
+
+}  // namespace sb

@@ -152,7 +152,7 @@ template <class R> static std::string tet_host_build(HostTet<R>& ff, size_t n_no
     tile_e = std::max(32, (tile_e + 31) / 32 * 32);
     for (;;) {
         const std::string err = build_plan(ff.plan, int(n_nodes), int(n_tets), 4, tets, pos.data(), tile_e, chunk, kStageFlag);
-        ff.smem_bytes = tet_smem_bytes<R>(ff.plan.max_touched, ff.plan.max_slots);
+        ff.smem_bytes = tile_smem_bytes<R>(ff.plan.max_touched, ff.plan.max_slots);
         const bool too_big = ff.smem_bytes > 200 * 1024 || err.find("use a smaller tile") != std::string::npos;
         if (too_big && !fixed_tile && tile_e > 32) {
             ++k_waves;

@@ -59,20 +59,6 @@ template <class R> HD TetRec<R> tet_load_rec(const TetDev<R>& d, size_t es, uint
     r.ja = rec_load(d.j0 + es, pol); r.jb = rec_load(d.j1 + es, pol); r.jc = rec_load(d.j2 + es, pol);
     return r;
 }
-HD uint2 idx_load(const uint2* p, uint64_t pol) {
-#ifdef __CUDA_ARCH__
-    return ldg_hint(p, pol);
-#else
-    (void)pol; return *p;
-#endif
-}
-HD uint4 idx_load(const uint4* p, uint64_t pol) {
-#ifdef __CUDA_ARCH__
-    return ldg_hint(p, pol);
-#else
-    (void)pol; return *p;
-#endif
-}
 template <class R, int MODE> HD void tet_element(const TetDev<R>& d, size_t es, const TetRec<R>& rec, const V3<R> P[4], V3<R> C[4]) {
     const Quad<R> q0 = rec.q0, q1 = rec.q1, q2 = rec.q2;
     const Quad<R> ja = rec.ja, jb = rec.jb, jc = rec.jc;
@@ -179,17 +165,6 @@ template <class R, int MODE> HD void tet_element(const TetDev<R>& d, size_t es, 
     }
 }
 
-// shared-memory staging of nodal vectors: float -> float4 (one LDS.128), double -> 3 doubles
-template <class R> struct SVec;
-template <> struct SVec<float> { typedef float4 T; static __device__ __forceinline__ T make(float x, float y, float z) { return make_float4(x, y, z, 0.f); } };
-template <> struct SVec<double> { struct T { double x, y, z; }; static __device__ __forceinline__ T make(double x, double y, double z) { T t; t.x = x; t.y = y; t.z = z; return t; } };
-
-template <class R> __host__ __device__ inline size_t tet_smem_bytes(int max_touched, int max_slots) {
-    size_t a = sizeof(typename SVec<R>::T) * size_t(max_touched);
-    a = (a + 15) & ~size_t(15);
-    return a + sizeof(R) * 3 * size_t(max_slots);
-}
-
 // MAXT: CTA size the kernel is compiled for (register budget 65536/MAXT); PF: software-prefetch the next element record
 template <class R, int MODE, int MAXT, bool PF>
 __global__ void __launch_bounds__(MAXT) tet_tile_kernel(TetDev<R> d, const R* __restrict__ in, NodeEpilogue<R> ep, int max_touched, int max_slots) {
@@ -204,18 +179,8 @@ __global__ void __launch_bounds__(MAXT) tet_tile_kernel(TetDev<R> d, const R* __
 
     const TileDev<R>& t = d.t;
     const int tile = blockIdx.x;
-    const uint32_t node_off = t.tile_node_off[tile];
-    const int n_touched = int(t.tile_node_off[tile + 1] - node_off);
-    const int n_int = int(t.tile_nint[tile]);
-
     // ---- phase 1: stage input vectors of the touched nodes
-    for (int k = threadIdx.x; k < n_touched; k += blockDim.x) {
-        const uint32_t g = t.tile_nodes[node_off + k];
-        const R* p = in + 3 * size_t(g);
-        s_in[k] = SVec<R>::make(p[0], p[1], p[2]);
-    }
-    for (int j = threadIdx.x; j <= t.maxval; j += blockDim.x) s_jds[j] = t.tile_jds[size_t(tile) * (t.maxval + 1) + j];
-    __syncthreads();
+    tile_phase1<R>(t, tile, in, s_in, s_jds);
 
     // ---- phase 2: elements
     const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
@@ -245,12 +210,7 @@ __global__ void __launch_bounds__(MAXT) tet_tile_kernel(TetDev<R> d, const R* __
             const unsigned s4[4] = {sl.x, sl.y, sl.z, sl.w};
 #pragma unroll
             for (int n = 0; n < 4; ++n) {
-                const unsigned s = s4[n];
-                if (s & kStageFlag) {
-                    stage_store(t.stage + (s & ~kStageFlag), C[n].x, C[n].y, C[n].z, pol_keep);
-                } else {
-                    s_slot[s] = C[n].x; s_slot[max_slots + s] = C[n].y; s_slot[2 * max_slots + s] = C[n].z;
-                }
+                tile_scatter<R>(t, s4[n], C[n].x, C[n].y, C[n].z, s_slot, max_slots, pol_keep);
             }
         }
         le = nle;
@@ -262,21 +222,8 @@ __global__ void __launch_bounds__(MAXT) tet_tile_kernel(TetDev<R> d, const R* __
     }
     __syncthreads();
 
-    // ---- phase 3: interior nodes, sequential sum in element order
-    double part = 0.0;
-    for (int k = threadIdx.x; k < n_int; k += blockDim.x) {
-        const uint32_t g = t.tile_nodes[node_off + k];
-        const int val = t.tile_val[node_off + k];
-        // mdx_src / dot_with are the kernel's own input vector whenever they are used (A*p: both are p), so the
-        // shared-memory copy staged in phase 1 serves them
-        const SV pv = s_in[k];
-        R ax, ay, az;
-        node_pre(ep, g, ax, ay, az);
-        node_mass_v(ep, ep.pre_kind, g, R(pv.x), R(pv.y), R(pv.z), ax, ay, az);
-        if (ep.sign > 0) for (int jj = 0; jj < val; ++jj) { const int s = s_jds[jj] + k; ax += s_slot[s]; ay += s_slot[max_slots + s]; az += s_slot[2 * max_slots + s]; }
-        else             for (int jj = 0; jj < val; ++jj) { const int s = s_jds[jj] + k; ax -= s_slot[s]; ay -= s_slot[max_slots + s]; az -= s_slot[2 * max_slots + s]; }
-        part += node_post_v(ep, g, R(pv.x), R(pv.y), R(pv.z), ax, ay, az);
-    }
+    // ---- phase 3: interior nodes, sequential sum in element order + fused epilogue
+    const double part = tile_phase3<R>(t, tile, ep, s_in, s_slot, max_slots, s_jds);
     if (ep.dot_kind != DOT_NONE) {
         const double tot = block_sum(part, red);
         finish_dot(ep, tot, red, false);
