@@ -172,7 +172,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dtype, template, s = (np.float32, "B200Vec3f", 4) if args.dtype == "f32" else (np.float64, "B200Vec3d", 8)
 
-    # ---- synthetic input of BASELINE's shape; every rank owns one independent beam of the workload (weak scaling)
+    if world > 1:
+        return run_ours_distributed(args, rank, world, local, dtype, template, s)
+    # ---- synthetic input of BASELINE's shape
     pos, tets, fixed = build_mesh(args.workload)
     ctx = sb.Context(local)
     mo = sb.MechanicalObject(ctx, template, position=pos)
@@ -264,6 +266,68 @@ def run_ours(args):
     }
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_steps, 1)
+    print(json.dumps(line))
+
+
+def run_ours_distributed(args, rank, world, local, dtype, template, s):
+    """N > 1: ONE beam N times as long as the workload's, cut into N z-slabs of the workload's size (weak scaling), with the
+    per-iteration halo exchange and the two scalar allreduces over NCCL (sofa_b200/parallel.py)."""
+    import torch
+    import torch.distributed as dist
+    import sofa_b200 as sb
+    import sofa_b200.parallel as PAR
+    from sofa_b200 import topology as T
+    w = WORKLOADS[args.workload]
+    nz = (w["n"][2] - 1) * world + 1
+    n = (w["n"][0], w["n"][1], nz)
+    mx = (w["mx"][0], w["mx"][1], w["mn"][2] + (w["mx"][2] - w["mn"][2]) * world)
+    pos, hexas = T.regular_grid(n, w["mn"], mx)
+    tets = T.hexas_to_tetras(hexas, n, "mapping_swapping")
+    fixed = T.box_roi(pos, (w["box"][0], w["box"][1], w["box"][2], mx[0] + 1, mx[1] + 1, w["box"][5]))
+    ctx = sb.Context(local)
+    node = PAR.DistributedSolverNode(pos, tets, fixed, SCENE["density"], SCENE["young"], SCENE["poisson"], SCENE["method"], ctx=ctx, template=template,
+                                     dt=SCENE["dt"], gravity=SCENE["gravity"], rayleighStiffness=SCENE["rK"], rayleighMass=SCENE["rM"],
+                                     iterations=SCENE["iterations"], tolerance=SCENE["tolerance"], threshold=SCENE["threshold"])
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        dist.barrier(); torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        node.step()
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    launches0 = ctx.launch_count
+    node.cg_iterations_total = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        node.step()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=ctx.device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    if rank != 0:
+        return
+    T_loc, N_loc = node.rm.elems.shape[0], node.rm.n_local
+    iters = node.cg_iterations_total
+    peak, peak_src = measured_peaks()
+    ab = algorithmic_bytes(T_loc, N_loc, s)
+    value = iters * world / (ms * 1e-3)    # every CG iteration processes `world` partitions of the workload's size
+    cg_gbs = ab["cg_iteration"] * iters / (ms * 1e-3) / 1e9
+    line = {"metric": "cg_iters_per_s", "value": value, "unit": "cg_iters/s (x partitions of 983040 tets)", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "steps_per_s": args.steps / (ms * 1e-3), "cg_iters_per_step": iters / args.steps,
+            "config": {"workload": f"{args.workload} x {world}: ONE RegularGridTopology {n} cantilever, {tets.shape[0]} tetrahedra, {pos.shape[0]} nodes, "
+                                   f"z-slab partition ({T_loc} tets, {N_loc} nodes per GPU), method=large, CG {CG_ITERS} it", "partition": f"{world} slabs, halo "
+                       f"{len(node.rm.interface)} nodes/rank, NCCL send/recv + allreduce, host-read CG scalars", "l2": "working set per CG iteration exceeds L2"},
+            "roofline": {"bound": "hbm", "achieved": cg_gbs, "peak": peak, "unit": "GB/s", "frac": cg_gbs / peak, "traffic": None,
+                         "kernel": "whole distributed CG iteration per GPU (algorithmic bytes of one partition)", "peak_source": peak_src},
+            "e2e": {"value": value, "unit": "cg_iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 16 * iters // max(args.steps, 1),
+                    "note": "state stays on the devices; per iteration two 8-byte scalars are read back by the host-driven distributed CG"},
+            "gpu_launches": launches, "clocks": clocks}
     print(json.dumps(line))
 
 

@@ -91,6 +91,9 @@ int sofab200_mo_vop(sofab200_ctx* ctx, sofab200_real real, size_t n, void* r_dev
 /* MechanicalObject::vDot [MO]:2333-2356.  Accumulated in double with a fixed-order tree (run-to-run
  * reproducible); the reference's serial Real accumulation order cannot be kept in parallel. (sync) */
 int sofab200_mo_vdot(sofab200_ctx* ctx, sofab200_real real, size_t n, const void* a_dev, const void* b_dev, double* result_host);
+/* The same dot product restricted to the nodes whose mask byte is non-zero (NULL = all) with the result left in device
+ * memory (no synchronisation): the per-rank term of a distributed vDot (owned nodes only) before its allreduce. */
+int sofab200_mo_vdot_dev(sofab200_ctx* ctx, sofab200_real real, size_t n, const void* a_dev, const void* b_dev, const unsigned char* node_mask_dev, double* result_dev);
 /* MechanicalObject::vMultiOp integration fast path [MO]:2208-2241: v += a*f_v_a ; x += v*f_x_v. */
 int sofab200_mo_vmultiop_integrate(sofab200_ctx* ctx, sofab200_real real, size_t n, void* v_dev, void* x_dev, const void* a_dev, double f_v_a, double f_x_v);
 
@@ -201,6 +204,14 @@ int sofab200_node_set_params(sofab200_node* node, const sofab200_solver_params* 
 int sofab200_node_compute_force(sofab200_node* node, void* f_dev, const void* x_dev);
 /* GraphScatteredMatrix::apply [GS]:33-46: q = project((m M + b B + k K) p), fused in one pass. */
 int sofab200_node_apply(sofab200_node* node, void* q_dev, const void* p_dev, double m_factor, double b_factor, double k_factor);
+/* The visitor form of the same pass, MechanicalAddMBKdxVisitor / mop.addMBKv (MechanicalOperations.cpp:291-307,
+ * MappingGraphMechanicalOperations.cpp:94-137): out = [init +] (m M + b B + k K) d, optionally scaled (b.teq(h)) and
+ * projected.  init_dev may be NULL (start from 0) or alias out_dev. */
+int sofab200_node_add_mbkdx(sofab200_node* node, void* out_dev, const void* init_dev, const void* d_dev, double m_factor, double b_factor, double k_factor,
+                            int scale, double scale_factor, int project);
+/* Replace the node's DiagonalMass vertexMass (n Reals, host).  Used by the multi-GPU host layer to give every rank the
+ * global lumped mass of its nodes, zeroed where another rank adds the mass term of a shared node. */
+int sofab200_node_set_vertex_mass(sofab200_node* node, const void* vertex_mass_host);
 /* CGLinearSolver::solve [CG]:73-315 for the matrix-free system (m M + b B + k K), entirely on the
  * device: no host round trip per iteration.  x_dev: solution (initial guess when warm_start).
  * nb_iter_host: NULL = leave the result on the device (async); else (sync) receives "CG iterations". */

@@ -55,6 +55,7 @@ SYMBOLS = {
     "sofab200_ctx_profile_end": (_I, [_P, C.POINTER(_D), C.POINTER(_U64)]),
     "sofab200_mo_vop": (_I, [_P, _I, _SZ, _P, _P, _P, _D]),
     "sofab200_mo_vdot": (_I, [_P, _I, _SZ, _P, _P, C.POINTER(_D)]),
+    "sofab200_mo_vdot_dev": (_I, [_P, _I, _SZ, _P, _P, _P, _P]),
     "sofab200_mo_vmultiop_integrate": (_I, [_P, _I, _SZ, _P, _P, _P, _D, _D]),
     "sofab200_mass_add_mdx": (_I, [_P, _I, _SZ, _P, _P, _P, _D]),
     "sofab200_mass_add_force": (_I, [_P, _I, _SZ, _P, _P, C.POINTER(_D)]),
@@ -77,6 +78,8 @@ SYMBOLS = {
     "sofab200_node_set_params": (_I, [_P, C.POINTER(SolverParams)]),
     "sofab200_node_compute_force": (_I, [_P, _P, _P]),
     "sofab200_node_apply": (_I, [_P, _P, _P, _D, _D, _D]),
+    "sofab200_node_add_mbkdx": (_I, [_P, _P, _P, _P, _D, _D, _D, _I, _D, _I]),
+    "sofab200_node_set_vertex_mass": (_I, [_P, _P]),
     "sofab200_node_cg_solve": (_I, [_P, _P, _P, _D, _D, _D, C.POINTER(_I)]),
     "sofab200_node_step": (_I, [_P, _P, _P]),
     "sofab200_node_step_host": (_I, [_P, _P, _P]),

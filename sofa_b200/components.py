@@ -102,6 +102,10 @@ class MechanicalObject:
         check(self.ctx.L.sofab200_mo_vdot(self.ctx.h, self.real, self.size, _dptr(a), _dptr(b), C.byref(out)))
         return out.value
 
+    def vDot_dev(self, a, b, result, node_mask=None):
+        """Masked dot product left in the 1-element float64 device tensor `result` (asynchronous)."""
+        check(self.ctx.L.sofab200_mo_vdot_dev(self.ctx.h, self.real, self.size, _dptr(a), _dptr(b), _dptr(node_mask), _dptr(result)))
+
     def vMultiOp_integrate(self, v, x, a, f_v_a=1.0, f_x_v=1.0):
         check(self.ctx.L.sofab200_mo_vmultiop_integrate(self.ctx.h, self.real, self.size, _dptr(v), _dptr(x), _dptr(a), float(f_v_a), float(f_x_v)))
 
@@ -291,6 +295,15 @@ class SolverNode:
     def apply(self, q, p, mFactor, bFactor, kFactor):
         """GraphScatteredMatrix::apply: q = project((m M + b B + k K) p)."""
         check(self.ctx.L.sofab200_node_apply(self.h, _dptr(q), _dptr(p), float(mFactor), float(bFactor), float(kFactor)))
+
+    def addMBKdx(self, out, d, mFactor, bFactor, kFactor, init=None, scale=None, project=False):
+        """out = [init +] (m M + b B + k K) d, optionally * scale and projected (mop.addMBKdx / addMBKv)."""
+        check(self.ctx.L.sofab200_node_add_mbkdx(self.h, _dptr(out), _dptr(init), _dptr(d), float(mFactor), float(bFactor), float(kFactor),
+                                                 int(scale is not None), float(scale if scale is not None else 1.0), int(project)))
+
+    def set_vertex_mass(self, m):
+        m = np.ascontiguousarray(m, self.mstate.ndtype)
+        check(self.ctx.L.sofab200_node_set_vertex_mass(self.h, m.ctypes.data_as(_P)))
 
     def cg_solve(self, x, b, mFactor, bFactor, kFactor, sync=True):
         it = C.c_int()

@@ -271,6 +271,14 @@ int sofab200_mo_vdot(sofab200_ctx* ctx, sofab200_real real, size_t n, const void
     if (real == SOFAB200_F32) return vdot_impl<float>(ctx, n, (const float*)a_dev, (const float*)b_dev, result_host);
     return vdot_impl<double>(ctx, n, (const double*)a_dev, (const double*)b_dev, result_host);
 }
+int sofab200_mo_vdot_dev(sofab200_ctx* ctx, sofab200_real real, size_t n, const void* a_dev, const void* b_dev, const unsigned char* mask_dev, double* result_dev) {
+    SB_CHECK(ctx && a_dev && b_dev && result_dev, "null argument");
+    int g = vec_grid(n, ctx->sm_count);
+    if (g > 2048) g = 2048;
+    if (real == SOFAB200_F32) LAUNCH(ctx, (vdot_masked_kernel<float>), g, kVecBlock, n, (const float*)a_dev, (const float*)b_dev, mask_dev, ctx->red_partials.p, ctx->red_counter.p, result_dev);
+    else LAUNCH(ctx, (vdot_masked_kernel<double>), g, kVecBlock, n, (const double*)a_dev, (const double*)b_dev, mask_dev, ctx->red_partials.p, ctx->red_counter.p, result_dev);
+    return SOFAB200_OK;
+}
 int sofab200_mo_vmultiop_integrate(sofab200_ctx* ctx, sofab200_real real, size_t n, void* v_dev, void* x_dev, const void* a_dev, double f_v_a, double f_x_v) {
     SB_CHECK(ctx && v_dev && x_dev && a_dev, "null argument");
     const size_t n3 = 3 * n;
@@ -339,6 +347,19 @@ int sofab200_node_compute_force(sofab200_node* node, void* f_dev, const void* x_
 int sofab200_node_apply(sofab200_node* node, void* q_dev, const void* p_dev, double m, double b, double k) {
     SB_CHECK(node && q_dev && p_dev && q_dev != p_dev, "null or aliased argument");
     return NODE_DISPATCH(node, NF(node)->apply((float*)q_dev, (const float*)p_dev, m, b, k), ND(node)->apply((double*)q_dev, (const double*)p_dev, m, b, k));
+}
+int sofab200_node_add_mbkdx(sofab200_node* node, void* out_dev, const void* init_dev, const void* d_dev, double m, double b, double k, int scale, double sf, int project) {
+    SB_CHECK(node && out_dev && d_dev && out_dev != d_dev, "null or aliased argument");
+    return NODE_DISPATCH(node, NF(node)->add_mbk((float*)out_dev, (const float*)init_dev, (const float*)d_dev, m, b, k, scale != 0, sf, project != 0, DOT_NONE, nullptr),
+                         ND(node)->add_mbk((double*)out_dev, (const double*)init_dev, (const double*)d_dev, m, b, k, scale != 0, sf, project != 0, DOT_NONE, nullptr));
+}
+int sofab200_node_set_vertex_mass(sofab200_node* node, const void* vertex_mass_host) {
+    SB_CHECK(node && vertex_mass_host, "null argument");
+    cudaStream_t s = node->ctx->stream;
+    if (node->real == SOFAB200_F32) { auto* n = NF(node); if (!n->mass.p) SB_TRY(n->mass.alloc(n->n)); n->has_mass = true; SB_CUDA(cudaMemcpyAsync(n->mass.p, vertex_mass_host, n->n * 4, cudaMemcpyHostToDevice, s)); }
+    else { auto* n = ND(node); if (!n->mass.p) SB_TRY(n->mass.alloc(n->n)); n->has_mass = true; SB_CUDA(cudaMemcpyAsync(n->mass.p, vertex_mass_host, n->n * 8, cudaMemcpyHostToDevice, s)); }
+    SB_CUDA(cudaStreamSynchronize(s));
+    return SOFAB200_OK;
 }
 int sofab200_node_cg_solve(sofab200_node* node, void* x_dev, const void* b_dev, double m, double b, double k, int* nb_iter_host) {
     SB_CHECK(node && x_dev && b_dev, "null argument");

@@ -70,6 +70,17 @@ template <class R> __global__ void __launch_bounds__(kVecBlock) vdot_kernel(size
     dot_epilogue<R>(part, partials, counter, action, result, cg);
 }
 
+// node-masked variant (distributed vDot: owned nodes only)
+template <class R> __global__ void __launch_bounds__(kVecBlock) vdot_masked_kernel(size_t n, const R* __restrict__ a, const R* __restrict__ b, const unsigned char* __restrict__ mask,
+                                                                                    double* partials, unsigned* counter, double* result) {
+    double part = 0.0;
+    for (size_t g = size_t(blockIdx.x) * blockDim.x + threadIdx.x; g < n; g += size_t(gridDim.x) * blockDim.x) {
+        if (mask && !mask[g]) continue;
+        part += double(a[3 * g]) * double(b[3 * g]) + double(a[3 * g + 1]) * double(b[3 * g + 1]) + double(a[3 * g + 2]) * double(b[3 * g + 2]);
+    }
+    dot_epilogue<R>(part, partials, counter, DF_STORE, result, nullptr);
+}
+
 // vMultiOp integration fast path, MechanicalObject.inl:2208-2241
 template <class R> __global__ void __launch_bounds__(kVecBlock) integrate_kernel(size_t n3, R* __restrict__ v, R* __restrict__ x, const R* __restrict__ a, R f_v_a, int f_v_a_is_one, R f_x_v) {
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n3; i += size_t(gridDim.x) * blockDim.x) {
