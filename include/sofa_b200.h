@@ -226,6 +226,43 @@ int sofab200_node_step_host(sofab200_node* node, void* x_host, void* v_host);
 int sofab200_node_last_solve(sofab200_node* node, int* nb_iter, int* end_cond, double* graph_error, size_t* n_error, double* graph_den, size_t* n_den, size_t cap);
 /* Device vectors of the last step for parity checks (sync): "f" (force), "b" (right-hand side), "dx" (solution) */
 int sofab200_node_get(sofab200_node* node, const char* what, void* out_host);
+/* ------------------------------------------------------------------------------------------------ */
+/* Multi-GPU: one process per GPU, the mesh partitioned by contiguous element ranges (sofa_b200/parallel.py).   */
+/* The reference has no distributed mode; these entry points are new.                                           */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct sofab200_comm sofab200_comm;   /* an NCCL communicator bound to a context */
+#define SOFAB200_UNIQUE_ID_BYTES 128
+/* Rank 0 calls get_unique_id and ships the bytes to the other ranks (torch.distributed / MPI / a file);
+ * then every rank calls comm_create (collective, blocking). */
+int sofab200_comm_get_unique_id(void* out_bytes);
+int sofab200_comm_create(sofab200_ctx* ctx, int world, int rank, const void* unique_id_bytes, sofab200_comm** out);
+int sofab200_comm_destroy(sofab200_comm* comm);
+
+/* Interface (halo) description of the rank-local node set, all arrays on the host:
+ *   owned[n_nodes]            1 where this rank owns the node (lowest sharing rank), else 0
+ *   interface[n_interface]    local ids of the nodes shared with other ranks, ascending
+ *   my_slot[n_interface]      position of this rank in the node's ascending list of sharing ranks
+ *   for neighbour k: nb_rank[k], nb_count[k] nodes; nb_rows[k][i] = row in `interface`, nb_slot[k][i] = the neighbour's
+ *   position in that node's list.  Both sides list the shared nodes of a pair in the same (global id) order. */
+typedef struct sofab200_halo_desc {
+    const unsigned char* owned;
+    size_t n_interface;
+    const uint32_t* interface;
+    const int32_t* my_slot;
+    int max_sharers;
+    int n_neighbours;
+    const int* nb_rank;
+    const size_t* nb_count;
+    const uint32_t* const* nb_rows;
+    const int32_t* const* nb_slot;
+} sofab200_halo_desc;
+/* Attach a communicator and a halo plan to a node: from then on sofab200_node_step / _cg_solve / _apply / _compute_force run
+ * the distributed algorithm -- rank-local fused element pass, NCCL send/recv of the interface partial sums added in
+ * ascending rank order on every sharing rank, dot products over owned nodes all-reduced -- still without any host round
+ * trip per iteration and still replayed from one CUDA graph per step.  The node's vertexMass must hold the global lumped
+ * mass on owned nodes and 0 elsewhere (sofab200_node_set_vertex_mass). */
+int sofab200_node_set_distributed(sofab200_node* node, sofab200_comm* comm, const sofab200_halo_desc* halo);
+
 /* CGLinearSolver keeps `timeStepCount` to silence first-step warnings ([CG]:161-176); reset() restores 0. */
 int sofab200_node_reset(sofab200_node* node);
 

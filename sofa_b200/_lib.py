@@ -34,6 +34,12 @@ class NodeDesc(C.Structure):
                 ("fix_all", C.c_int), ("mass_first", C.c_int)]
 
 
+class HaloDesc(C.Structure):
+    _fields_ = [("owned", C.POINTER(C.c_ubyte)), ("n_interface", C.c_size_t), ("interface", C.POINTER(C.c_uint32)), ("my_slot", C.POINTER(C.c_int32)),
+                ("max_sharers", C.c_int), ("n_neighbours", C.c_int), ("nb_rank", C.POINTER(C.c_int)), ("nb_count", C.POINTER(C.c_size_t)),
+                ("nb_rows", C.POINTER(C.POINTER(C.c_uint32))), ("nb_slot", C.POINTER(C.POINTER(C.c_int32)))]
+
+
 class SolverParams(C.Structure):
     _fields_ = [("gravity", C.c_double * 3), ("dt", C.c_double), ("rayleigh_stiffness", C.c_double), ("rayleigh_mass", C.c_double),
                 ("vdamping", C.c_double), ("first_order", C.c_int), ("trapezoidal", C.c_int), ("iterations", C.c_uint),
@@ -86,6 +92,10 @@ SYMBOLS = {
     "sofab200_node_last_solve": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_D), C.POINTER(_SZ), C.POINTER(_D), C.POINTER(_SZ), _SZ]),
     "sofab200_node_get": (_I, [_P, C.c_char_p, _P]),
     "sofab200_node_reset": (_I, [_P]),
+    "sofab200_comm_get_unique_id": (_I, [_P]),
+    "sofab200_comm_create": (_I, [_P, _I, _I, _P, C.POINTER(_P)]),
+    "sofab200_comm_destroy": (_I, [_P]),
+    "sofab200_node_set_distributed": (_I, [_P, _P, C.POINTER(HaloDesc)]),
 }
 
 _lib = None

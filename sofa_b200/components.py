@@ -75,6 +75,34 @@ class Context:
             pass
 
 
+class Communicator:
+    """An NCCL communicator of the library bound to a Context (sofab200_comm).  The unique id is created on rank 0 and
+    shipped with torch.distributed, which is only the bootstrap channel."""
+
+    def __init__(self, ctx, group=None):
+        import torch.distributed as dist
+        self.ctx = ctx
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_ubyte * 128)()
+            check(ctx.L.sofab200_comm_get_unique_id(buf))
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        if dist.get_backend(group) == "nccl":
+            t = ident.to(ctx.device); dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group); ident = t.cpu()
+        else:
+            dist.broadcast(ident, src=0, group=group)
+        raw = (C.c_ubyte * 128)(*ident.tolist())
+        self.h = _P()
+        check(ctx.L.sofab200_comm_create(ctx.h, self.world, self.rank, raw, C.byref(self.h)))
+
+    def __del__(self):
+        try:
+            self.ctx.L.sofab200_comm_destroy(self.h)
+        except Exception:
+            pass
+
+
 class MechanicalObject:
     """MechanicalObject<B200Vec3Types>: state vectors + vOp / vMultiOp / vDot."""
 
@@ -304,6 +332,28 @@ class SolverNode:
     def set_vertex_mass(self, m):
         m = np.ascontiguousarray(m, self.mstate.ndtype)
         check(self.ctx.L.sofab200_node_set_vertex_mass(self.h, m.ctypes.data_as(_P)))
+
+    def set_distributed(self, comm, rank_mesh):
+        """Attach an NCCL communicator and the halo plan of a parallel.RankMesh: step / cg_solve / apply / computeForce then run
+        the distributed algorithm inside the library."""
+        rm = rank_mesh
+        owned = np.ascontiguousarray(rm.owned, np.uint8)
+        interface = np.ascontiguousarray(rm.interface, np.uint32)
+        my_slot = np.ascontiguousarray(rm.my_slot, np.int32)
+        nbs = sorted(rm.neighbours.items())
+        nb_rank = (C.c_int * max(len(nbs), 1))(*[s for s, _ in nbs])
+        nb_count = (C.c_size_t * max(len(nbs), 1))(*[len(v["rows"]) for _, v in nbs])
+        rows = [np.ascontiguousarray(v["rows"], np.uint32) for _, v in nbs]
+        slots = [np.ascontiguousarray(v["slot"], np.int32) for _, v in nbs]
+        rows_p = (C.POINTER(C.c_uint32) * max(len(nbs), 1))(*[r.ctypes.data_as(C.POINTER(C.c_uint32)) for r in rows])
+        slots_p = (C.POINTER(C.c_int32) * max(len(nbs), 1))(*[r.ctypes.data_as(C.POINTER(C.c_int32)) for r in slots])
+        d = _lib.HaloDesc()
+        d.owned = owned.ctypes.data_as(C.POINTER(C.c_ubyte))
+        d.n_interface = len(interface); d.interface = interface.ctypes.data_as(C.POINTER(C.c_uint32)); d.my_slot = my_slot.ctypes.data_as(C.POINTER(C.c_int32))
+        d.max_sharers = int(rm.max_sharers); d.n_neighbours = len(nbs)
+        d.nb_rank, d.nb_count, d.nb_rows, d.nb_slot = nb_rank, nb_count, rows_p, slots_p
+        check(self.ctx.L.sofab200_node_set_distributed(self.h, comm.h, C.byref(d)))
+        self._comm = comm
 
     def cg_solve(self, x, b, mFactor, bFactor, kFactor, sync=True):
         it = C.c_int()

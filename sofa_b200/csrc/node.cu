@@ -4,6 +4,8 @@
 #include <cstring>
 #include <memory>
 
+#include <nccl.h>
+
 #include "vec_ops.cuh"
 
 using namespace sb;
@@ -26,6 +28,18 @@ int hex_real(sofab200_hexfem* ff); size_t hex_nodes(sofab200_hexfem* ff);
         (ctx)->launches++;                                                 \
         SB_CUDA(cudaGetLastError());                                       \
     } while (0)
+
+#define SB_NCCL(call)                                                                                   \
+    do {                                                                                                \
+        ncclResult_t r_ = (call);                                                                       \
+        if (r_ != ncclSuccess) return ::sb::fail(SOFAB200_ERR_CUDA, std::string(#call) + ": " + ncclGetErrorString(r_)); \
+    } while (0)
+
+struct sofab200_comm {
+    sofab200_ctx* ctx = nullptr;
+    ncclComm_t comm = nullptr;
+    int world = 1, rank = 0;
+};
 
 // ---------------------------------------------------------------------------------------------------
 // MechanicalObject::vOp dispatch (MechanicalObject.inl:2075-2203)
@@ -95,6 +109,45 @@ template <class R> struct Node : sofab200_node {
     bool use_graph = true;
     ~Node() { if (sg.exec) cudaGraphExecDestroy(sg.exec); }
 
+    // ---- multi-GPU state (sofab200_node_set_distributed) ------------------------------------------------
+    struct Halo {
+        sofab200_comm* comm = nullptr;
+        size_t n_if = 0, n_send = 0;
+        int max_sh = 1;
+        std::vector<int> nb_rank; std::vector<size_t> nb_count, nb_off;
+        DevBuf<uint32_t> if_idx, send_idx;
+        DevBuf<int32_t> src;
+        DevBuf<R> sendbuf, recvbuf;
+        DevBuf<unsigned char> owned;
+        DevBuf<double> scal;
+    } halo;
+    bool distributed() const { return halo.comm != nullptr; }
+    ncclDataType_t nccl_real() const { return sizeof(R) == 4 ? ncclFloat : ncclDouble; }
+    // interface rows of q: sum over the sharing ranks, ascending rank order, same bits on every rank
+    int halo_sum(R* qv, const CGDev* cgp) {
+        if (!distributed() || halo.n_if == 0) return SOFAB200_OK;
+        LAUNCH(ctx, (halo_pack_kernel<R>), vec_grid(halo.n_send, ctx->sm_count), kVecBlock, halo.n_send, (const uint32_t*)halo.send_idx.p, (const R*)qv, halo.sendbuf.p, cgp);
+        SB_NCCL(ncclGroupStart());
+        for (size_t k = 0; k < halo.nb_rank.size(); ++k) {
+            SB_NCCL(ncclSend(halo.sendbuf.p + 3 * halo.nb_off[k], 3 * halo.nb_count[k], nccl_real(), halo.nb_rank[k], halo.comm->comm, ctx->stream));
+            SB_NCCL(ncclRecv(halo.recvbuf.p + 3 * halo.nb_off[k], 3 * halo.nb_count[k], nccl_real(), halo.nb_rank[k], halo.comm->comm, ctx->stream));
+        }
+        SB_NCCL(ncclGroupEnd());
+        ctx->launches += 1;
+        LAUNCH(ctx, (halo_sum_kernel<R>), vec_grid(halo.n_if, ctx->sm_count), kVecBlock, halo.n_if, halo.max_sh, (const uint32_t*)halo.if_idx.p, (const int32_t*)halo.src.p,
+               (const R*)halo.recvbuf.p, qv, cgp);
+        return SOFAB200_OK;
+    }
+    // dot over owned nodes -> allreduce -> CG bookkeeping, all on the stream
+    int dist_dot(const R* a, const R* b, int action) {
+        int g = vec_grid(n, ctx->sm_count); if (g > 2048) g = 2048;
+        LAUNCH(ctx, (vdot_masked_kernel<R>), g, kVecBlock, n, a, b, (const unsigned char*)halo.owned.p, partials.p, counters.p + 1, halo.scal.p, (const CGDev*)cg.p);
+        SB_NCCL(ncclAllReduce(halo.scal.p, halo.scal.p, 1, ncclDouble, ncclSum, halo.comm->comm, ctx->stream));
+        ctx->launches += 1;
+        LAUNCH(ctx, cg_scalar_kernel, 1, 1, cg.p, (const double*)halo.scal.p, action);
+        return SOFAB200_OK;
+    }
+
     int fem_run(bool dforce, const R* in, R k_factor, const NodeEpilogue<R>& ep) {
         if (tet) return tet_run<R>(tet, dforce, in, k_factor, ep);
         return hex_run<R>(hex, dforce, in, k_factor, ep);
@@ -116,7 +169,8 @@ template <class R> struct Node : sofab200_node {
         NodeEpilogue<R> ep = base_ep();
         ep.init_src = nullptr; ep.sign = +1; ep.out = f_out;
         set_mass_term(ep, PRE_GRAVITY, nullptr, 1.0);
-        return fem_run(false, x, R(0), ep);
+        SB_TRY(fem_run(false, x, R(0), ep));
+        return halo_sum(f_out, nullptr);
     }
     // df = init + (m M + b B + k K) d, optionally scaled and projected; dot(out, dot_with) optional
     int add_mbk(R* out, const R* init, const R* d, double m, double bfac, double k, bool scale, double s, bool project, int dot_kind, CGDev* cgp) {
@@ -134,7 +188,8 @@ template <class R> struct Node : sofab200_node {
         return SOFAB200_OK;
     }
     int apply(R* q_out, const R* p_in, double m, double bfac, double k) {
-        return add_mbk(q_out, nullptr, p_in, m, bfac, k, false, 1.0, true, DOT_NONE, nullptr);
+        SB_TRY(add_mbk(q_out, nullptr, p_in, m, bfac, k, false, 1.0, true, DOT_NONE, nullptr));
+        return halo_sum(q_out, nullptr);
     }
     // CGLinearSolver::solve, device resident
     int cg_solve(R* x, const R* bvec, double m, double bfac, double k) {
@@ -151,12 +206,27 @@ template <class R> struct Node : sofab200_node {
         }
         // streaming CG kernels: two CTAs per SM, 16-byte accesses, grid-stride
         const int gd = std::max(1, std::min<int>(2 * ctx->sm_count, int((n3 / 4 + kVecBlock - 1) / kVecBlock)));
+        if (distributed()) {
+            // same loop, with the interface rows of q exchanged and the three dot products all-reduced over the ranks
+            SB_TRY(dist_dot(bvec, bvec, DF_CG_NORMB));
+            SB_TRY(dist_dot(r.p, r.p, DF_CG_RHO));
+            for (unsigned it = 1; it <= prm.iterations; ++it) {
+                LAUNCH(ctx, (cg_p_update_kernel<R>), gd, kVecBlock, n3, p.p, (const R*)r.p, (const CGDev*)cg.p);
+                SB_TRY(add_mbk(q.p, nullptr, p.p, m, bfac, k, false, 1.0, true, DOT_NONE, cg.p));
+                SB_TRY(halo_sum(q.p, cg.p));
+                SB_TRY(dist_dot(p.p, q.p, -1));
+                LAUNCH(ctx, (cg_xr_update_kernel<R>), gd, kVecBlock, n3, x, r.p, (const R*)p.p, (const R*)q.p, cg.p, partials.p, counters.p + 1, 0);
+                SB_TRY(dist_dot(r.p, r.p, DF_CG_RHO));
+            }
+            LAUNCH(ctx, cg_end_kernel, 1, 1, cg.p);
+            return SOFAB200_OK;
+        }
         LAUNCH(ctx, (vdot_kernel<R>), gd, kVecBlock, n3, bvec, bvec, partials.p, counters.p + 1, int(DF_CG_NORMB), (double*)nullptr, cg.p);
         LAUNCH(ctx, (vdot_kernel<R>), gd, kVecBlock, n3, (const R*)r.p, (const R*)r.p, partials.p, counters.p + 1, int(DF_CG_RHO), (double*)nullptr, cg.p);
         for (unsigned it = 1; it <= prm.iterations; ++it) {
             LAUNCH(ctx, (cg_p_update_kernel<R>), gd, kVecBlock, n3, p.p, (const R*)r.p, (const CGDev*)cg.p);
             SB_TRY(add_mbk(q.p, nullptr, p.p, m, bfac, k, false, 1.0, true, DOT_CG_DEN, cg.p));  // q = A p ; den = p.q
-            LAUNCH(ctx, (cg_xr_update_kernel<R>), gd, kVecBlock, n3, x, r.p, (const R*)p.p, (const R*)q.p, cg.p, partials.p, counters.p + 1);
+            LAUNCH(ctx, (cg_xr_update_kernel<R>), gd, kVecBlock, n3, x, r.p, (const R*)p.p, (const R*)q.p, cg.p, partials.p, counters.p + 1, 1);
         }
         LAUNCH(ctx, cg_end_kernel, 1, 1, cg.p);
         return SOFAB200_OK;
@@ -201,7 +271,13 @@ template <class R> struct Node : sofab200_node {
         SB_TRY(compute_force(f.p, x));
         if (!fo) {
             // b = (f + (-rM M + (h tr + rK) K) v) * h, projected          EulerImplicitSolver.cpp:147-162
-            SB_TRY(add_mbk(b.p, f.p, v, -prm.rayleigh_mass, 0.0, h * tr + prm.rayleigh_stiffness, true, h, true, DOT_NONE, nullptr));
+            const R* finit = f.p;
+            if (distributed() && halo.n_if) {   // the start value f of a shared node enters the distributed sum on its owner only
+                LAUNCH(ctx, (mask_rows_kernel<R>), vec_grid(n, ctx->sm_count), kVecBlock, n, (const unsigned char*)halo.owned.p, (const R*)f.p, p.p);
+                finit = p.p;
+            }
+            SB_TRY(add_mbk(b.p, finit, v, -prm.rayleigh_mass, 0.0, h * tr + prm.rayleigh_stiffness, true, h, true, DOT_NONE, nullptr));
+            SB_TRY(halo_sum(b.p, nullptr));
         } else {
             NodeEpilogue<R> ep = base_ep();
             ep.init_src = f.p; ep.out = b.p; ep.sign = -1; ep.fixed = has_fixed ? fixed.p : nullptr;
@@ -275,8 +351,8 @@ int sofab200_mo_vdot_dev(sofab200_ctx* ctx, sofab200_real real, size_t n, const 
     SB_CHECK(ctx && a_dev && b_dev && result_dev, "null argument");
     int g = vec_grid(n, ctx->sm_count);
     if (g > 2048) g = 2048;
-    if (real == SOFAB200_F32) LAUNCH(ctx, (vdot_masked_kernel<float>), g, kVecBlock, n, (const float*)a_dev, (const float*)b_dev, mask_dev, ctx->red_partials.p, ctx->red_counter.p, result_dev);
-    else LAUNCH(ctx, (vdot_masked_kernel<double>), g, kVecBlock, n, (const double*)a_dev, (const double*)b_dev, mask_dev, ctx->red_partials.p, ctx->red_counter.p, result_dev);
+    if (real == SOFAB200_F32) LAUNCH(ctx, (vdot_masked_kernel<float>), g, kVecBlock, n, (const float*)a_dev, (const float*)b_dev, mask_dev, ctx->red_partials.p, ctx->red_counter.p, result_dev, (const CGDev*)nullptr);
+    else LAUNCH(ctx, (vdot_masked_kernel<double>), g, kVecBlock, n, (const double*)a_dev, (const double*)b_dev, mask_dev, ctx->red_partials.p, ctx->red_counter.p, result_dev, (const CGDev*)nullptr);
     return SOFAB200_OK;
 }
 int sofab200_mo_vmultiop_integrate(sofab200_ctx* ctx, sofab200_real real, size_t n, void* v_dev, void* x_dev, const void* a_dev, double f_v_a, double f_x_v) {
@@ -321,6 +397,72 @@ int sofab200_fixed_project_response(sofab200_ctx* ctx, sofab200_real real, size_
     if (real == SOFAB200_F32) LAUNCH(ctx, (fixed_project_kernel<float>), g, kVecBlock, n_idx, idx_dev, (float*)res_dev);
     else LAUNCH(ctx, (fixed_project_kernel<double>), g, kVecBlock, n_idx, idx_dev, (double*)res_dev);
     return SOFAB200_OK;
+}
+
+int sofab200_comm_get_unique_id(void* out_bytes) {
+    SB_CHECK(out_bytes != nullptr, "null argument");
+    static_assert(sizeof(ncclUniqueId) <= SOFAB200_UNIQUE_ID_BYTES, "unique id does not fit");
+    ncclUniqueId id;
+    SB_NCCL(ncclGetUniqueId(&id));
+    std::memset(out_bytes, 0, SOFAB200_UNIQUE_ID_BYTES);
+    std::memcpy(out_bytes, &id, sizeof(id));
+    return SOFAB200_OK;
+}
+int sofab200_comm_create(sofab200_ctx* ctx, int world, int rank, const void* unique_id_bytes, sofab200_comm** out) {
+    SB_CHECK(ctx && unique_id_bytes && out && world >= 1 && rank >= 0 && rank < world, "bad argument");
+    SB_CUDA(cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id_bytes, sizeof(id));
+    std::unique_ptr<sofab200_comm> c(new sofab200_comm());
+    c->ctx = ctx; c->world = world; c->rank = rank;
+    SB_NCCL(ncclCommInitRank(&c->comm, world, id, rank));
+    *out = c.release();
+    return SOFAB200_OK;
+}
+int sofab200_comm_destroy(sofab200_comm* comm) {
+    if (!comm) return SOFAB200_OK;
+    if (comm->comm) ncclCommDestroy(comm->comm);
+    delete comm;
+    return SOFAB200_OK;
+}
+}  // extern "C"
+namespace sb {
+template <class R> static int node_set_distributed(Node<R>* nd, sofab200_comm* comm, const sofab200_halo_desc* h) {
+    cudaStream_t s = nd->ctx->stream;
+    auto& H = nd->halo;
+    H.n_if = h->n_interface; H.max_sh = std::max(1, h->max_sharers);
+    std::vector<unsigned char> owned(h->owned, h->owned + nd->n);
+    SB_TRY(H.owned.upload(owned, s));
+    std::vector<uint32_t> if_idx(h->interface, h->interface + h->n_interface), send_idx;
+    std::vector<int32_t> src(h->n_interface * size_t(H.max_sh), -2);
+    for (size_t i = 0; i < h->n_interface; ++i) { SB_CHECK(h->my_slot[i] >= 0 && h->my_slot[i] < H.max_sh, "my_slot out of range"); src[i * H.max_sh + h->my_slot[i]] = -1; }
+    H.nb_rank.clear(); H.nb_count.clear(); H.nb_off.clear();
+    size_t off = 0;
+    for (int k = 0; k < h->n_neighbours; ++k) {
+        H.nb_rank.push_back(h->nb_rank[k]); H.nb_count.push_back(h->nb_count[k]); H.nb_off.push_back(off);
+        for (size_t i = 0; i < h->nb_count[k]; ++i) {
+            const uint32_t row = h->nb_rows[k][i];
+            SB_CHECK(row < h->n_interface && h->nb_slot[k][i] >= 0 && h->nb_slot[k][i] < H.max_sh, "halo plan out of range");
+            send_idx.push_back(if_idx[row]);
+            src[size_t(row) * H.max_sh + h->nb_slot[k][i]] = int32_t(off + i);
+        }
+        off += h->nb_count[k];
+    }
+    H.n_send = off;
+    SB_TRY(H.if_idx.upload(if_idx, s)); SB_TRY(H.send_idx.upload(send_idx, s)); SB_TRY(H.src.upload(src, s));
+    SB_TRY(H.sendbuf.alloc(3 * std::max<size_t>(off, 1))); SB_TRY(H.recvbuf.alloc(3 * std::max<size_t>(off, 1)));
+    SB_TRY(H.scal.alloc(2)); SB_TRY(H.scal.zero(s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    H.comm = comm;
+    if (nd->sg.exec) { cudaGraphExecDestroy(nd->sg.exec); nd->sg.exec = nullptr; nd->sg.seen = 0; }
+    return SOFAB200_OK;
+}
+}  // namespace sb
+extern "C" {
+int sofab200_node_set_distributed(sofab200_node* node, sofab200_comm* comm, const sofab200_halo_desc* halo) {
+    SB_CHECK(node && comm && halo && halo->owned, "null argument");
+    SB_CHECK(comm->ctx == node->ctx, "communicator and node belong to different contexts");
+    return NODE_DISPATCH(node, node_set_distributed<float>(NF(node), comm, halo), node_set_distributed<double>(ND(node), comm, halo));
 }
 
 int sofab200_node_create(sofab200_ctx* ctx, sofab200_real real, size_t n_nodes, const sofab200_node_desc* desc, sofab200_node** out) {

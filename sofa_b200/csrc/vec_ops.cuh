@@ -72,7 +72,8 @@ template <class R> __global__ void __launch_bounds__(kVecBlock) vdot_kernel(size
 
 // node-masked variant (distributed vDot: owned nodes only)
 template <class R> __global__ void __launch_bounds__(kVecBlock) vdot_masked_kernel(size_t n, const R* __restrict__ a, const R* __restrict__ b, const unsigned char* __restrict__ mask,
-                                                                                    double* partials, unsigned* counter, double* result) {
+                                                                                    double* partials, unsigned* counter, double* result, const CGDev* cg) {
+    if (cg && cg->done) return;
     double part = 0.0;
     for (size_t g = size_t(blockIdx.x) * blockDim.x + threadIdx.x; g < n; g += size_t(gridDim.x) * blockDim.x) {
         if (mask && !mask[g]) continue;
@@ -159,7 +160,7 @@ template <class R> __device__ __forceinline__ double xr_one(R& x, R& r, R p, R q
     return double(r) * double(r);
 }
 template <class R> __global__ void __launch_bounds__(kVecBlock) cg_xr_update_kernel(size_t n3, R* __restrict__ x, R* __restrict__ r, const R* __restrict__ p, const R* __restrict__ q,
-                                                                                     CGDev* cg, double* partials, unsigned* counter) {
+                                                                                     CGDev* cg, double* partials, unsigned* counter, int fused_rho) {
     if (cg->done) return;
     const double alpha_d = cg->alpha;
     const R alpha = R(alpha_d), malpha = R(-alpha_d);
@@ -182,8 +183,50 @@ template <class R> __global__ void __launch_bounds__(kVecBlock) cg_xr_update_ker
     } else {
         for (size_t i = t0; i < n3; i += stride) part += xr_one<R>(x[i], r[i], p[i], q[i], alpha, malpha, a_one, ma_one);
     }
-    dot_epilogue<R>(part, partials, counter, DF_CG_RHO, nullptr, cg);
+    if (fused_rho) dot_epilogue<R>(part, partials, counter, DF_CG_RHO, nullptr, cg);   // distributed: rho comes from an all-reduced masked dot
 }
+// ---- multi-GPU halo kernels ------------------------------------------------------------------------
+// pack the interface rows that go to the neighbours (concatenated per neighbour)
+template <class R> __global__ void __launch_bounds__(kVecBlock) halo_pack_kernel(size_t n_send, const uint32_t* __restrict__ send_idx, const R* __restrict__ q, R* __restrict__ sendbuf, const CGDev* cg) {
+    if (cg && cg->done) return;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_send; i += size_t(gridDim.x) * blockDim.x) {
+        const size_t g = send_idx[i];
+        sendbuf[3 * i] = q[3 * g]; sendbuf[3 * i + 1] = q[3 * g + 1]; sendbuf[3 * i + 2] = q[3 * g + 2];
+    }
+}
+// every interface node: sum of the partial values of all sharing ranks in ascending rank order (src: -1 own value, -2 absent,
+// >= 0 row of the receive buffer) => identical bits on every sharing rank
+template <class R> __global__ void __launch_bounds__(kVecBlock) halo_sum_kernel(size_t n_if, int max_sh, const uint32_t* __restrict__ if_idx, const int32_t* __restrict__ src,
+                                                                                 const R* __restrict__ recvbuf, R* __restrict__ q, const CGDev* cg) {
+    if (cg && cg->done) return;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_if; i += size_t(gridDim.x) * blockDim.x) {
+        const size_t g = if_idx[i];
+        const R ox = q[3 * g], oy = q[3 * g + 1], oz = q[3 * g + 2];
+        R ax = 0, ay = 0, az = 0;
+        bool first = true;
+        for (int j = 0; j < max_sh; ++j) {
+            const int32_t sidx = src[i * max_sh + j];
+            if (sidx == -2) continue;
+            const R vx = sidx < 0 ? ox : recvbuf[3 * size_t(sidx)], vy = sidx < 0 ? oy : recvbuf[3 * size_t(sidx) + 1], vz = sidx < 0 ? oz : recvbuf[3 * size_t(sidx) + 2];
+            if (first) { ax = vx; ay = vy; az = vz; first = false; } else { ax += vx; ay += vy; az += vz; }
+        }
+        q[3 * g] = ax; q[3 * g + 1] = ay; q[3 * g + 2] = az;
+    }
+}
+// out[g] = owned[g] ? in[g] : 0  (the start value of a shared node enters the distributed sum on its owner only)
+template <class R> __global__ void __launch_bounds__(kVecBlock) mask_rows_kernel(size_t n, const unsigned char* __restrict__ owned, const R* __restrict__ in, R* __restrict__ out) {
+    for (size_t g = size_t(blockIdx.x) * blockDim.x + threadIdx.x; g < n; g += size_t(gridDim.x) * blockDim.x) {
+        const bool o = owned[g] != 0;
+        out[3 * g] = o ? in[3 * g] : R(0); out[3 * g + 1] = o ? in[3 * g + 1] : R(0); out[3 * g + 2] = o ? in[3 * g + 2] : R(0);
+    }
+}
+// the scalar bookkeeping of the CG after an all-reduced dot product
+__global__ void cg_scalar_kernel(CGDev* cg, const double* value, int action) {
+    if (cg->done) return;
+    if (action == DF_CG_NORMB || action == DF_CG_RHO) dot_finish_action(action, *value, nullptr, cg);
+    else cg_after_den(cg, *value);
+}
+
 struct CGBegin { unsigned max_iter; double tolerance, threshold; };
 __global__ void cg_begin_kernel(CGDev* cg, CGBegin b) {
     cg->done = 0; cg->nb_iter = 0; cg->end_cond = 0; cg->it = 0;

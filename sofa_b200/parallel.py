@@ -124,6 +124,15 @@ class DeviceBackend:
         self.x, self.v = self.mo.x, self.mo.v
         self.owned_mask = torch.from_numpy(rm.owned.astype(np.uint8)).to(self.device)
         self._scal = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self.native = False
+
+    def attach_native(self, rm, group=None):
+        """Run the whole distributed step inside the library: NCCL send/recv + allreduce enqueued by libsofa_b200 itself,
+        device-resident CG scalars, one CUDA graph per step (sofab200_node_set_distributed)."""
+        from . import components as C
+        self.comm = C.Communicator(self.ctx, group)
+        self.node.set_distributed(self.comm, rm)
+        self.native = True
 
     def new_vector(self):
         return self.mo.new_vector()
@@ -150,7 +159,7 @@ class DistributedSolverNode:
     CGLinearSolver.inl:73-315 with its scalars all-reduced (two small allreduces and one halo exchange per iteration)."""
 
     def __init__(self, positions, tets, fixed_global, massDensity, youngModulus, poissonRatio, method="large", group=None, ctx=None,
-                 template="B200Vec3f", backend_factory=None, dt=0.01, gravity=(0.0, -9.81, 0.0), rayleighStiffness=0.0, rayleighMass=0.0,
+                 template="B200Vec3f", backend_factory=None, native=True, dt=0.01, gravity=(0.0, -9.81, 0.0), rayleighStiffness=0.0, rayleighMass=0.0,
                  iterations=25, tolerance=1e-5, threshold=1e-5):
         from .topology import diagonal_mass
         self.group = group
@@ -166,6 +175,8 @@ class DistributedSolverNode:
         fixed_local = np.nonzero(fixed_mask[rm.global_ids])[0].astype(np.uint32)
         make = backend_factory or (lambda **kw: DeviceBackend(ctx, template, **kw))
         self.be = be = make(rm=rm, m_pass=m_pass, fixed_local=fixed_local, youngModulus=youngModulus, poissonRatio=poissonRatio, method=method, params=self.p)
+        if native and backend_factory is None:
+            be.attach_native(rm, group)
         self.plan = HaloPlan(rm, be.device)
         self.owner_scale = torch.from_numpy(rm.owned.astype(ndtype)).to(be.device)[:, None]
         self.f, self.b, self.dx = be.new_vector(), be.new_vector(), be.new_vector()
@@ -183,6 +194,9 @@ class DistributedSolverNode:
 
     def apply(self, q, p, m, b, k):
         """q = project((m M + b B + k K) p) over the whole partitioned mesh."""
+        if getattr(self.be, "native", False):
+            self.be.node.apply(q, p, m, b, k)
+            return q
         self.be.add_mbkdx(q, p, m, b, k, project=True)
         halo_exchange_sum(q, self.plan, self.group)
         return q
@@ -223,6 +237,11 @@ class DistributedSolverNode:
     def step(self):
         """EulerImplicitSolver::solve (EulerImplicitSolver.cpp:127-300) on the partitioned mesh."""
         be, P = self.be, self.p
+        if getattr(be, "native", False):      # everything below, inside the library (no host round trip)
+            be.node.step()
+            self.time_step_count += 1
+            self.cg_iterations_total += P["iterations"]     # upper bound; the exact count is last_solve()["iterations"]
+            return None
         h = P["dt"]
         be.compute_force(self.f, be.x)                                     # gravity*m (owner only) + local element forces
         halo_exchange_sum(self.f, self.plan, self.group)

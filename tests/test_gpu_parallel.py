@@ -17,7 +17,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, cfg_name, dtype_name, q_out):
+def _worker(rank, world, port, cfg_name, dtype_name, native, q_out):
     import torch.distributed as dist
     import sofa_b200 as sb
     import sofa_b200.parallel as PAR
@@ -28,7 +28,7 @@ def _worker(rank, world, port, cfg_name, dtype_name, q_out):
         c, pos, hexas, tets, fixed = mesh(cfg_name)
         ctx = sb.Context(rank)
         node = PAR.DistributedSolverNode(pos, tets, fixed, c["density"], c["young"], c["poisson"], "large", ctx=ctx,
-                                         template="B200Vec3f" if dtype_name == "f32" else "B200Vec3d", dt=c["dt"], gravity=c["gravity"],
+                                         template="B200Vec3f" if dtype_name == "f32" else "B200Vec3d", native=native, dt=c["dt"], gravity=c["gravity"],
                                          rayleighStiffness=c["rK"], rayleighMass=c["rM"], iterations=c["iterations"], tolerance=c["tolerance"], threshold=c["threshold"])
         rm = node.rm
         rng = np.random.default_rng(0)
@@ -38,6 +38,8 @@ def _worker(rank, world, port, cfg_name, dtype_name, q_out):
         q_loc = node.apply(node.be.new_vector(), p_loc, 1.001, -0.01, -0.0011)
         q_glob = node.gather_global(q_loc, pos.shape[0])
         its = [node.step() for _ in range(3)]
+        if native:
+            its = [node.be.node.last_solve()["iterations"]] * 3
         x_glob = node.gather_global(node.be.x, pos.shape[0])
         if rank == 0:
             q_out.put(dict(q=q_glob, x=x_glob, its=its))
@@ -45,8 +47,9 @@ def _worker(rank, world, port, cfg_name, dtype_name, q_out):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("native", [True, False])
 @pytest.mark.parametrize("dtype_name", ["f64", "f32"])
-def test_two_gpus_match_single_domain_oracle(dtype_name):
+def test_two_gpus_match_single_domain_oracle(dtype_name, native):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -54,7 +57,7 @@ def test_two_gpus_match_single_domain_oracle(dtype_name):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, cfg, dtype_name, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cfg, dtype_name, native, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = q.get(timeout=600)
