@@ -1,0 +1,54 @@
+"""Host-side input generators of the product (sofa_b200/topology.py) against the oracle's restatement of the reference's
+topology components, and the Gmsh v1 reader against the committed liver fixture."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from sofa_b200 import topology as T
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("n", [(4, 10, 4), (5, 5, 20), (3, 3, 4), (2, 2, 2)])
+def test_grid_and_tessellations_match_reference_order(n):
+    p1, h1 = T.regular_grid(n, (-5, -5, 0), (5, 5, 40)); p2, h2 = O.regular_grid(n, (-5, -5, 0), (5, 5, 40))
+    assert p1.tobytes() == p2.tobytes() and np.array_equal(h1, h2)
+    for mode, om in (("mapping", 0), ("mapping_swapping", 1), ("forcefield", 2)):
+        assert np.array_equal(T.hexas_to_tetras(h1, n, mode), O.hexas_to_tetras(n, om)), mode
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_diagonal_mass_lumping_bit_exact(dtype):
+    n = (4, 5, 9)
+    pos, hexas = T.regular_grid(n, (0, 0, 0), (1, 1.3, 2.7))
+    tets = T.hexas_to_tetras(hexas, n, "mapping_swapping")
+    for elems in (tets, hexas):
+        s = O.OracleScene(dtype, pos); s.set_mass_density(0.2, elems)
+        assert T.diagonal_mass(pos, elems, dtype, mass_density=0.2).tobytes() == s.get("vertexMass").tobytes()
+        s = O.OracleScene(dtype, pos); s.set_total_mass(50.0, elems)
+        assert T.diagonal_mass(pos, elems, dtype, total_mass=50.0).tobytes() == s.get("vertexMass").tobytes()
+
+
+def test_gmsh_v1_reader(tmp_path):
+    m = np.load(os.path.join(G, "liver_mesh.npz"))
+    assert m["positions"].shape == (181, 3) and m["tetrahedra"].shape == (596, 4) and m["tetrahedra"].max() == 180
+    # round trip through a file written in the same $NOD/$ELM format
+    p = tmp_path / "t.msh"
+    with open(p, "w") as fh:
+        fh.write("$NOD\n%d\n" % len(m["positions"]))
+        for i, x in enumerate(m["positions"]):
+            fh.write(f"{i + 1} {float(x[0])!r} {float(x[1])!r} {float(x[2])!r}\n")
+        fh.write("$ENDNOD\n$ELM\n%d\n" % len(m["tetrahedra"]))
+        for i, t in enumerate(m["tetrahedra"]):
+            fh.write(f"{i + 1} 4 1 1 4 {t[0] + 1} {t[1] + 1} {t[2] + 1} {t[3] + 1}\n")
+        fh.write("$ENDELM\n")
+    pos, tets, hexas = T.read_gmsh_v1(str(p))
+    assert np.array_equal(pos, m["positions"]) and np.array_equal(tets, m["tetrahedra"]) and hexas.shape == (0, 8)
+
+
+def test_box_roi_closed_intervals():
+    pos, _ = T.regular_grid((5, 5, 20), (-5, -5, 0), (5, 5, 40))
+    idx = T.box_roi(pos, (-6, -6, -1, 50, 6, 0.1))
+    assert len(idx) == 25 and np.array_equal(idx, O.box_roi(pos, (-6, -6, -1, 50, 6, 0.1)))
