@@ -304,10 +304,15 @@ template <class R> __host__ __device__ inline size_t tile_smem_bytes(int max_tou
 template <class R> __device__ __forceinline__ void tile_phase1(const TileDev<R>& t, int tile, const R* __restrict__ in, typename SVec<R>::T* s_in, uint16_t* s_jds) {
     const uint32_t node_off = t.tile_node_off[tile];
     const int n_touched = int(t.tile_node_off[tile + 1] - node_off);
-    for (int k = threadIdx.x; k < n_touched; k += blockDim.x) {
-        const uint32_t g = t.tile_nodes[node_off + k];
-        const R* p = in + 3 * size_t(g);
-        s_in[k] = SVec<R>::make(p[0], p[1], p[2]);
+    // two nodes per thread and per round: both node ids are requested before either nodal vector (dependent loads overlap)
+    for (int k = threadIdx.x; k < n_touched; k += 2 * blockDim.x) {
+        const int k2 = k + blockDim.x;
+        const uint32_t g1 = t.tile_nodes[node_off + k];
+        const uint32_t g2 = k2 < n_touched ? t.tile_nodes[node_off + k2] : g1;
+        const R* p1 = in + 3 * size_t(g1); const R* p2 = in + 3 * size_t(g2);
+        const R a0 = p1[0], a1 = p1[1], a2 = p1[2], b0 = p2[0], b1 = p2[1], b2 = p2[2];
+        s_in[k] = SVec<R>::make(a0, a1, a2);
+        if (k2 < n_touched) s_in[k2] = SVec<R>::make(b0, b1, b2);
     }
     for (int j = threadIdx.x; j <= t.maxval; j += blockDim.x) s_jds[j] = t.tile_jds[size_t(tile) * (t.maxval + 1) + j];
     __syncthreads();
@@ -332,8 +337,26 @@ template <class R> __device__ __forceinline__ double tile_phase3(const TileDev<R
         R ax, ay, az;
         node_pre(ep, g, ax, ay, az);
         node_mass_v(ep, ep.pre_kind, g, R(pv.x), R(pv.y), R(pv.z), ax, ay, az);
-        if (ep.sign > 0) for (int jj = 0; jj < val; ++jj) { const int s = s_jds[jj] + k; ax += s_slot[s]; ay += s_slot[max_slots + s]; az += s_slot[2 * max_slots + s]; }
-        else             for (int jj = 0; jj < val; ++jj) { const int s = s_jds[jj] + k; ax -= s_slot[s]; ay -= s_slot[max_slots + s]; az -= s_slot[2 * max_slots + s]; }
+        // slots are read four contributions ahead of the adds; the adds themselves stay strictly in element order
+        const bool plus = ep.sign > 0;
+        int jj = 0;
+        for (; jj + 4 <= val; jj += 4) {
+            R cx[4], cy[4], cz[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int s = s_jds[jj + u] + k; cx[u] = s_slot[s]; cy[u] = s_slot[max_slots + s]; cz[u] = s_slot[2 * max_slots + s]; }
+            if (plus) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { ax += cx[u]; ay += cy[u]; az += cz[u]; }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { ax -= cx[u]; ay -= cy[u]; az -= cz[u]; }
+            }
+        }
+        for (; jj < val; ++jj) {
+            const int s = s_jds[jj] + k;
+            if (plus) { ax += s_slot[s]; ay += s_slot[max_slots + s]; az += s_slot[2 * max_slots + s]; }
+            else { ax -= s_slot[s]; ay -= s_slot[max_slots + s]; az -= s_slot[2 * max_slots + s]; }
+        }
         part += node_post_v(ep, g, R(pv.x), R(pv.y), R(pv.z), ax, ay, az);
     }
     return part;
@@ -344,13 +367,13 @@ template <class R> __device__ __forceinline__ double tile_phase3(const TileDev<R
 // batches ahead of the one being consumed, and added ONE BY ONE IN ELEMENT ORDER.  The chunk's jagged-diagonal table
 // sits in shared memory so that the only dependent global loads are node id -> contributions.
 constexpr int kGatherBatch = 8;
-template <class R> __global__ void __launch_bounds__(kGatherChunk) gather_shared_kernel(TileDev<R> d, NodeEpilogue<R> ep) {
-    __shared__ double red[32];
-    __shared__ uint32_t s_jds[1024 + 3 * kGatherBatch];
-    if (ep.cg && ep.cg->done) return;
-    const int chunk = blockIdx.x, k = threadIdx.x;
+// one chunk of kGatherChunk shared nodes, one thread per node; returns the thread's share of the dot product.
+// s_jds: >= d.maxval + 3*kGatherBatch entries of shared memory.  Called by all threads of the CTA (contains barriers).
+template <class R> __device__ __forceinline__ double gather_chunk(const TileDev<R>& d, const NodeEpilogue<R>& ep, int chunk, uint32_t* s_jds) {
+    const int k = threadIdx.x;
+    __syncthreads();   // s_jds may still be in use by the previous chunk
     for (int j = k; j <= d.maxval + 3 * kGatherBatch - 1; j += blockDim.x) s_jds[j] = j <= d.maxval ? d.sh_jds[size_t(chunk) * (d.maxval + 1) + j] : 0u;
-    const uint32_t g = d.sh_nodes[size_t(chunk) * kGatherChunk + k];
+    const uint32_t g = k < kGatherChunk ? d.sh_nodes[size_t(chunk) * kGatherChunk + k] : 0xFFFFFFFFu;
     const int val = g != 0xFFFFFFFFu ? int(d.sh_val[size_t(chunk) * kGatherChunk + k]) : 0;
     const Quad<R>* st = d.stage + d.sh_base[chunk] + k;
     const uint64_t pol = l2_policy_evict_first();
@@ -381,6 +404,13 @@ template <class R> __global__ void __launch_bounds__(kGatherChunk) gather_shared
         }
         part = node_post(ep, g, ax, ay, az);
     }
+    return part;
+}
+template <class R> __global__ void __launch_bounds__(kGatherChunk) gather_shared_kernel(TileDev<R> d, NodeEpilogue<R> ep) {
+    __shared__ double red[32];
+    __shared__ uint32_t s_jds[1024 + 3 * kGatherBatch];
+    if (ep.cg && ep.cg->done) return;
+    const double part = gather_chunk<R>(d, ep, blockIdx.x, s_jds);
     if (ep.dot_kind != DOT_NONE) {
         const double tot = block_sum(part, red);
         finish_dot(ep, tot, red, true);

@@ -74,7 +74,12 @@ template <class R, int MODE> static int hex_launch_mode(HexFF<R>& ff, const HexD
     return SOFAB200_OK;
 }
 
-template <class R> int hex_run(sofab200_hexfem* base, bool dforce, const R* in, R k_factor, NodeEpilogue<R> ep) {
+template <class R> TileDev<R> hex_tiledev(sofab200_hexfem* base) { return static_cast<HexFF<R>*>(base)->dev().t; }
+template TileDev<float> hex_tiledev<float>(sofab200_hexfem*);
+template TileDev<double> hex_tiledev<double>(sofab200_hexfem*);
+
+// skip_gather: the caller sums the shared nodes itself (fused CG tail kernel)
+template <class R> int hex_run(sofab200_hexfem* base, bool dforce, const R* in, R k_factor, NodeEpilogue<R> ep, bool skip_gather) {
     HexFF<R>& ff = *static_cast<HexFF<R>*>(base);
     const HostPlan& plan = ff.h.plan;
     SB_CHECK((!ep.mdx_src || ep.mdx_src == in) && (!ep.dot_with || ep.dot_with == in), "mass / dot operands must be the pass's input vector");
@@ -86,6 +91,7 @@ template <class R> int hex_run(sofab200_hexfem* base, bool dforce, const R* in, 
     else if (ff.method == SOFAB200_HEX_SMALL) SB_TRY((hex_launch_mode<R, HM_F_SMALL>(ff, d, in, ep)));
     else if (ff.method == SOFAB200_HEX_LARGE) SB_TRY((hex_launch_mode<R, HM_F_LARGE>(ff, d, in, ep)));
     else SB_TRY((hex_launch_mode<R, HM_F_POLAR>(ff, d, in, ep)));
+    if (skip_gather) return SOFAB200_OK;
     ep.partial_base = plan.n_tiles;
     ff.ctx->prof_start(1);
     gather_shared_kernel<R><<<plan.n_chunks, kGatherChunk, 0, ff.ctx->stream>>>(d.t, ep);
@@ -94,8 +100,8 @@ template <class R> int hex_run(sofab200_hexfem* base, bool dforce, const R* in, 
     SB_CUDA(cudaGetLastError());
     return SOFAB200_OK;
 }
-template int hex_run<float>(sofab200_hexfem*, bool, const float*, float, NodeEpilogue<float>);
-template int hex_run<double>(sofab200_hexfem*, bool, const double*, double, NodeEpilogue<double>);
+template int hex_run<float>(sofab200_hexfem*, bool, const float*, float, NodeEpilogue<float>, bool);
+template int hex_run<double>(sofab200_hexfem*, bool, const double*, double, NodeEpilogue<double>, bool);
 
 int hex_real(sofab200_hexfem* ff) { return ff->real; }
 size_t hex_nodes(sofab200_hexfem* ff) { return ff->n_nodes; }
@@ -155,20 +161,20 @@ int sofab200_hexfem_add_force(sofab200_hexfem* ff, void* f_dev, const void* x_de
     SB_CHECK(ff && f_dev && x_dev, "null argument");
     if (ff->real == SOFAB200_F32) {
         NodeEpilogue<float> ep{}; ep.init_src = static_cast<float*>(f_dev); ep.out = static_cast<float*>(f_dev); ep.sign = +1;
-        return hex_run<float>(ff, false, static_cast<const float*>(x_dev), 0.f, ep);
+        return hex_run<float>(ff, false, static_cast<const float*>(x_dev), 0.f, ep, false);
     }
     NodeEpilogue<double> ep{}; ep.init_src = static_cast<double*>(f_dev); ep.out = static_cast<double*>(f_dev); ep.sign = +1;
-    return hex_run<double>(ff, false, static_cast<const double*>(x_dev), 0.0, ep);
+    return hex_run<double>(ff, false, static_cast<const double*>(x_dev), 0.0, ep, false);
 }
 int sofab200_hexfem_add_dforce(sofab200_hexfem* ff, void* df_dev, const void* dx_dev, double k_factor) {
     SB_CHECK(ff && df_dev && dx_dev, "null argument");
     SB_CHECK(df_dev != dx_dev, "df and dx must be distinct vectors");
     if (ff->real == SOFAB200_F32) {
         NodeEpilogue<float> ep{}; ep.init_src = static_cast<float*>(df_dev); ep.out = static_cast<float*>(df_dev); ep.sign = -1;
-        return hex_run<float>(ff, true, static_cast<const float*>(dx_dev), float(k_factor), ep);
+        return hex_run<float>(ff, true, static_cast<const float*>(dx_dev), float(k_factor), ep, false);
     }
     NodeEpilogue<double> ep{}; ep.init_src = static_cast<double*>(df_dev); ep.out = static_cast<double*>(df_dev); ep.sign = -1;
-    return hex_run<double>(ff, true, static_cast<const double*>(dx_dev), k_factor, ep);
+    return hex_run<double>(ff, true, static_cast<const double*>(dx_dev), k_factor, ep, false);
 }
 int sofab200_hexfem_get(sofab200_hexfem* ff, const char* what, void* out_host) {
     SB_CHECK(ff && what && out_host, "null argument");

@@ -12,9 +12,11 @@ using namespace sb;
 
 namespace sb {
 // implemented in tet_fem.cu / hex_fem.cu
-template <class R> int tet_run(sofab200_tetfem* ff, bool dforce, const R* in, R k_factor, NodeEpilogue<R> ep);
+template <class R> int tet_run(sofab200_tetfem* ff, bool dforce, const R* in, R k_factor, NodeEpilogue<R> ep, bool skip_gather);
+template <class R> TileDev<R> tet_tiledev(sofab200_tetfem* ff);
+template <class R> TileDev<R> hex_tiledev(sofab200_hexfem* ff);
 int tet_partial_count(sofab200_tetfem* ff);
-template <class R> int hex_run(sofab200_hexfem* ff, bool dforce, const R* in, R k_factor, NodeEpilogue<R> ep);
+template <class R> int hex_run(sofab200_hexfem* ff, bool dforce, const R* in, R k_factor, NodeEpilogue<R> ep, bool skip_gather);
 int hex_partial_count(sofab200_hexfem* ff);
 int tet_real(sofab200_tetfem* ff); size_t tet_nodes(sofab200_tetfem* ff);
 int hex_real(sofab200_hexfem* ff); size_t hex_nodes(sofab200_hexfem* ff);
@@ -148,9 +150,32 @@ template <class R> struct Node : sofab200_node {
         return SOFAB200_OK;
     }
 
-    int fem_run(bool dforce, const R* in, R k_factor, const NodeEpilogue<R>& ep) {
-        if (tet) return tet_run<R>(tet, dforce, in, k_factor, ep);
-        return hex_run<R>(hex, dforce, in, k_factor, ep);
+    int fem_run(bool dforce, const R* in, R k_factor, const NodeEpilogue<R>& ep, bool skip_gather = false) {
+        if (tet) return tet_run<R>(tet, dforce, in, k_factor, ep, skip_gather);
+        return hex_run<R>(hex, dforce, in, k_factor, ep, skip_gather);
+    }
+    // ---- fused CG tail (cooperative kernel): gather + den | x,r update + rho | p update
+    bool fused_tail = true;
+    int tail_grid = 0;
+    DevBuf<double> partials_rho;
+    int cg_tail(R* x, double m, double bfac, double k) {
+        NodeEpilogue<R> ep = make_mbk_ep(q.p, nullptr, p.p, m, bfac, false, 1.0, true, DOT_STORE, cg.p);
+        TileDev<R> td = tet ? tet_tiledev<R>(tet) : hex_tiledev<R>(hex);
+        if (!tail_grid) {
+            int per_sm = 0;
+            SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_tail_kernel<R>, kTailBlock, 0));
+            tail_grid = std::max(1, std::min(per_sm, 4)) * ctx->sm_count;
+            SB_TRY(partials_rho.alloc(size_t(tail_grid) + 8));
+            if (partials.n < size_t(td.n_tiles + tail_grid + 8)) return fail(SOFAB200_ERR_INVALID, "partials buffer too small");
+        }
+        size_t n3 = 3 * n;
+        R* rp = r.p; R* pp = p.p; const R* qp = q.p; CGDev* cgp = cg.p; double* pd = partials.p; int ntp = td.n_tiles; double* pr = partials_rho.p;
+        void* args[] = {&td, &ep, &n3, &x, &rp, &pp, &qp, &cgp, &pd, &ntp, &pr};
+        ctx->prof_start(3);
+        SB_CUDA(cudaLaunchCooperativeKernel((void*)cg_tail_kernel<R>, dim3(tail_grid), dim3(kTailBlock), args, 0, ctx->stream));
+        ctx->prof_stop(3);
+        ctx->launches++;
+        return SOFAB200_OK;
     }
     NodeEpilogue<R> base_ep() {
         NodeEpilogue<R> ep{};
@@ -173,16 +198,20 @@ template <class R> struct Node : sofab200_node {
         return halo_sum(f_out, nullptr);
     }
     // df = init + (m M + b B + k K) d, optionally scaled and projected; dot(out, dot_with) optional
-    int add_mbk(R* out, const R* init, const R* d, double m, double bfac, double k, bool scale, double s, bool project, int dot_kind, CGDev* cgp) {
+    NodeEpilogue<R> make_mbk_ep(R* out, const R* init, const R* d, double m, double bfac, bool scale, double s, bool project, int dot_kind, CGDev* cgp) {
         NodeEpilogue<R> ep = base_ep();
         ep.init_src = init; ep.sign = -1; ep.out = out;
         const double mf = m - bfac * prm.mass_rayleigh_mass;          // MechanicalParams.h:64
-        const double kf = k + bfac * prm.ff_rayleigh_stiffness;       // MechanicalParams.h:62
         set_mass_term(ep, PRE_MDX, d, mf);
         ep.has_scale = scale; ep.scale = R(s);
         ep.fixed = (project && has_fixed) ? fixed.p : nullptr;
         ep.dot_kind = dot_kind; ep.dot_with = d; ep.cg = cgp;
-        if (kf != 0.0 || bfac != 0.0) return fem_run(true, d, R(kf), ep);   // BaseForceField::addMBKdx, BaseForceField.cpp:38-47
+        return ep;
+    }
+    int add_mbk(R* out, const R* init, const R* d, double m, double bfac, double k, bool scale, double s, bool project, int dot_kind, CGDev* cgp, bool skip_gather = false) {
+        NodeEpilogue<R> ep = make_mbk_ep(out, init, d, m, bfac, scale, s, project, dot_kind, cgp);
+        const double kf = k + bfac * prm.ff_rayleigh_stiffness;       // MechanicalParams.h:62
+        if (kf != 0.0 || bfac != 0.0) return fem_run(true, d, R(kf), ep, skip_gather);   // BaseForceField::addMBKdx, BaseForceField.cpp:38-47
         if (dot_kind != DOT_NONE) return fail(SOFAB200_ERR_UNSUPPORTED, "system without a stiffness term is not supported in the CG loop");
         LAUNCH(ctx, (node_only_kernel<R>), vec_grid(n, ctx->sm_count), kVecBlock, n, ep);
         return SOFAB200_OK;
@@ -223,6 +252,17 @@ template <class R> struct Node : sofab200_node {
         }
         LAUNCH(ctx, (vdot_kernel<R>), gd, kVecBlock, n3, bvec, bvec, partials.p, counters.p + 1, int(DF_CG_NORMB), (double*)nullptr, cg.p);
         LAUNCH(ctx, (vdot_kernel<R>), gd, kVecBlock, n3, (const R*)r.p, (const R*)r.p, partials.p, counters.p + 1, int(DF_CG_RHO), (double*)nullptr, cg.p);
+        const double kf_chk = k + bfac * prm.ff_rayleigh_stiffness;
+        if (fused_tail && (kf_chk != 0.0 || bfac != 0.0)) {
+            // two launches per iteration: the element pass, then the fused cooperative tail (which also prepares the next p)
+            SB_CUDA(cudaMemcpyAsync(p.p, r.p, n3 * sizeof(R), cudaMemcpyDeviceToDevice, ctx->stream));   // p = r (first iteration)
+            for (unsigned it = 1; it <= prm.iterations; ++it) {
+                SB_TRY(add_mbk(q.p, nullptr, p.p, m, bfac, k, false, 1.0, true, DOT_STORE, cg.p, true));
+                SB_TRY(cg_tail(x, m, bfac, k));
+            }
+            LAUNCH(ctx, cg_end_kernel, 1, 1, cg.p);
+            return SOFAB200_OK;
+        }
         for (unsigned it = 1; it <= prm.iterations; ++it) {
             LAUNCH(ctx, (cg_p_update_kernel<R>), gd, kVecBlock, n3, p.p, (const R*)r.p, (const CGDev*)cg.p);
             SB_TRY(add_mbk(q.p, nullptr, p.p, m, bfac, k, false, 1.0, true, DOT_CG_DEN, cg.p));  // q = A p ; den = p.q
@@ -305,6 +345,7 @@ template <class R> static int node_create(sofab200_ctx* ctx, size_t n, const sof
     nd->ctx = ctx; nd->real = sizeof(R) == 4 ? SOFAB200_F32 : SOFAB200_F64; nd->n = n;
     nd->tet = d->tetfem; nd->hex = d->hexfem; nd->mass_first = d->mass_first != 0;
     if (const char* env = getenv("SOFAB200_GRAPH")) nd->use_graph = atoi(env) != 0;
+    if (const char* env = getenv("SOFAB200_FUSED_TAIL")) nd->fused_tail = atoi(env) != 0;
     std::memset(&nd->prm, 0, sizeof(nd->prm));
     nd->prm.gravity[1] = -9.81; nd->prm.dt = 0.01; nd->prm.iterations = 25; nd->prm.tolerance = 1e-5; nd->prm.threshold = 1e-5;
     cudaStream_t s = ctx->stream;

@@ -89,7 +89,12 @@ template <class R, int MODE> static int tet_launch_mode(TetFF<R>& ff, const TetD
 }
 
 // Element pass + boundary gather with a caller-provided epilogue (also used by the solver node).
-template <class R> int tet_run(sofab200_tetfem* base, bool dforce, const R* in, R k_factor, NodeEpilogue<R> ep) {
+template <class R> TileDev<R> tet_tiledev(sofab200_tetfem* base) { return static_cast<TetFF<R>*>(base)->dev().t; }
+template TileDev<float> tet_tiledev<float>(sofab200_tetfem*);
+template TileDev<double> tet_tiledev<double>(sofab200_tetfem*);
+
+// skip_gather: the caller sums the shared nodes itself (fused CG tail kernel)
+template <class R> int tet_run(sofab200_tetfem* base, bool dforce, const R* in, R k_factor, NodeEpilogue<R> ep, bool skip_gather) {
     TetFF<R>& ff = *static_cast<TetFF<R>*>(base);
     const HostPlan& plan = ff.h.plan;
     SB_CHECK((!ep.mdx_src || ep.mdx_src == in) && (!ep.dot_with || ep.dot_with == in), "mass / dot operands must be the pass's input vector");
@@ -108,6 +113,7 @@ template <class R> int tet_run(sofab200_tetfem* base, bool dforce, const R* in, 
         default: SB_TRY((tet_launch_mode<R, TM_F_SVD>(ff, d, in, ep))); break;
         }
     }
+    if (skip_gather) return SOFAB200_OK;
     ep.partial_base = plan.n_tiles;
     ff.ctx->prof_start(1);
     gather_shared_kernel<R><<<plan.n_chunks, kGatherChunk, 0, ff.ctx->stream>>>(d.t, ep);
@@ -116,8 +122,8 @@ template <class R> int tet_run(sofab200_tetfem* base, bool dforce, const R* in, 
     SB_CUDA(cudaGetLastError());
     return SOFAB200_OK;
 }
-template int tet_run<float>(sofab200_tetfem*, bool, const float*, float, NodeEpilogue<float>);
-template int tet_run<double>(sofab200_tetfem*, bool, const double*, double, NodeEpilogue<double>);
+template int tet_run<float>(sofab200_tetfem*, bool, const float*, float, NodeEpilogue<float>, bool);
+template int tet_run<double>(sofab200_tetfem*, bool, const double*, double, NodeEpilogue<double>, bool);
 
 int tet_real(sofab200_tetfem* ff) { return ff->real; }
 size_t tet_nodes(sofab200_tetfem* ff) { return ff->n_nodes; }
@@ -182,20 +188,20 @@ int sofab200_tetfem_add_force(sofab200_tetfem* ff, void* f_dev, const void* x_de
     SB_CHECK(ff && f_dev && x_dev, "null argument");
     if (ff->real == SOFAB200_F32) {
         NodeEpilogue<float> ep{}; ep.init_src = static_cast<float*>(f_dev); ep.out = static_cast<float*>(f_dev); ep.sign = +1;
-        return tet_run<float>(ff, false, static_cast<const float*>(x_dev), 0.f, ep);
+        return tet_run<float>(ff, false, static_cast<const float*>(x_dev), 0.f, ep, false);
     }
     NodeEpilogue<double> ep{}; ep.init_src = static_cast<double*>(f_dev); ep.out = static_cast<double*>(f_dev); ep.sign = +1;
-    return tet_run<double>(ff, false, static_cast<const double*>(x_dev), 0.0, ep);
+    return tet_run<double>(ff, false, static_cast<const double*>(x_dev), 0.0, ep, false);
 }
 int sofab200_tetfem_add_dforce(sofab200_tetfem* ff, void* df_dev, const void* dx_dev, double k_factor) {
     SB_CHECK(ff && df_dev && dx_dev, "null argument");
     SB_CHECK(df_dev != dx_dev, "df and dx must be distinct vectors");
     if (ff->real == SOFAB200_F32) {
         NodeEpilogue<float> ep{}; ep.init_src = static_cast<float*>(df_dev); ep.out = static_cast<float*>(df_dev); ep.sign = -1;
-        return tet_run<float>(ff, true, static_cast<const float*>(dx_dev), float(k_factor), ep);
+        return tet_run<float>(ff, true, static_cast<const float*>(dx_dev), float(k_factor), ep, false);
     }
     NodeEpilogue<double> ep{}; ep.init_src = static_cast<double*>(df_dev); ep.out = static_cast<double*>(df_dev); ep.sign = -1;
-    return tet_run<double>(ff, true, static_cast<const double*>(dx_dev), k_factor, ep);
+    return tet_run<double>(ff, true, static_cast<const double*>(dx_dev), k_factor, ep, false);
 }
 int sofab200_tetfem_get(sofab200_tetfem* ff, const char* what, void* out_host) {
     SB_CHECK(ff && what && out_host, "null argument");

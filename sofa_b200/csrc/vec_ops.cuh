@@ -1,6 +1,8 @@
 // MechanicalObject vector operations and the CG vector updates (streaming kernels).
 // Vec3 operations of the reference are componentwise, so the kernels run on the flat 3n array.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "fem_layout.cuh"
 
 namespace sb {
@@ -225,6 +227,89 @@ __global__ void cg_scalar_kernel(CGDev* cg, const double* value, int action) {
     if (cg->done) return;
     if (action == DF_CG_NORMB || action == DF_CG_RHO) dot_finish_action(action, *value, nullptr, cg);
     else cg_after_den(cg, *value);
+}
+
+// ---- fused tail of a CG iteration (cooperative launch, two grid barriers) --------------------------------------------
+//   A  boundary gather of q = A p (shared nodes) + the rest of den = p.q      | grid barrier, every CTA sums the partials
+//   B  alpha = rho/den ; x += alpha p ; r -= alpha q ; partial rho' = r.r     | grid barrier, every CTA sums the partials
+//   C  tolerance test ; beta = rho'/rho ; p = p*beta + r  (the NEXT iteration's direction)
+// Every CTA adds the same partials in the same order, so all take the same branch; CTA 0 records the scalars in CGDev.
+constexpr int kTailBlock = kGatherChunk;
+template <class R> __device__ __forceinline__ double sum_partials_all(const double* partials, int n, double* red, double* bcast) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += __ldcg(partials + i);
+    __syncthreads();
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) *bcast = s;
+    __syncthreads();
+    return *bcast;
+}
+template <class R> __global__ void __launch_bounds__(kTailBlock) cg_tail_kernel(TileDev<R> d, NodeEpilogue<R> ep, size_t n3, R* __restrict__ x, R* __restrict__ r, R* __restrict__ p,
+                                                                                 const R* __restrict__ q, CGDev* cg, double* partials_den, int n_tile_partials, double* partials_rho) {
+    namespace cgp = cooperative_groups;
+    __shared__ double red[32];
+    __shared__ double bcast;
+    __shared__ uint32_t s_jds[1024 + 3 * kGatherBatch];
+    if (cg->done) return;
+    cgp::grid_group grid = cgp::this_grid();
+    // snapshot of the scalars this iteration starts from (CTA 0 rewrites CGDev after each barrier)
+    const double rho = cg->rho, normb = cg->normb, tol = cg->tolerance, thr = cg->threshold;
+    const int it = cg->it;
+    const unsigned tsc = cg->time_step_count, max_iter = cg->max_iter;
+    // ---- A
+    double part = 0.0;
+    for (int chunk = blockIdx.x; chunk < d.n_chunks; chunk += gridDim.x) part += gather_chunk<R>(d, ep, chunk, s_jds);
+    __syncthreads();
+    part = block_sum(part, red);
+    if (threadIdx.x == 0) partials_den[n_tile_partials + blockIdx.x] = part;
+    grid.sync();
+    const double den = sum_partials_all<R>(partials_den, n_tile_partials + int(gridDim.x), red, &bcast);
+    bool stop = false;
+    if (den != 0.0) { if (fabs(den) <= thr && !(it == 1 && tsc == 0)) stop = true; } else stop = true;
+    if (blockIdx.x == 0 && threadIdx.x == 0) cg_after_den(cg, den);
+    if (stop) return;
+    const double alpha_d = rho / den;
+    // ---- B
+    const R alpha = R(alpha_d), malpha = R(-alpha_d);
+    const bool a_one = (alpha_d == 1.0), ma_one = (-alpha_d == 1.0);
+    const size_t stride = size_t(gridDim.x) * blockDim.x, t0 = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    double prr = 0.0;
+    if (sizeof(R) == 4) {
+        const size_t nv = n3 / 4;
+        float4* xv = reinterpret_cast<float4*>(x); float4* rv = reinterpret_cast<float4*>(r);
+        const float4* pv = reinterpret_cast<const float4*>(p); const float4* qv = reinterpret_cast<const float4*>(q);
+        for (size_t i = t0; i < nv; i += stride) {
+            float4 xx = xv[i], rr = rv[i]; const float4 pp = pv[i], qq = __ldcg(qv + i);
+            prr += xr_one<float>(xx.x, rr.x, pp.x, qq.x, alpha, malpha, a_one, ma_one);
+            prr += xr_one<float>(xx.y, rr.y, pp.y, qq.y, alpha, malpha, a_one, ma_one);
+            prr += xr_one<float>(xx.z, rr.z, pp.z, qq.z, alpha, malpha, a_one, ma_one);
+            prr += xr_one<float>(xx.w, rr.w, pp.w, qq.w, alpha, malpha, a_one, ma_one);
+            xv[i] = xx; rv[i] = rr;
+        }
+        for (size_t i = nv * 4 + t0; i < n3; i += stride) { R qq = __ldcg(q + i); prr += xr_one<R>(x[i], r[i], p[i], qq, alpha, malpha, a_one, ma_one); }
+    } else {
+        for (size_t i = t0; i < n3; i += stride) { R qq = __ldcg(q + i); prr += xr_one<R>(x[i], r[i], p[i], qq, alpha, malpha, a_one, ma_one); }
+    }
+    __syncthreads();
+    prr = block_sum(prr, red);
+    if (threadIdx.x == 0) partials_rho[blockIdx.x] = prr;
+    grid.sync();
+    const double rho_new = sum_partials_all<R>(partials_rho, int(gridDim.x), red, &bcast);
+    const int it2 = it + 1;
+    bool stop2 = unsigned(it2) > max_iter;
+    if (!stop2) { const double err = sqrt(rho_new) / normb; if (err <= tol && !(it2 == 1 && tsc == 0)) stop2 = true; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) cg_after_rho(cg, rho_new);
+    if (stop2) return;
+    // ---- C : p = p*beta + r   (cgstep_beta)
+    const R beta = R(rho_new / rho);
+    if (sizeof(R) == 4) {
+        const size_t nv = n3 / 4;
+        float4* pv = reinterpret_cast<float4*>(p); const float4* rv = reinterpret_cast<const float4*>(r);
+        for (size_t i = t0; i < nv; i += stride) { float4 a = pv[i]; v4_avf(a, rv[i], float(beta)); pv[i] = a; }
+        for (size_t i = nv * 4 + t0; i < n3; i += stride) { R t = p[i]; t *= beta; t += r[i]; p[i] = t; }
+    } else {
+        for (size_t i = t0; i < n3; i += stride) { R t = p[i]; t *= beta; t += r[i]; p[i] = t; }
+    }
 }
 
 struct CGBegin { unsigned max_iter; double tolerance, threshold; };
