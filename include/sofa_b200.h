@@ -80,6 +80,12 @@ uint64_t sofab200_ctx_launch_count(const sofab200_ctx* ctx);
 #define SOFAB200_PROFILE_CLASSES 4
 int sofab200_ctx_profile_begin(sofab200_ctx* ctx);
 int sofab200_ctx_profile_end(sofab200_ctx* ctx, double* total_ms, uint64_t* count);
+/* In-kernel phase timestamps (diagnostics; no reference counterpart).  After trace_begin every tile CTA of the solver
+ * node's element passes and every CTA of the fused CG tail records %globaltimer (ns) at its phase boundaries, 16 words per
+ * CTA (word 7 = SM id); later launches overwrite earlier ones.  trace_end (sync) copies the first n words to `out` and
+ * turns tracing off.  Words [0, 4096*16): element pass; [4096*16, 2*4096*16): CG loop. */
+int sofab200_ctx_trace_begin(sofab200_ctx* ctx);
+int sofab200_ctx_trace_end(sofab200_ctx* ctx, uint64_t* out, size_t n);
 
 /* ------------------------------------------------------------------------------------------------ */
 /* MechanicalObject<B200Vec3Types> vector operations  -- [MO]                                       */

@@ -59,6 +59,8 @@ SYMBOLS = {
     "sofab200_ctx_launch_count": (_U64, [_P]),
     "sofab200_ctx_profile_begin": (_I, [_P]),
     "sofab200_ctx_profile_end": (_I, [_P, C.POINTER(_D), C.POINTER(_U64)]),
+    "sofab200_ctx_trace_begin": (_I, [_P]),
+    "sofab200_ctx_trace_end": (_I, [_P, C.POINTER(_U64), _SZ]),
     "sofab200_mo_vop": (_I, [_P, _I, _SZ, _P, _P, _P, _D]),
     "sofab200_mo_vdot": (_I, [_P, _I, _SZ, _P, _P, C.POINTER(_D)]),
     "sofab200_mo_vdot_dev": (_I, [_P, _I, _SZ, _P, _P, _P, _P]),

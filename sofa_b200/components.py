@@ -68,6 +68,16 @@ class Context:
         check(self.L.sofab200_ctx_profile_end(self.h, ms, cnt))
         return {k: dict(ms=ms[i], launches=int(cnt[i])) for i, k in enumerate(self.PROFILE_CLASSES)}
 
+    def trace_begin(self):
+        check(self.L.sofab200_ctx_trace_begin(self.h))
+
+    def trace_end(self):
+        """(element_pass[4096, 16], cg_tail[4096, 16]) uint64 %globaltimer ns per CTA and phase boundary; column 7 = SM id."""
+        import numpy as np
+        out = np.zeros(2 * 4096 * 16, dtype=np.uint64)
+        check(self.L.sofab200_ctx_trace_end(self.h, out.ctypes.data_as(C.POINTER(C.c_uint64)), out.size))
+        return out[:4096 * 16].reshape(4096, 16), out[4096 * 16:].reshape(4096, 16)
+
     def __del__(self):
         try:
             self.L.sofab200_ctx_destroy(self.h)

@@ -84,6 +84,8 @@ struct sofab200_ctx {
         if (!profiling) return;
         cudaEventRecord(prof[cls].back().second, stream);
     }
+    // optional in-kernel timestamps (sofab200_ctx_trace_begin/end): [CTA][8] globaltimer values of the last launch
+    sb::DevBuf<unsigned long long> trace;
     // scratch for reductions (vdot): partial sums + result + counter
     sb::DevBuf<double> red_partials;
     sb::DevBuf<double> red_result;

@@ -61,6 +61,19 @@ int sofab200_ctx_synchronize(sofab200_ctx* ctx) {
     return SOFAB200_OK;
 }
 uint64_t sofab200_ctx_launch_count(const sofab200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int sofab200_ctx_trace_begin(sofab200_ctx* ctx) {
+    SB_CHECK(ctx != nullptr, "ctx is null");
+    SB_TRY(ctx->trace.alloc(size_t(2) * 4096 * 16));
+    return ctx->trace.zero(ctx->stream);
+}
+int sofab200_ctx_trace_end(sofab200_ctx* ctx, uint64_t* out, size_t n) {
+    SB_CHECK(ctx && out, "null argument");
+    SB_CHECK(ctx->trace.p != nullptr, "trace_begin was not called");
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    SB_CUDA(cudaMemcpy(out, ctx->trace.p, std::min(n, ctx->trace.n) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    ctx->trace.release();
+    return SOFAB200_OK;
+}
 int sofab200_ctx_profile_begin(sofab200_ctx* ctx) {
     SB_CHECK(ctx != nullptr, "ctx is null");
     for (auto& v : ctx->prof) { for (auto& e : v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } v.clear(); }

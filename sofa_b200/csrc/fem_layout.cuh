@@ -66,7 +66,19 @@ template <class R> struct NodeEpilogue {
     unsigned* counter;      // last-CTA detection (boundary kernel only)
     double* dot_result;
     CGDev* cg;
+    unsigned long long* trace;   // diagnostics: per-CTA phase timestamps (null = off)
 };
+constexpr int kTraceWords = 16;          // words per CTA
+constexpr int kTraceTail = 4096 * kTraceWords;   // the CG tail kernel's records start here
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ void trace_mark(unsigned long long* trace, int base, int i) {
+    if (trace && threadIdx.x == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        trace[base + blockIdx.x * kTraceWords + i] = t;
+        if (i == 0) { unsigned sm; asm volatile("mov.u32 %0, %smid;" : "=r"(sm)); trace[base + blockIdx.x * kTraceWords + 7] = sm; }
+    }
+}
+#endif
 
 template <class R> struct TileDev {
     int n_nodes, n_elems, n_tiles, tile_e, maxval;
@@ -80,8 +92,7 @@ template <class R> struct TileDev {
     int n_shared, n_chunks;
     const uint32_t* sh_nodes;        // [n_chunks*kGatherChunk] (padded with 0xFFFFFFFF)
     const uint16_t* sh_val;
-    const uint32_t* sh_jds;          // [n_chunks][maxval+1]
-    const uint32_t* sh_base;         // [n_chunks]
+    const uint32_t* sh_base;         // [n_chunks] first entry of the chunk's ELL block: contribution j of node k at sh_base + j*kGatherChunk + k
     Quad<R>* stage;                  // one (x,y,z,-) quad per staged contribution: a single 16-byte store / load
     size_t stage_n;
 };
@@ -189,15 +200,17 @@ template <class R> HD void node_pre(const NodeEpilogue<R>& ep, uint32_t g, R& ax
     else { ax = R(0); ay = R(0); az = R(0); }
 }
 // (vx,vy,vz): the node's entry of mdx_src / dot_with when the caller already holds it (shared-memory copy of the input vector)
-template <class R> HD void node_mass_v(const NodeEpilogue<R>& ep, int kind, uint32_t g, R vx, R vy, R vz, R& ax, R& ay, R& az) {
+// m: the node's vertexMass (already loaded)
+template <class R> HD void node_mass_m(const NodeEpilogue<R>& ep, int kind, R m, R vx, R vy, R vz, R& ax, R& ay, R& az) {
     if (kind == PRE_GRAVITY) {  // DiagonalMass::addForce: f[i] += theGravity*masses[i]
-        const R m = ep.mass[g];
         ax += ep.gx * m; ay += ep.gy * m; az += ep.gz * m;
     } else if (kind == PRE_MDX) {  // DiagonalMass::addMDx
-        const R m = ep.mass[g];
         if (ep.mass_factor_is_one) { ax += vx * m; ay += vy * m; az += vz * m; }
         else { ax += (vx * m) * ep.mass_factor; ay += (vy * m) * ep.mass_factor; az += (vz * m) * ep.mass_factor; }
     }
+}
+template <class R> HD void node_mass_v(const NodeEpilogue<R>& ep, int kind, uint32_t g, R vx, R vy, R vz, R& ax, R& ay, R& az) {
+    if (kind == PRE_GRAVITY || kind == PRE_MDX) node_mass_m(ep, kind, ep.mass[g], vx, vy, vz, ax, ay, az);
 }
 template <class R> HD void node_mass(const NodeEpilogue<R>& ep, int kind, uint32_t g, R& ax, R& ay, R& az) {
     R vx = 0, vy = 0, vz = 0;
@@ -209,6 +222,15 @@ template <class R> HD double node_post_v(const NodeEpilogue<R>& ep, uint32_t g, 
     node_mass_v(ep, ep.post_kind, g, vx, vy, vz, ax, ay, az);
     if (ep.has_scale) { ax *= ep.scale; ay *= ep.scale; az *= ep.scale; }
     if (ep.fixed && ep.fixed[g]) { ax = R(0); ay = R(0); az = R(0); }
+    ep.out[3 * size_t(g)] = ax; ep.out[3 * size_t(g) + 1] = ay; ep.out[3 * size_t(g) + 2] = az;
+    if (ep.dot_kind != DOT_NONE) return double(ax) * double(vx) + double(ay) * double(vy) + double(az) * double(vz);
+    return 0.0;
+}
+// same with the node's mass and fixed flag already loaded
+template <class R> HD double node_post_m(const NodeEpilogue<R>& ep, uint32_t g, R m, bool is_fixed, R vx, R vy, R vz, R ax, R ay, R az) {
+    node_mass_m(ep, ep.post_kind, m, vx, vy, vz, ax, ay, az);
+    if (ep.has_scale) { ax *= ep.scale; ay *= ep.scale; az *= ep.scale; }
+    if (is_fixed) { ax = R(0); ay = R(0); az = R(0); }
     ep.out[3 * size_t(g)] = ax; ep.out[3 * size_t(g) + 1] = ay; ep.out[3 * size_t(g) + 2] = az;
     if (ep.dot_kind != DOT_NONE) return double(ax) * double(vx) + double(ay) * double(vy) + double(az) * double(vz);
     return 0.0;
@@ -362,55 +384,60 @@ template <class R> __device__ __forceinline__ double tile_phase3(const TileDev<R
     return part;
 }
 
-// ---- boundary kernel: sums the HBM-staged contributions of the shared nodes -------------------------------
-// One thread per node.  The node's contributions are fetched in batches of kGatherBatch independent 16-byte loads, two
-// batches ahead of the one being consumed, and added ONE BY ONE IN ELEMENT ORDER.  The chunk's jagged-diagonal table
-// sits in shared memory so that the only dependent global loads are node id -> contributions.
+// ---- shared nodes: ordered sum of the staged contributions ---------------------------------------------------------
+// One thread per node.  The node's contributions are fetched in batches of kGatherBatch independent 16-byte loads, three
+// batches in flight, and added ONE BY ONE IN ELEMENT ORDER.  st: the node's first staged entry (stride kGatherChunk).
 constexpr int kGatherBatch = 8;
-// one chunk of kGatherChunk shared nodes, one thread per node; returns the thread's share of the dot product.
-// s_jds: >= d.maxval + 3*kGatherBatch entries of shared memory.  Called by all threads of the CTA (contains barriers).
-template <class R> __device__ __forceinline__ double gather_chunk(const TileDev<R>& d, const NodeEpilogue<R>& ep, int chunk, uint32_t* s_jds) {
-    const int k = threadIdx.x;
-    __syncthreads();   // s_jds may still be in use by the previous chunk
-    for (int j = k; j <= d.maxval + 3 * kGatherBatch - 1; j += blockDim.x) s_jds[j] = j <= d.maxval ? d.sh_jds[size_t(chunk) * (d.maxval + 1) + j] : 0u;
-    const uint32_t g = k < kGatherChunk ? d.sh_nodes[size_t(chunk) * kGatherChunk + k] : 0xFFFFFFFFu;
-    const int val = g != 0xFFFFFFFFu ? int(d.sh_val[size_t(chunk) * kGatherChunk + k]) : 0;
+template <class R> __device__ __forceinline__ void gather_load(Quad<R> (&b)[kGatherBatch], const Quad<R>* st, int j, int val, uint64_t pol) {
+    const Quad<R> zero{R(0), R(0), R(0), R(0)};
+#pragma unroll
+    for (int u = 0; u < kGatherBatch; ++u) b[u] = (j + u < val) ? stage_load(st + size_t(j + u) * kGatherChunk, pol) : zero;
+}
+template <class R> __device__ __forceinline__ void gather_add(const Quad<R> (&b)[kGatherBatch], int j, int val, bool plus, R& ax, R& ay, R& az) {
+#pragma unroll
+    for (int u = 0; u < kGatherBatch; ++u) {
+        if (j + u < val) {
+            if (plus) { ax += b[u].a; ay += b[u].b; az += b[u].c; } else { ax -= b[u].a; ay -= b[u].b; az -= b[u].c; }
+        }
+    }
+}
+// first two batches are requested by the caller as early as possible (gather_load b0 @0, b1 @kGatherBatch)
+template <class R> __device__ __forceinline__ void gather_sum(Quad<R> (&b0)[kGatherBatch], Quad<R> (&b1)[kGatherBatch], const Quad<R>* st, int val, bool plus,
+                                                              R& ax, R& ay, R& az, uint64_t pol) {
+    constexpr int B = kGatherBatch;
+    Quad<R> b2[B];
+    gather_load<R>(b2, st, 2 * B, val, pol);
+    for (int j0 = 0; j0 < val; j0 += 3 * B) {
+        gather_add<R>(b0, j0, val, plus, ax, ay, az);
+        if (j0 + B >= val) break;
+        gather_load<R>(b0, st, j0 + 3 * B, val, pol);
+        gather_add<R>(b1, j0 + B, val, plus, ax, ay, az);
+        if (j0 + 2 * B >= val) break;
+        gather_load<R>(b1, st, j0 + 4 * B, val, pol);
+        gather_add<R>(b2, j0 + 2 * B, val, plus, ax, ay, az);
+        gather_load<R>(b2, st, j0 + 5 * B, val, pol);
+    }
+}
+// node k of `chunk`; returns the node's share of the dot product
+template <class R> __device__ __forceinline__ double gather_chunk(const TileDev<R>& d, const NodeEpilogue<R>& ep, int chunk, int k) {
+    const uint32_t g = d.sh_nodes[size_t(chunk) * kGatherChunk + k];
+    if (g == 0xFFFFFFFFu) return 0.0;
+    const int val = int(d.sh_val[size_t(chunk) * kGatherChunk + k]);
     const Quad<R>* st = d.stage + d.sh_base[chunk] + k;
     const uint64_t pol = l2_policy_evict_first();
-    __syncthreads();
-    double part = 0.0;
-    if (g != 0xFFFFFFFFu) {
-        const Quad<R> zero{R(0), R(0), R(0), R(0)};
-        Quad<R> b0[kGatherBatch], b1[kGatherBatch], b2[kGatherBatch];
-#pragma unroll
-        for (int u = 0; u < kGatherBatch; ++u) b0[u] = (u < val) ? stage_load(st + s_jds[u], pol) : zero;
-#pragma unroll
-        for (int u = 0; u < kGatherBatch; ++u) b1[u] = (kGatherBatch + u < val) ? stage_load(st + s_jds[kGatherBatch + u], pol) : zero;
-        R ax, ay, az;
-        node_pre(ep, g, ax, ay, az);
-        node_mass(ep, ep.pre_kind, g, ax, ay, az);
-        const bool plus = ep.sign > 0;
-        for (int j0 = 0; j0 < val; j0 += kGatherBatch) {
-#pragma unroll
-            for (int u = 0; u < kGatherBatch; ++u) { const int j = j0 + 2 * kGatherBatch + u; b2[u] = (j < val) ? stage_load(st + s_jds[j], pol) : zero; }
-#pragma unroll
-            for (int u = 0; u < kGatherBatch; ++u) {
-                if (j0 + u < val) {
-                    if (plus) { ax += b0[u].a; ay += b0[u].b; az += b0[u].c; } else { ax -= b0[u].a; ay -= b0[u].b; az -= b0[u].c; }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kGatherBatch; ++u) { b0[u] = b1[u]; b1[u] = b2[u]; }
-        }
-        part = node_post(ep, g, ax, ay, az);
-    }
-    return part;
+    Quad<R> b0[kGatherBatch], b1[kGatherBatch];
+    gather_load<R>(b0, st, 0, val, pol);
+    gather_load<R>(b1, st, kGatherBatch, val, pol);
+    R ax, ay, az;
+    node_pre(ep, g, ax, ay, az);
+    node_mass(ep, ep.pre_kind, g, ax, ay, az);
+    gather_sum<R>(b0, b1, st, val, ep.sign > 0, ax, ay, az, pol);
+    return node_post(ep, g, ax, ay, az);
 }
 template <class R> __global__ void __launch_bounds__(kGatherChunk) gather_shared_kernel(TileDev<R> d, NodeEpilogue<R> ep) {
     __shared__ double red[32];
-    __shared__ uint32_t s_jds[1024 + 3 * kGatherBatch];
     if (ep.cg && ep.cg->done) return;
-    const double part = gather_chunk<R>(d, ep, blockIdx.x, s_jds);
+    const double part = gather_chunk<R>(d, ep, blockIdx.x, threadIdx.x);
     if (ep.dot_kind != DOT_NONE) {
         const double tot = block_sum(part, red);
         finish_dot(ep, tot, red, true);

@@ -21,7 +21,7 @@ template <class R> struct HexFF : sofab200_hexfem {
     DevBuf<uint32_t> orig, kidx, tile_kuniq;
     DevBuf<Quad<R>> r0, r1, r2, x0;
     DevBuf<R> ktab;
-    DevBuf<uint32_t> tile_node_off, tile_nodes, tile_nint, sh_nodes, sh_jds, sh_base;
+    DevBuf<uint32_t> tile_node_off, tile_nodes, tile_nint, sh_nodes, sh_base;
     DevBuf<uint16_t> tile_val, tile_jds, sh_val;
     DevBuf<Quad<R>> stage;
     DevBuf<R> rot_export;
@@ -31,7 +31,7 @@ template <class R> struct HexFF : sofab200_hexfem {
         HexDev<R> d;
         d.t.n_nodes = int(n_nodes); d.t.n_elems = int(n_hexas); d.t.n_tiles = plan.n_tiles; d.t.tile_e = plan.tile_e; d.t.maxval = plan.maxval;
         d.t.tile_node_off = tile_node_off.p; d.t.tile_nodes = tile_nodes.p; d.t.tile_nint = tile_nint.p; d.t.tile_val = tile_val.p; d.t.tile_jds = tile_jds.p;
-        d.t.n_shared = plan.n_shared; d.t.n_chunks = plan.n_chunks; d.t.sh_nodes = sh_nodes.p; d.t.sh_val = sh_val.p; d.t.sh_jds = sh_jds.p; d.t.sh_base = sh_base.p;
+        d.t.n_shared = plan.n_shared; d.t.n_chunks = plan.n_chunks; d.t.sh_nodes = sh_nodes.p; d.t.sh_val = sh_val.p; d.t.sh_base = sh_base.p;
         d.t.stage = stage.p; d.t.stage_n = plan.stage_n;
         d.lnode = lnode.p; d.slot_a = slot_a.p; d.slot_b = slot_b.p; d.r0 = r0.p; d.r1 = r1.p; d.r2 = r2.p;
         d.kidx = kidx.p; d.ktab = ktab.p; d.tile_kuniq = tile_kuniq.p; d.x0 = x0.p; d.n_slots = size_t(plan.n_tiles) * plan.tile_e;
@@ -49,7 +49,7 @@ template <class R> static int hex_upload(HexFF<R>& ff) {
     SB_TRY(ff.kidx.upload(H.kidx, s)); SB_TRY(ff.tile_kuniq.upload(H.tile_kuniq, s)); SB_TRY(ff.ktab.upload(H.ktab, s));
     SB_TRY(ff.tile_node_off.upload(P.tile_node_off, s)); SB_TRY(ff.tile_nodes.upload(P.tile_nodes, s)); SB_TRY(ff.tile_nint.upload(P.tile_nint, s));
     SB_TRY(ff.tile_val.upload(P.tile_val, s)); SB_TRY(ff.tile_jds.upload(P.tile_jds, s));
-    SB_TRY(ff.sh_nodes.upload(P.sh_nodes, s)); SB_TRY(ff.sh_val.upload(P.sh_val, s)); SB_TRY(ff.sh_jds.upload(P.sh_jds, s)); SB_TRY(ff.sh_base.upload(P.sh_base, s));
+    SB_TRY(ff.sh_nodes.upload(P.sh_nodes, s)); SB_TRY(ff.sh_val.upload(P.sh_val, s)); SB_TRY(ff.sh_base.upload(P.sh_base, s));
     SB_TRY(ff.stage.alloc(P.stage_n)); SB_TRY(ff.stage.zero(s));
     SB_CUDA(cudaStreamSynchronize(s));
     ff.n_unique = H.ktab.size() / 576;

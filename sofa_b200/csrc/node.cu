@@ -13,6 +13,7 @@ using namespace sb;
 namespace sb {
 // implemented in tet_fem.cu / hex_fem.cu
 template <class R> int tet_run(sofab200_tetfem* ff, bool dforce, const R* in, R k_factor, NodeEpilogue<R> ep, bool skip_gather);
+template <class R> int tet_cg_persistent(sofab200_tetfem* ff, R k_factor, PersistCG<R> a, size_t part_capacity);
 template <class R> TileDev<R> tet_tiledev(sofab200_tetfem* ff);
 template <class R> TileDev<R> hex_tiledev(sofab200_hexfem* ff);
 int tet_partial_count(sofab200_tetfem* ff);
@@ -156,6 +157,9 @@ template <class R> struct Node : sofab200_node {
     }
     // ---- fused CG tail (cooperative kernel): gather + den | x,r update + rho | p update
     bool fused_tail = true;
+    bool persistent = true;      // SOFAB200_CG_PERSISTENT=0 selects the multi-kernel loop
+    DevBuf<R> p2;
+    DevBuf<unsigned long long> sync_slots;
     int tail_grid = 0;
     DevBuf<double> partials_rho;
     int cg_tail(R* x, double m, double bfac, double k) {
@@ -179,7 +183,7 @@ template <class R> struct Node : sofab200_node {
     }
     NodeEpilogue<R> base_ep() {
         NodeEpilogue<R> ep{};
-        ep.mass = mass.p; ep.partials = partials.p; ep.counter = counters.p; ep.cg = nullptr;
+        ep.mass = mass.p; ep.partials = partials.p; ep.counter = counters.p; ep.cg = nullptr; ep.trace = ctx->trace.p;
         return ep;
     }
     void set_mass_term(NodeEpilogue<R>& ep, int kind, const R* src, double factor) {
@@ -253,6 +257,20 @@ template <class R> struct Node : sofab200_node {
         LAUNCH(ctx, (vdot_kernel<R>), gd, kVecBlock, n3, bvec, bvec, partials.p, counters.p + 1, int(DF_CG_NORMB), (double*)nullptr, cg.p);
         LAUNCH(ctx, (vdot_kernel<R>), gd, kVecBlock, n3, (const R*)r.p, (const R*)r.p, partials.p, counters.p + 1, int(DF_CG_RHO), (double*)nullptr, cg.p);
         const double kf_chk = k + bfac * prm.ff_rayleigh_stiffness;
+        if (persistent && tet && (kf_chk != 0.0 || bfac != 0.0)) {
+            // the whole loop in one cooperative launch (cg_persist.cuh)
+            if (!p2.p) SB_TRY(p2.alloc(n3));
+            if (!sync_slots.p) SB_TRY(sync_slots.alloc(3 * 2048 + 2));
+            PersistCG<R> a;
+            a.ep = make_mbk_ep(q.p, nullptr, p.p, m, bfac, false, 1.0, true, DOT_STORE, cg.p);
+            a.x = x; a.r = r.p; a.p0 = p.p; a.p1 = p2.p; a.n3 = n3; a.cg = cg.p; a.sync = sync_slots.p;
+            a.debug = 0; if (const char* env = getenv("SOFAB200_DEBUG_MODE")) a.debug = atoi(env);
+            SB_CUDA(cudaMemsetAsync(sync_slots.p, 0, sync_slots.n * sizeof(unsigned long long), ctx->stream));
+            const int rc = tet_cg_persistent<R>(tet, R(kf_chk), a, sync_slots.n);
+            if (rc == SOFAB200_OK) { ctx->launches++; LAUNCH(ctx, cg_end_kernel, 1, 1, cg.p); return SOFAB200_OK; }
+            if (rc != kPersistNotEligible) return rc;
+            persistent = false;      // this mesh does not fit: multi-kernel loop from now on
+        }
         if (fused_tail && (kf_chk != 0.0 || bfac != 0.0)) {
             // two launches per iteration: the element pass, then the fused cooperative tail (which also prepares the next p)
             SB_CUDA(cudaMemcpyAsync(p.p, r.p, n3 * sizeof(R), cudaMemcpyDeviceToDevice, ctx->stream));   // p = r (first iteration)
@@ -273,7 +291,7 @@ template <class R> struct Node : sofab200_node {
     }
     // EulerImplicitSolver::solve, replayed from a captured CUDA graph once the same (x, v, params) have been seen twice
     int step(R* x, R* v) {
-        if (!use_graph || ctx->profiling) return step_direct(x, v);
+        if (!use_graph || ctx->profiling || ctx->trace.p) return step_direct(x, v);
         const bool same = sg.x == x && sg.v == v && std::memcmp(&sg.prm, &prm, sizeof(prm)) == 0;
         if (!same) {
             if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; }
@@ -346,6 +364,7 @@ template <class R> static int node_create(sofab200_ctx* ctx, size_t n, const sof
     nd->tet = d->tetfem; nd->hex = d->hexfem; nd->mass_first = d->mass_first != 0;
     if (const char* env = getenv("SOFAB200_GRAPH")) nd->use_graph = atoi(env) != 0;
     if (const char* env = getenv("SOFAB200_FUSED_TAIL")) nd->fused_tail = atoi(env) != 0;
+    if (const char* env = getenv("SOFAB200_CG_PERSISTENT")) nd->persistent = atoi(env) != 0;
     std::memset(&nd->prm, 0, sizeof(nd->prm));
     nd->prm.gravity[1] = -9.81; nd->prm.dt = 0.01; nd->prm.iterations = 25; nd->prm.tolerance = 1e-5; nd->prm.threshold = 1e-5;
     cudaStream_t s = ctx->stream;

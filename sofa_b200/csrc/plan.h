@@ -22,11 +22,10 @@ struct HostPlan {
     int n_shared = 0, n_chunks = 0;
     std::vector<uint32_t> sh_nodes;       // [n_chunks*chunk]
     std::vector<uint16_t> sh_val;
-    std::vector<uint32_t> sh_jds;         // [n_chunks][maxval+1]
-    std::vector<uint32_t> sh_base;        // [n_chunks]
+    std::vector<uint32_t> sh_base;        // [n_chunks] first staging entry of the chunk's ELL block
     size_t stage_n = 0;
-    int max_touched = 0, max_slots = 0;
-    size_t n_interior = 0, n_staged_corners = 0;
+    int max_touched = 0, max_slots = 0, max_int = 1;
+    size_t n_interior = 0, n_staged_corners = 0, n_demoted = 0;
 };
 
 inline uint64_t morton_spread(uint64_t v) {  // 21 bits -> every third bit
@@ -41,8 +40,11 @@ inline uint64_t morton_spread(uint64_t v) {  // 21 bits -> every third bit
 
 // elems: n_elems x npe node indices (original topology order); pos: 3*n_nodes doubles (rest positions).
 // Returns "" or an error text.
+// smem_limit / sv_bytes / slot_bytes (optional): shared-memory budget of a tile CTA, bytes of one staged nodal vector and of
+// one slot.  When a tile's interior nodes need more slots than fit, its highest-valence interior nodes are demoted to
+// shared nodes (their contributions go through the HBM/L2 staging buffer instead), so any tile size can be made to fit.
 inline std::string build_plan(HostPlan& P, int n_nodes, int n_elems, int npe, const uint32_t* elems, const double* pos,
-                              int tile_e, int chunk, uint32_t stage_flag) {
+                              int tile_e, int chunk, uint32_t stage_flag, size_t smem_limit = 0, size_t sv_bytes = 0, size_t slot_bytes = 0) {
     P = HostPlan();
     P.n_nodes = n_nodes; P.n_elems = n_elems; P.npe = npe; P.tile_e = tile_e;
     P.n_tiles = std::max(1, (n_elems + tile_e - 1) / tile_e);
@@ -101,6 +103,35 @@ inline std::string build_plan(HostPlan& P, int n_nodes, int n_elems, int npe, co
     }
     std::vector<std::vector<uint32_t>> tile_int(P.n_tiles);
     for (int i = 0; i < n_nodes; ++i) if (interior_tile[i] >= 0) tile_int[interior_tile[i]].push_back(uint32_t(i));
+    if (smem_limit) {
+        // nodes touched per tile (independent of the classification) -> slot budget -> demotion
+        std::vector<uint32_t> mark(n_nodes, 0xFFFFFFFFu);
+        size_t max_touched = 1;
+        for (int t = 0; t < P.n_tiles; ++t) {
+            size_t cnt = 0;
+            const size_t s0 = size_t(t) * tile_e, s1 = std::min(n_slots, s0 + tile_e);
+            for (size_t s = s0; s < s1; ++s) {
+                const uint32_t e = P.order[s];
+                if (e == 0xFFFFFFFFu) continue;
+                for (int c = 0; c < npe; ++c) { const uint32_t n = elems[size_t(e) * npe + c]; if (mark[n] != uint32_t(t)) { mark[n] = uint32_t(t); ++cnt; } }
+            }
+            max_touched = std::max(max_touched, cnt);
+        }
+        const size_t in_bytes = (sv_bytes * max_touched + 15) & ~size_t(15);
+        if (in_bytes + slot_bytes * size_t(maxval) > smem_limit) return "tile touches too many nodes for shared memory; use a smaller tile";
+        const size_t budget = std::min<size_t>(65535, (smem_limit - in_bytes) / slot_bytes);
+        for (int t = 0; t < P.n_tiles; ++t) {
+            std::vector<uint32_t>& in = tile_int[t];
+            auto val = [&](uint32_t n) { return size_t(inc_off[n + 1] - inc_off[n]); };
+            std::stable_sort(in.begin(), in.end(), [&](uint32_t a, uint32_t b) { return val(a) > val(b); });
+            size_t total = 0;
+            for (uint32_t n : in) total += val(n);
+            size_t drop = 0;
+            while (total > budget && drop < in.size()) { total -= val(in[drop]); interior_tile[in[drop]] = -1; ++drop; }
+            in.erase(in.begin(), in.begin() + drop);
+            P.n_demoted += drop;
+        }
+    }
 
     std::vector<uint32_t> corner_slot(size_t(n_elems) * npe, 0);
     std::vector<int32_t> local_idx(n_nodes, -1);
@@ -130,9 +161,11 @@ inline std::string build_plan(HostPlan& P, int n_nodes, int n_elems, int npe, co
             local_idx[n] = int32_t(k);
             P.tile_nodes.push_back(n);
             P.tile_val.push_back(uint16_t(val(n)));
+
             for (uint32_t j = 0; j < val(n); ++j) corner_slot[inc[inc_off[n] + j]] = jds[j] + uint32_t(k);
         }
         P.n_interior += in.size();
+        P.max_int = std::max<int>(P.max_int, int(in.size()));
         // shared nodes touched by this tile, ascending id
         std::vector<uint32_t> sh;
         const size_t s0 = size_t(t) * tile_e, s1 = std::min(n_slots, s0 + tile_e);
@@ -158,41 +191,33 @@ inline std::string build_plan(HostPlan& P, int n_nodes, int n_elems, int npe, co
     if (P.max_touched < 1) P.max_touched = 1;
     if (P.max_slots < 1) P.max_slots = 1;
 
-    // ---- shared nodes: chunks of `chunk`, ranked by valence inside a chunk, HBM staging positions
+    // ---- shared nodes, ascending id, in chunks of `chunk` nodes.  Contribution j (element order) of the node of rank k in
+    // chunk c is staged at sh_base[c] + j*chunk + k: an ELL block per chunk, padded to the chunk's largest valence, so that
+    // the staging address needs no index table and consecutive threads (k) read consecutive 16-byte entries.
     std::vector<uint32_t> shared;
     for (int i = 0; i < n_nodes; ++i) if (interior_tile[i] < 0) shared.push_back(uint32_t(i));
     P.n_shared = int(shared.size());
     P.n_chunks = std::max(1, (P.n_shared + chunk - 1) / chunk);
     P.sh_nodes.assign(size_t(P.n_chunks) * chunk, 0xFFFFFFFFu);
     P.sh_val.assign(size_t(P.n_chunks) * chunk, 0);
-    P.sh_jds.assign(size_t(P.n_chunks) * (maxval + 1), 0);
     P.sh_base.assign(P.n_chunks, 0);
     size_t stage = 0;
     for (int c = 0; c < P.n_chunks; ++c) {
         const size_t b = size_t(c) * chunk, e = std::min(shared.size(), b + chunk);
-        std::vector<uint32_t> ns(shared.begin() + std::min(b, shared.size()), shared.begin() + e);
         auto val = [&](uint32_t n) { return inc_off[n + 1] - inc_off[n]; };
-        std::stable_sort(ns.begin(), ns.end(), [&](uint32_t a, uint32_t b2) { return val(a) > val(b2); });
-        std::vector<uint32_t> jds(maxval + 1, 0);
-        for (int j = 0; j < maxval; ++j) {
-            uint32_t cnt = 0;
-            while (cnt < ns.size() && val(ns[cnt]) > uint32_t(j)) ++cnt;
-            jds[j + 1] = jds[j] + cnt;
-        }
-        for (int j = 0; j <= maxval; ++j) P.sh_jds[size_t(c) * (maxval + 1) + j] = jds[j];
+        uint32_t mv = 0;
+        for (size_t i = b; i < e; ++i) mv = std::max(mv, val(shared[i]));
+        if (stage + size_t(mv) * chunk >= 0x7fffffffu) return "staging buffer exceeds 2^31 entries";
         P.sh_base[c] = uint32_t(stage);
-        for (size_t k = 0; k < ns.size(); ++k) {
-            const uint32_t n = ns[k];
-            P.sh_nodes[b + k] = n;
-            P.sh_val[b + k] = uint16_t(val(n));
-            for (uint32_t j = 0; j < val(n); ++j) {
-                const size_t p = stage + jds[j] + k;
-                if (p >= 0x7fffffffu) return "staging buffer exceeds 2^31 entries";
-                corner_slot[inc[inc_off[n] + j]] = stage_flag | uint32_t(p);
-            }
+        for (size_t i = b; i < e; ++i) {
+            const uint32_t n = shared[i];
+            const size_t k = i - b;
+            P.sh_nodes[i] = n;
+            P.sh_val[i] = uint16_t(val(n));
+            for (uint32_t j = 0; j < val(n); ++j) corner_slot[inc[inc_off[n] + j]] = stage_flag | uint32_t(stage + size_t(j) * chunk + k);
+            P.n_staged_corners += val(n);
         }
-        stage += jds[maxval];
-        P.n_staged_corners += jds[maxval];
+        stage += size_t(mv) * chunk;
     }
     P.stage_n = std::max<size_t>(stage, 1);
 

@@ -19,7 +19,7 @@ template <class R> struct TetFF : sofab200_tetfem {
     HostTet<R> h;
     DevBuf<ushort4> lnode; DevBuf<uint4> slot; DevBuf<uint32_t> orig;
     DevBuf<Quad<R>> rk0, rk1, rk2, j0, j1, j2, x0a, x0b, x0c, sv0, sv1, sv2, sv3, sv4;
-    DevBuf<uint32_t> tile_node_off, tile_nodes, tile_nint, sh_nodes, sh_jds, sh_base;
+    DevBuf<uint32_t> tile_node_off, tile_nodes, tile_nint, sh_nodes, sh_base;
     DevBuf<uint16_t> tile_val, tile_jds, sh_val;
     DevBuf<Quad<R>> stage;
     DevBuf<R> rot_export;
@@ -30,7 +30,7 @@ template <class R> struct TetFF : sofab200_tetfem {
         TetDev<R> d;
         d.t.n_nodes = int(n_nodes); d.t.n_elems = int(n_tets); d.t.n_tiles = plan.n_tiles; d.t.tile_e = plan.tile_e; d.t.maxval = plan.maxval;
         d.t.tile_node_off = tile_node_off.p; d.t.tile_nodes = tile_nodes.p; d.t.tile_nint = tile_nint.p; d.t.tile_val = tile_val.p; d.t.tile_jds = tile_jds.p;
-        d.t.n_shared = plan.n_shared; d.t.n_chunks = plan.n_chunks; d.t.sh_nodes = sh_nodes.p; d.t.sh_val = sh_val.p; d.t.sh_jds = sh_jds.p; d.t.sh_base = sh_base.p;
+        d.t.n_shared = plan.n_shared; d.t.n_chunks = plan.n_chunks; d.t.sh_nodes = sh_nodes.p; d.t.sh_val = sh_val.p; d.t.sh_base = sh_base.p;
         d.t.stage = stage.p; d.t.stage_n = plan.stage_n;
         d.lnode = lnode.p; d.slot = slot.p;
         d.rk0 = rk0.p; d.rk1 = rk1.p; d.rk2 = rk2.p; d.j0 = j0.p; d.j1 = j1.p; d.j2 = j2.p;
@@ -54,7 +54,7 @@ template <class R> static int tet_upload(TetFF<R>& ff) {
     }
     SB_TRY(ff.tile_node_off.upload(P.tile_node_off, s)); SB_TRY(ff.tile_nodes.upload(P.tile_nodes, s)); SB_TRY(ff.tile_nint.upload(P.tile_nint, s));
     SB_TRY(ff.tile_val.upload(P.tile_val, s)); SB_TRY(ff.tile_jds.upload(P.tile_jds, s));
-    SB_TRY(ff.sh_nodes.upload(P.sh_nodes, s)); SB_TRY(ff.sh_val.upload(P.sh_val, s)); SB_TRY(ff.sh_jds.upload(P.sh_jds, s)); SB_TRY(ff.sh_base.upload(P.sh_base, s));
+    SB_TRY(ff.sh_nodes.upload(P.sh_nodes, s)); SB_TRY(ff.sh_val.upload(P.sh_val, s)); SB_TRY(ff.sh_base.upload(P.sh_base, s));
     SB_TRY(ff.stage.alloc(P.stage_n)); SB_TRY(ff.stage.zero(s));
     SB_CUDA(cudaStreamSynchronize(s));
     // the tile-ordered host planes are no longer needed once they are resident in HBM
@@ -67,13 +67,15 @@ template <class R> static int tet_upload(TetFF<R>& ff) {
 template <class R, int MODE, int MAXT, bool PF> static int tet_launch_variant(TetFF<R>& ff, const TetDev<R>& d, const R* in, const NodeEpilogue<R>& ep) {
     auto kern = tet_tile_kernel<R, MODE, MAXT, PF>;
     static thread_local size_t configured = 0;
-    if (ff.h.smem_bytes > 48 * 1024 && configured < ff.h.smem_bytes) {
-        SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ff.h.smem_bytes)));
-        configured = ff.h.smem_bytes;
+    static const size_t extra = getenv("SOFAB200_EXTRA_SMEM_KB") ? size_t(atoi(getenv("SOFAB200_EXTRA_SMEM_KB"))) * 1024 : 0;   // tuning experiment
+    const size_t smem_total = ff.h.smem_bytes + extra;
+    if (smem_total > 48 * 1024 && configured < smem_total) {
+        SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_total)));
+        configured = smem_total;
     }
     const int cls = (MODE == TM_DF_COROT || MODE == TM_DF_SMALL) ? 0 : 2;
     ff.ctx->prof_start(cls);
-    kern<<<ff.h.plan.n_tiles, (MODE == TM_DF_COROT && sizeof(R) == 4) ? ff.threads : 256, ff.h.smem_bytes, ff.ctx->stream>>>(d, in, ep, ff.h.plan.max_touched, ff.h.plan.max_slots);
+    kern<<<ff.h.plan.n_tiles, (MODE == TM_DF_COROT && sizeof(R) == 4) ? ff.threads : 256, smem_total, ff.ctx->stream>>>(d, in, ep, ff.h.plan.max_touched, ff.h.plan.max_slots);
     ff.ctx->prof_stop(cls);
     ff.ctx->launches++;
     SB_CUDA(cudaGetLastError());
@@ -87,6 +89,52 @@ template <class R, int MODE> static int tet_launch_mode(TetFF<R>& ff, const TetD
     if (ff.threads > 256) return ff.prefetch ? tet_launch_variant<R, MODE, 512, true>(ff, d, in, ep) : tet_launch_variant<R, MODE, 512, false>(ff, d, in, ep);
     return ff.prefetch ? tet_launch_variant<R, MODE, 256, true>(ff, d, in, ep) : tet_launch_variant<R, MODE, 256, false>(ff, d, in, ep);
 }
+
+// ---- persistent CG kernel (cooperative launch: every CTA must be resident, the kernel crosses grid-wide syncs) -----------
+// Returns SOFAB200_OK, an error, or kPersistNotEligible (> 0) when the mesh does not fit the kernel's assumptions (at most
+// two tiles and one chunk of shared nodes per thread group and CTA): the caller then runs the multi-kernel loop.
+template <class R, int MODE, int MAXT, bool PF> static int tet_persist_variant(TetFF<R>& ff, TetDev<R> d, PersistCG<R> a, int threads, size_t sync_capacity) {
+    auto kern = tet_cg_persistent_kernel<R, MODE, MAXT, PF>;
+    const HostPlan& P = ff.h.plan;
+    const int groups = threads / kGatherChunk;
+    // grid: as many CTAs as the GPU holds at once, at most one per tile (or per group of chunks if there are more of those)
+    cudaFuncAttributes fa;
+    SB_CUDA(cudaFuncGetAttributes(&fa, kern));
+    int dev_smem_optin = 0;
+    SB_CUDA(cudaDeviceGetAttribute(&dev_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ff.ctx->device));
+    for (int tiles_per_cta = 1; tiles_per_cta <= 2; ++tiles_per_cta) {
+        const PersistLayout L = persist_layout<R>(tiles_per_cta, P.max_touched, P.max_slots, P.max_int);
+        if (L.total + fa.sharedSizeBytes > size_t(dev_smem_optin)) break;
+        SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<unsigned>(L.total, 1024))));
+        int per_sm = 0;
+        SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, L.total));
+        const int max_grid = per_sm * ff.ctx->sm_count;
+        if (max_grid < 1) break;
+        const int need_tiles = (P.n_tiles + tiles_per_cta - 1) / tiles_per_cta, need_chunks = (P.n_chunks + groups - 1) / groups;
+        const int grid = std::max(need_tiles, need_chunks);
+        if (grid > max_grid) continue;
+        if (size_t(3) * grid + 1 > sync_capacity) return fail(SOFAB200_ERR_INVALID, "sync buffer too small for the persistent CG kernel");
+        a.lay = L;
+        void* args[] = {&d, &a};
+        ff.ctx->prof_start(0);
+        SB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(threads), args, L.total, ff.ctx->stream));
+        ff.ctx->prof_stop(0);
+        ff.ctx->launches++;
+        return SOFAB200_OK;
+    }
+    return kPersistNotEligible;
+}
+template <class R> int tet_cg_persistent(sofab200_tetfem* base, R k_factor, PersistCG<R> a, size_t sync_capacity) {
+    TetFF<R>& ff = *static_cast<TetFF<R>*>(base);
+    TetDev<R> d = ff.dev();
+    d.k_factor = k_factor;
+    if (ff.method == SOFAB200_TET_SMALL) return tet_persist_variant<R, TM_DF_SMALL, 256, false>(ff, d, a, 256, sync_capacity);
+    if (sizeof(R) == 8) return tet_persist_variant<R, TM_DF_COROT, 256, false>(ff, d, a, 256, sync_capacity);
+    if (ff.threads > 256) return tet_persist_variant<R, TM_DF_COROT, 512, true>(ff, d, a, 512, sync_capacity);
+    return tet_persist_variant<R, TM_DF_COROT, 256, true>(ff, d, a, 256, sync_capacity);
+}
+template int tet_cg_persistent<float>(sofab200_tetfem*, float, PersistCG<float>, size_t);
+template int tet_cg_persistent<double>(sofab200_tetfem*, double, PersistCG<double>, size_t);
 
 // Element pass + boundary gather with a caller-provided epilogue (also used by the solver node).
 template <class R> TileDev<R> tet_tiledev(sofab200_tetfem* base) { return static_cast<TetFF<R>*>(base)->dev().t; }

@@ -140,25 +140,29 @@ template <class R> static std::string tet_host_build(HostTet<R>& ff, size_t n_no
     tet_init_elements(ff, x0, tets, desc);
     std::vector<double> pos(3 * n_nodes);
     for (size_t i = 0; i < 3 * n_nodes; ++i) pos[i] = double(x0[i]);
-    // Tile size.  One CTA streams one tile, so the number of tiles should be a whole multiple of the CTAs the GPU holds at
-    // once (no partial last wave), and a tile must fit in shared memory.  Default: the largest tile <= 3584 (Vec3f) / 1536
-    // (Vec3d) elements that cuts the mesh into k * sm_count equal parts.  desc->tile_elems or SOFAB200_TILE_ELEMS override.
+    // Tile size.  One CTA streams one tile, so the number of tiles should be a whole multiple of the SM count (no partial
+    // last wave), and the fewer waves the fewer times the per-tile phases (nodal staging, ordered sums) are paid: default is
+    // the largest tile that cuts the mesh into k * sm_count equal parts and still keeps at least half of the corner
+    // contributions in shared memory (build_plan demotes interior nodes beyond the budget to the L2 staging path).
+    // desc->tile_elems or SOFAB200_TILE_ELEMS override; SOFAB200_SMEM_KB sets the budget.
     const bool fixed_tile = desc->tile_elems > 0 || getenv("SOFAB200_TILE_ELEMS");
     int tile_e = desc->tile_elems;
     if (const char* env = getenv("SOFAB200_TILE_ELEMS")) { const int v = atoi(env); if (v > 0) tile_e = v; }
-    const int cap = sizeof(R) == 4 ? 3584 : 1536;
-    int k_waves = std::max<int>(1, int((n_tets + size_t(sm_count) * cap - 1) / (size_t(sm_count) * cap)));
-    if (tile_e <= 0) tile_e = int((n_tets + size_t(sm_count) * k_waves - 1) / (size_t(sm_count) * k_waves));
+    size_t smem_limit = 150 * 1024;   // what is left of the 256 KB L1/shared array holds the in-flight element records: a larger carve-out throttles the stream
+    if (const char* env = getenv("SOFAB200_SMEM_KB")) { const int v = atoi(env); if (v >= 16 && v <= 224) smem_limit = size_t(v) * 1024; }
+    typedef typename SVec<R>::T SV;
+    // first guess: the tile whose corners would fit if 45 % of them were interior
+    int k_waves = std::max<int>(1, int((double(n_tets) * 4 * 0.45 * 3 * sizeof(R)) / (double(sm_count) * smem_limit) + 0.999));
+    if (const char* env = getenv("SOFAB200_TILE_WAVES")) { const int v = atoi(env); if (v > 0) k_waves = v; }
+    auto tile_for = [&](int k) { return std::max(32, (int((n_tets + size_t(sm_count) * k - 1) / (size_t(sm_count) * k)) + 31) / 32 * 32); };
+    if (tile_e <= 0) tile_e = tile_for(k_waves);
     tile_e = std::max(32, (tile_e + 31) / 32 * 32);
     for (;;) {
-        const std::string err = build_plan(ff.plan, int(n_nodes), int(n_tets), 4, tets, pos.data(), tile_e, chunk, kStageFlag);
+        const std::string err = build_plan(ff.plan, int(n_nodes), int(n_tets), 4, tets, pos.data(), tile_e, chunk, kStageFlag, smem_limit, sizeof(SV), 3 * sizeof(R));
         ff.smem_bytes = tile_smem_bytes<R>(ff.plan.max_touched, ff.plan.max_slots);
-        const bool too_big = ff.smem_bytes > 200 * 1024 || err.find("use a smaller tile") != std::string::npos;
-        if (too_big && !fixed_tile && tile_e > 32) {
-            ++k_waves;
-            tile_e = std::max(32, (int((n_tets + size_t(sm_count) * k_waves - 1) / (size_t(sm_count) * k_waves)) + 31) / 32 * 32);
-            continue;
-        }
+        const bool too_big = ff.smem_bytes > smem_limit || err.find("use a smaller tile") != std::string::npos;
+        const bool too_staged = err.empty() && ff.plan.n_staged_corners * 2 > 4 * n_tets && ff.plan.n_demoted > 0;
+        if ((too_big || too_staged) && !fixed_tile && tile_e > 32) { tile_e = tile_for(++k_waves); continue; }
         if (!err.empty()) return err;
         if (too_big) return "tile does not fit in shared memory; use a smaller tile_elems";
         break;

@@ -7,7 +7,7 @@
 // Arithmetic follows the reference statement by statement (file:line cited per function); compiled with
 // -fmad=false so no multiply-add is contracted.
 #pragma once
-#include "fem_layout.cuh"
+#include "cg_persist.cuh"
 #include "math3.cuh"
 
 namespace sb {
@@ -165,27 +165,14 @@ template <class R, int MODE> HD void tet_element(const TetDev<R>& d, size_t es, 
     }
 }
 
-// MAXT: CTA size the kernel is compiled for (register budget 65536/MAXT); PF: software-prefetch the next element record
-template <class R, int MODE, int MAXT, bool PF>
-__global__ void __launch_bounds__(MAXT) tet_tile_kernel(TetDev<R> d, const R* __restrict__ in, NodeEpilogue<R> ep, int max_touched, int max_slots) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double red[32];
-    __shared__ uint16_t s_jds[1024];
+// phase 2 of a tile: one thread per element, 4 corner contributions scattered to their slots.
+// PF: software-prefetch the next element record (the record of the thread's NEXT element is requested before the current
+// one is processed, so one element's worth of HBM latency is always overlapped with ~500 instructions of arithmetic).
+template <class R, int MODE, bool PF>
+__device__ __forceinline__ void tet_tile_elements(const TetDev<R>& d, int tile, const typename SVec<R>::T* s_in, R* s_slot, int max_slots) {
     typedef typename SVec<R>::T SV;
-    if (ep.cg && ep.cg->done) return;
-    SV* s_in = reinterpret_cast<SV*>(smem_raw);
-    size_t off = (sizeof(SV) * size_t(max_touched) + 15) & ~size_t(15);
-    R* s_slot = reinterpret_cast<R*>(smem_raw + off);  // 3 planes of max_slots
-
     const TileDev<R>& t = d.t;
-    const int tile = blockIdx.x;
-    // ---- phase 1: stage input vectors of the touched nodes
-    tile_phase1<R>(t, tile, in, s_in, s_jds);
-
-    // ---- phase 2: elements
     const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
-    // Software pipeline: the record of the thread's NEXT element is requested before the current one is processed,
-    // so one element's worth of HBM latency is always overlapped with ~500 instructions of arithmetic.
     int le = threadIdx.x;
     uint2 lnw = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); uint4 sl = make_uint4(0, 0, 0, 0);
     TetRec<R> rec;
@@ -220,13 +207,87 @@ __global__ void __launch_bounds__(MAXT) tet_tile_kernel(TetDev<R> d, const R* __
             lnw = idx_load(reinterpret_cast<const uint2*>(d.lnode + nes), pol_stream); sl = idx_load(d.slot + nes, pol_stream); rec = tet_load_rec(d, nes, pol_stream);
         }
     }
+}
+
+// MAXT: CTA size the kernel is compiled for (register budget 65536/MAXT)
+template <class R, int MODE, int MAXT, bool PF>
+__global__ void __launch_bounds__(MAXT) tet_tile_kernel(TetDev<R> d, const R* __restrict__ in, NodeEpilogue<R> ep, int max_touched, int max_slots) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[32];
+    __shared__ uint16_t s_jds[1024];
+    typedef typename SVec<R>::T SV;
+    if (ep.cg && ep.cg->done) return;
+    SV* s_in = reinterpret_cast<SV*>(smem_raw);
+    size_t off = (sizeof(SV) * size_t(max_touched) + 15) & ~size_t(15);
+    R* s_slot = reinterpret_cast<R*>(smem_raw + off);  // 3 planes of max_slots
+
+    const TileDev<R>& t = d.t;
+    const int tile = blockIdx.x;
+    trace_mark(ep.trace, 0, 0);
+    // ---- phase 1: stage input vectors of the touched nodes
+    tile_phase1<R>(t, tile, in, s_in, s_jds);
+    trace_mark(ep.trace, 0, 1);
+    // ---- phase 2: elements
+    tet_tile_elements<R, MODE, PF>(d, tile, s_in, s_slot, max_slots);
+    trace_mark(ep.trace, 0, 2);
     __syncthreads();
+    trace_mark(ep.trace, 0, 3);
 
     // ---- phase 3: interior nodes, sequential sum in element order + fused epilogue
     const double part = tile_phase3<R>(t, tile, ep, s_in, s_slot, max_slots, s_jds);
     if (ep.dot_kind != DOT_NONE) {
         const double tot = block_sum(part, red);
         finish_dot(ep, tot, red, false);
+    }
+    trace_mark(ep.trace, 0, 4);
+}
+
+// ---- the whole CG loop of CGLinearSolver::solve in ONE persistent cooperative kernel ----------------------------------
+// One CTA per SM keeps its (one or two) tiles for the whole solve; the three global dependencies of an iteration (staged
+// contributions of the shared nodes, den = p.q, rho = r.r) are crossed with a grid-wide sync-and-sum instead of a kernel
+// boundary, and everything static (node ids, valences, masses, fixed flags) is read from HBM once per solve:
+//   [A] p = p*beta + r for the nodes of the CTA's tiles; per tile: element pass, interior nodes -> q, partial p.q
+//   [B] shared nodes (ordered sum of the staged contributions) -> q, p                        -> den, alpha
+//   [C] x += alpha p ; r -= alpha q                                                            -> rho, beta
+// Every CTA sums the same partials in the same order, so all CTAs take the same branches.
+template <class R, int MODE, int MAXT, bool PF>
+__global__ void __launch_bounds__(MAXT) tet_cg_persistent_kernel(TetDev<R> d, PersistCG<R> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[32];
+    __shared__ double bcast;
+    __shared__ uint16_t s_jds[2][1024];
+    __shared__ NodeRec s_grec[MAXT];
+    __shared__ uint32_t s_gbase[MAXT];
+    typedef typename SVec<R>::T SV;
+    CGDev* cg = a.cg;
+    if (cg->done) return;
+    const TileDev<R>& t = d.t;
+    const PersistLayout& L = a.lay;
+    SV* s_in = reinterpret_cast<SV*>(smem_raw);
+    R* s_slot = reinterpret_cast<R*>(smem_raw + L.off_slot);
+    PersistState<R> st(a);
+    for (int c = 0; c < L.tiles_cached; ++c) {
+        const int tile = blockIdx.x + c * gridDim.x;
+        if (tile < t.n_tiles) for (int j = threadIdx.x; j <= t.maxval; j += blockDim.x) s_jds[c][j] = t.tile_jds[size_t(tile) * (t.maxval + 1) + j];
+    }
+    persist_load_tables<R>(t, a, smem_raw, s_grec, s_gbase);
+    for (;;) {
+        trace_mark(a.ep.trace, kTraceTail, 0);
+        // ---- [A]
+        persist_phase1<R>(t, a, st, smem_raw);
+        trace_mark(a.ep.trace, kTraceTail, 12);
+        double part = 0.0;
+        for (int c = 0; c < L.tiles_cached; ++c) {
+            const int tile = blockIdx.x + c * gridDim.x;
+            if (tile >= t.n_tiles) break;
+            tet_tile_elements<R, MODE, PF>(d, tile, s_in + c * L.max_touched, s_slot, L.max_slots);
+            __syncthreads();
+            if (c == 0) trace_mark(a.ep.trace, kTraceTail, 13);
+            part += persist_phase3<R>(t, tile, c, a, smem_raw, s_jds[c]);
+            __syncthreads();
+            if (c == 0) trace_mark(a.ep.trace, kTraceTail, 14);
+        }
+        if (!persist_rest<R>(t, a, st, part, red, &bcast, s_grec, s_gbase)) break;
     }
 }
 

@@ -3,7 +3,7 @@
 #pragma once
 #include <cooperative_groups.h>
 
-#include "fem_layout.cuh"
+#include "cg_persist.cuh"
 
 namespace sb {
 
@@ -131,12 +131,6 @@ template <class R> __global__ void __launch_bounds__(kVecBlock) node_only_kernel
 // ---- CG vector steps -------------------------------------------------------------------------------
 // 16-byte vector accesses on the flat 3n array (cudaMalloc'ed vectors are 256-byte aligned); the last n3 % 4 scalars
 // are handled by the first threads of CTA 0.
-template <class R> struct Vec4T;
-template <> struct Vec4T<float> { typedef float4 T; static constexpr int N = 4; };
-template <> struct Vec4T<double> { typedef double2 T; static constexpr int N = 2; };
-__device__ __forceinline__ void v4_avf(float4& p, const float4& r, float b) { p.x *= b; p.x += r.x; p.y *= b; p.y += r.y; p.z *= b; p.z += r.z; p.w *= b; p.w += r.w; }
-__device__ __forceinline__ void v4_avf(double2& p, const double2& r, double b) { p.x *= b; p.x += r.x; p.y *= b; p.y += r.y; }
-
 // p = r (first iteration) or p = p*beta + r  (cgstep_beta -> vOp_avf), CGLinearSolver.inl:184-197
 template <class R> __global__ void __launch_bounds__(kVecBlock) cg_p_update_kernel(size_t n3, R* __restrict__ p, const R* __restrict__ r, const CGDev* cg) {
     if (cg->done) return;
@@ -155,12 +149,7 @@ template <class R> __global__ void __launch_bounds__(kVecBlock) cg_p_update_kern
         else { R t = p[i]; t *= beta; t += r[i]; p[i] = t; }
     }
 }
-// x += p*alpha ; r += q*(-alpha)  (cgstep_alpha -> two vOp_v_inc_bf), then rho' = r.r for the next iteration
-template <class R> __device__ __forceinline__ double xr_one(R& x, R& r, R p, R q, R alpha, R malpha, bool a_one, bool ma_one) {
-    if (a_one) x += p; else x += p * alpha;      // vOp takes `r += b` when k == 1
-    if (ma_one) r += q; else r += q * malpha;
-    return double(r) * double(r);
-}
+// x += p*alpha ; r += q*(-alpha), then rho' = r.r for the next iteration (xr_one, cg_persist.cuh)
 template <class R> __global__ void __launch_bounds__(kVecBlock) cg_xr_update_kernel(size_t n3, R* __restrict__ x, R* __restrict__ r, const R* __restrict__ p, const R* __restrict__ q,
                                                                                      CGDev* cg, double* partials, unsigned* counter, int fused_rho) {
     if (cg->done) return;
@@ -235,40 +224,34 @@ __global__ void cg_scalar_kernel(CGDev* cg, const double* value, int action) {
 //   C  tolerance test ; beta = rho'/rho ; p = p*beta + r  (the NEXT iteration's direction)
 // Every CTA adds the same partials in the same order, so all take the same branch; CTA 0 records the scalars in CGDev.
 constexpr int kTailBlock = kGatherChunk;
-template <class R> __device__ __forceinline__ double sum_partials_all(const double* partials, int n, double* red, double* bcast) {
-    double s = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s += __ldcg(partials + i);
-    __syncthreads();
-    s = block_sum(s, red);
-    if (threadIdx.x == 0) *bcast = s;
-    __syncthreads();
-    return *bcast;
-}
 template <class R> __global__ void __launch_bounds__(kTailBlock) cg_tail_kernel(TileDev<R> d, NodeEpilogue<R> ep, size_t n3, R* __restrict__ x, R* __restrict__ r, R* __restrict__ p,
                                                                                  const R* __restrict__ q, CGDev* cg, double* partials_den, int n_tile_partials, double* partials_rho) {
     namespace cgp = cooperative_groups;
     __shared__ double red[32];
     __shared__ double bcast;
-    __shared__ uint32_t s_jds[1024 + 3 * kGatherBatch];
     if (cg->done) return;
     cgp::grid_group grid = cgp::this_grid();
     // snapshot of the scalars this iteration starts from (CTA 0 rewrites CGDev after each barrier)
     const double rho = cg->rho, normb = cg->normb, tol = cg->tolerance, thr = cg->threshold;
     const int it = cg->it;
     const unsigned tsc = cg->time_step_count, max_iter = cg->max_iter;
+    trace_mark(ep.trace, kTraceTail, 0);
     // ---- A
     double part = 0.0;
-    for (int chunk = blockIdx.x; chunk < d.n_chunks; chunk += gridDim.x) part += gather_chunk<R>(d, ep, chunk, s_jds);
+    for (int chunk = blockIdx.x; chunk < d.n_chunks; chunk += gridDim.x) part += gather_chunk<R>(d, ep, chunk, threadIdx.x);
     __syncthreads();
     part = block_sum(part, red);
     if (threadIdx.x == 0) partials_den[n_tile_partials + blockIdx.x] = part;
+    trace_mark(ep.trace, kTraceTail, 1);
     grid.sync();
+    trace_mark(ep.trace, kTraceTail, 2);
     const double den = sum_partials_all<R>(partials_den, n_tile_partials + int(gridDim.x), red, &bcast);
     bool stop = false;
     if (den != 0.0) { if (fabs(den) <= thr && !(it == 1 && tsc == 0)) stop = true; } else stop = true;
     if (blockIdx.x == 0 && threadIdx.x == 0) cg_after_den(cg, den);
     if (stop) return;
     const double alpha_d = rho / den;
+    trace_mark(ep.trace, kTraceTail, 3);
     // ---- B
     const R alpha = R(alpha_d), malpha = R(-alpha_d);
     const bool a_one = (alpha_d == 1.0), ma_one = (-alpha_d == 1.0);
@@ -293,7 +276,9 @@ template <class R> __global__ void __launch_bounds__(kTailBlock) cg_tail_kernel(
     __syncthreads();
     prr = block_sum(prr, red);
     if (threadIdx.x == 0) partials_rho[blockIdx.x] = prr;
+    trace_mark(ep.trace, kTraceTail, 4);
     grid.sync();
+    trace_mark(ep.trace, kTraceTail, 5);
     const double rho_new = sum_partials_all<R>(partials_rho, int(gridDim.x), red, &bcast);
     const int it2 = it + 1;
     bool stop2 = unsigned(it2) > max_iter;
@@ -309,6 +294,10 @@ template <class R> __global__ void __launch_bounds__(kTailBlock) cg_tail_kernel(
         for (size_t i = nv * 4 + t0; i < n3; i += stride) { R t = p[i]; t *= beta; t += r[i]; p[i] = t; }
     } else {
         for (size_t i = t0; i < n3; i += stride) { R t = p[i]; t *= beta; t += r[i]; p[i] = t; }
+    }
+    if (ep.trace && threadIdx.x == 0) {   // duration of phase C (the last iteration of a solve returns before it)
+        unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        ep.trace[kTraceTail + blockIdx.x * kTraceWords + 6] = t - ep.trace[kTraceTail + blockIdx.x * kTraceWords + 5];
     }
 }
 

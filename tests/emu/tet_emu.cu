@@ -19,7 +19,7 @@ template <class R> struct Emu {
         d.t.tile_node_off = P.tile_node_off.data(); d.t.tile_nodes = P.tile_nodes.data(); d.t.tile_nint = P.tile_nint.data();
         d.t.tile_val = P.tile_val.data(); d.t.tile_jds = P.tile_jds.data();
         d.t.n_shared = P.n_shared; d.t.n_chunks = P.n_chunks; d.t.sh_nodes = P.sh_nodes.data(); d.t.sh_val = P.sh_val.data();
-        d.t.sh_jds = P.sh_jds.data(); d.t.sh_base = P.sh_base.data(); d.t.stage = stage.data(); d.t.stage_n = P.stage_n;
+        d.t.sh_base = P.sh_base.data(); d.t.stage = stage.data(); d.t.stage_n = P.stage_n;
         d.lnode = h.lnode.data(); d.slot = h.slot.data();
         d.rk0 = h.rk0.data(); d.rk1 = h.rk1.data(); d.rk2 = h.rk2.data(); d.j0 = h.j0.data(); d.j1 = h.j1.data(); d.j2 = h.j2.data();
         d.x0a = h.x0a.data(); d.x0b = h.x0b.data(); d.x0c = h.x0c.data();
@@ -76,13 +76,12 @@ template <class R, int MODE> double run_mode(Emu<R>& E, const R* in, R kf, NodeE
             const uint32_t g = t.sh_nodes[size_t(chunk) * kGatherChunk + k];
             if (g == 0xFFFFFFFFu) continue;
             const int val = t.sh_val[size_t(chunk) * kGatherChunk + k];
-            const uint32_t* jds = t.sh_jds + size_t(chunk) * (t.maxval + 1);
             const size_t base = t.sh_base[chunk];
             R ax, ay, az;
             node_pre(ep, g, ax, ay, az);
             node_mass(ep, ep.pre_kind, g, ax, ay, az);
             for (int j = 0; j < val; ++j) {
-                const Quad<R> v = stage_load(t.stage + (base + jds[j] + k), 0);
+                const Quad<R> v = stage_load(t.stage + (base + size_t(j) * kGatherChunk + k), 0);
                 if (ep.sign > 0) { ax += v.a; ay += v.b; az += v.c; } else { ax -= v.a; ay -= v.b; az -= v.c; }
             }
             dot += node_post(ep, g, ax, ay, az);

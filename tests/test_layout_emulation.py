@@ -88,3 +88,23 @@ def test_layout_invariants_and_isolated_nodes():
     xr = np.vstack([x, pos[-2:]]).astype(np.float32)
     f0 = rng.standard_normal(pos.shape).astype(np.float32)
     assert e.run(False, xr, init=f0).tobytes() == s.fem_add_force(f0, xr).tobytes()
+
+
+def test_slot_budget_demotes_interior_nodes_bit_exact(monkeypatch):
+    """A tile whose interior corners exceed the shared-memory budget keeps only what fits; the rest goes through the
+    staging path.  Same bits either way."""
+    pos, tets, x, rng = _beam(n=(6, 6, 11))
+    monkeypatch.setenv("SOFAB200_SMEM_KB", "16")
+    e = EmuTet(np.float32, pos, tets, "large", 1000.0, 0.3, 1024)
+    st = e.stats()
+    assert st["smem"] <= 16 * 1024
+    monkeypatch.delenv("SOFAB200_SMEM_KB")
+    e_free = EmuTet(np.float32, pos, tets, "large", 1000.0, 0.3, 1024)
+    assert e_free.stats()["staged"] < st["staged"]          # the budget pushed corners to the staging path
+    s = O.OracleScene(np.float32, pos); s.set_tets(tets, "large", 1000.0, 0.3)
+    f0 = rng.standard_normal(pos.shape).astype(np.float32)
+    f_ref = s.fem_add_force(f0, x.astype(np.float32))
+    assert e.run(False, x.astype(np.float32), init=f0).tobytes() == f_ref.tobytes()
+    dx = (1e-3 * rng.standard_normal(pos.shape)).astype(np.float32)
+    df0 = rng.standard_normal(pos.shape).astype(np.float32)
+    assert e.run(True, dx, kf=-0.37, init=df0).tobytes() == s.fem_add_dforce(df0, dx, -0.37).tobytes()
