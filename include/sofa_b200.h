@@ -75,9 +75,10 @@ uint64_t sofab200_ctx_launch_count(const sofab200_ctx* ctx);
 /* Per-kernel-class device timing with CUDA events recorded on the context's stream around every launch
  * (replaces SofaCUDA's CUDA_TIMER_SYNC env switch, mycuda.cpp:146).  Classes:
  *   0 element pass of addDForce / A*p   1 boundary gather   2 element pass of addForce   3 CG / vector kernels
+ *   4 persistent CG kernel (the whole CGLinearSolver loop: one launch per solve)
  * profile_begin enables recording; profile_end (sync) disables it and returns, per class, the summed
  * milliseconds and the number of launches.  total_ms / count: arrays of SOFAB200_PROFILE_CLASSES. */
-#define SOFAB200_PROFILE_CLASSES 4
+#define SOFAB200_PROFILE_CLASSES 5
 int sofab200_ctx_profile_begin(sofab200_ctx* ctx);
 int sofab200_ctx_profile_end(sofab200_ctx* ctx, double* total_ms, uint64_t* count);
 /* In-kernel phase timestamps (diagnostics; no reference counterpart).  After trace_begin every tile CTA of the solver

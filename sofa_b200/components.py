@@ -58,13 +58,13 @@ class Context:
     def launch_count(self):
         return int(self.L.sofab200_ctx_launch_count(self.h))
 
-    PROFILE_CLASSES = ("element_pass_dforce", "boundary_gather", "element_pass_force", "cg_vector_kernels")
+    PROFILE_CLASSES = ("element_pass_dforce", "boundary_gather", "element_pass_force", "cg_vector_kernels", "cg_persistent")
 
     def profile_begin(self):
         check(self.L.sofab200_ctx_profile_begin(self.h))
 
     def profile_end(self):
-        ms = (C.c_double * 4)(); cnt = (C.c_uint64 * 4)()
+        ms = (C.c_double * 5)(); cnt = (C.c_uint64 * 5)()
         check(self.L.sofab200_ctx_profile_end(self.h, ms, cnt))
         return {k: dict(ms=ms[i], launches=int(cnt[i])) for i, k in enumerate(self.PROFILE_CLASSES)}
 

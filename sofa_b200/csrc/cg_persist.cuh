@@ -266,7 +266,11 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
         R* d = st.pnew + 3 * size_t(grec.g); d[0] = gp0; d[1] = gp1; d[2] = gp2;       // nobody else writes a shared node's p
         R ax = R(0), ay = R(0), az = R(0);
         node_mass_m(ep, ep.pre_kind, m, gp0, gp1, gp2, ax, ay, az);
+        if (b0[0].a == R(123456789)) trace_mark(ep.trace, kTraceTail, 15);   // (waits for the first staged entry)
+        trace_mark(ep.trace, kTraceTail, 8);
         gather_sum<R>(b0, b1, stg, val, ep.sign > 0, ax, ay, az, pol);
+        if (ax == R(123456789)) trace_mark(ep.trace, kTraceTail, 15);
+        trace_mark(ep.trace, kTraceTail, 9);
         part2 = node_post_m(ep, grec.g, m, (grec.val_fixed & 0x10000u) != 0, gp0, gp1, gp2, ax, ay, az);
     }
     __syncthreads();

@@ -75,7 +75,7 @@ template <class R, int MODE, int MAXT, bool PF> static int tet_launch_variant(Te
     }
     const int cls = (MODE == TM_DF_COROT || MODE == TM_DF_SMALL) ? 0 : 2;
     ff.ctx->prof_start(cls);
-    kern<<<ff.h.plan.n_tiles, (MODE == TM_DF_COROT && sizeof(R) == 4) ? ff.threads : 256, smem_total, ff.ctx->stream>>>(d, in, ep, ff.h.plan.max_touched, ff.h.plan.max_slots);
+    kern<<<ff.h.plan.n_tiles, ((MODE == TM_DF_COROT || (MODE == TM_F_LARGE && MAXT > 256)) && sizeof(R) == 4) ? ff.threads : 256, smem_total, ff.ctx->stream>>>(d, in, ep, ff.h.plan.max_touched, ff.h.plan.max_slots);
     ff.ctx->prof_stop(cls);
     ff.ctx->launches++;
     SB_CUDA(cudaGetLastError());
@@ -83,6 +83,7 @@ template <class R, int MODE, int MAXT, bool PF> static int tet_launch_variant(Te
 }
 template <class R, int MODE> static int tet_launch_mode(TetFF<R>& ff, const TetDev<R>& d, const R* in, const NodeEpilogue<R>& ep) {
     // the addForce passes run once per step: one conservative variant; the addDForce pass (26x per step) is tuned
+    if (MODE == TM_F_LARGE && sizeof(R) == 4 && ff.threads > 256) return ff.prefetch ? tet_launch_variant<R, MODE, 512, true>(ff, d, in, ep) : tet_launch_variant<R, MODE, 512, false>(ff, d, in, ep);
     if (MODE != TM_DF_COROT) return tet_launch_variant<R, MODE, 256, false>(ff, d, in, ep);
     if (sizeof(R) == 8) return tet_launch_variant<R, MODE, 256, false>(ff, d, in, ep);
     if (ff.threads > 512) return tet_launch_variant<R, MODE, 1024, false>(ff, d, in, ep);
@@ -116,9 +117,9 @@ template <class R, int MODE, int MAXT, bool PF> static int tet_persist_variant(T
         if (size_t(3) * grid + 1 > sync_capacity) return fail(SOFAB200_ERR_INVALID, "sync buffer too small for the persistent CG kernel");
         a.lay = L;
         void* args[] = {&d, &a};
-        ff.ctx->prof_start(0);
+        ff.ctx->prof_start(4);
         SB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(threads), args, L.total, ff.ctx->stream));
-        ff.ctx->prof_stop(0);
+        ff.ctx->prof_stop(4);
         ff.ctx->launches++;
         return SOFAB200_OK;
     }
