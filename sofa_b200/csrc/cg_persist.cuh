@@ -43,41 +43,42 @@ template <class R> __device__ __forceinline__ double sum_partials_all(const doub
 
 constexpr int kPersistNotEligible = 1;
 // ---- persistent CG --------------------------------------------------------------------------------------------------
-// Shared-memory plan of the kernel (bytes from the start of dynamic shared memory), computed by persist_layout().
+// Node ownership inside the kernel: a tile's interior nodes belong to the tile's CTA, a shared node belongs to the one thread
+// that sums its staged contributions.  The owner alone reads and writes x, r and q of its nodes, so for interior nodes p and q
+// never leave shared memory, and the x / r values an owner needs after a grid sync can be requested before it.  Only the p
+// and r of SHARED nodes travel through HBM/L2 (p double-buffered), for the tiles that touch them.
+// Shared-memory plan (bytes from the start of dynamic shared memory), computed by persist_layout().
 struct PersistLayout {
     int tiles_cached;       // tiles per CTA (1 or 2): their node tables and staged vectors stay in shared memory
-    int max_touched, max_slots, max_int;
-    unsigned off_slot, off_tidx, off_nrec, total;
+    int max_touched, max_slots, max_int, max_shtouch, maxval;
+    unsigned off_slot, off_tidx, off_nrec, off_qr, off_jds, total;
 };
-template <class R> inline PersistLayout persist_layout(int tiles_per_cta, int max_touched, int max_slots, int max_int) {
+// static per-node data of a tile's interior nodes, kept in shared memory for the whole solve
+template <class R> struct NodeRec { uint32_t g; uint32_t val_fixed; R mass; };        // val | fixed<<16
+// ... and of the shared node a thread owns
+template <class R> struct GRec { uint32_t g; uint32_t val_fixed; uint32_t base; R mass; };
+template <class R> inline PersistLayout persist_layout(int tiles_per_cta, int max_touched, int max_slots, int max_int, int max_shtouch, int maxval) {
     PersistLayout L;
-    L.tiles_cached = tiles_per_cta; L.max_touched = max_touched; L.max_slots = max_slots; L.max_int = max_int;
-    size_t o = sizeof(typename SVec<R>::T) * size_t(max_touched) * tiles_per_cta;
-    o = (o + 15) & ~size_t(15); L.off_slot = unsigned(o);
-    o += sizeof(R) * 3 * size_t(max_slots);
-    o = (o + 15) & ~size_t(15); L.off_tidx = unsigned(o);
-    o += sizeof(uint32_t) * size_t(max_touched) * tiles_per_cta;
-    o = (o + 15) & ~size_t(15); L.off_nrec = unsigned(o);
-    o += 16 * size_t(max_int) * tiles_per_cta;
+    L.tiles_cached = tiles_per_cta; L.max_touched = max_touched; L.max_slots = max_slots; L.max_int = max_int; L.max_shtouch = max_shtouch; L.maxval = maxval;
+    auto up = [](size_t o) { return (o + 15) & ~size_t(15); };
+    size_t o = up(sizeof(typename SVec<R>::T) * size_t(max_touched) * tiles_per_cta);
+    L.off_slot = unsigned(o); o = up(o + sizeof(R) * 3 * size_t(max_slots));
+    L.off_tidx = unsigned(o); o = up(o + sizeof(uint32_t) * size_t(max_shtouch) * tiles_per_cta);
+    L.off_nrec = unsigned(o); o = up(o + sizeof(NodeRec<R>) * size_t(max_int) * tiles_per_cta);
+    L.off_qr = unsigned(o); o = up(o + sizeof(R) * 3 * size_t(max_int) * tiles_per_cta);
+    L.off_jds = unsigned(o); o = up(o + sizeof(uint16_t) * size_t(maxval + 1) * tiles_per_cta);
     L.total = unsigned(o);
     return L;
 }
-// static per-node data of the nodes a thread finishes, kept in shared memory for the whole solve
-struct alignas(16) NodeRec { uint32_t g; uint32_t val_fixed; uint32_t mass_lo, mass_hi; };   // val | fixed<<16 ; mass bits (float in lo, double in lo/hi)
-template <class R> __device__ __forceinline__ NodeRec make_node_rec(uint32_t g, unsigned val, bool fx, R m);
-template <> __device__ __forceinline__ NodeRec make_node_rec<float>(uint32_t g, unsigned val, bool fx, float m) { return NodeRec{g, val | (fx ? 0x10000u : 0u), __float_as_uint(m), 0u}; }
-template <> __device__ __forceinline__ NodeRec make_node_rec<double>(uint32_t g, unsigned val, bool fx, double m) {
-    const unsigned long long b = (unsigned long long)__double_as_longlong(m);
-    return NodeRec{g, val | (fx ? 0x10000u : 0u), unsigned(b), unsigned(b >> 32)};
-}
-template <class R> __device__ __forceinline__ R node_rec_mass(const NodeRec& n);
-template <> __device__ __forceinline__ float node_rec_mass<float>(const NodeRec& n) { return __uint_as_float(n.mass_lo); }
-template <> __device__ __forceinline__ double node_rec_mass<double>(const NodeRec& n) { return __longlong_as_double((long long)((unsigned long long)n.mass_lo | ((unsigned long long)n.mass_hi << 32))); }
+// static shared memory of the kernel for a CTA of `threads` (the per-thread shared-node records + reduction scratch)
+template <class R> inline size_t persist_static_smem(int threads) { return sizeof(GRec<R>) * size_t(threads) + 33 * sizeof(double); }
 
 template <class R> struct PersistCG {
-    NodeEpilogue<R> ep;     // epilogue of q = A p: out = q, mass / projection terms, dot_kind = DOT_STORE
+    NodeEpilogue<R> ep;     // epilogue of q = A p: mass / projection terms, dot_kind = DOT_STORE (out is not used)
     R* x; R* r;
-    R* p0; R* p1;           // the search direction is double-buffered: tiles read p_old of shared nodes while p_new is written
+    typename SVec<R>::T* xt; typename SVec<R>::T* rt;   // x and r of the interior nodes in tile order (private to the owner CTA: one coalesced access per node)
+    R* gstate;              // [9][gridDim.x * blockDim.x] p, r, x of each thread's shared node (private, coalesced), between iterations
+    R* p0; R* p1;           // p of the shared nodes, double-buffered: tiles read p_old while the owners write p_new
     size_t n3;
     CGDev* cg;
     unsigned long long* sync;   // [3 * gridDim.x + 1] grid_sync_sum slots and arrival counter, zero at launch
@@ -135,19 +136,15 @@ template <class R> struct PersistState {
     }
 };
 
-// p_new = r (first iteration) or p_old*beta + r (cgstep_beta -> vOp_avf, CGLinearSolver.inl:184-197) for one node
-template <class R> __device__ __forceinline__ void persist_p_node(const PersistState<R>& st, const R* r, size_t g, R& p0, R& p1, R& p2) {
-    const R r0 = __ldcg(r + 3 * g), r1 = __ldcg(r + 3 * g + 1), r2 = __ldcg(r + 3 * g + 2);
-    if (st.first) { p0 = r0; p1 = r1; p2 = r2; return; }
-    p0 = __ldcg(st.pold + 3 * g); p1 = __ldcg(st.pold + 3 * g + 1); p2 = __ldcg(st.pold + 3 * g + 2);
-    p0 *= st.beta; p0 += r0; p1 *= st.beta; p1 += r1; p2 *= st.beta; p2 += r2;
-}
+// p = p*beta + r  (cgstep_beta -> vOp_avf, CGLinearSolver.inl:184-197), one component
+template <class R> __device__ __forceinline__ R p_update(R p, R beta, R r) { p *= beta; p += r; return p; }
 
 // once per solve: the node tables of the CTA's tiles and of the thread's shared node go to shared memory
-template <class R> __device__ __forceinline__ void persist_load_tables(const TileDev<R>& t, const PersistCG<R>& a, unsigned char* smem_raw, NodeRec* s_grec, uint32_t* s_gbase) {
+template <class R> __device__ __forceinline__ void persist_load_tables(const TileDev<R>& t, const PersistCG<R>& a, unsigned char* smem_raw, GRec<R>* s_grec) {
     const PersistLayout& L = a.lay;
     uint32_t* s_tidx = reinterpret_cast<uint32_t*>(smem_raw + L.off_tidx);
-    NodeRec* s_nrec = reinterpret_cast<NodeRec*>(smem_raw + L.off_nrec);
+    NodeRec<R>* s_nrec = reinterpret_cast<NodeRec<R>*>(smem_raw + L.off_nrec);
+    uint16_t* s_jds = reinterpret_cast<uint16_t*>(smem_raw + L.off_jds);
     const NodeEpilogue<R>& ep = a.ep;
     for (int c = 0; c < L.tiles_cached; ++c) {
         const int tile = blockIdx.x + c * gridDim.x;
@@ -156,66 +153,81 @@ template <class R> __device__ __forceinline__ void persist_load_tables(const Til
         const int n_touched = int(t.tile_node_off[tile + 1] - node_off), n_int = int(t.tile_nint[tile]);
         for (int k = threadIdx.x; k < n_touched; k += blockDim.x) {
             const uint32_t g = t.tile_nodes[node_off + k];
-            s_tidx[c * L.max_touched + k] = g;
-            if (k < n_int) s_nrec[c * L.max_int + k] = make_node_rec<R>(g, t.tile_val[node_off + k], ep.fixed && ep.fixed[g], ep.mass ? ep.mass[g] : R(0));
+            if (k < n_int) s_nrec[c * L.max_int + k] = NodeRec<R>{g, unsigned(t.tile_val[node_off + k]) | ((ep.fixed && ep.fixed[g]) ? 0x10000u : 0u), ep.mass ? ep.mass[g] : R(0)};
+            else s_tidx[c * L.max_shtouch + (k - n_int)] = g;
         }
+        for (int j = threadIdx.x; j <= t.maxval; j += blockDim.x) s_jds[c * (L.maxval + 1) + j] = t.tile_jds[size_t(tile) * (t.maxval + 1) + j];
     }
     // the thread's shared node: chunk = blockIdx.x * groups + threadIdx.x / kGatherChunk (one round: checked by the host)
     const int chunk = blockIdx.x * (blockDim.x / kGatherChunk) + threadIdx.x / kGatherChunk, k = threadIdx.x % kGatherChunk;
-    NodeRec rec{0xFFFFFFFFu, 0u, 0u, 0u};
-    uint32_t base = 0;
+    GRec<R> rec{0xFFFFFFFFu, 0u, 0u, R(0)};
     if (chunk < t.n_chunks) {
         const uint32_t g = t.sh_nodes[size_t(chunk) * kGatherChunk + k];
-        if (g != 0xFFFFFFFFu) {
-            rec = make_node_rec<R>(g, t.sh_val[size_t(chunk) * kGatherChunk + k], ep.fixed && ep.fixed[g], ep.mass ? ep.mass[g] : R(0));
-            base = t.sh_base[chunk] + k;
-        }
+        if (g != 0xFFFFFFFFu)
+            rec = GRec<R>{g, unsigned(t.sh_val[size_t(chunk) * kGatherChunk + k]) | ((ep.fixed && ep.fixed[g]) ? 0x10000u : 0u), t.sh_base[chunk] + k, ep.mass ? ep.mass[g] : R(0)};
     }
-    s_grec[threadIdx.x] = rec; s_gbase[threadIdx.x] = base;
+    s_grec[threadIdx.x] = rec;
     __syncthreads();
 }
 
-// phase 1 of an iteration: the new search direction of every node touched by the CTA's tiles goes to shared memory (one
-// round trip for all tiles); the tile that holds a node as interior also writes it to the p_new vector.
+// [A0] the new search direction of every node touched by the CTA's tiles, in shared memory.  Interior nodes: from the p and
+// the r the CTA itself left in shared memory (from HBM on the first iteration); shared nodes: from their owners' p_old and r.
 template <class R> __device__ __forceinline__ void persist_phase1(const TileDev<R>& t, const PersistCG<R>& a, const PersistState<R>& st, unsigned char* smem_raw) {
     typedef typename SVec<R>::T SV;
     const PersistLayout& L = a.lay;
     SV* s_in = reinterpret_cast<SV*>(smem_raw);
     const uint32_t* s_tidx = reinterpret_cast<const uint32_t*>(smem_raw + L.off_tidx);
+    const NodeRec<R>* s_nrec = reinterpret_cast<const NodeRec<R>*>(smem_raw + L.off_nrec);
+    const R* s_qr = reinterpret_cast<const R*>(smem_raw + L.off_qr);
     for (int c = 0; c < L.tiles_cached; ++c) {
         const int tile = blockIdx.x + c * gridDim.x;
         if (tile >= t.n_tiles) break;
         const int n_touched = int(t.tile_node_off[tile + 1] - t.tile_node_off[tile]), n_int = int(t.tile_nint[tile]);
         for (int k = threadIdx.x; k < n_touched; k += blockDim.x) {
-            const uint32_t g = s_tidx[c * L.max_touched + k];
             R p0, p1, p2;
-            persist_p_node<R>(st, a.r, g, p0, p1, p2);
+            if (k < n_int) {
+                if (st.first) { const R* r = a.r + 3 * size_t(s_nrec[c * L.max_int + k].g); p0 = r[0]; p1 = r[1]; p2 = r[2]; }
+                else {
+                    const SV po = s_in[c * L.max_touched + k];
+                    const R* rn = s_qr + 3 * size_t(c * L.max_int + k);
+                    p0 = p_update<R>(R(po.x), st.beta, rn[0]); p1 = p_update<R>(R(po.y), st.beta, rn[1]); p2 = p_update<R>(R(po.z), st.beta, rn[2]);
+                }
+            } else {
+                const size_t g = s_tidx[c * L.max_shtouch + (k - n_int)];
+                const R r0 = __ldcg(a.r + 3 * g), r1 = __ldcg(a.r + 3 * g + 1), r2 = __ldcg(a.r + 3 * g + 2);
+                if (st.first) { p0 = r0; p1 = r1; p2 = r2; }
+                else {
+                    p0 = p_update<R>(__ldcg(st.pold + 3 * g), st.beta, r0); p1 = p_update<R>(__ldcg(st.pold + 3 * g + 1), st.beta, r1);
+                    p2 = p_update<R>(__ldcg(st.pold + 3 * g + 2), st.beta, r2);
+                }
+            }
             s_in[c * L.max_touched + k] = SVec<R>::make(p0, p1, p2);
-            if (k < n_int) { R* d = st.pnew + 3 * size_t(g); d[0] = p0; d[1] = p1; d[2] = p2; }
         }
     }
     __syncthreads();
 }
 
-// phase 3 of a tile inside the CG loop: like tile_phase3, with the node's id / valence / mass / fixed flag from shared memory
-template <class R> __device__ __forceinline__ double persist_phase3(const TileDev<R>& t, int tile, int c, const PersistCG<R>& a, unsigned char* smem_raw, const uint16_t* s_jds) {
+// phase 3 of a tile inside the CG loop: like tile_phase3, with the node's valence / mass / fixed flag from shared memory, and
+// q left in shared memory for the x / r update
+template <class R> __device__ __forceinline__ double persist_phase3(const TileDev<R>& t, int tile, int c, const PersistCG<R>& a, unsigned char* smem_raw) {
     typedef typename SVec<R>::T SV;
     const PersistLayout& L = a.lay;
     const NodeEpilogue<R>& ep = a.ep;
     const SV* s_in = reinterpret_cast<const SV*>(smem_raw) + c * L.max_touched;
     const R* s_slot = reinterpret_cast<const R*>(smem_raw + L.off_slot);
-    const NodeRec* s_nrec = reinterpret_cast<const NodeRec*>(smem_raw + L.off_nrec) + c * L.max_int;
+    const NodeRec<R>* s_nrec = reinterpret_cast<const NodeRec<R>*>(smem_raw + L.off_nrec) + c * L.max_int;
+    R* s_qr = reinterpret_cast<R*>(smem_raw + L.off_qr) + 3 * size_t(c * L.max_int);
+    const uint16_t* s_jds = reinterpret_cast<const uint16_t*>(smem_raw + L.off_jds) + c * (L.maxval + 1);
     const int max_slots = L.max_slots;
     const int n_int = int(t.tile_nint[tile]);
     const bool plus = ep.sign > 0;
     double part = 0.0;
     for (int k = threadIdx.x; k < n_int; k += blockDim.x) {
-        const NodeRec rec = s_nrec[k];
+        const NodeRec<R> rec = s_nrec[k];
         const int val = int(rec.val_fixed & 0xFFFFu);
-        const R m = node_rec_mass<R>(rec);
         const SV pv = s_in[k];
         R ax = R(0), ay = R(0), az = R(0);
-        node_mass_m(ep, ep.pre_kind, m, R(pv.x), R(pv.y), R(pv.z), ax, ay, az);
+        node_mass_m(ep, ep.pre_kind, rec.mass, R(pv.x), R(pv.y), R(pv.z), ax, ay, az);
         int jj = 0;
         for (; jj + 4 <= val; jj += 4) {
             R cx[4], cy[4], cz[4];
@@ -234,7 +246,8 @@ template <class R> __device__ __forceinline__ double persist_phase3(const TileDe
             if (plus) { ax += s_slot[s]; ay += s_slot[max_slots + s]; az += s_slot[2 * max_slots + s]; }
             else { ax -= s_slot[s]; ay -= s_slot[max_slots + s]; az -= s_slot[2 * max_slots + s]; }
         }
-        part += node_post_m(ep, rec.g, m, (rec.val_fixed & 0x10000u) != 0, R(pv.x), R(pv.y), R(pv.z), ax, ay, az);
+        part += node_finish_m(ep, rec.mass, (rec.val_fixed & 0x10000u) != 0, R(pv.x), R(pv.y), R(pv.z), ax, ay, az);
+        s_qr[3 * k] = ax; s_qr[3 * k + 1] = ay; s_qr[3 * k + 2] = az;
     }
     return part;
 }
@@ -242,67 +255,102 @@ template <class R> __device__ __forceinline__ double persist_phase3(const TileDe
 // Everything of an iteration after the tiles: returns false when the solve is over.  `part`: this thread's share of
 // p.q over the interior nodes of the CTA's tiles.
 template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>& t, const PersistCG<R>& a, PersistState<R>& st, double part, double* red, double* bcast,
-                                                                const NodeRec* s_grec, const uint32_t* s_gbase) {
+                                                                unsigned char* smem_raw, const GRec<R>* s_grec) {
+    typedef typename SVec<R>::T SV;
     CGDev* cg = a.cg;
     const NodeEpilogue<R>& ep = a.ep;
-    // ---- [B] shared nodes.  Everything that does not depend on the other CTAs is requested before the barrier.
-    const NodeRec grec = s_grec[threadIdx.x];
+    const PersistLayout& L = a.lay;
+    // ---- [B] the thread's shared node.  Its p and r live in registers; x is requested before the barrier.
+    const GRec<R> grec = s_grec[threadIdx.x];
     const bool has_node = grec.g != 0xFFFFFFFFu;
-    R gp0 = R(0), gp1 = R(0), gp2 = R(0);
-    if (has_node) persist_p_node<R>(st, a.r, grec.g, gp0, gp1, gp2);
+    // p, r, x of the node are private to this thread; between iterations they rest in a coalesced scratch array (registers
+    // held across the element pass would spill there)
+    const size_t gs_n = size_t(gridDim.x) * blockDim.x, gs_i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    R gp0 = R(0), gp1 = R(0), gp2 = R(0), gr0 = R(0), gr1 = R(0), gr2 = R(0);
+    if (has_node) {
+        const size_t g3 = 3 * size_t(grec.g);
+        if (st.first) { gr0 = a.r[g3]; gr1 = a.r[g3 + 1]; gr2 = a.r[g3 + 2]; gp0 = gr0; gp1 = gr1; gp2 = gr2; }
+        else {
+            gr0 = a.gstate[3 * gs_n + gs_i]; gr1 = a.gstate[4 * gs_n + gs_i]; gr2 = a.gstate[5 * gs_n + gs_i];
+            gp0 = p_update<R>(a.gstate[gs_i], st.beta, gr0); gp1 = p_update<R>(a.gstate[gs_n + gs_i], st.beta, gr1); gp2 = p_update<R>(a.gstate[2 * gs_n + gs_i], st.beta, gr2);
+        }
+        R* d = st.pnew + g3; d[0] = gp0; d[1] = gp1; d[2] = gp2;      // for the tiles that touch the node, next iteration
+    }
     part = block_sum(part, red);
     trace_mark(ep.trace, kTraceTail, 1);
     const double den_tiles = grid_sync_sum(a.sync, st.sync_count, part, red, bcast);     // staged contributions are complete
     trace_mark(ep.trace, kTraceTail, 2);
     double part2 = 0.0;
+    R gq0 = R(0), gq1 = R(0), gq2 = R(0);
     if (has_node) {
         const int val = int(grec.val_fixed & 0xFFFFu);
-        const Quad<R>* stg = t.stage + s_gbase[threadIdx.x];
+        const Quad<R>* stg = t.stage + grec.base;
         const uint64_t pol = l2_policy_evict_first();
         Quad<R> b0[kGatherBatch], b1[kGatherBatch];
         gather_load<R>(b0, stg, 0, val, pol);
         gather_load<R>(b1, stg, kGatherBatch, val, pol);
-        const R m = node_rec_mass<R>(grec);
-        R* d = st.pnew + 3 * size_t(grec.g); d[0] = gp0; d[1] = gp1; d[2] = gp2;       // nobody else writes a shared node's p
-        R ax = R(0), ay = R(0), az = R(0);
-        node_mass_m(ep, ep.pre_kind, m, gp0, gp1, gp2, ax, ay, az);
-        if (b0[0].a == R(123456789)) trace_mark(ep.trace, kTraceTail, 15);   // (waits for the first staged entry)
-        trace_mark(ep.trace, kTraceTail, 8);
-        gather_sum<R>(b0, b1, stg, val, ep.sign > 0, ax, ay, az, pol);
-        if (ax == R(123456789)) trace_mark(ep.trace, kTraceTail, 15);
-        trace_mark(ep.trace, kTraceTail, 9);
-        part2 = node_post_m(ep, grec.g, m, (grec.val_fixed & 0x10000u) != 0, gp0, gp1, gp2, ax, ay, az);
+        node_mass_m(ep, ep.pre_kind, grec.mass, gp0, gp1, gp2, gq0, gq1, gq2);
+        gather_sum<R>(b0, b1, stg, val, ep.sign > 0, gq0, gq1, gq2, pol);
+        part2 = node_finish_m(ep, grec.mass, (grec.val_fixed & 0x10000u) != 0, gp0, gp1, gp2, gq0, gq1, gq2);
     }
+    const SV* s_in = reinterpret_cast<const SV*>(smem_raw);
+    const NodeRec<R>* s_nrec = reinterpret_cast<const NodeRec<R>*>(smem_raw + L.off_nrec);
+    R* s_qr = reinterpret_cast<R*>(smem_raw + L.off_qr);
     __syncthreads();
     part2 = block_sum(part2, red);
     trace_mark(ep.trace, kTraceTail, 3);
-    const double den = den_tiles + grid_sync_sum(a.sync, st.sync_count, part2, red, bcast);   // q and p_new are complete
+    const double den = den_tiles + grid_sync_sum(a.sync, st.sync_count, part2, red, bcast);
     trace_mark(ep.trace, kTraceTail, 4);
     bool stop = false;
     if (den != 0.0) { if (fabs(den) <= st.thr && !(st.it == 1 && st.tsc == 0)) stop = true; } else stop = true;
     if (blockIdx.x == 0 && threadIdx.x == 0) cg_after_den(cg, den);
     if (stop) return false;
-    // ---- [C]
+    // ---- [C] x += alpha p ; r -= alpha q, by the owners
     const double alpha_d = st.rho / den;
     const R alpha = R(alpha_d), malpha = R(-alpha_d);
     const bool a_one = (alpha_d == 1.0), ma_one = (-alpha_d == 1.0);
-    const size_t stride = size_t(gridDim.x) * blockDim.x, t0 = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    typedef typename Vec4T<R>::T V;
-    constexpr int N = Vec4T<R>::N;
-    const size_t nv = a.n3 / N;
-    V* xv = reinterpret_cast<V*>(a.x); V* rv = reinterpret_cast<V*>(a.r);
-    const V* pv = reinterpret_cast<const V*>(st.pnew); const V* qv = reinterpret_cast<const V*>(ep.out);
     double prr = 0.0;
-    for (size_t i = t0; i < nv; i += stride) {
-        V xx = xv[i], rr = __ldcg(rv + i); const V pp = __ldcg(pv + i), qq = __ldcg(qv + i);
-        prr += xr_vec(xx, rr, pp, qq, alpha, malpha, a_one, ma_one);
-        xv[i] = xx; rv[i] = rr;
+    if (has_node) {
+        const size_t g3 = 3 * size_t(grec.g);
+        R gx0, gx1, gx2;
+        if (st.first) { gx0 = a.x[g3]; gx1 = a.x[g3 + 1]; gx2 = a.x[g3 + 2]; }
+        else { gx0 = a.gstate[6 * gs_n + gs_i]; gx1 = a.gstate[7 * gs_n + gs_i]; gx2 = a.gstate[8 * gs_n + gs_i]; }
+        prr += xr_one<R>(gx0, gr0, gp0, gq0, alpha, malpha, a_one, ma_one);
+        prr += xr_one<R>(gx1, gr1, gp1, gq1, alpha, malpha, a_one, ma_one);
+        prr += xr_one<R>(gx2, gr2, gp2, gq2, alpha, malpha, a_one, ma_one);
+        a.r[g3] = gr0; a.r[g3 + 1] = gr1; a.r[g3 + 2] = gr2;                    // for the tiles that touch the node
+        a.gstate[gs_i] = gp0; a.gstate[gs_n + gs_i] = gp1; a.gstate[2 * gs_n + gs_i] = gp2;
+        a.gstate[3 * gs_n + gs_i] = gr0; a.gstate[4 * gs_n + gs_i] = gr1; a.gstate[5 * gs_n + gs_i] = gr2;
+        a.gstate[6 * gs_n + gs_i] = gx0; a.gstate[7 * gs_n + gs_i] = gx1; a.gstate[8 * gs_n + gs_i] = gx2;
     }
-    for (size_t i = nv * N + t0; i < a.n3; i += stride) { const R pp = __ldcg(st.pnew + i), qq = __ldcg(ep.out + i); prr += xr_one<R>(a.x[i], a.r[i], pp, qq, alpha, malpha, a_one, ma_one); }
+    // (requesting x / r before the den barrier was tried: the extra live registers spill in the shared-node phase, net loss)
+    for (int c = 0; c < L.tiles_cached; ++c) {
+        const int tile = blockIdx.x + c * gridDim.x;
+        if (tile >= t.n_tiles) break;
+        const int n_int = int(t.tile_nint[tile]);
+        const uint32_t node_off = t.tile_node_off[tile];
+        for (int k = threadIdx.x; k < n_int; k += blockDim.x) {
+            const SV pv = s_in[c * L.max_touched + k];
+            R* q = s_qr + 3 * size_t(c * L.max_int + k);
+            R x0, x1, x2, r0, r1, r2;
+            if (st.first) {
+                const size_t g3 = 3 * size_t(s_nrec[c * L.max_int + k].g);
+                x0 = a.x[g3]; x1 = a.x[g3 + 1]; x2 = a.x[g3 + 2]; r0 = a.r[g3]; r1 = a.r[g3 + 1]; r2 = a.r[g3 + 2];
+            } else {
+                const SV xv = a.xt[node_off + k], rv = a.rt[node_off + k];
+                x0 = R(xv.x); x1 = R(xv.y); x2 = R(xv.z); r0 = R(rv.x); r1 = R(rv.y); r2 = R(rv.z);
+            }
+            prr += xr_one<R>(x0, r0, R(pv.x), q[0], alpha, malpha, a_one, ma_one);
+            prr += xr_one<R>(x1, r1, R(pv.y), q[1], alpha, malpha, a_one, ma_one);
+            prr += xr_one<R>(x2, r2, R(pv.z), q[2], alpha, malpha, a_one, ma_one);
+            a.xt[node_off + k] = SVec<R>::make(x0, x1, x2); a.rt[node_off + k] = SVec<R>::make(r0, r1, r2);
+            q[0] = r0; q[1] = r1; q[2] = r2;
+        }
+    }
     __syncthreads();
     prr = block_sum(prr, red);
     trace_mark(ep.trace, kTraceTail, 5);
-    const double rho_new = grid_sync_sum(a.sync, st.sync_count, prr, red, bcast);          // x, r are complete
+    const double rho_new = grid_sync_sum(a.sync, st.sync_count, prr, red, bcast);          // r of the shared nodes is complete
     trace_mark(ep.trace, kTraceTail, 6);
     const int it2 = st.it + 1;
     bool stop2 = unsigned(it2) > st.max_iter;
@@ -313,6 +361,30 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
     st.rho = rho_new; st.it = it2; st.first = false;
     R* tmp = st.pold; st.pold = st.pnew; st.pnew = tmp;
     return true;
+}
+
+// after the last iteration: x back in the caller's flat vector (during the solve the owners keep it to themselves)
+template <class R> __device__ __forceinline__ void persist_finish(const TileDev<R>& t, const PersistCG<R>& a, const PersistState<R>& st, unsigned char* smem_raw, const GRec<R>* s_grec) {
+    typedef typename SVec<R>::T SV;
+    const PersistLayout& L = a.lay;
+    if (st.first) return;                    // no update was made: x is untouched
+    const GRec<R> grec = s_grec[threadIdx.x];
+    if (grec.g != 0xFFFFFFFFu) {
+        const size_t gs_n = size_t(gridDim.x) * blockDim.x, gs_i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+        R* d = a.x + 3 * size_t(grec.g); d[0] = a.gstate[6 * gs_n + gs_i]; d[1] = a.gstate[7 * gs_n + gs_i]; d[2] = a.gstate[8 * gs_n + gs_i];
+    }
+    const NodeRec<R>* s_nrec = reinterpret_cast<const NodeRec<R>*>(smem_raw + L.off_nrec);
+    for (int c = 0; c < L.tiles_cached; ++c) {
+        const int tile = blockIdx.x + c * gridDim.x;
+        if (tile >= t.n_tiles) break;
+        const int n_int = int(t.tile_nint[tile]);
+        const uint32_t node_off = t.tile_node_off[tile];
+        for (int k = threadIdx.x; k < n_int; k += blockDim.x) {
+            const SV xv = a.xt[node_off + k];
+            R* d = a.x + 3 * size_t(s_nrec[c * L.max_int + k].g);
+            d[0] = R(xv.x); d[1] = R(xv.y); d[2] = R(xv.z);
+        }
+    }
 }
 
 }  // namespace sb

@@ -227,13 +227,18 @@ template <class R> HD double node_post_v(const NodeEpilogue<R>& ep, uint32_t g, 
     return 0.0;
 }
 // same with the node's mass and fixed flag already loaded
-template <class R> HD double node_post_m(const NodeEpilogue<R>& ep, uint32_t g, R m, bool is_fixed, R vx, R vy, R vz, R ax, R ay, R az) {
+// ... and the result left in (ax, ay, az) instead of ep.out
+template <class R> HD double node_finish_m(const NodeEpilogue<R>& ep, R m, bool is_fixed, R vx, R vy, R vz, R& ax, R& ay, R& az) {
     node_mass_m(ep, ep.post_kind, m, vx, vy, vz, ax, ay, az);
     if (ep.has_scale) { ax *= ep.scale; ay *= ep.scale; az *= ep.scale; }
     if (is_fixed) { ax = R(0); ay = R(0); az = R(0); }
-    ep.out[3 * size_t(g)] = ax; ep.out[3 * size_t(g) + 1] = ay; ep.out[3 * size_t(g) + 2] = az;
     if (ep.dot_kind != DOT_NONE) return double(ax) * double(vx) + double(ay) * double(vy) + double(az) * double(vz);
     return 0.0;
+}
+template <class R> HD double node_post_m(const NodeEpilogue<R>& ep, uint32_t g, R m, bool is_fixed, R vx, R vy, R vz, R ax, R ay, R az) {
+    const double d = node_finish_m(ep, m, is_fixed, vx, vy, vz, ax, ay, az);
+    ep.out[3 * size_t(g)] = ax; ep.out[3 * size_t(g) + 1] = ay; ep.out[3 * size_t(g) + 2] = az;
+    return d;
 }
 template <class R> HD double node_post(const NodeEpilogue<R>& ep, uint32_t g, R ax, R ay, R az) {
     R vx = 0, vy = 0, vz = 0;

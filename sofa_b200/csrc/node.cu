@@ -14,6 +14,7 @@ namespace sb {
 // implemented in tet_fem.cu / hex_fem.cu
 template <class R> int tet_run(sofab200_tetfem* ff, bool dforce, const R* in, R k_factor, NodeEpilogue<R> ep, bool skip_gather);
 template <class R> int tet_cg_persistent(sofab200_tetfem* ff, R k_factor, PersistCG<R> a, size_t part_capacity);
+size_t tet_tile_node_count(sofab200_tetfem* ff);
 template <class R> TileDev<R> tet_tiledev(sofab200_tetfem* ff);
 template <class R> TileDev<R> hex_tiledev(sofab200_hexfem* ff);
 int tet_partial_count(sofab200_tetfem* ff);
@@ -160,6 +161,8 @@ template <class R> struct Node : sofab200_node {
     bool persistent = true;      // SOFAB200_CG_PERSISTENT=0 selects the multi-kernel loop
     DevBuf<R> p2;
     DevBuf<unsigned long long> sync_slots;
+    DevBuf<typename SVec<R>::T> xt, rt;
+    DevBuf<R> gstate;
     int tail_grid = 0;
     DevBuf<double> partials_rho;
     int cg_tail(R* x, double m, double bfac, double k) {
@@ -260,10 +263,13 @@ template <class R> struct Node : sofab200_node {
         if (persistent && tet && (kf_chk != 0.0 || bfac != 0.0)) {
             // the whole loop in one cooperative launch (cg_persist.cuh)
             if (!p2.p) SB_TRY(p2.alloc(n3));
+            const size_t n_tile_nodes = tet_tile_node_count(tet);
+            if (xt.n < n_tile_nodes) { SB_TRY(xt.alloc(n_tile_nodes)); SB_TRY(rt.alloc(n_tile_nodes)); }
+            if (!gstate.p) SB_TRY(gstate.alloc(size_t(9) * ctx->sm_count * 2048));
             if (!sync_slots.p) SB_TRY(sync_slots.alloc(3 * 2048 + 2));
             PersistCG<R> a;
             a.ep = make_mbk_ep(q.p, nullptr, p.p, m, bfac, false, 1.0, true, DOT_STORE, cg.p);
-            a.x = x; a.r = r.p; a.p0 = p.p; a.p1 = p2.p; a.n3 = n3; a.cg = cg.p; a.sync = sync_slots.p;
+            a.x = x; a.r = r.p; a.xt = xt.p; a.rt = rt.p; a.gstate = gstate.p; a.p0 = p.p; a.p1 = p2.p; a.n3 = n3; a.cg = cg.p; a.sync = sync_slots.p;
             a.debug = 0; if (const char* env = getenv("SOFAB200_DEBUG_MODE")) a.debug = atoi(env);
             SB_CUDA(cudaMemsetAsync(sync_slots.p, 0, sync_slots.n * sizeof(unsigned long long), ctx->stream));
             const int rc = tet_cg_persistent<R>(tet, R(kf_chk), a, sync_slots.n);

@@ -24,7 +24,7 @@ struct HostPlan {
     std::vector<uint16_t> sh_val;
     std::vector<uint32_t> sh_base;        // [n_chunks] first staging entry of the chunk's ELL block
     size_t stage_n = 0;
-    int max_touched = 0, max_slots = 0, max_int = 1;
+    int max_touched = 0, max_slots = 0, max_int = 1, max_shtouch = 1;
     size_t n_interior = 0, n_staged_corners = 0, n_demoted = 0;
 };
 
@@ -179,6 +179,7 @@ inline std::string build_plan(HostPlan& P, int n_nodes, int n_elems, int npe, co
         const size_t touched = in.size() + sh.size();
         if (touched >= 65535) return "tile touches more than 65534 nodes; use a smaller tile";
         P.max_touched = std::max<int>(P.max_touched, int(touched));
+        P.max_shtouch = std::max<int>(P.max_shtouch, int(sh.size()));
         for (size_t s = s0; s < s1; ++s) {
             const uint32_t e = P.order[s];
             if (e == 0xFFFFFFFFu) continue;

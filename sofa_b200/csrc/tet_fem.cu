@@ -104,7 +104,7 @@ template <class R, int MODE, int MAXT, bool PF> static int tet_persist_variant(T
     int dev_smem_optin = 0;
     SB_CUDA(cudaDeviceGetAttribute(&dev_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ff.ctx->device));
     for (int tiles_per_cta = 1; tiles_per_cta <= 2; ++tiles_per_cta) {
-        const PersistLayout L = persist_layout<R>(tiles_per_cta, P.max_touched, P.max_slots, P.max_int);
+        const PersistLayout L = persist_layout<R>(tiles_per_cta, P.max_touched, P.max_slots, P.max_int, P.max_shtouch, P.maxval);
         if (L.total + fa.sharedSizeBytes > size_t(dev_smem_optin)) break;
         SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<unsigned>(L.total, 1024))));
         int per_sm = 0;
@@ -175,6 +175,10 @@ template int tet_run<float>(sofab200_tetfem*, bool, const float*, float, NodeEpi
 template int tet_run<double>(sofab200_tetfem*, bool, const double*, double, NodeEpilogue<double>, bool);
 
 int tet_real(sofab200_tetfem* ff) { return ff->real; }
+size_t tet_tile_node_count(sofab200_tetfem* base) {
+    if (base->real == SOFAB200_F32) return static_cast<TetFF<float>*>(base)->h.plan.tile_nodes.size();
+    return static_cast<TetFF<double>*>(base)->h.plan.tile_nodes.size();
+}
 size_t tet_nodes(sofab200_tetfem* ff) { return ff->n_nodes; }
 int tet_partial_count(sofab200_tetfem* base) {
     if (base->real == SOFAB200_F32) { auto& ff = *static_cast<TetFF<float>*>(base); return ff.h.plan.n_tiles + ff.h.plan.n_chunks; }

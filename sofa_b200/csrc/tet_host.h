@@ -157,6 +157,7 @@ template <class R> static std::string tet_host_build(HostTet<R>& ff, size_t n_no
     auto tile_for = [&](int k) { return std::max(32, (int((n_tets + size_t(sm_count) * k - 1) / (size_t(sm_count) * k)) + 31) / 32 * 32); };
     if (tile_e <= 0) tile_e = tile_for(k_waves);
     tile_e = std::max(32, (tile_e + 31) / 32 * 32);
+    int persist_tries = 0;
     for (;;) {
         const std::string err = build_plan(ff.plan, int(n_nodes), int(n_tets), 4, tets, pos.data(), tile_e, chunk, kStageFlag, smem_limit, sizeof(SV), 3 * sizeof(R));
         ff.smem_bytes = tile_smem_bytes<R>(ff.plan.max_touched, ff.plan.max_slots);
@@ -165,8 +166,26 @@ template <class R> static std::string tet_host_build(HostTet<R>& ff, size_t n_no
         if ((too_big || too_staged) && !fixed_tile && tile_e > 32) { tile_e = tile_for(++k_waves); continue; }
         if (!err.empty()) return err;
         if (too_big) return "tile does not fit in shared memory; use a smaller tile_elems";
+        // The persistent CG kernel keeps the node tables of two tiles next to the slots.  196 KB is the largest shared-memory
+        // carve-out that still leaves the L1 enough room for the in-flight element records (measured: the next step, 228 KB,
+        // slows the stream by 15 %), so if its layout is a little over, give the slots a smaller budget and plan again.
+        if (!fixed_tile && ff.plan.n_tiles <= 2 * sm_count && persist_tries < 3) {
+            const int tpc = ff.plan.n_tiles > sm_count ? 2 : 1;
+            const PersistLayout L = persist_layout<R>(tpc, ff.plan.max_touched, ff.plan.max_slots, ff.plan.max_int, ff.plan.max_shtouch, ff.plan.maxval);
+            const size_t need = L.total + persist_static_smem<R>(512) + 1024, target = 196 * 1024;
+            if (need > target && need - target < 24 * 1024) {
+                const size_t tile_bytes = tile_smem_bytes<R>(ff.plan.max_touched, ff.plan.max_slots);
+                smem_limit = std::min(smem_limit, tile_bytes) - (need - target) - 256;
+                ++persist_tries;
+                continue;
+            }
+        }
         break;
     }
+    if (getenv("SOFAB200_VERBOSE"))
+        fprintf(stderr, "[sofa_b200] tet plan: %d tiles x %d elems, max_touched %d, max_slots %d, max_int %d, shared %d in %d chunks, staged %zu, demoted %zu, smem %zu B\n",
+                ff.plan.n_tiles, ff.plan.tile_e, ff.plan.max_touched, ff.plan.max_slots, ff.plan.max_int, ff.plan.n_shared, ff.plan.n_chunks, ff.plan.n_staged_corners,
+                ff.plan.n_demoted, ff.smem_bytes);
     tet_fill_planes(ff);
     return "";
 }

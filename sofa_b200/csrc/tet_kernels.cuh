@@ -274,9 +274,7 @@ __global__ void __launch_bounds__(MAXT) tet_cg_persistent_kernel(TetDev<R> d, Pe
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[32];
     __shared__ double bcast;
-    __shared__ uint16_t s_jds[2][1024];
-    __shared__ NodeRec s_grec[MAXT];
-    __shared__ uint32_t s_gbase[MAXT];
+    __shared__ GRec<R> s_grec[MAXT];
     typedef typename SVec<R>::T SV;
     CGDev* cg = a.cg;
     if (cg->done) return;
@@ -285,11 +283,7 @@ __global__ void __launch_bounds__(MAXT) tet_cg_persistent_kernel(TetDev<R> d, Pe
     SV* s_in = reinterpret_cast<SV*>(smem_raw);
     R* s_slot = reinterpret_cast<R*>(smem_raw + L.off_slot);
     PersistState<R> st(a);
-    for (int c = 0; c < L.tiles_cached; ++c) {
-        const int tile = blockIdx.x + c * gridDim.x;
-        if (tile < t.n_tiles) for (int j = threadIdx.x; j <= t.maxval; j += blockDim.x) s_jds[c][j] = t.tile_jds[size_t(tile) * (t.maxval + 1) + j];
-    }
-    persist_load_tables<R>(t, a, smem_raw, s_grec, s_gbase);
+    persist_load_tables<R>(t, a, smem_raw, s_grec);
     for (;;) {
         trace_mark(a.ep.trace, kTraceTail, 0);
         // ---- [A]
@@ -299,20 +293,16 @@ __global__ void __launch_bounds__(MAXT) tet_cg_persistent_kernel(TetDev<R> d, Pe
         for (int c = 0; c < L.tiles_cached; ++c) {
             const int tile = blockIdx.x + c * gridDim.x;
             if (tile >= t.n_tiles) break;
-            if (a.debug & 8) {   // HBM -> L2 prefetch of the NEXT tile's records (the next iteration's first tile after the last one)
-                const int nt = tile + gridDim.x;
-                if (c + 1 < L.tiles_cached && nt < t.n_tiles) tet_prefetch_tile<R>(d, nt, (a.debug >> 4) & 3);
-            }
             tet_tile_elements<R, MODE, PF>(d, tile, s_in + c * L.max_touched, s_slot, L.max_slots);
-            if ((a.debug & 4) && (c + 1 == L.tiles_cached || tile + int(gridDim.x) >= t.n_tiles)) tet_prefetch_tile<R>(d, blockIdx.x, (a.debug >> 4) & 3);
             __syncthreads();
             if (c == 0) trace_mark(a.ep.trace, kTraceTail, 13);
-            part += persist_phase3<R>(t, tile, c, a, smem_raw, s_jds[c]);
+            part += persist_phase3<R>(t, tile, c, a, smem_raw);
             __syncthreads();
             if (c == 0) trace_mark(a.ep.trace, kTraceTail, 14);
         }
-        if (!persist_rest<R>(t, a, st, part, red, &bcast, s_grec, s_gbase)) break;
+        if (!persist_rest<R>(t, a, st, part, red, &bcast, smem_raw, s_grec)) break;
     }
+    persist_finish<R>(t, a, st, smem_raw, s_grec);
 }
 
 // rotations[e] back in ORIGINAL element order (getRotations-style accessors, parity checks)
