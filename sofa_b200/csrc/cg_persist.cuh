@@ -96,24 +96,41 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// arrive + wait, no value
+__device__ __forceinline__ void grid_sync(unsigned long long* slots, unsigned& s) {
+    const unsigned G = gridDim.x;
+    unsigned* counter = reinterpret_cast<unsigned*>(slots + size_t(3) * G);
+    __syncthreads();                       // the CTA's writes precede thread 0's release
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const unsigned target = (s + 1) * G;
+        while (ld_acquire_u32(counter) < target) { }
+    }
+    __syncthreads();                       // thread 0's acquire precedes every thread's later reads
+    ++s;
+}
 __device__ __forceinline__ double grid_sync_sum(unsigned long long* slots, unsigned& s, double cta_value /* thread 0 */, double* red, double* bcast) {
     const unsigned G = gridDim.x;
     double* cur = reinterpret_cast<double*>(slots) + size_t(s % 3) * G;
     unsigned* counter = reinterpret_cast<unsigned*>(slots + size_t(3) * G);
-    __syncthreads();                       // the CTA's writes precede thread 0's release
+    __syncthreads();
     if (threadIdx.x == 0) {
         cur[blockIdx.x] = cta_value;
         __threadfence();
         atomicAdd(counter, 1u);
         const unsigned target = (s + 1) * G;
         while (ld_acquire_u32(counter) < target) { }
-        __threadfence();
     }
     __syncthreads();
-    double v = 0.0;
-    for (unsigned i = threadIdx.x; i < G; i += blockDim.x) v += __ldcg(cur + i);
-    v = block_sum(v, red);
-    if (threadIdx.x == 0) *bcast = v;
+    // warp 0 adds the G values in a fixed order and broadcasts
+    if (threadIdx.x < 32) {
+        double v = 0.0;
+        for (unsigned i = threadIdx.x; i < G; i += 32) v += __ldcg(cur + i);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) *bcast = v;
+    }
     __syncthreads();
     ++s;
     return *bcast;
@@ -276,11 +293,10 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
         }
         R* d = st.pnew + g3; d[0] = gp0; d[1] = gp1; d[2] = gp2;      // for the tiles that touch the node, next iteration
     }
-    part = block_sum(part, red);
     trace_mark(ep.trace, kTraceTail, 1);
-    const double den_tiles = grid_sync_sum(a.sync, st.sync_count, part, red, bcast);     // staged contributions are complete
+    grid_sync(a.sync, st.sync_count);                  // staged contributions are complete
     trace_mark(ep.trace, kTraceTail, 2);
-    double part2 = 0.0;
+    double part2 = part;                               // p.q of the interior nodes + (below) of the thread's shared node
     R gq0 = R(0), gq1 = R(0), gq2 = R(0);
     if (has_node) {
         const int val = int(grec.val_fixed & 0xFFFFu);
@@ -291,7 +307,7 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
         gather_load<R>(b1, stg, kGatherBatch, val, pol);
         node_mass_m(ep, ep.pre_kind, grec.mass, gp0, gp1, gp2, gq0, gq1, gq2);
         gather_sum<R>(b0, b1, stg, val, ep.sign > 0, gq0, gq1, gq2, pol);
-        part2 = node_finish_m(ep, grec.mass, (grec.val_fixed & 0x10000u) != 0, gp0, gp1, gp2, gq0, gq1, gq2);
+        part2 += node_finish_m(ep, grec.mass, (grec.val_fixed & 0x10000u) != 0, gp0, gp1, gp2, gq0, gq1, gq2);
     }
     const SV* s_in = reinterpret_cast<const SV*>(smem_raw);
     const NodeRec<R>* s_nrec = reinterpret_cast<const NodeRec<R>*>(smem_raw + L.off_nrec);
@@ -299,7 +315,7 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
     __syncthreads();
     part2 = block_sum(part2, red);
     trace_mark(ep.trace, kTraceTail, 3);
-    const double den = den_tiles + grid_sync_sum(a.sync, st.sync_count, part2, red, bcast);
+    const double den = grid_sync_sum(a.sync, st.sync_count, part2, red, bcast);
     trace_mark(ep.trace, kTraceTail, 4);
     bool stop = false;
     if (den != 0.0) { if (fabs(den) <= st.thr && !(st.it == 1 && st.tsc == 0)) stop = true; } else stop = true;
