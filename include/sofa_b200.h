@@ -128,6 +128,8 @@ typedef struct sofab200_tetfem_desc {
     size_t n_local_stiffness;   /* Data `localStiffnessFactor` (may be 0)                                  */
     const double* local_stiffness;
     int tile_elems;             /* elements per CTA tile of the device layout; 0 = library default         */
+    const unsigned char* shared_nodes; /* optional, n_nodes flags: nodes whose contributions must take the staging path
+                                 * (partition-interface nodes of a multi-GPU run, see sofab200_node_set_peer); NULL = none */
 } sofab200_tetfem_desc;
 
 /* init()+reinit() [TFF].inl:1257-1545: per-element material stiffness, rest rotation, rotated rest
@@ -269,6 +271,32 @@ typedef struct sofab200_halo_desc {
  * trip per iteration and still replayed from one CUDA graph per step.  The node's vertexMass must hold the global lumped
  * mass on owned nodes and 0 elsewhere (sofab200_node_set_vertex_mass). */
 int sofab200_node_set_distributed(sofab200_node* node, sofab200_comm* comm, const sofab200_halo_desc* halo);
+
+/* ---- peer memory: the multi-GPU CG loop in ONE persistent kernel per GPU, exchanging over NVLink ------------------------
+ * Every rank allocates a mailbox (sofab200_peer_alloc: cudaMalloc + CUDA IPC handle), ships the 64-byte handle to the other
+ * ranks of the node by any means (tests and bench use torch.distributed), maps theirs (sofab200_peer_open) and hands all the
+ * mapped base pointers to its solver node (sofab200_node_set_peer, after sofab200_node_set_distributed).  From then on
+ * sofab200_node_cg_solve / _step run the persistent CG kernel on every GPU: the partial sums of the interface nodes are stored
+ * straight into the neighbours' mailboxes, the dot products are all-reduced through the mailboxes (every rank adds the ranks'
+ * values in rank order), and the GPUs synchronise with sequence-numbered flags -- no NCCL call and no kernel boundary inside
+ * the loop.  The force field must have been created with the interface nodes flagged in sofab200_tetfem_desc::shared_nodes.
+ * Falls back to the NCCL loop when the mesh does not fit the persistent kernel.  No reference counterpart. */
+#define SOFAB200_IPC_HANDLE_BYTES 64
+int sofab200_peer_alloc(sofab200_ctx* ctx, size_t bytes, void** dev_ptr, unsigned char handle[SOFAB200_IPC_HANDLE_BYTES]);
+int sofab200_peer_open(sofab200_ctx* ctx, const unsigned char handle[SOFAB200_IPC_HANDLE_BYTES], void** dev_ptr);
+int sofab200_peer_close(sofab200_ctx* ctx, void* dev_ptr);   /* a pointer obtained from sofab200_peer_open  */
+int sofab200_peer_free(sofab200_ctx* ctx, void* dev_ptr);    /* a pointer obtained from sofab200_peer_alloc */
+/* Bytes this node's mailbox needs (valid after sofab200_node_set_distributed). */
+size_t sofab200_node_peer_bytes(const sofab200_node* node);
+typedef struct sofab200_peer_desc {
+    int rank, world;            /* world <= 8 (one NVSwitch domain)                                                        */
+    void* const* peer_base;     /* [world] mailbox of every rank as mapped in THIS process (own allocation at [rank])      */
+    const size_t* remote_off;   /* [n_neighbours] (order of sofab200_halo_desc::nb_rank): first inbox row, in neighbour k's
+                                 * mailbox, of the block it receives from this rank (= its cumulated nb_count before us)    */
+} sofab200_peer_desc;
+/* peer->peer_base == NULL leaves peer mode (every rank of a job must run the same loop).  SOFAB200_ERR_UNSUPPORTED when the
+ * rank's partition does not fit the persistent kernel. */
+int sofab200_node_set_peer(sofab200_node* node, const sofab200_peer_desc* peer);
 
 /* CGLinearSolver keeps `timeStepCount` to silence first-step warnings ([CG]:161-176); reset() restores 0. */
 int sofab200_node_reset(sofab200_node* node);

@@ -21,7 +21,7 @@ class Sofab200Error(RuntimeError):
 class TetFemDesc(C.Structure):
     _fields_ = [("method", C.c_int), ("n_young", C.c_size_t), ("young", C.POINTER(C.c_double)), ("n_poisson", C.c_size_t),
                 ("poisson", C.POINTER(C.c_double)), ("n_local_stiffness", C.c_size_t), ("local_stiffness", C.POINTER(C.c_double)),
-                ("tile_elems", C.c_int)]
+                ("tile_elems", C.c_int), ("shared_nodes", C.POINTER(C.c_ubyte))]
 
 
 class HexFemDesc(C.Structure):
@@ -38,6 +38,10 @@ class HaloDesc(C.Structure):
     _fields_ = [("owned", C.POINTER(C.c_ubyte)), ("n_interface", C.c_size_t), ("interface", C.POINTER(C.c_uint32)), ("my_slot", C.POINTER(C.c_int32)),
                 ("max_sharers", C.c_int), ("n_neighbours", C.c_int), ("nb_rank", C.POINTER(C.c_int)), ("nb_count", C.POINTER(C.c_size_t)),
                 ("nb_rows", C.POINTER(C.POINTER(C.c_uint32))), ("nb_slot", C.POINTER(C.POINTER(C.c_int32)))]
+
+
+class PeerDesc(C.Structure):
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("peer_base", C.POINTER(C.c_void_p)), ("remote_off", C.POINTER(C.c_size_t))]
 
 
 class SolverParams(C.Structure):
@@ -98,6 +102,12 @@ SYMBOLS = {
     "sofab200_comm_create": (_I, [_P, _I, _I, _P, C.POINTER(_P)]),
     "sofab200_comm_destroy": (_I, [_P]),
     "sofab200_node_set_distributed": (_I, [_P, _P, C.POINTER(HaloDesc)]),
+    "sofab200_peer_alloc": (_I, [_P, _SZ, C.POINTER(_P), C.POINTER(C.c_ubyte)]),
+    "sofab200_peer_open": (_I, [_P, C.POINTER(C.c_ubyte), C.POINTER(_P)]),
+    "sofab200_peer_close": (_I, [_P, _P]),
+    "sofab200_peer_free": (_I, [_P, _P]),
+    "sofab200_node_peer_bytes": (_SZ, [_P]),
+    "sofab200_node_set_peer": (_I, [_P, C.POINTER(PeerDesc)]),
 }
 
 _lib = None

@@ -68,6 +68,17 @@ class Context:
         check(self.L.sofab200_ctx_profile_end(self.h, ms, cnt))
         return {k: dict(ms=ms[i], launches=int(cnt[i])) for i, k in enumerate(self.PROFILE_CLASSES)}
 
+    def peer_alloc(self, nbytes):
+        """A zeroed mailbox in device memory + its 64-byte CUDA IPC handle (bytes) for the other ranks of the node."""
+        ptr = _P(); h = (C.c_ubyte * 64)()
+        check(self.L.sofab200_peer_alloc(self.h, int(nbytes), C.byref(ptr), h))
+        return ptr.value, bytes(h)
+
+    def peer_open(self, handle):
+        ptr = _P(); h = (C.c_ubyte * 64)(*handle)
+        check(self.L.sofab200_peer_open(self.h, h, C.byref(ptr)))
+        return ptr.value
+
     def trace_begin(self):
         check(self.L.sofab200_ctx_trace_begin(self.h))
 
@@ -156,7 +167,7 @@ class TetrahedronFEMForceField:
     rayleighStiffness (BaseForceField)."""
 
     def __init__(self, mstate, tetrahedra, youngModulus=5000.0, poissonRatio=0.45, method="large", localStiffnessFactor=None,
-                 rayleighStiffness=0.0, tileElems=0):
+                 rayleighStiffness=0.0, tileElems=0, sharedNodes=None):
         if method not in TET_METHODS:
             raise ValueError(f"method must be one of {list(TET_METHODS)}")
         self.mstate, self.ctx = mstate, mstate.ctx
@@ -168,6 +179,9 @@ class TetrahedronFEMForceField:
         if localStiffnessFactor is not None:
             l, lp = _darr(localStiffnessFactor); d.n_local_stiffness, d.local_stiffness = len(l), lp
         d.tile_elems = int(tileElems)
+        if sharedNodes is not None:      # nodes that must take the staging path (partition interface of a multi-GPU run)
+            self._shared = np.zeros(mstate.size, np.uint8); self._shared[np.asarray(sharedNodes, np.int64)] = 1
+            d.shared_nodes = self._shared.ctypes.data_as(C.POINTER(C.c_ubyte))
         self.h = _P()
         rest = mstate.rest_position_host
         check(self.ctx.L.sofab200_tetfem_create(self.ctx.h, mstate.real, mstate.size, rest.ctypes.data_as(_P), self.tetrahedra.shape[0],
@@ -364,6 +378,24 @@ class SolverNode:
         d.nb_rank, d.nb_count, d.nb_rows, d.nb_slot = nb_rank, nb_count, rows_p, slots_p
         check(self.ctx.L.sofab200_node_set_distributed(self.h, comm.h, C.byref(d)))
         self._comm = comm
+        self._nb_ranks = [s for s, _ in nbs]
+        self._nb_counts = [len(v["rows"]) for _, v in nbs]
+
+    def peer_bytes(self):
+        return int(self.ctx.L.sofab200_node_peer_bytes(self.h))
+
+    def set_peer(self, rank, world, peer_bases, remote_off):
+        """Multi-GPU CG in one persistent kernel per GPU over peer memory (sofab200_node_set_peer).  peer_bases: every rank's
+        mailbox as mapped here; remote_off[k]: first inbox row of our block in neighbour k's mailbox."""
+        d = _lib.PeerDesc(); d.rank, d.world = int(rank), int(world)
+        bases = (C.c_void_p * world)(*[int(b) for b in peer_bases])
+        offs = (C.c_size_t * max(len(remote_off), 1))(*[int(o) for o in remote_off])
+        d.peer_base, d.remote_off = bases, offs
+        check(self.ctx.L.sofab200_node_set_peer(self.h, C.byref(d)))
+
+    def clear_peer(self):
+        d = _lib.PeerDesc()
+        check(self.ctx.L.sofab200_node_set_peer(self.h, C.byref(d)))
 
     def cg_solve(self, x, b, mFactor, bFactor, kFactor, sync=True):
         it = C.c_int()

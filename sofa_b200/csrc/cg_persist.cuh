@@ -73,6 +73,25 @@ template <class R> inline PersistLayout persist_layout(int tiles_per_cta, int ma
 // static shared memory of the kernel for a CTA of `threads` (the per-thread shared-node records + reduction scratch)
 template <class R> inline size_t persist_static_smem(int threads) { return sizeof(GRec<R>) * size_t(threads) + 33 * sizeof(double); }
 
+// ---- multi-GPU: peer memory over NVLink (CUDA IPC mappings of every rank's mailbox), no NCCL inside the loop ---------------
+constexpr int kMaxPeers = 8;
+struct ARSlot { double v; unsigned long long seq; };
+template <class R> struct PeerDev {
+    int enabled, rank, world, n_nb, max_sh;
+    int nb_rank[kMaxPeers];
+    unsigned long long* hflag;                 // local: [kMaxPeers] halo sequence number written by rank r
+    unsigned long long* nb_hflag[kMaxPeers];   // neighbour k's hflag array (peer memory)
+    ARSlot* ar;                                // local: [2][kMaxPeers] all-reduce slots (double-buffered by sequence parity)
+    ARSlot* peer_ar[kMaxPeers];                // rank r's ar array (peer memory, own included)
+    unsigned long long* epoch;                 // local: launches done so far (sequence numbers are never reset)
+    R* inbox;                                  // local: partial q of interface nodes received from the neighbours
+    R* nb_inbox[kMaxPeers];                    // neighbour k's inbox (peer memory)
+    const int32_t* sh_if_row;                  // aligned with sh_nodes: row of the node in the interface table, or -1
+    const int32_t* src;                        // [n_if][max_sh] in ascending-rank order: -1 own partial, -2 nobody, else inbox row
+    const int2* if_send;                       // [n_if][max_sh-1]: {neighbour index or -1, row in that neighbour's inbox}
+    const unsigned char* owned;                // [n_nodes] 1 = this rank counts the node in dot products
+};
+
 template <class R> struct PersistCG {
     NodeEpilogue<R> ep;     // epilogue of q = A p: mass / projection terms, dot_kind = DOT_STORE (out is not used)
     R* x; R* r;
@@ -83,6 +102,7 @@ template <class R> struct PersistCG {
     CGDev* cg;
     unsigned long long* sync;   // [3 * gridDim.x + 1] grid_sync_sum slots and arrival counter, zero at launch
     PersistLayout lay;
+    PeerDev<R> peer;
     int debug;              // tuning experiments (SOFAB200_DEBUG_MODE)
 };
 
@@ -136,6 +156,92 @@ __device__ __forceinline__ double grid_sync_sum(unsigned long long* slots, unsig
     return *bcast;
 }
 
+// ---- grid sync that also crosses the GPUs (multi-GPU mode) ------------------------------------------------------------------
+// Local arrival as above; CTA 0 is the leader: once every CTA of this GPU has arrived it adds their values, talks to the other
+// GPUs through peer memory (kind 1: tells the neighbours "my halo rows are in your inbox" and waits for theirs; kind 2: all-reduce
+// of one double, every rank adds the ranks' values in rank order), publishes the result and releases the local CTAs.
+// Every wait gives up after ~4 s (a rank that never arrives must not hang the GPUs): the solve is then marked as failed.
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+constexpr unsigned long long kSyncTimeoutNs = 4000000000ull;
+struct DistSeq { unsigned long long base; unsigned halo, ar; };
+template <class R> __device__ __forceinline__ double dist_sync(const PersistCG<R>& a, unsigned& s, DistSeq& xs, double cta_value, int kind, double* bcast, bool& failed) {
+    const unsigned G = gridDim.x;
+    unsigned long long* slots = a.sync;
+    double* cur = reinterpret_cast<double*>(slots) + size_t(s % 3) * G;
+    unsigned* counter = reinterpret_cast<unsigned*>(slots + size_t(3) * G);
+    unsigned* release = counter + 1;
+    double* result = reinterpret_cast<double*>(slots + size_t(3) * G + 1);
+    unsigned* abort_flag = reinterpret_cast<unsigned*>(slots + size_t(3) * G + 2);
+    const PeerDev<R>& P = a.peer;
+    __syncthreads();
+    if (threadIdx.x == 0) { cur[blockIdx.x] = cta_value; __threadfence_system(); atomicAdd(counter, 1u); }
+    if (blockIdx.x == 0) {
+        __shared__ int s_fail;
+        if (threadIdx.x == 0) {
+            s_fail = 0;
+            const unsigned long long t0 = globaltimer_ns();
+            while (ld_acquire_u32(counter) < (s + 1) * G) { if (globaltimer_ns() - t0 > kSyncTimeoutNs) { s_fail = 1; break; } }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            double v = 0.0;
+            for (unsigned i = threadIdx.x; i < G; i += 32) v += __ldcg(cur + i);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (threadIdx.x == 0) {
+                double tot = v;
+                int fail = s_fail;
+                const unsigned long long t0 = globaltimer_ns();
+                if (kind == 1 && !fail) {
+                    const unsigned long long seq = xs.base + xs.halo + 1;
+                    for (int k = 0; k < P.n_nb; ++k) st_release_sys_u64(P.nb_hflag[k] + P.rank, seq);
+                    for (int k = 0; k < P.n_nb && !fail; ++k)
+                        while (ld_acquire_sys_u64(P.hflag + P.nb_rank[k]) < seq) { if (globaltimer_ns() - t0 > kSyncTimeoutNs) { fail = 1; break; } }
+                } else if (kind == 2 && !fail) {
+                    const unsigned long long seq = xs.base + xs.ar + 1;
+                    const int set = int(seq & 1ull);
+                    for (int r = 0; r < P.world; ++r) {
+                        ARSlot* dst = P.peer_ar[r] + set * kMaxPeers + P.rank;
+                        dst->v = v;
+                        st_release_sys_u64(&dst->seq, seq);
+                    }
+                    tot = 0.0;
+                    for (int r = 0; r < P.world && !fail; ++r) {
+                        const ARSlot* src = P.ar + set * kMaxPeers + r;
+                        while (ld_acquire_sys_u64(&src->seq) != seq) { if (globaltimer_ns() - t0 > kSyncTimeoutNs) { fail = 1; break; } }
+                        tot += *reinterpret_cast<const volatile double*>(&src->v);
+                    }
+                }
+                if (fail) *abort_flag = 1u;
+                *result = tot;
+                __threadfence();
+                st_release_gpu_u32(release, s + 1);
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        const unsigned long long t0 = globaltimer_ns();
+        while (ld_acquire_u32(release) < s + 1) { if (globaltimer_ns() - t0 > 3 * kSyncTimeoutNs) { *abort_flag = 1u; break; } }
+        *bcast = __ldcg(result);
+        if (*reinterpret_cast<volatile unsigned*>(abort_flag)) *bcast = __longlong_as_double(0x7FF8000000000001ll);   // NaN: failed
+    }
+    __syncthreads();
+    ++s;
+    if (kind == 1) ++xs.halo; else if (kind == 2) ++xs.ar;
+    const double r = *bcast;
+    if (r != r && (__double_as_longlong(r) & 0xFFFFFFFFll) == 1ll) failed = true;
+    return r;
+}
+
 template <class R> struct PersistState {
     R* pold; R* pnew;
     double rho, normb, tol, thr;
@@ -144,12 +250,16 @@ template <class R> struct PersistState {
     bool first;
     R beta;
     unsigned sync_count;
+    DistSeq xs;
+    bool failed;
+    bool updated;           // x has been updated at least once (persist_finish must write it back)
     __device__ explicit PersistState(const PersistCG<R>& a) {
         pold = a.p0; pnew = a.p1;
         const CGDev* cg = a.cg;
         rho = cg->rho; normb = cg->normb; tol = cg->tolerance; thr = cg->threshold;
         it = cg->it; tsc = cg->time_step_count; max_iter = cg->max_iter;
-        first = true; beta = R(0); sync_count = 0;
+        first = true; beta = R(0); sync_count = 0; failed = false; updated = false;
+        xs.base = a.peer.enabled ? (*a.peer.epoch) * 65536ull : 0ull; xs.halo = 0; xs.ar = 0;
     }
 };
 
@@ -283,6 +393,10 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
     // p, r, x of the node are private to this thread; between iterations they rest in a coalesced scratch array (registers
     // held across the element pass would spill there)
     const size_t gs_n = size_t(gridDim.x) * blockDim.x, gs_i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const PeerDev<R>& P = a.peer;
+    // multi-GPU: is the node on the partition interface (row of the halo tables), and does this rank count it in dot products
+    const int if_row = (P.enabled && has_node) ? P.sh_if_row[gs_i] : -1;
+    const bool counted = if_row < 0 || P.owned[grec.g] != 0;
     R gp0 = R(0), gp1 = R(0), gp2 = R(0), gr0 = R(0), gr1 = R(0), gr2 = R(0);
     if (has_node) {
         const size_t g3 = 3 * size_t(grec.g);
@@ -307,7 +421,31 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
         gather_load<R>(b1, stg, kGatherBatch, val, pol);
         node_mass_m(ep, ep.pre_kind, grec.mass, gp0, gp1, gp2, gq0, gq1, gq2);
         gather_sum<R>(b0, b1, stg, val, ep.sign > 0, gq0, gq1, gq2, pol);
-        part2 += node_finish_m(ep, grec.mass, (grec.val_fixed & 0x10000u) != 0, gp0, gp1, gp2, gq0, gq1, gq2);
+        const double dterm = node_finish_m(ep, grec.mass, (grec.val_fixed & 0x10000u) != 0, gp0, gp1, gp2, gq0, gq1, gq2);
+        if (if_row < 0) part2 += dterm;
+        else {
+            // interface node: (gq) is this rank's partial sum; every other sharing rank gets it in its inbox (NVLink store)
+            for (int e = 0; e < P.max_sh - 1; ++e) {
+                const int2 to = P.if_send[if_row * (P.max_sh - 1) + e];
+                if (to.x >= 0) { R* d = P.nb_inbox[to.x] + 3 * size_t(to.y); d[0] = gq0; d[1] = gq1; d[2] = gq2; }
+            }
+        }
+    }
+    if (P.enabled) {
+        dist_sync<R>(a, st.sync_count, st.xs, 0.0, 1, bcast, st.failed);       // the neighbours' partials are in the inbox
+        if (if_row >= 0) {
+            // sum over the sharing ranks in ascending rank order: the same operands in the same order on every rank
+            R s0 = R(0), s1 = R(0), s2 = R(0);
+            for (int j = 0; j < P.max_sh; ++j) {
+                const int sj = P.src[if_row * P.max_sh + j];
+                R c0 = R(0), c1 = R(0), c2 = R(0);
+                if (sj == -1) { c0 = gq0; c1 = gq1; c2 = gq2; }
+                else if (sj >= 0) { c0 = __ldcg(P.inbox + 3 * size_t(sj)); c1 = __ldcg(P.inbox + 3 * size_t(sj) + 1); c2 = __ldcg(P.inbox + 3 * size_t(sj) + 2); }
+                if (j == 0) { s0 = c0; s1 = c1; s2 = c2; } else { s0 += c0; s1 += c1; s2 += c2; }
+            }
+            gq0 = s0; gq1 = s1; gq2 = s2;
+            if (counted) part2 += double(gq0) * double(gp0) + double(gq1) * double(gp1) + double(gq2) * double(gp2);
+        }
     }
     const SV* s_in = reinterpret_cast<const SV*>(smem_raw);
     const NodeRec<R>* s_nrec = reinterpret_cast<const NodeRec<R>*>(smem_raw + L.off_nrec);
@@ -315,7 +453,8 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
     __syncthreads();
     part2 = block_sum(part2, red);
     trace_mark(ep.trace, kTraceTail, 3);
-    const double den = grid_sync_sum(a.sync, st.sync_count, part2, red, bcast);
+    const double den = P.enabled ? dist_sync<R>(a, st.sync_count, st.xs, part2, 2, bcast, st.failed) : grid_sync_sum(a.sync, st.sync_count, part2, red, bcast);
+    if (st.failed) { if (blockIdx.x == 0 && threadIdx.x == 0) { cg->done = 1; cg->end_cond = 99; } return false; }
     trace_mark(ep.trace, kTraceTail, 4);
     bool stop = false;
     if (den != 0.0) { if (fabs(den) <= st.thr && !(st.it == 1 && st.tsc == 0)) stop = true; } else stop = true;
@@ -331,9 +470,10 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
         R gx0, gx1, gx2;
         if (st.first) { gx0 = a.x[g3]; gx1 = a.x[g3 + 1]; gx2 = a.x[g3 + 2]; }
         else { gx0 = a.gstate[6 * gs_n + gs_i]; gx1 = a.gstate[7 * gs_n + gs_i]; gx2 = a.gstate[8 * gs_n + gs_i]; }
-        prr += xr_one<R>(gx0, gr0, gp0, gq0, alpha, malpha, a_one, ma_one);
-        prr += xr_one<R>(gx1, gr1, gp1, gq1, alpha, malpha, a_one, ma_one);
-        prr += xr_one<R>(gx2, gr2, gp2, gq2, alpha, malpha, a_one, ma_one);
+        double own = xr_one<R>(gx0, gr0, gp0, gq0, alpha, malpha, a_one, ma_one);
+        own += xr_one<R>(gx1, gr1, gp1, gq1, alpha, malpha, a_one, ma_one);
+        own += xr_one<R>(gx2, gr2, gp2, gq2, alpha, malpha, a_one, ma_one);
+        if (counted) prr += own;
         a.r[g3] = gr0; a.r[g3 + 1] = gr1; a.r[g3 + 2] = gr2;                    // for the tiles that touch the node
         a.gstate[gs_i] = gp0; a.gstate[gs_n + gs_i] = gp1; a.gstate[2 * gs_n + gs_i] = gp2;
         a.gstate[3 * gs_n + gs_i] = gr0; a.gstate[4 * gs_n + gs_i] = gr1; a.gstate[5 * gs_n + gs_i] = gr2;
@@ -363,10 +503,12 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
             q[0] = r0; q[1] = r1; q[2] = r2;
         }
     }
+    st.updated = true;
     __syncthreads();
     prr = block_sum(prr, red);
     trace_mark(ep.trace, kTraceTail, 5);
-    const double rho_new = grid_sync_sum(a.sync, st.sync_count, prr, red, bcast);          // r of the shared nodes is complete
+    const double rho_new = P.enabled ? dist_sync<R>(a, st.sync_count, st.xs, prr, 2, bcast, st.failed) : grid_sync_sum(a.sync, st.sync_count, prr, red, bcast);
+    if (st.failed) { if (blockIdx.x == 0 && threadIdx.x == 0) { cg->done = 1; cg->end_cond = 99; } return false; }
     trace_mark(ep.trace, kTraceTail, 6);
     const int it2 = st.it + 1;
     bool stop2 = unsigned(it2) > st.max_iter;
@@ -383,7 +525,8 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
 template <class R> __device__ __forceinline__ void persist_finish(const TileDev<R>& t, const PersistCG<R>& a, const PersistState<R>& st, unsigned char* smem_raw, const GRec<R>* s_grec) {
     typedef typename SVec<R>::T SV;
     const PersistLayout& L = a.lay;
-    if (st.first) return;                    // no update was made: x is untouched
+    if (a.peer.enabled && blockIdx.x == 0 && threadIdx.x == 0) *a.peer.epoch += 1ull;   // (every CTA read it at the start)
+    if (!st.updated) return;                 // no update was made: x is untouched
     const GRec<R> grec = s_grec[threadIdx.x];
     if (grec.g != 0xFFFFFFFFu) {
         const size_t gs_n = size_t(gridDim.x) * blockDim.x, gs_i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;

@@ -1,4 +1,6 @@
 // Context, error reporting.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace sb {
@@ -61,6 +63,36 @@ int sofab200_ctx_synchronize(sofab200_ctx* ctx) {
     return SOFAB200_OK;
 }
 uint64_t sofab200_ctx_launch_count(const sofab200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int sofab200_peer_alloc(sofab200_ctx* ctx, size_t bytes, void** dev_ptr, unsigned char handle[SOFAB200_IPC_HANDLE_BYTES]) {
+    SB_CHECK(ctx && dev_ptr && handle && bytes > 0, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == SOFAB200_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+    SB_CUDA(cudaSetDevice(ctx->device));
+    SB_CUDA(cudaMalloc(dev_ptr, bytes));
+    SB_CUDA(cudaMemset(*dev_ptr, 0, bytes));
+    cudaIpcMemHandle_t h;
+    SB_CUDA(cudaIpcGetMemHandle(&h, *dev_ptr));
+    std::memcpy(handle, &h, sizeof(h));
+    SB_CUDA(cudaDeviceSynchronize());
+    return SOFAB200_OK;
+}
+int sofab200_peer_open(sofab200_ctx* ctx, const unsigned char handle[SOFAB200_IPC_HANDLE_BYTES], void** dev_ptr) {
+    SB_CHECK(ctx && dev_ptr && handle, "null argument");
+    SB_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    SB_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SOFAB200_OK;
+}
+int sofab200_peer_close(sofab200_ctx* ctx, void* dev_ptr) {
+    SB_CHECK(ctx != nullptr, "ctx is null");
+    if (dev_ptr) SB_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return SOFAB200_OK;
+}
+int sofab200_peer_free(sofab200_ctx* ctx, void* dev_ptr) {
+    SB_CHECK(ctx != nullptr, "ctx is null");
+    if (dev_ptr) SB_CUDA(cudaFree(dev_ptr));
+    return SOFAB200_OK;
+}
 int sofab200_ctx_trace_begin(sofab200_ctx* ctx) {
     SB_CHECK(ctx != nullptr, "ctx is null");
     SB_TRY(ctx->trace.alloc(size_t(2) * 4096 * 16));

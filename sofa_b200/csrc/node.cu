@@ -13,8 +13,9 @@ using namespace sb;
 namespace sb {
 // implemented in tet_fem.cu / hex_fem.cu
 template <class R> int tet_run(sofab200_tetfem* ff, bool dforce, const R* in, R k_factor, NodeEpilogue<R> ep, bool skip_gather);
-template <class R> int tet_cg_persistent(sofab200_tetfem* ff, R k_factor, PersistCG<R> a, size_t part_capacity);
+template <class R> int tet_cg_persistent(sofab200_tetfem* ff, R k_factor, PersistCG<R> a, size_t part_capacity, bool dry_run);
 size_t tet_tile_node_count(sofab200_tetfem* ff);
+const std::vector<uint32_t>& tet_shared_node_table(sofab200_tetfem* ff);
 template <class R> TileDev<R> tet_tiledev(sofab200_tetfem* ff);
 template <class R> TileDev<R> hex_tiledev(sofab200_hexfem* ff);
 int tet_partial_count(sofab200_tetfem* ff);
@@ -124,7 +125,16 @@ template <class R> struct Node : sofab200_node {
         DevBuf<R> sendbuf, recvbuf;
         DevBuf<unsigned char> owned;
         DevBuf<double> scal;
+        std::vector<uint32_t> if_idx_host;
+        std::vector<std::vector<uint32_t>> nb_rows_host;
     } halo;
+    // peer-memory mode (sofab200_node_set_peer): the persistent CG kernel talks to the other GPUs itself
+    struct Peer {
+        bool ready = false;
+        PeerDev<R> dev;
+        DevBuf<int32_t> sh_if_row;
+        DevBuf<int2> if_send;
+    } peer;
     bool distributed() const { return halo.comm != nullptr; }
     ncclDataType_t nccl_real() const { return sizeof(R) == 4 ? ncclFloat : ncclDouble; }
     // interface rows of q: sum over the sharing ranks, ascending rank order, same bits on every rank
@@ -183,6 +193,24 @@ template <class R> struct Node : sofab200_node {
         ctx->prof_stop(3);
         ctx->launches++;
         return SOFAB200_OK;
+    }
+    // the whole CG loop in one cooperative launch (cg_persist.cuh); pd != null: multi-GPU over peer memory
+    int launch_persistent(R* x, double m, double bfac, double kf, const PeerDev<R>* pd) {
+        const size_t n3 = 3 * n;
+        if (!p2.p) SB_TRY(p2.alloc(n3));
+        const size_t n_tile_nodes = tet_tile_node_count(tet);
+        if (xt.n < n_tile_nodes) { SB_TRY(xt.alloc(n_tile_nodes)); SB_TRY(rt.alloc(n_tile_nodes)); }
+        if (!gstate.p) SB_TRY(gstate.alloc(size_t(9) * ctx->sm_count * 2048));
+        if (!sync_slots.p) SB_TRY(sync_slots.alloc(3 * 2048 + 8));
+        PersistCG<R> a;
+        a.ep = make_mbk_ep(q.p, nullptr, p.p, m, bfac, false, 1.0, true, DOT_STORE, cg.p);
+        a.x = x; a.r = r.p; a.xt = xt.p; a.rt = rt.p; a.gstate = gstate.p; a.p0 = p.p; a.p1 = p2.p; a.n3 = n3; a.cg = cg.p; a.sync = sync_slots.p;
+        if (pd) a.peer = *pd; else std::memset(&a.peer, 0, sizeof(a.peer));
+        a.debug = 0; if (const char* env = getenv("SOFAB200_DEBUG_MODE")) a.debug = atoi(env);
+        SB_CUDA(cudaMemsetAsync(sync_slots.p, 0, sync_slots.n * sizeof(unsigned long long), ctx->stream));
+        const int rc = tet_cg_persistent<R>(tet, R(kf), a, sync_slots.n - 8, false);
+        if (rc == SOFAB200_OK) ctx->launches++;
+        return rc;
     }
     NodeEpilogue<R> base_ep() {
         NodeEpilogue<R> ep{};
@@ -246,6 +274,15 @@ template <class R> struct Node : sofab200_node {
             // same loop, with the interface rows of q exchanged and the three dot products all-reduced over the ranks
             SB_TRY(dist_dot(bvec, bvec, DF_CG_NORMB));
             SB_TRY(dist_dot(r.p, r.p, DF_CG_RHO));
+            const double kf_d = k + bfac * prm.ff_rayleigh_stiffness;
+            if (peer.ready && persistent && tet && (kf_d != 0.0 || bfac != 0.0)) {
+                // the loop in ONE persistent kernel per GPU; halo rows and dot products go through peer memory (cg_persist.cuh)
+                const int rc = launch_persistent(x, m, bfac, kf_d, &peer.dev);
+                if (rc == SOFAB200_OK) { LAUNCH(ctx, cg_end_kernel, 1, 1, cg.p); return SOFAB200_OK; }
+                if (rc != kPersistNotEligible) return rc;
+                peer.ready = false;      // this partition does not fit the kernel: NCCL loop from now on (every rank decides alike
+                                         // only if the partitions are alike -- the caller checks with sofab200_node_last_solve)
+            }
             for (unsigned it = 1; it <= prm.iterations; ++it) {
                 LAUNCH(ctx, (cg_p_update_kernel<R>), gd, kVecBlock, n3, p.p, (const R*)r.p, (const CGDev*)cg.p);
                 SB_TRY(add_mbk(q.p, nullptr, p.p, m, bfac, k, false, 1.0, true, DOT_NONE, cg.p));
@@ -261,19 +298,8 @@ template <class R> struct Node : sofab200_node {
         LAUNCH(ctx, (vdot_kernel<R>), gd, kVecBlock, n3, (const R*)r.p, (const R*)r.p, partials.p, counters.p + 1, int(DF_CG_RHO), (double*)nullptr, cg.p);
         const double kf_chk = k + bfac * prm.ff_rayleigh_stiffness;
         if (persistent && tet && (kf_chk != 0.0 || bfac != 0.0)) {
-            // the whole loop in one cooperative launch (cg_persist.cuh)
-            if (!p2.p) SB_TRY(p2.alloc(n3));
-            const size_t n_tile_nodes = tet_tile_node_count(tet);
-            if (xt.n < n_tile_nodes) { SB_TRY(xt.alloc(n_tile_nodes)); SB_TRY(rt.alloc(n_tile_nodes)); }
-            if (!gstate.p) SB_TRY(gstate.alloc(size_t(9) * ctx->sm_count * 2048));
-            if (!sync_slots.p) SB_TRY(sync_slots.alloc(3 * 2048 + 2));
-            PersistCG<R> a;
-            a.ep = make_mbk_ep(q.p, nullptr, p.p, m, bfac, false, 1.0, true, DOT_STORE, cg.p);
-            a.x = x; a.r = r.p; a.xt = xt.p; a.rt = rt.p; a.gstate = gstate.p; a.p0 = p.p; a.p1 = p2.p; a.n3 = n3; a.cg = cg.p; a.sync = sync_slots.p;
-            a.debug = 0; if (const char* env = getenv("SOFAB200_DEBUG_MODE")) a.debug = atoi(env);
-            SB_CUDA(cudaMemsetAsync(sync_slots.p, 0, sync_slots.n * sizeof(unsigned long long), ctx->stream));
-            const int rc = tet_cg_persistent<R>(tet, R(kf_chk), a, sync_slots.n);
-            if (rc == SOFAB200_OK) { ctx->launches++; LAUNCH(ctx, cg_end_kernel, 1, 1, cg.p); return SOFAB200_OK; }
+            const int rc = launch_persistent(x, m, bfac, kf_chk, nullptr);
+            if (rc == SOFAB200_OK) { LAUNCH(ctx, cg_end_kernel, 1, 1, cg.p); return SOFAB200_OK; }
             if (rc != kPersistNotEligible) return rc;
             persistent = false;      // this mesh does not fit: multi-kernel loop from now on
         }
@@ -515,6 +541,10 @@ template <class R> static int node_set_distributed(Node<R>* nd, sofab200_comm* c
         off += h->nb_count[k];
     }
     H.n_send = off;
+    H.if_idx_host = if_idx;
+    H.nb_rows_host.clear();
+    for (int k = 0; k < h->n_neighbours; ++k) H.nb_rows_host.emplace_back(h->nb_rows[k], h->nb_rows[k] + h->nb_count[k]);
+    nd->peer.ready = false;
     SB_TRY(H.if_idx.upload(if_idx, s)); SB_TRY(H.send_idx.upload(send_idx, s)); SB_TRY(H.src.upload(src, s));
     SB_TRY(H.sendbuf.alloc(3 * std::max<size_t>(off, 1))); SB_TRY(H.recvbuf.alloc(3 * std::max<size_t>(off, 1)));
     SB_TRY(H.scal.alloc(2)); SB_TRY(H.scal.zero(s));
@@ -523,8 +553,77 @@ template <class R> static int node_set_distributed(Node<R>* nd, sofab200_comm* c
     if (nd->sg.exec) { cudaGraphExecDestroy(nd->sg.exec); nd->sg.exec = nullptr; nd->sg.seen = 0; }
     return SOFAB200_OK;
 }
+// mailbox layout (bytes): 0 halo flags [kMaxPeers] u64 | 64 all-reduce slots [2][kMaxPeers] {double, u64} | 320 epoch u64 | 1024 inbox rows
+constexpr size_t kMailboxFlags = 0, kMailboxAr = 64, kMailboxEpoch = 320, kMailboxInbox = 1024;
+template <class R> static size_t node_peer_bytes(const Node<R>* nd) { return kMailboxInbox + 3 * std::max<size_t>(nd->halo.n_send, 1) * sizeof(R) + 256; }
+template <class R> static int node_set_peer(Node<R>* nd, const sofab200_peer_desc* d) {
+    if (!d->peer_base) { nd->peer.ready = false; if (nd->sg.exec) { cudaGraphExecDestroy(nd->sg.exec); nd->sg.exec = nullptr; nd->sg.seen = 0; } return SOFAB200_OK; }
+    SB_CHECK(nd->distributed(), "sofab200_node_set_distributed must come first");
+    {
+        PersistCG<R> probe; std::memset(&probe, 0, sizeof(probe));
+        const int rc = tet_cg_persistent<R>(nd->tet, R(1), probe, size_t(3) * 2048, true);
+        if (rc == kPersistNotEligible) return fail(SOFAB200_ERR_UNSUPPORTED, "this partition does not fit the persistent CG kernel (more than two tiles per SM)");
+        if (rc != SOFAB200_OK) return rc;
+    }
+    SB_CHECK(nd->tet != nullptr, "peer mode is implemented for the tetrahedral force field");
+    SB_CHECK(d->world >= 1 && d->world <= kMaxPeers && d->rank >= 0 && d->rank < d->world, "rank / world out of range (world <= 8)");
+    auto& H = nd->halo;
+    SB_CHECK(int(H.nb_rank.size()) <= kMaxPeers, "too many neighbours");
+    cudaStream_t s = nd->ctx->stream;
+    PeerDev<R>& P = nd->peer.dev;
+    std::memset(&P, 0, sizeof(P));
+    P.rank = d->rank; P.world = d->world; P.n_nb = int(H.nb_rank.size()); P.max_sh = H.max_sh;
+    unsigned char* mine = static_cast<unsigned char*>(d->peer_base[d->rank]);
+    P.hflag = reinterpret_cast<unsigned long long*>(mine + kMailboxFlags);
+    P.ar = reinterpret_cast<ARSlot*>(mine + kMailboxAr);
+    P.epoch = reinterpret_cast<unsigned long long*>(mine + kMailboxEpoch);
+    P.inbox = reinterpret_cast<R*>(mine + kMailboxInbox);
+    for (int r = 0; r < d->world; ++r) { SB_CHECK(d->peer_base[r] != nullptr, "peer_base entry is null"); P.peer_ar[r] = reinterpret_cast<ARSlot*>(static_cast<unsigned char*>(d->peer_base[r]) + kMailboxAr); }
+    for (int k = 0; k < P.n_nb; ++k) {
+        const int r = H.nb_rank[k];
+        SB_CHECK(r >= 0 && r < d->world && r != d->rank, "neighbour rank out of range");
+        unsigned char* base = static_cast<unsigned char*>(d->peer_base[r]);
+        P.nb_rank[k] = r;
+        P.nb_hflag[k] = reinterpret_cast<unsigned long long*>(base + kMailboxFlags);
+        P.nb_inbox[k] = reinterpret_cast<R*>(base + kMailboxInbox);
+    }
+    // interface row of every entry of the plan's shared-node table; every interface node must be there
+    const std::vector<uint32_t>& sh = tet_shared_node_table(nd->tet);
+    std::vector<int32_t> row_of(nd->n, -1);
+    for (size_t i = 0; i < H.if_idx_host.size(); ++i) row_of[H.if_idx_host[i]] = int32_t(i);
+    std::vector<int32_t> sh_if_row(sh.size(), -1);
+    size_t found = 0;
+    for (size_t i = 0; i < sh.size(); ++i) if (sh[i] != 0xFFFFFFFFu && row_of[sh[i]] >= 0) { sh_if_row[i] = row_of[sh[i]]; ++found; }
+    SB_CHECK(found == H.if_idx_host.size(), "interface nodes must be flagged in sofab200_tetfem_desc::shared_nodes when the force field is created");
+    // where each interface row goes: {neighbour, row in its inbox}
+    const int ms1 = std::max(1, H.max_sh - 1);
+    std::vector<int2> if_send(H.if_idx_host.size() * size_t(ms1), make_int2(-1, 0));
+    std::vector<int> fill(H.if_idx_host.size(), 0);
+    for (int k = 0; k < P.n_nb; ++k)
+        for (size_t i = 0; i < H.nb_rows_host[k].size(); ++i) {
+            const uint32_t row = H.nb_rows_host[k][i];
+            SB_CHECK(fill[row] < ms1, "interface node shared by more ranks than max_sharers");
+            if_send[size_t(row) * ms1 + fill[row]++] = make_int2(k, int(d->remote_off[k] + i));
+        }
+    if (if_send.empty()) if_send.push_back(make_int2(-1, 0));
+    SB_TRY(nd->peer.sh_if_row.upload(sh_if_row, s)); SB_TRY(nd->peer.if_send.upload(if_send, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    P.sh_if_row = nd->peer.sh_if_row.p; P.if_send = nd->peer.if_send.p; P.src = H.src.p; P.owned = H.owned.p;
+    P.enabled = 1;
+    nd->peer.ready = true;
+    if (nd->sg.exec) { cudaGraphExecDestroy(nd->sg.exec); nd->sg.exec = nullptr; nd->sg.seen = 0; }
+    return SOFAB200_OK;
+}
 }  // namespace sb
 extern "C" {
+size_t sofab200_node_peer_bytes(const sofab200_node* node) {
+    if (!node) return 0;
+    return node->real == SOFAB200_F32 ? node_peer_bytes<float>(static_cast<const Node<float>*>(node)) : node_peer_bytes<double>(static_cast<const Node<double>*>(node));
+}
+int sofab200_node_set_peer(sofab200_node* node, const sofab200_peer_desc* peer) {
+    SB_CHECK(node && peer, "null argument");   /* peer->peer_base == NULL: leave peer mode */
+    return NODE_DISPATCH(node, node_set_peer<float>(NF(node), peer), node_set_peer<double>(ND(node), peer));
+}
 int sofab200_node_set_distributed(sofab200_node* node, sofab200_comm* comm, const sofab200_halo_desc* halo) {
     SB_CHECK(node && comm && halo && halo->owned, "null argument");
     SB_CHECK(comm->ctx == node->ctx, "communicator and node belong to different contexts");

@@ -40,11 +40,13 @@ inline uint64_t morton_spread(uint64_t v) {  // 21 bits -> every third bit
 
 // elems: n_elems x npe node indices (original topology order); pos: 3*n_nodes doubles (rest positions).
 // Returns "" or an error text.
+// force_shared (optional): n_nodes flags, nodes that must take the staging path whatever their incident elements.
 // smem_limit / sv_bytes / slot_bytes (optional): shared-memory budget of a tile CTA, bytes of one staged nodal vector and of
 // one slot.  When a tile's interior nodes need more slots than fit, its highest-valence interior nodes are demoted to
 // shared nodes (their contributions go through the HBM/L2 staging buffer instead), so any tile size can be made to fit.
 inline std::string build_plan(HostPlan& P, int n_nodes, int n_elems, int npe, const uint32_t* elems, const double* pos,
-                              int tile_e, int chunk, uint32_t stage_flag, size_t smem_limit = 0, size_t sv_bytes = 0, size_t slot_bytes = 0) {
+                              int tile_e, int chunk, uint32_t stage_flag, size_t smem_limit = 0, size_t sv_bytes = 0, size_t slot_bytes = 0,
+                              const unsigned char* force_shared = nullptr) {
     P = HostPlan();
     P.n_nodes = n_nodes; P.n_elems = n_elems; P.npe = npe; P.tile_e = tile_e;
     P.n_tiles = std::max(1, (n_elems + tile_e - 1) / tile_e);
@@ -96,6 +98,7 @@ inline std::string build_plan(HostPlan& P, int n_nodes, int n_elems, int npe, co
     for (int i = 0; i < n_nodes; ++i) {
         const uint32_t b = inc_off[i], e = inc_off[i + 1];
         if (b == e) continue;
+        if (force_shared && force_shared[i]) continue;   // (e.g. partition-interface nodes of a multi-GPU run)
         const uint32_t t0 = tile_of[inc[b] / npe];
         bool same = true;
         for (uint32_t k = b + 1; k < e && same; ++k) same = tile_of[inc[k] / npe] == t0;

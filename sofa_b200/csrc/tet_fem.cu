@@ -94,7 +94,7 @@ template <class R, int MODE> static int tet_launch_mode(TetFF<R>& ff, const TetD
 // ---- persistent CG kernel (cooperative launch: every CTA must be resident, the kernel crosses grid-wide syncs) -----------
 // Returns SOFAB200_OK, an error, or kPersistNotEligible (> 0) when the mesh does not fit the kernel's assumptions (at most
 // two tiles and one chunk of shared nodes per thread group and CTA): the caller then runs the multi-kernel loop.
-template <class R, int MODE, int MAXT, bool PF> static int tet_persist_variant(TetFF<R>& ff, TetDev<R> d, PersistCG<R> a, int threads, size_t sync_capacity) {
+template <class R, int MODE, int MAXT, bool PF> static int tet_persist_variant(TetFF<R>& ff, TetDev<R> d, PersistCG<R> a, int threads, size_t sync_capacity, bool dry_run = false) {
     auto kern = tet_cg_persistent_kernel<R, MODE, MAXT, PF>;
     const HostPlan& P = ff.h.plan;
     const int groups = threads / kGatherChunk;
@@ -115,6 +115,7 @@ template <class R, int MODE, int MAXT, bool PF> static int tet_persist_variant(T
         const int grid = std::max(need_tiles, need_chunks);
         if (grid > max_grid) continue;
         if (size_t(3) * grid + 1 > sync_capacity) return fail(SOFAB200_ERR_INVALID, "sync buffer too small for the persistent CG kernel");
+        if (dry_run) return SOFAB200_OK;
         a.lay = L;
         void* args[] = {&d, &a};
         ff.ctx->prof_start(4);
@@ -125,17 +126,18 @@ template <class R, int MODE, int MAXT, bool PF> static int tet_persist_variant(T
     }
     return kPersistNotEligible;
 }
-template <class R> int tet_cg_persistent(sofab200_tetfem* base, R k_factor, PersistCG<R> a, size_t sync_capacity) {
+// dry_run: only tell whether the mesh fits the kernel (SOFAB200_OK) or not (kPersistNotEligible)
+template <class R> int tet_cg_persistent(sofab200_tetfem* base, R k_factor, PersistCG<R> a, size_t sync_capacity, bool dry_run) {
     TetFF<R>& ff = *static_cast<TetFF<R>*>(base);
     TetDev<R> d = ff.dev();
     d.k_factor = k_factor;
-    if (ff.method == SOFAB200_TET_SMALL) return tet_persist_variant<R, TM_DF_SMALL, 256, false>(ff, d, a, 256, sync_capacity);
-    if (sizeof(R) == 8) return tet_persist_variant<R, TM_DF_COROT, 256, false>(ff, d, a, 256, sync_capacity);
-    if (ff.threads > 256) return tet_persist_variant<R, TM_DF_COROT, 512, true>(ff, d, a, 512, sync_capacity);
-    return tet_persist_variant<R, TM_DF_COROT, 256, true>(ff, d, a, 256, sync_capacity);
+    if (ff.method == SOFAB200_TET_SMALL) return tet_persist_variant<R, TM_DF_SMALL, 256, false>(ff, d, a, 256, sync_capacity, dry_run);
+    if (sizeof(R) == 8) return tet_persist_variant<R, TM_DF_COROT, 256, false>(ff, d, a, 256, sync_capacity, dry_run);
+    if (ff.threads > 256) return tet_persist_variant<R, TM_DF_COROT, 512, true>(ff, d, a, 512, sync_capacity, dry_run);
+    return tet_persist_variant<R, TM_DF_COROT, 256, true>(ff, d, a, 256, sync_capacity, dry_run);
 }
-template int tet_cg_persistent<float>(sofab200_tetfem*, float, PersistCG<float>, size_t);
-template int tet_cg_persistent<double>(sofab200_tetfem*, double, PersistCG<double>, size_t);
+template int tet_cg_persistent<float>(sofab200_tetfem*, float, PersistCG<float>, size_t, bool);
+template int tet_cg_persistent<double>(sofab200_tetfem*, double, PersistCG<double>, size_t, bool);
 
 // Element pass + boundary gather with a caller-provided epilogue (also used by the solver node).
 template <class R> TileDev<R> tet_tiledev(sofab200_tetfem* base) { return static_cast<TetFF<R>*>(base)->dev().t; }
@@ -175,6 +177,11 @@ template int tet_run<float>(sofab200_tetfem*, bool, const float*, float, NodeEpi
 template int tet_run<double>(sofab200_tetfem*, bool, const double*, double, NodeEpilogue<double>, bool);
 
 int tet_real(sofab200_tetfem* ff) { return ff->real; }
+// the plan's table of shared nodes (chunks of kGatherChunk, 0xFFFFFFFF = padding), for the multi-GPU set-up
+const std::vector<uint32_t>& tet_shared_node_table(sofab200_tetfem* base) {
+    if (base->real == SOFAB200_F32) return static_cast<TetFF<float>*>(base)->h.plan.sh_nodes;
+    return static_cast<TetFF<double>*>(base)->h.plan.sh_nodes;
+}
 size_t tet_tile_node_count(sofab200_tetfem* base) {
     if (base->real == SOFAB200_F32) return static_cast<TetFF<float>*>(base)->h.plan.tile_nodes.size();
     return static_cast<TetFF<double>*>(base)->h.plan.tile_nodes.size();

@@ -159,7 +159,7 @@ template <class R> static std::string tet_host_build(HostTet<R>& ff, size_t n_no
     tile_e = std::max(32, (tile_e + 31) / 32 * 32);
     int persist_tries = 0;
     for (;;) {
-        const std::string err = build_plan(ff.plan, int(n_nodes), int(n_tets), 4, tets, pos.data(), tile_e, chunk, kStageFlag, smem_limit, sizeof(SV), 3 * sizeof(R));
+        const std::string err = build_plan(ff.plan, int(n_nodes), int(n_tets), 4, tets, pos.data(), tile_e, chunk, kStageFlag, smem_limit, sizeof(SV), 3 * sizeof(R), desc->shared_nodes);
         ff.smem_bytes = tile_smem_bytes<R>(ff.plan.max_touched, ff.plan.max_slots);
         const bool too_big = ff.smem_bytes > smem_limit || err.find("use a smaller tile") != std::string::npos;
         const bool too_staged = err.empty() && ff.plan.n_staged_corners * 2 > 4 * n_tets && ff.plan.n_demoted > 0;

@@ -114,7 +114,8 @@ class DeviceBackend:
         from . import components as C
         self.ctx = ctx
         self.mo = C.MechanicalObject(ctx, template, position=rm.positions)
-        self.ff = C.TetrahedronFEMForceField(self.mo, rm.elems, youngModulus=youngModulus, poissonRatio=poissonRatio, method=method)
+        # the partition-interface nodes take the staging path, so that one thread per node owns their halo exchange (peer mode)
+        self.ff = C.TetrahedronFEMForceField(self.mo, rm.elems, youngModulus=youngModulus, poissonRatio=poissonRatio, method=method, sharedNodes=rm.interface)
         self.mass = C.DiagonalMass(self.mo, vertexMass=m_pass)
         self.fix = C.FixedProjectiveConstraint(self.mo, fixed_local)
         self.node = C.SolverNode(self.mo, self.ff, self.mass, self.fix, dt=params["dt"], gravity=params["gravity"], rayleighStiffness=params["rK"],
@@ -133,6 +134,49 @@ class DeviceBackend:
         self.comm = C.Communicator(self.ctx, group)
         self.node.set_distributed(self.comm, rm)
         self.native = True
+        self.peer = False
+        import os
+        if os.environ.get("SOFAB200_PEER", "1") != "0" and rm.world <= 8:
+            self.peer = self._attach_peer(rm, group)
+
+    def _attach_peer(self, rm, group):
+        """Peer-memory mode: every rank's mailbox mapped into every process with CUDA IPC (torch.distributed only ships the
+        64-byte handles), then the CG loop is one persistent kernel per GPU that exchanges over NVLink by itself."""
+        try:
+            ptr, handle = self.ctx.peer_alloc(self.node.peer_bytes())
+        except Exception:
+            handle, ptr = None, None
+        handles = [None] * rm.world
+        dist.all_gather_object(handles, handle, group=group)
+        # first inbox row of each neighbour's block on this rank (neighbours in ascending rank order, like set_distributed)
+        nbs = sorted(rm.neighbours.items())
+        offs, acc = {}, 0
+        for s, v in nbs:
+            offs[s] = acc; acc += len(v["rows"])
+        all_offs = [None] * rm.world
+        dist.all_gather_object(all_offs, offs, group=group)
+        ok = all(h is not None for h in handles)
+        bases = []
+        if ok:
+            try:
+                bases = [ptr if r == rm.rank else self.ctx.peer_open(handles[r]) for r in range(rm.world)]
+            except Exception:
+                ok = False
+        flags = [None] * rm.world
+        dist.all_gather_object(flags, ok, group=group)
+        if not all(flags):
+            return False
+        remote_off = [all_offs[s][rm.rank] for s, _ in nbs]
+        try:
+            self.node.set_peer(rm.rank, rm.world, bases, remote_off)
+            ok = True
+        except Exception as e:  # e.g. the partition does not fit the persistent kernel's assumptions
+            ok = False
+        dist.all_gather_object(flags, ok, group=group)
+        if not all(flags):
+            self.node.clear_peer()       # every rank must run the same loop
+        dist.barrier(group=group)
+        return all(flags)
 
     def new_vector(self):
         return self.mo.new_vector()
