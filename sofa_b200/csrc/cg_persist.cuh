@@ -73,19 +73,23 @@ template <class R> inline PersistLayout persist_layout(int tiles_per_cta, int ma
 // static shared memory of the kernel for a CTA of `threads` (the per-thread shared-node records + reduction scratch)
 template <class R> inline size_t persist_static_smem(int threads) { return sizeof(GRec<R>) * size_t(threads) + 33 * sizeof(double); }
 
+template <class R> struct InboxWords;
+template <> struct InboxWords<float> { static constexpr int N = 3; };
+template <> struct InboxWords<double> { static constexpr int N = 6; };
 // ---- multi-GPU: peer memory over NVLink (CUDA IPC mappings of every rank's mailbox), no NCCL inside the loop ---------------
 constexpr int kMaxPeers = 8;
-struct ARSlot { double v; unsigned long long seq; };
+// Everything that crosses NVLink is written as 8-byte words carrying 32 bits of payload and a 32-bit sequence number (the scheme
+// of NCCL's LL protocol): an aligned 8-byte store is single-copy atomic, so a reader that sees the sequence number it waits for
+// has the payload too -- no system-scope fence on either side, no separate "data is ready" flag.
+struct ARSlot { unsigned long long w[2]; };          // a double: {lo32 | seq<<32, hi32 | seq<<32}
 template <class R> struct PeerDev {
     int enabled, rank, world, n_nb, max_sh;
     int nb_rank[kMaxPeers];
-    unsigned long long* hflag;                 // local: [kMaxPeers] halo sequence number written by rank r
-    unsigned long long* nb_hflag[kMaxPeers];   // neighbour k's hflag array (peer memory)
     ARSlot* ar;                                // local: [2][kMaxPeers] all-reduce slots (double-buffered by sequence parity)
     ARSlot* peer_ar[kMaxPeers];                // rank r's ar array (peer memory, own included)
     unsigned long long* epoch;                 // local: launches done so far (sequence numbers are never reset)
-    R* inbox;                                  // local: partial q of interface nodes received from the neighbours
-    R* nb_inbox[kMaxPeers];                    // neighbour k's inbox (peer memory)
+    unsigned long long* inbox;                 // local: partial q of interface nodes received from the neighbours, kInboxWords<R> words per row
+    unsigned long long* nb_inbox[kMaxPeers];   // neighbour k's inbox (peer memory)
     const int32_t* sh_if_row;                  // aligned with sh_nodes: row of the node in the interface table, or -1
     const int32_t* src;                        // [n_if][max_sh] in ascending-rank order: -1 own partial, -2 nobody, else inbox row
     const int2* if_send;                       // [n_if][max_sh-1]: {neighbour index or -1, row in that neighbour's inbox}
@@ -173,23 +177,48 @@ __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsign
 __device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 constexpr unsigned long long kSyncTimeoutNs = 4000000000ull;
 struct DistSeq { unsigned long long base; unsigned halo, ar; };
-template <class R> __device__ __forceinline__ double dist_sync(const PersistCG<R>& a, unsigned& s, DistSeq& xs, double cta_value, int kind, double* bcast, bool& failed) {
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) { asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long* p, unsigned long long v) { asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+// payload words of the interface rows: one per float, two per double
+__device__ __forceinline__ void inbox_put(unsigned long long* row, int c, float v, unsigned seq) { st_relaxed_sys_u64(row + c, (unsigned long long)__float_as_uint(v) | ((unsigned long long)seq << 32)); }
+__device__ __forceinline__ void inbox_put(unsigned long long* row, int c, double v, unsigned seq) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    st_relaxed_sys_u64(row + 2 * c, (b & 0xFFFFFFFFull) | ((unsigned long long)seq << 32));
+    st_relaxed_sys_u64(row + 2 * c + 1, (b >> 32) | ((unsigned long long)seq << 32));
+}
+__device__ __forceinline__ bool inbox_get(const unsigned long long* row, int c, unsigned seq, float& v) {
+    const unsigned long long w = ld_relaxed_sys_u64(row + c);
+    if (unsigned(w >> 32) != seq) return false;
+    v = __uint_as_float(unsigned(w)); return true;
+}
+__device__ __forceinline__ bool inbox_get(const unsigned long long* row, int c, unsigned seq, double& v) {
+    const unsigned long long w0 = ld_relaxed_sys_u64(row + 2 * c), w1 = ld_relaxed_sys_u64(row + 2 * c + 1);
+    if (unsigned(w0 >> 32) != seq || unsigned(w1 >> 32) != seq) return false;
+    v = __longlong_as_double((long long)((w0 & 0xFFFFFFFFull) | (w1 << 32))); return true;
+}
+// All-reduce of one double across the GPUs, fused with the grid sync: CTA 0 adds the CTAs' values once all have arrived and
+// stores the sum into every rank's slot (own slot first, with release: it also publishes this GPU's CTAs' writes); every
+// CTA then polls the `world` slots of its own GPU and adds them in rank order.  Waits give up after ~4 s.
+template <class R> __device__ __forceinline__ double dist_sync(const PersistCG<R>& a, unsigned& s, DistSeq& xs, double cta_value, double* bcast, bool& failed) {
     const unsigned G = gridDim.x;
     unsigned long long* slots = a.sync;
     double* cur = reinterpret_cast<double*>(slots) + size_t(s % 3) * G;
     unsigned* counter = reinterpret_cast<unsigned*>(slots + size_t(3) * G);
-    unsigned* release = counter + 1;
-    double* result = reinterpret_cast<double*>(slots + size_t(3) * G + 1);
-    unsigned* abort_flag = reinterpret_cast<unsigned*>(slots + size_t(3) * G + 2);
     const PeerDev<R>& P = a.peer;
+    const unsigned long long aseq64 = xs.base + xs.ar + 1;
+    const unsigned aseq = unsigned(aseq64);
+    const int set = int(aseq64 & 1ull);
     __syncthreads();
-    if (threadIdx.x == 0) { cur[blockIdx.x] = cta_value; __threadfence_system(); atomicAdd(counter, 1u); }
+    if (threadIdx.x == 0) { cur[blockIdx.x] = cta_value; __threadfence(); atomicAdd(counter, 1u); }
     if (blockIdx.x == 0) {
-        __shared__ int s_fail;
         if (threadIdx.x == 0) {
-            s_fail = 0;
             const unsigned long long t0 = globaltimer_ns();
-            while (ld_acquire_u32(counter) < (s + 1) * G) { if (globaltimer_ns() - t0 > kSyncTimeoutNs) { s_fail = 1; break; } }
+            while (ld_acquire_u32(counter) < (s + 1) * G) { if (globaltimer_ns() - t0 > kSyncTimeoutNs) break; }
         }
         __syncthreads();
         if (threadIdx.x < 32) {
@@ -198,45 +227,35 @@ template <class R> __device__ __forceinline__ double dist_sync(const PersistCG<R
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
             if (threadIdx.x == 0) {
-                double tot = v;
-                int fail = s_fail;
-                const unsigned long long t0 = globaltimer_ns();
-                if (kind == 1 && !fail) {
-                    const unsigned long long seq = xs.base + xs.halo + 1;
-                    for (int k = 0; k < P.n_nb; ++k) st_release_sys_u64(P.nb_hflag[k] + P.rank, seq);
-                    for (int k = 0; k < P.n_nb && !fail; ++k)
-                        while (ld_acquire_sys_u64(P.hflag + P.nb_rank[k]) < seq) { if (globaltimer_ns() - t0 > kSyncTimeoutNs) { fail = 1; break; } }
-                } else if (kind == 2 && !fail) {
-                    const unsigned long long seq = xs.base + xs.ar + 1;
-                    const int set = int(seq & 1ull);
-                    for (int r = 0; r < P.world; ++r) {
-                        ARSlot* dst = P.peer_ar[r] + set * kMaxPeers + P.rank;
-                        dst->v = v;
-                        st_release_sys_u64(&dst->seq, seq);
-                    }
-                    tot = 0.0;
-                    for (int r = 0; r < P.world && !fail; ++r) {
-                        const ARSlot* src = P.ar + set * kMaxPeers + r;
-                        while (ld_acquire_sys_u64(&src->seq) != seq) { if (globaltimer_ns() - t0 > kSyncTimeoutNs) { fail = 1; break; } }
-                        tot += *reinterpret_cast<const volatile double*>(&src->v);
-                    }
-                }
-                if (fail) *abort_flag = 1u;
-                *result = tot;
-                __threadfence();
-                st_release_gpu_u32(release, s + 1);
+                const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+                const unsigned long long w0 = (b & 0xFFFFFFFFull) | ((unsigned long long)aseq << 32), w1 = (b >> 32) | ((unsigned long long)aseq << 32);
+                ARSlot* mine = P.ar + set * kMaxPeers + P.rank;
+                mine->w[0] = w0;
+                st_release_gpu_u64(&mine->w[1], w1);
+                for (int r = 0; r < P.world; ++r)
+                    if (r != P.rank) { ARSlot* dst = P.peer_ar[r] + set * kMaxPeers + P.rank; st_relaxed_sys_u64(&dst->w[0], w0); st_relaxed_sys_u64(&dst->w[1], w1); }
             }
         }
     }
     if (threadIdx.x == 0) {
         const unsigned long long t0 = globaltimer_ns();
-        while (ld_acquire_u32(release) < s + 1) { if (globaltimer_ns() - t0 > 3 * kSyncTimeoutNs) { *abort_flag = 1u; break; } }
-        *bcast = __ldcg(result);
-        if (*reinterpret_cast<volatile unsigned*>(abort_flag)) *bcast = __longlong_as_double(0x7FF8000000000001ll);   // NaN: failed
+        double tot = 0.0;
+        bool fail = false;
+        for (int r = 0; r < P.world && !fail; ++r) {
+            const ARSlot* src = P.ar + set * kMaxPeers + r;
+            unsigned long long w0, w1;
+            for (;;) {
+                w0 = ld_relaxed_sys_u64(&src->w[0]); w1 = ld_relaxed_sys_u64(&src->w[1]);
+                if (unsigned(w0 >> 32) == aseq && unsigned(w1 >> 32) == aseq) break;
+                if (globaltimer_ns() - t0 > kSyncTimeoutNs) { fail = true; break; }
+            }
+            tot += __longlong_as_double((long long)((w0 & 0xFFFFFFFFull) | (w1 << 32)));      // rank order
+        }
+        __threadfence();
+        *bcast = fail ? __longlong_as_double(0x7FF8000000000001ll) : tot;
     }
     __syncthreads();
-    ++s;
-    if (kind == 1) ++xs.halo; else if (kind == 2) ++xs.ar;
+    ++s; ++xs.ar;
     const double r = *bcast;
     if (r != r && (__double_as_longlong(r) & 0xFFFFFFFFll) == 1ll) failed = true;
     return r;
@@ -421,30 +440,19 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
         gather_load<R>(b1, stg, kGatherBatch, val, pol);
         node_mass_m(ep, ep.pre_kind, grec.mass, gp0, gp1, gp2, gq0, gq1, gq2);
         gather_sum<R>(b0, b1, stg, val, ep.sign > 0, gq0, gq1, gq2, pol);
-        const double dterm = node_finish_m(ep, grec.mass, (grec.val_fixed & 0x10000u) != 0, gp0, gp1, gp2, gq0, gq1, gq2);
-        if (if_row < 0) part2 += dterm;
-        else {
-            // interface node: (gq) is this rank's partial sum; every other sharing rank gets it in its inbox (NVLink store)
+        // p.q of the node.  Multi-GPU: (gq) of an interface node is this rank's PARTIAL sum; since p is the same on every sharing
+        // rank, the ranks' p.q_partial add up to p.q, so den needs no exchanged q: halo and all-reduce share one cross-GPU sync.
+        part2 += node_finish_m(ep, grec.mass, (grec.val_fixed & 0x10000u) != 0, gp0, gp1, gp2, gq0, gq1, gq2);
+        if (if_row >= 0) {
+            // every other sharing rank gets the partial sum in its inbox (NVLink store)
             for (int e = 0; e < P.max_sh - 1; ++e) {
                 const int2 to = P.if_send[if_row * (P.max_sh - 1) + e];
-                if (to.x >= 0) { R* d = P.nb_inbox[to.x] + 3 * size_t(to.y); d[0] = gq0; d[1] = gq1; d[2] = gq2; }
+                if (to.x >= 0) {
+                    unsigned long long* d = P.nb_inbox[to.x] + size_t(InboxWords<R>::N) * size_t(to.y);
+                    const unsigned hseq = unsigned(st.xs.base + st.xs.halo + 1);
+                    inbox_put(d, 0, gq0, hseq); inbox_put(d, 1, gq1, hseq); inbox_put(d, 2, gq2, hseq);
+                }
             }
-        }
-    }
-    if (P.enabled) {
-        dist_sync<R>(a, st.sync_count, st.xs, 0.0, 1, bcast, st.failed);       // the neighbours' partials are in the inbox
-        if (if_row >= 0) {
-            // sum over the sharing ranks in ascending rank order: the same operands in the same order on every rank
-            R s0 = R(0), s1 = R(0), s2 = R(0);
-            for (int j = 0; j < P.max_sh; ++j) {
-                const int sj = P.src[if_row * P.max_sh + j];
-                R c0 = R(0), c1 = R(0), c2 = R(0);
-                if (sj == -1) { c0 = gq0; c1 = gq1; c2 = gq2; }
-                else if (sj >= 0) { c0 = __ldcg(P.inbox + 3 * size_t(sj)); c1 = __ldcg(P.inbox + 3 * size_t(sj) + 1); c2 = __ldcg(P.inbox + 3 * size_t(sj) + 2); }
-                if (j == 0) { s0 = c0; s1 = c1; s2 = c2; } else { s0 += c0; s1 += c1; s2 += c2; }
-            }
-            gq0 = s0; gq1 = s1; gq2 = s2;
-            if (counted) part2 += double(gq0) * double(gp0) + double(gq1) * double(gp1) + double(gq2) * double(gp2);
         }
     }
     const SV* s_in = reinterpret_cast<const SV*>(smem_raw);
@@ -453,7 +461,28 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
     __syncthreads();
     part2 = block_sum(part2, red);
     trace_mark(ep.trace, kTraceTail, 3);
-    const double den = P.enabled ? dist_sync<R>(a, st.sync_count, st.xs, part2, 2, bcast, st.failed) : grid_sync_sum(a.sync, st.sync_count, part2, red, bcast);
+    const double den = P.enabled ? dist_sync<R>(a, st.sync_count, st.xs, part2, bcast, st.failed) : grid_sync_sum(a.sync, st.sync_count, part2, red, bcast);
+    bool halo_timeout = false, prr_poison = false;
+    if (P.enabled && if_row >= 0 && !st.failed) {
+        // q of an interface node: the sharing ranks' partial sums in ascending rank order -- same operands, same order, same bits on every rank
+        R s0 = R(0), s1 = R(0), s2 = R(0);
+        for (int j = 0; j < P.max_sh; ++j) {
+            const int sj = P.src[if_row * P.max_sh + j];
+            R c0 = R(0), c1 = R(0), c2 = R(0);
+            if (sj == -1) { c0 = gq0; c1 = gq1; c2 = gq2; }
+            else if (sj >= 0) {
+                // (the words were sent before the neighbour's contribution to den, so they have normally landed by now)
+                const unsigned long long* row = P.inbox + size_t(InboxWords<R>::N) * size_t(sj);
+                const unsigned hseq = unsigned(st.xs.base + st.xs.halo + 1);
+                const unsigned long long t0 = globaltimer_ns();
+                while (!(inbox_get(row, 0, hseq, c0) && inbox_get(row, 1, hseq, c1) && inbox_get(row, 2, hseq, c2)))
+                    if (globaltimer_ns() - t0 > kSyncTimeoutNs) { halo_timeout = true; break; }
+            }
+            if (j == 0) { s0 = c0; s1 = c1; s2 = c2; } else { s0 += c0; s1 += c1; s2 += c2; }
+        }
+        gq0 = s0; gq1 = s1; gq2 = s2;
+    }
+    if (P.enabled) { ++st.xs.halo; if (__syncthreads_or(halo_timeout ? 1 : 0)) prr_poison = true; }
     if (st.failed) { if (blockIdx.x == 0 && threadIdx.x == 0) { cg->done = 1; cg->end_cond = 99; } return false; }
     trace_mark(ep.trace, kTraceTail, 4);
     bool stop = false;
@@ -464,7 +493,7 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
     const double alpha_d = st.rho / den;
     const R alpha = R(alpha_d), malpha = R(-alpha_d);
     const bool a_one = (alpha_d == 1.0), ma_one = (-alpha_d == 1.0);
-    double prr = 0.0;
+    double prr = prr_poison ? __longlong_as_double(0x7FF8000000000001ll) : 0.0;    // a lost halo row fails the solve on every rank through the next all-reduce
     if (has_node) {
         const size_t g3 = 3 * size_t(grec.g);
         R gx0, gx1, gx2;
@@ -507,7 +536,7 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
     __syncthreads();
     prr = block_sum(prr, red);
     trace_mark(ep.trace, kTraceTail, 5);
-    const double rho_new = P.enabled ? dist_sync<R>(a, st.sync_count, st.xs, prr, 2, bcast, st.failed) : grid_sync_sum(a.sync, st.sync_count, prr, red, bcast);
+    const double rho_new = P.enabled ? dist_sync<R>(a, st.sync_count, st.xs, prr, bcast, st.failed) : grid_sync_sum(a.sync, st.sync_count, prr, red, bcast);
     if (st.failed) { if (blockIdx.x == 0 && threadIdx.x == 0) { cg->done = 1; cg->end_cond = 99; } return false; }
     trace_mark(ep.trace, kTraceTail, 6);
     const int it2 = st.it + 1;

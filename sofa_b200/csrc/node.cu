@@ -555,7 +555,7 @@ template <class R> static int node_set_distributed(Node<R>* nd, sofab200_comm* c
 }
 // mailbox layout (bytes): 0 halo flags [kMaxPeers] u64 | 64 all-reduce slots [2][kMaxPeers] {double, u64} | 320 epoch u64 | 1024 inbox rows
 constexpr size_t kMailboxFlags = 0, kMailboxAr = 64, kMailboxEpoch = 320, kMailboxInbox = 1024;
-template <class R> static size_t node_peer_bytes(const Node<R>* nd) { return kMailboxInbox + 3 * std::max<size_t>(nd->halo.n_send, 1) * sizeof(R) + 256; }
+template <class R> static size_t node_peer_bytes(const Node<R>* nd) { return kMailboxInbox + size_t(InboxWords<R>::N) * std::max<size_t>(nd->halo.n_send, 1) * sizeof(unsigned long long) + 256; }
 template <class R> static int node_set_peer(Node<R>* nd, const sofab200_peer_desc* d) {
     if (!d->peer_base) { nd->peer.ready = false; if (nd->sg.exec) { cudaGraphExecDestroy(nd->sg.exec); nd->sg.exec = nullptr; nd->sg.seen = 0; } return SOFAB200_OK; }
     SB_CHECK(nd->distributed(), "sofab200_node_set_distributed must come first");
@@ -574,18 +574,16 @@ template <class R> static int node_set_peer(Node<R>* nd, const sofab200_peer_des
     std::memset(&P, 0, sizeof(P));
     P.rank = d->rank; P.world = d->world; P.n_nb = int(H.nb_rank.size()); P.max_sh = H.max_sh;
     unsigned char* mine = static_cast<unsigned char*>(d->peer_base[d->rank]);
-    P.hflag = reinterpret_cast<unsigned long long*>(mine + kMailboxFlags);
     P.ar = reinterpret_cast<ARSlot*>(mine + kMailboxAr);
     P.epoch = reinterpret_cast<unsigned long long*>(mine + kMailboxEpoch);
-    P.inbox = reinterpret_cast<R*>(mine + kMailboxInbox);
+    P.inbox = reinterpret_cast<unsigned long long*>(mine + kMailboxInbox);
     for (int r = 0; r < d->world; ++r) { SB_CHECK(d->peer_base[r] != nullptr, "peer_base entry is null"); P.peer_ar[r] = reinterpret_cast<ARSlot*>(static_cast<unsigned char*>(d->peer_base[r]) + kMailboxAr); }
     for (int k = 0; k < P.n_nb; ++k) {
         const int r = H.nb_rank[k];
         SB_CHECK(r >= 0 && r < d->world && r != d->rank, "neighbour rank out of range");
         unsigned char* base = static_cast<unsigned char*>(d->peer_base[r]);
         P.nb_rank[k] = r;
-        P.nb_hflag[k] = reinterpret_cast<unsigned long long*>(base + kMailboxFlags);
-        P.nb_inbox[k] = reinterpret_cast<R*>(base + kMailboxInbox);
+        P.nb_inbox[k] = reinterpret_cast<unsigned long long*>(base + kMailboxInbox);
     }
     // interface row of every entry of the plan's shared-node table; every interface node must be there
     const std::vector<uint32_t>& sh = tet_shared_node_table(nd->tet);
