@@ -286,11 +286,13 @@ int sofab200_peer_alloc(sofab200_ctx* ctx, size_t bytes, void** dev_ptr, unsigne
 int sofab200_peer_open(sofab200_ctx* ctx, const unsigned char handle[SOFAB200_IPC_HANDLE_BYTES], void** dev_ptr);
 int sofab200_peer_close(sofab200_ctx* ctx, void* dev_ptr);   /* a pointer obtained from sofab200_peer_open  */
 int sofab200_peer_free(sofab200_ctx* ctx, void* dev_ptr);    /* a pointer obtained from sofab200_peer_alloc */
-/* Bytes this node's mailbox needs (valid after sofab200_node_set_distributed). */
-size_t sofab200_node_peer_bytes(const sofab200_node* node);
+/* Bytes this node's mailbox needs (valid after sofab200_node_set_distributed).  inbox_rows: the largest number of interface rows
+ * any rank receives (sum of its nb_count) -- the same value on every rank, also passed in sofab200_peer_desc. */
+size_t sofab200_node_peer_bytes(const sofab200_node* node, size_t inbox_rows);
 typedef struct sofab200_peer_desc {
     int rank, world;            /* world <= 8 (one NVSwitch domain)                                                        */
     void* const* peer_base;     /* [world] mailbox of every rank as mapped in THIS process (own allocation at [rank])      */
+    size_t inbox_rows;          /* rows of one inbox buffer: max over the ranks of the rows a rank receives                */
     const size_t* remote_off;   /* [n_neighbours] (order of sofab200_halo_desc::nb_rank): first inbox row, in neighbour k's
                                  * mailbox, of the block it receives from this rank (= its cumulated nb_count before us)    */
 } sofab200_peer_desc;

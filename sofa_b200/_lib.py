@@ -41,7 +41,7 @@ class HaloDesc(C.Structure):
 
 
 class PeerDesc(C.Structure):
-    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("peer_base", C.POINTER(C.c_void_p)), ("remote_off", C.POINTER(C.c_size_t))]
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("peer_base", C.POINTER(C.c_void_p)), ("inbox_rows", C.c_size_t), ("remote_off", C.POINTER(C.c_size_t))]
 
 
 class SolverParams(C.Structure):
@@ -106,7 +106,7 @@ SYMBOLS = {
     "sofab200_peer_open": (_I, [_P, C.POINTER(C.c_ubyte), C.POINTER(_P)]),
     "sofab200_peer_close": (_I, [_P, _P]),
     "sofab200_peer_free": (_I, [_P, _P]),
-    "sofab200_node_peer_bytes": (_SZ, [_P]),
+    "sofab200_node_peer_bytes": (_SZ, [_P, _SZ]),
     "sofab200_node_set_peer": (_I, [_P, C.POINTER(PeerDesc)]),
 }
 

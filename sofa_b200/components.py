@@ -381,16 +381,16 @@ class SolverNode:
         self._nb_ranks = [s for s, _ in nbs]
         self._nb_counts = [len(v["rows"]) for _, v in nbs]
 
-    def peer_bytes(self):
-        return int(self.ctx.L.sofab200_node_peer_bytes(self.h))
+    def peer_bytes(self, inbox_rows):
+        return int(self.ctx.L.sofab200_node_peer_bytes(self.h, int(inbox_rows)))
 
-    def set_peer(self, rank, world, peer_bases, remote_off):
+    def set_peer(self, rank, world, peer_bases, inbox_rows, remote_off):
         """Multi-GPU CG in one persistent kernel per GPU over peer memory (sofab200_node_set_peer).  peer_bases: every rank's
         mailbox as mapped here; remote_off[k]: first inbox row of our block in neighbour k's mailbox."""
         d = _lib.PeerDesc(); d.rank, d.world = int(rank), int(world)
         bases = (C.c_void_p * world)(*[int(b) for b in peer_bases])
         offs = (C.c_size_t * max(len(remote_off), 1))(*[int(o) for o in remote_off])
-        d.peer_base, d.remote_off = bases, offs
+        d.peer_base, d.remote_off, d.inbox_rows = bases, offs, int(inbox_rows)
         check(self.ctx.L.sofab200_node_set_peer(self.h, C.byref(d)))
 
     def clear_peer(self):

@@ -99,6 +99,7 @@ template <class R> struct PeerDev {
 template <class R> struct PersistCG {
     NodeEpilogue<R> ep;     // epilogue of q = A p: mass / projection terms, dot_kind = DOT_STORE (out is not used)
     R* x; R* r;
+    const R* b;             // right-hand side: |b| and the first rho = r.r are computed by the kernel itself (r == b unless warm start)
     typename SVec<R>::T* xt; typename SVec<R>::T* rt;   // x and r of the interior nodes in tile order (private to the owner CTA: one coalesced access per node)
     R* gstate;              // [9][gridDim.x * blockDim.x] p, r, x of each thread's shared node (private, coalesced), between iterations
     R* p0; R* p1;           // p of the shared nodes, double-buffered: tiles read p_old while the owners write p_new
@@ -547,6 +548,38 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
     st.beta = R(rho_new / st.rho);
     st.rho = rho_new; st.it = it2; st.first = false;
     R* tmp = st.pold; st.pold = st.pnew; st.pnew = tmp;
+    return true;
+}
+
+// Start of the solve: normb = |b| and rho = r.r (CGLinearSolver.inl:130-180), all-reduced over the GPUs in multi-GPU mode (owned
+// nodes only).  Returns false when the solve is already over (b == 0, or the initial residual meets the tolerance).
+template <class R> __device__ __forceinline__ bool persist_init(const PersistCG<R>& a, PersistState<R>& st, double* red, double* bcast) {
+    const PeerDev<R>& P = a.peer;
+    CGDev* cg = a.cg;
+    const size_t n = a.n3 / 3;
+    double sb = 0.0, sr = 0.0;
+    for (size_t g = size_t(blockIdx.x) * blockDim.x + threadIdx.x; g < n; g += size_t(gridDim.x) * blockDim.x) {
+        if (P.enabled && !P.owned[g]) continue;
+        const R b0 = a.b[3 * g], b1 = a.b[3 * g + 1], b2 = a.b[3 * g + 2], r0 = a.r[3 * g], r1 = a.r[3 * g + 1], r2 = a.r[3 * g + 2];
+        sb += double(b0) * double(b0) + double(b1) * double(b1) + double(b2) * double(b2);
+        sr += double(r0) * double(r0) + double(r1) * double(r1) + double(r2) * double(r2);
+    }
+    __syncthreads();
+    sb = block_sum(sb, red);
+    const double nb2 = P.enabled ? dist_sync<R>(a, st.sync_count, st.xs, sb, bcast, st.failed) : grid_sync_sum(a.sync, st.sync_count, sb, red, bcast);
+    __syncthreads();
+    sr = block_sum(sr, red);
+    const double rho0 = P.enabled ? dist_sync<R>(a, st.sync_count, st.xs, sr, bcast, st.failed) : grid_sync_sum(a.sync, st.sync_count, sr, red, bcast);
+    const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
+    if (st.failed) { if (lead) { cg->done = 1; cg->end_cond = 99; } return false; }
+    st.normb = sqrt(nb2);
+    if (lead) cg->normb = st.normb;
+    if (st.normb == 0.0) { if (lead) { cg->done = 1; cg->nb_iter = 0; cg->end_cond = 4; } return false; }
+    if (lead) cg_after_rho(cg, rho0);                      // it: 0 -> 1, first entry of the error graph, tolerance test
+    st.rho = rho0; st.it = 1;
+    if (1u > st.max_iter) return false;
+    const double err = sqrt(rho0) / st.normb;
+    if (err <= st.tol && !(st.tsc == 0)) return false;
     return true;
 }
 

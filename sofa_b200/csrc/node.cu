@@ -134,12 +134,20 @@ template <class R> struct Node : sofab200_node {
         PeerDev<R> dev;
         DevBuf<int32_t> sh_if_row;
         DevBuf<int2> if_send;
+        DevBuf<int> fail_flag;
+        unsigned long long* hcount = nullptr;   // in the mailbox: halo_peer_kernel calls so far
+        size_t buf_words = 0;                   // 8-byte words of one inbox buffer (three buffers: CG kernel, halo even, halo odd)
     } peer;
     bool distributed() const { return halo.comm != nullptr; }
     ncclDataType_t nccl_real() const { return sizeof(R) == 4 ? ncclFloat : ncclDouble; }
     // interface rows of q: sum over the sharing ranks, ascending rank order, same bits on every rank
     int halo_sum(R* qv, const CGDev* cgp) {
         if (!distributed() || halo.n_if == 0) return SOFAB200_OK;
+        if (peer.ready && !cgp) {
+            // over peer memory, one small kernel (the NCCL route below costs three launches and a send/recv group)
+            LAUNCH(ctx, (halo_peer_kernel<R>), 1, 1024, peer.dev, halo.n_if, (const uint32_t*)halo.if_idx.p, qv, peer.hcount, peer.buf_words, peer.fail_flag.p);
+            return SOFAB200_OK;
+        }
         LAUNCH(ctx, (halo_pack_kernel<R>), vec_grid(halo.n_send, ctx->sm_count), kVecBlock, halo.n_send, (const uint32_t*)halo.send_idx.p, (const R*)qv, halo.sendbuf.p, cgp);
         SB_NCCL(ncclGroupStart());
         for (size_t k = 0; k < halo.nb_rank.size(); ++k) {
@@ -195,7 +203,7 @@ template <class R> struct Node : sofab200_node {
         return SOFAB200_OK;
     }
     // the whole CG loop in one cooperative launch (cg_persist.cuh); pd != null: multi-GPU over peer memory
-    int launch_persistent(R* x, double m, double bfac, double kf, const PeerDev<R>* pd) {
+    int launch_persistent(R* x, const R* bvec, double m, double bfac, double kf, const PeerDev<R>* pd) {
         const size_t n3 = 3 * n;
         if (!p2.p) SB_TRY(p2.alloc(n3));
         const size_t n_tile_nodes = tet_tile_node_count(tet);
@@ -204,7 +212,7 @@ template <class R> struct Node : sofab200_node {
         if (!sync_slots.p) SB_TRY(sync_slots.alloc(3 * 2048 + 8));
         PersistCG<R> a;
         a.ep = make_mbk_ep(q.p, nullptr, p.p, m, bfac, false, 1.0, true, DOT_STORE, cg.p);
-        a.x = x; a.r = r.p; a.xt = xt.p; a.rt = rt.p; a.gstate = gstate.p; a.p0 = p.p; a.p1 = p2.p; a.n3 = n3; a.cg = cg.p; a.sync = sync_slots.p;
+        a.x = x; a.r = r.p; a.b = bvec; a.xt = xt.p; a.rt = rt.p; a.gstate = gstate.p; a.p0 = p.p; a.p1 = p2.p; a.n3 = n3; a.cg = cg.p; a.sync = sync_slots.p;
         if (pd) a.peer = *pd; else std::memset(&a.peer, 0, sizeof(a.peer));
         a.debug = 0; if (const char* env = getenv("SOFAB200_DEBUG_MODE")) a.debug = atoi(env);
         SB_CUDA(cudaMemsetAsync(sync_slots.p, 0, sync_slots.n * sizeof(unsigned long long), ctx->stream));
@@ -272,17 +280,16 @@ template <class R> struct Node : sofab200_node {
         const int gd = std::max(1, std::min<int>(2 * ctx->sm_count, int((n3 / 4 + kVecBlock - 1) / kVecBlock)));
         if (distributed()) {
             // same loop, with the interface rows of q exchanged and the three dot products all-reduced over the ranks
-            SB_TRY(dist_dot(bvec, bvec, DF_CG_NORMB));
-            SB_TRY(dist_dot(r.p, r.p, DF_CG_RHO));
             const double kf_d = k + bfac * prm.ff_rayleigh_stiffness;
             if (peer.ready && persistent && tet && (kf_d != 0.0 || bfac != 0.0)) {
                 // the loop in ONE persistent kernel per GPU; halo rows and dot products go through peer memory (cg_persist.cuh)
-                const int rc = launch_persistent(x, m, bfac, kf_d, &peer.dev);
+                const int rc = launch_persistent(x, bvec, m, bfac, kf_d, &peer.dev);
                 if (rc == SOFAB200_OK) { LAUNCH(ctx, cg_end_kernel, 1, 1, cg.p); return SOFAB200_OK; }
                 if (rc != kPersistNotEligible) return rc;
-                peer.ready = false;      // this partition does not fit the kernel: NCCL loop from now on (every rank decides alike
-                                         // only if the partitions are alike -- the caller checks with sofab200_node_last_solve)
+                peer.ready = false;      // (cannot happen after sofab200_node_set_peer's probe; kept for safety)
             }
+            SB_TRY(dist_dot(bvec, bvec, DF_CG_NORMB));
+            SB_TRY(dist_dot(r.p, r.p, DF_CG_RHO));
             for (unsigned it = 1; it <= prm.iterations; ++it) {
                 LAUNCH(ctx, (cg_p_update_kernel<R>), gd, kVecBlock, n3, p.p, (const R*)r.p, (const CGDev*)cg.p);
                 SB_TRY(add_mbk(q.p, nullptr, p.p, m, bfac, k, false, 1.0, true, DOT_NONE, cg.p));
@@ -294,15 +301,15 @@ template <class R> struct Node : sofab200_node {
             LAUNCH(ctx, cg_end_kernel, 1, 1, cg.p);
             return SOFAB200_OK;
         }
-        LAUNCH(ctx, (vdot_kernel<R>), gd, kVecBlock, n3, bvec, bvec, partials.p, counters.p + 1, int(DF_CG_NORMB), (double*)nullptr, cg.p);
-        LAUNCH(ctx, (vdot_kernel<R>), gd, kVecBlock, n3, (const R*)r.p, (const R*)r.p, partials.p, counters.p + 1, int(DF_CG_RHO), (double*)nullptr, cg.p);
         const double kf_chk = k + bfac * prm.ff_rayleigh_stiffness;
         if (persistent && tet && (kf_chk != 0.0 || bfac != 0.0)) {
-            const int rc = launch_persistent(x, m, bfac, kf_chk, nullptr);
+            const int rc = launch_persistent(x, bvec, m, bfac, kf_chk, nullptr);     // (|b| and the first rho included)
             if (rc == SOFAB200_OK) { LAUNCH(ctx, cg_end_kernel, 1, 1, cg.p); return SOFAB200_OK; }
             if (rc != kPersistNotEligible) return rc;
             persistent = false;      // this mesh does not fit: multi-kernel loop from now on
         }
+        LAUNCH(ctx, (vdot_kernel<R>), gd, kVecBlock, n3, bvec, bvec, partials.p, counters.p + 1, int(DF_CG_NORMB), (double*)nullptr, cg.p);
+        LAUNCH(ctx, (vdot_kernel<R>), gd, kVecBlock, n3, (const R*)r.p, (const R*)r.p, partials.p, counters.p + 1, int(DF_CG_RHO), (double*)nullptr, cg.p);
         if (fused_tail && (kf_chk != 0.0 || bfac != 0.0)) {
             // two launches per iteration: the element pass, then the fused cooperative tail (which also prepares the next p)
             SB_CUDA(cudaMemcpyAsync(p.p, r.p, n3 * sizeof(R), cudaMemcpyDeviceToDevice, ctx->stream));   // p = r (first iteration)
@@ -553,9 +560,13 @@ template <class R> static int node_set_distributed(Node<R>* nd, sofab200_comm* c
     if (nd->sg.exec) { cudaGraphExecDestroy(nd->sg.exec); nd->sg.exec = nullptr; nd->sg.seen = 0; }
     return SOFAB200_OK;
 }
-// mailbox layout (bytes): 0 halo flags [kMaxPeers] u64 | 64 all-reduce slots [2][kMaxPeers] {double, u64} | 320 epoch u64 | 1024 inbox rows
-constexpr size_t kMailboxFlags = 0, kMailboxAr = 64, kMailboxEpoch = 320, kMailboxInbox = 1024;
-template <class R> static size_t node_peer_bytes(const Node<R>* nd) { return kMailboxInbox + size_t(InboxWords<R>::N) * std::max<size_t>(nd->halo.n_send, 1) * sizeof(unsigned long long) + 256; }
+// mailbox layout (bytes): 64 all-reduce slots [2][kMaxPeers][2 words] | 320 epoch u64 | 328 halo-call counter u64 | 1024 three inbox
+// buffers of inbox_rows rows each (the same inbox_rows on every rank, so that the offsets in a peer's mailbox are known)
+constexpr size_t kMailboxFlags = 0, kMailboxAr = 64, kMailboxEpoch = 320, kMailboxHcount = 328, kMailboxInbox = 1024;
+template <class R> static size_t inbox_buf_words(size_t rows) { return (size_t(InboxWords<R>::N) * std::max<size_t>(rows, 1) + 31) & ~size_t(31); }
+template <class R> static size_t node_peer_bytes(const Node<R>* nd, size_t rows) {
+    return kMailboxInbox + 3 * inbox_buf_words<R>(std::max(rows, nd->halo.n_send)) * sizeof(unsigned long long) + 256;
+}
 template <class R> static int node_set_peer(Node<R>* nd, const sofab200_peer_desc* d) {
     if (!d->peer_base) { nd->peer.ready = false; if (nd->sg.exec) { cudaGraphExecDestroy(nd->sg.exec); nd->sg.exec = nullptr; nd->sg.seen = 0; } return SOFAB200_OK; }
     SB_CHECK(nd->distributed(), "sofab200_node_set_distributed must come first");
@@ -576,6 +587,10 @@ template <class R> static int node_set_peer(Node<R>* nd, const sofab200_peer_des
     unsigned char* mine = static_cast<unsigned char*>(d->peer_base[d->rank]);
     P.ar = reinterpret_cast<ARSlot*>(mine + kMailboxAr);
     P.epoch = reinterpret_cast<unsigned long long*>(mine + kMailboxEpoch);
+    nd->peer.hcount = reinterpret_cast<unsigned long long*>(mine + kMailboxHcount);
+    SB_CHECK(d->inbox_rows >= H.n_send, "inbox_rows must be the largest number of received rows over all ranks");
+    nd->peer.buf_words = inbox_buf_words<R>(d->inbox_rows);
+    SB_TRY(nd->peer.fail_flag.alloc(1)); SB_TRY(nd->peer.fail_flag.zero(s));
     P.inbox = reinterpret_cast<unsigned long long*>(mine + kMailboxInbox);
     for (int r = 0; r < d->world; ++r) { SB_CHECK(d->peer_base[r] != nullptr, "peer_base entry is null"); P.peer_ar[r] = reinterpret_cast<ARSlot*>(static_cast<unsigned char*>(d->peer_base[r]) + kMailboxAr); }
     for (int k = 0; k < P.n_nb; ++k) {
@@ -614,9 +629,9 @@ template <class R> static int node_set_peer(Node<R>* nd, const sofab200_peer_des
 }
 }  // namespace sb
 extern "C" {
-size_t sofab200_node_peer_bytes(const sofab200_node* node) {
+size_t sofab200_node_peer_bytes(const sofab200_node* node, size_t inbox_rows) {
     if (!node) return 0;
-    return node->real == SOFAB200_F32 ? node_peer_bytes<float>(static_cast<const Node<float>*>(node)) : node_peer_bytes<double>(static_cast<const Node<double>*>(node));
+    return node->real == SOFAB200_F32 ? node_peer_bytes<float>(static_cast<const Node<float>*>(node), inbox_rows) : node_peer_bytes<double>(static_cast<const Node<double>*>(node), inbox_rows);
 }
 int sofab200_node_set_peer(sofab200_node* node, const sofab200_peer_desc* peer) {
     SB_CHECK(node && peer, "null argument");   /* peer->peer_base == NULL: leave peer mode */

@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(MAXT) tet_cg_persistent_kernel(TetDev<R> d, Pe
     R* s_slot = reinterpret_cast<R*>(smem_raw + L.off_slot);
     PersistState<R> st(a);
     persist_load_tables<R>(t, a, smem_raw, s_grec);
+    if (!persist_init<R>(a, st, red, &bcast)) { persist_finish<R>(t, a, st, smem_raw, s_grec); return; }
     for (;;) {
         trace_mark(a.ep.trace, kTraceTail, 0);
         // ---- [A]

@@ -211,6 +211,46 @@ template <class R> __global__ void __launch_bounds__(kVecBlock) mask_rows_kernel
         out[3 * g] = o ? in[3 * g] : R(0); out[3 * g + 1] = o ? in[3 * g + 1] : R(0); out[3 * g + 2] = o ? in[3 * g + 2] : R(0);
     }
 }
+// ---- halo sum over peer memory (multi-GPU, outside the CG kernel: addForce and the right-hand side) ---------------------------
+// One CTA: every interface row of q is stored into the sharing neighbours' inboxes as self-validating 8-byte words (payload +
+// sequence number, see cg_persist.cuh), then the rows are rebuilt from the own value and the neighbours' words in ascending rank
+// order.  Two inbox buffers alternate from call to call (a neighbour may start call k+1 before this rank has read call k).
+template <class R> __global__ void __launch_bounds__(1024) halo_peer_kernel(PeerDev<R> P, size_t n_if, const uint32_t* __restrict__ if_idx, R* q,
+                                                                             unsigned long long* hcount, size_t buf_words, int* fail_flag) {
+    const unsigned long long c = *hcount + 1;
+    const unsigned seq = unsigned(c);
+    const size_t boff = (1 + (c & 1ull)) * buf_words;       // buffer 0 belongs to the CG kernel
+    const int ms1 = P.max_sh - 1;
+    __syncthreads();                                          // everyone has read hcount before thread 0 bumps it
+    for (size_t row = threadIdx.x; row < n_if; row += blockDim.x) {
+        const size_t g3 = 3 * size_t(if_idx[row]);
+        const R v0 = q[g3], v1 = q[g3 + 1], v2 = q[g3 + 2];
+        for (int e = 0; e < ms1; ++e) {
+            const int2 to = P.if_send[row * ms1 + e];
+            if (to.x >= 0) { unsigned long long* d = P.nb_inbox[to.x] + boff + size_t(InboxWords<R>::N) * size_t(to.y); inbox_put(d, 0, v0, seq); inbox_put(d, 1, v1, seq); inbox_put(d, 2, v2, seq); }
+        }
+    }
+    for (size_t row = threadIdx.x; row < n_if; row += blockDim.x) {
+        const size_t g3 = 3 * size_t(if_idx[row]);
+        R s0 = R(0), s1 = R(0), s2 = R(0);
+        for (int j = 0; j < P.max_sh; ++j) {
+            const int sj = P.src[row * P.max_sh + j];
+            R c0 = R(0), c1 = R(0), c2 = R(0);
+            if (sj == -1) { c0 = q[g3]; c1 = q[g3 + 1]; c2 = q[g3 + 2]; }
+            else if (sj >= 0) {
+                const unsigned long long* w = P.inbox + boff + size_t(InboxWords<R>::N) * size_t(sj);
+                const unsigned long long t0 = globaltimer_ns();
+                while (!(inbox_get(w, 0, seq, c0) && inbox_get(w, 1, seq, c1) && inbox_get(w, 2, seq, c2)))
+                    if (globaltimer_ns() - t0 > kSyncTimeoutNs) { *fail_flag = 1; break; }
+            }
+            if (j == 0) { s0 = c0; s1 = c1; s2 = c2; } else { s0 += c0; s1 += c1; s2 += c2; }
+        }
+        q[g3] = s0; q[g3 + 1] = s1; q[g3 + 2] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *hcount = c;
+}
+
 // the scalar bookkeeping of the CG after an all-reduced dot product
 __global__ void cg_scalar_kernel(CGDev* cg, const double* value, int action) {
     if (cg->done) return;

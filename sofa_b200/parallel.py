@@ -142,8 +142,11 @@ class DeviceBackend:
     def _attach_peer(self, rm, group):
         """Peer-memory mode: every rank's mailbox mapped into every process with CUDA IPC (torch.distributed only ships the
         64-byte handles), then the CG loop is one persistent kernel per GPU that exchanges over NVLink by itself."""
+        rows = [None] * rm.world
+        dist.all_gather_object(rows, int(sum(len(v["rows"]) for v in rm.neighbours.values())), group=group)
+        inbox_rows = max(rows)
         try:
-            ptr, handle = self.ctx.peer_alloc(self.node.peer_bytes())
+            ptr, handle = self.ctx.peer_alloc(self.node.peer_bytes(inbox_rows))
         except Exception:
             handle, ptr = None, None
         handles = [None] * rm.world
@@ -168,7 +171,7 @@ class DeviceBackend:
             return False
         remote_off = [all_offs[s][rm.rank] for s, _ in nbs]
         try:
-            self.node.set_peer(rm.rank, rm.world, bases, remote_off)
+            self.node.set_peer(rm.rank, rm.world, bases, inbox_rows, remote_off)
             ok = True
         except Exception as e:  # e.g. the partition does not fit the persistent kernel's assumptions
             ok = False

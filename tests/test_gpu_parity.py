@@ -143,7 +143,7 @@ def test_cg_solve_matches_oracle(dtype):
     s.fem_add_force(np.zeros_like(x), x); z = mo.new_vector(); g["ff"].addForce(z, dev(mo, x))   # cache rotations at x on both sides
     b = rng.standard_normal(x.shape).astype(dtype); b[g["fixed"]] = 0
     m, bf, k = 1.001, -0.01, -0.0011
-    for iters, tol in ((25, 1e-9), (100, 1e-4)):
+    for iters, tol in ((25, 1e-9), (100, 1e-4), (1, 1e-9), (2, 1e-9)):   # (1 and 2: the solve ends inside its first iterations)
         node.set_params(iterations=iters, tolerance=tol, threshold=1e-9)
         sol_d = mo.new_vector()
         it = node.cg_solve(sol_d, dev(mo, b), m, bf, k)
@@ -160,6 +160,11 @@ def test_cg_solve_matches_oracle(dtype):
             if it == it_ref:
                 assert rel_err(sol_d.cpu().numpy(), sol_ref) <= (1e-8 if (dd or dtype == np.float64) else 2e-3)
                 assert info["end_condition"] == s.end_condition
+    # b == 0: the reference returns at once with x = 0 (CGLinearSolver.inl:141-152)
+    node.set_params(iterations=25, tolerance=1e-9, threshold=1e-9)
+    sol_d = mo.new_vector(); sol_d.fill_(7.0)
+    it = node.cg_solve(sol_d, dev(mo, np.zeros_like(b)), m, bf, k)
+    assert it == 0 and float(sol_d.abs().max()) == 0.0
 
 
 def _sync_state(g, s):
