@@ -102,13 +102,14 @@ template <class R> struct PersistCG {
     const R* b;             // right-hand side: |b| and the first rho = r.r are computed by the kernel itself (r == b unless warm start)
     typename SVec<R>::T* xt; typename SVec<R>::T* rt;   // x and r of the interior nodes in tile order (private to the owner CTA: one coalesced access per node)
     R* gstate;              // [9][gridDim.x * blockDim.x] p, r, x of each thread's shared node (private, coalesced), between iterations
-    R* p0; R* p1;           // p of the shared nodes, double-buffered: tiles read p_old while the owners write p_new
+    typename SVec<R>::T* p0; typename SVec<R>::T* p1;   // p of the shared nodes by node id, padded (one 16-byte access in Vec3f), double-buffered:
+                            // tiles read p_old while the owners write p_new
+    typename SVec<R>::T* rs; // r of the shared nodes by node id, padded (the flat r is only read in the first iteration)
     size_t n3;
     CGDev* cg;
     unsigned long long* sync;   // [3 * gridDim.x + 1] grid_sync_sum slots and arrival counter, zero at launch
     PersistLayout lay;
     PeerDev<R> peer;
-    int debug;              // tuning experiments (SOFAB200_DEBUG_MODE)
 };
 
 // ---- grid-wide barrier that also sums one double per CTA --------------------------------------------------------------
@@ -263,7 +264,7 @@ template <class R> __device__ __forceinline__ double dist_sync(const PersistCG<R
 }
 
 template <class R> struct PersistState {
-    R* pold; R* pnew;
+    typename SVec<R>::T* pold; typename SVec<R>::T* pnew;
     double rho, normb, tol, thr;
     int it;
     unsigned tsc, max_iter;
@@ -283,6 +284,11 @@ template <class R> struct PersistState {
     }
 };
 
+// L2-coherent load of a padded nodal vector (written by another CTA earlier in the same kernel)
+__device__ __forceinline__ float4 sv_ldcg(const float4* p) { return __ldcg(p); }
+__device__ __forceinline__ SVec<double>::T sv_ldcg(const SVec<double>::T* p) {
+    SVec<double>::T v; const double* d = reinterpret_cast<const double*>(p); v.x = __ldcg(d); v.y = __ldcg(d + 1); v.z = __ldcg(d + 2); return v;
+}
 // p = p*beta + r  (cgstep_beta -> vOp_avf, CGLinearSolver.inl:184-197), one component
 template <class R> __device__ __forceinline__ R p_update(R p, R beta, R r) { p *= beta; p += r; return p; }
 
@@ -341,11 +347,10 @@ template <class R> __device__ __forceinline__ void persist_phase1(const TileDev<
                 }
             } else {
                 const size_t g = s_tidx[c * L.max_shtouch + (k - n_int)];
-                const R r0 = __ldcg(a.r + 3 * g), r1 = __ldcg(a.r + 3 * g + 1), r2 = __ldcg(a.r + 3 * g + 2);
-                if (st.first) { p0 = r0; p1 = r1; p2 = r2; }
+                if (st.first) { p0 = __ldcg(a.r + 3 * g); p1 = __ldcg(a.r + 3 * g + 1); p2 = __ldcg(a.r + 3 * g + 2); }
                 else {
-                    p0 = p_update<R>(__ldcg(st.pold + 3 * g), st.beta, r0); p1 = p_update<R>(__ldcg(st.pold + 3 * g + 1), st.beta, r1);
-                    p2 = p_update<R>(__ldcg(st.pold + 3 * g + 2), st.beta, r2);
+                    const SV rv = sv_ldcg(a.rs + g), po = sv_ldcg(st.pold + g);
+                    p0 = p_update<R>(R(po.x), st.beta, R(rv.x)); p1 = p_update<R>(R(po.y), st.beta, R(rv.y)); p2 = p_update<R>(R(po.z), st.beta, R(rv.z));
                 }
             }
             s_in[c * L.max_touched + k] = SVec<R>::make(p0, p1, p2);
@@ -425,7 +430,7 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
             gr0 = a.gstate[3 * gs_n + gs_i]; gr1 = a.gstate[4 * gs_n + gs_i]; gr2 = a.gstate[5 * gs_n + gs_i];
             gp0 = p_update<R>(a.gstate[gs_i], st.beta, gr0); gp1 = p_update<R>(a.gstate[gs_n + gs_i], st.beta, gr1); gp2 = p_update<R>(a.gstate[2 * gs_n + gs_i], st.beta, gr2);
         }
-        R* d = st.pnew + g3; d[0] = gp0; d[1] = gp1; d[2] = gp2;      // for the tiles that touch the node, next iteration
+        st.pnew[grec.g] = SVec<R>::make(gp0, gp1, gp2);               // for the tiles that touch the node, next iteration
     }
     trace_mark(ep.trace, kTraceTail, 1);
     grid_sync(a.sync, st.sync_count);                  // staged contributions are complete
@@ -504,7 +509,7 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
         own += xr_one<R>(gx1, gr1, gp1, gq1, alpha, malpha, a_one, ma_one);
         own += xr_one<R>(gx2, gr2, gp2, gq2, alpha, malpha, a_one, ma_one);
         if (counted) prr += own;
-        a.r[g3] = gr0; a.r[g3 + 1] = gr1; a.r[g3 + 2] = gr2;                    // for the tiles that touch the node
+        a.rs[grec.g] = SVec<R>::make(gr0, gr1, gr2);                           // for the tiles that touch the node
         a.gstate[gs_i] = gp0; a.gstate[gs_n + gs_i] = gp1; a.gstate[2 * gs_n + gs_i] = gp2;
         a.gstate[3 * gs_n + gs_i] = gr0; a.gstate[4 * gs_n + gs_i] = gr1; a.gstate[5 * gs_n + gs_i] = gr2;
         a.gstate[6 * gs_n + gs_i] = gx0; a.gstate[7 * gs_n + gs_i] = gx1; a.gstate[8 * gs_n + gs_i] = gx2;
@@ -547,7 +552,7 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
     if (stop2) return false;
     st.beta = R(rho_new / st.rho);
     st.rho = rho_new; st.it = it2; st.first = false;
-    R* tmp = st.pold; st.pold = st.pnew; st.pnew = tmp;
+    typename SVec<R>::T* tmp = st.pold; st.pold = st.pnew; st.pnew = tmp;
     return true;
 }
 

@@ -177,9 +177,8 @@ template <class R> struct Node : sofab200_node {
     // ---- fused CG tail (cooperative kernel): gather + den | x,r update + rho | p update
     bool fused_tail = true;
     bool persistent = true;      // SOFAB200_CG_PERSISTENT=0 selects the multi-kernel loop
-    DevBuf<R> p2;
     DevBuf<unsigned long long> sync_slots;
-    DevBuf<typename SVec<R>::T> xt, rt;
+    DevBuf<typename SVec<R>::T> xt, rt, ps0, ps1, rs;
     DevBuf<R> gstate;
     int tail_grid = 0;
     DevBuf<double> partials_rho;
@@ -205,16 +204,15 @@ template <class R> struct Node : sofab200_node {
     // the whole CG loop in one cooperative launch (cg_persist.cuh); pd != null: multi-GPU over peer memory
     int launch_persistent(R* x, const R* bvec, double m, double bfac, double kf, const PeerDev<R>* pd) {
         const size_t n3 = 3 * n;
-        if (!p2.p) SB_TRY(p2.alloc(n3));
+        if (!ps0.p) { SB_TRY(ps0.alloc(n)); SB_TRY(ps1.alloc(n)); SB_TRY(rs.alloc(n)); }
         const size_t n_tile_nodes = tet_tile_node_count(tet);
         if (xt.n < n_tile_nodes) { SB_TRY(xt.alloc(n_tile_nodes)); SB_TRY(rt.alloc(n_tile_nodes)); }
         if (!gstate.p) SB_TRY(gstate.alloc(size_t(9) * ctx->sm_count * 2048));
         if (!sync_slots.p) SB_TRY(sync_slots.alloc(3 * 2048 + 8));
         PersistCG<R> a;
         a.ep = make_mbk_ep(q.p, nullptr, p.p, m, bfac, false, 1.0, true, DOT_STORE, cg.p);
-        a.x = x; a.r = r.p; a.b = bvec; a.xt = xt.p; a.rt = rt.p; a.gstate = gstate.p; a.p0 = p.p; a.p1 = p2.p; a.n3 = n3; a.cg = cg.p; a.sync = sync_slots.p;
+        a.x = x; a.r = r.p; a.b = bvec; a.xt = xt.p; a.rt = rt.p; a.gstate = gstate.p; a.p0 = ps0.p; a.p1 = ps1.p; a.rs = rs.p; a.n3 = n3; a.cg = cg.p; a.sync = sync_slots.p;
         if (pd) a.peer = *pd; else std::memset(&a.peer, 0, sizeof(a.peer));
-        a.debug = 0; if (const char* env = getenv("SOFAB200_DEBUG_MODE")) a.debug = atoi(env);
         SB_CUDA(cudaMemsetAsync(sync_slots.p, 0, sync_slots.n * sizeof(unsigned long long), ctx->stream));
         const int rc = tet_cg_persistent<R>(tet, R(kf), a, sync_slots.n - 8, false);
         if (rc == SOFAB200_OK) ctx->launches++;

@@ -67,8 +67,7 @@ template <class R> static int tet_upload(TetFF<R>& ff) {
 template <class R, int MODE, int MAXT, bool PF> static int tet_launch_variant(TetFF<R>& ff, const TetDev<R>& d, const R* in, const NodeEpilogue<R>& ep) {
     auto kern = tet_tile_kernel<R, MODE, MAXT, PF>;
     static thread_local size_t configured = 0;
-    static const size_t extra = getenv("SOFAB200_EXTRA_SMEM_KB") ? size_t(atoi(getenv("SOFAB200_EXTRA_SMEM_KB"))) * 1024 : 0;   // tuning experiment
-    const size_t smem_total = ff.h.smem_bytes + extra;
+    const size_t smem_total = ff.h.smem_bytes;
     if (smem_total > 48 * 1024 && configured < smem_total) {
         SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_total)));
         configured = smem_total;

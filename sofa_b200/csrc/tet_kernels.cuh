@@ -209,25 +209,6 @@ __device__ __forceinline__ void tet_tile_elements(const TetDev<R>& d, int tile, 
     }
 }
 
-// Asks the L2 to fetch the record planes of a tile (addDForce planes) from HBM: the CG kernel issues this while its SM is busy
-// with latency-bound phases, so that HBM keeps streaming and the element pass then reads from L2.
-__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
-}
-template <class R> __device__ __forceinline__ void tet_prefetch_tile(const TetDev<R>& d, int tile, int shift = 0) {
-    const size_t e0 = size_t(tile) * d.t.tile_e;
-    const unsigned ne = (unsigned(d.t.tile_e) >> shift) & ~31u;
-    const char* base[8] = {reinterpret_cast<const char*>(d.lnode + e0), reinterpret_cast<const char*>(d.slot + e0),
-                           reinterpret_cast<const char*>(d.rk0 + e0), reinterpret_cast<const char*>(d.rk1 + e0), reinterpret_cast<const char*>(d.rk2 + e0),
-                           reinterpret_cast<const char*>(d.j0 + e0), reinterpret_cast<const char*>(d.j1 + e0), reinterpret_cast<const char*>(d.j2 + e0)};
-    const unsigned bytes[8] = {ne * 8u, ne * 16u, ne * unsigned(sizeof(Quad<R>)), ne * unsigned(sizeof(Quad<R>)), ne * unsigned(sizeof(Quad<R>)),
-                               ne * unsigned(sizeof(Quad<R>)), ne * unsigned(sizeof(Quad<R>)), ne * unsigned(sizeof(Quad<R>))};
-    constexpr unsigned kPiece = 4096;
-#pragma unroll
-    for (int pl = 0; pl < 8; ++pl)
-        for (unsigned off = threadIdx.x * kPiece; off < bytes[pl]; off += blockDim.x * kPiece) l2_prefetch_bulk(base[pl] + off, min(kPiece, bytes[pl] - off));
-}
-
 // MAXT: CTA size the kernel is compiled for (register budget 65536/MAXT)
 template <class R, int MODE, int MAXT, bool PF>
 __global__ void __launch_bounds__(MAXT) tet_tile_kernel(TetDev<R> d, const R* __restrict__ in, NodeEpilogue<R> ep, int max_touched, int max_slots) {
