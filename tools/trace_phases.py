@@ -65,8 +65,7 @@ if s:
     tl = tail[tail[:, 0] > 0].astype(np.int64)
     us = lambda a, b: round(float(np.median(tl[:, b] - tl[:, a])) / 1000.0, 2)
     res["cg_persistent_last_iteration"]["detail_us"] = {
-        "p-update + staging (all tiles of the CTA)": us(0, 12), "first tile: elements": us(12, 13), "first tile: interior sums": us(13, 14),
-        "shared: barrier1 -> first staged entry": us(2, 8), "shared: ordered sum": us(8, 9), "shared: epilogue + CTA sum": us(9, 3)}
+        "p-update + staging (all tiles of the CTA)": us(0, 12), "first tile: elements": us(12, 13), "first tile: interior sums": us(13, 14)}
 print(json.dumps(res, indent=1))
 if args.out:
     np.savez_compressed(args.out, tile=tile, tail=tail)
