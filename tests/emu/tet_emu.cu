@@ -110,9 +110,9 @@ struct EmuEpilogue {
 
 extern "C" {
 void* emu_tet_create(int real, size_t n_nodes, const void* rest, size_t n_tets, const uint32_t* tets, int method, size_t ny, const double* young,
-                     size_t np, const double* poisson, int tile_e) {
+                     size_t np, const double* poisson, int tile_e, const unsigned char* shared_nodes) {
     EmuAny* e = new EmuAny(); e->real = real;
-    sofab200_tetfem_desc d{}; d.method = method; d.n_young = ny; d.young = young; d.n_poisson = np; d.poisson = poisson; d.tile_elems = tile_e;
+    sofab200_tetfem_desc d{}; d.method = method; d.n_young = ny; d.young = young; d.n_poisson = np; d.poisson = poisson; d.tile_elems = tile_e; d.shared_nodes = shared_nodes;
     if (real == 0) { e->err = tet_host_build(e->f.h, n_nodes, (const float*)rest, n_tets, tets, &d, kGatherChunk); e->f.stage.assign(e->f.h.plan.stage_n, Quad<float>{777.f, 777.f, 777.f, 0.f}); }
     else { e->err = tet_host_build(e->d.h, n_nodes, (const double*)rest, n_tets, tets, &d, kGatherChunk); e->d.stage.assign(e->d.h.plan.stage_n, Quad<double>{777.0, 777.0, 777.0, 0.0}); }
     return e;

@@ -50,15 +50,18 @@ def _ptr(a):
 class EmuTet:
     METHODS = {"small": 0, "large": 1, "polar": 2, "svd": 3}
 
-    def __init__(self, dtype, rest, tets, method, young, poisson, tile_e=256):
+    def __init__(self, dtype, rest, tets, method, young, poisson, tile_e=256, shared_nodes=None):
         self.dtype = np.dtype(dtype)
         self.real = 0 if self.dtype == np.float32 else 1
         rest = np.ascontiguousarray(rest, self.dtype)
         tets = np.ascontiguousarray(tets, np.uint32)
         y = np.atleast_1d(np.asarray(young, np.float64)); p = np.atleast_1d(np.asarray(poisson, np.float64))
         self.n = rest.shape[0]
+        shared = None
+        if shared_nodes is not None:
+            shared = np.zeros(self.n, np.uint8); shared[np.asarray(shared_nodes, np.int64)] = 1
         self.h = _P(lib().emu_tet_create(self.real, C.c_size_t(self.n), _ptr(rest), C.c_size_t(tets.shape[0]), _ptr(tets), self.METHODS[method],
-                                         C.c_size_t(len(y)), _ptr(y), C.c_size_t(len(p)), _ptr(p), int(tile_e)))
+                                         C.c_size_t(len(y)), _ptr(y), C.c_size_t(len(p)), _ptr(p), int(tile_e), _ptr(shared) if shared is not None else None))
         err = lib().emu_tet_error(self.h).decode()
         if err:
             raise RuntimeError(err)

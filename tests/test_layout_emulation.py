@@ -108,3 +108,18 @@ def test_slot_budget_demotes_interior_nodes_bit_exact(monkeypatch):
     dx = (1e-3 * rng.standard_normal(pos.shape)).astype(np.float32)
     df0 = rng.standard_normal(pos.shape).astype(np.float32)
     assert e.run(True, dx, kf=-0.37, init=df0).tobytes() == s.fem_add_dforce(df0, dx, -0.37).tobytes()
+
+
+def test_forced_shared_nodes_bit_exact():
+    """Nodes flagged in sofab200_tetfem_desc::shared_nodes (the partition interface of a multi-GPU run) take the staging path even
+    when all their elements sit in one tile; the sums stay bit-identical."""
+    pos, tets, x, rng = _beam(n=(6, 6, 11))
+    forced = np.arange(0, pos.shape[0], 3)
+    e = EmuTet(np.float32, pos, tets, "large", 1000.0, 0.3, 512, shared_nodes=forced)
+    e0 = EmuTet(np.float32, pos, tets, "large", 1000.0, 0.3, 512)
+    assert e.stats()["shared"] > e0.stats()["shared"] and e.stats()["shared"] >= len(forced)
+    s = O.OracleScene(np.float32, pos); s.set_tets(tets, "large", 1000.0, 0.3)
+    f0 = rng.standard_normal(pos.shape).astype(np.float32)
+    assert e.run(False, x.astype(np.float32), init=f0).tobytes() == s.fem_add_force(f0, x.astype(np.float32)).tobytes()
+    dx = (1e-3 * rng.standard_normal(pos.shape)).astype(np.float32)
+    assert e.run(True, dx, kf=-0.37, init=f0).tobytes() == s.fem_add_dforce(f0, dx, -0.37).tobytes()
