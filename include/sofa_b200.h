@@ -268,7 +268,8 @@ typedef struct sofab200_halo_desc {
 /* Attach a communicator and a halo plan to a node: from then on sofab200_node_step / _cg_solve / _apply / _compute_force run
  * the distributed algorithm -- rank-local fused element pass, NCCL send/recv of the interface partial sums added in
  * ascending rank order on every sharing rank, dot products over owned nodes all-reduced -- still without any host round
- * trip per iteration and still replayed from one CUDA graph per step.  The node's vertexMass must hold the global lumped
+ * trip per iteration and still replayed from one CUDA graph per step.  sofab200_node_set_peer (below) then replaces the
+ * NCCL traffic by stores into peer memory from inside one persistent kernel per GPU.  The node's vertexMass must hold the global lumped
  * mass on owned nodes and 0 elsewhere (sofab200_node_set_vertex_mass). */
 int sofab200_node_set_distributed(sofab200_node* node, sofab200_comm* comm, const sofab200_halo_desc* halo);
 

@@ -6,20 +6,22 @@
 //     one CTA processes one tile.
 //   * a node whose incident elements all lie in one tile is INTERIOR to it: its corner contributions
 //     are staged in shared memory and summed in-kernel.  Every other node is SHARED: its contributions
-//     are staged in HBM (`stage`) and summed by the boundary kernel.
+//     are staged in HBM/L2 (`stage`) and summed by one thread per node -- in the boundary kernel
+//     (gather_shared_kernel), in the fused CG tail, or inside the persistent CG kernel (cg_persist.cuh).
 //   * in both cases the contributions of one node are added one by one in ascending ORIGINAL element
 //     index, starting from the incoming value -- the exact order of the reference's sequential
 //     `f[index[k]] += ...` loop (TetrahedronFEMForceField.inl:928-929,1220-1235).  No atomics:
 //     results are bit-reproducible run to run and independent of the tiling.
-//   * slots are laid out as jagged diagonals: nodes of a tile (or of a 256-node chunk of shared nodes)
-//     are ranked by descending valence and contribution j of rank k lives at jds[j] + k, so that the
-//     per-node sequential sums are conflict-free in shared memory and coalesced in HBM.
+//   * shared-memory slots are laid out as jagged diagonals: the interior nodes of a tile are ranked by
+//     descending valence and contribution j of rank k lives at jds[j] + k (conflict-free sequential sums,
+//     no padding).  The HBM stage is an ELL block per chunk of kGatherChunk consecutive shared nodes:
+//     contribution j of the chunk's node k at sh_base[chunk] + j*kGatherChunk + k (coalesced, no table).
 #pragma once
 #include "common.cuh"
 
 namespace sb {
 
-constexpr int kGatherChunk = 128;      // shared nodes per CTA of the boundary kernel
+constexpr int kGatherChunk = 128;      // shared nodes per chunk (= per CTA of the boundary kernel, per thread group of the CG kernels)
 constexpr unsigned kStageFlag = 0x80000000u;
 
 // epilogue selection for the per-node gather
