@@ -110,9 +110,16 @@ template <class R> struct Node : sofab200_node {
     int n_fem_partials = 0;
     double mF = 0, bF = 0, kF = 0;
     // CUDA graph of one whole EulerImplicit step (about 110 kernels): replayed while (x, v, params) stay the same
-    struct StepGraph { cudaGraphExec_t exec = nullptr; R* x = nullptr; R* v = nullptr; sofab200_solver_params prm; uint64_t launches = 0; int seen = 0; } sg;
+    struct StepGraph { cudaGraphExec_t exec = nullptr; R* x = nullptr; R* v = nullptr; sofab200_solver_params prm; uint64_t launches = 0; int seen = 0; } sg, sg_rest;
+    cudaStream_t side_stream = nullptr;    // step_host: the v copy runs here while addForce (which only needs x) runs on the main stream
+    cudaEvent_t side_event = nullptr;
     bool use_graph = true;
-    ~Node() { if (sg.exec) cudaGraphExecDestroy(sg.exec); }
+    ~Node() {
+        if (sg.exec) cudaGraphExecDestroy(sg.exec);
+        if (sg_rest.exec) cudaGraphExecDestroy(sg_rest.exec);
+        if (side_event) cudaEventDestroy(side_event);
+        if (side_stream) cudaStreamDestroy(side_stream);
+    }
 
     // ---- multi-GPU state (sofab200_node_set_distributed) ------------------------------------------------
     struct Halo {
@@ -327,15 +334,17 @@ template <class R> struct Node : sofab200_node {
         return SOFAB200_OK;
     }
     // EulerImplicitSolver::solve, replayed from a captured CUDA graph once the same (x, v, params) have been seen twice
-    int step(R* x, R* v) {
-        if (!use_graph || ctx->profiling || ctx->trace.p) return step_direct(x, v);
+    // skip_force: the caller has already run compute_force(f, x) (step_host overlaps it with the copy of v)
+    int step(R* x, R* v, bool skip_force = false) {
+        if (!use_graph || ctx->profiling || ctx->trace.p) return step_direct(x, v, skip_force);
+        StepGraph& sg = skip_force ? this->sg_rest : this->sg;
         const bool same = sg.x == x && sg.v == v && std::memcmp(&sg.prm, &prm, sizeof(prm)) == 0;
         if (!same) {
             if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; }
             sg.x = x; sg.v = v; sg.prm = prm; sg.seen = 0;
         }
         if (!sg.exec) {
-            if (sg.seen++ == 0) return step_direct(x, v);   // first time: plain launches (also configures the kernels)
+            if (sg.seen++ == 0) return step_direct(x, v, skip_force);   // first time: plain launches (also configures the kernels)
             if (!ctx->capture_stream) SB_CUDA(cudaStreamCreateWithFlags(&ctx->capture_stream, cudaStreamNonBlocking));
             cudaStream_t user = ctx->stream;
             const uint64_t l0 = ctx->launches;
@@ -344,7 +353,7 @@ template <class R> struct Node : sofab200_node {
             int rc = SOFAB200_OK;
             cudaGraph_t graph = nullptr;
             if (e == cudaSuccess) {
-                rc = step_direct(x, v);
+                rc = step_direct(x, v, skip_force);
                 e = cudaStreamEndCapture(ctx->capture_stream, &graph);
             }
             ctx->stream = user;
@@ -360,10 +369,10 @@ template <class R> struct Node : sofab200_node {
         ctx->launches += sg.launches;
         return SOFAB200_OK;
     }
-    int step_direct(R* x, R* v) {
+    int step_direct(R* x, R* v, bool skip_force = false) {
         const double h = prm.dt, tr = prm.trapezoidal ? 0.5 : 1.0;
         const bool fo = prm.first_order != 0;
-        SB_TRY(compute_force(f.p, x));
+        if (!skip_force) SB_TRY(compute_force(f.p, x));
         if (!fo) {
             // b = (f + (-rM M + (h tr + rK) K) v) * h, projected          EulerImplicitSolver.cpp:147-162
             const R* finit = f.p;
@@ -556,6 +565,7 @@ template <class R> static int node_set_distributed(Node<R>* nd, sofab200_comm* c
     SB_CUDA(cudaStreamSynchronize(s));
     H.comm = comm;
     if (nd->sg.exec) { cudaGraphExecDestroy(nd->sg.exec); nd->sg.exec = nullptr; nd->sg.seen = 0; }
+    if (nd->sg_rest.exec) { cudaGraphExecDestroy(nd->sg_rest.exec); nd->sg_rest.exec = nullptr; nd->sg_rest.seen = 0; }
     return SOFAB200_OK;
 }
 // mailbox layout (bytes): 64 all-reduce slots [2][kMaxPeers][2 words] | 320 epoch u64 | 328 halo-call counter u64 | 1024 three inbox
@@ -566,7 +576,8 @@ template <class R> static size_t node_peer_bytes(const Node<R>* nd, size_t rows)
     return kMailboxInbox + 3 * inbox_buf_words<R>(std::max(rows, nd->halo.n_send)) * sizeof(unsigned long long) + 256;
 }
 template <class R> static int node_set_peer(Node<R>* nd, const sofab200_peer_desc* d) {
-    if (!d->peer_base) { nd->peer.ready = false; if (nd->sg.exec) { cudaGraphExecDestroy(nd->sg.exec); nd->sg.exec = nullptr; nd->sg.seen = 0; } return SOFAB200_OK; }
+    if (!d->peer_base) { nd->peer.ready = false; if (nd->sg.exec) { cudaGraphExecDestroy(nd->sg.exec); nd->sg.exec = nullptr; nd->sg.seen = 0; }
+    if (nd->sg_rest.exec) { cudaGraphExecDestroy(nd->sg_rest.exec); nd->sg_rest.exec = nullptr; nd->sg_rest.seen = 0; } return SOFAB200_OK; }
     SB_CHECK(nd->distributed(), "sofab200_node_set_distributed must come first");
     {
         PersistCG<R> probe; std::memset(&probe, 0, sizeof(probe));
@@ -623,6 +634,7 @@ template <class R> static int node_set_peer(Node<R>* nd, const sofab200_peer_des
     P.enabled = 1;
     nd->peer.ready = true;
     if (nd->sg.exec) { cudaGraphExecDestroy(nd->sg.exec); nd->sg.exec = nullptr; nd->sg.seen = 0; }
+    if (nd->sg_rest.exec) { cudaGraphExecDestroy(nd->sg_rest.exec); nd->sg_rest.exec = nullptr; nd->sg_rest.seen = 0; }
     return SOFAB200_OK;
 }
 }  // namespace sb
@@ -689,20 +701,32 @@ int sofab200_node_step(sofab200_node* node, void* x_dev, void* v_dev) {
     SB_CHECK(node && x_dev && v_dev, "null argument");
     return NODE_DISPATCH(node, NF(node)->step((float*)x_dev, (float*)v_dev), ND(node)->step((double*)x_dev, (double*)v_dev));
 }
-int sofab200_node_step_host(sofab200_node* node, void* x_host, void* v_host) {
-    SB_CHECK(node && x_host && v_host, "null argument");
-    const size_t bytes = 3 * node->n * (node->real == SOFAB200_F32 ? 4 : 8);
-    cudaStream_t s = node->ctx->stream;
-    void* dx; void* dv;
-    if (node->real == SOFAB200_F32) { auto* n = NF(node); if (!n->hx.p) { SB_TRY(n->hx.alloc(3 * n->n)); SB_TRY(n->hv.alloc(3 * n->n)); } dx = n->hx.p; dv = n->hv.p; }
-    else { auto* n = ND(node); if (!n->hx.p) { SB_TRY(n->hx.alloc(3 * n->n)); SB_TRY(n->hv.alloc(3 * n->n)); } dx = n->hx.p; dv = n->hv.p; }
-    SB_CUDA(cudaMemcpyAsync(dx, x_host, bytes, cudaMemcpyHostToDevice, s));
-    SB_CUDA(cudaMemcpyAsync(dv, v_host, bytes, cudaMemcpyHostToDevice, s));
-    SB_TRY(sofab200_node_step(node, dx, dv));
-    SB_CUDA(cudaMemcpyAsync(x_host, dx, bytes, cudaMemcpyDeviceToHost, s));
-    SB_CUDA(cudaMemcpyAsync(v_host, dv, bytes, cudaMemcpyDeviceToHost, s));
+}  // extern "C"
+namespace sb {
+template <class R> static int node_step_host(Node<R>* n, void* x_host, void* v_host) {
+    const size_t bytes = 3 * n->n * sizeof(R);
+    cudaStream_t s = n->ctx->stream;
+    if (!n->hx.p) { SB_TRY(n->hx.alloc(3 * n->n)); SB_TRY(n->hv.alloc(3 * n->n)); }
+    if (!n->side_stream) { SB_CUDA(cudaStreamCreateWithFlags(&n->side_stream, cudaStreamNonBlocking)); SB_CUDA(cudaEventCreateWithFlags(&n->side_event, cudaEventDisableTiming)); }
+    // x first on the main stream, v on the side stream: addForce needs only x and runs while v is still on the bus
+    SB_CUDA(cudaEventRecord(n->side_event, s));
+    SB_CUDA(cudaStreamWaitEvent(n->side_stream, n->side_event, 0));           // (the previous step's readers of hv are done)
+    SB_CUDA(cudaMemcpyAsync(n->hx.p, x_host, bytes, cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(n->hv.p, v_host, bytes, cudaMemcpyHostToDevice, n->side_stream));
+    SB_CUDA(cudaEventRecord(n->side_event, n->side_stream));
+    SB_TRY(n->compute_force(n->f.p, n->hx.p));
+    SB_CUDA(cudaStreamWaitEvent(s, n->side_event, 0));
+    SB_TRY(n->step(n->hx.p, n->hv.p, true));
+    SB_CUDA(cudaMemcpyAsync(x_host, n->hx.p, bytes, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaMemcpyAsync(v_host, n->hv.p, bytes, cudaMemcpyDeviceToHost, s));
     SB_CUDA(cudaStreamSynchronize(s));
     return SOFAB200_OK;
+}
+}  // namespace sb
+extern "C" {
+int sofab200_node_step_host(sofab200_node* node, void* x_host, void* v_host) {
+    SB_CHECK(node && x_host && v_host, "null argument");
+    return NODE_DISPATCH(node, sb::node_step_host<float>(NF(node), x_host, v_host), sb::node_step_host<double>(ND(node), x_host, v_host));
 }
 int sofab200_node_last_solve(sofab200_node* node, int* nb_iter, int* end_cond, double* graph_error, size_t* n_error, double* graph_den, size_t* n_den, size_t cap) {
     SB_CHECK(node != nullptr, "null argument");
