@@ -374,6 +374,8 @@ def run_ours_distributed(args, rank, world, local, dtype, template, s):
         return
     T_loc, N_loc = node.rm.elems.shape[0], node.rm.n_local
     info = node.be.node.last_solve()
+    if info["end_condition"] == 99:
+        raise RuntimeError("a cross-GPU wait timed out inside the CG kernel (end_condition 99): the numbers of this run are void")
     iters = min(info["iterations"], CG_ITERS) * args.steps     # every step of this workload runs the same forced iteration count
     peer = bool(getattr(node.be, "peer", False))
     exchange = ("ONE persistent CG kernel per GPU; interface partial sums stored into the neighbours' mailboxes over NVLink (CUDA IPC peer memory), "

@@ -227,10 +227,12 @@ int sofab200_node_set_vertex_mass(sofab200_node* node, const void* vertex_mass_h
 int sofab200_node_cg_solve(sofab200_node* node, void* x_dev, const void* b_dev, double m_factor, double b_factor, double k_factor, int* nb_iter_host);
 /* EulerImplicitSolver::solve [EI]:83-341 on device-resident x, v (async). */
 int sofab200_node_step(sofab200_node* node, void* x_dev, void* v_dev);
-/* The same step for HOST state vectors (pinned or pageable): H2D of x,v, step, D2H of x,v. (sync) */
+/* The same step for HOST state vectors (pinned or pageable): H2D of x,v, step, D2H of x,v; the upload of v overlaps addForce,
+ * which only needs x. (sync) */
 int sofab200_node_step_host(sofab200_node* node, void* x_host, void* v_host);
 /* Results of the last solve (sync): nb_iter ("CG iterations" as the reference reports it), end condition
- * (0 iterations exhausted, 1 tolerance, 2 threshold, 3 den==0, 4 b==0), and the `graph` Data
+ * (0 iterations exhausted, 1 tolerance, 2 threshold, 3 den==0, 4 b==0; 99 = multi-GPU only: a wait on another GPU timed out
+ * inside the CG kernel and the solve was abandoned), and the `graph` Data
  * (Error / Denominator histories, [CG]:109-116,148,213).  Any pointer may be NULL. */
 int sofab200_node_last_solve(sofab200_node* node, int* nb_iter, int* end_cond, double* graph_error, size_t* n_error, double* graph_den, size_t* n_den, size_t cap);
 /* Device vectors of the last step for parity checks (sync): "f" (force), "b" (right-hand side), "dx" (solution) */

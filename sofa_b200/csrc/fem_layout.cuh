@@ -34,7 +34,7 @@ constexpr int kMaxGraph = 1026;
 struct CGDev {
     int done;               // set once a break condition is met; later kernels of the solve become no-ops
     int nb_iter;            // "CG iterations" as the reference reports it
-    int end_cond;           // 0 iterations, 1 tolerance, 2 threshold, 3 den==0, 4 b==0
+    int end_cond;           // 0 iterations, 1 tolerance, 2 threshold, 3 den==0, 4 b==0, 99 a wait inside the persistent kernel timed out
     int it;                 // current iteration (1-based)
     unsigned time_step_count;
     unsigned max_iter;
