@@ -1,5 +1,7 @@
-"""Multi-GPU path on real devices (needs >= 2 GPUs; `gpurun --gpus 2`): NCCL halo exchange + allreduce, against the
-single-domain oracle."""
+"""Multi-GPU path on real devices (needs >= 2 GPUs; `gpurun --gpus 2`), against the single-domain oracle, in its three forms:
+"peer"  one persistent CG kernel per GPU exchanging over NVLink peer memory (sofab200_node_set_peer),
+"nccl"  the library's multi-kernel loop with NCCL send/recv + allreduce (sofab200_node_set_distributed only),
+"torch" the host-driven loop of sofa_b200/parallel.py over torch.distributed (what tests/test_parallel_cpu.py runs on gloo)."""
 import os
 import socket
 
@@ -17,11 +19,13 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, cfg_name, dtype_name, native, q_out):
+def _worker(rank, world, port, cfg_name, dtype_name, mode, q_out):
     import torch.distributed as dist
     import sofa_b200 as sb
     import sofa_b200.parallel as PAR
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    os.environ["SOFAB200_PEER"] = "1" if mode == "peer" else "0"
+    native = mode != "torch"
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -42,14 +46,14 @@ def _worker(rank, world, port, cfg_name, dtype_name, native, q_out):
             its = [node.be.node.last_solve()["iterations"]] * 3
         x_glob = node.gather_global(node.be.x, pos.shape[0])
         if rank == 0:
-            q_out.put(dict(q=q_glob, x=x_glob, its=its))
+            q_out.put(dict(q=q_glob, x=x_glob, its=its, peer=bool(getattr(node.be, "peer", False))))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("native", [True, False])
+@pytest.mark.parametrize("mode", ["peer", "nccl", "torch"])
 @pytest.mark.parametrize("dtype_name", ["f64", "f32"])
-def test_two_gpus_match_single_domain_oracle(dtype_name, native):
+def test_two_gpus_match_single_domain_oracle(dtype_name, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -57,13 +61,14 @@ def test_two_gpus_match_single_domain_oracle(dtype_name, native):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, cfg, dtype_name, native, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cfg, dtype_name, mode, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = q.get(timeout=600)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
+    assert res["peer"] == (mode == "peer")     # the mode under test is the one that ran
     dtype = np.float32 if dtype_name == "f32" else np.float64
     c, pos, hexas, tets, fixed = mesh(cfg)
     s = O.OracleScene(dtype, pos)
