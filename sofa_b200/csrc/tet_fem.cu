@@ -74,7 +74,7 @@ template <class R, int MODE, int MAXT, bool PF> static int tet_launch_variant(Te
     }
     const int cls = (MODE == TM_DF_COROT || MODE == TM_DF_SMALL) ? 0 : 2;
     ff.ctx->prof_start(cls);
-    kern<<<ff.h.plan.n_tiles, ((MODE == TM_DF_COROT || (MODE == TM_F_LARGE && MAXT > 256)) && sizeof(R) == 4) ? ff.threads : 256, smem_total, ff.ctx->stream>>>(d, in, ep, ff.h.plan.max_touched, ff.h.plan.max_slots);
+    kern<<<ff.h.plan.n_tiles, ((MODE == TM_DF_COROT || (MODE == TM_F_LARGE && MAXT > 256)) && sizeof(R) == 4) ? std::min(ff.threads, MAXT) : 256, smem_total, ff.ctx->stream>>>(d, in, ep, ff.h.plan.max_touched, ff.h.plan.max_slots);
     ff.ctx->prof_stop(cls);
     ff.ctx->launches++;
     SB_CUDA(cudaGetLastError());
