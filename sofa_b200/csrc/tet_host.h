@@ -162,7 +162,9 @@ template <class R> static std::string tet_host_build(HostTet<R>& ff, size_t n_no
         const std::string err = build_plan(ff.plan, int(n_nodes), int(n_tets), 4, tets, pos.data(), tile_e, chunk, kStageFlag, smem_limit, sizeof(SV), 3 * sizeof(R), desc->shared_nodes);
         ff.smem_bytes = tile_smem_bytes<R>(ff.plan.max_touched, ff.plan.max_slots);
         const bool too_big = ff.smem_bytes > smem_limit || err.find("use a smaller tile") != std::string::npos;
-        const bool too_staged = err.empty() && ff.plan.n_staged_corners * 2 > 4 * n_tets && ff.plan.n_demoted > 0;
+        // demotion is meant to shave a tile that is a little too large, not to push a third of the mesh through the staging path:
+        // when more than 2 % of the nodes had to be demoted, smaller tiles (one more wave) are the better layout
+        const bool too_staged = err.empty() && ff.plan.n_demoted * 50 > n_nodes;
         if ((too_big || too_staged) && !fixed_tile && tile_e > 32) { tile_e = tile_for(++k_waves); continue; }
         if (!err.empty()) return err;
         if (too_big) return "tile does not fit in shared memory; use a smaller tile_elems";
