@@ -133,8 +133,16 @@ def test_node_compute_force_and_apply_bit_exact(dtype, method):
         assert q_d.cpu().numpy().tobytes() == s.apply(p, m, b, k).tobytes(), (m, b, k)
 
 
+# the three device implementations of CGLinearSolver::solve (node.cu: Node::cg_solve): ONE persistent cooperative kernel; element
+# pass + cooperative tail kernel per iteration; four plain kernels per iteration (the latter two serve meshes the first cannot hold)
+CG_PATHS = {"persistent": {}, "fused_tail": {"SOFAB200_CG_PERSISTENT": "0"}, "multi_kernel": {"SOFAB200_CG_PERSISTENT": "0", "SOFAB200_FUSED_TAIL": "0"}}
+
+
+@pytest.mark.parametrize("path", list(CG_PATHS))
 @pytest.mark.parametrize("dtype", DTYPES)
-def test_cg_solve_matches_oracle(dtype):
+def test_cg_solve_matches_oracle(dtype, path, monkeypatch):
+    for k, v in CG_PATHS[path].items():
+        monkeypatch.setenv(k, v)          # read when the solver node is created
     g = gpu_scene("C1", dtype)
     s = oracle_scene("C1", dtype)
     mo, node = g["mo"], g["node"]
