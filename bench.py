@@ -31,6 +31,7 @@ CG_ITERS = 25
 WORKLOADS = {
     "C2": dict(n=(33, 33, 161), mn=(0, 0, 0), mx=(4, 4, 20), box=(-1, -1, -1, 5, 5, 1e-6)),
     "C5": dict(n=(129, 129, 161), mn=(0, 0, 0), mx=(16, 16, 20), box=(-1, -1, -1, 17, 17, 1e-6)),
+    "C1": dict(n=(5, 5, 20), mn=(-5, -5, 0), mx=(5, 5, 40), box=(-6, -6, -1, 50, 6, 0.1)),     # the reference's example scene (1824 tets): pure latency
     "SMALL": dict(n=(17, 17, 41), mn=(0, 0, 0), mx=(4, 4, 10), box=(-1, -1, -1, 5, 5, 1e-6)),
     "L2FIT": dict(n=(33, 33, 41), mn=(0, 0, 0), mx=(4, 4, 5), box=(-1, -1, -1, 5, 5, 1e-6)),   # 245 760 tets: the element records fit in L2
 }
