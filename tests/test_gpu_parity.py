@@ -207,6 +207,38 @@ def test_euler_implicit_step_parity_from_same_state(dtype, method):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("opts", [dict(warmStart=1), dict(trapezoidalScheme=1), dict(firstOrder=1), dict(vdamping=0.7), dict(warmStart=1, trapezoidalScheme=1, vdamping=0.3)],
+                         ids=["warmStart", "trapezoidal", "firstOrder", "vdamping", "combined"])
+def test_solver_options_step_parity_from_same_state(dtype, opts):
+    """The Data of EulerImplicitSolver (trapezoidalScheme, firstOrder, vdamping: EulerImplicitSolver.cpp:117-123,169-171,285-300) and of
+    CGLinearSolver (warmStart: CGLinearSolver.inl:118-128): f and b bit-identical, iteration count +-1, and the CG solution within
+    10x the reference's OWN sensitivity to the summation order of its dot products on that system (a second oracle, same state, dots
+    summed in double in reverse order, is the yardstick; the first-order system is the most sensitive one)."""
+    g = gpu_scene("C1", dtype, "large")
+    s = oracle_scene("C1", dtype, "large")
+    s2 = oracle_scene("C1", dtype, "large"); s2.set_dot_double(True, reverse=True)
+    node = g["node"]
+    node.set_params(**opts)
+    o = dict(opts)
+    if "trapezoidalScheme" in o:
+        o["trapezoidal"] = o.pop("trapezoidalScheme")
+    s.set_params(**o); s2.set_params(**o)
+    for step in range(6):
+        _sync_state(g, s)
+        s2.set_x(s.get("x")); s2.set_v(s.get("v"))
+        node.step()
+        it = node.last_solve()["iterations"]
+        it_ref = s.step(); s2.step()
+        assert node.get("f").tobytes() == s.get("f").tobytes(), step
+        assert node.get("b").tobytes() == s.get("b").tobytes(), step
+        assert abs(it - it_ref) <= 1, (step, it, it_ref)
+        yard = rel_err(s2.get("sol"), s.get("sol"))
+        assert rel_err(node.get("dx"), s.get("sol")) <= max(10 * yard, 1e-8 if dtype == np.float64 else 2e-4), (step, yard)
+        xyard = np.abs(s2.get("x") - s.get("x")).max()
+        assert np.abs(g["mo"].x.cpu().numpy().astype(np.float64) - s.get("x")).max() <= max(10 * xyard, 1e-11 if dtype == np.float64 else 1e-5)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_free_running_trajectory_stays_within_the_references_own_sensitivity(dtype):
     """Free-running 10 steps.  A 25-iteration truncated CG on a stiff system amplifies last-bit differences of the dot
     products from step to step, in the reference itself: the oracle run with its dots summed in reverse order drifts
