@@ -69,6 +69,31 @@ def test_add_force_add_dforce_bit_exact(dtype, method):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+def test_per_element_material_data_bit_exact(dtype):
+    """youngModulus / poissonRatio given per element (getYoungModulusInElement, BaseLinearElasticityFEMForceField.inl:125-139) and
+    localStiffnessFactor (TetrahedronFEMForceField.inl:261): the material values are computed on the host in the reference's arithmetic."""
+    import sofa_b200 as sb
+    from gpu_common import mesh
+    c, pos, hexas, tets, fixed = mesh("C1")
+    rng = np.random.default_rng(11)
+    young = rng.uniform(500.0, 5000.0, tets.shape[0]); poisson = rng.uniform(0.1, 0.45, tets.shape[0])
+    lsf = np.array([0.5, 1.0, 2.0, 1.5])
+    x = (pos + 0.05 * rng.standard_normal(pos.shape)).astype(dtype)
+    dx = (1e-3 * rng.standard_normal(pos.shape)).astype(dtype)
+    for kw_dev, kw_ref in ((dict(youngModulus=young, poissonRatio=poisson), dict(young=young, poisson=poisson)),
+                           (dict(youngModulus=1000.0, poissonRatio=0.4, localStiffnessFactor=lsf), dict(young=1000.0, poisson=0.4, local_stiffness_factor=lsf))):
+        ctx = sb.Context(0)
+        mo = sb.MechanicalObject(ctx, "B200Vec3f" if dtype == np.float32 else "B200Vec3d", position=pos)
+        ff = sb.TetrahedronFEMForceField(mo, tets, method="polar", **kw_dev)
+        s = O.OracleScene(dtype, pos); s.set_tets(tets, "polar", **kw_ref)
+        f0 = rng.standard_normal(pos.shape).astype(dtype)
+        f_d = dev(mo, f0); ff.addForce(f_d, dev(mo, x))
+        assert f_d.cpu().numpy().tobytes() == s.fem_add_force(f0, x).tobytes()
+        df_d = dev(mo, f0); ff.addDForce(df_d, dev(mo, dx), -0.37)
+        assert df_d.cpu().numpy().tobytes() == s.fem_add_dforce(f0, dx, -0.37).tobytes()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_svd_inverted_elements(dtype):
     g = gpu_scene("C1", dtype, "svd")
     s = oracle_scene("C1", dtype, "svd")
