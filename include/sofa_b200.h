@@ -113,6 +113,10 @@ int sofab200_mass_add_mdx(sofab200_ctx* ctx, sofab200_real real, size_t n, void*
 int sofab200_mass_add_force(sofab200_ctx* ctx, sofab200_real real, size_t n, void* f_dev, const void* vertex_mass_dev, const double gravity[3]);
 /* DiagonalMass::accFromF [DM]:563-575: a[i] = f[i]/m[i]. */
 int sofab200_mass_acc_from_f(sofab200_ctx* ctx, sofab200_real real, size_t n, void* a_dev, const void* f_dev, const void* vertex_mass_dev);
+/* UniformMass<DataTypes>::addMDx (Mass/.../UniformMass.inl:403-420): m = vertexMass (*= Real(factor) if factor != 1); res[i] += dx[i]*m
+ * and ::addForce (:469-496): mg = gravity*m once; f[i] += mg. */
+int sofab200_uniform_mass_add_mdx(sofab200_ctx* ctx, sofab200_real real, size_t n, void* res_dev, const void* dx_dev, double vertex_mass, double factor);
+int sofab200_uniform_mass_add_force(sofab200_ctx* ctx, sofab200_real real, size_t n, void* f_dev, double vertex_mass, const double gravity[3]);
 /* FixedProjectiveConstraint::projectResponse / projectVelocity [FPC]:183-206,236-258. */
 int sofab200_fixed_project_response(sofab200_ctx* ctx, sofab200_real real, size_t n, void* res_dev, size_t n_indices, const uint32_t* indices_dev, int fix_all);
 
@@ -187,6 +191,8 @@ typedef struct sofab200_node_desc {
     const uint32_t* fixed_host;
     int fix_all;                    /* Data `fixAll`                                                      */
     int mass_first;                 /* 1: the mass precedes the force field in the scene (all reference scenes) */
+    int uniform_mass;               /* 1: the mass is a UniformMass (Mass/.../UniformMass.inl:403-496) with the MassType below;  */
+    double uniform_vertex_mass;     /*    vertex_mass_host is then ignored                                       */
 } sofab200_node_desc;
 
 typedef struct sofab200_solver_params {

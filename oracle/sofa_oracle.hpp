@@ -926,6 +926,16 @@ template <class R> struct DiagonalMass {
     std::vector<R> vertexMass;  // d_vertexMass
     R massDensity = 1;
     R totalMass = 0;
+    // UniformMass (Sofa/Component/Mass/src/sofa/component/mass/UniformMass.inl): one MassType for every node.  Kept in the same
+    // struct because the solver node holds exactly one mass component.
+    bool uniform = false;
+    R uniformVertexMass = 0;    // d_vertexMass of UniformMass
+    void initUniformFromVertexMass(R m, size_t n) { uniform = true; uniformVertexMass = m; vertexMass.assign(n, m); totalMass = R(double(m) * double(n)); }   // :300-309
+    void initUniformFromTotalMass(double tm, size_t n) {   // :329-345: *m = d_totalMass.getValue() / Real(size)
+        uniform = true; totalMass = R(tm);
+        uniformVertexMass = n > 0 ? R(tm / R(n)) : R(0);
+        vertexMass.assign(n, uniformVertexMass);
+    }
     // computeVertexMass :1000-1100 (tetrahedra branch :1061-1079, hexahedra branch :1080-1100)
     R computeVertexMassTets(R density, const std::vector<Vec3<R>>& pos, const std::vector<uint32_t>& tets) {
         vertexMass.assign(pos.size(), R(0));
@@ -975,12 +985,23 @@ template <class R> struct DiagonalMass {
         size_t n = vertexMass.size();
         if (dx.size() < n) n = dx.size();
         if (res.size() < n) n = res.size();
+        if (uniform) {   // UniformMass::addMDx, UniformMass.inl:403-420
+            R m = uniformVertexMass;
+            if (factor != 1.0) m *= R(factor);
+            for (size_t i = 0; i < n; ++i) res[i] += dx[i] * m;
+            return;
+        }
         if (factor == 1.0) for (size_t i = 0; i < n; ++i) res[i] += dx[i] * vertexMass[i];
         else for (size_t i = 0; i < n; ++i) res[i] += (dx[i] * vertexMass[i]) * R(factor);
     }
     // addForce :1392-1413 (gravity as Vec3d narrowed to Deriv)
     void addForce(VecDeriv<R>& f, const double g[3]) const {
         const Vec3<R> theGravity((R)g[0], (R)g[1], (R)g[2]);
+        if (uniform) {   // UniformMass::addForce, UniformMass.inl:469-496: mg = theGravity * m once, then f[i] += mg
+            const Vec3<R> mg = theGravity * uniformVertexMass;
+            for (size_t i = 0; i < vertexMass.size(); ++i) f[i] += mg;
+            return;
+        }
         for (size_t i = 0; i < vertexMass.size(); ++i) f[i] += theGravity * vertexMass[i];
     }
 };

@@ -124,11 +124,15 @@ void orc_scene_set_hexas(void* h, size_t H, const uint32_t* hexas, int method, i
         sc.hex.reinit(sc.x0);
     });
 }
-// DiagonalMass: kind 0 = massDensity, 1 = totalMass, lumped over `elems` (elemSize 4 or 8); kind 2 = explicit vertexMass array
+// DiagonalMass: kind 0 = massDensity, 1 = totalMass, lumped over `elems` (elemSize 4 or 8); kind 2 = explicit vertexMass array;
+// UniformMass: kind 3 = vertexMass, kind 4 = totalMass
 void orc_scene_set_mass(void* h, int kind, double value, size_t nelems, const uint32_t* elems, int elemSize, const void* vertexMass) {
     DISPATCH(h, {
         sc.hasMass = true;
-        if (kind == 2) { sc.mass.vertexMass.resize(sc.x.size()); std::memcpy(sc.mass.vertexMass.data(), vertexMass, sc.x.size() * sizeof(R)); }
+        sc.mass.uniform = false;
+        if (kind == 3) sc.mass.initUniformFromVertexMass(R(value), sc.x.size());
+        else if (kind == 4) sc.mass.initUniformFromTotalMass(value, sc.x.size());
+        else if (kind == 2) { sc.mass.vertexMass.resize(sc.x.size()); std::memcpy(sc.mass.vertexMass.data(), vertexMass, sc.x.size() * sizeof(R)); }
         else {
             std::vector<uint32_t> e(elems, elems + nelems * elemSize);
             if (kind == 0) sc.mass.initFromMassDensity(R(value), sc.x0, e, elemSize);

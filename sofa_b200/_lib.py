@@ -31,7 +31,7 @@ class HexFemDesc(C.Structure):
 
 class NodeDesc(C.Structure):
     _fields_ = [("tetfem", _P), ("hexfem", _P), ("vertex_mass_host", _P), ("n_fixed", C.c_size_t), ("fixed_host", C.POINTER(C.c_uint32)),
-                ("fix_all", C.c_int), ("mass_first", C.c_int)]
+                ("fix_all", C.c_int), ("mass_first", C.c_int), ("uniform_mass", C.c_int), ("uniform_vertex_mass", C.c_double)]
 
 
 class HaloDesc(C.Structure):
@@ -70,6 +70,8 @@ SYMBOLS = {
     "sofab200_mo_vdot_dev": (_I, [_P, _I, _SZ, _P, _P, _P, _P]),
     "sofab200_mo_vmultiop_integrate": (_I, [_P, _I, _SZ, _P, _P, _P, _D, _D]),
     "sofab200_mass_add_mdx": (_I, [_P, _I, _SZ, _P, _P, _P, _D]),
+    "sofab200_uniform_mass_add_mdx": (_I, [_P, _I, _SZ, _P, _P, _D, _D]),
+    "sofab200_uniform_mass_add_force": (_I, [_P, _I, _SZ, _P, _D, C.POINTER(_D)]),
     "sofab200_mass_add_force": (_I, [_P, _I, _SZ, _P, _P, C.POINTER(_D)]),
     "sofab200_mass_acc_from_f": (_I, [_P, _I, _SZ, _P, _P, _P]),
     "sofab200_fixed_project_response": (_I, [_P, _I, _SZ, _P, _SZ, _P, _I]),

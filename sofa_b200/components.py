@@ -281,6 +281,27 @@ class DiagonalMass:
         check(self.ctx.L.sofab200_mass_acc_from_f(self.ctx.h, self.mstate.real, self.mstate.size, _dptr(a), _dptr(f), _dptr(self.vertexMass)))
 
 
+class UniformMass:
+    """UniformMass<B200Vec3Types>: Data vertexMass | totalMass (+ rayleighMass of Mass); Mass/.../UniformMass.inl:300-345,403-496."""
+
+    def __init__(self, mstate, vertexMass=None, totalMass=None, rayleighMass=0.0):
+        self.mstate, self.ctx = mstate, mstate.ctx
+        self.rayleighMass = float(rayleighMass)
+        real = np.dtype(mstate.ndtype).type
+        if totalMass is not None:      # initFromTotalMass: *m = d_totalMass.getValue() / Real(size), stored as MassType = Real
+            self.vertexMass_value = float(real(float(totalMass) / float(real(mstate.size))))
+        else:
+            self.vertexMass_value = float(real(1.0 if vertexMass is None else vertexMass))
+        self.vertexMass_host = np.full(mstate.size, self.vertexMass_value, mstate.ndtype)
+
+    def addMDx(self, res, dx, factor=1.0):
+        check(self.ctx.L.sofab200_uniform_mass_add_mdx(self.ctx.h, self.mstate.real, self.mstate.size, _dptr(res), _dptr(dx), self.vertexMass_value, float(factor)))
+
+    def addForce(self, f, gravity):
+        g = (C.c_double * 3)(*[float(v) for v in gravity])
+        check(self.ctx.L.sofab200_uniform_mass_add_force(self.ctx.h, self.mstate.real, self.mstate.size, _dptr(f), self.vertexMass_value, g))
+
+
 class FixedProjectiveConstraint:
     """FixedProjectiveConstraint<B200Vec3Types>: Data indices, fixAll."""
 
@@ -310,7 +331,9 @@ class SolverNode:
             d.tetfem = forcefield.h
         else:
             d.hexfem = forcefield.h
-        if mass is not None:
+        if isinstance(mass, UniformMass):
+            d.uniform_mass, d.uniform_vertex_mass = 1, mass.vertexMass_value
+        elif mass is not None:
             d.vertex_mass_host = mass.vertexMass_host.ctypes.data_as(_P)
         if constraint is not None:
             d.n_fixed = len(constraint.indices_host)

@@ -54,6 +54,8 @@ template <class R> struct NodeEpilogue {
     const R* mdx_src;       // dx of addMDx (== the kernel's input vector p / v)
     R mass_factor;          // addMDx factor (narrowed to Real as the reference does)
     int mass_factor_is_one; // reference takes `res += dx*m` when factor == 1.0
+    int mass_uniform;       // UniformMass: res += dx * um_f with um_f = vertexMass (* Real(factor) if factor != 1), UniformMass.inl:414-419
+    R um_f;
     R gx, gy, gz;           // gravity (narrowed)
     int has_scale;          // b.teq(h)
     R scale;
@@ -206,8 +208,9 @@ template <class R> HD void node_pre(const NodeEpilogue<R>& ep, uint32_t g, R& ax
 template <class R> HD void node_mass_m(const NodeEpilogue<R>& ep, int kind, R m, R vx, R vy, R vz, R& ax, R& ay, R& az) {
     if (kind == PRE_GRAVITY) {  // DiagonalMass::addForce: f[i] += theGravity*masses[i]
         ax += ep.gx * m; ay += ep.gy * m; az += ep.gz * m;
-    } else if (kind == PRE_MDX) {  // DiagonalMass::addMDx
-        if (ep.mass_factor_is_one) { ax += vx * m; ay += vy * m; az += vz * m; }
+    } else if (kind == PRE_MDX) {  // DiagonalMass::addMDx / UniformMass::addMDx
+        if (ep.mass_uniform) { ax += vx * ep.um_f; ay += vy * ep.um_f; az += vz * ep.um_f; }
+        else if (ep.mass_factor_is_one) { ax += vx * m; ay += vy * m; az += vz * m; }
         else { ax += (vx * m) * ep.mass_factor; ay += (vy * m) * ep.mass_factor; az += (vz * m) * ep.mass_factor; }
     }
 }

@@ -99,6 +99,7 @@ template <class R> struct Node : sofab200_node {
     sofab200_tetfem* tet = nullptr;
     sofab200_hexfem* hex = nullptr;
     bool has_mass = false, mass_first = true;
+    bool uniform_mass = false; double um = 0.0;   // UniformMass: every entry of `mass` holds Real(um)
     DevBuf<R> mass;
     DevBuf<unsigned char> fixed;
     bool has_fixed = false;
@@ -235,6 +236,8 @@ template <class R> struct Node : sofab200_node {
         if (kind == PRE_MDX && factor == 0.0) return;  // Mass::addMBKdx skips a null factor (Mass.inl:96-99)
         if (mass_first) ep.pre_kind = kind; else ep.post_kind = kind;
         ep.mdx_src = src; ep.mass_factor = R(factor); ep.mass_factor_is_one = (factor == 1.0);
+        ep.mass_uniform = uniform_mass ? 1 : 0;
+        if (uniform_mass) { R m = R(um); if (factor != 1.0) m *= R(factor); ep.um_f = m; }
         ep.gx = R(prm.gravity[0]); ep.gy = R(prm.gravity[1]); ep.gz = R(prm.gravity[2]);
     }
     // mop.computeForce
@@ -414,7 +417,12 @@ template <class R> static int node_create(sofab200_ctx* ctx, size_t n, const sof
     std::memset(&nd->prm, 0, sizeof(nd->prm));
     nd->prm.gravity[1] = -9.81; nd->prm.dt = 0.01; nd->prm.iterations = 25; nd->prm.tolerance = 1e-5; nd->prm.threshold = 1e-5;
     cudaStream_t s = ctx->stream;
-    if (d->vertex_mass_host) {
+    if (d->uniform_mass) {
+        nd->has_mass = true; nd->uniform_mass = true; nd->um = d->uniform_vertex_mass;
+        std::vector<R> um(n, R(d->uniform_vertex_mass));
+        SB_TRY(nd->mass.upload(um, s));
+        SB_CUDA(cudaStreamSynchronize(s));
+    } else if (d->vertex_mass_host) {
         nd->has_mass = true;
         SB_TRY(nd->mass.alloc(n));
         SB_CUDA(cudaMemcpyAsync(nd->mass.p, d->vertex_mass_host, n * sizeof(R), cudaMemcpyHostToDevice, s));
@@ -476,6 +484,25 @@ int sofab200_mass_add_mdx(sofab200_ctx* ctx, sofab200_real real, size_t n, void*
     const int g = vec_grid(3 * n, ctx->sm_count);
     if (real == SOFAB200_F32) LAUNCH(ctx, (mass_mdx_kernel<float>), g, kVecBlock, n, (float*)res_dev, (const float*)dx_dev, (const float*)m_dev, float(factor), int(factor == 1.0));
     else LAUNCH(ctx, (mass_mdx_kernel<double>), g, kVecBlock, n, (double*)res_dev, (const double*)dx_dev, (const double*)m_dev, factor, int(factor == 1.0));
+    return SOFAB200_OK;
+}
+int sofab200_uniform_mass_add_mdx(sofab200_ctx* ctx, sofab200_real real, size_t n, void* res_dev, const void* dx_dev, double vertex_mass, double factor) {
+    SB_CHECK(ctx && res_dev && dx_dev, "null argument");
+    if (n == 0) return SOFAB200_OK;
+    const int g = vec_grid(3 * n, ctx->sm_count);
+    // res[i] += dx[i] * m, m = vertexMass (*= Real(factor) if factor != 1): the vOp_v_inc_bf kernel computes exactly r[i] += b[i]*k
+    if (real == SOFAB200_F32) { float m = float(vertex_mass); if (factor != 1.0) m *= float(factor); LAUNCH(ctx, (vop_kernel<float, VOP_PEQ_BF>), g, kVecBlock, 3 * n, (float*)res_dev, (const float*)nullptr, (const float*)dx_dev, m); }
+    else { double m = vertex_mass; if (factor != 1.0) m *= factor; LAUNCH(ctx, (vop_kernel<double, VOP_PEQ_BF>), g, kVecBlock, 3 * n, (double*)res_dev, (const double*)nullptr, (const double*)dx_dev, m); }
+    return SOFAB200_OK;
+}
+int sofab200_uniform_mass_add_force(sofab200_ctx* ctx, sofab200_real real, size_t n, void* f_dev, double vertex_mass, const double gravity[3]) {
+    SB_CHECK(ctx && f_dev && gravity, "null argument");
+    if (n == 0) return SOFAB200_OK;
+    const int g = vec_grid(3 * n, ctx->sm_count);
+    if (real == SOFAB200_F32) {
+        const float m = float(vertex_mass);
+        LAUNCH(ctx, (add_const3_kernel<float>), g, kVecBlock, n, (float*)f_dev, float(gravity[0]) * m, float(gravity[1]) * m, float(gravity[2]) * m);
+    } else LAUNCH(ctx, (add_const3_kernel<double>), g, kVecBlock, n, (double*)f_dev, gravity[0] * vertex_mass, gravity[1] * vertex_mass, gravity[2] * vertex_mass);
     return SOFAB200_OK;
 }
 int sofab200_mass_add_force(sofab200_ctx* ctx, sofab200_real real, size_t n, void* f_dev, const void* m_dev, const double gravity[3]) {

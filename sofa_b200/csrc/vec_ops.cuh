@@ -108,6 +108,13 @@ template <class R> __global__ void __launch_bounds__(kVecBlock) mass_gravity_ker
         f[i] += g * m[i / 3];
     }
 }
+// f[i] += (cx, cy, cz)   (UniformMass::addForce: the weight of a node is the same vector for every node)
+template <class R> __global__ void __launch_bounds__(kVecBlock) add_const3_kernel(size_t n, R* __restrict__ f, R cx, R cy, R cz) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < 3 * n; i += size_t(gridDim.x) * blockDim.x) {
+        const int c = int(i % 3);
+        f[i] += c == 0 ? cx : (c == 1 ? cy : cz);
+    }
+}
 template <class R> __global__ void __launch_bounds__(kVecBlock) mass_acc_kernel(size_t n, R* __restrict__ a, const R* __restrict__ f, const R* __restrict__ m) {
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < 3 * n; i += size_t(gridDim.x) * blockDim.x) a[i] = f[i] / m[i / 3];
 }

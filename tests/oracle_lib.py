@@ -156,6 +156,11 @@ class OracleScene:
         e = np.ascontiguousarray(elems, np.uint32)
         self.L.orc_scene_set_mass(self.h, 1, C.c_double(total), C.c_size_t(e.shape[0]), _ptr(e), e.shape[1], None)
 
+    def set_uniform_mass(self, vertexMass=None, totalMass=None):
+        """UniformMass (Data vertexMass | totalMass) instead of DiagonalMass."""
+        kind, val = (3, vertexMass) if vertexMass is not None else (4, totalMass)
+        self.L.orc_scene_set_mass(self.h, kind, C.c_double(val), C.c_size_t(0), None, 4, None)
+
     def set_vertex_mass(self, m):
         m = np.ascontiguousarray(m, self.dtype)
         self.L.orc_scene_set_mass(self.h, 2, C.c_double(0), C.c_size_t(0), None, 4, _ptr(m))

@@ -69,6 +69,55 @@ def test_add_force_add_dforce_bit_exact(dtype, method):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("how", ["vertexMass", "totalMass"])
+def test_uniform_mass_parity(dtype, how):
+    """UniformMass instead of DiagonalMass ("UniformMass equivalents"): its addMDx multiplies the MassType by the
+    factor first (UniformMass.inl:414-419), its addForce adds one precomputed weight vector (:484-496).  Per-op entry points and the
+    fused solver node: f, b and A*p bit-identical, steps as in the DiagonalMass test."""
+    import sofa_b200 as sb
+    from gpu_common import mesh
+    c, pos, hexas, tets, fixed = mesh("C1")
+    kw = dict(vertexMass=0.37) if how == "vertexMass" else dict(totalMass=123.4)
+    ctx = sb.Context(0)
+    mo = sb.MechanicalObject(ctx, "B200Vec3f" if dtype == np.float32 else "B200Vec3d", position=pos)
+    ff = sb.TetrahedronFEMForceField(mo, tets, youngModulus=c["young"], poissonRatio=c["poisson"], method="large")
+    mass = sb.UniformMass(mo, **kw)
+    node = sb.SolverNode(mo, ff, mass, sb.FixedProjectiveConstraint(mo, fixed), dt=c["dt"], gravity=c["gravity"], rayleighStiffness=c["rK"], rayleighMass=c["rM"],
+                         iterations=c["iterations"], tolerance=c["tolerance"], threshold=c["threshold"])
+    s = O.OracleScene(dtype, pos)
+    s.set_params(gravity=c["gravity"], dt=c["dt"], rayleighStiffness=c["rK"], rayleighMass=c["rM"], iterations=c["iterations"], tolerance=c["tolerance"], threshold=c["threshold"])
+    s.set_uniform_mass(**kw); s.set_tets(tets, "large", c["young"], c["poisson"]); s.set_fixed(fixed)
+    assert mass.vertexMass_host.tobytes() == s.get("vertexMass").tobytes()
+    rng = np.random.default_rng(3)
+    # per-op entry points against the fused operator with the stiffness switched off: A = m M
+    p = rng.standard_normal(pos.shape).astype(dtype)
+    for fac in (1.0, 1.001, -0.3):
+        r0 = rng.standard_normal(pos.shape).astype(dtype)
+        r_d = dev(mo, r0); mass.addMDx(r_d, dev(mo, p), fac)
+        m = np.asarray(mass.vertexMass_value, dtype)
+        if fac != 1.0:
+            m = m * dtype(fac)
+        assert r_d.cpu().numpy().tobytes() == (r0 + p * m).astype(dtype).tobytes()
+    g = g0 = rng.standard_normal(pos.shape).astype(dtype)
+    g_d = dev(mo, g0); mass.addForce(g_d, c["gravity"])
+    mg = np.array([dtype(v) * dtype(mass.vertexMass_value) for v in c["gravity"]], dtype)
+    assert g_d.cpu().numpy().tobytes() == (g0 + mg).astype(dtype).tobytes()
+    for (mf, bf, kf) in ((1.001, -0.01, -0.0011), (1.0, 0.0, -0.01)):
+        q_d = mo.new_vector(); node.apply(q_d, dev(mo, p), mf, bf, kf)
+        assert q_d.cpu().numpy().tobytes() == s.apply(p, mf, bf, kf).tobytes(), (mf, bf, kf)
+    for step in range(4):
+        import torch
+        mo.x.copy_(torch.from_numpy(s.get("x"))); mo.v.copy_(torch.from_numpy(s.get("v")))
+        node.step()
+        it = node.last_solve()["iterations"]
+        it_ref = s.step()
+        assert node.get("f").tobytes() == s.get("f").tobytes(), step
+        assert node.get("b").tobytes() == s.get("b").tobytes(), step
+        assert abs(it - it_ref) <= 1
+        assert rel_err(node.get("dx"), s.get("sol")) <= (1e-8 if dtype == np.float64 else 2e-4), step
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_per_element_material_data_bit_exact(dtype):
     """youngModulus / poissonRatio given per element (getYoungModulusInElement, BaseLinearElasticityFEMForceField.inl:125-139) and
     localStiffnessFactor (TetrahedronFEMForceField.inl:261): the material values are computed on the host in the reference's arithmetic."""
