@@ -88,6 +88,16 @@ int sofab200_ctx_profile_end(sofab200_ctx* ctx, double* total_ms, uint64_t* coun
 int sofab200_ctx_trace_begin(sofab200_ctx* ctx);
 int sofab200_ctx_trace_end(sofab200_ctx* ctx, uint64_t* out, size_t n);
 
+/* PlaneForceField<B200Vec3Types> (MechanicalLoad/.../PlaneForceField.inl; in every SofaCUDA FEM benchmark scene), per-operation
+ * level: addForce :158-205 (penalty + damping below the plane, optional maxForce clamp, records the contacts), addDForce
+ * :208-226 (df[p] += n * (fact * (dx[p].n)) on the recorded contacts, fact = Real(-stiffness * k_factor)).  normal / d are the Data
+ * values BEFORE setPlane's normalisation (:139-145), which is applied here in Real.  contacts_dev: n bytes, written by add_force. */
+typedef struct sofab200_plane_desc { double normal[3]; double d; double stiffness, damping, max_force; int bilateral; } sofab200_plane_desc;
+int sofab200_plane_add_force(sofab200_ctx* ctx, sofab200_real real, size_t n, void* f_dev, const void* x_dev, const void* v_dev,
+                             const sofab200_plane_desc* plane, unsigned char* contacts_dev);
+int sofab200_plane_add_dforce(sofab200_ctx* ctx, sofab200_real real, size_t n, void* df_dev, const void* dx_dev,
+                              const sofab200_plane_desc* plane, const unsigned char* contacts_dev, double k_factor);
+
 /* ------------------------------------------------------------------------------------------------ */
 /* MechanicalObject<B200Vec3Types> vector operations  -- [MO]                                       */
 /* ------------------------------------------------------------------------------------------------ */

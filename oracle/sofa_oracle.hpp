@@ -1006,6 +1006,39 @@ template <class R> struct DiagonalMass {
     }
 };
 
+// PlaneForceField  Sofa/Component/MechanicalLoad/src/sofa/component/mechanicalload/PlaneForceField.inl
+// (present in every SofaCUDA FEM benchmark scene).  setPlane :139-145, addForce :158-205, addDForce :208-226.
+template <class R> struct PlaneForceField {
+    Vec3<R> planeNormal = Vec3<R>(0, 1, 0);
+    R planeD = 0, stiffness = 500, damping = 5, maxForce = 0;
+    bool bilateral = false;
+    std::vector<uint32_t> contacts;      // m_contacts
+    void setPlane(const Vec3<R>& normal, R d) { const R n = normal.norm(); planeNormal = normal / n; planeD = d / n; }
+    void addForce(VecDeriv<R>& f, const std::vector<Vec3<R>>& p, const VecDeriv<R>& v) {
+        contacts.clear();
+        R limit = maxForce;
+        limit *= limit;
+        const R stiff = stiffness, damp = damping;
+        const Vec3<R> planeN = planeNormal;
+        for (size_t i = 0; i < p.size(); ++i) {
+            const R d = dot(p[i], planeN) - planeD;
+            if (bilateral || d < 0) {
+                const R forceIntensity = -stiff * d;
+                const R dampingIntensity = -damp * d;
+                Vec3<R> force = planeN * forceIntensity - v[i] * dampingIntensity;
+                const R amplitude = force.norm2();
+                if (limit > 0 && amplitude > limit) force *= std::sqrt(limit / amplitude);
+                f[i] += force;
+                contacts.push_back(uint32_t(i));
+            }
+        }
+    }
+    void addDForce(VecDeriv<R>& df, const VecDeriv<R>& dx, double kFactorIncludingRayleighDamping) const {
+        const R fact = (R)(-stiffness * kFactorIncludingRayleighDamping);
+        for (uint32_t p : contacts) df[p] = df[p] + planeNormal * (fact * dot(dx[p], planeNormal));
+    }
+};
+
 // FixedProjectiveConstraint::projectResponse
 // Sofa/Component/Constraint/Projective/src/sofa/component/constraint/projective/FixedProjectiveConstraint.inl:183-206
 template <class R> inline void projectResponse(VecDeriv<R>& res, const std::vector<uint32_t>& indices, bool fixAll) {

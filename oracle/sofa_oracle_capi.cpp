@@ -43,6 +43,25 @@ template <class R> void copyMats(const std::vector<Mat3<R>>& v, void* out) { if 
 
 }  // namespace
 
+// PlaneForceField stand-alone: prm = {nx, ny, nz, d (both before setPlane's normalisation), stiffness, damping, maxForce, bilateral}
+// addForce: f += ..., contacts_out[i] = 1 for the nodes in contact; addDForce uses the contacts of the given flags
+namespace {
+template <class R> void planeRun(size_t n, const double* prm, void* f, const void* x, const void* v, unsigned char* contacts, const void* dx, double kf, int dforce) {
+    PlaneForceField<R> pf;
+    pf.stiffness = R(prm[4]); pf.damping = R(prm[5]); pf.maxForce = R(prm[6]); pf.bilateral = prm[7] != 0;
+    pf.setPlane(Vec3<R>(R(prm[0]), R(prm[1]), R(prm[2])), R(prm[3]));
+    VecDeriv<R> F = toVec<R>(f, n);
+    if (!dforce) {
+        pf.addForce(F, toVec<R>(x, n), toVec<R>(v, n));
+        std::memset(contacts, 0, n);
+        for (uint32_t i : pf.contacts) contacts[i] = 1;
+    } else {
+        for (size_t i = 0; i < n; ++i) if (contacts[i]) pf.contacts.push_back(uint32_t(i));
+        pf.addDForce(F, toVec<R>(dx, n), kf);
+    }
+    fromVec(F, f);
+}
+}  // namespace
 extern "C" {
 
 // ---- mesh generation ------------------------------------------------------------------------------------------
@@ -75,6 +94,9 @@ MATH(f, float)
 MATH(d, double)
 
 // ---- MechanicalObject vector ops on raw arrays (aliasing by pointer identity, null = no operand) ---------------
+void orc_plane(int real, size_t n, const double* prm, void* f, const void* x, const void* v, unsigned char* contacts, const void* dx, double kf, int dforce) {
+    if (real == 0) planeRun<float>(n, prm, f, x, v, contacts, dx, kf, dforce); else planeRun<double>(n, prm, f, x, v, contacts, dx, kf, dforce);
+}
 void orc_vop(int real, size_t n, void* r, const void* a, const void* b, double k) {
     auto run = [&](auto tag) {
         typedef decltype(tag) R;

@@ -44,6 +44,11 @@ class PeerDesc(C.Structure):
     _fields_ = [("rank", C.c_int), ("world", C.c_int), ("peer_base", C.POINTER(C.c_void_p)), ("inbox_rows", C.c_size_t), ("remote_off", C.POINTER(C.c_size_t))]
 
 
+class PlaneDesc(C.Structure):
+    _fields_ = [("normal", C.c_double * 3), ("d", C.c_double), ("stiffness", C.c_double), ("damping", C.c_double), ("max_force", C.c_double),
+                ("bilateral", C.c_int)]
+
+
 class SolverParams(C.Structure):
     _fields_ = [("gravity", C.c_double * 3), ("dt", C.c_double), ("rayleigh_stiffness", C.c_double), ("rayleigh_mass", C.c_double),
                 ("vdamping", C.c_double), ("first_order", C.c_int), ("trapezoidal", C.c_int), ("iterations", C.c_uint),
@@ -70,6 +75,8 @@ SYMBOLS = {
     "sofab200_mo_vdot_dev": (_I, [_P, _I, _SZ, _P, _P, _P, _P]),
     "sofab200_mo_vmultiop_integrate": (_I, [_P, _I, _SZ, _P, _P, _P, _D, _D]),
     "sofab200_mass_add_mdx": (_I, [_P, _I, _SZ, _P, _P, _P, _D]),
+    "sofab200_plane_add_force": (_I, [_P, _I, _SZ, _P, _P, _P, C.POINTER(PlaneDesc), _P]),
+    "sofab200_plane_add_dforce": (_I, [_P, _I, _SZ, _P, _P, C.POINTER(PlaneDesc), _P, _D]),
     "sofab200_uniform_mass_add_mdx": (_I, [_P, _I, _SZ, _P, _P, _D, _D]),
     "sofab200_uniform_mass_add_force": (_I, [_P, _I, _SZ, _P, _D, C.POINTER(_D)]),
     "sofab200_mass_add_force": (_I, [_P, _I, _SZ, _P, _P, C.POINTER(_D)]),

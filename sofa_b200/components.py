@@ -302,6 +302,26 @@ class UniformMass:
         check(self.ctx.L.sofab200_uniform_mass_add_force(self.ctx.h, self.mstate.real, self.mstate.size, _dptr(f), self.vertexMass_value, g))
 
 
+class PlaneForceField:
+    """PlaneForceField<B200Vec3Types>: Data normal, d, stiffness, damping, maxForce, bilateral (+ rayleighStiffness of BaseForceField);
+    per-operation level (MechanicalLoad/.../PlaneForceField.inl:158-226)."""
+
+    def __init__(self, mstate, normal=(0.0, 1.0, 0.0), d=0.0, stiffness=500.0, damping=5.0, maxForce=0.0, bilateral=False, rayleighStiffness=0.0):
+        self.mstate, self.ctx = mstate, mstate.ctx
+        self.rayleighStiffness = float(rayleighStiffness)
+        self.desc = _lib.PlaneDesc()
+        self.desc.normal = (C.c_double * 3)(*[float(v) for v in normal])
+        self.desc.d, self.desc.stiffness, self.desc.damping, self.desc.max_force, self.desc.bilateral = float(d), float(stiffness), float(damping), float(maxForce), int(bilateral)
+        self.contacts = torch.zeros(mstate.size, dtype=torch.uint8, device=self.ctx.device)      # m_contacts as a per-node flag
+
+    def addForce(self, f, x, v):
+        check(self.ctx.L.sofab200_plane_add_force(self.ctx.h, self.mstate.real, self.mstate.size, _dptr(f), _dptr(x), _dptr(v), C.byref(self.desc), _dptr(self.contacts)))
+
+    def addDForce(self, df, dx, kFactor=1.0, bFactor=0.0):
+        check(self.ctx.L.sofab200_plane_add_dforce(self.ctx.h, self.mstate.real, self.mstate.size, _dptr(df), _dptr(dx), C.byref(self.desc), _dptr(self.contacts),
+                                                   float(kFactor) + float(bFactor) * self.rayleighStiffness))
+
+
 class FixedProjectiveConstraint:
     """FixedProjectiveConstraint<B200Vec3Types>: Data indices, fixAll."""
 

@@ -486,6 +486,45 @@ int sofab200_mass_add_mdx(sofab200_ctx* ctx, sofab200_real real, size_t n, void*
     else LAUNCH(ctx, (mass_mdx_kernel<double>), g, kVecBlock, n, (double*)res_dev, (const double*)dx_dev, (const double*)m_dev, factor, int(factor == 1.0));
     return SOFAB200_OK;
 }
+}  // extern "C"
+namespace sb {
+template <class R> static PlaneDev<R> plane_dev(const sofab200_plane_desc* p) {
+    // setPlane, PlaneForceField.inl:139-145: n = |normal| (sqrt of norm2 accumulated x, y, z); planeNormal = normal / n; planeD = d / n
+    const R a = R(p->normal[0]), b = R(p->normal[1]), c = R(p->normal[2]);
+    R n2 = a * a; n2 += b * b; n2 += c * c;
+    const R nn = R(std::sqrt(n2));
+    PlaneDev<R> P;
+    P.nx = a / nn; P.ny = b / nn; P.nz = c / nn; P.d = R(p->d) / nn;
+    P.stiff = R(p->stiffness); P.damp = R(p->damping);
+    R lim = R(p->max_force); lim *= lim; P.limit2 = lim;
+    P.bilateral = p->bilateral;
+    return P;
+}
+}  // namespace sb
+extern "C" {
+int sofab200_plane_add_force(sofab200_ctx* ctx, sofab200_real real, size_t n, void* f_dev, const void* x_dev, const void* v_dev, const sofab200_plane_desc* plane,
+                             unsigned char* contacts_dev) {
+    SB_CHECK(ctx && f_dev && x_dev && v_dev && plane && contacts_dev, "null argument");
+    if (n == 0) return SOFAB200_OK;
+    const int g = vec_grid(n, ctx->sm_count);
+    if (real == SOFAB200_F32) LAUNCH(ctx, (plane_add_force_kernel<float>), g, kVecBlock, n, plane_dev<float>(plane), (float*)f_dev, (const float*)x_dev, (const float*)v_dev, contacts_dev);
+    else LAUNCH(ctx, (plane_add_force_kernel<double>), g, kVecBlock, n, plane_dev<double>(plane), (double*)f_dev, (const double*)x_dev, (const double*)v_dev, contacts_dev);
+    return SOFAB200_OK;
+}
+int sofab200_plane_add_dforce(sofab200_ctx* ctx, sofab200_real real, size_t n, void* df_dev, const void* dx_dev, const sofab200_plane_desc* plane,
+                              const unsigned char* contacts_dev, double k_factor) {
+    SB_CHECK(ctx && df_dev && dx_dev && plane && contacts_dev, "null argument");
+    if (n == 0) return SOFAB200_OK;
+    const int g = vec_grid(n, ctx->sm_count);
+    if (real == SOFAB200_F32) {
+        const PlaneDev<float> P = plane_dev<float>(plane);
+        LAUNCH(ctx, (plane_add_dforce_kernel<float>), g, kVecBlock, n, P, float(-double(float(plane->stiffness)) * k_factor), (float*)df_dev, (const float*)dx_dev, contacts_dev);
+    } else {
+        const PlaneDev<double> P = plane_dev<double>(plane);
+        LAUNCH(ctx, (plane_add_dforce_kernel<double>), g, kVecBlock, n, P, -plane->stiffness * k_factor, (double*)df_dev, (const double*)dx_dev, contacts_dev);
+    }
+    return SOFAB200_OK;
+}
 int sofab200_uniform_mass_add_mdx(sofab200_ctx* ctx, sofab200_real real, size_t n, void* res_dev, const void* dx_dev, double vertex_mass, double factor) {
     SB_CHECK(ctx && res_dev && dx_dev, "null argument");
     if (n == 0) return SOFAB200_OK;

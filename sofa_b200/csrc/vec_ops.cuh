@@ -125,6 +125,35 @@ template <class R> __global__ void __launch_bounds__(kVecBlock) fixed_project_ke
         res[3 * g] = R(0); res[3 * g + 1] = R(0); res[3 * g + 2] = R(0);
     }
 }
+// PlaneForceField::addForce / addDForce (PlaneForceField.inl:158-226), one thread per node, the reference's operation order
+template <class R> struct PlaneDev { R nx, ny, nz, d, stiff, damp, limit2; int bilateral; };
+template <class R> __global__ void __launch_bounds__(kVecBlock) plane_add_force_kernel(size_t n, PlaneDev<R> P, R* __restrict__ f, const R* __restrict__ x, const R* __restrict__ v,
+                                                                                       unsigned char* __restrict__ contacts) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        R d = x[3 * i] * P.nx; d += x[3 * i + 1] * P.ny; d += x[3 * i + 2] * P.nz;     // p * planeN
+        d = d - P.d;
+        unsigned char hit = 0;
+        if (P.bilateral || d < R(0)) {
+            const R fi = -P.stiff * d, di = -P.damp * d;
+            R f0 = P.nx * fi - v[3 * i] * di, f1 = P.ny * fi - v[3 * i + 1] * di, f2 = P.nz * fi - v[3 * i + 2] * di;
+            R amp = f0 * f0; amp += f1 * f1; amp += f2 * f2;
+            if (P.limit2 > R(0) && amp > P.limit2) { const R s = sqrt(P.limit2 / amp); f0 *= s; f1 *= s; f2 *= s; }
+            f[3 * i] += f0; f[3 * i + 1] += f1; f[3 * i + 2] += f2;
+            hit = 1;
+        }
+        contacts[i] = hit;
+    }
+}
+template <class R> __global__ void __launch_bounds__(kVecBlock) plane_add_dforce_kernel(size_t n, PlaneDev<R> P, R fact, R* __restrict__ df, const R* __restrict__ dx,
+                                                                                        const unsigned char* __restrict__ contacts) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        if (!contacts[i]) continue;
+        R s = dx[3 * i] * P.nx; s += dx[3 * i + 1] * P.ny; s += dx[3 * i + 2] * P.nz;
+        const R t = fact * s;
+        df[3 * i] = df[3 * i] + P.nx * t; df[3 * i + 1] = df[3 * i + 1] + P.ny * t; df[3 * i + 2] = df[3 * i + 2] + P.nz * t;
+    }
+}
+
 // generic per-node epilogue without element contributions (right-hand side when the stiffness term is absent)
 template <class R> __global__ void __launch_bounds__(kVecBlock) node_only_kernel(size_t n, NodeEpilogue<R> ep) {
     for (size_t g = size_t(blockIdx.x) * blockDim.x + threadIdx.x; g < n; g += size_t(gridDim.x) * blockDim.x) {

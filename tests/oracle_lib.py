@@ -257,6 +257,23 @@ def vop(dtype, r, a, b, k):
     return r
 
 
+def plane_add_force(dtype, prm, f, x, v):
+    """PlaneForceField::addForce on (f, x, v); prm = (normal[3], d, stiffness, damping, maxForce, bilateral).  Returns (f, contacts)."""
+    L = lib(); dtype = np.dtype(dtype)
+    f = np.ascontiguousarray(f, dtype).copy(); x = np.ascontiguousarray(x, dtype); v = np.ascontiguousarray(v, dtype)
+    p = np.ascontiguousarray(prm, np.float64); c = np.zeros(f.shape[0], np.uint8)
+    L.orc_plane(0 if dtype == np.float32 else 1, C.c_size_t(f.shape[0]), _ptr(p), _ptr(f), _ptr(x), _ptr(v), _ptr(c), None, C.c_double(0.0), 0)
+    return f, c
+
+
+def plane_add_dforce(dtype, prm, df, dx, contacts, k_factor):
+    L = lib(); dtype = np.dtype(dtype)
+    df = np.ascontiguousarray(df, dtype).copy(); dx = np.ascontiguousarray(dx, dtype)
+    p = np.ascontiguousarray(prm, np.float64); c = np.ascontiguousarray(contacts, np.uint8)
+    L.orc_plane(0 if dtype == np.float32 else 1, C.c_size_t(df.shape[0]), _ptr(p), _ptr(df), None, None, _ptr(c), _ptr(dx), C.c_double(k_factor), 1)
+    return df
+
+
 def vdot(dtype, a, b):
     real = 0 if np.dtype(dtype) == np.float32 else 1
     return float(lib().orc_vdot(real, C.c_size_t(a.shape[0]), _ptr(a), _ptr(b)))

@@ -69,6 +69,34 @@ def test_add_force_add_dforce_bit_exact(dtype, method):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", [dict(), dict(maxForce=0.05), dict(bilateral=True, normal=(0.3, 1.0, -0.2), d=0.7)], ids=["default", "maxForce", "bilateral"])
+def test_plane_force_field_bit_exact(dtype, case):
+    """PlaneForceField addForce / addDForce (per-operation level; in every SofaCUDA FEM benchmark scene), bit-identical to the
+    restatement of PlaneForceField.inl:139-226, including the contact set."""
+    import sofa_b200 as sb
+    from gpu_common import mesh
+    c, pos, hexas, tets, fixed = mesh("C1")
+    rng = np.random.default_rng(5)
+    x = (pos + 0.3 * rng.standard_normal(pos.shape)).astype(dtype)
+    x[:, 1] -= 4.0                                   # part of the beam below the plane y = d
+    v = rng.standard_normal(pos.shape).astype(dtype)
+    kw = dict(normal=(0.0, 2.0, 0.0), d=-1.0, stiffness=500.0, damping=5.0, maxForce=0.0, bilateral=False); kw.update(case)
+    prm = list(kw["normal"]) + [kw["d"], kw["stiffness"], kw["damping"], kw["maxForce"], float(kw["bilateral"])]
+    ctx = sb.Context(0)
+    mo = sb.MechanicalObject(ctx, "B200Vec3f" if dtype == np.float32 else "B200Vec3d", position=pos)
+    pf = sb.PlaneForceField(mo, rayleighStiffness=0.1, **kw)
+    f0 = rng.standard_normal(pos.shape).astype(dtype)
+    f_d = dev(mo, f0); pf.addForce(f_d, dev(mo, x), dev(mo, v))
+    f_ref, c_ref = O.plane_add_force(dtype, prm, f0, x, v)
+    assert 0 < c_ref.sum() <= pos.shape[0]
+    assert pf.contacts.cpu().numpy().tobytes() == c_ref.tobytes()
+    assert f_d.cpu().numpy().tobytes() == f_ref.tobytes()
+    dx = (1e-2 * rng.standard_normal(pos.shape)).astype(dtype)
+    df_d = dev(mo, f0); pf.addDForce(df_d, dev(mo, dx), kFactor=-0.0011, bFactor=-0.01)
+    assert df_d.cpu().numpy().tobytes() == O.plane_add_dforce(dtype, prm, f0, dx, c_ref, -0.0011 + -0.01 * 0.1).tobytes()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("how", ["vertexMass", "totalMass"])
 def test_uniform_mass_parity(dtype, how):
     """UniformMass instead of DiagonalMass ("UniformMass equivalents"): its addMDx multiplies the MassType by the

@@ -143,3 +143,21 @@ def test_vop_semantics(dtype):
     r = np.zeros_like(a); O.vop(dtype, r, a, b, k); assert np.array_equal(r, a + b * kr)   # r = a + b*k
     d = O.vdot(dtype, a, b)
     assert abs(d - float(np.sum(a.astype(np.float64) * b))) < (1e-12 if dtype == np.float64 else 1e-4)
+
+
+def test_plane_force_field_restatement_properties():
+    """PlaneForceField.inl:139-226 restated: only nodes below the (normalised) plane are pushed back along the normal, the contact
+    set drives addDForce, and addDForce equals the finite difference of addForce's stiffness part."""
+    rng = np.random.default_rng(2)
+    x = rng.uniform(-1, 1, (200, 3)); v = np.zeros_like(x)
+    prm = [0.0, 2.0, 0.0, 0.5, 500.0, 0.0, 0.0, 0.0]          # plane y = 0.25 after normalisation, no damping
+    f, c = O.plane_add_force(np.float64, prm, np.zeros_like(x), x, v)
+    below = x[:, 1] < 0.25
+    assert (c.astype(bool) == below).all()
+    assert np.allclose(f[below], np.stack([np.zeros(below.sum()), -500.0 * (x[below, 1] - 0.25), np.zeros(below.sum())], 1), rtol=1e-13, atol=1e-13)
+    assert (f[~below] == 0).all()
+    dx = 1e-6 * rng.standard_normal(x.shape)
+    f2, c2 = O.plane_add_force(np.float64, prm, np.zeros_like(x), x + dx, v)
+    same = (c == c2)
+    df = O.plane_add_dforce(np.float64, prm, np.zeros_like(x), dx, c, 1.0)
+    assert np.allclose((f2 - f)[same], df[same], rtol=1e-6, atol=1e-12)
