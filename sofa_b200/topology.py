@@ -137,3 +137,39 @@ def read_gmsh_v1(path):
             hexas.append(nodes)
         i += 5 + nnodes
     return pos, np.array(tets, np.uint32).reshape(-1, 4), np.array(hexas, np.uint32).reshape(-1, 8)
+
+
+# ---------------------------------------------------------------------------------------------------
+# WriteState / ReadState text dumps (Sofa/Component/Playback/src/sofa/component/playback/WriteState.inl:350-381,
+# ReadState.inl:219-262): one block per exported time, "T= <time>" then "  X= x0 y0 z0 x1 ...", "  V= ...", optionally "  F= ...",
+# "  X0= ...".  The reference writes with the stream's default precision (6 significant digits); `precision=17` keeps doubles exact.
+# ---------------------------------------------------------------------------------------------------
+def write_state(path, frames, precision=6):
+    """frames: iterable of dicts {"T": time, "X": [n,3], "V": [n,3], ...} (keys other than T are optional)."""
+    fmt = f"%.{int(precision)}g"
+    with open(path, "w") as fh:
+        for fr in frames:
+            fh.write("T= " + (fmt % float(fr["T"])) + "\n")
+            for key in ("X", "X0", "V", "F"):
+                if key in fr and fr[key] is not None:
+                    a = np.asarray(fr[key], np.float64).reshape(-1)
+                    fh.write(f"  {key}= " + " ".join(fmt % v for v in a) + "\n")
+
+
+def read_state(path):
+    """Inverse of write_state / of SOFA's WriteState: list of {"T": float, "X": [n,3], "V": [n,3], ...}."""
+    frames = []
+    with open(path) as fh:
+        for line in fh:
+            tok = line.split()
+            if not tok:
+                continue
+            cmd = tok[0]
+            if cmd == "T=":
+                frames.append({"T": float(tok[1])})
+            elif cmd in ("X=", "X0=", "V=", "F=") and frames:
+                a = np.array([float(v) for v in tok[1:]], np.float64)
+                if a.size % 3:
+                    raise ValueError(f"{path}: {cmd} holds {a.size} values, not a multiple of 3")
+                frames[-1][cmd[:-1]] = a.reshape(-1, 3)
+    return frames

@@ -52,3 +52,20 @@ def test_box_roi_closed_intervals():
     pos, _ = T.regular_grid((5, 5, 20), (-5, -5, 0), (5, 5, 40))
     idx = T.box_roi(pos, (-6, -6, -1, 50, 6, 0.1))
     assert len(idx) == 25 and np.array_equal(idx, O.box_roi(pos, (-6, -6, -1, 50, 6, 0.1)))
+
+
+def test_write_state_read_state_round_trip(tmp_path):
+    """WriteState / ReadState text dumps (Playback/WriteState.inl:350-381): the reference's layout, exact with precision=17."""
+    rng = np.random.default_rng(4)
+    frames = [dict(T=0.01 * k, X=rng.standard_normal((7, 3)), V=rng.standard_normal((7, 3))) for k in range(3)]
+    p = tmp_path / "beam.state"
+    T.write_state(p, frames, precision=17)
+    txt = p.read_text().splitlines()
+    assert txt[0].startswith("T= ") and txt[1].startswith("  X= ") and txt[2].startswith("  V= ")
+    back = T.read_state(p)
+    assert len(back) == 3
+    for a, b in zip(frames, back):
+        assert a["T"] == b["T"] and (a["X"] == b["X"]).all() and (a["V"] == b["V"]).all()
+    T.write_state(p, frames)                           # the reference's default stream precision: 6 significant digits
+    back = T.read_state(p)
+    assert np.allclose(back[1]["X"], frames[1]["X"], rtol=1e-5, atol=1e-6)
