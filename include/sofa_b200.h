@@ -203,6 +203,9 @@ typedef struct sofab200_node_desc {
     int mass_first;                 /* 1: the mass precedes the force field in the scene (all reference scenes) */
     int uniform_mass;               /* 1: the mass is a UniformMass (Mass/.../UniformMass.inl:403-496) with the MassType below;  */
     double uniform_vertex_mass;     /*    vertex_mass_host is then ignored                                       */
+    const sofab200_plane_desc* plane; /* optional PlaneForceField, the node's LAST force field (as in the SofaCUDA benchmark scenes): its
+                                     * addForce / addDForce are fused into the per-node epilogue of the element passes        */
+    double plane_rayleigh_stiffness;
 } sofab200_node_desc;
 
 typedef struct sofab200_solver_params {
@@ -251,7 +254,8 @@ int sofab200_node_step_host(sofab200_node* node, void* x_host, void* v_host);
  * inside the CG kernel and the solve was abandoned), and the `graph` Data
  * (Error / Denominator histories, [CG]:109-116,148,213).  Any pointer may be NULL. */
 int sofab200_node_last_solve(sofab200_node* node, int* nb_iter, int* end_cond, double* graph_error, size_t* n_error, double* graph_den, size_t* n_den, size_t cap);
-/* Device vectors of the last step for parity checks (sync): "f" (force), "b" (right-hand side), "dx" (solution) */
+/* Device vectors of the last step for parity checks (sync): "f" (force), "b" (right-hand side), "dx" (solution): n Vec3 of Real;
+ * "plane_contacts": n bytes, the PlaneForceField contact flags of the last addForce. */
 int sofab200_node_get(sofab200_node* node, const char* what, void* out_host);
 /* ------------------------------------------------------------------------------------------------ */
 /* Multi-GPU: one process per GPU, the mesh partitioned by contiguous element ranges (sofa_b200/parallel.py).   */

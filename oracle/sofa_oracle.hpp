@@ -1061,6 +1061,8 @@ template <class R> struct Scene {
     HexaFEM<R> hex; bool hasHex = false;
     double ffRayleighStiffness = 0;   // BaseForceField::rayleighStiffness of the FEM component (default 0)
     bool massFirst = true;            // scene order of the two force fields (mass before FEM in every reference scene)
+    PlaneForceField<R> plane; bool hasPlane = false;   // last force field of the node (as in the SofaCUDA benchmark scenes)
+    double planeRayleighStiffness = 0;
     std::vector<uint32_t> fixed; bool fixAll = false;
     double gravity[3] = {0, -9.81, 0};
     // EulerImplicitSolver Data (EulerImplicitSolver.cpp:40-50)
@@ -1127,6 +1129,7 @@ template <class R> struct Scene {
         if (massFirst && hasMass) mass.addForce(F, gravity);
         femAddForce(F);
         if (!massFirst && hasMass) mass.addForce(F, gravity);
+        if (hasPlane) plane.addForce(F, x, v);
     }
     // addMBKdx over the node's force fields: BaseForceField::addMBKdx (BaseForceField.cpp:38-47) and
     // Mass::addMBKdx (Sofa/framework/Core/src/sofa/core/behavior/Mass.inl:93-105); factors per MechanicalParams.h:62-64
@@ -1141,6 +1144,10 @@ template <class R> struct Scene {
             if (kf != 0.0 || b != 0.0) femAddDForce(df, d, kf);
         };
         if (massFirst) { massPart(); femPart(); } else { femPart(); massPart(); }
+        if (hasPlane) {   // BaseForceField::addMBKdx again, for the plane
+            const double kf = k + b * planeRayleighStiffness;
+            if (kf != 0.0 || b != 0.0) plane.addDForce(df, d, kf);
+        }
     }
     // GraphScatteredMatrix::apply  Sofa/Component/LinearSolver/Iterative/src/sofa/component/linearsolver/iterative/GraphScatteredTypes.cpp:33-46
     void applyA(VecDeriv<R>& res, const VecDeriv<R>& p) {

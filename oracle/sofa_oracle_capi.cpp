@@ -162,6 +162,14 @@ void orc_scene_set_mass(void* h, int kind, double value, size_t nelems, const ui
         }
     });
 }
+// PlaneForceField of the node: prm as for orc_plane, + its rayleighStiffness
+void orc_scene_set_plane(void* h, const double* prm, double rayleigh) {
+    DISPATCH(h, {
+        sc.hasPlane = true; sc.planeRayleighStiffness = rayleigh;
+        sc.plane.stiffness = R(prm[4]); sc.plane.damping = R(prm[5]); sc.plane.maxForce = R(prm[6]); sc.plane.bilateral = prm[7] != 0;
+        sc.plane.setPlane(Vec3<R>(R(prm[0]), R(prm[1]), R(prm[2])), R(prm[3]));
+    });
+}
 void orc_scene_set_fixed(void* h, size_t n, const uint32_t* idx, int fixAll) {
     DISPATCH(h, { sc.fixed.assign(idx, idx + n); sc.fixAll = fixAll != 0; });
 }

@@ -29,9 +29,14 @@ class HexFemDesc(C.Structure):
                 ("poisson", C.POINTER(C.c_double)), ("tile_elems", C.c_int)]
 
 
+class PlaneDesc(C.Structure):
+    _fields_ = [("normal", C.c_double * 3), ("d", C.c_double), ("stiffness", C.c_double), ("damping", C.c_double), ("max_force", C.c_double),
+                ("bilateral", C.c_int)]
+
+
 class NodeDesc(C.Structure):
     _fields_ = [("tetfem", _P), ("hexfem", _P), ("vertex_mass_host", _P), ("n_fixed", C.c_size_t), ("fixed_host", C.POINTER(C.c_uint32)),
-                ("fix_all", C.c_int), ("mass_first", C.c_int), ("uniform_mass", C.c_int), ("uniform_vertex_mass", C.c_double)]
+                ("fix_all", C.c_int), ("mass_first", C.c_int), ("uniform_mass", C.c_int), ("uniform_vertex_mass", C.c_double), ("plane", C.POINTER(PlaneDesc)), ("plane_rayleigh_stiffness", C.c_double)]
 
 
 class HaloDesc(C.Structure):
@@ -42,11 +47,6 @@ class HaloDesc(C.Structure):
 
 class PeerDesc(C.Structure):
     _fields_ = [("rank", C.c_int), ("world", C.c_int), ("peer_base", C.POINTER(C.c_void_p)), ("inbox_rows", C.c_size_t), ("remote_off", C.POINTER(C.c_size_t))]
-
-
-class PlaneDesc(C.Structure):
-    _fields_ = [("normal", C.c_double * 3), ("d", C.c_double), ("stiffness", C.c_double), ("damping", C.c_double), ("max_force", C.c_double),
-                ("bilateral", C.c_int)]
 
 
 class SolverParams(C.Structure):

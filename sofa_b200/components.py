@@ -342,7 +342,7 @@ class SolverNode:
     Data (EulerImplicitSolver): rayleighStiffness, rayleighMass, vdamping, firstOrder, trapezoidalScheme;
     Data (CGLinearSolver): iterations, tolerance, threshold, warmStart; context: dt, gravity."""
 
-    def __init__(self, mstate, forcefield, mass=None, constraint=None, massFirst=True, dt=0.01, gravity=(0.0, -9.81, 0.0), rayleighStiffness=0.0,
+    def __init__(self, mstate, forcefield, mass=None, constraint=None, massFirst=True, plane=None, dt=0.01, gravity=(0.0, -9.81, 0.0), rayleighStiffness=0.0,
                  rayleighMass=0.0, vdamping=0.0, firstOrder=False, trapezoidalScheme=False, iterations=25, tolerance=1e-5, threshold=1e-5,
                  warmStart=False):
         self.mstate, self.ctx, self.forcefield, self.mass, self.constraint = mstate, mstate.ctx, forcefield, mass, constraint
@@ -360,6 +360,9 @@ class SolverNode:
             d.fixed_host = constraint.indices_host.ctypes.data_as(C.POINTER(C.c_uint32))
             d.fix_all = int(constraint.fixAll)
         d.mass_first = int(massFirst)
+        if plane is not None:          # PlaneForceField, the node's last force field: fused into the element passes' epilogue
+            self.plane = plane
+            d.plane = C.pointer(plane.desc); d.plane_rayleigh_stiffness = plane.rayleighStiffness
         self.h = _P()
         check(self.ctx.L.sofab200_node_create(self.ctx.h, mstate.real, mstate.size, C.byref(d), C.byref(self.h)))
         self.params = dict(dt=dt, gravity=tuple(gravity), rayleighStiffness=rayleighStiffness, rayleighMass=rayleighMass, vdamping=vdamping,
@@ -466,6 +469,11 @@ class SolverNode:
     def get(self, what):
         out = np.empty((self.mstate.size, 3), self.mstate.ndtype)
         check(self.ctx.L.sofab200_node_get(self.h, what.encode(), out.ctypes.data_as(_P)))
+        return out
+
+    def get_plane_contacts(self):
+        out = np.empty(self.mstate.size, np.uint8)
+        check(self.ctx.L.sofab200_node_get(self.h, b"plane_contacts", out.ctypes.data_as(_P)))
         return out
 
     def reset(self):

@@ -398,7 +398,7 @@ template <class R> __device__ __forceinline__ double persist_phase3(const TileDe
             if (plus) { ax += s_slot[s]; ay += s_slot[max_slots + s]; az += s_slot[2 * max_slots + s]; }
             else { ax -= s_slot[s]; ay -= s_slot[max_slots + s]; az -= s_slot[2 * max_slots + s]; }
         }
-        part += node_finish_m(ep, rec.mass, (rec.val_fixed & 0x10000u) != 0, R(pv.x), R(pv.y), R(pv.z), ax, ay, az);
+        part += node_finish_m(ep, rec.g, rec.mass, (rec.val_fixed & 0x10000u) != 0, R(pv.x), R(pv.y), R(pv.z), ax, ay, az);
         s_qr[3 * k] = ax; s_qr[3 * k + 1] = ay; s_qr[3 * k + 2] = az;
     }
     return part;
@@ -448,7 +448,7 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
         gather_sum<R>(b0, b1, stg, val, ep.sign > 0, gq0, gq1, gq2, pol);
         // p.q of the node.  Multi-GPU: (gq) of an interface node is this rank's PARTIAL sum; since p is the same on every sharing
         // rank, the ranks' p.q_partial add up to p.q, so den needs no exchanged q: halo and all-reduce share one cross-GPU sync.
-        part2 += node_finish_m(ep, grec.mass, (grec.val_fixed & 0x10000u) != 0, gp0, gp1, gp2, gq0, gq1, gq2);
+        part2 += node_finish_m(ep, grec.g, grec.mass, (grec.val_fixed & 0x10000u) != 0, gp0, gp1, gp2, gq0, gq1, gq2);
         if (if_row >= 0) {
             // every other sharing rank gets the partial sum in its inbox (NVLink store)
             for (int e = 0; e < P.max_sh - 1; ++e) {

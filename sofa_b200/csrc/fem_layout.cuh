@@ -45,6 +45,9 @@ struct CGDev {
     double graph_den[kMaxGraph];
 };
 
+// PlaneForceField parameters after setPlane's normalisation (PlaneForceField.inl:139-145)
+template <class R> struct PlaneDev { R nx, ny, nz, d, stiff, damp, limit2; int bilateral; };
+
 template <class R> struct NodeEpilogue {
     const R* init_src;      // acc starts from init_src[node] (may alias out), or 0 when null
     int sign;               // +1: acc += c_i ; -1: acc -= c_i  (per contribution, in order)
@@ -71,6 +74,13 @@ template <class R> struct NodeEpilogue {
     double* dot_result;
     CGDev* cg;
     unsigned long long* trace;   // diagnostics: per-CTA phase timestamps (null = off)
+    // PlaneForceField as the node's LAST force field, fused: 0 none, 1 addForce (input vector = positions), 2 addDForce
+    int plane_mode;
+    PlaneDev<R> plane;
+    R plane_fact;                          // addDForce: Real(-stiffness * kFactorIncludingRayleighDamping)
+    const R* plane_v;                      // addForce: velocities (null = zero)
+    unsigned char* plane_contacts;         // m_contacts as a per-node flag: written by addForce, read by addDForce
+    const R* plane_in;                     // the pass's input vector, for the callers that do not hold the node's entry already
 };
 constexpr int kTraceWords = 16;          // words per CTA
 constexpr int kTraceTail = 4096 * kTraceWords;   // the CG tail kernel's records start here
@@ -222,9 +232,35 @@ template <class R> HD void node_mass(const NodeEpilogue<R>& ep, int kind, uint32
     if (kind == PRE_MDX) { vx = ep.mdx_src[3 * size_t(g)]; vy = ep.mdx_src[3 * size_t(g) + 1]; vz = ep.mdx_src[3 * size_t(g) + 2]; }
     node_mass_v(ep, kind, g, vx, vy, vz, ax, ay, az);
 }
+// PlaneForceField::addForce :158-205 / addDForce :208-226 for one node, (vx, vy, vz) = the node's entry of the pass's input vector
+template <class R> HD void node_plane(const NodeEpilogue<R>& ep, uint32_t g, R vx, R vy, R vz, R& ax, R& ay, R& az) {
+    const PlaneDev<R>& P = ep.plane;
+    if (ep.plane_mode == 2) {
+        if (ep.plane_contacts[g]) {
+            R s = vx * P.nx; s += vy * P.ny; s += vz * P.nz;
+            const R t = ep.plane_fact * s;
+            ax = ax + P.nx * t; ay = ay + P.ny * t; az = az + P.nz * t;
+        }
+    } else if (ep.plane_mode == 1) {
+        R d = vx * P.nx; d += vy * P.ny; d += vz * P.nz;
+        d = d - P.d;
+        unsigned char hit = 0;
+        if (P.bilateral || d < R(0)) {
+            const R fi = -P.stiff * d, di = -P.damp * d;
+            const R w0 = ep.plane_v ? ep.plane_v[3 * size_t(g)] : R(0), w1 = ep.plane_v ? ep.plane_v[3 * size_t(g) + 1] : R(0), w2 = ep.plane_v ? ep.plane_v[3 * size_t(g) + 2] : R(0);
+            R f0 = P.nx * fi - w0 * di, f1 = P.ny * fi - w1 * di, f2 = P.nz * fi - w2 * di;
+            R amp = f0 * f0; amp += f1 * f1; amp += f2 * f2;
+            if (P.limit2 > R(0) && amp > P.limit2) { const R sc = sqrt(P.limit2 / amp); f0 *= sc; f1 *= sc; f2 *= sc; }
+            ax += f0; ay += f1; az += f2;
+            hit = 1;
+        }
+        ep.plane_contacts[g] = hit;
+    }
+}
 // returns this node's contribution to the dot product
 template <class R> HD double node_post_v(const NodeEpilogue<R>& ep, uint32_t g, R vx, R vy, R vz, R ax, R ay, R az) {
     node_mass_v(ep, ep.post_kind, g, vx, vy, vz, ax, ay, az);
+    if (ep.plane_mode) node_plane(ep, g, vx, vy, vz, ax, ay, az);
     if (ep.has_scale) { ax *= ep.scale; ay *= ep.scale; az *= ep.scale; }
     if (ep.fixed && ep.fixed[g]) { ax = R(0); ay = R(0); az = R(0); }
     ep.out[3 * size_t(g)] = ax; ep.out[3 * size_t(g) + 1] = ay; ep.out[3 * size_t(g) + 2] = az;
@@ -233,21 +269,23 @@ template <class R> HD double node_post_v(const NodeEpilogue<R>& ep, uint32_t g, 
 }
 // same with the node's mass and fixed flag already loaded
 // ... and the result left in (ax, ay, az) instead of ep.out
-template <class R> HD double node_finish_m(const NodeEpilogue<R>& ep, R m, bool is_fixed, R vx, R vy, R vz, R& ax, R& ay, R& az) {
+template <class R> HD double node_finish_m(const NodeEpilogue<R>& ep, uint32_t g, R m, bool is_fixed, R vx, R vy, R vz, R& ax, R& ay, R& az) {
     node_mass_m(ep, ep.post_kind, m, vx, vy, vz, ax, ay, az);
+    if (ep.plane_mode) node_plane(ep, g, vx, vy, vz, ax, ay, az);
     if (ep.has_scale) { ax *= ep.scale; ay *= ep.scale; az *= ep.scale; }
     if (is_fixed) { ax = R(0); ay = R(0); az = R(0); }
     if (ep.dot_kind != DOT_NONE) return double(ax) * double(vx) + double(ay) * double(vy) + double(az) * double(vz);
     return 0.0;
 }
 template <class R> HD double node_post_m(const NodeEpilogue<R>& ep, uint32_t g, R m, bool is_fixed, R vx, R vy, R vz, R ax, R ay, R az) {
-    const double d = node_finish_m(ep, m, is_fixed, vx, vy, vz, ax, ay, az);
+    const double d = node_finish_m(ep, g, m, is_fixed, vx, vy, vz, ax, ay, az);
     ep.out[3 * size_t(g)] = ax; ep.out[3 * size_t(g) + 1] = ay; ep.out[3 * size_t(g) + 2] = az;
     return d;
 }
 template <class R> HD double node_post(const NodeEpilogue<R>& ep, uint32_t g, R ax, R ay, R az) {
     R vx = 0, vy = 0, vz = 0;
     const R* src = ep.dot_kind != DOT_NONE ? ep.dot_with : (ep.post_kind == PRE_MDX ? ep.mdx_src : nullptr);
+    if (ep.plane_mode) src = ep.plane_in;
     if (src) { vx = src[3 * size_t(g)]; vy = src[3 * size_t(g) + 1]; vz = src[3 * size_t(g) + 2]; }
     return node_post_v(ep, g, vx, vy, vz, ax, ay, az);
 }

@@ -100,6 +100,8 @@ template <class R> struct Node : sofab200_node {
     sofab200_hexfem* hex = nullptr;
     bool has_mass = false, mass_first = true;
     bool uniform_mass = false; double um = 0.0;   // UniformMass: every entry of `mass` holds Real(um)
+    bool has_plane = false; PlaneDev<R> plane; double plane_stiffness = 0, plane_rayleigh = 0;   // PlaneForceField, last force field of the node
+    DevBuf<unsigned char> plane_contacts;
     DevBuf<R> mass;
     DevBuf<unsigned char> fixed;
     bool has_fixed = false;
@@ -191,7 +193,7 @@ template <class R> struct Node : sofab200_node {
     int tail_grid = 0;
     DevBuf<double> partials_rho;
     int cg_tail(R* x, double m, double bfac, double k) {
-        NodeEpilogue<R> ep = make_mbk_ep(q.p, nullptr, p.p, m, bfac, false, 1.0, true, DOT_STORE, cg.p);
+        NodeEpilogue<R> ep = make_mbk_ep(q.p, nullptr, p.p, m, bfac, k, false, 1.0, true, DOT_STORE, cg.p);
         TileDev<R> td = tet ? tet_tiledev<R>(tet) : hex_tiledev<R>(hex);
         if (!tail_grid) {
             int per_sm = 0;
@@ -210,7 +212,8 @@ template <class R> struct Node : sofab200_node {
         return SOFAB200_OK;
     }
     // the whole CG loop in one cooperative launch (cg_persist.cuh); pd != null: multi-GPU over peer memory
-    int launch_persistent(R* x, const R* bvec, double m, double bfac, double kf, const PeerDev<R>* pd) {
+    int launch_persistent(R* x, const R* bvec, double m, double bfac, double k, const PeerDev<R>* pd) {
+        const double kf = k + bfac * prm.ff_rayleigh_stiffness;
         const size_t n3 = 3 * n;
         if (!ps0.p) { SB_TRY(ps0.alloc(n)); SB_TRY(ps1.alloc(n)); SB_TRY(rs.alloc(n)); }
         const size_t n_tile_nodes = tet_tile_node_count(tet);
@@ -218,7 +221,7 @@ template <class R> struct Node : sofab200_node {
         if (!gstate.p) SB_TRY(gstate.alloc(size_t(9) * ctx->sm_count * 2048));
         if (!sync_slots.p) SB_TRY(sync_slots.alloc(3 * 2048 + 8));
         PersistCG<R> a;
-        a.ep = make_mbk_ep(q.p, nullptr, p.p, m, bfac, false, 1.0, true, DOT_STORE, cg.p);
+        a.ep = make_mbk_ep(q.p, nullptr, p.p, m, bfac, k, false, 1.0, true, DOT_STORE, cg.p);
         a.x = x; a.r = r.p; a.b = bvec; a.xt = xt.p; a.rt = rt.p; a.gstate = gstate.p; a.p0 = ps0.p; a.p1 = ps1.p; a.rs = rs.p; a.n3 = n3; a.cg = cg.p; a.sync = sync_slots.p;
         if (pd) a.peer = *pd; else std::memset(&a.peer, 0, sizeof(a.peer));
         SB_CUDA(cudaMemsetAsync(sync_slots.p, 0, sync_slots.n * sizeof(unsigned long long), ctx->stream));
@@ -241,15 +244,16 @@ template <class R> struct Node : sofab200_node {
         ep.gx = R(prm.gravity[0]); ep.gy = R(prm.gravity[1]); ep.gz = R(prm.gravity[2]);
     }
     // mop.computeForce
-    int compute_force(R* f_out, const R* x) {
+    int compute_force(R* f_out, const R* x, const R* v = nullptr) {
         NodeEpilogue<R> ep = base_ep();
         ep.init_src = nullptr; ep.sign = +1; ep.out = f_out;
         set_mass_term(ep, PRE_GRAVITY, nullptr, 1.0);
+        if (has_plane) { ep.plane_mode = 1; ep.plane = plane; ep.plane_v = v; ep.plane_contacts = plane_contacts.p; ep.plane_in = x; }
         SB_TRY(fem_run(false, x, R(0), ep));
         return halo_sum(f_out, nullptr);
     }
     // df = init + (m M + b B + k K) d, optionally scaled and projected; dot(out, dot_with) optional
-    NodeEpilogue<R> make_mbk_ep(R* out, const R* init, const R* d, double m, double bfac, bool scale, double s, bool project, int dot_kind, CGDev* cgp) {
+    NodeEpilogue<R> make_mbk_ep(R* out, const R* init, const R* d, double m, double bfac, double k, bool scale, double s, bool project, int dot_kind, CGDev* cgp) {
         NodeEpilogue<R> ep = base_ep();
         ep.init_src = init; ep.sign = -1; ep.out = out;
         const double mf = m - bfac * prm.mass_rayleigh_mass;          // MechanicalParams.h:64
@@ -257,10 +261,17 @@ template <class R> struct Node : sofab200_node {
         ep.has_scale = scale; ep.scale = R(s);
         ep.fixed = (project && has_fixed) ? fixed.p : nullptr;
         ep.dot_kind = dot_kind; ep.dot_with = d; ep.cg = cgp;
+        if (has_plane) {   // BaseForceField::addMBKdx for the plane: skipped when its kFactor and bFactor are both zero
+            const double kfp = k + bfac * plane_rayleigh;
+            if (kfp != 0.0 || bfac != 0.0) {
+                ep.plane_mode = 2; ep.plane = plane; ep.plane_contacts = plane_contacts.p; ep.plane_in = d;
+                ep.plane_fact = R(-double(R(plane_stiffness)) * kfp);
+            }
+        }
         return ep;
     }
     int add_mbk(R* out, const R* init, const R* d, double m, double bfac, double k, bool scale, double s, bool project, int dot_kind, CGDev* cgp, bool skip_gather = false) {
-        NodeEpilogue<R> ep = make_mbk_ep(out, init, d, m, bfac, scale, s, project, dot_kind, cgp);
+        NodeEpilogue<R> ep = make_mbk_ep(out, init, d, m, bfac, k, scale, s, project, dot_kind, cgp);
         const double kf = k + bfac * prm.ff_rayleigh_stiffness;       // MechanicalParams.h:62
         if (kf != 0.0 || bfac != 0.0) return fem_run(true, d, R(kf), ep, skip_gather);   // BaseForceField::addMBKdx, BaseForceField.cpp:38-47
         if (dot_kind != DOT_NONE) return fail(SOFAB200_ERR_UNSUPPORTED, "system without a stiffness term is not supported in the CG loop");
@@ -291,7 +302,7 @@ template <class R> struct Node : sofab200_node {
             const double kf_d = k + bfac * prm.ff_rayleigh_stiffness;
             if (peer.ready && persistent && tet && (kf_d != 0.0 || bfac != 0.0)) {
                 // the loop in ONE persistent kernel per GPU; halo rows and dot products go through peer memory (cg_persist.cuh)
-                const int rc = launch_persistent(x, bvec, m, bfac, kf_d, &peer.dev);
+                const int rc = launch_persistent(x, bvec, m, bfac, k, &peer.dev);
                 if (rc == SOFAB200_OK) { LAUNCH(ctx, cg_end_kernel, 1, 1, cg.p); return SOFAB200_OK; }
                 if (rc != kPersistNotEligible) return rc;
                 peer.ready = false;      // (cannot happen after sofab200_node_set_peer's probe; kept for safety)
@@ -311,7 +322,7 @@ template <class R> struct Node : sofab200_node {
         }
         const double kf_chk = k + bfac * prm.ff_rayleigh_stiffness;
         if (persistent && tet && (kf_chk != 0.0 || bfac != 0.0)) {
-            const int rc = launch_persistent(x, bvec, m, bfac, kf_chk, nullptr);     // (|b| and the first rho included)
+            const int rc = launch_persistent(x, bvec, m, bfac, k, nullptr);     // (|b| and the first rho included)
             if (rc == SOFAB200_OK) { LAUNCH(ctx, cg_end_kernel, 1, 1, cg.p); return SOFAB200_OK; }
             if (rc != kPersistNotEligible) return rc;
             persistent = false;      // this mesh does not fit: multi-kernel loop from now on
@@ -375,7 +386,7 @@ template <class R> struct Node : sofab200_node {
     int step_direct(R* x, R* v, bool skip_force = false) {
         const double h = prm.dt, tr = prm.trapezoidal ? 0.5 : 1.0;
         const bool fo = prm.first_order != 0;
-        if (!skip_force) SB_TRY(compute_force(f.p, x));
+        if (!skip_force) SB_TRY(compute_force(f.p, x, v));
         if (!fo) {
             // b = (f + (-rM M + (h tr + rK) K) v) * h, projected          EulerImplicitSolver.cpp:147-162
             const R* finit = f.p;
@@ -407,6 +418,7 @@ template <class R> struct Node : sofab200_node {
     }
 };
 
+template <class R> static PlaneDev<R> plane_dev(const sofab200_plane_desc* p);
 template <class R> static int node_create(sofab200_ctx* ctx, size_t n, const sofab200_node_desc* d, sofab200_node** out) {
     std::unique_ptr<Node<R>> nd(new Node<R>());
     nd->ctx = ctx; nd->real = sizeof(R) == 4 ? SOFAB200_F32 : SOFAB200_F64; nd->n = n;
@@ -417,6 +429,10 @@ template <class R> static int node_create(sofab200_ctx* ctx, size_t n, const sof
     std::memset(&nd->prm, 0, sizeof(nd->prm));
     nd->prm.gravity[1] = -9.81; nd->prm.dt = 0.01; nd->prm.iterations = 25; nd->prm.tolerance = 1e-5; nd->prm.threshold = 1e-5;
     cudaStream_t s = ctx->stream;
+    if (d->plane) {
+        nd->has_plane = true; nd->plane = plane_dev<R>(d->plane); nd->plane_stiffness = d->plane->stiffness; nd->plane_rayleigh = d->plane_rayleigh_stiffness;
+        SB_TRY(nd->plane_contacts.alloc(n)); SB_TRY(nd->plane_contacts.zero(s));
+    }
     if (d->uniform_mass) {
         nd->has_mass = true; nd->uniform_mass = true; nd->um = d->uniform_vertex_mass;
         std::vector<R> um(n, R(d->uniform_vertex_mass));
@@ -780,7 +796,8 @@ template <class R> static int node_step_host(Node<R>* n, void* x_host, void* v_h
     SB_CUDA(cudaMemcpyAsync(n->hx.p, x_host, bytes, cudaMemcpyHostToDevice, s));
     SB_CUDA(cudaMemcpyAsync(n->hv.p, v_host, bytes, cudaMemcpyHostToDevice, n->side_stream));
     SB_CUDA(cudaEventRecord(n->side_event, n->side_stream));
-    SB_TRY(n->compute_force(n->f.p, n->hx.p));
+    if (n->has_plane) SB_CUDA(cudaStreamWaitEvent(s, n->side_event, 0));      // (the plane's damping term reads v: no overlap then)
+    SB_TRY(n->compute_force(n->f.p, n->hx.p, n->has_plane ? n->hv.p : nullptr));
     SB_CUDA(cudaStreamWaitEvent(s, n->side_event, 0));
     SB_TRY(n->step(n->hx.p, n->hv.p, true));
     SB_CUDA(cudaMemcpyAsync(x_host, n->hx.p, bytes, cudaMemcpyDeviceToHost, s));
@@ -813,6 +830,13 @@ int sofab200_node_get(sofab200_node* node, const char* what, void* out_host) {
     const std::string w(what);
     const void* src = nullptr;
     const size_t es = node->real == SOFAB200_F32 ? 4 : 8;
+    if (w == "plane_contacts") {   // PlaneForceField m_contacts as n bytes (1 = in contact at the last addForce)
+        const unsigned char* c = node->real == SOFAB200_F32 ? NF(node)->plane_contacts.p : ND(node)->plane_contacts.p;
+        SB_CHECK(c != nullptr, "the node has no PlaneForceField");
+        SB_CUDA(cudaMemcpyAsync(out_host, c, node->n, cudaMemcpyDeviceToHost, node->ctx->stream));
+        SB_CUDA(cudaStreamSynchronize(node->ctx->stream));
+        return SOFAB200_OK;
+    }
     if (node->real == SOFAB200_F32) { auto* n = NF(node); src = w == "f" ? n->f.p : w == "b" ? n->b.p : w == "dx" ? n->dx.p : nullptr; }
     else { auto* n = ND(node); src = w == "f" ? n->f.p : w == "b" ? n->b.p : w == "dx" ? n->dx.p : nullptr; }
     SB_CHECK(src != nullptr, "unknown vector name");

@@ -147,7 +147,7 @@ template TileDev<double> tet_tiledev<double>(sofab200_tetfem*);
 template <class R> int tet_run(sofab200_tetfem* base, bool dforce, const R* in, R k_factor, NodeEpilogue<R> ep, bool skip_gather) {
     TetFF<R>& ff = *static_cast<TetFF<R>*>(base);
     const HostPlan& plan = ff.h.plan;
-    SB_CHECK((!ep.mdx_src || ep.mdx_src == in) && (!ep.dot_with || ep.dot_with == in), "mass / dot operands must be the pass's input vector");
+    SB_CHECK((!ep.mdx_src || ep.mdx_src == in) && (!ep.dot_with || ep.dot_with == in) && (!ep.plane_mode || ep.plane_in == in), "mass / dot / plane operands must be the pass's input vector");
     TetDev<R> d = ff.dev();
     d.k_factor = k_factor;
     ep.partial_base = 0;

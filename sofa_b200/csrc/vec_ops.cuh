@@ -126,7 +126,6 @@ template <class R> __global__ void __launch_bounds__(kVecBlock) fixed_project_ke
     }
 }
 // PlaneForceField::addForce / addDForce (PlaneForceField.inl:158-226), one thread per node, the reference's operation order
-template <class R> struct PlaneDev { R nx, ny, nz, d, stiff, damp, limit2; int bilateral; };
 template <class R> __global__ void __launch_bounds__(kVecBlock) plane_add_force_kernel(size_t n, PlaneDev<R> P, R* __restrict__ f, const R* __restrict__ x, const R* __restrict__ v,
                                                                                        unsigned char* __restrict__ contacts) {
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {

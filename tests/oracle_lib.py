@@ -165,6 +165,11 @@ class OracleScene:
         m = np.ascontiguousarray(m, self.dtype)
         self.L.orc_scene_set_mass(self.h, 2, C.c_double(0), C.c_size_t(0), None, 4, _ptr(m))
 
+    def set_plane(self, prm, rayleighStiffness=0.0):
+        """PlaneForceField as the node's last force field; prm = (normal[3], d, stiffness, damping, maxForce, bilateral)."""
+        p = np.ascontiguousarray(prm, np.float64)
+        self.L.orc_scene_set_plane(self.h, _ptr(p), C.c_double(rayleighStiffness))
+
     def set_fixed(self, indices, fix_all=False):
         i = np.ascontiguousarray(indices, np.uint32)
         self.L.orc_scene_set_fixed(self.h, C.c_size_t(len(i)), _ptr(i), int(fix_all))

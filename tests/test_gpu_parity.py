@@ -97,6 +97,45 @@ def test_plane_force_field_bit_exact(dtype, case):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+def test_solver_node_with_plane_force_field(dtype):
+    """The SofaCUDA benchmark scenes' node: mass, TetrahedronFEMForceField, FixedConstraint, PlaneForceField.  The plane's addForce /
+    addDForce are fused into the epilogue of the element passes: f, b and A*p bit-identical, steps as in the plain test."""
+    import sofa_b200 as sb
+    import torch
+    from gpu_common import mesh
+    c, pos, hexas, tets, fixed = mesh("C1")
+    kw = dict(normal=(0.0, 1.0, 0.0), d=-4.0, stiffness=200.0, damping=1.0)       # the beam (y in [-5, 5]) dips below y = -4
+    prm = list(kw["normal"]) + [kw["d"], kw["stiffness"], kw["damping"], 0.0, 0.0]
+    ctx = sb.Context(0)
+    mo = sb.MechanicalObject(ctx, "B200Vec3f" if dtype == np.float32 else "B200Vec3d", position=pos)
+    ff = sb.TetrahedronFEMForceField(mo, tets, youngModulus=c["young"], poissonRatio=c["poisson"], method="large")
+    mass = sb.DiagonalMass(mo, tets, massDensity=c["density"])
+    plane = sb.PlaneForceField(mo, rayleighStiffness=0.05, **kw)
+    node = sb.SolverNode(mo, ff, mass, sb.FixedProjectiveConstraint(mo, fixed), plane=plane, dt=c["dt"], gravity=c["gravity"], rayleighStiffness=c["rK"],
+                         rayleighMass=c["rM"], iterations=c["iterations"], tolerance=c["tolerance"], threshold=c["threshold"])
+    s = oracle_scene("C1", dtype, "large")
+    s.set_plane(prm, 0.05)
+    rng = np.random.default_rng(8)
+    p = rng.standard_normal(pos.shape).astype(dtype)
+    for step in range(5):
+        mo.x.copy_(torch.from_numpy(s.get("x"))); mo.v.copy_(torch.from_numpy(s.get("v")))
+        node.step()
+        it = node.last_solve()["iterations"]
+        it_ref = s.step()
+        assert node.get("f").tobytes() == s.get("f").tobytes(), step
+        assert node.get("b").tobytes() == s.get("b").tobytes(), step
+        assert abs(it - it_ref) <= 1
+        assert rel_err(node.get("dx"), s.get("sol")) <= (1e-8 if dtype == np.float64 else 2e-4), step
+        q_d = mo.new_vector(); node.apply(q_d, dev(mo, p), 1.001, -0.01, -0.0011)      # contacts of this step's addForce
+        assert q_d.cpu().numpy().tobytes() == s.apply(p, 1.001, -0.01, -0.0011).tobytes(), step
+    assert int(plane_contacts_of(node).sum()) > 0
+
+
+def plane_contacts_of(node):
+    return node.get_plane_contacts()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("how", ["vertexMass", "totalMass"])
 def test_uniform_mass_parity(dtype, how):
     """UniformMass instead of DiagonalMass ("UniformMass equivalents"): its addMDx multiplies the MassType by the
