@@ -51,13 +51,13 @@ constexpr int kPersistNotEligible = 1;
 struct PersistLayout {
     int tiles_cached;       // tiles per CTA (1 or 2): their node tables and staged vectors stay in shared memory
     int max_touched, max_slots, max_int, max_shtouch, maxval;
-    unsigned off_slot, off_tidx, off_nrec, off_qr, off_jds, total;
+    unsigned off_slot, off_tidx, off_nrec, off_qr, off_jds, off_extra, total;   // off_extra: element-type scratch (hexahedra: cached stiffness matrices)
 };
 // static per-node data of a tile's interior nodes, kept in shared memory for the whole solve
 template <class R> struct NodeRec { uint32_t g; uint32_t val_fixed; R mass; };        // val | fixed<<16
 // ... and of the shared node a thread owns
 template <class R> struct GRec { uint32_t g; uint32_t val_fixed; uint32_t base; R mass; };
-template <class R> inline PersistLayout persist_layout(int tiles_per_cta, int max_touched, int max_slots, int max_int, int max_shtouch, int maxval) {
+template <class R> inline PersistLayout persist_layout(int tiles_per_cta, int max_touched, int max_slots, int max_int, int max_shtouch, int maxval, size_t extra_bytes = 0) {
     PersistLayout L;
     L.tiles_cached = tiles_per_cta; L.max_touched = max_touched; L.max_slots = max_slots; L.max_int = max_int; L.max_shtouch = max_shtouch; L.maxval = maxval;
     auto up = [](size_t o) { return (o + 15) & ~size_t(15); };
@@ -67,6 +67,7 @@ template <class R> inline PersistLayout persist_layout(int tiles_per_cta, int ma
     L.off_nrec = unsigned(o); o = up(o + sizeof(NodeRec<R>) * size_t(max_int) * tiles_per_cta);
     L.off_qr = unsigned(o); o = up(o + sizeof(R) * 3 * size_t(max_int) * tiles_per_cta);
     L.off_jds = unsigned(o); o = up(o + sizeof(uint16_t) * size_t(maxval + 1) * tiles_per_cta);
+    L.off_extra = unsigned(o); o = up(o + extra_bytes);
     L.total = unsigned(o);
     return L;
 }

@@ -74,6 +74,52 @@ template <class R, int MODE> static int hex_launch_mode(HexFF<R>& ff, const HexD
     return SOFAB200_OK;
 }
 
+// persistent CG kernel (see tet_fem.cu: tet_persist_variant); hexahedral tiles, 256 threads
+template <class R> int hex_cg_persistent(sofab200_hexfem* base, R k_factor, PersistCG<R> a, size_t sync_capacity, bool dry_run) {
+    HexFF<R>& ff = *static_cast<HexFF<R>*>(base);
+    HexDev<R> d = ff.dev();
+    d.k_factor = k_factor;
+    auto kern = hex_cg_persistent_kernel<R>;
+    const HostPlan& P = ff.h.plan;
+    const int threads = 256, groups = threads / kGatherChunk;
+    cudaFuncAttributes fa;
+    SB_CUDA(cudaFuncGetAttributes(&fa, kern));
+    int dev_smem_optin = 0;
+    SB_CUDA(cudaDeviceGetAttribute(&dev_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ff.ctx->device));
+    for (int tiles_per_cta = 1; tiles_per_cta <= 2; ++tiles_per_cta) {
+        const PersistLayout L = persist_layout<R>(tiles_per_cta, P.max_touched, P.max_slots, P.max_int, P.max_shtouch, P.maxval, sizeof(R) * 576 * kHexSmemMatrices);
+        if (L.total + fa.sharedSizeBytes > size_t(dev_smem_optin)) break;
+        SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<unsigned>(L.total, 1024))));
+        int per_sm = 0;
+        SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, L.total));
+        const int max_grid = per_sm * ff.ctx->sm_count;
+        if (max_grid < 1) break;
+        const int need_tiles = (P.n_tiles + tiles_per_cta - 1) / tiles_per_cta, need_chunks = (P.n_chunks + groups - 1) / groups;
+        const int grid = std::max(need_tiles, need_chunks);
+        if (grid > max_grid) continue;
+        if (size_t(3) * grid + 1 > sync_capacity) return fail(SOFAB200_ERR_INVALID, "sync buffer too small for the persistent CG kernel");
+        if (dry_run) return SOFAB200_OK;
+        a.lay = L;
+        void* args[] = {&d, &a};
+        ff.ctx->prof_start(4);
+        SB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(threads), args, L.total, ff.ctx->stream));
+        ff.ctx->prof_stop(4);
+        ff.ctx->launches++;
+        return SOFAB200_OK;
+    }
+    return kPersistNotEligible;
+}
+template int hex_cg_persistent<float>(sofab200_hexfem*, float, PersistCG<float>, size_t, bool);
+template int hex_cg_persistent<double>(sofab200_hexfem*, double, PersistCG<double>, size_t, bool);
+const std::vector<uint32_t>& hex_shared_node_table(sofab200_hexfem* base) {
+    if (base->real == SOFAB200_F32) return static_cast<HexFF<float>*>(base)->h.plan.sh_nodes;
+    return static_cast<HexFF<double>*>(base)->h.plan.sh_nodes;
+}
+size_t hex_tile_node_count(sofab200_hexfem* base) {
+    if (base->real == SOFAB200_F32) return static_cast<HexFF<float>*>(base)->h.plan.tile_nodes.size();
+    return static_cast<HexFF<double>*>(base)->h.plan.tile_nodes.size();
+}
+
 template <class R> TileDev<R> hex_tiledev(sofab200_hexfem* base) { return static_cast<HexFF<R>*>(base)->dev().t; }
 template TileDev<float> hex_tiledev<float>(sofab200_hexfem*);
 template TileDev<double> hex_tiledev<double>(sofab200_hexfem*);

@@ -5,7 +5,7 @@
 // bit-identical (all elements of a grid whose spacing is exactly representable) are stored once: the element record keeps
 // an index into a table of unique matrices, and a CTA whose tile refers to few matrices serves them from shared memory.
 #pragma once
-#include "fem_layout.cuh"
+#include "cg_persist.cuh"
 #include "math3.cuh"
 
 namespace sb {
@@ -105,26 +105,16 @@ template <class R> __host__ __device__ inline size_t hex_smem_bytes(int max_touc
     return a + sizeof(R) * 576 * kHexSmemMatrices;
 }
 
+// phase 2 of a tile: one thread per hexahedron, 8 corner contributions scattered to their slots.  The tile's (few) distinct
+// element stiffness matrices are cached in shared memory first (s_k: kHexSmemMatrices x 576 Reals); ends with no barrier.
 template <class R, int MODE>
-__global__ void __launch_bounds__(256) hex_tile_kernel(HexDev<R> d, const R* __restrict__ in, NodeEpilogue<R> ep, int max_touched, int max_slots) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double red[32];
-    __shared__ uint16_t s_jds[1024];
+__device__ __forceinline__ void hex_tile_elements(const HexDev<R>& d, int tile, const typename SVec<R>::T* s_in, R* s_slot, int max_slots, R* s_k) {
     typedef typename SVec<R>::T SV;
-    if (ep.cg && ep.cg->done) return;
-    SV* s_in = reinterpret_cast<SV*>(smem_raw);
-    size_t off = (sizeof(SV) * size_t(max_touched) + 15) & ~size_t(15);
-    R* s_slot = reinterpret_cast<R*>(smem_raw + off);
-    off = (off + sizeof(R) * 3 * size_t(max_slots) + 15) & ~size_t(15);
-    R* s_k = reinterpret_cast<R*>(smem_raw + off);   // kHexSmemMatrices x 576
-
     const TileDev<R>& t = d.t;
-    const int tile = blockIdx.x;
     const uint32_t* ku = d.tile_kuniq + size_t(tile) * (kHexSmemMatrices + 1);
     const int n_ku = int(ku[0]);
     for (int i = threadIdx.x; i < n_ku * 576; i += blockDim.x) s_k[i] = d.ktab[size_t(ku[1 + i / 576]) * 576 + i % 576];
-    tile_phase1<R>(t, tile, in, s_in, s_jds);   // ends with __syncthreads()
-
+    __syncthreads();
     const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
     for (int le = threadIdx.x; le < t.tile_e; le += blockDim.x) {
         const size_t es = size_t(tile) * t.tile_e + le;
@@ -143,12 +133,66 @@ __global__ void __launch_bounds__(256) hex_tile_kernel(HexDev<R> d, const R* __r
 #pragma unroll
         for (int w = 0; w < 8; ++w) tile_scatter<R>(t, s8[w], C[w].x, C[w].y, C[w].z, s_slot, max_slots, pol_keep);
     }
+}
+
+template <class R, int MODE>
+__global__ void __launch_bounds__(256) hex_tile_kernel(HexDev<R> d, const R* __restrict__ in, NodeEpilogue<R> ep, int max_touched, int max_slots) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[32];
+    __shared__ uint16_t s_jds[1024];
+    typedef typename SVec<R>::T SV;
+    if (ep.cg && ep.cg->done) return;
+    SV* s_in = reinterpret_cast<SV*>(smem_raw);
+    size_t off = (sizeof(SV) * size_t(max_touched) + 15) & ~size_t(15);
+    R* s_slot = reinterpret_cast<R*>(smem_raw + off);
+    off = (off + sizeof(R) * 3 * size_t(max_slots) + 15) & ~size_t(15);
+    R* s_k = reinterpret_cast<R*>(smem_raw + off);   // kHexSmemMatrices x 576
+
+    const TileDev<R>& t = d.t;
+    const int tile = blockIdx.x;
+    tile_phase1<R>(t, tile, in, s_in, s_jds);   // ends with __syncthreads()
+    hex_tile_elements<R, MODE>(d, tile, s_in, s_slot, max_slots, s_k);
     __syncthreads();
     const double part = tile_phase3<R>(t, tile, ep, s_in, s_slot, max_slots, s_jds);
     if (ep.dot_kind != DOT_NONE) {
         const double tot = block_sum(part, red);
         finish_dot(ep, tot, red, false);
     }
+}
+
+// The whole CG loop in one persistent cooperative kernel: same skeleton as tet_cg_persistent_kernel (cg_persist.cuh), with the
+// hexahedral element pass.
+template <class R>
+__global__ void __launch_bounds__(256) hex_cg_persistent_kernel(HexDev<R> d, PersistCG<R> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[32];
+    __shared__ double bcast;
+    __shared__ GRec<R> s_grec[256];
+    typedef typename SVec<R>::T SV;
+    CGDev* cg = a.cg;
+    if (cg->done) return;
+    const TileDev<R>& t = d.t;
+    const PersistLayout& L = a.lay;
+    SV* s_in = reinterpret_cast<SV*>(smem_raw);
+    R* s_slot = reinterpret_cast<R*>(smem_raw + L.off_slot);
+    R* s_k = reinterpret_cast<R*>(smem_raw + L.off_extra);
+    PersistState<R> st(a);
+    persist_load_tables<R>(t, a, smem_raw, s_grec);
+    if (!persist_init<R>(a, st, red, &bcast)) { persist_finish<R>(t, a, st, smem_raw, s_grec); return; }
+    for (;;) {
+        persist_phase1<R>(t, a, st, smem_raw);
+        double part = 0.0;
+        for (int c = 0; c < L.tiles_cached; ++c) {
+            const int tile = blockIdx.x + c * gridDim.x;
+            if (tile >= t.n_tiles) break;
+            hex_tile_elements<R, HM_DF>(d, tile, s_in + c * L.max_touched, s_slot, L.max_slots, s_k);
+            __syncthreads();
+            part += persist_phase3<R>(t, tile, c, a, smem_raw);
+            __syncthreads();
+        }
+        if (!persist_rest<R>(t, a, st, part, red, &bcast, smem_raw, s_grec)) break;
+    }
+    persist_finish<R>(t, a, st, smem_raw, s_grec);
 }
 
 template <class R> __global__ void hex_export_rotations_kernel(HexDev<R> d, const uint32_t* __restrict__ orig, R* __restrict__ out) {

@@ -20,6 +20,8 @@ template <class R> TileDev<R> tet_tiledev(sofab200_tetfem* ff);
 template <class R> TileDev<R> hex_tiledev(sofab200_hexfem* ff);
 int tet_partial_count(sofab200_tetfem* ff);
 template <class R> int hex_run(sofab200_hexfem* ff, bool dforce, const R* in, R k_factor, NodeEpilogue<R> ep, bool skip_gather);
+template <class R> int hex_cg_persistent(sofab200_hexfem* ff, R k_factor, PersistCG<R> a, size_t sync_capacity, bool dry_run);
+size_t hex_tile_node_count(sofab200_hexfem* ff);
 int hex_partial_count(sofab200_hexfem* ff);
 int tet_real(sofab200_tetfem* ff); size_t tet_nodes(sofab200_tetfem* ff);
 int hex_real(sofab200_hexfem* ff); size_t hex_nodes(sofab200_hexfem* ff);
@@ -216,7 +218,7 @@ template <class R> struct Node : sofab200_node {
         const double kf = k + bfac * prm.ff_rayleigh_stiffness;
         const size_t n3 = 3 * n;
         if (!ps0.p) { SB_TRY(ps0.alloc(n)); SB_TRY(ps1.alloc(n)); SB_TRY(rs.alloc(n)); }
-        const size_t n_tile_nodes = tet_tile_node_count(tet);
+        const size_t n_tile_nodes = tet ? tet_tile_node_count(tet) : hex_tile_node_count(hex);
         if (xt.n < n_tile_nodes) { SB_TRY(xt.alloc(n_tile_nodes)); SB_TRY(rt.alloc(n_tile_nodes)); }
         if (!gstate.p) SB_TRY(gstate.alloc(size_t(9) * ctx->sm_count * 2048));
         if (!sync_slots.p) SB_TRY(sync_slots.alloc(3 * 2048 + 8));
@@ -225,7 +227,7 @@ template <class R> struct Node : sofab200_node {
         a.x = x; a.r = r.p; a.b = bvec; a.xt = xt.p; a.rt = rt.p; a.gstate = gstate.p; a.p0 = ps0.p; a.p1 = ps1.p; a.rs = rs.p; a.n3 = n3; a.cg = cg.p; a.sync = sync_slots.p;
         if (pd) a.peer = *pd; else std::memset(&a.peer, 0, sizeof(a.peer));
         SB_CUDA(cudaMemsetAsync(sync_slots.p, 0, sync_slots.n * sizeof(unsigned long long), ctx->stream));
-        const int rc = tet_cg_persistent<R>(tet, R(kf), a, sync_slots.n - 8, false);
+        const int rc = tet ? tet_cg_persistent<R>(tet, R(kf), a, sync_slots.n - 8, false) : hex_cg_persistent<R>(hex, R(kf), a, sync_slots.n - 8, false);
         if (rc == SOFAB200_OK) ctx->launches++;
         return rc;
     }
@@ -321,7 +323,7 @@ template <class R> struct Node : sofab200_node {
             return SOFAB200_OK;
         }
         const double kf_chk = k + bfac * prm.ff_rayleigh_stiffness;
-        if (persistent && tet && (kf_chk != 0.0 || bfac != 0.0)) {
+        if (persistent && (kf_chk != 0.0 || bfac != 0.0)) {
             const int rc = launch_persistent(x, bvec, m, bfac, k, nullptr);     // (|b| and the first rho included)
             if (rc == SOFAB200_OK) { LAUNCH(ctx, cg_end_kernel, 1, 1, cg.p); return SOFAB200_OK; }
             if (rc != kPersistNotEligible) return rc;
