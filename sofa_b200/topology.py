@@ -139,6 +139,52 @@ def read_gmsh_v1(path):
     return pos, np.array(tets, np.uint32).reshape(-1, 4), np.array(hexas, np.uint32).reshape(-1, 8)
 
 
+def read_gmsh_v2(path):
+    """Gmsh file format 2.x, ASCII ($MeshFormat 2.* / $Nodes / $Elements: "id type ntags tags... nodes...") -> (positions,
+    tetrahedra, hexahedra), the subset MeshGmshLoader feeds this path (Sofa/Component/IO/Mesh/src/sofa/component/io/mesh/MeshGmshLoader.cpp:60-100,
+    element types 4 = tetrahedron, 5 = hexahedron)."""
+    with open(path) as fh:
+        tok = fh.read().split()
+    i = tok.index("$MeshFormat") + 1
+    if int(float(tok[i])) != 2 or int(tok[i + 1]) != 0:
+        raise ValueError(f"{path}: only ASCII MSH 2.x is read here (header: {tok[i]} {tok[i + 1]})")
+    i = tok.index("$Nodes") + 1
+    n = int(tok[i]); i += 1
+    ids = {}
+    pos = np.empty((n, 3), np.float64)
+    for k in range(n):
+        ids[int(tok[i])] = k
+        pos[k] = [float(tok[i + 1]), float(tok[i + 2]), float(tok[i + 3])]
+        i += 4
+    i = tok.index("$Elements") + 1
+    ne = int(tok[i]); i += 1
+    nnodes_of = {1: 2, 2: 3, 3: 4, 4: 4, 5: 8, 6: 6, 7: 5, 15: 1}
+    tets, hexas = [], []
+    for _ in range(ne):
+        etype, ntags = int(tok[i + 1]), int(tok[i + 2])
+        if etype not in nnodes_of:
+            raise ValueError(f"{path}: element type {etype} is not supported")
+        nn = nnodes_of[etype]
+        nodes = [ids[int(v)] for v in tok[i + 3 + ntags:i + 3 + ntags + nn]]
+        if etype == 4:
+            tets.append(nodes)
+        elif etype == 5:
+            hexas.append(nodes)
+        i += 3 + ntags + nn
+    return pos, np.array(tets, np.uint32).reshape(-1, 4), np.array(hexas, np.uint32).reshape(-1, 8)
+
+
+def read_gmsh(path):
+    """Gmsh .msh, format 1.0 or 2.x (ASCII), chosen by the first keyword like MeshGmshLoader does."""
+    with open(path) as fh:
+        first = fh.readline().strip()
+    if first.startswith("$MeshFormat"):
+        return read_gmsh_v2(path)
+    if first.startswith("$NOD"):
+        return read_gmsh_v1(path)
+    raise ValueError(f"{path}: neither $MeshFormat nor $NOD at the top: not a registered MSH format")
+
+
 # ---------------------------------------------------------------------------------------------------
 # WriteState / ReadState text dumps (Sofa/Component/Playback/src/sofa/component/playback/WriteState.inl:350-381,
 # ReadState.inl:219-262): one block per exported time, "T= <time>" then "  X= x0 y0 z0 x1 ...", "  V= ...", optionally "  F= ...",

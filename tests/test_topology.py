@@ -69,3 +69,19 @@ def test_write_state_read_state_round_trip(tmp_path):
     T.write_state(p, frames)                           # the reference's default stream precision: 6 significant digits
     back = T.read_state(p)
     assert np.allclose(back[1]["X"], frames[1]["X"], rtol=1e-5, atol=1e-6)
+
+
+def test_gmsh_v2_reader_matches_v1(tmp_path):
+    """The same small mesh written as MSH 1.0 and as MSH 2.2 (with tags, a surface triangle and a point element to skip)."""
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 1]], float)
+    tets = [[1, 2, 3, 4], [2, 3, 4, 5]]
+    v1 = tmp_path / "m1.msh"
+    v1.write_text("$NOD\n5\n" + "".join(f"{i + 1} {float(p[0])!r} {float(p[1])!r} {float(p[2])!r}\n" for i, p in enumerate(pos)) + "$ENDNOD\n$ELM\n2\n"
+                  + "".join(f"{i + 1} 4 1 1 4 {t[0]} {t[1]} {t[2]} {t[3]}\n" for i, t in enumerate(tets)) + "$ENDELM\n")
+    v2 = tmp_path / "m2.msh"
+    v2.write_text("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n5\n" + "".join(f"{i + 1} {float(p[0])!r} {float(p[1])!r} {float(p[2])!r}\n" for i, p in enumerate(pos))
+                  + "$EndNodes\n$Elements\n4\n1 15 2 0 1 1\n2 2 2 0 1 1 2 3\n"
+                  + "".join(f"{i + 3} 4 2 0 1 {t[0]} {t[1]} {t[2]} {t[3]}\n" for i, t in enumerate(tets)) + "$EndElements\n")
+    p1, t1, h1 = T.read_gmsh(v1)
+    p2, t2, h2 = T.read_gmsh(v2)
+    assert (p1 == p2).all() and (t1 == t2).all() and t1.tolist() == [[0, 1, 2, 3], [1, 2, 3, 4]] and h1.shape == (0, 8) and h2.shape == (0, 8)
