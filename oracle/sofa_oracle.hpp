@@ -927,7 +927,8 @@ template <class R> struct DiagonalMass {
     R massDensity = 1;
     R totalMass = 0;
     // UniformMass (Sofa/Component/Mass/src/sofa/component/mass/UniformMass.inl): one MassType for every node.  Kept in the same
-    // struct because the solver node holds exactly one mass component.
+    // struct because the solver node holds exactly one mass component.  PARITY UNPINNED by reference vectors (no numerical KAT
+    // for its addMDx / addForce in the reference tree).
     bool uniform = false;
     R uniformVertexMass = 0;    // d_vertexMass of UniformMass
     void initUniformFromVertexMass(R m, size_t n) { uniform = true; uniformVertexMass = m; vertexMass.assign(n, m); totalMass = R(double(m) * double(n)); }   // :300-309
@@ -1008,6 +1009,8 @@ template <class R> struct DiagonalMass {
 
 // PlaneForceField  Sofa/Component/MechanicalLoad/src/sofa/component/mechanicalload/PlaneForceField.inl
 // (present in every SofaCUDA FEM benchmark scene).  setPlane :139-145, addForce :158-205, addDForce :208-226.
+// PARITY UNPINNED by reference vectors: the reference tree holds no numerical KAT for this class, only the behaviour test
+// MechanicalLoad/tests/PlaneForceField_test.cpp (reproduced in tests/test_oracle_golden.py).
 template <class R> struct PlaneForceField {
     Vec3<R> planeNormal = Vec3<R>(0, 1, 0);
     R planeD = 0, stiffness = 500, damping = 5, maxForce = 0;

@@ -161,3 +161,22 @@ def test_plane_force_field_restatement_properties():
     same = (c == c2)
     df = O.plane_add_dforce(np.float64, prm, np.zeros_like(x), dx, c, 1.0)
     assert np.allclose((f2 - f)[same], df[same], rtol=1e-6, atol=1e-12)
+
+
+def test_reference_plane_force_field_test_scene():
+    """The reference's own behaviour test for PlaneForceField + UniformMass (MechanicalLoad/tests/PlaneForceField_test.cpp:118-171,322-339):
+    one particle at x = 1, UniformMass totalMass = 1, gravity (-9.8, 0, 0), plane normal (1, 0, 0) d = 0 with the default stiffness 500 /
+    damping 5, EulerImplicitSolver + CGLinearSolver(25, 1e-5, 1e-5), 100 steps of 0.01: the particle must not have crossed the plane by
+    more than 0.1."""
+    for dtype in (np.float64, np.float32):
+        s = O.OracleScene(dtype, np.array([[1.0, 0.0, 0.0]]))
+        s.set_params(gravity=(-9.8, 0.0, 0.0), dt=0.01, iterations=25, tolerance=1e-5, threshold=1e-5)
+        s.set_uniform_mass(totalMass=1.0)
+        s.set_plane([1.0, 0.0, 0.0, 0.0, 500.0, 5.0, 0.0, 0.0])
+        xs = []
+        for _ in range(100):
+            s.step()
+            xs.append(float(s.get("x")[0, 0]))
+        assert min(xs) < 0.05            # it did fall down to the plane ...
+        assert xs[-1] >= -0.1            # ... and was sent back by it: the reference's criterion on the position after 100 steps
+        assert min(xs) > -0.5 and xs[-1] > 0.0
