@@ -264,8 +264,11 @@ __global__ void __launch_bounds__(MAXT) tet_cg_persistent_kernel(TetDev<R> d, Pe
     SV* s_in = reinterpret_cast<SV*>(smem_raw);
     R* s_slot = reinterpret_cast<R*>(smem_raw + L.off_slot);
     PersistState<R> st(a);
+    trace_mark(a.ep.trace, kTraceTail, 8);
     persist_load_tables<R>(t, a, smem_raw, s_grec);
+    trace_mark(a.ep.trace, kTraceTail, 9);
     if (!persist_init<R>(a, st, red, &bcast)) { persist_finish<R>(t, a, st, smem_raw, s_grec); return; }
+    trace_mark(a.ep.trace, kTraceTail, 10);
     for (;;) {
         trace_mark(a.ep.trace, kTraceTail, 0);
         // ---- [A]
@@ -285,6 +288,7 @@ __global__ void __launch_bounds__(MAXT) tet_cg_persistent_kernel(TetDev<R> d, Pe
         if (!persist_rest<R>(t, a, st, part, red, &bcast, smem_raw, s_grec)) break;
     }
     persist_finish<R>(t, a, st, smem_raw, s_grec);
+    trace_mark(a.ep.trace, kTraceTail, 11);
 }
 
 // rotations[e] back in ORIGINAL element order (getRotations-style accessors, parity checks)

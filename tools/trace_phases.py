@@ -66,6 +66,8 @@ if s:
     us = lambda a, b: round(float(np.median(tl[:, b] - tl[:, a])) / 1000.0, 2)
     res["cg_persistent_last_iteration"]["detail_us"] = {
         "p-update + staging (all tiles of the CTA)": us(0, 12), "first tile: elements": us(12, 13), "first tile: interior sums": us(13, 14)}
+    res["cg_persistent_kernel"] = {"node tables -> shared memory": us(8, 9), "|b| and first rho (two grid syncs)": us(9, 10),
+                                   "kernel start -> kernel end (median CTA)": us(8, 11), "x written back after the last sync": us(6, 11)}
 print(json.dumps(res, indent=1))
 if args.out:
     np.savez_compressed(args.out, tile=tile, tail=tail)
