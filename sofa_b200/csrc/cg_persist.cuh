@@ -18,6 +18,13 @@ template <class R> __device__ __forceinline__ double xr_one(R& x, R& r, R p, R q
     if (ma_one) r += q; else r += q * malpha;
     return double(r) * double(r);
 }
+template <class R> __device__ __forceinline__ double r_one(R& r, R q, R malpha, bool ma_one) {
+    if (ma_one) r += q; else r += q * malpha;
+    return double(r) * double(r);
+}
+template <class R> __device__ __forceinline__ void x_one(R& x, R p, R alpha, bool a_one) {
+    if (a_one) x += p; else x += p * alpha;      // vOp takes `r += b` when k == 1
+}
 __device__ __forceinline__ double xr_vec(float4& x, float4& r, const float4& p, const float4& q, float alpha, float malpha, bool a_one, bool ma_one) {
     double s = xr_one<float>(x.x, r.x, p.x, q.x, alpha, malpha, a_one, ma_one);
     s += xr_one<float>(x.y, r.y, p.y, q.y, alpha, malpha, a_one, ma_one);
@@ -123,33 +130,39 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// arrive + wait, no value
-__device__ __forceinline__ void grid_sync(unsigned long long* slots, unsigned& s) {
+// The barrier in two halves, so that work which nobody else waits for can run between them:
+//   grid_arrive  -- everything the CTA wrote so far is released (and, with a value, the CTA's term of the sum is posted)
+//   grid_wait    -- returns once every CTA has arrived; what they wrote before arriving is visible to all threads
+// (`who`: the thread that releases -- its warp stalls in the fence until the CTA's stores have drained, so a caller with more
+// work ahead picks a warp that has the least of it)
+__device__ __forceinline__ void grid_arrive(unsigned long long* slots, unsigned s, unsigned who = 0u) {
     const unsigned G = gridDim.x;
     unsigned* counter = reinterpret_cast<unsigned*>(slots + size_t(3) * G);
-    __syncthreads();                       // the CTA's writes precede thread 0's release
+    (void)s;
+    __syncthreads();                       // the CTA's writes precede the release
+    if (threadIdx.x == who) { __threadfence(); atomicAdd(counter, 1u); }
+}
+__device__ __forceinline__ void grid_arrive_value(unsigned long long* slots, unsigned s, double cta_value /* thread 0 */) {
+    const unsigned G = gridDim.x;
+    double* cur = reinterpret_cast<double*>(slots) + size_t(s % 3) * G;
+    unsigned* counter = reinterpret_cast<unsigned*>(slots + size_t(3) * G);
+    __syncthreads();
+    if (threadIdx.x == 0) { cur[blockIdx.x] = cta_value; __threadfence(); atomicAdd(counter, 1u); }
+}
+__device__ __forceinline__ void grid_wait(unsigned long long* slots, unsigned& s) {
+    const unsigned G = gridDim.x;
+    const unsigned* counter = reinterpret_cast<const unsigned*>(slots + size_t(3) * G);
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
         const unsigned target = (s + 1) * G;
         while (ld_acquire_u32(counter) < target) { }
     }
     __syncthreads();                       // thread 0's acquire precedes every thread's later reads
     ++s;
 }
-__device__ __forceinline__ double grid_sync_sum(unsigned long long* slots, unsigned& s, double cta_value /* thread 0 */, double* red, double* bcast) {
+__device__ __forceinline__ double grid_wait_sum(unsigned long long* slots, unsigned& s, double* bcast) {
     const unsigned G = gridDim.x;
-    double* cur = reinterpret_cast<double*>(slots) + size_t(s % 3) * G;
-    unsigned* counter = reinterpret_cast<unsigned*>(slots + size_t(3) * G);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        cur[blockIdx.x] = cta_value;
-        __threadfence();
-        atomicAdd(counter, 1u);
-        const unsigned target = (s + 1) * G;
-        while (ld_acquire_u32(counter) < target) { }
-    }
-    __syncthreads();
+    const double* cur = reinterpret_cast<const double*>(slots) + size_t(s % 3) * G;
+    grid_wait(slots, s);
     // warp 0 adds the G values in a fixed order and broadcasts
     if (threadIdx.x < 32) {
         double v = 0.0;
@@ -159,8 +172,17 @@ __device__ __forceinline__ double grid_sync_sum(unsigned long long* slots, unsig
         if (threadIdx.x == 0) *bcast = v;
     }
     __syncthreads();
-    ++s;
     return *bcast;
+}
+// arrive + wait, no value
+__device__ __forceinline__ void grid_sync(unsigned long long* slots, unsigned& s) {
+    grid_arrive(slots, s);
+    grid_wait(slots, s);
+}
+__device__ __forceinline__ double grid_sync_sum(unsigned long long* slots, unsigned& s, double cta_value /* thread 0 */, double* red, double* bcast) {
+    (void)red;
+    grid_arrive_value(slots, s, cta_value);
+    return grid_wait_sum(slots, s, bcast);
 }
 
 // ---- grid sync that also crosses the GPUs (multi-GPU mode) ------------------------------------------------------------------
@@ -293,6 +315,9 @@ __device__ __forceinline__ SVec<double>::T sv_ldcg(const SVec<double>::T* p) {
 // p = p*beta + r  (cgstep_beta -> vOp_avf, CGLinearSolver.inl:184-197), one component
 template <class R> __device__ __forceinline__ R p_update(R p, R beta, R r) { p *= beta; p += r; return p; }
 
+// Chunks of shared nodes are dealt to the CTAs round-robin (group g of CTA b sums chunk g * gridDim.x + b), so that every CTA gets
+// n_chunks / gridDim.x of them, give or take one: with consecutive chunks per CTA the last CTAs of the grid would have none.
+__device__ __forceinline__ int persist_chunk_of_thread() { return int(threadIdx.x / kGatherChunk) * int(gridDim.x) + int(blockIdx.x); }
 // once per solve: the node tables of the CTA's tiles and of the thread's shared node go to shared memory
 template <class R> __device__ __forceinline__ void persist_load_tables(const TileDev<R>& t, const PersistCG<R>& a, unsigned char* smem_raw, GRec<R>* s_grec) {
     const PersistLayout& L = a.lay;
@@ -312,8 +337,8 @@ template <class R> __device__ __forceinline__ void persist_load_tables(const Til
         }
         for (int j = threadIdx.x; j <= t.maxval; j += blockDim.x) s_jds[c * (L.maxval + 1) + j] = t.tile_jds[size_t(tile) * (t.maxval + 1) + j];
     }
-    // the thread's shared node: chunk = blockIdx.x * groups + threadIdx.x / kGatherChunk (one round: checked by the host)
-    const int chunk = blockIdx.x * (blockDim.x / kGatherChunk) + threadIdx.x / kGatherChunk, k = threadIdx.x % kGatherChunk;
+    // the thread's shared node (one round: checked by the host)
+    const int chunk = persist_chunk_of_thread(), k = threadIdx.x % kGatherChunk;
     GRec<R> rec{0xFFFFFFFFu, 0u, 0u, R(0)};
     if (chunk < t.n_chunks) {
         const uint32_t g = t.sh_nodes[size_t(chunk) * kGatherChunk + k];
@@ -333,29 +358,68 @@ template <class R> __device__ __forceinline__ void persist_phase1(const TileDev<
     const uint32_t* s_tidx = reinterpret_cast<const uint32_t*>(smem_raw + L.off_tidx);
     const NodeRec<R>* s_nrec = reinterpret_cast<const NodeRec<R>*>(smem_raw + L.off_nrec);
     const R* s_qr = reinterpret_cast<const R*>(smem_raw + L.off_qr);
-    for (int c = 0; c < L.tiles_cached; ++c) {
-        const int tile = blockIdx.x + c * gridDim.x;
-        if (tile >= t.n_tiles) break;
-        const int n_touched = int(t.tile_node_off[tile + 1] - t.tile_node_off[tile]), n_int = int(t.tile_nint[tile]);
-        for (int k = threadIdx.x; k < n_touched; k += blockDim.x) {
-            R p0, p1, p2;
-            if (k < n_int) {
-                if (st.first) { const R* r = a.r + 3 * size_t(s_nrec[c * L.max_int + k].g); p0 = r[0]; p1 = r[1]; p2 = r[2]; }
-                else {
-                    const SV po = s_in[c * L.max_touched + k];
-                    const R* rn = s_qr + 3 * size_t(c * L.max_int + k);
-                    p0 = p_update<R>(R(po.x), st.beta, rn[0]); p1 = p_update<R>(R(po.y), st.beta, rn[1]); p2 = p_update<R>(R(po.z), st.beta, rn[2]);
-                }
-            } else {
-                const size_t g = s_tidx[c * L.max_shtouch + (k - n_int)];
-                if (st.first) { p0 = __ldcg(a.r + 3 * g); p1 = __ldcg(a.r + 3 * g + 1); p2 = __ldcg(a.r + 3 * g + 2); }
-                else {
-                    const SV rv = sv_ldcg(a.rs + g), po = sv_ldcg(st.pold + g);
-                    p0 = p_update<R>(R(po.x), st.beta, R(rv.x)); p1 = p_update<R>(R(po.y), st.beta, R(rv.y)); p2 = p_update<R>(R(po.z), st.beta, R(rv.z));
+    // one node: interior (k < n_int) from shared memory, shared from the owners' p_old and r (rv, po: requested by the caller)
+    auto one = [&](int c, int k, int n_int, const SV& rv, const SV& po_sh) {
+        R p0, p1, p2;
+        if (k < n_int) {
+            const SV po = s_in[c * L.max_touched + k];
+            const R* rn = s_qr + 3 * size_t(c * L.max_int + k);
+            p0 = p_update<R>(R(po.x), st.beta, rn[0]); p1 = p_update<R>(R(po.y), st.beta, rn[1]); p2 = p_update<R>(R(po.z), st.beta, rn[2]);
+        } else {
+            p0 = p_update<R>(R(po_sh.x), st.beta, R(rv.x)); p1 = p_update<R>(R(po_sh.y), st.beta, R(rv.y)); p2 = p_update<R>(R(po_sh.z), st.beta, R(rv.z));
+        }
+        s_in[c * L.max_touched + k] = SVec<R>::make(p0, p1, p2);
+    };
+    if (st.first) {
+        for (int c = 0; c < L.tiles_cached; ++c) {
+            const int tile = blockIdx.x + c * gridDim.x;
+            if (tile >= t.n_tiles) break;
+            const int n_touched = int(t.tile_node_off[tile + 1] - t.tile_node_off[tile]), n_int = int(t.tile_nint[tile]);
+            for (int k = threadIdx.x; k < n_touched; k += blockDim.x) {
+                const size_t g = k < n_int ? size_t(s_nrec[c * L.max_int + k].g) : size_t(s_tidx[c * L.max_shtouch + (k - n_int)]);
+                s_in[c * L.max_touched + k] = SVec<R>::make(__ldcg(a.r + 3 * g), __ldcg(a.r + 3 * g + 1), __ldcg(a.r + 3 * g + 2));
+            }
+        }
+    } else {
+        // The p_old / r of the shared nodes come out of L2: all the requests of a thread (two tiles x two rounds) are issued
+        // before the first is used, so the phase pays one L2 round trip instead of four.
+        constexpr int kTiles = 2, kRounds = 2;
+        SV rv[kTiles][kRounds], po[kTiles][kRounds];
+        int n_touched[kTiles], n_int[kTiles];
+#pragma unroll
+        for (int c = 0; c < kTiles; ++c)
+#pragma unroll
+            for (int u = 0; u < kRounds; ++u) { rv[c][u] = SVec<R>::make(R(0), R(0), R(0)); po[c][u] = rv[c][u]; }
+#pragma unroll
+        for (int c = 0; c < kTiles; ++c) {
+            const int tile = blockIdx.x + c * gridDim.x;
+            const bool on = c < L.tiles_cached && tile < t.n_tiles;
+            n_touched[c] = on ? int(t.tile_node_off[tile + 1] - t.tile_node_off[tile]) : 0;
+            n_int[c] = on ? int(t.tile_nint[tile]) : 0;
+        }
+#pragma unroll
+        for (int c = 0; c < kTiles; ++c)
+#pragma unroll
+            for (int u = 0; u < kRounds; ++u) {
+                const int k = threadIdx.x + u * blockDim.x;
+                if (k >= n_int[c] && k < n_touched[c]) {
+                    const size_t g = s_tidx[c * L.max_shtouch + (k - n_int[c])];
+                    rv[c][u] = sv_ldcg(a.rs + g); po[c][u] = sv_ldcg(st.pold + g);
                 }
             }
-            s_in[c * L.max_touched + k] = SVec<R>::make(p0, p1, p2);
-        }
+#pragma unroll
+        for (int c = 0; c < kTiles; ++c)
+#pragma unroll
+            for (int u = 0; u < kRounds; ++u) {
+                const int k = threadIdx.x + u * blockDim.x;
+                if (k < n_touched[c]) one(c, k, n_int[c], rv[c][u], po[c][u]);
+            }
+        for (int c = 0; c < kTiles; ++c)
+            for (int k = threadIdx.x + kRounds * blockDim.x; k < n_touched[c]; k += blockDim.x) {
+                SV r1 = SVec<R>::make(R(0), R(0), R(0)), p1 = r1;
+                if (k >= n_int[c]) { const size_t g = s_tidx[c * L.max_shtouch + (k - n_int[c])]; r1 = sv_ldcg(a.rs + g); p1 = sv_ldcg(st.pold + g); }
+                one(c, k, n_int[c], r1, p1);
+            }
     }
     __syncthreads();
 }
@@ -407,8 +471,9 @@ template <class R> __device__ __forceinline__ double persist_phase3(const TileDe
 
 // Everything of an iteration after the tiles: returns false when the solve is over.  `part`: this thread's share of
 // p.q over the interior nodes of the CTA's tiles.
+// `arrived`: the CTA has already arrived at the staging barrier (during its last tile); only the wait is left.
 template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>& t, const PersistCG<R>& a, PersistState<R>& st, double part, double* red, double* bcast,
-                                                                unsigned char* smem_raw, const GRec<R>* s_grec) {
+                                                                unsigned char* smem_raw, const GRec<R>* s_grec, bool arrived = false) {
     typedef typename SVec<R>::T SV;
     CGDev* cg = a.cg;
     const NodeEpilogue<R>& ep = a.ep;
@@ -421,7 +486,7 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
     const size_t gs_n = size_t(gridDim.x) * blockDim.x, gs_i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const PeerDev<R>& P = a.peer;
     // multi-GPU: is the node on the partition interface (row of the halo tables), and does this rank count it in dot products
-    const int if_row = (P.enabled && has_node) ? P.sh_if_row[gs_i] : -1;
+    const int if_row = (P.enabled && has_node) ? P.sh_if_row[size_t(persist_chunk_of_thread()) * kGatherChunk + threadIdx.x % kGatherChunk] : -1;
     const bool counted = if_row < 0 || P.owned[grec.g] != 0;
     R gp0 = R(0), gp1 = R(0), gp2 = R(0), gr0 = R(0), gr1 = R(0), gr2 = R(0);
     if (has_node) {
@@ -434,7 +499,8 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
         st.pnew[grec.g] = SVec<R>::make(gp0, gp1, gp2);               // for the tiles that touch the node, next iteration
     }
     trace_mark(ep.trace, kTraceTail, 1);
-    grid_sync(a.sync, st.sync_count);                  // staged contributions are complete
+    if (!arrived) grid_arrive(a.sync, st.sync_count);
+    grid_wait(a.sync, st.sync_count);                  // staged contributions are complete
     trace_mark(ep.trace, kTraceTail, 2);
     double part2 = part;                               // p.q of the interior nodes + (below) of the thread's shared node
     R gq0 = R(0), gq1 = R(0), gq2 = R(0);
@@ -501,49 +567,104 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
     const R alpha = R(alpha_d), malpha = R(-alpha_d);
     const bool a_one = (alpha_d == 1.0), ma_one = (-alpha_d == 1.0);
     double prr = prr_poison ? __longlong_as_double(0x7FF8000000000001ll) : 0.0;    // a lost halo row fails the solve on every rank through the next all-reduce
+    // The r half of the update comes first: rho = r.r is what the other CTAs wait for.  The x half (nobody reads x before the
+    // solve ends) runs between the arrival at the rho sync and the wait, under the barrier's latency.
+    if (has_node) {
+        double own = r_one<R>(gr0, gq0, malpha, ma_one);
+        own += r_one<R>(gr1, gq1, malpha, ma_one);
+        own += r_one<R>(gr2, gq2, malpha, ma_one);
+        if (counted) prr += own;
+        a.rs[grec.g] = SVec<R>::make(gr0, gr1, gr2);                           // for the tiles that touch the node
+    }
+    constexpr int kTiles = 2, kRounds = 2;
+    int n_int[kTiles]; uint32_t node_off[kTiles];
+#pragma unroll
+    for (int c = 0; c < kTiles; ++c) {
+        const int tile = blockIdx.x + c * gridDim.x;
+        const bool on = c < L.tiles_cached && tile < t.n_tiles;
+        n_int[c] = on ? int(t.tile_nint[tile]) : 0;
+        node_off[c] = on ? t.tile_node_off[tile] : 0u;
+    }
+    auto r_node = [&](int c, int k, R r0, R r1, R r2) {
+        R* q = s_qr + 3 * size_t(c * L.max_int + k);
+        prr += r_one<R>(r0, q[0], malpha, ma_one);
+        prr += r_one<R>(r1, q[1], malpha, ma_one);
+        prr += r_one<R>(r2, q[2], malpha, ma_one);
+        a.rt[node_off[c] + k] = SVec<R>::make(r0, r1, r2);
+        q[0] = r0; q[1] = r1; q[2] = r2;
+    };
+    auto x_node = [&](int c, int k, R x0, R x1, R x2) {
+        const SV pv = s_in[c * L.max_touched + k];
+        x_one<R>(x0, R(pv.x), alpha, a_one); x_one<R>(x1, R(pv.y), alpha, a_one); x_one<R>(x2, R(pv.z), alpha, a_one);
+        a.xt[node_off[c] + k] = SVec<R>::make(x0, x1, x2);
+    };
+    if (st.first) {
+        for (int c = 0; c < kTiles; ++c)
+            for (int k = threadIdx.x; k < n_int[c]; k += blockDim.x) {
+                const size_t g3 = 3 * size_t(s_nrec[c * L.max_int + k].g);
+                r_node(c, k, a.r[g3], a.r[g3 + 1], a.r[g3 + 2]);
+            }
+    } else {
+        SV rv[kTiles][kRounds];
+#pragma unroll
+        for (int c = 0; c < kTiles; ++c)
+#pragma unroll
+            for (int u = 0; u < kRounds; ++u) {
+                const int k = threadIdx.x + u * blockDim.x;
+                rv[c][u] = k < n_int[c] ? a.rt[node_off[c] + k] : SVec<R>::make(R(0), R(0), R(0));
+            }
+#pragma unroll
+        for (int c = 0; c < kTiles; ++c)
+#pragma unroll
+            for (int u = 0; u < kRounds; ++u) {
+                const int k = threadIdx.x + u * blockDim.x;
+                if (k < n_int[c]) r_node(c, k, R(rv[c][u].x), R(rv[c][u].y), R(rv[c][u].z));
+            }
+        for (int c = 0; c < kTiles; ++c)
+            for (int k = threadIdx.x + kRounds * blockDim.x; k < n_int[c]; k += blockDim.x) { const SV v = a.rt[node_off[c] + k]; r_node(c, k, R(v.x), R(v.y), R(v.z)); }
+    }
+    __syncthreads();
+    prr = block_sum(prr, red);
+    trace_mark(ep.trace, kTraceTail, 5);
+    if (!P.enabled) grid_arrive_value(a.sync, st.sync_count, prr);
+    // ---- x += alpha p (owners only; private data, needs no release)
     if (has_node) {
         const size_t g3 = 3 * size_t(grec.g);
         R gx0, gx1, gx2;
         if (st.first) { gx0 = a.x[g3]; gx1 = a.x[g3 + 1]; gx2 = a.x[g3 + 2]; }
         else { gx0 = a.gstate[6 * gs_n + gs_i]; gx1 = a.gstate[7 * gs_n + gs_i]; gx2 = a.gstate[8 * gs_n + gs_i]; }
-        double own = xr_one<R>(gx0, gr0, gp0, gq0, alpha, malpha, a_one, ma_one);
-        own += xr_one<R>(gx1, gr1, gp1, gq1, alpha, malpha, a_one, ma_one);
-        own += xr_one<R>(gx2, gr2, gp2, gq2, alpha, malpha, a_one, ma_one);
-        if (counted) prr += own;
-        a.rs[grec.g] = SVec<R>::make(gr0, gr1, gr2);                           // for the tiles that touch the node
+        x_one<R>(gx0, gp0, alpha, a_one); x_one<R>(gx1, gp1, alpha, a_one); x_one<R>(gx2, gp2, alpha, a_one);
         a.gstate[gs_i] = gp0; a.gstate[gs_n + gs_i] = gp1; a.gstate[2 * gs_n + gs_i] = gp2;
         a.gstate[3 * gs_n + gs_i] = gr0; a.gstate[4 * gs_n + gs_i] = gr1; a.gstate[5 * gs_n + gs_i] = gr2;
         a.gstate[6 * gs_n + gs_i] = gx0; a.gstate[7 * gs_n + gs_i] = gx1; a.gstate[8 * gs_n + gs_i] = gx2;
     }
-    // (requesting x / r before the den barrier was tried: the extra live registers spill in the shared-node phase, net loss)
-    for (int c = 0; c < L.tiles_cached; ++c) {
-        const int tile = blockIdx.x + c * gridDim.x;
-        if (tile >= t.n_tiles) break;
-        const int n_int = int(t.tile_nint[tile]);
-        const uint32_t node_off = t.tile_node_off[tile];
-        for (int k = threadIdx.x; k < n_int; k += blockDim.x) {
-            const SV pv = s_in[c * L.max_touched + k];
-            R* q = s_qr + 3 * size_t(c * L.max_int + k);
-            R x0, x1, x2, r0, r1, r2;
-            if (st.first) {
+    if (st.first) {
+        for (int c = 0; c < kTiles; ++c)
+            for (int k = threadIdx.x; k < n_int[c]; k += blockDim.x) {
                 const size_t g3 = 3 * size_t(s_nrec[c * L.max_int + k].g);
-                x0 = a.x[g3]; x1 = a.x[g3 + 1]; x2 = a.x[g3 + 2]; r0 = a.r[g3]; r1 = a.r[g3 + 1]; r2 = a.r[g3 + 2];
-            } else {
-                const SV xv = a.xt[node_off + k], rv = a.rt[node_off + k];
-                x0 = R(xv.x); x1 = R(xv.y); x2 = R(xv.z); r0 = R(rv.x); r1 = R(rv.y); r2 = R(rv.z);
+                x_node(c, k, a.x[g3], a.x[g3 + 1], a.x[g3 + 2]);
             }
-            prr += xr_one<R>(x0, r0, R(pv.x), q[0], alpha, malpha, a_one, ma_one);
-            prr += xr_one<R>(x1, r1, R(pv.y), q[1], alpha, malpha, a_one, ma_one);
-            prr += xr_one<R>(x2, r2, R(pv.z), q[2], alpha, malpha, a_one, ma_one);
-            a.xt[node_off + k] = SVec<R>::make(x0, x1, x2); a.rt[node_off + k] = SVec<R>::make(r0, r1, r2);
-            q[0] = r0; q[1] = r1; q[2] = r2;
-        }
+    } else {
+        SV xv[kTiles][kRounds];
+#pragma unroll
+        for (int c = 0; c < kTiles; ++c)
+#pragma unroll
+            for (int u = 0; u < kRounds; ++u) {
+                const int k = threadIdx.x + u * blockDim.x;
+                xv[c][u] = k < n_int[c] ? a.xt[node_off[c] + k] : SVec<R>::make(R(0), R(0), R(0));
+            }
+#pragma unroll
+        for (int c = 0; c < kTiles; ++c)
+#pragma unroll
+            for (int u = 0; u < kRounds; ++u) {
+                const int k = threadIdx.x + u * blockDim.x;
+                if (k < n_int[c]) x_node(c, k, R(xv[c][u].x), R(xv[c][u].y), R(xv[c][u].z));
+            }
+        for (int c = 0; c < kTiles; ++c)
+            for (int k = threadIdx.x + kRounds * blockDim.x; k < n_int[c]; k += blockDim.x) { const SV v = a.xt[node_off[c] + k]; x_node(c, k, R(v.x), R(v.y), R(v.z)); }
     }
     st.updated = true;
-    __syncthreads();
-    prr = block_sum(prr, red);
-    trace_mark(ep.trace, kTraceTail, 5);
-    const double rho_new = P.enabled ? dist_sync<R>(a, st.sync_count, st.xs, prr, bcast, st.failed) : grid_sync_sum(a.sync, st.sync_count, prr, red, bcast);
+    const double rho_new = P.enabled ? dist_sync<R>(a, st.sync_count, st.xs, prr, bcast, st.failed) : grid_wait_sum(a.sync, st.sync_count, bcast);
     if (st.failed) { if (blockIdx.x == 0 && threadIdx.x == 0) { cg->done = 1; cg->end_cond = 99; } return false; }
     trace_mark(ep.trace, kTraceTail, 6);
     const int it2 = st.it + 1;

@@ -100,6 +100,7 @@ template <class R> struct TileDev {
     const uint32_t* tile_node_off;   // [n_tiles+1] into tile_nodes
     const uint32_t* tile_nodes;      // global node ids: interior (ranked by valence desc) then shared
     const uint32_t* tile_nint;       // [n_tiles]
+    const uint32_t* tile_nb;         // [n_tiles] leading elements of the tile that feed shared nodes (null: unknown)
     const uint16_t* tile_val;        // valence of each interior node, aligned with tile_nodes (shared entries unused)
     const uint16_t* tile_jds;        // [n_tiles][maxval+1]
     // shared nodes

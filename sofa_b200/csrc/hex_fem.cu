@@ -30,7 +30,7 @@ template <class R> struct HexFF : sofab200_hexfem {
         const HostPlan& plan = h.plan;
         HexDev<R> d;
         d.t.n_nodes = int(n_nodes); d.t.n_elems = int(n_hexas); d.t.n_tiles = plan.n_tiles; d.t.tile_e = plan.tile_e; d.t.maxval = plan.maxval;
-        d.t.tile_node_off = tile_node_off.p; d.t.tile_nodes = tile_nodes.p; d.t.tile_nint = tile_nint.p; d.t.tile_val = tile_val.p; d.t.tile_jds = tile_jds.p;
+        d.t.tile_node_off = tile_node_off.p; d.t.tile_nodes = tile_nodes.p; d.t.tile_nint = tile_nint.p; d.t.tile_nb = nullptr; d.t.tile_val = tile_val.p; d.t.tile_jds = tile_jds.p;
         d.t.n_shared = plan.n_shared; d.t.n_chunks = plan.n_chunks; d.t.sh_nodes = sh_nodes.p; d.t.sh_val = sh_val.p; d.t.sh_base = sh_base.p;
         d.t.stage = stage.p; d.t.stage_n = plan.stage_n;
         d.lnode = lnode.p; d.slot_a = slot_a.p; d.slot_b = slot_b.p; d.r0 = r0.p; d.r1 = r1.p; d.r2 = r2.p;

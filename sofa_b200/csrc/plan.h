@@ -15,6 +15,7 @@ struct HostPlan {
     std::vector<uint32_t> tile_node_off;  // [n_tiles+1]
     std::vector<uint32_t> tile_nodes;
     std::vector<uint32_t> tile_nint;
+    std::vector<uint32_t> tile_nb;        // [n_tiles] elements of the tile that feed at least one shared node, when they come FIRST in the tile (else 0xFFFFFFFF)
     std::vector<uint16_t> tile_val;
     std::vector<uint16_t> tile_jds;       // [n_tiles][maxval+1]
     std::vector<uint16_t> lnode;          // [n_tiles*tile_e*npe]
@@ -41,12 +42,13 @@ inline uint64_t morton_spread(uint64_t v) {  // 21 bits -> every third bit
 // elems: n_elems x npe node indices (original topology order); pos: 3*n_nodes doubles (rest positions).
 // Returns "" or an error text.
 // force_shared (optional): n_nodes flags, nodes that must take the staging path whatever their incident elements.
+// reorder_from_tile (optional): tiles from this index on list their elements that feed shared nodes first (tile_nb).
 // smem_limit / sv_bytes / slot_bytes (optional): shared-memory budget of a tile CTA, bytes of one staged nodal vector and of
 // one slot.  When a tile's interior nodes need more slots than fit, its highest-valence interior nodes are demoted to
 // shared nodes (their contributions go through the HBM/L2 staging buffer instead), so any tile size can be made to fit.
 inline std::string build_plan(HostPlan& P, int n_nodes, int n_elems, int npe, const uint32_t* elems, const double* pos,
                               int tile_e, int chunk, uint32_t stage_flag, size_t smem_limit = 0, size_t sv_bytes = 0, size_t slot_bytes = 0,
-                              const unsigned char* force_shared = nullptr) {
+                              const unsigned char* force_shared = nullptr, int reorder_from_tile = 0x7fffffff) {
     P = HostPlan();
     P.n_nodes = n_nodes; P.n_elems = n_elems; P.npe = npe; P.tile_e = tile_e;
     P.n_tiles = std::max(1, (n_elems + tile_e - 1) / tile_e);
@@ -134,6 +136,25 @@ inline std::string build_plan(HostPlan& P, int n_nodes, int n_elems, int npe, co
             in.erase(in.begin(), in.begin() + drop);
             P.n_demoted += drop;
         }
+    }
+
+    // ---- inside a tile, the elements that touch a shared node come first (both groups keep their spatial order): once they
+    // are done the tile has nothing more to stage, which lets the persistent CG kernel announce "my staged contributions are
+    // complete" before the tile's remaining elements and hide the grid barrier behind them.  The order of the elements inside a
+    // tile has no influence on any result (every sum runs in ORIGINAL element order).  Only the tiles a CTA processes LAST
+    // (t >= reorder_from_tile) are reordered: the mixed order streams a little faster (measured: +0.45 us per 3328-tet tile).
+    P.tile_nb.assign(P.n_tiles, 0xFFFFFFFFu);
+    for (int t = std::max(0, reorder_from_tile); t < P.n_tiles; ++t) {
+        const size_t s0 = size_t(t) * tile_e, s1 = std::min(n_slots, s0 + tile_e);
+        auto feeds_shared = [&](uint32_t e) {
+            if (e == 0xFFFFFFFFu) return false;
+            for (int c = 0; c < npe; ++c) if (interior_tile[elems[size_t(e) * npe + c]] < 0) return true;
+            return false;
+        };
+        auto mid = std::stable_partition(P.order.begin() + s0, P.order.begin() + s1, feeds_shared);
+        P.tile_nb[t] = uint32_t(mid - (P.order.begin() + s0));
+        // (padding slots, if any, stay behind the real elements)
+        std::stable_partition(mid, P.order.begin() + s1, [](uint32_t e) { return e != 0xFFFFFFFFu; });
     }
 
     std::vector<uint32_t> corner_slot(size_t(n_elems) * npe, 0);

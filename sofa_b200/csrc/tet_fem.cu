@@ -19,7 +19,7 @@ template <class R> struct TetFF : sofab200_tetfem {
     HostTet<R> h;
     DevBuf<ushort4> lnode; DevBuf<uint4> slot; DevBuf<uint32_t> orig;
     DevBuf<Quad<R>> rk0, rk1, rk2, j0, j1, j2, x0a, x0b, x0c, sv0, sv1, sv2, sv3, sv4;
-    DevBuf<uint32_t> tile_node_off, tile_nodes, tile_nint, sh_nodes, sh_base;
+    DevBuf<uint32_t> tile_node_off, tile_nodes, tile_nint, tile_nb, sh_nodes, sh_base;
     DevBuf<uint16_t> tile_val, tile_jds, sh_val;
     DevBuf<Quad<R>> stage;
     DevBuf<R> rot_export;
@@ -29,7 +29,7 @@ template <class R> struct TetFF : sofab200_tetfem {
         const HostPlan& plan = h.plan;
         TetDev<R> d;
         d.t.n_nodes = int(n_nodes); d.t.n_elems = int(n_tets); d.t.n_tiles = plan.n_tiles; d.t.tile_e = plan.tile_e; d.t.maxval = plan.maxval;
-        d.t.tile_node_off = tile_node_off.p; d.t.tile_nodes = tile_nodes.p; d.t.tile_nint = tile_nint.p; d.t.tile_val = tile_val.p; d.t.tile_jds = tile_jds.p;
+        d.t.tile_node_off = tile_node_off.p; d.t.tile_nodes = tile_nodes.p; d.t.tile_nint = tile_nint.p; d.t.tile_nb = tile_nb.p; d.t.tile_val = tile_val.p; d.t.tile_jds = tile_jds.p;
         d.t.n_shared = plan.n_shared; d.t.n_chunks = plan.n_chunks; d.t.sh_nodes = sh_nodes.p; d.t.sh_val = sh_val.p; d.t.sh_base = sh_base.p;
         d.t.stage = stage.p; d.t.stage_n = plan.stage_n;
         d.lnode = lnode.p; d.slot = slot.p;
@@ -52,7 +52,7 @@ template <class R> static int tet_upload(TetFF<R>& ff) {
         SB_TRY(ff.sv0.upload(H.sv[0], s)); SB_TRY(ff.sv1.upload(H.sv[1], s)); SB_TRY(ff.sv2.upload(H.sv[2], s));
         SB_TRY(ff.sv3.upload(H.sv[3], s)); SB_TRY(ff.sv4.upload(H.sv[4], s));
     }
-    SB_TRY(ff.tile_node_off.upload(P.tile_node_off, s)); SB_TRY(ff.tile_nodes.upload(P.tile_nodes, s)); SB_TRY(ff.tile_nint.upload(P.tile_nint, s));
+    SB_TRY(ff.tile_node_off.upload(P.tile_node_off, s)); SB_TRY(ff.tile_nodes.upload(P.tile_nodes, s)); SB_TRY(ff.tile_nint.upload(P.tile_nint, s)); SB_TRY(ff.tile_nb.upload(P.tile_nb, s));
     SB_TRY(ff.tile_val.upload(P.tile_val, s)); SB_TRY(ff.tile_jds.upload(P.tile_jds, s));
     SB_TRY(ff.sh_nodes.upload(P.sh_nodes, s)); SB_TRY(ff.sh_val.upload(P.sh_val, s)); SB_TRY(ff.sh_base.upload(P.sh_base, s));
     SB_TRY(ff.stage.alloc(P.stage_n)); SB_TRY(ff.stage.zero(s));

@@ -168,8 +168,12 @@ template <class R, int MODE> HD void tet_element(const TetDev<R>& d, size_t es, 
 // phase 2 of a tile: one thread per element, 4 corner contributions scattered to their slots.
 // PF: software-prefetch the next element record (the record of the thread's NEXT element is requested before the current
 // one is processed, so one element's worth of HBM latency is always overlapped with ~500 instructions of arithmetic).
+// arrive_slots (persistent CG kernel, the CTA's last tile): once the elements [0, arrive_at) are done -- the plan puts the elements
+// that feed shared nodes first -- the CTA arrives at the "staged contributions complete" grid barrier and goes on with the
+// rest of the tile; arrive_at is a multiple of blockDim.x with arrive_at + blockDim.x <= tile_e (every thread passes there).
 template <class R, int MODE, bool PF>
-__device__ __forceinline__ void tet_tile_elements(const TetDev<R>& d, int tile, const typename SVec<R>::T* s_in, R* s_slot, int max_slots) {
+__device__ __forceinline__ void tet_tile_elements(const TetDev<R>& d, int tile, const typename SVec<R>::T* s_in, R* s_slot, int max_slots,
+                                                  unsigned long long* arrive_slots = nullptr, int arrive_at = 0) {
     typedef typename SVec<R>::T SV;
     const TileDev<R>& t = d.t;
     const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
@@ -181,6 +185,9 @@ __device__ __forceinline__ void tet_tile_elements(const TetDev<R>& d, int tile, 
         lnw = idx_load(reinterpret_cast<const uint2*>(d.lnode + es), pol_stream); sl = idx_load(d.slot + es, pol_stream); rec = tet_load_rec(d, es, pol_stream);
     }
     while (le < t.tile_e) {
+#ifdef __CUDA_ARCH__
+        if (arrive_slots && le - int(threadIdx.x) == arrive_at) grid_arrive(arrive_slots, 0u, blockDim.x - 32u);   // the last warp has the shortest tail of the tile
+#endif
         const size_t es = size_t(tile) * t.tile_e + le;
         const int nle = le + blockDim.x;
         uint2 n_lnw = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); uint4 n_sl = make_uint4(0, 0, 0, 0);
@@ -275,17 +282,27 @@ __global__ void __launch_bounds__(MAXT) tet_cg_persistent_kernel(TetDev<R> d, Pe
         persist_phase1<R>(t, a, st, smem_raw);
         trace_mark(a.ep.trace, kTraceTail, 12);
         double part = 0.0;
+        bool arrived = false;
         for (int c = 0; c < L.tiles_cached; ++c) {
             const int tile = blockIdx.x + c * gridDim.x;
             if (tile >= t.n_tiles) break;
-            tet_tile_elements<R, MODE, PF>(d, tile, s_in + c * L.max_touched, s_slot, L.max_slots);
+            // the CTA's last tile: its elements that feed shared nodes come first; after them the staged contributions of this
+            // CTA are complete, and the rest of the tile (plus its interior sums) runs while the other CTAs arrive
+            const bool last = c + 1 == L.tiles_cached || tile + int(gridDim.x) >= t.n_tiles;
+            int arrive_at = -1;
+            if (last && t.tile_nb && t.tile_nb[tile] != 0xFFFFFFFFu) {
+                const int nb_up = (int(t.tile_nb[tile]) + int(blockDim.x) - 1) / int(blockDim.x) * int(blockDim.x);
+                if (nb_up + int(blockDim.x) <= t.tile_e) arrive_at = nb_up;
+            }
+            tet_tile_elements<R, MODE, PF>(d, tile, s_in + c * L.max_touched, s_slot, L.max_slots, arrive_at >= 0 ? a.sync : nullptr, arrive_at);
+            if (arrive_at >= 0) arrived = true;
             __syncthreads();
             if (c == 0) trace_mark(a.ep.trace, kTraceTail, 13);
             part += persist_phase3<R>(t, tile, c, a, smem_raw);
             __syncthreads();
             if (c == 0) trace_mark(a.ep.trace, kTraceTail, 14);
         }
-        if (!persist_rest<R>(t, a, st, part, red, &bcast, smem_raw, s_grec)) break;
+        if (!persist_rest<R>(t, a, st, part, red, &bcast, smem_raw, s_grec, arrived)) break;
     }
     persist_finish<R>(t, a, st, smem_raw, s_grec);
     trace_mark(a.ep.trace, kTraceTail, 11);
