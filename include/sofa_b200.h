@@ -127,6 +127,21 @@ int sofab200_mass_acc_from_f(sofab200_ctx* ctx, sofab200_real real, size_t n, vo
  * and ::addForce (:469-496): mg = gravity*m once; f[i] += mg. */
 int sofab200_uniform_mass_add_mdx(sofab200_ctx* ctx, sofab200_real real, size_t n, void* res_dev, const void* dx_dev, double vertex_mass, double factor);
 int sofab200_uniform_mass_add_force(sofab200_ctx* ctx, sofab200_real real, size_t n, void* f_dev, double vertex_mass, const double gravity[3]);
+/* MeshMatrixMass<DataTypes> (Sofa/Component/Mass/src/sofa/component/mass/MeshMatrixMass.inl) -- [MMM].  The component's init() stays on
+ * the host (d_vertexMass, d_edgeMass, m_massLumpingCoeff as the CPU class computes them, l_topology->getEdges() in topology order); the
+ * device applies the matrix.  Every node gathers its half-edges in ascending edge index after the vertex term -- the order the
+ * reference's sequential scatter adds them in -- so the result is bit-identical and reproducible (no atomics). (create: sync) */
+typedef struct sofab200_meshmass sofab200_meshmass;
+int sofab200_meshmass_create(sofab200_ctx* ctx, sofab200_real real, size_t n_nodes, const void* vertex_mass_host, size_t n_edges,
+                             const uint32_t* edges_host /* n_edges x 2 */, const void* edge_mass_host, int lumping, double mass_lumping_coeff,
+                             sofab200_meshmass** out);
+int sofab200_meshmass_destroy(sofab200_meshmass* mm);
+/* addMDx [MMM]:1987-2048 */
+int sofab200_meshmass_add_mdx(sofab200_meshmass* mm, void* res_dev, const void* dx_dev, double factor);
+/* addForce [MMM]:2072-2092: f[i] += gravity*vertexMass[i]*m_massLumpingCoeff */
+int sofab200_meshmass_add_force(sofab200_meshmass* mm, void* f_dev, const double gravity[3]);
+/* accFromF [MMM]:2050-2069: lumped only; SOFAB200_ERR_UNSUPPORTED otherwise (the reference prints an error and returns) */
+int sofab200_meshmass_acc_from_f(sofab200_meshmass* mm, void* a_dev, const void* f_dev);
 /* FixedProjectiveConstraint::projectResponse / projectVelocity [FPC]:183-206,236-258. */
 int sofab200_fixed_project_response(sofab200_ctx* ctx, sofab200_real real, size_t n, void* res_dev, size_t n_indices, const uint32_t* indices_dev, int fix_all);
 
@@ -163,6 +178,11 @@ int sofab200_tetfem_add_dforce(sofab200_tetfem* ff, void* df_dev, const void* dx
  *   "strainDisplacements" (T x 12: the 12 distinct cofactors), "materialsStiffnesses" (T x 3: K00,K01,K33),
  *   "rotatedInitialElements" (T x 12), "initialTransformation" (T x 9, svd only). */
 int sofab200_tetfem_get(sofab200_tetfem* ff, const char* what, void* out_host);
+/* getRotations(VecReal& vecR) [TFF].inl:781-833,2033-2042 (what WarpPreconditioner / RotationMatrix consumers read; SofaCUDA:
+ * CudaTetrahedronFEMForceField.inl getRotations): per node the mean of rotations[t] * R0(t) over the tetrahedra around it, in
+ * ascending tetrahedron index, made orthogonal by polarDecomposition; identity for method small.  vecR_dev: n_nodes x 9 `real`
+ * (row-major 3x3), device memory. */
+int sofab200_tetfem_get_rotations(sofab200_tetfem* ff, void* vecR_dev);
 /* Layout statistics: out[0]=tiles, [1]=elements per tile, [2]=interior nodes, [3]=shared nodes,
  * [4]=staged (HBM) corner contributions, [5]=dynamic shared memory bytes, [6]=max valence, [7]=n_tets */
 int sofab200_tetfem_stats(const sofab200_tetfem* ff, uint64_t out[8]);

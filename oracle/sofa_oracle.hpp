@@ -27,6 +27,7 @@
 #include <limits>
 #include <mutex>
 #include <thread>
+#include <map>
 #include <vector>
 
 namespace orc {
@@ -726,6 +727,35 @@ template <class R> struct TetFEM {
             fn[2] -= rot(2, 0) * F[3 * n] + rot(2, 1) * F[3 * n + 1] + rot(2, 2) * F[3 * n + 2];
         }
     }
+    // getRotation :781-833 (what WarpPreconditioner / RotationMatrix consumers read): the mean of rotations[t] * R0(t) over the
+    // tetrahedra around the node (TetrahedraAroundVertex lists them in ascending index), made orthogonal by polarDecomposition.
+    // A node without tetrahedra takes the element _rotationIdx names (:803-808; the array is zero-filled, :850-853 overwrite it).
+    void getRotation(Mat3<R>& Rn, uint32_t nodeIdx, const std::vector<std::vector<uint32_t>>& tetrahedraAroundVertex) const {
+        if (method == SMALL) { Rn.identity(); return; }
+        const std::vector<uint32_t>& liste = tetrahedraAroundVertex[nodeIdx];
+        Rn = Mat3<R>();
+        const std::size_t numTetra = liste.size();
+        if (numTetra == 0) {
+            if (!rotationIdx.empty()) Rn = rotations[rotationIdx[nodeIdx]] * initialRotations[rotationIdx[nodeIdx]].transposed();
+            else Rn.identity();
+            return;
+        }
+        for (std::size_t ti = 0; ti < numTetra; ++ti) {
+            const Mat3<R> prod = rotations[liste[ti]] * initialRotations[liste[ti]].transposed();
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rn.m[i][j] += prod.m[i][j];   // Mat.h operator+=
+        }
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rn.m[i][j] = Rn.m[i][j] / numTetra;   // Real / size_t, as written at :823-825
+        Mat3<R> Rmoy;
+        Decompose<R>::polarDecomposition(Rn, Rmoy);
+        Rn = Rmoy;
+    }
+    // getRotations(VecReal&) :2033-2042: 9 Reals per node, row-major
+    void getRotations(std::vector<Mat3<R>>& vecR, size_t nbdof) const {
+        std::vector<std::vector<uint32_t>> around(nbdof);
+        for (size_t t = 0; t < nbTets(); ++t) for (int k = 0; k < 4; ++k) around[tets[4 * t + k]].push_back(uint32_t(t));   // TetrahedronSetTopologyContainer::createTetrahedraAroundVertexArray
+        vecR.assign(nbdof, Mat3<R>());
+        for (uint32_t i = 0; i < nbdof; ++i) getRotation(vecR[i], i, around);
+    }
     // addDForce :1606-1636.  kFactor already includes the Rayleigh term
     // (MechanicalParams.h:62) and is narrowed to Real there (:1615).
     void addDForce(VecDeriv<R>& df, const VecDeriv<R>& dx, SReal kFactorIncludingRayleigh) {
@@ -1006,6 +1036,86 @@ template <class R> struct DiagonalMass {
         for (size_t i = 0; i < vertexMass.size(); ++i) f[i] += theGravity * vertexMass[i];
     }
 };
+
+// ---------------------------------------------------------------------------
+// MeshMatrixMass<Vec3Types> on a tetrahedral topology
+// Sofa/Component/Mass/src/sofa/component/mass/MeshMatrixMass.inl
+// PARITY UNPINNED by reference vectors: the reference's MeshMatrixMass_test.cpp checks totals and vertex/edge masses of tiny meshes
+// (reproduced in tests/test_oracle_golden.py), not addMDx outputs.
+// ---------------------------------------------------------------------------
+template <class R> struct MeshMatrixMass {
+    std::vector<R> vertexMass, edgeMass;      // d_vertexMass / d_edgeMass
+    std::vector<uint32_t> edges;              // 2*E, l_topology->getEdges()
+    bool lumping = false;                     // d_lumping
+    R massLumpingCoeff = R(0);                // m_massLumpingCoeff (:994; 2.5 on tetrahedra whether lumped or not, :1484)
+    double totalMass = 0;
+    // TetrahedronSetTopologyContainer::createEdgeSetArray (Topology/Container/Dynamic/.../TetrahedronSetTopologyContainer.cpp): edges in order of
+    // first appearance over the tetrahedra, local edges {0,1},{0,2},{0,3},{1,2},{1,3},{2,3} (core/topology/Topology.cpp:44), vertices sorted.
+    // edgesInTet: 6 edge ids per tetrahedron (m_edgesInTetrahedron).
+    static void createEdgeSetArray(const std::vector<uint32_t>& tets, std::vector<uint32_t>& edgesOut, std::vector<uint32_t>& edgesInTet) {
+        static const int L[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+        std::map<std::pair<uint32_t, uint32_t>, uint32_t> edgeMap;
+        edgesOut.clear(); edgesInTet.assign(tets.size() / 4 * 6, 0);
+        for (size_t i = 0; i < tets.size() / 4; ++i)
+            for (int j = 0; j < 6; ++j) {
+                const uint32_t v1 = tets[4 * i + L[j][0]], v2 = tets[4 * i + L[j][1]];
+                const std::pair<uint32_t, uint32_t> e = v1 < v2 ? std::make_pair(v1, v2) : std::make_pair(v2, v1);
+                auto it = edgeMap.find(e);
+                if (it == edgeMap.end()) { it = edgeMap.emplace(e, uint32_t(edgeMap.size())).first; edgesOut.push_back(e.first); edgesOut.push_back(e.second); }
+                edgesInTet[6 * i + j] = it->second;
+            }
+    }
+    // massInitialization on tetrahedra :1476-1490 with applyVertexMassTetrahedronCreation :547-603 and applyEdgeMassTetrahedronCreation :606-665,
+    // uniform d_massDensity
+    void initFromMassDensityTets(R density, const std::vector<Vec3<R>>& pos, const std::vector<uint32_t>& tets, bool lumped) {
+        lumping = lumped;
+        massLumpingCoeff = R(2.5);
+        std::vector<uint32_t> eit;
+        createEdgeSetArray(tets, edges, eit);
+        vertexMass.assign(pos.size(), R(0)); edgeMass.assign(edges.size() / 2, R(0));
+        totalMass = 0;
+        auto volume = [&](const uint32_t* t) {   // sofa::geometry::Tetrahedron::volume (Geometry/.../Tetrahedron.h:55-82)
+            const Vec3<R> a = pos[t[1]] - pos[t[0]], b = pos[t[2]] - pos[t[0]], c = pos[t[3]] - pos[t[0]];
+            return R(std::abs(dot(cross(a, b), c) / R(6)));
+        };
+        if (!lumping)
+            for (size_t i = 0; i < tets.size() / 4; ++i) {
+                const R mass = (density * volume(&tets[4 * i])) / R(20.0);
+                for (int j = 0; j < 6; ++j) edgeMass[eit[6 * i + j]] += mass;
+                totalMass += 6.0 * mass * 2.0;
+            }
+        for (size_t i = 0; i < tets.size() / 4; ++i) {
+            const R mass = (density * volume(&tets[4 * i])) / R(10.0);
+            for (int j = 0; j < 4; ++j) vertexMass[tets[4 * i + j]] += mass;
+            totalMass += !lumping ? 4.0 * mass : 4.0 * mass * massLumpingCoeff;
+        }
+    }
+    // addMDx :1987-2048
+    void addMDx(VecDeriv<R>& res, const VecDeriv<R>& dx, SReal factor) const {
+        if (lumping) {
+            for (size_t i = 0; i < dx.size(); i++) res[i] += dx[i] * vertexMass[i] * massLumpingCoeff * R(factor);
+        } else {
+            for (size_t i = 0; i < dx.size(); i++) res[i] += dx[i] * vertexMass[i] * R(factor);
+            for (size_t j = 0; j < edges.size() / 2; ++j) {
+                const R tempMass = edgeMass[j] * R(factor);
+                res[edges[2 * j]] += dx[edges[2 * j + 1]] * tempMass;
+                res[edges[2 * j + 1]] += dx[edges[2 * j]] * tempMass;
+            }
+        }
+    }
+    // accFromF :2050-2069 (lumped only; the reference refuses otherwise)
+    bool accFromF(VecDeriv<R>& a, const VecDeriv<R>& f) const {
+        if (!lumping) return false;
+        for (size_t i = 0; i < vertexMass.size(); i++) a[i] = f[i] / (vertexMass[i] * massLumpingCoeff);
+        return true;
+    }
+    // addForce :2072-2092
+    void addForce(VecDeriv<R>& f, const double g[3]) const {
+        const Vec3<R> theGravity = Vec3<R>(R(g[0]), R(g[1]), R(g[2]));
+        for (size_t i = 0; i < f.size(); ++i) f[i] += theGravity * vertexMass[i] * massLumpingCoeff;
+    }
+};
+
 
 // PlaneForceField  Sofa/Component/MechanicalLoad/src/sofa/component/mechanicalload/PlaneForceField.inl
 // (present in every SofaCUDA FEM benchmark scene).  setPlane :139-145, addForce :158-205, addDForce :208-226.

@@ -271,6 +271,44 @@ void orc_scene_tet_matrices(void* h, size_t e, double* J72, double* K36) {
         for (int i = 0; i < 36; ++i) K36[i] = k[i];
     });
 }
+// MeshMatrixMass on tetrahedra, stand-alone.  orc_meshmass_create returns a handle; arrays are copied out with the getters.
+namespace {
+struct MeshMassAny { int real; MeshMatrixMass<float> f; MeshMatrixMass<double> d; };
+}
+void* orc_meshmass_create(int real, size_t n, const void* pos, size_t T, const uint32_t* tets, double density, int lumping) {
+    MeshMassAny* m = new MeshMassAny(); m->real = real;
+    std::vector<uint32_t> t(tets, tets + 4 * T);
+    if (real == 0) m->f.initFromMassDensityTets(float(density), toVec<float>(pos, n), t, lumping != 0);
+    else m->d.initFromMassDensityTets(density, toVec<double>(pos, n), t, lumping != 0);
+    return m;
+}
+void orc_meshmass_destroy(void* h) { delete static_cast<MeshMassAny*>(h); }
+size_t orc_meshmass_n_edges(void* h) { MeshMassAny* m = static_cast<MeshMassAny*>(h); return (m->real == 0 ? m->f.edges.size() : m->d.edges.size()) / 2; }
+double orc_meshmass_total(void* h) { MeshMassAny* m = static_cast<MeshMassAny*>(h); return m->real == 0 ? m->f.totalMass : m->d.totalMass; }
+void orc_meshmass_arrays(void* h, uint32_t* edges, void* vertexMass, void* edgeMass) {
+    MeshMassAny* m = static_cast<MeshMassAny*>(h);
+    if (m->real == 0) { copyOut(m->f.edges, edges); copyOut(m->f.vertexMass, vertexMass); copyOut(m->f.edgeMass, edgeMass); }
+    else { copyOut(m->d.edges, edges); copyOut(m->d.vertexMass, vertexMass); copyOut(m->d.edgeMass, edgeMass); }
+}
+// op 0: addMDx(res, dx, factor); 1: addForce(res, gravity = g); 2: accFromF(res = a, dx = f) -> returns 0 when refused
+int orc_meshmass_op(void* h, int op, size_t n, void* res, const void* dx, double factor, const double* g) {
+    MeshMassAny* m = static_cast<MeshMassAny*>(h);
+    int ok = 1;
+    auto run = [&](auto& mm, auto tag) {
+        typedef decltype(tag) R;
+        VecDeriv<R> r = toVec<R>(res, n);
+        if (op == 0) mm.addMDx(r, toVec<R>(dx, n), factor);
+        else if (op == 1) mm.addForce(r, g);
+        else ok = mm.accFromF(r, toVec<R>(dx, n)) ? 1 : 0;
+        fromVec(r, res);
+    };
+    if (m->real == 0) run(m->f, float()); else run(m->d, double());
+    return ok;
+}
+// TetrahedronFEMForceField::getRotations(VecReal&): out = 9 Reals per node
+void orc_scene_tet_get_rotations(void* h, void* out) {
+    DISPATCH(h, { std::vector<Mat3<R>> v; sc.tet.getRotations(v, sc.x.size()); copyMats(v, out); });
+}
 double orc_scene_hex_potential_energy(void* h) { double e = 0; DISPATCH(h, { e = sc.hex.potentialEnergy; }); return e; }
 
 }  // extern "C"

@@ -6,9 +6,9 @@ DiagonalMass, FixedProjectiveConstraint, and the EulerImplicitSolver + CGLinearS
 The computing is done by sofa_b200/lib/libsofa_b200.so (hand-written sm_100a CUDA); nothing here computes.
 """
 from ._lib import F32, F64, Sofab200Error, load  # noqa: F401
-from .components import (Communicator, Context, DiagonalMass, UniformMass, PlaneForceField, FixedProjectiveConstraint, HexahedronFEMForceField,  # noqa: F401
+from .components import (Communicator, Context, DiagonalMass, MeshMatrixMass, UniformMass, PlaneForceField, FixedProjectiveConstraint, HexahedronFEMForceField,  # noqa: F401
                          MechanicalObject, SolverNode, TetrahedronFEMForceField)
 from . import topology  # noqa: F401
 
-__all__ = ["Context", "Communicator", "MechanicalObject", "TetrahedronFEMForceField", "HexahedronFEMForceField", "DiagonalMass", "UniformMass", "PlaneForceField",
+__all__ = ["Context", "Communicator", "MechanicalObject", "TetrahedronFEMForceField", "HexahedronFEMForceField", "DiagonalMass", "MeshMatrixMass", "UniformMass", "PlaneForceField",
            "FixedProjectiveConstraint", "SolverNode", "topology", "load", "Sofab200Error", "F32", "F64"]

@@ -78,6 +78,11 @@ SYMBOLS = {
     "sofab200_plane_add_force": (_I, [_P, _I, _SZ, _P, _P, _P, C.POINTER(PlaneDesc), _P]),
     "sofab200_plane_add_dforce": (_I, [_P, _I, _SZ, _P, _P, C.POINTER(PlaneDesc), _P, _D]),
     "sofab200_uniform_mass_add_mdx": (_I, [_P, _I, _SZ, _P, _P, _D, _D]),
+    "sofab200_meshmass_create": (_I, [_P, _I, _SZ, _P, _SZ, _P, _P, _I, _D, C.POINTER(_P)]),
+    "sofab200_meshmass_destroy": (_I, [_P]),
+    "sofab200_meshmass_add_mdx": (_I, [_P, _P, _P, _D]),
+    "sofab200_meshmass_add_force": (_I, [_P, _P, C.POINTER(_D)]),
+    "sofab200_meshmass_acc_from_f": (_I, [_P, _P, _P]),
     "sofab200_uniform_mass_add_force": (_I, [_P, _I, _SZ, _P, _D, C.POINTER(_D)]),
     "sofab200_mass_add_force": (_I, [_P, _I, _SZ, _P, _P, C.POINTER(_D)]),
     "sofab200_mass_acc_from_f": (_I, [_P, _I, _SZ, _P, _P, _P]),
@@ -88,6 +93,7 @@ SYMBOLS = {
     "sofab200_tetfem_add_dforce": (_I, [_P, _P, _P, _D]),
     "sofab200_tetfem_get": (_I, [_P, C.c_char_p, _P]),
     "sofab200_tetfem_stats": (_I, [_P, C.POINTER(_U64)]),
+    "sofab200_tetfem_get_rotations": (_I, [_P, _P]),
     "sofab200_hexfem_create": (_I, [_P, _I, _SZ, _P, _SZ, _P, C.POINTER(HexFemDesc), C.POINTER(_P)]),
     "sofab200_hexfem_destroy": (_I, [_P]),
     "sofab200_hexfem_add_force": (_I, [_P, _P, _P]),

@@ -202,6 +202,14 @@ class TetrahedronFEMForceField:
         check(self.ctx.L.sofab200_tetfem_get(self.h, what.encode(), out.ctypes.data_as(_P)))
         return out
 
+    def getRotations(self, vecR=None):
+        """getRotations(VecReal&) (TetrahedronFEMForceField.inl:2033-2042): per-node rotations, n x 3 x 3 device tensor."""
+        import torch
+        if vecR is None:
+            vecR = torch.empty((self.mstate.size, 3, 3), dtype=self.mstate.tdtype, device=self.ctx.device)
+        check(self.ctx.L.sofab200_tetfem_get_rotations(self.h, _dptr(vecR)))
+        return vecR
+
     def stats(self):
         out = (C.c_uint64 * 8)()
         check(self.ctx.L.sofab200_tetfem_stats(self.h, out))
@@ -279,6 +287,42 @@ class DiagonalMass:
 
     def accFromF(self, a, f):
         check(self.ctx.L.sofab200_mass_acc_from_f(self.ctx.h, self.mstate.real, self.mstate.size, _dptr(a), _dptr(f), _dptr(self.vertexMass)))
+
+
+class MeshMatrixMass:
+    """MeshMatrixMass<B200Vec3Types> on a tetrahedral topology: Data massDensity, lumping (vertexMass / edgeMass computed as the CPU
+    class does, MeshMatrixMass.inl:547-665), or vertexMass + edges + edgeMass given."""
+
+    def __init__(self, mstate, tetrahedra=None, massDensity=1.0, lumping=False, vertexMass=None, edges=None, edgeMass=None, massLumpingCoeff=2.5, rayleighMass=0.0):
+        from .topology import mesh_matrix_mass
+        self.mstate, self.ctx = mstate, mstate.ctx
+        self.lumping, self.rayleighMass = bool(lumping), float(rayleighMass)
+        if vertexMass is None:
+            vertexMass, edges, edgeMass, massLumpingCoeff = mesh_matrix_mass(mstate.rest_position_host, tetrahedra, mstate.ndtype, massDensity, lumping)
+        self.vertexMass_host = np.ascontiguousarray(vertexMass, mstate.ndtype)
+        self.edges = np.ascontiguousarray(edges if edges is not None else np.zeros((0, 2)), np.uint32).reshape(-1, 2)
+        self.edgeMass_host = np.ascontiguousarray(edgeMass if edgeMass is not None else np.zeros(0), mstate.ndtype)
+        self.massLumpingCoeff = float(massLumpingCoeff)
+        self.h = _P()
+        check(self.ctx.L.sofab200_meshmass_create(self.ctx.h, mstate.real, mstate.size, self.vertexMass_host.ctypes.data_as(_P), self.edges.shape[0],
+                                                  self.edges.ctypes.data_as(_P), self.edgeMass_host.ctypes.data_as(_P), int(self.lumping),
+                                                  self.massLumpingCoeff, C.byref(self.h)))
+
+    def addMDx(self, res, dx, factor=1.0):
+        check(self.ctx.L.sofab200_meshmass_add_mdx(self.h, _dptr(res), _dptr(dx), float(factor)))
+
+    def addForce(self, f, gravity):
+        g = (C.c_double * 3)(*[float(v) for v in gravity])
+        check(self.ctx.L.sofab200_meshmass_add_force(self.h, _dptr(f), g))
+
+    def accFromF(self, a, f):
+        check(self.ctx.L.sofab200_meshmass_acc_from_f(self.h, _dptr(a), _dptr(f)))
+
+    def __del__(self):
+        try:
+            self.ctx.L.sofab200_meshmass_destroy(self.h)
+        except Exception:
+            pass
 
 
 class UniformMass:

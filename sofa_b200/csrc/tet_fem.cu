@@ -23,6 +23,7 @@ template <class R> struct TetFF : sofab200_tetfem {
     DevBuf<uint16_t> tile_val, tile_jds, sh_val;
     DevBuf<Quad<R>> stage;
     DevBuf<R> rot_export;
+    DevBuf<uint32_t> inc_off, inc_es, inc_e; DevBuf<R> r0t_el; uint32_t es_of_first = 0;   // getRotations: node -> incident elements (built at the first call)
     int threads = 256;   // CTA size of the addDForce tile kernel
     bool prefetch = true;
     TetDev<R> dev() {
@@ -227,6 +228,42 @@ template <class R> static int tet_get(TetFF<R>& ff, const std::string& what, voi
     return fail(SOFAB200_ERR_INVALID, "unknown array name: " + what);
 }
 
+// getRotations(VecReal&): 9 Reals per node into a device array
+template <class R> static int tet_node_rotations(TetFF<R>& ff, R* out_dev) {
+    cudaStream_t s = ff.ctx->stream;
+    if (ff.method == SOFAB200_TET_SMALL) {   // :783-791: identity (and a warning) when no rotation is computed
+        std::vector<R> id(9 * ff.n_nodes, R(0));
+        for (size_t n = 0; n < ff.n_nodes; ++n) id[9 * n] = id[9 * n + 4] = id[9 * n + 8] = R(1);
+        SB_CUDA(cudaMemcpyAsync(out_dev, id.data(), id.size() * sizeof(R), cudaMemcpyHostToDevice, s));
+        SB_CUDA(cudaStreamSynchronize(s));
+        return SOFAB200_OK;
+    }
+    if (!ff.inc_off.p) {
+        const HostPlan& P = ff.h.plan;
+        const size_t NS = size_t(P.n_tiles) * P.tile_e, T = ff.n_tets;
+        std::vector<uint32_t> es_of(T, 0), node_of(4 * T);
+        for (size_t es = 0; es < NS; ++es) if (P.order[es] != 0xFFFFFFFFu) es_of[P.order[es]] = uint32_t(es);
+        // the corner nodes of element e in original order: local ids of its tile -> node ids
+        std::vector<uint32_t> off(ff.n_nodes + 1, 0);
+        for (size_t es = 0; es < NS; ++es) {
+            const uint32_t e = P.order[es];
+            if (e == 0xFFFFFFFFu) continue;
+            const size_t tile = es / size_t(P.tile_e);
+            for (int k = 0; k < 4; ++k) { const uint32_t g = P.tile_nodes[P.tile_node_off[tile] + P.lnode[4 * es + k]]; node_of[4 * size_t(e) + k] = g; ++off[g + 1]; }
+        }
+        for (size_t n = 0; n < ff.n_nodes; ++n) off[n + 1] += off[n];
+        std::vector<uint32_t> fill(off.begin(), off.end() - 1), ies(4 * T), ie(4 * T);
+        for (size_t e = 0; e < T; ++e) for (int k = 0; k < 4; ++k) { const uint32_t at = fill[node_of[4 * e + k]]++; ies[at] = es_of[e]; ie[at] = uint32_t(e); }   // ascending element index
+        ff.es_of_first = T ? es_of[0] : 0;
+        SB_TRY(ff.inc_off.upload(off, s)); SB_TRY(ff.inc_es.upload(ies, s)); SB_TRY(ff.inc_e.upload(ie, s)); SB_TRY(ff.r0t_el.upload(ff.h.h_R0t, s));
+        SB_CUDA(cudaStreamSynchronize(s));
+    }
+    tet_node_rotations_kernel<R><<<unsigned((ff.n_nodes + 127) / 128), 128, 0, s>>>(ff.dev(), ff.inc_off.p, ff.inc_es.p, ff.inc_e.p, ff.r0t_el.p, ff.es_of_first, out_dev);
+    ff.ctx->launches++;
+    SB_CUDA(cudaGetLastError());
+    return SOFAB200_OK;
+}
+
 }  // namespace sb
 
 extern "C" {
@@ -266,6 +303,11 @@ int sofab200_tetfem_get(sofab200_tetfem* ff, const char* what, void* out_host) {
     SB_CHECK(ff && what && out_host, "null argument");
     if (ff->real == SOFAB200_F32) return tet_get(*static_cast<TetFF<float>*>(ff), what, out_host);
     return tet_get(*static_cast<TetFF<double>*>(ff), what, out_host);
+}
+int sofab200_tetfem_get_rotations(sofab200_tetfem* ff, void* vecR_dev) {
+    SB_CHECK(ff && vecR_dev, "null argument");
+    if (ff->real == SOFAB200_F32) return tet_node_rotations(*static_cast<TetFF<float>*>(ff), static_cast<float*>(vecR_dev));
+    return tet_node_rotations(*static_cast<TetFF<double>*>(ff), static_cast<double*>(vecR_dev));
 }
 int sofab200_tetfem_stats(const sofab200_tetfem* ff, uint64_t out[8]) {
     SB_CHECK(ff && out, "null argument");

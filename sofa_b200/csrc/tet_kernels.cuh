@@ -319,4 +319,63 @@ template <class R> __global__ void tet_export_rotations_kernel(TetDev<R> d, cons
     o[0] = q0.a; o[1] = q0.b; o[2] = q0.c; o[3] = q0.d; o[4] = q1.a; o[5] = q1.b; o[6] = q1.c; o[7] = q1.d; o[8] = q2.a;
 }
 
+// getRotation / getRotations(VecReal&), TetrahedronFEMForceField.inl:781-833,2033-2042: per node, the mean of rotations[t] * R0(t) over the
+// tetrahedra around it in ascending index, made orthogonal by polarDecomposition.  One thread per node; `inc` lists the tile-order slot
+// of the incident elements and `r0t` holds _initialRotations in ORIGINAL element order.  A node without tetrahedra takes element
+// _rotationIdx[node] = 0 (the array is zero-filled by resize, :1471).
+template <class R> __global__ void tet_node_rotations_kernel(TetDev<R> d, const uint32_t* __restrict__ inc_off, const uint32_t* __restrict__ inc_es,
+                                                             const uint32_t* __restrict__ inc_e, const R* __restrict__ r0t, uint32_t es_of_first, R* __restrict__ out) {
+    const size_t n = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (n >= size_t(d.t.n_nodes)) return;
+    auto elem_product = [&](uint32_t es, uint32_t e) {
+        const Quad<R> q0 = d.rk0[es], q1 = d.rk1[es], q2 = d.rk2[es];
+        M3<R> rot, r0;
+        rot.m[0][0] = q0.a; rot.m[0][1] = q0.b; rot.m[0][2] = q0.c; rot.m[1][0] = q0.d; rot.m[1][1] = q1.a; rot.m[1][2] = q1.b;
+        rot.m[2][0] = q1.c; rot.m[2][1] = q1.d; rot.m[2][2] = q2.a;
+        const R* p = r0t + 9 * size_t(e);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) r0.m[i][j] = p[3 * j + i];   // R0t.transpose(_initialRotations[t])
+        return mul(rot, r0);
+    };
+    const uint32_t b = inc_off[n], e = inc_off[n + 1];
+    M3<R> acc;
+    if (b == e) {
+        if (d.t.n_elems > 0) acc = elem_product(es_of_first, 0u);
+        else {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) acc.m[i][j] = i == j ? R(1) : R(0);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) acc.m[i][j] = R(0);
+        for (uint32_t k = b; k < e; ++k) {
+            const M3<R> pr = elem_product(inc_es[k], inc_e[k]);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) acc.m[i][j] += pr.m[i][j];
+        }
+        const R cnt = R(e - b);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) acc.m[i][j] = acc.m[i][j] / cnt;
+        M3<R> q;
+        polar_decomposition(acc, q);
+        acc = q;
+    }
+    R* o = out + 9 * n;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) o[3 * i + j] = acc.m[i][j];
+}
+
+
 }  // namespace sb

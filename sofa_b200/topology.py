@@ -113,6 +113,37 @@ def diagonal_mass(positions, elems, dtype, mass_density=None, total_mass=None):
     return masses
 
 
+def tetra_edges(tets):
+    """Edge array of a tetrahedral topology in the order TetrahedronSetTopologyContainer::createEdgeSetArray builds it (first appearance
+    over the tetrahedra, local edges {0,1},{0,2},{0,3},{1,2},{1,3},{2,3}, vertices sorted) and the 6 edge ids of every tetrahedron."""
+    t = np.asarray(tets, np.int64).reshape(-1, 4)
+    loc = np.array([[0, 1], [0, 2], [0, 3], [1, 2], [1, 3], [2, 3]])
+    pairs = np.sort(t[:, loc], axis=2).reshape(-1, 2)            # tetra-major, local-edge order
+    nmax = int(t.max()) + 1 if t.size else 1
+    key = pairs[:, 0] * nmax + pairs[:, 1]
+    uniq, first, inv = np.unique(key, return_index=True, return_inverse=True)
+    order = np.argsort(first, kind="stable")                       # unique keys ranked by first appearance
+    rank = np.empty_like(order); rank[order] = np.arange(order.size)
+    edges = pairs[first[order]].astype(np.uint32)
+    return edges, rank[inv].reshape(-1, 6).astype(np.uint32)
+
+
+def mesh_matrix_mass(positions, tets, dtype, mass_density=1.0, lumping=False):
+    """MeshMatrixMass on tetrahedra (MeshMatrixMass.inl:547-665,1476-1490) in the reference's Real arithmetic:
+    returns (vertexMass, edges, edgeMass, massLumpingCoeff)."""
+    dt = np.dtype(dtype).type
+    p = np.ascontiguousarray(positions, dtype)
+    t = np.asarray(tets, np.int64).reshape(-1, 4)
+    vol = _tet_volume(p, t)
+    edges, eit = tetra_edges(t)
+    vm = np.zeros(p.shape[0], dtype)
+    np.add.at(vm, t.ravel(), np.repeat((dt(mass_density) * vol) / dt(10.0), 4))        # sequential: tetra order, then corner order
+    em = np.zeros(edges.shape[0], dtype)
+    if not lumping:
+        np.add.at(em, eit.astype(np.int64).ravel(), np.repeat((dt(mass_density) * vol) / dt(20.0), 6))
+    return vm, edges, em, 2.5
+
+
 def read_gmsh_v1(path):
     """Gmsh file format 1.0 ($NOD / $ELM) -> (positions float64 [N,3], tetrahedra uint32 [T,4], hexahedra uint32 [H,8])."""
     with open(path) as fh:

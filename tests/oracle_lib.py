@@ -45,6 +45,9 @@ def lib():
         L.orc_scene_get.restype = C.c_size_t
         L.orc_scene_graph.restype = C.c_size_t
         L.orc_vdot.restype = C.c_double
+        L.orc_meshmass_create.restype = _P
+        L.orc_meshmass_n_edges.restype = C.c_size_t
+        L.orc_meshmass_total.restype = C.c_double
         L.orc_scene_hex_potential_energy.restype = C.c_double
         for sfx, ct in (("f", C.c_float), ("d", C.c_double)):
             getattr(L, "orc_polar_" + sfx).restype = ct
@@ -230,6 +233,12 @@ class OracleScene:
         self.L.orc_scene_fem_add_dforce(self.h, _ptr(df), _ptr(np.ascontiguousarray(dx, self.dtype)), C.c_double(k_factor))
         return df
 
+    def tet_get_rotations(self):
+        """TetrahedronFEMForceField::getRotations(VecReal&): per-node 3x3."""
+        out = np.empty((self.n, 3, 3), self.dtype)
+        self.L.orc_scene_tet_get_rotations(self.h, _ptr(out))
+        return out
+
     def compute_force(self):
         f = np.empty((self.n, 3), self.dtype)
         self.L.orc_scene_compute_force(self.h, _ptr(f))
@@ -282,3 +291,41 @@ def plane_add_dforce(dtype, prm, df, dx, contacts, k_factor):
 def vdot(dtype, a, b):
     real = 0 if np.dtype(dtype) == np.float32 else 1
     return float(lib().orc_vdot(real, C.c_size_t(a.shape[0]), _ptr(a), _ptr(b)))
+
+
+class OracleMeshMatrixMass:
+    """MeshMatrixMass on tetrahedra in the oracle (oracle/sofa_oracle.hpp: MeshMatrixMass)."""
+
+    def __init__(self, dtype, pos, tets, density=1.0, lumping=False):
+        self.L = lib()
+        self.dtype = np.dtype(dtype).type
+        self.real = 0 if self.dtype == np.float32 else 1
+        p = np.ascontiguousarray(pos, self.dtype); t = np.ascontiguousarray(tets, np.uint32)
+        self.n = p.shape[0]
+        self.h = _P(self.L.orc_meshmass_create(self.real, C.c_size_t(self.n), _ptr(p), C.c_size_t(t.shape[0]), _ptr(t), C.c_double(density), int(lumping)))
+        E = self.L.orc_meshmass_n_edges(self.h)
+        self.edges = np.zeros((E, 2), np.uint32); self.vertexMass = np.zeros(self.n, self.dtype); self.edgeMass = np.zeros(E, self.dtype)
+        self.L.orc_meshmass_arrays(self.h, _ptr(self.edges), _ptr(self.vertexMass), _ptr(self.edgeMass))
+        self.totalMass = self.L.orc_meshmass_total(self.h)
+
+    def _op(self, op, res, dx=None, factor=1.0, g=(0, 0, 0)):
+        r = np.array(res, self.dtype, order="C")
+        d = None if dx is None else np.ascontiguousarray(dx, self.dtype)
+        gg = (C.c_double * 3)(*[float(v) for v in g])
+        ok = self.L.orc_meshmass_op(self.h, op, C.c_size_t(self.n), _ptr(r), _ptr(d) if d is not None else None, C.c_double(factor), gg)
+        return r, ok
+
+    def addMDx(self, res, dx, factor=1.0):
+        return self._op(0, res, dx, factor)[0]
+
+    def addForce(self, f, g):
+        return self._op(1, f, None, 1.0, g)[0]
+
+    def accFromF(self, f):
+        return self._op(2, np.zeros_like(f), f)
+
+    def __del__(self):
+        try:
+            self.L.orc_meshmass_destroy(self.h)
+        except Exception:
+            pass

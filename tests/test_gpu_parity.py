@@ -69,6 +69,27 @@ def test_add_force_add_dforce_bit_exact(dtype, method):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("method", ["small", "large", "polar", "svd"])
+def test_get_rotations_per_node_bit_exact(dtype, method):
+    """getRotations(VecReal&) (TetrahedronFEMForceField.inl:781-833): mean of rotations[t] * R0(t) around each node + polar."""
+    g = gpu_scene("C1", dtype, method)
+    s = oracle_scene("C1", dtype, method)
+    mo, ff = g["mo"], g["ff"]
+    rng = np.random.default_rng(5)
+    for amp in (0.0, 0.3):
+        x = (g["pos"] + amp * rng.standard_normal(g["pos"].shape)).astype(dtype)
+        f0 = np.zeros_like(x)
+        ff.addForce(dev(mo, f0), dev(mo, x))
+        s.fem_add_force(f0, x)
+        R_d = ff.getRotations().cpu().numpy()
+        R_ref = s.tet_get_rotations()
+        assert R_d.tobytes() == R_ref.tobytes(), (method, amp)
+        if method != "small":
+            eye = np.einsum("nij,nkj->nik", R_d.astype(np.float64), R_d.astype(np.float64))
+            assert np.abs(eye - np.eye(3)).max() < (1e-5 if dtype == np.float32 else 1e-12)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("case", [dict(), dict(maxForce=0.05), dict(bilateral=True, normal=(0.3, 1.0, -0.2), d=0.7)], ids=["default", "maxForce", "bilateral"])
 def test_plane_force_field_bit_exact(dtype, case):
     """PlaneForceField addForce / addDForce (per-operation level; in every SofaCUDA FEM benchmark scene), bit-identical to the

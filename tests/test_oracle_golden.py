@@ -180,3 +180,21 @@ def test_reference_plane_force_field_test_scene():
         assert min(xs) < 0.05            # it did fall down to the plane ...
         assert xs[-1] >= -0.1            # ... and was sent back by it: the reference's criterion on the position after 100 steps
         assert min(xs) > -0.5 and xs[-1] > 0.0
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("method", ["large", "polar", "svd"])
+def test_get_rotations_restatement_properties(dtype, method):
+    """getRotation (TetrahedronFEMForceField.inl:781-833) has no KAT in the reference tree: checked through what it must satisfy --
+    identity in the rest configuration, and a rigidly rotated mesh gives that rotation at every node.  PARITY UNPINNED by vectors."""
+    pos, hexas = O.regular_grid((3, 3, 4), (0, 0, 0), (1, 1, 2))
+    tets = O.hexas_to_tetras((3, 3, 4), 1)
+    s = O.OracleScene(dtype, pos)
+    s.set_tets(tets, method, 1000.0, 0.3)
+    tol = 1e-5 if dtype == np.float32 else 1e-12
+    s.fem_add_force(np.zeros_like(pos, dtype), pos)
+    assert np.abs(s.tet_get_rotations() - np.eye(3)).max() < tol
+    a = 0.7
+    Q = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    s.fem_add_force(np.zeros_like(pos, dtype), pos @ Q.T)
+    assert np.abs(s.tet_get_rotations() - Q).max() < 10 * tol
