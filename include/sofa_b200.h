@@ -159,6 +159,9 @@ typedef struct sofab200_tetfem_desc {
     int tile_elems;             /* elements per CTA tile of the device layout; 0 = library default         */
     const unsigned char* shared_nodes; /* optional, n_nodes flags: nodes whose contributions must take the staging path
                                  * (partition-interface nodes of a multi-GPU run, see sofab200_node_set_peer); NULL = none */
+    double plastic_max_threshold;   /* Data `plasticMaxThreshold` (2-norm of the strain); <= 0 = no plasticity (the default)   */
+    double plastic_yield_threshold; /* Data `plasticYieldThreshold` (reference default 0.0001)                                  */
+    double plastic_creep;           /* Data `plasticCreep` (reference default 0.9)                                              */
 } sofab200_tetfem_desc;
 
 /* init()+reinit() [TFF].inl:1257-1545: per-element material stiffness, rest rotation, rotated rest
@@ -168,7 +171,8 @@ typedef struct sofab200_tetfem_desc {
 int sofab200_tetfem_create(sofab200_ctx* ctx, sofab200_real real, size_t n_nodes, const void* rest_position_host,
                            size_t n_tets, const uint32_t* tets_host, const sofab200_tetfem_desc* desc, sofab200_tetfem** out);
 int sofab200_tetfem_destroy(sofab200_tetfem* ff);
-/* addForce(mparams, f, x, v) [TFF].inl:1548-1604: f += elastic forces at x; caches rotations[e]. */
+/* addForce(mparams, f, x, v) [TFF].inl:1548-1604: f += elastic forces at x; caches rotations[e].  With plastic_max_threshold > 0
+ * the plasticity branch of computeForce ([TFF].inl:357-371) runs and updates the per-element plastic strain. */
 int sofab200_tetfem_add_force(sofab200_tetfem* ff, void* f_dev, const void* x_dev);
 /* addDForce(mparams, df, dx) [TFF].inl:1606-1636 with k_factor = kFactorIncludingRayleighDamping
  * (MechanicalParams.h:62): df -= R K_e R^T dx * k_factor using the cached rotations. */
@@ -176,8 +180,11 @@ int sofab200_tetfem_add_dforce(sofab200_tetfem* ff, void* df_dev, const void* dx
 /* Element-ordered copies for inspection / parity (sync).  what:
  *   "rotations" (T x 9, rotations[e] = R^T, [TFF].inl:880), "initialRotations" (T x 9),
  *   "strainDisplacements" (T x 12: the 12 distinct cofactors), "materialsStiffnesses" (T x 3: K00,K01,K33),
- *   "rotatedInitialElements" (T x 12), "initialTransformation" (T x 9, svd only). */
+ *   "rotatedInitialElements" (T x 12), "initialTransformation" (T x 9, svd only),
+ *   "plasticStrains" (T x 6, _plasticStrains; only with plastic_max_threshold > 0). */
 int sofab200_tetfem_get(sofab200_tetfem* ff, const char* what, void* out_host);
+/* reset() [TFF].inl:1380-1388: clears the plastic strains (nothing else is reset by the reference). */
+int sofab200_tetfem_reset(sofab200_tetfem* ff);
 /* getRotations(VecReal& vecR) [TFF].inl:781-833,2033-2042 (what WarpPreconditioner / RotationMatrix consumers read; SofaCUDA:
  * CudaTetrahedronFEMForceField.inl getRotations): per node the mean of rotations[t] * R0(t) over the tetrahedra around it, in
  * ascending tetrahedron index, made orthogonal by polarDecomposition; identity for method small.  vecR_dev: n_nodes x 9 `real`

@@ -483,6 +483,10 @@ template <class R> struct TetFEM {
     std::vector<Coord> X0;                // _rotatedInitialElements[e][0..3]
     std::vector<Mat3<R>> initialTransformation;  // _initialTransformation (svd: A0^-1)
     std::vector<uint32_t> rotationIdx;    // _rotationIdx
+    std::vector<R> plasticStrains;        // _plasticStrains: 6 Voigt components per element
+    R plastic[3] = {R(0), R(0.0001f), R(0.9f)};  // d_plasticMaxThreshold, d_plasticYieldThreshold, d_plasticCreep (defaults :51-53)
+    R* plasticPtr(size_t e) { return plastic[0] > 0 ? &plasticStrains[6 * e] : nullptr; }
+    void reset() { std::fill(plasticStrains.begin(), plasticStrains.end(), R(0)); }   // reset() :1380-1388
     double restVolume = 0;
 
     size_t nbTets() const { return tets.size() / 4; }
@@ -586,6 +590,7 @@ template <class R> struct TetFEM {
         initialPoints = restPosition;
         const size_t T = nbTets();
         K.assign(3 * T, 0); J.assign(12 * T, 0);
+        plasticStrains.assign(6 * T, R(0));   // :1415
         restVolume = 0;
         if (method != SMALL) {
             rotations.assign(T, Mat3<R>()); initialRotations.assign(T, Mat3<R>());
@@ -605,7 +610,8 @@ template <class R> struct TetFEM {
     }
 
     // computeForce :293-415 (plasticity off) and :417-521 (with `fact`); useFact selects `KJtD *= fact`.
-    static void computeForce(R F[12], const R D[12], const R* k, const R* j, bool useFact, SReal fact) {
+    // plasticStrain / plastic = {max, yield, creep}: the plasticity branch :357-371 (only when d_plasticMaxThreshold > 0)
+    static void computeForce(R F[12], const R D[12], const R* k, const R* j, bool useFact, SReal fact, R* plasticStrain = nullptr, const R* plastic = nullptr) {
         // J(3n,0)=j[3n] J(3n+1,1)=j[3n+1] J(3n+2,2)=j[3n+2]; J(3n,3)=j[3n+1] J(3n+1,3)=j[3n];
         // J(3n+1,4)=j[3n+2] J(3n+2,4)=j[3n+1]; J(3n,5)=j[3n+2] J(3n+2,5)=j[3n]
         R JtD[6];
@@ -615,6 +621,20 @@ template <class R> struct TetFEM {
         JtD[3] = j[1] * D[0] + j[0] * D[1] + j[4] * D[3] + j[3] * D[4] + j[7] * D[6] + j[6] * D[7] + j[10] * D[9] + j[9] * D[10];
         JtD[4] = j[2] * D[1] + j[1] * D[2] + j[5] * D[4] + j[4] * D[5] + j[8] * D[7] + j[7] * D[8] + j[11] * D[10] + j[10] * D[11];
         JtD[5] = j[2] * D[0] + j[0] * D[2] + j[5] * D[3] + j[3] * D[5] + j[8] * D[6] + j[6] * D[8] + j[11] * D[9] + j[9] * D[11];
+        if (plasticStrain && plastic[0] > 0) {
+            R elasticStrain[6];
+            for (int i = 0; i < 6; ++i) elasticStrain[i] = JtD[i] - plasticStrain[i];           // VoigtTensor elasticStrain = JtD; elasticStrain -= plasticStrain
+            R n2 = elasticStrain[0] * elasticStrain[0];                                         // Vec::norm2, Vec.h:483-493
+            for (int i = 1; i < 6; ++i) n2 += elasticStrain[i] * elasticStrain[i];
+            if (n2 > plastic[1] * plastic[1]) for (int i = 0; i < 6; ++i) plasticStrain[i] += elasticStrain[i] * plastic[2];   // += creep * elasticStrain
+            R plasticStrainNorm2 = plasticStrain[0] * plasticStrain[0];
+            for (int i = 1; i < 6; ++i) plasticStrainNorm2 += plasticStrain[i] * plasticStrain[i];
+            if (plasticStrainNorm2 > plastic[0] * plastic[0]) {
+                const R sc = plastic[0] / R(std::sqrt(plasticStrainNorm2));                      // helper::rsqrt = square root (rmath.h:125-138)
+                for (int i = 0; i < 6; ++i) plasticStrain[i] *= sc;
+            }
+            for (int i = 0; i < 6; ++i) JtD[i] -= plasticStrain[i];
+        }
         R KJtD[6];
         KJtD[0] = k[0] * JtD[0] + k[1] * JtD[1] + k[1] * JtD[2];
         KJtD[1] = k[1] * JtD[0] + k[0] * JtD[1] + k[1] * JtD[2];
@@ -640,7 +660,7 @@ template <class R> struct TetFEM {
         for (int n = 0; n < 3; ++n) for (int k = 0; k < 3; ++k)
             D[3 * (n + 1) + k] = ip[idx[n]][k] - ip[a][k] - p[idx[n]][k] + p[a][k];
         R F[12];
-        computeForce(F, D, &K[3 * e], &J[12 * e], false, 0);
+        computeForce(F, D, &K[3 * e], &J[12 * e], false, 0, plasticPtr(e), plastic);
         f[a] += Coord(F[0], F[1], F[2]); f[b] += Coord(F[3], F[4], F[5]);
         f[c] += Coord(F[6], F[7], F[8]); f[d] += Coord(F[9], F[10], F[11]);
     }
@@ -662,7 +682,7 @@ template <class R> struct TetFEM {
         D[6] = x0[2][0] - deforme[2][0]; D[7] = x0[2][1] - deforme[2][1]; D[8] = 0;
         D[9] = x0[3][0] - deforme[3][0]; D[10] = x0[3][1] - deforme[3][1]; D[11] = x0[3][2] - deforme[3][2];
         R F[12];
-        computeForce(F, D, &K[3 * e], &J[12 * e], false, 0);
+        computeForce(F, D, &K[3 * e], &J[12 * e], false, 0, plasticPtr(e), plastic);
         for (int i = 0; i < 12; i += 3) f[index[i / 3]] += rotations[e] * Coord(F[i], F[i + 1], F[i + 2]);
     }
     void accumulateForcePolarLike(VecDeriv<R>& f, const std::vector<Coord>& p, size_t e, bool svd) {  // :1025-1079, :1122-1185
@@ -686,7 +706,7 @@ template <class R> struct TetFEM {
         R D[12];
         for (int n = 0; n < 4; ++n) for (int k = 0; k < 3; ++k) D[3 * n + k] = x0[n][k] - deforme[n][k];
         R F[12];
-        computeForce(F, D, &K[3 * e], &J[12 * e], false, 0);
+        computeForce(F, D, &K[3 * e], &J[12 * e], false, 0, plasticPtr(e), plastic);
         for (int i = 0; i < 12; i += 3) f[index[i / 3]] += rotations[e] * Coord(F[i], F[i + 1], F[i + 2]);
     }
     // addForce :1547-1604

@@ -164,10 +164,11 @@ class MechanicalObject:
 
 class TetrahedronFEMForceField:
     """TetrahedronFEMForceField<B200Vec3Types>.  Data: youngModulus, poissonRatio, method, localStiffnessFactor,
-    rayleighStiffness (BaseForceField)."""
+    rayleighStiffness (BaseForceField), plasticMaxThreshold / plasticYieldThreshold / plasticCreep (defaults are the reference's
+    (Real)0.0001f and (Real)0.9f, TetrahedronFEMForceField.inl:51-53)."""
 
     def __init__(self, mstate, tetrahedra, youngModulus=5000.0, poissonRatio=0.45, method="large", localStiffnessFactor=None,
-                 rayleighStiffness=0.0, tileElems=0, sharedNodes=None):
+                 rayleighStiffness=0.0, tileElems=0, sharedNodes=None, plasticMaxThreshold=0.0, plasticYieldThreshold=float(np.float32(0.0001)), plasticCreep=float(np.float32(0.9))):
         if method not in TET_METHODS:
             raise ValueError(f"method must be one of {list(TET_METHODS)}")
         self.mstate, self.ctx = mstate, mstate.ctx
@@ -179,6 +180,7 @@ class TetrahedronFEMForceField:
         if localStiffnessFactor is not None:
             l, lp = _darr(localStiffnessFactor); d.n_local_stiffness, d.local_stiffness = len(l), lp
         d.tile_elems = int(tileElems)
+        d.plastic_max_threshold, d.plastic_yield_threshold, d.plastic_creep = float(plasticMaxThreshold), float(plasticYieldThreshold), float(plasticCreep)
         if sharedNodes is not None:      # nodes that must take the staging path (partition interface of a multi-GPU run)
             self._shared = np.zeros(mstate.size, np.uint8); self._shared[np.asarray(sharedNodes, np.int64)] = 1
             d.shared_nodes = self._shared.ctypes.data_as(C.POINTER(C.c_ubyte))
@@ -197,10 +199,14 @@ class TetrahedronFEMForceField:
     def get(self, what):
         T = self.tetrahedra.shape[0]
         shape = {"rotations": (T, 3, 3), "initialRotations": (T, 3, 3), "strainDisplacements": (T, 4, 3), "materialsStiffnesses": (T, 3),
-                 "rotatedInitialElements": (T, 4, 3), "initialTransformation": (T, 3, 3)}[what]
+                 "rotatedInitialElements": (T, 4, 3), "initialTransformation": (T, 3, 3), "plasticStrains": (T, 6)}[what]
         out = np.empty(shape, self.mstate.ndtype)
         check(self.ctx.L.sofab200_tetfem_get(self.h, what.encode(), out.ctypes.data_as(_P)))
         return out
+
+    def reset(self):
+        """reset() (TetrahedronFEMForceField.inl:1380-1388): clears the plastic strains."""
+        check(self.ctx.L.sofab200_tetfem_reset(self.h))
 
     def getRotations(self, vecR=None):
         """getRotations(VecReal&) (TetrahedronFEMForceField.inl:2033-2042): per-node rotations, n x 3 x 3 device tensor."""

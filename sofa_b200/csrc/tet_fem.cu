@@ -22,6 +22,7 @@ template <class R> struct TetFF : sofab200_tetfem {
     DevBuf<uint32_t> tile_node_off, tile_nodes, tile_nint, tile_nb, sh_nodes, sh_base;
     DevBuf<uint16_t> tile_val, tile_jds, sh_val;
     DevBuf<Quad<R>> stage;
+    DevBuf<Quad<R>> pl0, pl1; double plastic[3] = {0, 0, 0};   // _plasticStrains in tile order (plasticMaxThreshold > 0 only)
     DevBuf<R> rot_export;
     DevBuf<uint32_t> inc_off, inc_es, inc_e; DevBuf<R> r0t_el; uint32_t es_of_first = 0;   // getRotations: node -> incident elements (built at the first call)
     int threads = 256;   // CTA size of the addDForce tile kernel
@@ -37,6 +38,7 @@ template <class R> struct TetFF : sofab200_tetfem {
         d.rk0 = rk0.p; d.rk1 = rk1.p; d.rk2 = rk2.p; d.j0 = j0.p; d.j1 = j1.p; d.j2 = j2.p;
         d.x0a = x0a.p; d.x0b = x0b.p; d.x0c = x0c.p; d.sv0 = sv0.p; d.sv1 = sv1.p; d.sv2 = sv2.p; d.sv3 = sv3.p; d.sv4 = sv4.p;
         d.k_factor = R(0);
+        d.pl0 = pl0.p; d.pl1 = pl1.p; d.plastic_max = R(plastic[0]); d.plastic_yield = R(plastic[1]); d.plastic_creep = R(plastic[2]);
         return d;
     }
 };
@@ -57,6 +59,7 @@ template <class R> static int tet_upload(TetFF<R>& ff) {
     SB_TRY(ff.tile_val.upload(P.tile_val, s)); SB_TRY(ff.tile_jds.upload(P.tile_jds, s));
     SB_TRY(ff.sh_nodes.upload(P.sh_nodes, s)); SB_TRY(ff.sh_val.upload(P.sh_val, s)); SB_TRY(ff.sh_base.upload(P.sh_base, s));
     SB_TRY(ff.stage.alloc(P.stage_n)); SB_TRY(ff.stage.zero(s));
+    if (ff.plastic[0] > 0) { const size_t NS = size_t(P.n_tiles) * P.tile_e; SB_TRY(ff.pl0.alloc(NS)); SB_TRY(ff.pl0.zero(s)); SB_TRY(ff.pl1.alloc(NS)); SB_TRY(ff.pl1.zero(s)); }
     SB_CUDA(cudaStreamSynchronize(s));
     // the tile-ordered host planes are no longer needed once they are resident in HBM
     for (auto* v : {&H.rk0, &H.rk1, &H.rk2, &H.j0, &H.j1, &H.j2, &H.x0a, &H.x0b, &H.x0c}) { v->clear(); v->shrink_to_fit(); }
@@ -202,6 +205,7 @@ template <class R> static int tet_create(sofab200_ctx* ctx, size_t n_nodes, cons
     ff->threads = (ff->h.plan.tile_e >= 2048 && sizeof(R) == 4) ? 512 : 256;
     if (const char* env = getenv("SOFAB200_TILE_THREADS")) { const int v = atoi(env); if (v >= 64 && v <= 1024 && v % 32 == 0) ff->threads = v; }
     if (const char* env = getenv("SOFAB200_PREFETCH")) ff->prefetch = atoi(env) != 0;
+    ff->plastic[0] = desc->plastic_max_threshold; ff->plastic[1] = desc->plastic_yield_threshold; ff->plastic[2] = desc->plastic_creep;
     SB_TRY(tet_upload(*ff));
     *out = ff.release();
     return SOFAB200_OK;
@@ -223,6 +227,22 @@ template <class R> static int tet_get(TetFF<R>& ff, const std::string& what, voi
         SB_CUDA(cudaGetLastError());
         SB_CUDA(cudaMemcpyAsync(out, ff.rot_export.p, 9 * ff.n_tets * sizeof(R), cudaMemcpyDeviceToHost, ff.ctx->stream));
         SB_CUDA(cudaStreamSynchronize(ff.ctx->stream));
+        return SOFAB200_OK;
+    }
+    if (what == "plasticStrains") {
+        if (!ff.pl0.p) return fail(SOFAB200_ERR_UNSUPPORTED, "no plastic strains: plasticMaxThreshold <= 0");
+        const size_t NS = size_t(ff.h.plan.n_tiles) * ff.h.plan.tile_e;
+        std::vector<Quad<R>> a(NS), b(NS);
+        SB_CUDA(cudaMemcpyAsync(a.data(), ff.pl0.p, NS * sizeof(Quad<R>), cudaMemcpyDeviceToHost, ff.ctx->stream));
+        SB_CUDA(cudaMemcpyAsync(b.data(), ff.pl1.p, NS * sizeof(Quad<R>), cudaMemcpyDeviceToHost, ff.ctx->stream));
+        SB_CUDA(cudaStreamSynchronize(ff.ctx->stream));
+        R* o = static_cast<R*>(out);
+        for (size_t es = 0; es < NS; ++es) {
+            const uint32_t e = ff.h.plan.order[es];
+            if (e == 0xFFFFFFFFu) continue;
+            R* q = o + 6 * size_t(e);
+            q[0] = a[es].a; q[1] = a[es].b; q[2] = a[es].c; q[3] = a[es].d; q[4] = b[es].a; q[5] = b[es].b;
+        }
         return SOFAB200_OK;
     }
     return fail(SOFAB200_ERR_INVALID, "unknown array name: " + what);
@@ -303,6 +323,12 @@ int sofab200_tetfem_get(sofab200_tetfem* ff, const char* what, void* out_host) {
     SB_CHECK(ff && what && out_host, "null argument");
     if (ff->real == SOFAB200_F32) return tet_get(*static_cast<TetFF<float>*>(ff), what, out_host);
     return tet_get(*static_cast<TetFF<double>*>(ff), what, out_host);
+}
+int sofab200_tetfem_reset(sofab200_tetfem* ff) {
+    SB_CHECK(ff, "null argument");
+    if (ff->real == SOFAB200_F32) { auto* f = static_cast<TetFF<float>*>(ff); SB_TRY(f->pl0.zero(ff->ctx->stream)); SB_TRY(f->pl1.zero(ff->ctx->stream)); }
+    else { auto* f = static_cast<TetFF<double>*>(ff); SB_TRY(f->pl0.zero(ff->ctx->stream)); SB_TRY(f->pl1.zero(ff->ctx->stream)); }
+    return SOFAB200_OK;
 }
 int sofab200_tetfem_get_rotations(sofab200_tetfem* ff, void* vecR_dev) {
     SB_CHECK(ff && vecR_dev, "null argument");

@@ -23,18 +23,41 @@ template <class R> struct TetDev {
     const Quad<R>* x0a; const Quad<R>* x0b; const Quad<R>* x0c;  // _rotatedInitialElements (small: rest positions)
     const Quad<R>* sv0; const Quad<R>* sv1; const Quad<R>* sv2; const Quad<R>* sv3; const Quad<R>* sv4;  // svd: A0^-1 (9) + R0^T (9)
     R k_factor;                // addDForce: (Real)kFactorIncludingRayleighDamping
+    Quad<R>* pl0; Quad<R>* pl1;  // _plasticStrains[e] (6 Voigt components: pl0 = 0..3, pl1.a/b = 4..5); null unless plasticMaxThreshold > 0
+    R plastic_max, plastic_yield, plastic_creep;
 };
 
 // computeForce (TetrahedronFEMForceField.inl:293-415 without plasticity, :417-521 with `fact`).
 // j[3n..3n+2] = (jx,jy,jz) of node n: J(3n,0)=J(3n+1,3)=J(3n+2,5)=jx, J(3n,3)=J(3n+1,1)=J(3n+2,4)=jy,
 // J(3n,5)=J(3n+1,4)=J(3n+2,2)=jz; K has three distinct values k0=K(i,i) i<3, k1=K(i,j) i!=j<3, k2=K(i,i) i>=3.
-template <class R, bool USE_FACT> HD void tet_compute_force(R F[12], const R D[12], const R j[12], R k0, R k1, R k2, R fact) {
+// `ps` (addForce with plasticMaxThreshold > 0): the element's plastic strain, updated as :357-371 do; pp = {max, yield, creep}.
+template <class R, bool USE_FACT, bool PLASTIC = false> HD void tet_compute_force(R F[12], const R D[12], const R j[12], R k0, R k1, R k2, R fact, R* ps = nullptr, const R* pp = nullptr) {
     R s0 = j[0] * D[0] + j[3] * D[3] + j[6] * D[6] + j[9] * D[9];
     R s1 = j[1] * D[1] + j[4] * D[4] + j[7] * D[7] + j[10] * D[10];
     R s2 = j[2] * D[2] + j[5] * D[5] + j[8] * D[8] + j[11] * D[11];
     R s3 = j[1] * D[0] + j[0] * D[1] + j[4] * D[3] + j[3] * D[4] + j[7] * D[6] + j[6] * D[7] + j[10] * D[9] + j[9] * D[10];
     R s4 = j[2] * D[1] + j[1] * D[2] + j[5] * D[4] + j[4] * D[5] + j[8] * D[7] + j[7] * D[8] + j[11] * D[10] + j[10] * D[11];
     R s5 = j[2] * D[0] + j[0] * D[2] + j[5] * D[3] + j[3] * D[5] + j[8] * D[6] + j[6] * D[8] + j[11] * D[9] + j[9] * D[11];
+    if (PLASTIC) {
+        // elasticStrain = JtD - plasticStrain; creep when |elastic|^2 > yield^2; clamp |plastic| to max; JtD -= plasticStrain
+        const R el[6] = {s0 - ps[0], s1 - ps[1], s2 - ps[2], s3 - ps[3], s4 - ps[4], s5 - ps[5]};
+        R n2 = el[0] * el[0];
+#pragma unroll
+        for (int i = 1; i < 6; ++i) n2 += el[i] * el[i];
+        if (n2 > pp[1] * pp[1]) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) ps[i] += pp[2] * el[i];
+        }
+        R pn2 = ps[0] * ps[0];
+#pragma unroll
+        for (int i = 1; i < 6; ++i) pn2 += ps[i] * ps[i];
+        if (pn2 > pp[0] * pp[0]) {
+            const R sc = pp[0] / R(sqrt(pn2));   // helper::rsqrt is the square root (rmath.h:125-138)
+#pragma unroll
+            for (int i = 0; i < 6; ++i) ps[i] *= sc;
+        }
+        s0 -= ps[0]; s1 -= ps[1]; s2 -= ps[2]; s3 -= ps[3]; s4 -= ps[4]; s5 -= ps[5];
+    }
     R t0 = k0 * s0 + k1 * s1 + k1 * s2;
     R t1 = k1 * s0 + k0 * s1 + k1 * s2;
     R t2 = k1 * s0 + k1 * s1 + k0 * s2;
@@ -58,6 +81,16 @@ template <class R> HD TetRec<R> tet_load_rec(const TetDev<R>& d, size_t es, uint
     r.q0 = rec_load(d.rk0 + es, pol); r.q1 = rec_load(d.rk1 + es, pol); r.q2 = rec_load(d.rk2 + es, pol);
     r.ja = rec_load(d.j0 + es, pol); r.jb = rec_load(d.j1 + es, pol); r.jc = rec_load(d.j2 + es, pol);
     return r;
+}
+// computeForce(F, D, _plasticStrains[e], K, J) as addForce calls it (:560,927,1071,1180)
+template <class R> HD void tet_compute_force_addforce(const TetDev<R>& d, size_t es, R F[12], const R D[12], const R j[12], R k0, R k1, R k2) {
+    if (d.pl0) {
+        const Quad<R> a = d.pl0[es], b = d.pl1[es];
+        R ps[6] = {a.a, a.b, a.c, a.d, b.a, b.b};
+        const R pp[3] = {d.plastic_max, d.plastic_yield, d.plastic_creep};
+        tet_compute_force<R, false, true>(F, D, j, k0, k1, k2, R(0), ps, pp);
+        d.pl0[es] = Quad<R>{ps[0], ps[1], ps[2], ps[3]}; d.pl1[es] = Quad<R>{ps[4], ps[5], R(0), R(0)};
+    } else tet_compute_force<R, false>(F, D, j, k0, k1, k2, R(0));
 }
 template <class R, int MODE> HD void tet_element(const TetDev<R>& d, size_t es, const TetRec<R>& rec, const V3<R> P[4], V3<R> C[4]) {
     const Quad<R> q0 = rec.q0, q1 = rec.q1, q2 = rec.q2;
@@ -103,7 +136,7 @@ template <class R, int MODE> HD void tet_element(const TetDev<R>& d, size_t es, 
                 D[3 * n + 1] = X0[3 * n + 1] - X0[1] - P[n].y + P[0].y;
                 D[3 * n + 2] = X0[3 * n + 2] - X0[2] - P[n].z + P[0].z;
             }
-            tet_compute_force<R, false>(F, D, j, k0, k1, k2, R(0));
+            tet_compute_force_addforce<R>(d, es, F, D, j, k0, k1, k2);
 #pragma unroll
             for (int n = 0; n < 4; ++n) C[n] = mk3<R>(F[3 * n], F[3 * n + 1], F[3 * n + 2]);
         } else {
@@ -157,7 +190,7 @@ template <class R, int MODE> HD void tet_element(const TetDev<R>& d, size_t es, 
 #pragma unroll
                 for (int n = 0; n < 4; ++n) { D[3 * n] = X0[3 * n] - def[n].x; D[3 * n + 1] = X0[3 * n + 1] - def[n].y; D[3 * n + 2] = X0[3 * n + 2] - def[n].z; }
             }
-            tet_compute_force<R, false>(F, D, j, k0, k1, k2, R(0));
+            tet_compute_force_addforce<R>(d, es, F, D, j, k0, k1, k2);
             // f[index[i/3]] += rotations[e] * Deriv(F[i],F[i+1],F[i+2]), :928-929
 #pragma unroll
             for (int n = 0; n < 4; ++n) C[n] = mul(rot, mk3<R>(F[3 * n], F[3 * n + 1], F[3 * n + 2]));

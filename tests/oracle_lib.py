@@ -144,6 +144,12 @@ class OracleScene:
                                   0 if lsf is None else len(lsf), _ptr(lsf))
         self.tets = t
 
+    def set_plastic(self, max_threshold, yield_threshold=0.0001, creep=0.9):
+        self.L.orc_scene_tet_set_plastic(self.h, C.c_double(max_threshold), C.c_double(yield_threshold), C.c_double(creep))
+
+    def tet_reset(self):
+        self.L.orc_scene_tet_reset(self.h)
+
     def set_hexas(self, hexas, method="large", young=5000.0, poisson=0.45):
         hx = np.ascontiguousarray(hexas, np.uint32)
         y = np.atleast_1d(np.asarray(young, np.float64))
@@ -207,6 +213,8 @@ class OracleScene:
             return out.reshape(-1, 3, 3)
         if what == "tet.J":
             return out.reshape(-1, 4, 3)
+        if what == "tet.plasticStrains":
+            return out.reshape(-1, 6)
         if what == "tet.K":
             return out.reshape(-1, 3)
         if what == "tet.X0":

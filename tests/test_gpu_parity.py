@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
+import gpu_common
 from gpu_common import dev, gpu_scene, oracle_scene, rel_err
 
 pytestmark = pytest.mark.gpu
@@ -66,6 +67,43 @@ def test_add_force_add_dforce_bit_exact(dtype, method):
         df_d = dev(mo, f0)
         ff.addDForce(df_d, dev(mo, dx), kf)
         assert df_d.cpu().numpy().tobytes() == s.fem_add_dforce(f0, dx, kf).tobytes(), kf
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("method", ["small", "large", "polar", "svd"])
+@pytest.mark.parametrize("plastic", [(3.0, 1.0, 0.5), (4.0, 6.0, 0.9)], ids=["creep_everywhere", "yield_gate"])
+def test_plasticity_branch_bit_exact(dtype, method, plastic):
+    """computeForce with plasticMaxThreshold > 0 (TetrahedronFEMForceField.inl:357-371): the per-element plastic strain evolves over
+    successive addForce calls; forces and strains must equal the oracle's bit for bit, addDForce is untouched, reset() clears."""
+    import sofa_b200 as sb
+    c, pos, hexas, tets, fixed = gpu_common.mesh("C1")
+    s = oracle_scene("C1", dtype, method)
+    s.set_plastic(*plastic)
+    ctx = sb.Context(0)
+    mo = sb.MechanicalObject(ctx, "B200Vec3f" if dtype == np.float32 else "B200Vec3d", position=pos)
+    ff = sb.TetrahedronFEMForceField(mo, tets, youngModulus=c["young"], poissonRatio=c["poisson"], method=method, plasticMaxThreshold=plastic[0],
+                                     plasticYieldThreshold=plastic[1], plasticCreep=plastic[2])
+    rng = np.random.default_rng(11)
+    f0 = rng.standard_normal(pos.shape).astype(dtype)
+    for it in range(3):
+        x = (pos + (0.3 - 0.1 * it) * rng.standard_normal(pos.shape)).astype(dtype)
+        f_d = dev(mo, f0)
+        ff.addForce(f_d, dev(mo, x))
+        assert f_d.cpu().numpy().tobytes() == s.fem_add_force(f0, x).tobytes(), it
+        assert ff.get("plasticStrains").tobytes() == s.get("tet.plasticStrains").tobytes(), it
+    n = np.linalg.norm(ff.get("plasticStrains").astype(np.float64), axis=1)
+    assert (n > 0).any() and n.max() <= plastic[0] * (1 + 1e-5)
+    dx = rng.standard_normal(pos.shape).astype(dtype)
+    df_d = dev(mo, f0)
+    ff.addDForce(df_d, dev(mo, dx), 0.11)
+    assert df_d.cpu().numpy().tobytes() == s.fem_add_dforce(f0, dx, 0.11).tobytes()
+    # a permanent set remains once the load is gone: at the rest shape the force is not zero any more
+    f_d = dev(mo, np.zeros_like(f0))
+    ff.addForce(f_d, dev(mo, pos.astype(dtype)))
+    f_ref = s.fem_add_force(np.zeros_like(f0), pos.astype(dtype))
+    assert f_d.cpu().numpy().tobytes() == f_ref.tobytes() and np.abs(f_ref).max() > 0
+    ff.reset(); s.tet_reset()
+    assert np.abs(ff.get("plasticStrains")).max() == 0
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

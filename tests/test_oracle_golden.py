@@ -198,3 +198,29 @@ def test_get_rotations_restatement_properties(dtype, method):
     Q = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
     s.fem_add_force(np.zeros_like(pos, dtype), pos @ Q.T)
     assert np.abs(s.tet_get_rotations() - Q).max() < 10 * tol
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_plasticity_restatement_properties(dtype):
+    """The plasticity branch of computeForce (TetrahedronFEMForceField.inl:357-371) has no KAT in the reference tree (PARITY UNPINNED by
+    vectors): plasticMaxThreshold <= 0 leaves the force untouched, the plastic strain never exceeds the max threshold, an element
+    below the yield threshold keeps a zero plastic strain, and a permanent set remains after unloading."""
+    pos, hexas = O.regular_grid((3, 3, 4), (0, 0, 0), (3, 3, 6))
+    tets = O.hexas_to_tetras((3, 3, 4), 1)
+    rng = np.random.default_rng(2)
+    x = (pos + 0.3 * rng.standard_normal(pos.shape)).astype(dtype)
+    zero = np.zeros_like(x)
+    base = O.OracleScene(dtype, pos); base.set_tets(tets, "large", 1000.0, 0.3)
+    off = O.OracleScene(dtype, pos); off.set_tets(tets, "large", 1000.0, 0.3); off.set_plastic(0.0, 0.5, 0.9)
+    assert base.fem_add_force(zero, x).tobytes() == off.fem_add_force(zero, x).tobytes()
+    s = O.OracleScene(dtype, pos); s.set_tets(tets, "large", 1000.0, 0.3); s.set_plastic(0.7, 1e9, 0.9)
+    s.fem_add_force(zero, x)
+    assert np.abs(s.get("tet.plasticStrains")).max() == 0          # never above the yield threshold
+    s.set_plastic(0.7, 0.05, 0.9)
+    f1 = s.fem_add_force(zero, x)
+    n = np.linalg.norm(s.get("tet.plasticStrains").astype(np.float64), axis=1)
+    assert n.max() > 0 and n.max() <= 0.7 * (1 + 1e-5)
+    assert np.abs(f1 - base.fem_add_force(zero, x)).max() > 0
+    assert np.abs(s.fem_add_force(zero, pos.astype(dtype))).max() > 0   # permanent set
+    s.tet_reset()
+    assert np.abs(s.fem_add_force(zero, pos.astype(dtype))).max() < (1e-2 if dtype == np.float32 else 1e-9)
