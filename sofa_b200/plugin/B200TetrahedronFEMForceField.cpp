@@ -34,6 +34,9 @@ public:
         desc.n_young = young.size(); desc.young = young.data();                                                                      \
         desc.n_poisson = poisson.size(); desc.poisson = poisson.data();                                                              \
         desc.n_local_stiffness = lsf.size(); desc.local_stiffness = lsf.data();                                                     \
+        desc.plastic_max_threshold = double(d_plasticMaxThreshold.getValue());     /* plasticity branch of computeForce, .inl:357-371 */ \
+        desc.plastic_yield_threshold = double(d_plasticYieldThreshold.getValue());                                                  \
+        desc.plastic_creep = double(d_plasticCreep.getValue());                                                                      \
         if (data.ff) { sofab200_tetfem_destroy(data.ff); data.ff = nullptr; }                                                        \
         const int rc = sofab200_tetfem_create(sofa::b200::threadContext(), B200Vec3Types<TReal>::abiReal, rest.size(), rest.hostRead(), \
                                               _indexedElements->size(), reinterpret_cast<const uint32_t*>(_indexedElements->data()), \
@@ -60,6 +63,13 @@ public:
         const double k = sofa::core::mechanicalparams::kFactorIncludingRayleighDamping(mparams, this->rayleighStiffness.getValue()); \
         if (sofab200_tetfem_add_dforce(data.ff, df.deviceWrite(), dx.deviceRead(), k) != SOFAB200_OK) msg_error() << sofab200_last_error(); \
         d_df.endEdit();                                                                                                              \
+    }                                                                                                                                \
+    template <> void TetrahedronFEMForceField<B200Vec3Types<TReal>>::reset() { /* .inl:1380-1388 */                                  \
+        if (data.ff && sofab200_tetfem_reset(data.ff) != SOFAB200_OK) msg_error() << sofab200_last_error();                          \
+    }                                                                                                                                \
+    template <> void TetrahedronFEMForceField<B200Vec3Types<TReal>>::getRotations(VecReal& vecR) { /* .inl:2033-2042 */             \
+        vecR.resize(9 * this->mstate->getSize());                                                                                    \
+        if (sofab200_tetfem_get_rotations(data.ff, vecR.deviceWrite()) != SOFAB200_OK) msg_error() << sofab200_last_error();         \
     }
 B200_TETFEM(float)
 B200_TETFEM(double)
