@@ -221,6 +221,75 @@ def read_gmsh(path):
 # ReadState.inl:219-262): one block per exported time, "T= <time>" then "  X= x0 y0 z0 x1 ...", "  V= ...", optionally "  F= ...",
 # "  X0= ...".  The reference writes with the stream's default precision (6 significant digits); `precision=17` keeps doubles exact.
 # ---------------------------------------------------------------------------------------------------
+def read_vtk_legacy(path):
+    """Legacy VTK file ("# vtk DataFile Version x.y"), DATASET UNSTRUCTURED_GRID, ASCII or BINARY (big-endian), the volumetric subset
+    MeshVTKLoader feeds this path (Sofa/Component/IO/Mesh/src/sofa/component/io/mesh/MeshVTKLoader.cpp: LegacyVTKReader; cell types
+    10 = VTK_TETRA, 12 = VTK_HEXAHEDRON, same corner order as SOFA's Tetrahedron / Hexahedron) -> (positions, tetrahedra, hexahedra).
+    Other cell types are skipped; POINT_DATA / CELL_DATA are ignored."""
+    with open(path, "rb") as fh:
+        raw = fh.read()
+    pos_in_file = 0
+
+    def line():
+        nonlocal pos_in_file
+        while True:
+            j = raw.find(b"\n", pos_in_file)
+            if j < 0:
+                j = len(raw)
+            ln = raw[pos_in_file:j].decode("ascii", "replace").strip()
+            pos_in_file = min(j + 1, len(raw))
+            if ln or pos_in_file >= len(raw):
+                return ln
+
+    if not line().lower().startswith("# vtk datafile"):
+        raise ValueError(f"{path}: not a legacy VTK file")
+    line()                                   # title
+    binary = line().upper() == "BINARY"
+    ds = line().upper().split()
+    if ds[:2] != ["DATASET", "UNSTRUCTURED_GRID"]:
+        raise ValueError(f"{path}: only DATASET UNSTRUCTURED_GRID is read here (found {' '.join(ds)})")
+    vtk_types = {"float": ">f4", "double": ">f8", "int": ">i4", "unsigned_int": ">u4", "long": ">i8", "vtktypeint64": ">i8", "vtktypeint32": ">i4",
+                 "unsigned_char": ">u1", "char": ">i1", "short": ">i2", "unsigned_short": ">u2", "unsigned_long": ">u8"}
+
+    def numbers(count, vtype):
+        nonlocal pos_in_file
+        if binary:
+            dt = np.dtype(vtk_types[vtype])
+            a = np.frombuffer(raw, dt, count, pos_in_file)
+            pos_in_file += count * dt.itemsize
+            return a
+        out = []
+        while len(out) < count:
+            out.extend(line().split())
+        return np.array(out[:count], np.float64 if vtype in ("float", "double") else np.int64)
+
+    pos = np.zeros((0, 3)); cells = None; ctypes_ = None; n_cells = 0
+    while pos_in_file < len(raw):
+        w = line().split()
+        if not w:
+            continue
+        key = w[0].upper()
+        if key == "POINTS":
+            pos = numbers(3 * int(w[1]), w[2].lower()).astype(np.float64).reshape(-1, 3)
+        elif key == "CELLS":
+            n_cells = int(w[1]); cells = numbers(int(w[2]), "int").astype(np.int64)
+        elif key == "CELL_TYPES":
+            ctypes_ = numbers(int(w[1]), "int").astype(np.int64)
+        elif key in ("POINT_DATA", "CELL_DATA"):
+            break
+    if cells is None or ctypes_ is None:
+        raise ValueError(f"{path}: CELLS / CELL_TYPES missing")
+    tets, hexas = [], []
+    i = 0
+    for c in range(n_cells):
+        k = int(cells[i]); nodes = cells[i + 1:i + 1 + k]; i += 1 + k
+        if ctypes_[c] == 10 and k == 4:
+            tets.append(nodes)
+        elif ctypes_[c] == 12 and k == 8:
+            hexas.append(nodes)
+    return pos, np.array(tets, np.uint32).reshape(-1, 4), np.array(hexas, np.uint32).reshape(-1, 8)
+
+
 def write_state(path, frames, precision=6):
     """frames: iterable of dicts {"T": time, "X": [n,3], "V": [n,3], ...} (keys other than T are optional)."""
     fmt = f"%.{int(precision)}g"

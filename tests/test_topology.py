@@ -85,3 +85,34 @@ def test_gmsh_v2_reader_matches_v1(tmp_path):
     p1, t1, h1 = T.read_gmsh(v1)
     p2, t2, h2 = T.read_gmsh(v2)
     assert (p1 == p2).all() and (t1 == t2).all() and t1.tolist() == [[0, 1, 2, 3], [1, 2, 3, 4]] and h1.shape == (0, 8) and h2.shape == (0, 8)
+
+
+@pytest.mark.parametrize("binary", [False, True], ids=["ascii", "binary"])
+def test_vtk_legacy_unstructured_grid_reader(tmp_path, binary):
+    """Legacy VTK UNSTRUCTURED_GRID, the volumetric subset of MeshVTKLoader (cell types 10 tetra / 12 hexahedron; 5 = triangle skipped)."""
+    from sofa_b200 import topology as T
+    pos, hexas = T.regular_grid((3, 2, 2), (0, 0, 0), (2, 1, 1))
+    tets = T.hexas_to_tetras(hexas[:1], (3, 2, 2), "mapping")
+    cells = [(10, t) for t in tets] + [(5, [0, 1, 2])] + [(12, h) for h in hexas[1:]]
+    size = sum(1 + len(c[1]) for c in cells)
+    path = tmp_path / "mesh.vtk"
+    with open(path, "wb") as fh:
+        fh.write(b"# vtk DataFile Version 3.0\nsofa_b200 test\n" + (b"BINARY" if binary else b"ASCII") + b"\nDATASET UNSTRUCTURED_GRID\n")
+        fh.write(f"POINTS {pos.shape[0]} {'double' if binary else 'float'}\n".encode())
+        if binary:
+            fh.write(pos.astype(">f8").tobytes() + b"\n")
+        else:
+            fh.write("\n".join(" ".join(repr(float(v)) for v in p) for p in pos).encode() + b"\n")
+        fh.write(f"\nCELLS {len(cells)} {size}\n".encode())
+        flat = np.concatenate([np.concatenate([[len(c[1])], np.asarray(c[1], np.int64)]) for c in cells])
+        fh.write(flat.astype(">i4").tobytes() + b"\n" if binary else (" ".join(str(int(v)) for v in flat) + "\n").encode())
+        fh.write(f"CELL_TYPES {len(cells)}\n".encode())
+        ct = np.array([c[0] for c in cells])
+        fh.write(ct.astype(">i4").tobytes() + b"\n" if binary else ("\n".join(str(int(v)) for v in ct) + "\n").encode())
+        fh.write(b"CELL_DATA 1\nSCALARS x float\n")
+    p2, t2, h2 = T.read_vtk_legacy(str(path))
+    assert np.array_equal(p2, pos) and np.array_equal(t2, tets) and np.array_equal(h2, hexas[1:])
+    with open(tmp_path / "poly.vtk", "wb") as fh:
+        fh.write(b"# vtk DataFile Version 3.0\nt\nASCII\nDATASET POLYDATA\nPOINTS 0 float\n")
+    with pytest.raises(ValueError):
+        T.read_vtk_legacy(str(tmp_path / "poly.vtk"))
