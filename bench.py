@@ -218,7 +218,13 @@ def run_ours(args):
     dtype, template, s = (np.float32, "B200Vec3f", 4) if args.dtype == "f32" else (np.float64, "B200Vec3d", 8)
 
     if world > 1:
-        return run_ours_distributed(args, rank, world, local, dtype, template, s)
+        try:
+            return run_ours_distributed(args, rank, world, local, dtype, template, s)
+        finally:
+            import sys
+            sys.stdout.flush()
+            dist.barrier()
+            dist.destroy_process_group()
     # ---- synthetic input of BASELINE's shape
     pos, tets, fixed = build_mesh(args.workload)
     ctx = sb.Context(local)
