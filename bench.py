@@ -223,7 +223,6 @@ def run_ours(args):
         finally:
             import sys
             sys.stdout.flush()
-            dist.barrier()
             dist.destroy_process_group()
     # ---- synthetic input of BASELINE's shape
     pos, tets, fixed = build_mesh(args.workload)
