@@ -162,6 +162,8 @@ typedef struct sofab200_tetfem_desc {
     double plastic_max_threshold;   /* Data `plasticMaxThreshold` (2-norm of the strain); <= 0 = no plasticity (the default)   */
     double plastic_yield_threshold; /* Data `plasticYieldThreshold` (reference default 0.0001)                                  */
     double plastic_creep;           /* Data `plasticCreep` (reference default 0.9)                                              */
+    int compute_von_mises;          /* Data `computeVonMisesStress` (0 = off, 1 = corotational strain, 2 = Green-Lagrange strain):
+                                     * non-zero makes init keep the shape-function matrices and Lame coefficients ([TFF].inl:278-282,1521-1541) */
 } sofab200_tetfem_desc;
 
 /* init()+reinit() [TFF].inl:1257-1545: per-element material stiffness, rest rotation, rotated rest
@@ -183,6 +185,11 @@ int sofab200_tetfem_add_dforce(sofab200_tetfem* ff, void* df_dev, const void* dx
  *   "rotatedInitialElements" (T x 12), "initialTransformation" (T x 9, svd only),
  *   "plasticStrains" (T x 6, _plasticStrains; only with plastic_max_threshold > 0). */
 int sofab200_tetfem_get(sofab200_tetfem* ff, const char* what, void* out_host);
+/* computeVonMisesStress() [TFF].inl:2196-2416 at positions x (the reference runs it on AnimateEndEvent): von Mises stress per element
+ * (d_vonMisesPerElement, topology order) and per node (d_vonMisesPerNode: mean over the tetrahedra around the node, ascending index).
+ * Method 1 also rewrites rotations[e] from x, as the reference does.  Either output may be NULL.  Needs compute_von_mises != 0 at
+ * creation (the value passed there selects the method).  The colour map of the reference is display code and is not computed. */
+int sofab200_tetfem_compute_von_mises(sofab200_tetfem* ff, const void* x_dev, void* per_element_dev, void* per_node_dev);
 /* reset() [TFF].inl:1380-1388: clears the plastic strains (nothing else is reset by the reference). */
 int sofab200_tetfem_reset(sofab200_tetfem* ff);
 /* getRotations(VecReal& vecR) [TFF].inl:781-833,2033-2042 (what WarpPreconditioner / RotationMatrix consumers read; SofaCUDA:

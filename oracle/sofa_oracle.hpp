@@ -539,6 +539,7 @@ template <class R> struct TetFEM {
         R k33 = (1 - 2 * poissonRatio) / (2 * (1 - poissonRatio));
         const R s = (youngModulus * (1 - poissonRatio)) / ((1 + poissonRatio) * (1 - 2 * poissonRatio));
         k00 *= s; k01 *= s; k33 *= s;
+        elemLambda[i] = k01; elemMu[i] = k33;   // :278-282, before the division by 36 V
         const Coord A = initialPoints[b] - initialPoints[a], B = initialPoints[c] - initialPoints[a], C = initialPoints[d] - initialPoints[a];
         const R tetrahedronVolume = std::abs(dot(cross(A, B), C) / R(6));
         restVolume += tetrahedronVolume;
@@ -591,6 +592,7 @@ template <class R> struct TetFEM {
         const size_t T = nbTets();
         K.assign(3 * T, 0); J.assign(12 * T, 0);
         plasticStrains.assign(6 * T, R(0));   // :1415
+        elemLambda.assign(T, R(0)); elemMu.assign(T, R(0));   // :1424-1425
         restVolume = 0;
         if (method != SMALL) {
             rotations.assign(T, Mat3<R>()); initialRotations.assign(T, Mat3<R>());
@@ -747,6 +749,133 @@ template <class R> struct TetFEM {
             fn[2] -= rot(2, 0) * F[3 * n] + rot(2, 1) * F[3 * n + 1] + rot(2, 2) * F[3 * n + 2];
         }
     }
+    // ---- von Mises stress.  PARITY UNPINNED by reference vectors (no KAT in the reference tree).
+    // invertMatrix, general case (Sofa/framework/Type/src/sofa/type/Mat.h:1103-1166): Gauss-Jordan with full pivoting, S = 4
+    static bool invertMatrix4(R dest[4][4], const R from[4][4]) {
+        const int S = 4;
+        int r[S] = {0, 0, 0, 0}, c[S] = {0, 0, 0, 0}, row[S] = {0, 0, 0, 0}, col[S] = {0, 0, 0, 0};
+        R m1[S][S], m2[S][S];
+        for (int i = 0; i < S; ++i) for (int j = 0; j < S; ++j) { m1[i][j] = from[i][j]; m2[i][j] = i == j ? R(1) : R(0); }
+        for (int k = 0; k < S; k++) {
+            R pivot = 0;
+            for (int i = 0; i < S; i++) {
+                if (row[i]) continue;
+                for (int j = 0; j < S; j++) {
+                    if (col[j]) continue;
+                    R t = m1[i][j]; if (t < 0) t = -t;
+                    if (t > pivot) { pivot = t; r[k] = i; c[k] = j; }
+                }
+            }
+            if (rabs(pivot) <= std::numeric_limits<R>::epsilon()) return false;
+            row[r[k]] = col[c[k]] = 1;
+            pivot = m1[r[k]][c[k]];
+            for (int j = 0; j < S; ++j) m1[r[k]][j] /= pivot;
+            m1[r[k]][c[k]] = 1;
+            for (int j = 0; j < S; ++j) m2[r[k]][j] /= pivot;
+            for (int i = 0; i < S; i++) {
+                if (i != r[k]) {
+                    const R f = m1[i][c[k]];
+                    for (int j = 0; j < S; ++j) m1[i][j] -= m1[r[k]][j] * f;
+                    m1[i][c[k]] = 0;
+                    for (int j = 0; j < S; ++j) m2[i][j] -= m2[r[k]][j] * f;
+                }
+            }
+        }
+        for (int i = 0; i < S; i++) for (int j = 0; j < S; j++) if (c[j] == i) row[i] = r[j];
+        for (int i = 0; i < S; i++) for (int j = 0; j < S; ++j) dest[i][j] = m2[row[i]][j];
+        return true;
+    }
+    std::vector<R> elemLambda, elemMu;    // Lame coefficients of the element's material (:278-282)
+    std::vector<R> elemShapeFun;          // elemShapeFun[e]: inverse of [1 x0 y0 z0] rows, 16 per element (:1521-1541)
+    std::vector<R> vonMisesPerElement, vonMisesPerNode;
+    void initVonMises() {
+        const size_t T = nbTets();
+        elemShapeFun.assign(16 * T, R(0));
+        for (size_t i = 0; i < T; ++i) {
+            R matVert[4][4], inv[4][4];
+            for (int k = 0; k < 4; k++) { const uint32_t ix = tets[4 * i + k]; matVert[k][0] = R(1.0); for (int l = 1; l < 4; l++) matVert[k][l] = initialPoints[ix][l - 1]; }
+            for (auto& rw : inv) for (auto& v : rw) v = R(0);
+            invertMatrix4(inv, matVert);
+            for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) elemShapeFun[16 * i + 4 * a + b] = inv[a][b];
+        }
+    }
+    // computeVonMisesStress :2196-2416 (values only; the colour map is display code).  how = d_computeVonMisesStress (1 or 2).
+    void computeVonMisesStress(const std::vector<Coord>& X, int how) {
+        const size_t T = nbTets();
+        if (elemShapeFun.size() != 16 * T) initVonMises();
+        vonMisesPerElement.assign(T, R(0));
+        for (size_t el = 0; el < T; ++el) {
+            const uint32_t* index = &tets[4 * el];
+            const R* shf = &elemShapeFun[16 * el];
+            R vStrain[6];
+            Mat3<R> gradU;
+            if (how == 2) {
+                Coord U[4];
+                for (int m = 0; m < 4; ++m) U[m] = X[index[m]] - initialPoints[index[m]];
+                for (int k = 0; k < 3; k++) for (int l = 0; l < 3; l++) {
+                    gradU(k, l) = 0.0;
+                    for (int m = 0; m < 4; m++) gradU(k, l) += shf[4 * (l + 1) + m] * U[m][k];
+                }
+                const Mat3<R> gT = gradU.transposed();
+                const Mat3<R> strain = ((gradU + gT) + gT * gradU) * R(0.5);     // (Real)0.5 * (gradU + gradU^T + gradU^T gradU)
+                for (int i = 0; i < 3; i++) vStrain[i] = strain(i, i);
+                vStrain[3] = strain(1, 2); vStrain[4] = strain(0, 2); vStrain[5] = strain(0, 1);
+            } else {
+                Mat3<R> R_0_2;
+                R D[12];
+                const Coord* x0 = &X0[4 * el];
+                if (method == LARGE) {
+                    computeRotationLarge(R_0_2, X, index[0], index[1], index[2]);
+                    rotations[el] = R_0_2.transposed();
+                    Coord deforme[4];
+                    for (int i = 0; i < 4; ++i) deforme[i] = R_0_2 * X[index[i]];
+                    deforme[1][0] -= deforme[0][0];
+                    deforme[2][0] -= deforme[0][0];
+                    deforme[2][1] -= deforme[0][1];
+                    deforme[3] -= deforme[0];
+                    D[0] = 0; D[1] = 0; D[2] = 0;
+                    D[3] = x0[1][0] - deforme[1][0]; D[4] = 0; D[5] = 0;
+                    D[6] = x0[2][0] - deforme[2][0]; D[7] = x0[2][1] - deforme[2][1]; D[8] = 0;
+                    D[9] = x0[3][0] - deforme[3][0]; D[10] = x0[3][1] - deforme[3][1]; D[11] = x0[3][2] - deforme[3][2];
+                } else {  // POLAR / SVD: always the plain polar decomposition here (:2291-2299)
+                    Mat3<R> A;
+                    A.setRow(0, X[index[1]] - X[index[0]]); A.setRow(1, X[index[2]] - X[index[0]]); A.setRow(2, X[index[3]] - X[index[0]]);
+                    Decompose<R>::polarDecomposition(A, R_0_2);
+                    rotations[el] = R_0_2.transposed();
+                    Coord deforme[4];
+                    for (int i = 0; i < 4; ++i) deforme[i] = R_0_2 * X[index[i]];
+                    for (int n = 0; n < 4; ++n) for (int k = 0; k < 3; ++k) D[3 * n + k] = x0[n][k] - deforme[n][k];
+                }
+                for (int k = 0; k < 3; k++) for (int l = 0; l < 3; l++) {
+                    gradU(k, l) = 0.0;
+                    for (int m = 0; m < 4; m++) gradU(k, l) += shf[4 * (l + 1) + m] * D[3 * m + k];
+                }
+                const Mat3<R> strain = (gradU + gradU.transposed()) * R(0.5);
+                for (int i = 0; i < 3; i++) vStrain[i] = strain(i, i);
+                vStrain[3] = strain(1, 2); vStrain[4] = strain(0, 2); vStrain[5] = strain(0, 1);
+            }
+            const R lambda = elemLambda[el], mu = elemMu[el];
+            R s[6];
+            R traceStrain = 0.0;
+            for (int k = 0; k < 3; k++) { traceStrain += vStrain[k]; s[k] = vStrain[k] * 2 * mu; }
+            for (int k = 3; k < 6; k++) s[k] = vStrain[k] * 2 * mu;
+            for (int k = 0; k < 3; k++) s[k] += lambda * traceStrain;
+            R v = Decompose<R>::rsqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2] - s[0] * s[1] - s[1] * s[2] - s[2] * s[0] + 3 * s[3] * s[3] + 3 * s[4] * s[4] + 3 * s[5] * s[5]);
+            if (v < 1e-10) v = 0.0;
+            vonMisesPerElement[el] = v;
+        }
+        const size_t N = X.size();
+        std::vector<std::vector<uint32_t>> around(N);
+        for (size_t t = 0; t < T; ++t) for (int k = 0; k < 4; ++k) around[tets[4 * t + k]].push_back(uint32_t(t));
+        vonMisesPerNode.assign(N, R(0));
+        for (size_t dof = 0; dof < N; dof++) {
+            R a = 0.0;
+            for (size_t at = 0; at < around[dof].size(); at++) a += vonMisesPerElement[around[dof][at]];
+            if (!around[dof].empty()) a /= R(around[dof].size());
+            vonMisesPerNode[dof] = a;
+        }
+    }
+
     // getRotation :781-833 (what WarpPreconditioner / RotationMatrix consumers read): the mean of rotations[t] * R0(t) over the
     // tetrahedra around the node (TetrahedraAroundVertex lists them in ascending index), made orthogonal by polarDecomposition.
     // A node without tetrahedra takes the element _rotationIdx names (:803-808; the array is zero-filled, :850-853 overwrite it).

@@ -257,6 +257,7 @@ size_t orc_scene_get(void* h, const char* what, void* out) {
         else if (w == "tet.rotations") mats(sc.tet.rotations); else if (w == "tet.initialRotations") mats(sc.tet.initialRotations);
         else if (w == "tet.initialTransformation") mats(sc.tet.initialTransformation);
         else if (w == "tet.plasticStrains") reals(sc.tet.plasticStrains);
+        else if (w == "tet.elemShapeFun") reals(sc.tet.elemShapeFun);
         else if (w == "tet.J") reals(sc.tet.J); else if (w == "tet.K") reals(sc.tet.K); else if (w == "tet.X0") vec3(sc.tet.X0);
         else if (w == "hex.rotations") mats(sc.hex.rotations); else if (w == "hex.initialRotations") mats(sc.hex.initialRotations);
         else if (w == "hex.Ke") reals(sc.hex.Ke); else if (w == "hex.X0") vec3(sc.hex.X0); else if (w == "hex.Kmat") reals(sc.hex.Kmat);
@@ -311,6 +312,13 @@ void orc_scene_tet_set_plastic(void* h, double mx, double yield, double creep) {
     DISPATCH(h, { sc.tet.plastic[0] = R(mx); sc.tet.plastic[1] = R(yield); sc.tet.plastic[2] = R(creep); sc.tet.reset(); });
 }
 void orc_scene_tet_reset(void* h) { DISPATCH(h, { sc.tet.reset(); }); }
+// computeVonMisesStress at positions x (how = 1 or 2): per_element T Reals, per_node N Reals
+void orc_scene_tet_von_mises(void* h, const void* x, int how, void* per_element, void* per_node) {
+    DISPATCH(h, {
+        sc.tet.computeVonMisesStress(toVec<R>(x, sc.x.size()), how);
+        copyOut(sc.tet.vonMisesPerElement, per_element); copyOut(sc.tet.vonMisesPerNode, per_node);
+    });
+}
 // TetrahedronFEMForceField::getRotations(VecReal&): out = 9 Reals per node
 void orc_scene_tet_get_rotations(void* h, void* out) {
     DISPATCH(h, { std::vector<Mat3<R>> v; sc.tet.getRotations(v, sc.x.size()); copyMats(v, out); });

@@ -22,7 +22,7 @@ class TetFemDesc(C.Structure):
     _fields_ = [("method", C.c_int), ("n_young", C.c_size_t), ("young", C.POINTER(C.c_double)), ("n_poisson", C.c_size_t),
                 ("poisson", C.POINTER(C.c_double)), ("n_local_stiffness", C.c_size_t), ("local_stiffness", C.POINTER(C.c_double)),
                 ("tile_elems", C.c_int), ("shared_nodes", C.POINTER(C.c_ubyte)),
-                ("plastic_max_threshold", C.c_double), ("plastic_yield_threshold", C.c_double), ("plastic_creep", C.c_double)]
+                ("plastic_max_threshold", C.c_double), ("plastic_yield_threshold", C.c_double), ("plastic_creep", C.c_double), ("compute_von_mises", C.c_int)]
 
 
 class HexFemDesc(C.Structure):
@@ -96,6 +96,7 @@ SYMBOLS = {
     "sofab200_tetfem_stats": (_I, [_P, C.POINTER(_U64)]),
     "sofab200_tetfem_get_rotations": (_I, [_P, _P]),
     "sofab200_tetfem_reset": (_I, [_P]),
+    "sofab200_tetfem_compute_von_mises": (_I, [_P, _P, _P, _P]),
     "sofab200_hexfem_create": (_I, [_P, _I, _SZ, _P, _SZ, _P, C.POINTER(HexFemDesc), C.POINTER(_P)]),
     "sofab200_hexfem_destroy": (_I, [_P]),
     "sofab200_hexfem_add_force": (_I, [_P, _P, _P]),

@@ -168,7 +168,7 @@ class TetrahedronFEMForceField:
     (Real)0.0001f and (Real)0.9f, TetrahedronFEMForceField.inl:51-53)."""
 
     def __init__(self, mstate, tetrahedra, youngModulus=5000.0, poissonRatio=0.45, method="large", localStiffnessFactor=None,
-                 rayleighStiffness=0.0, tileElems=0, sharedNodes=None, plasticMaxThreshold=0.0, plasticYieldThreshold=float(np.float32(0.0001)), plasticCreep=float(np.float32(0.9))):
+                 rayleighStiffness=0.0, tileElems=0, sharedNodes=None, plasticMaxThreshold=0.0, plasticYieldThreshold=float(np.float32(0.0001)), plasticCreep=float(np.float32(0.9)), computeVonMisesStress=0):
         if method not in TET_METHODS:
             raise ValueError(f"method must be one of {list(TET_METHODS)}")
         self.mstate, self.ctx = mstate, mstate.ctx
@@ -180,6 +180,7 @@ class TetrahedronFEMForceField:
         if localStiffnessFactor is not None:
             l, lp = _darr(localStiffnessFactor); d.n_local_stiffness, d.local_stiffness = len(l), lp
         d.tile_elems = int(tileElems)
+        d.compute_von_mises = int(computeVonMisesStress)
         d.plastic_max_threshold, d.plastic_yield_threshold, d.plastic_creep = float(plasticMaxThreshold), float(plasticYieldThreshold), float(plasticCreep)
         if sharedNodes is not None:      # nodes that must take the staging path (partition interface of a multi-GPU run)
             self._shared = np.zeros(mstate.size, np.uint8); self._shared[np.asarray(sharedNodes, np.int64)] = 1
@@ -203,6 +204,14 @@ class TetrahedronFEMForceField:
         out = np.empty(shape, self.mstate.ndtype)
         check(self.ctx.L.sofab200_tetfem_get(self.h, what.encode(), out.ctypes.data_as(_P)))
         return out
+
+    def computeVonMisesStress(self, x):
+        """computeVonMisesStress() (TetrahedronFEMForceField.inl:2196-2416) at positions x -> (vonMisesPerElement, vonMisesPerNode) device tensors."""
+        import torch
+        pe = torch.empty(self.tetrahedra.shape[0], dtype=self.mstate.tdtype, device=self.ctx.device)
+        pn = torch.empty(self.mstate.size, dtype=self.mstate.tdtype, device=self.ctx.device)
+        check(self.ctx.L.sofab200_tetfem_compute_von_mises(self.h, _dptr(x), _dptr(pe), _dptr(pn)))
+        return pe, pn
 
     def reset(self):
         """reset() (TetrahedronFEMForceField.inl:1380-1388): clears the plastic strains."""

@@ -22,6 +22,7 @@ template <class R> struct TetFF : sofab200_tetfem {
     DevBuf<uint32_t> tile_node_off, tile_nodes, tile_nint, tile_nb, sh_nodes, sh_base;
     DevBuf<uint16_t> tile_val, tile_jds, sh_val;
     DevBuf<Quad<R>> stage;
+    DevBuf<R> vm_shf, vm_lambda, vm_mu, vm_rest, vm_elem; int von_mises = 0;   // computeVonMisesStress (uploaded at the first call)
     DevBuf<Quad<R>> pl0, pl1; double plastic[3] = {0, 0, 0};   // _plasticStrains in tile order (plasticMaxThreshold > 0 only)
     DevBuf<R> rot_export;
     DevBuf<uint32_t> inc_off, inc_es, inc_e; DevBuf<R> r0t_el; uint32_t es_of_first = 0;   // getRotations: node -> incident elements (built at the first call)
@@ -205,6 +206,7 @@ template <class R> static int tet_create(sofab200_ctx* ctx, size_t n_nodes, cons
     ff->threads = (ff->h.plan.tile_e >= 2048 && sizeof(R) == 4) ? 512 : 256;
     if (const char* env = getenv("SOFAB200_TILE_THREADS")) { const int v = atoi(env); if (v >= 64 && v <= 1024 && v % 32 == 0) ff->threads = v; }
     if (const char* env = getenv("SOFAB200_PREFETCH")) ff->prefetch = atoi(env) != 0;
+    ff->von_mises = desc->compute_von_mises;
     ff->plastic[0] = desc->plastic_max_threshold; ff->plastic[1] = desc->plastic_yield_threshold; ff->plastic[2] = desc->plastic_creep;
     SB_TRY(tet_upload(*ff));
     *out = ff.release();
@@ -248,6 +250,7 @@ template <class R> static int tet_get(TetFF<R>& ff, const std::string& what, voi
     return fail(SOFAB200_ERR_INVALID, "unknown array name: " + what);
 }
 
+template <class R> static int tet_build_incidence(TetFF<R>& ff);
 // getRotations(VecReal&): 9 Reals per node into a device array
 template <class R> static int tet_node_rotations(TetFF<R>& ff, R* out_dev) {
     cudaStream_t s = ff.ctx->stream;
@@ -258,6 +261,15 @@ template <class R> static int tet_node_rotations(TetFF<R>& ff, R* out_dev) {
         SB_CUDA(cudaStreamSynchronize(s));
         return SOFAB200_OK;
     }
+    SB_TRY(tet_build_incidence(ff));
+    tet_node_rotations_kernel<R><<<unsigned((ff.n_nodes + 127) / 128), 128, 0, s>>>(ff.dev(), ff.inc_off.p, ff.inc_es.p, ff.inc_e.p, ff.r0t_el.p, ff.es_of_first, out_dev);
+    ff.ctx->launches++;
+    SB_CUDA(cudaGetLastError());
+    return SOFAB200_OK;
+}
+// node -> incident elements in ascending element index (TetrahedraAroundVertex order), built at the first use
+template <class R> static int tet_build_incidence(TetFF<R>& ff) {
+    cudaStream_t s = ff.ctx->stream;
     if (!ff.inc_off.p) {
         const HostPlan& P = ff.h.plan;
         const size_t NS = size_t(P.n_tiles) * P.tile_e, T = ff.n_tets;
@@ -278,9 +290,30 @@ template <class R> static int tet_node_rotations(TetFF<R>& ff, R* out_dev) {
         SB_TRY(ff.inc_off.upload(off, s)); SB_TRY(ff.inc_es.upload(ies, s)); SB_TRY(ff.inc_e.upload(ie, s)); SB_TRY(ff.r0t_el.upload(ff.h.h_R0t, s));
         SB_CUDA(cudaStreamSynchronize(s));
     }
-    tet_node_rotations_kernel<R><<<unsigned((ff.n_nodes + 127) / 128), 128, 0, s>>>(ff.dev(), ff.inc_off.p, ff.inc_es.p, ff.inc_e.p, ff.r0t_el.p, ff.es_of_first, out_dev);
+    return SOFAB200_OK;
+}
+// computeVonMisesStress(): per element (original order) and per node
+template <class R> static int tet_von_mises(TetFF<R>& ff, const R* x, R* per_element, R* per_node) {
+    if (!ff.von_mises) return fail(SOFAB200_ERR_UNSUPPORTED, "computeVonMisesStress was 0 when the force field was created");
+    if (ff.von_mises == 1 && ff.method == SOFAB200_TET_SMALL) return fail(SOFAB200_ERR_UNSUPPORTED, "computeVonMisesStress=1 needs a corotational method (the reference reads rotations it does not have with method small)");
+    cudaStream_t s = ff.ctx->stream;
+    if (!ff.vm_shf.p) {
+        SB_TRY(ff.vm_shf.upload(ff.h.h_shf, s)); SB_TRY(ff.vm_lambda.upload(ff.h.h_lambda, s)); SB_TRY(ff.vm_mu.upload(ff.h.h_mu, s)); SB_TRY(ff.vm_rest.upload(ff.h.h_rest, s));
+        SB_TRY(ff.vm_elem.alloc(ff.n_tets));
+        SB_CUDA(cudaStreamSynchronize(s));
+    }
+    R* vme = per_element ? per_element : ff.vm_elem.p;
+    const size_t NS = size_t(ff.h.plan.n_tiles) * ff.h.plan.tile_e;
+    if (NS) tet_von_mises_kernel<R><<<unsigned((NS + 127) / 128), 128, 0, s>>>(ff.dev(), ff.orig.p, x, ff.vm_rest.p, ff.vm_shf.p, ff.vm_lambda.p, ff.vm_mu.p, ff.von_mises,
+                                                                             ff.method == SOFAB200_TET_LARGE ? 1 : 0, vme);
     ff.ctx->launches++;
     SB_CUDA(cudaGetLastError());
+    if (per_node && ff.n_nodes) {
+        SB_TRY(tet_build_incidence(ff));
+        tet_von_mises_nodes_kernel<R><<<unsigned((ff.n_nodes + 127) / 128), 128, 0, s>>>(ff.n_nodes, ff.inc_off.p, ff.inc_e.p, vme, per_node);
+        ff.ctx->launches++;
+        SB_CUDA(cudaGetLastError());
+    }
     return SOFAB200_OK;
 }
 
@@ -292,6 +325,7 @@ int sofab200_tetfem_create(sofab200_ctx* ctx, sofab200_real real, size_t n_nodes
                            const uint32_t* tets_host, const sofab200_tetfem_desc* desc, sofab200_tetfem** out) {
     SB_CHECK(ctx && out && desc && rest_position_host && (tets_host || n_tets == 0), "null argument");
     SB_CHECK(desc->method >= 0 && desc->method <= 3, "method must be small, large, polar or svd");
+    SB_CHECK(desc->compute_von_mises >= 0 && desc->compute_von_mises <= 2, "computeVonMisesStress must be 0, 1 or 2");
     SB_CHECK(desc->n_young > 0 && desc->young && desc->n_poisson > 0 && desc->poisson, "youngModulus / poissonRatio are required");
     SB_CHECK(n_nodes < 0xFFFFFFFFull && n_tets < 0x3FFFFFFFull, "mesh too large for 32-bit indices");
     SB_CUDA(cudaSetDevice(ctx->device));
@@ -323,6 +357,11 @@ int sofab200_tetfem_get(sofab200_tetfem* ff, const char* what, void* out_host) {
     SB_CHECK(ff && what && out_host, "null argument");
     if (ff->real == SOFAB200_F32) return tet_get(*static_cast<TetFF<float>*>(ff), what, out_host);
     return tet_get(*static_cast<TetFF<double>*>(ff), what, out_host);
+}
+int sofab200_tetfem_compute_von_mises(sofab200_tetfem* ff, const void* x_dev, void* per_element_dev, void* per_node_dev) {
+    SB_CHECK(ff && x_dev, "null argument");
+    if (ff->real == SOFAB200_F32) return tet_von_mises(*static_cast<TetFF<float>*>(ff), static_cast<const float*>(x_dev), static_cast<float*>(per_element_dev), static_cast<float*>(per_node_dev));
+    return tet_von_mises(*static_cast<TetFF<double>*>(ff), static_cast<const double*>(x_dev), static_cast<double*>(per_element_dev), static_cast<double*>(per_node_dev));
 }
 int sofab200_tetfem_reset(sofab200_tetfem* ff) {
     SB_CHECK(ff, "null argument");

@@ -2,6 +2,7 @@
 // gather plan, and the element planes in tile order.  Pure host code (also used by tests/emu).
 #pragma once
 #include <cstring>
+#include <limits>
 
 #include "math3.cuh"
 #include "plan.h"
@@ -15,6 +16,7 @@ template <class R> struct HostTet {
     HostPlan plan;
     // element-ordered values, as the reference class keeps them
     std::vector<R> h_K, h_J, h_X0, h_R0t, h_A0inv;
+    std::vector<R> h_shf, h_lambda, h_mu, h_rest;   // computeVonMisesStress != 0: elemShapeFun rows 1..3 (12 per element), elemLambda, elemMu, d_initialPoints
     // element planes in tile order
     std::vector<ushort4> lnode; std::vector<uint4> slot;
     std::vector<Quad<R>> rk0, rk1, rk2, j0, j1, j2, x0a, x0b, x0c, sv[5];
@@ -41,6 +43,42 @@ template <class R> static void strain_displacement(R* j, const V3<R>& a, const V
     j[11] = pdet(a.x, b.x, c.x, a.y, b.y, c.y);
 }
 
+// invertMatrix, general case (Sofa/framework/Type/src/sofa/type/Mat.h:1103-1166): Gauss-Jordan with full pivoting, S = 4
+template <class R> static bool invert4(R dest[4][4], const R from[4][4]) {
+    const int S = 4;
+    int r[S] = {0, 0, 0, 0}, c[S] = {0, 0, 0, 0}, row[S] = {0, 0, 0, 0}, col[S] = {0, 0, 0, 0};
+    R m1[S][S], m2[S][S];
+    for (int i = 0; i < S; ++i) for (int j = 0; j < S; ++j) { m1[i][j] = from[i][j]; m2[i][j] = i == j ? R(1) : R(0); dest[i][j] = R(0); }
+    for (int k = 0; k < S; k++) {
+        R pivot = 0;
+        for (int i = 0; i < S; i++) {
+            if (row[i]) continue;
+            for (int j = 0; j < S; j++) {
+                if (col[j]) continue;
+                R t = m1[i][j]; if (t < 0) t = -t;
+                if (t > pivot) { pivot = t; r[k] = i; c[k] = j; }
+            }
+        }
+        if (std::abs(pivot) <= std::numeric_limits<R>::epsilon()) return false;
+        row[r[k]] = col[c[k]] = 1;
+        pivot = m1[r[k]][c[k]];
+        for (int j = 0; j < S; ++j) m1[r[k]][j] /= pivot;
+        m1[r[k]][c[k]] = 1;
+        for (int j = 0; j < S; ++j) m2[r[k]][j] /= pivot;
+        for (int i = 0; i < S; i++) {
+            if (i != r[k]) {
+                const R f = m1[i][c[k]];
+                for (int j = 0; j < S; ++j) m1[i][j] -= m1[r[k]][j] * f;
+                m1[i][c[k]] = 0;
+                for (int j = 0; j < S; ++j) m2[i][j] -= m2[r[k]][j] * f;
+            }
+        }
+    }
+    for (int i = 0; i < S; i++) for (int j = 0; j < S; j++) if (c[j] == i) row[i] = r[j];
+    for (int i = 0; i < S; i++) for (int j = 0; j < S; ++j) dest[i][j] = m2[row[i]][j];
+    return true;
+}
+
 // reinit(): TetrahedronFEMForceField.inl:1390-1505 with computeMaterialStiffness :255-291,
 // initSmall :526-532, initLarge :834-868, initPolar :992-1023, initSVD :1086-1117
 template <class R> static int tet_init_elements(HostTet<R>& ff, const R* x0, const uint32_t* tets, const sofab200_tetfem_desc* desc) {
@@ -52,6 +90,16 @@ template <class R> static int tet_init_elements(HostTet<R>& ff, const R* x0, con
     ff.h_K.assign(3 * T, 0); ff.h_J.assign(12 * T, 0); ff.h_X0.assign(12 * T, 0); ff.h_R0t.assign(9 * T, 0);
     if (ff.method == SOFAB200_TET_SVD) ff.h_A0inv.assign(9 * T, 0);
     auto P = [&](uint32_t n) { return mk3<R>(x0[3 * size_t(n)], x0[3 * size_t(n) + 1], x0[3 * size_t(n) + 2]); };
+    if (desc->compute_von_mises) {
+        // elemShapeFun :1521-1541: inverse of the matrix whose rows are (1, x0, y0, z0) of the 4 corners; only rows 1..3 are ever read
+        ff.h_lambda.assign(T, 0); ff.h_mu.assign(T, 0); ff.h_shf.assign(12 * T, 0); ff.h_rest.assign(x0, x0 + 3 * ff.n_nodes);
+        for (size_t i = 0; i < T; ++i) {
+            R mv[4][4], inv[4][4];
+            for (int k = 0; k < 4; ++k) { const size_t ix = tets[4 * i + k]; mv[k][0] = R(1.0); for (int l = 1; l < 4; ++l) mv[k][l] = x0[3 * ix + l - 1]; }
+            invert4(inv, mv);
+            for (int l = 1; l < 4; ++l) for (int m = 0; m < 4; ++m) ff.h_shf[12 * i + 4 * (l - 1) + m] = inv[l][m];
+        }
+    }
     for (size_t i = 0; i < T; ++i) {
         const uint32_t ia = tets[4 * i], ib = tets[4 * i + 1], ic = tets[4 * i + 2], id = tets[4 * i + 3];
         const V3<R> a = P(ia), b = P(ib), c = P(ic), d = P(id);
@@ -62,6 +110,7 @@ template <class R> static int tet_init_elements(HostTet<R>& ff, const R* x0, con
         R k00 = 1, k01 = nu / (1 - nu), k33 = (1 - 2 * nu) / (2 * (1 - nu));
         const R s = (E * (1 - nu)) / ((1 + nu) * (1 - 2 * nu));
         k00 *= s; k01 *= s; k33 *= s;
+        if (desc->compute_von_mises) { ff.h_lambda[i] = k01; ff.h_mu[i] = k33; }   // elemLambda / elemMu, :278-282 (before the division by 36 V)
         const R vol = std::abs(dot3(cross3(b - a, c - a), d - a) / R(6));  // geometry::Tetrahedron::volume
         const R div = vol * 36;
         ff.h_K[3 * i] = k00 / div; ff.h_K[3 * i + 1] = k01 / div; ff.h_K[3 * i + 2] = k33 / div;

@@ -352,6 +352,114 @@ template <class R> __global__ void tet_export_rotations_kernel(TetDev<R> d, cons
     o[0] = q0.a; o[1] = q0.b; o[2] = q0.c; o[3] = q0.d; o[4] = q1.a; o[5] = q1.b; o[6] = q1.c; o[7] = q1.d; o[8] = q2.a;
 }
 
+// computeVonMisesStress, TetrahedronFEMForceField.inl:2196-2360: one thread per element (tile order).  how = 1: strain of the corotational
+// displacement D (rotation recomputed from x and written to rotations[e], as the reference does); how = 2: Green-Lagrange strain of
+// U = x - x0.  shf = rows 1..3 of elemShapeFun in ORIGINAL element order, out = d_vonMisesPerElement in original order.
+template <class R> __global__ void tet_von_mises_kernel(TetDev<R> d, const uint32_t* __restrict__ orig, const R* __restrict__ x, const R* __restrict__ rest,
+                                                        const R* __restrict__ shf_all, const R* __restrict__ lambda, const R* __restrict__ mu, int how, int large,
+                                                        R* __restrict__ out) {
+    const size_t es = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (es >= size_t(d.t.n_tiles) * d.t.tile_e) return;
+    const uint32_t e = orig[es];
+    if (e == 0xFFFFFFFFu) return;
+    const size_t tile = es / size_t(d.t.tile_e);
+    const ushort4 ln = d.lnode[es];
+    const uint32_t* tn = d.t.tile_nodes + d.t.tile_node_off[tile];
+    const uint32_t g[4] = {tn[ln.x], tn[ln.y], tn[ln.z], tn[ln.w]};
+    V3<R> P[4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) P[n] = mk3<R>(x[3 * size_t(g[n])], x[3 * size_t(g[n]) + 1], x[3 * size_t(g[n]) + 2]);
+    const R* shf = shf_all + 12 * size_t(e);
+    R D[12];
+    if (how == 2) {
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            D[3 * n] = P[n].x - rest[3 * size_t(g[n])]; D[3 * n + 1] = P[n].y - rest[3 * size_t(g[n]) + 1]; D[3 * n + 2] = P[n].z - rest[3 * size_t(g[n]) + 2];
+        }
+    } else {
+        const Quad<R> xa = d.x0a[es], xb = d.x0b[es], xc = d.x0c[es];
+        const R X0[12] = {xa.a, xa.b, xa.c, xa.d, xb.a, xb.b, xb.c, xb.d, xc.a, xc.b, xc.c, xc.d};
+        M3<R> R02;
+        if (large) {
+            V3<R> ex = P[1] - P[0];
+            normalize3(ex);
+            V3<R> ey = P[2] - P[0];
+            V3<R> ez = cross3(ex, ey);
+            normalize3(ez);
+            ey = cross3(ez, ex);
+            set_row(R02, 0, ex); set_row(R02, 1, ey); set_row(R02, 2, ez);
+        } else {
+            M3<R> A;
+            set_row(A, 0, P[1] - P[0]); set_row(A, 1, P[2] - P[0]); set_row(A, 2, P[3] - P[0]);
+            polar_decomposition(A, R02);
+        }
+        const M3<R> rot = transpose(R02);
+        const Quad<R> q2 = d.rk2[es];
+        d.rk0[es] = Quad<R>{rot.m[0][0], rot.m[0][1], rot.m[0][2], rot.m[1][0]};
+        d.rk1[es] = Quad<R>{rot.m[1][1], rot.m[1][2], rot.m[2][0], rot.m[2][1]};
+        d.rk2[es] = Quad<R>{rot.m[2][2], q2.b, q2.c, q2.d};
+        V3<R> def[4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) def[n] = mul(R02, P[n]);
+        if (large) {
+            def[1].x -= def[0].x;
+            def[2].x -= def[0].x;
+            def[2].y -= def[0].y;
+            def[3].x -= def[0].x; def[3].y -= def[0].y; def[3].z -= def[0].z;
+            D[0] = 0; D[1] = 0; D[2] = 0;
+            D[3] = X0[3] - def[1].x; D[4] = 0; D[5] = 0;
+            D[6] = X0[6] - def[2].x; D[7] = X0[7] - def[2].y; D[8] = 0;
+            D[9] = X0[9] - def[3].x; D[10] = X0[10] - def[3].y; D[11] = X0[11] - def[3].z;
+        } else {
+#pragma unroll
+            for (int n = 0; n < 4; ++n) { D[3 * n] = X0[3 * n] - def[n].x; D[3 * n + 1] = X0[3 * n + 1] - def[n].y; D[3 * n + 2] = X0[3 * n + 2] - def[n].z; }
+        }
+    }
+    // gradU(k,l) = sum_m shf(l+1,m) * D[3m+k], accumulated from 0.0 (:2236-2241, 2319-2324)
+    R gu[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            R a = R(0);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) a += shf[4 * l + m] * D[3 * m + k];
+            gu[k][l] = a;
+        }
+    R st[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            R v = gu[i][j] + gu[j][i];
+            if (how == 2) v = v + (gu[0][i] * gu[0][j] + gu[1][i] * gu[1][j] + gu[2][i] * gu[2][j]);   // + gradU^T gradU (Mat.h 3x3 product)
+            st[i][j] = v * R(0.5);
+        }
+    const R vs[6] = {st[0][0], st[1][1], st[2][2], st[1][2], st[0][2], st[0][1]};
+    const R lam = lambda[e], m_ = mu[e];
+    R s[6];
+    R tr = R(0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { tr += vs[k]; s[k] = vs[k] * 2 * m_; }
+#pragma unroll
+    for (int k = 3; k < 6; ++k) s[k] = vs[k] * 2 * m_;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s[k] += lam * tr;
+    R v = R(sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2] - s[0] * s[1] - s[1] * s[2] - s[2] * s[0] + 3 * s[3] * s[3] + 3 * s[4] * s[4] + 3 * s[5] * s[5]));
+    if (double(v) < 1e-10) v = R(0);
+    out[e] = v;
+}
+// d_vonMisesPerNode :2363-2372: mean of the incident elements' values, ascending element index
+template <class R> __global__ void tet_von_mises_nodes_kernel(size_t n, const uint32_t* __restrict__ inc_off, const uint32_t* __restrict__ inc_e, const R* __restrict__ vme, R* __restrict__ out) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t b = inc_off[i], e = inc_off[i + 1];
+    R a = R(0);
+    for (uint32_t k = b; k < e; ++k) a += vme[inc_e[k]];
+    if (e > b) a /= R(e - b);
+    out[i] = a;
+}
+
 // getRotation / getRotations(VecReal&), TetrahedronFEMForceField.inl:781-833,2033-2042: per node, the mean of rotations[t] * R0(t) over the
 // tetrahedra around it in ascending index, made orthogonal by polarDecomposition.  One thread per node; `inc` lists the tile-order slot
 // of the incident elements and `r0t` holds _initialRotations in ORIGINAL element order.  A node without tetrahedra takes element

@@ -37,6 +37,7 @@ public:
         desc.plastic_max_threshold = double(d_plasticMaxThreshold.getValue());     /* plasticity branch of computeForce, .inl:357-371 */ \
         desc.plastic_yield_threshold = double(d_plasticYieldThreshold.getValue());                                                  \
         desc.plastic_creep = double(d_plasticCreep.getValue());                                                                      \
+        desc.compute_von_mises = isComputeVonMisesStressMethodSet() ? int(d_computeVonMisesStress.getValue()) : 0;                   \
         if (data.ff) { sofab200_tetfem_destroy(data.ff); data.ff = nullptr; }                                                        \
         const int rc = sofab200_tetfem_create(sofa::b200::threadContext(), B200Vec3Types<TReal>::abiReal, rest.size(), rest.hostRead(), \
                                               _indexedElements->size(), reinterpret_cast<const uint32_t*>(_indexedElements->data()), \
@@ -66,6 +67,16 @@ public:
     }                                                                                                                                \
     template <> void TetrahedronFEMForceField<B200Vec3Types<TReal>>::reset() { /* .inl:1380-1388 */                                  \
         if (data.ff && sofab200_tetfem_reset(data.ff) != SOFAB200_OK) msg_error() << sofab200_last_error();                          \
+    }                                                                                                                                \
+    template <> void TetrahedronFEMForceField<B200Vec3Types<TReal>>::computeVonMisesStress() { /* .inl:2196-2372, values only */   \
+        if (!data.ff || !isComputeVonMisesStressMethodSet()) return;                                                                 \
+        const VecCoord& x = this->mstate->read(core::vec_id::read_access::position)->getValue();                                     \
+        auto& vME = *d_vonMisesPerElement.beginEdit(); auto& vMN = *d_vonMisesPerNode.beginEdit();                                   \
+        vME.resize(_indexedElements->size()); vMN.resize(x.size());                                                                  \
+        if (sofab200_tetfem_compute_von_mises(data.ff, x.deviceRead(), vME.deviceWrite(), vMN.deviceWrite()) != SOFAB200_OK)         \
+            msg_error() << sofab200_last_error();                                                                                    \
+        d_vonMisesPerElement.endEdit(); d_vonMisesPerNode.endEdit();                                                                 \
+        updateVonMisesStress = false;                                                                                                \
     }                                                                                                                                \
     template <> void TetrahedronFEMForceField<B200Vec3Types<TReal>>::getRotations(VecReal& vecR) { /* .inl:2033-2042 */             \
         vecR.resize(9 * this->mstate->getSize());                                                                                    \

@@ -241,6 +241,12 @@ class OracleScene:
         self.L.orc_scene_fem_add_dforce(self.h, _ptr(df), _ptr(np.ascontiguousarray(dx, self.dtype)), C.c_double(k_factor))
         return df
 
+    def tet_von_mises(self, x, how=1):
+        """computeVonMisesStress at positions x: (per element, per node)."""
+        pe = np.zeros(self.tets.shape[0], self.dtype); pn = np.zeros(self.n, self.dtype)
+        self.L.orc_scene_tet_von_mises(self.h, _ptr(np.ascontiguousarray(x, self.dtype)), int(how), _ptr(pe), _ptr(pn))
+        return pe, pn
+
     def tet_get_rotations(self):
         """TetrahedronFEMForceField::getRotations(VecReal&): per-node 3x3."""
         out = np.empty((self.n, 3, 3), self.dtype)

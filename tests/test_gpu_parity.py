@@ -108,6 +108,38 @@ def test_plasticity_branch_bit_exact(dtype, method, plastic):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("method", ["small", "large", "polar", "svd"])
+@pytest.mark.parametrize("how", [1, 2])
+def test_von_mises_stress_bit_exact(dtype, method, how):
+    """computeVonMisesStress (TetrahedronFEMForceField.inl:2196-2372): per element and per node, both strain measures."""
+    import sofa_b200 as sb
+    c, pos, hexas, tets, fixed = gpu_common.mesh("C1")
+    ctx = sb.Context(0)
+    mo = sb.MechanicalObject(ctx, "B200Vec3f" if dtype == np.float32 else "B200Vec3d", position=pos)
+    ff = sb.TetrahedronFEMForceField(mo, tets, youngModulus=c["young"], poissonRatio=c["poisson"], method=method, computeVonMisesStress=how)
+    rng = np.random.default_rng(21)
+    x = (pos + 0.2 * rng.standard_normal(pos.shape)).astype(dtype)
+    if method == "small" and how == 1:
+        with pytest.raises(sb.Sofab200Error):
+            ff.computeVonMisesStress(dev(mo, x))
+        return
+    s = oracle_scene("C1", dtype, method)
+    pe_ref, pn_ref = s.tet_von_mises(x, how)
+    pe, pn = ff.computeVonMisesStress(dev(mo, x))
+    assert pe.cpu().numpy().tobytes() == pe_ref.tobytes()
+    assert pn.cpu().numpy().tobytes() == pn_ref.tobytes()
+    assert pe_ref.max() > 0
+    if how == 1:
+        assert ff.get("rotations").tobytes() == s.get("tet.rotations").tobytes()     # method 1 rewrites rotations[e], as the reference does
+    # no stress in the rest configuration
+    pe0, _ = ff.computeVonMisesStress(dev(mo, pos.astype(dtype)))
+    assert float(pe0.max()) <= (1e-2 if dtype == np.float32 else 1e-9)
+    off = sb.TetrahedronFEMForceField(mo, tets, youngModulus=c["young"], poissonRatio=c["poisson"], method=method)
+    with pytest.raises(sb.Sofab200Error):
+        off.computeVonMisesStress(dev(mo, x))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("method", ["small", "large", "polar", "svd"])
 def test_get_rotations_per_node_bit_exact(dtype, method):
     """getRotations(VecReal&) (TetrahedronFEMForceField.inl:781-833): mean of rotations[t] * R0(t) around each node + polar."""
     g = gpu_scene("C1", dtype, method)

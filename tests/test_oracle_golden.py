@@ -224,3 +224,32 @@ def test_plasticity_restatement_properties(dtype):
     assert np.abs(s.fem_add_force(zero, pos.astype(dtype))).max() > 0   # permanent set
     s.tet_reset()
     assert np.abs(s.fem_add_force(zero, pos.astype(dtype))).max() < (1e-2 if dtype == np.float32 else 1e-9)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("method", ["large", "polar"])
+def test_von_mises_restatement_properties(dtype, method):
+    """computeVonMisesStress (TetrahedronFEMForceField.inl:2196-2372) has no KAT in the reference tree (PARITY UNPINNED by vectors):
+    a uniaxial strain eps with nu = 0 gives E*eps, a rigid motion gives zero with both strain measures, and the nodal value is the mean
+    of the incident elements' values."""
+    pos, hexas = O.regular_grid((3, 3, 3), (0, 0, 0), (2, 2, 2))
+    tets = O.hexas_to_tetras((3, 3, 3), 1)
+    s = O.OracleScene(dtype, pos); s.set_tets(tets, method, 1000.0, 0.0)
+    tol = 2e-3 if dtype == np.float32 else 1e-9
+    x = pos.copy(); x[:, 0] *= 1.001
+    # (strain measure 1 is only approximately E*eps in the reference itself: the element frames of `large` and `polar` are built from
+    # the edge matrix, not from the deformation gradient, and turn a little under a pure stretch -- 0.94 .. 1.37 on this mesh)
+    pe, pn = s.tet_von_mises(x, 1)
+    assert 0.9 < pe.min() and pe.max() < 1.5
+    pe, pn = s.tet_von_mises(x, 2)   # Green-Lagrange: E (eps + eps^2 / 2), whatever the method
+    assert np.abs(pe - 1.0005).max() < 50 * tol + 1e-5
+    a = 0.4
+    Q = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    for how in (1, 2):
+        pe, pn = s.tet_von_mises(pos @ Q.T + np.array([0.3, -0.2, 0.1]), how)
+        assert np.abs(pe).max() < (0.5 if dtype == np.float32 else 1e-9)
+    rng = np.random.default_rng(4)
+    pe, pn = s.tet_von_mises(pos + 0.05 * rng.standard_normal(pos.shape), 2)
+    acc = np.zeros(pos.shape[0]); cnt = np.zeros(pos.shape[0])
+    np.add.at(acc, tets.astype(np.int64).ravel(), np.repeat(pe.astype(np.float64), 4)); np.add.at(cnt, tets.astype(np.int64).ravel(), 1)
+    assert np.allclose(pn, acc / cnt, rtol=1e-5 if dtype == np.float32 else 1e-12)
