@@ -124,14 +124,17 @@ int sofab200_meshmass_create(sofab200_ctx* ctx, sofab200_real real, size_t n_nod
 }
 int sofab200_meshmass_destroy(sofab200_meshmass* mm) { delete mm; return SOFAB200_OK; }
 int sofab200_meshmass_add_mdx(sofab200_meshmass* mm, void* res_dev, const void* dx_dev, double factor) {
-    SB_CHECK(mm && res_dev && dx_dev, "null argument");
+    SB_CHECK(mm, "null argument");
+    if (!mm->n_nodes) return SOFAB200_OK;      // an empty state has no device arrays
+    SB_CHECK(res_dev && dx_dev, "null argument");
     SB_CHECK(res_dev != dx_dev, "res and dx must be distinct vectors");
     if (mm->real == SOFAB200_F32) return meshmass_mdx(*static_cast<MeshMass<float>*>(mm), static_cast<float*>(res_dev), static_cast<const float*>(dx_dev), factor);
     return meshmass_mdx(*static_cast<MeshMass<double>*>(mm), static_cast<double*>(res_dev), static_cast<const double*>(dx_dev), factor);
 }
 int sofab200_meshmass_add_force(sofab200_meshmass* mm, void* f_dev, const double gravity[3]) {
-    SB_CHECK(mm && f_dev && gravity, "null argument");
+    SB_CHECK(mm && gravity, "null argument");
     if (!mm->n_nodes) return SOFAB200_OK;
+    SB_CHECK(f_dev, "null argument");
     const unsigned g = unsigned((mm->n_nodes + 127) / 128);
     if (mm->real == SOFAB200_F32) { auto* m = static_cast<MeshMass<float>*>(mm); meshmass_force_kernel<float><<<g, 128, 0, mm->ctx->stream>>>(mm->n_nodes, static_cast<float*>(f_dev), m->vm.p, float(gravity[0]), float(gravity[1]), float(gravity[2]), float(mm->coeff)); }
     else { auto* m = static_cast<MeshMass<double>*>(mm); meshmass_force_kernel<double><<<g, 128, 0, mm->ctx->stream>>>(mm->n_nodes, static_cast<double*>(f_dev), m->vm.p, gravity[0], gravity[1], gravity[2], mm->coeff); }
@@ -140,7 +143,7 @@ int sofab200_meshmass_add_force(sofab200_meshmass* mm, void* f_dev, const double
     return SOFAB200_OK;
 }
 int sofab200_meshmass_acc_from_f(sofab200_meshmass* mm, void* a_dev, const void* f_dev) {
-    SB_CHECK(mm && a_dev && f_dev, "null argument");
+    SB_CHECK(mm && (mm->n_nodes == 0 || (a_dev && f_dev)), "null argument");
     if (!mm->lumping) return fail(SOFAB200_ERR_UNSUPPORTED, "accFromF cannot be used with the sparse MeshMatrixMass (the reference refuses too, MeshMatrixMass.inl:2053-2058): use lumping");
     if (!mm->n_nodes) return SOFAB200_OK;
     const unsigned g = unsigned((mm->n_nodes + 127) / 128);

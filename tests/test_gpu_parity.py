@@ -544,3 +544,47 @@ def test_empty_and_degenerate_inputs():
     ff0 = sb.TetrahedronFEMForceField(mo, np.zeros((0, 4), np.uint32), 1000.0, 0.3, "large")
     f_d = dev(mo, f0); ff0.addForce(f_d, dev(mo, x))
     assert f_d.cpu().numpy().tobytes() == f0.tobytes()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_per_node_outputs_with_isolated_nodes_and_no_elements(dtype):
+    """getRotations / computeVonMisesStress / MeshMatrixMass on degenerate topologies: nodes that belong to no element (the reference
+    gives them element _rotationIdx[node] = 0, a zero nodal stress and a zero mass row), one single element, and no element at all."""
+    import torch
+    import sofa_b200 as sb
+    ctx = sb.Context(0)
+    template = "B200Vec3f" if dtype == np.float32 else "B200Vec3d"
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [5, 5, 5], [1, 1, 1], [-3, 0, 2]], np.float64)
+    tets = np.array([[2, 3, 1, 0], [1, 2, 3, 5]], np.uint32)                      # nodes 4 and 6 are isolated
+    mo = sb.MechanicalObject(ctx, template, position=pos)
+    x = (pos + 0.1 * np.random.default_rng(8).standard_normal(pos.shape)).astype(dtype)
+    for method in ("large", "polar"):
+        ff = sb.TetrahedronFEMForceField(mo, tets, 1000.0, 0.3, method, computeVonMisesStress=1)
+        s = O.OracleScene(dtype, pos); s.set_tets(tets, method, 1000.0, 0.3)
+        f0 = np.zeros_like(x)
+        ff.addForce(dev(mo, f0), dev(mo, x)); s.fem_add_force(f0, x)
+        assert ff.getRotations().cpu().numpy().tobytes() == s.tet_get_rotations().tobytes()
+        pe, pn = ff.computeVonMisesStress(dev(mo, x))
+        pe_ref, pn_ref = s.tet_von_mises(x, 1)
+        assert pe.cpu().numpy().tobytes() == pe_ref.tobytes() and pn.cpu().numpy().tobytes() == pn_ref.tobytes()
+        assert pn_ref[4] == 0 and pn_ref[6] == 0
+    mm = sb.MeshMatrixMass(mo, tets, massDensity=2.0)
+    ref = O.OracleMeshMatrixMass(dtype, pos, tets, 2.0)
+    assert mm.vertexMass_host[4] == 0 and mm.edges.shape[0] == 9
+    r0 = np.ones_like(x); r = dev(mo, r0)
+    mm.addMDx(r, dev(mo, x), 0.7)
+    assert r.cpu().numpy().tobytes() == ref.addMDx(r0, x, 0.7).tobytes()
+    # no element at all
+    none = np.zeros((0, 4), np.uint32)
+    ff0 = sb.TetrahedronFEMForceField(mo, none, 1000.0, 0.3, "large", computeVonMisesStress=2)
+    R0 = ff0.getRotations().cpu().numpy()
+    assert np.array_equal(R0, np.broadcast_to(np.eye(3, dtype=dtype), R0.shape))
+    pe, pn = ff0.computeVonMisesStress(dev(mo, x))
+    assert pe.numel() == 0 and float(pn.abs().max()) == 0
+    mm0 = sb.MeshMatrixMass(mo, none, massDensity=2.0)
+    r = dev(mo, r0); mm0.addMDx(r, dev(mo, x), 0.7)
+    assert r.cpu().numpy().tobytes() == r0.astype(dtype).tobytes()
+    mo0 = sb.MechanicalObject(ctx, template, position=np.zeros((0, 3)))
+    mme = sb.MeshMatrixMass(mo0, none)
+    e = torch.zeros((0, 3), dtype=mo0.tdtype, device=ctx.device)
+    mme.addMDx(e, e.clone(), 1.0); mme.addForce(e, (0, -9, 0))
