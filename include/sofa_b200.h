@@ -220,6 +220,10 @@ int sofab200_hexfem_add_force(sofab200_hexfem* ff, void* f_dev, const void* x_de
 int sofab200_hexfem_add_dforce(sofab200_hexfem* ff, void* df_dev, const void* dx_dev, double k_factor);
 /* what: "rotations" (H x 9, _rotations[e] = R), "elementStiffnesses" (H x 576), "rotatedInitialElements" (H x 24) */
 int sofab200_hexfem_get(sofab200_hexfem* ff, const char* what, void* out_host);
+/* getRotations [HFF].inl:946-1023: getNodeRotation for every node -- identity + sum of _rotations[h] * _initialrotations[h]^T over the
+ * hexahedra around the node (ascending index), divided by their number, polar-decomposed (the reference starts the sum from the identity;
+ * reproduced as is).  vecR_dev: n_nodes x 9 `real`, row-major, device memory. */
+int sofab200_hexfem_get_rotations(sofab200_hexfem* ff, void* vecR_dev);
 /* as sofab200_tetfem_stats, except out[6] = number of unique (bit-identical) element stiffness matrices stored */
 int sofab200_hexfem_stats(const sofab200_hexfem* ff, uint64_t out[8]);
 

@@ -1080,6 +1080,26 @@ template <class R> struct HexaFEM {
         potentialEnergy /= -2.0;
     }
     // addDForce :248-286
+    // getNodeRotation :946-974: starts from the IDENTITY (not zero), adds _rotations[h] * _initialrotations[h]^T over the hexahedra around
+    // the node (ascending index), divides by their number and takes the polar decomposition.  getRotations :976-1023 stores it row-major.
+    void getNodeRotation(Mat3<R>& Rn, const std::vector<uint32_t>& liste_hexa) const {
+        Rn.identity();
+        const std::size_t numHexa = liste_hexa.size();
+        for (std::size_t ti = 0; ti < numHexa; ti++) {
+            const Mat3<R> prod = rotations[liste_hexa[ti]] * initialRotations[liste_hexa[ti]].transposed();
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rn.m[i][j] += prod.m[i][j];
+        }
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rn.m[i][j] = Rn.m[i][j] / numHexa;
+        Mat3<R> Rmoy;
+        Decompose<R>::polarDecomposition(Rn, Rmoy);
+        Rn = Rmoy;
+    }
+    void getRotations(std::vector<Mat3<R>>& vecR, size_t nbdof) const {
+        std::vector<std::vector<uint32_t>> around(nbdof);
+        for (size_t h = 0; h < hexas.size() / 8; ++h) for (int k = 0; k < 8; ++k) around[hexas[8 * h + k]].push_back(uint32_t(h));
+        vecR.assign(nbdof, Mat3<R>());
+        for (size_t i = 0; i < nbdof; ++i) getNodeRotation(vecR[i], around[i]);
+    }
     void addDForce(VecDeriv<R>& df, const VecDeriv<R>& dx, SReal kFactorIncludingRayleigh) {
         const R kFactor = (R)kFactorIncludingRayleigh;
         if (df.size() != dx.size()) df.resize(dx.size());

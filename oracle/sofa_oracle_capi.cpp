@@ -323,6 +323,10 @@ void orc_scene_tet_von_mises(void* h, const void* x, int how, void* per_element,
 void orc_scene_tet_get_rotations(void* h, void* out) {
     DISPATCH(h, { std::vector<Mat3<R>> v; sc.tet.getRotations(v, sc.x.size()); copyMats(v, out); });
 }
+// HexahedronFEMForceField::getNodeRotation for every node: out = 9 Reals per node
+void orc_scene_hex_get_rotations(void* h, void* out) {
+    DISPATCH(h, { std::vector<Mat3<R>> v; sc.hex.getRotations(v, sc.x.size()); copyMats(v, out); });
+}
 double orc_scene_hex_potential_energy(void* h) { double e = 0; DISPATCH(h, { e = sc.hex.potentialEnergy; }); return e; }
 
 }  // extern "C"

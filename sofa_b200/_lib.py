@@ -103,6 +103,7 @@ SYMBOLS = {
     "sofab200_hexfem_add_dforce": (_I, [_P, _P, _P, _D]),
     "sofab200_hexfem_get": (_I, [_P, C.c_char_p, _P]),
     "sofab200_hexfem_stats": (_I, [_P, C.POINTER(_U64)]),
+    "sofab200_hexfem_get_rotations": (_I, [_P, _P]),
     "sofab200_node_create": (_I, [_P, _I, _SZ, C.POINTER(NodeDesc), C.POINTER(_P)]),
     "sofab200_node_destroy": (_I, [_P]),
     "sofab200_node_set_params": (_I, [_P, C.POINTER(SolverParams)]),

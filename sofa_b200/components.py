@@ -268,6 +268,13 @@ class HexahedronFEMForceField:
         check(self.ctx.L.sofab200_hexfem_get(self.h, what.encode(), out.ctypes.data_as(_P)))
         return out
 
+    def getRotations(self, vecR=None):
+        """getNodeRotation for every node (HexahedronFEMForceField.inl:946-1023): n x 3 x 3 device tensor."""
+        if vecR is None:
+            vecR = torch.empty((self.mstate.size, 3, 3), dtype=self.mstate.tdtype, device=self.ctx.device)
+        check(self.ctx.L.sofab200_hexfem_get_rotations(self.h, _dptr(vecR)))
+        return vecR
+
     def stats(self):
         out = (C.c_uint64 * 8)()
         check(self.ctx.L.sofab200_hexfem_stats(self.h, out))

@@ -25,6 +25,7 @@ template <class R> struct HexFF : sofab200_hexfem {
     DevBuf<uint16_t> tile_val, tile_jds, sh_val;
     DevBuf<Quad<R>> stage;
     DevBuf<R> rot_export;
+    DevBuf<uint32_t> inc_off, inc_es, inc_e; DevBuf<R> rot0_el;   // getRotations: node -> incident elements (built at the first call)
     size_t n_unique = 0;
     HexDev<R> dev() {
         const HostPlan& plan = h.plan;
@@ -188,9 +189,42 @@ template <class R> static int hex_get(HexFF<R>& ff, const std::string& what, voi
     return fail(SOFAB200_ERR_INVALID, "unknown array name: " + what);
 }
 
+// getRotations: getNodeRotation for every node, 9 Reals per node into a device array
+template <class R> static int hex_node_rotations(HexFF<R>& ff, R* out_dev) {
+    cudaStream_t s = ff.ctx->stream;
+    if (!ff.inc_off.p) {
+        const HostPlan& P = ff.h.plan;
+        const size_t NS = size_t(P.n_tiles) * P.tile_e, H = ff.n_hexas;
+        std::vector<uint32_t> es_of(H, 0), node_of(8 * H), off(ff.n_nodes + 1, 0);
+        for (size_t es = 0; es < NS; ++es) {
+            const uint32_t e = P.order[es];
+            if (e == 0xFFFFFFFFu) continue;
+            es_of[e] = uint32_t(es);
+            const size_t tile = es / size_t(P.tile_e);
+            for (int k = 0; k < 8; ++k) { const uint32_t g = P.tile_nodes[P.tile_node_off[tile] + P.lnode[8 * es + k]]; node_of[8 * size_t(e) + k] = g; ++off[g + 1]; }
+        }
+        for (size_t n = 0; n < ff.n_nodes; ++n) off[n + 1] += off[n];
+        std::vector<uint32_t> fill(off.begin(), off.end() - 1), ies(8 * H), ie(8 * H);
+        for (size_t e = 0; e < H; ++e) for (int k = 0; k < 8; ++k) { const uint32_t at = fill[node_of[8 * e + k]]++; ies[at] = es_of[e]; ie[at] = uint32_t(e); }   // ascending element index
+        SB_TRY(ff.inc_off.upload(off, s)); SB_TRY(ff.inc_es.upload(ies, s)); SB_TRY(ff.inc_e.upload(ie, s)); SB_TRY(ff.rot0_el.upload(ff.h.h_rot0, s));
+        SB_CUDA(cudaStreamSynchronize(s));
+    }
+    if (!ff.n_nodes) return SOFAB200_OK;
+    hex_node_rotations_kernel<R><<<unsigned((ff.n_nodes + 127) / 128), 128, 0, s>>>(ff.dev(), ff.inc_off.p, ff.inc_es.p, ff.inc_e.p, ff.rot0_el.p, out_dev);
+    ff.ctx->launches++;
+    SB_CUDA(cudaGetLastError());
+    return SOFAB200_OK;
+}
+
 }  // namespace sb
 
 extern "C" {
+int sofab200_hexfem_get_rotations(sofab200_hexfem* ff, void* vecR_dev) {
+    SB_CHECK(ff && vecR_dev, "null argument");
+    if (ff->real == SOFAB200_F32) return hex_node_rotations(*static_cast<HexFF<float>*>(ff), static_cast<float*>(vecR_dev));
+    return hex_node_rotations(*static_cast<HexFF<double>*>(ff), static_cast<double*>(vecR_dev));
+}
+
 
 int sofab200_hexfem_create(sofab200_ctx* ctx, sofab200_real real, size_t n_nodes, const void* rest_position_host, size_t n_hexas,
                            const uint32_t* hexas_host, const sofab200_hexfem_desc* desc, sofab200_hexfem** out) {

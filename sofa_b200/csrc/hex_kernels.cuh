@@ -205,4 +205,49 @@ template <class R> __global__ void hex_export_rotations_kernel(HexDev<R> d, cons
     o[0] = q0.a; o[1] = q0.b; o[2] = q0.c; o[3] = q0.d; o[4] = q1.a; o[5] = q1.b; o[6] = q1.c; o[7] = q1.d; o[8] = q2.a;
 }
 
+// getNodeRotation, HexahedronFEMForceField.inl:946-974 (getRotations :976-1023): per node, identity + the sum of _rotations[h] * _initialrotations[h]^T
+// over the hexahedra around it (ascending index), divided by their number, made orthogonal by polarDecomposition.  The reference starts
+// the sum from the identity, not from zero; reproduced as is.  rot0 = _initialrotations in ORIGINAL element order.
+template <class R> __global__ void hex_node_rotations_kernel(HexDev<R> d, const uint32_t* __restrict__ inc_off, const uint32_t* __restrict__ inc_es,
+                                                             const uint32_t* __restrict__ inc_e, const R* __restrict__ rot0, R* __restrict__ out) {
+    const size_t n = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (n >= size_t(d.t.n_nodes)) return;
+    M3<R> acc;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc.m[i][j] = i == j ? R(1) : R(0);
+    const uint32_t b = inc_off[n], e = inc_off[n + 1];
+    for (uint32_t k = b; k < e; ++k) {
+        const uint32_t es = inc_es[k];
+        const Quad<R> q0 = d.r0[es], q1 = d.r1[es], q2 = d.r2[es];
+        M3<R> rot, r0t;
+        rot.m[0][0] = q0.a; rot.m[0][1] = q0.b; rot.m[0][2] = q0.c; rot.m[1][0] = q0.d; rot.m[1][1] = q1.a; rot.m[1][2] = q1.b;
+        rot.m[2][0] = q1.c; rot.m[2][1] = q1.d; rot.m[2][2] = q2.a;
+        const R* p = rot0 + 9 * size_t(inc_e[k]);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) r0t.m[i][j] = p[3 * j + i];
+        const M3<R> pr = mul(rot, r0t);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) acc.m[i][j] += pr.m[i][j];
+    }
+    const R cnt = R(e - b);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc.m[i][j] = acc.m[i][j] / cnt;
+    M3<R> q;
+    polar_decomposition(acc, q);
+    R* o = out + 9 * n;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) o[3 * i + j] = q.m[i][j];
+}
+
+
 }  // namespace sb

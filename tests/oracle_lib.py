@@ -241,6 +241,12 @@ class OracleScene:
         self.L.orc_scene_fem_add_dforce(self.h, _ptr(df), _ptr(np.ascontiguousarray(dx, self.dtype)), C.c_double(k_factor))
         return df
 
+    def hex_get_rotations(self):
+        """HexahedronFEMForceField::getNodeRotation for every node."""
+        out = np.empty((self.n, 3, 3), self.dtype)
+        self.L.orc_scene_hex_get_rotations(self.h, _ptr(out))
+        return out
+
     def tet_von_mises(self, x, how=1):
         """computeVonMisesStress at positions x: (per element, per node)."""
         pe = np.zeros(self.tets.shape[0], self.dtype); pn = np.zeros(self.n, self.dtype)

@@ -49,6 +49,8 @@ def test_hexa_add_force_add_dforce_bit_exact(dtype, method, perturb):
     assert f_d.cpu().numpy().tobytes() == s.fem_add_force(f0, x).tobytes()
     if method != "small":
         assert ff.get("rotations").tobytes() == s.get("hex.rotations").tobytes()
+    # getNodeRotation for every node (HexahedronFEMForceField.inl:946-974; the reference starts the mean from the identity)
+    assert ff.getRotations().cpu().numpy().tobytes() == s.hex_get_rotations().tobytes()
     dx = rng.standard_normal(x.shape).astype(dtype)
     for kf in (1.0, -0.0011):
         df_d = dev(mo, f0); ff.addDForce(df_d, dev(mo, dx), kf)
