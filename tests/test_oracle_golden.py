@@ -253,3 +253,22 @@ def test_von_mises_restatement_properties(dtype, method):
     acc = np.zeros(pos.shape[0]); cnt = np.zeros(pos.shape[0])
     np.add.at(acc, tets.astype(np.int64).ravel(), np.repeat(pe.astype(np.float64), 4)); np.add.at(cnt, tets.astype(np.int64).ravel(), 1)
     assert np.allclose(pn, acc / cnt, rtol=1e-5 if dtype == np.float32 else 1e-12)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_hexa_node_rotation_restatement(dtype):
+    """HexahedronFEMForceField::getNodeRotation (.inl:946-974; PARITY UNPINNED by vectors): the mean starts from the identity, so
+    at rest every node gets polar((1 + n) / n * I) = I, and under a rigid rotation Q a node with n hexahedra gets polar(I / n + Q)."""
+    pos, hexas = O.regular_grid((3, 3, 4), (0, 0, 0), (1, 1, 2))
+    s = O.OracleScene(dtype, pos); s.set_hexas(hexas, "polar", 1000.0, 0.3)
+    tol = 1e-5 if dtype == np.float32 else 1e-12
+    s.fem_add_force(np.zeros_like(pos, dtype), pos)
+    assert np.abs(s.hex_get_rotations() - np.eye(3)).max() < tol
+    a = 0.6
+    Q = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    s.fem_add_force(np.zeros_like(pos, dtype), pos @ Q.T)
+    cnt = np.zeros(pos.shape[0]); np.add.at(cnt, hexas.astype(np.int64).ravel(), 1)
+    got = s.hex_get_rotations().astype(np.float64)
+    for n in (0, 13, pos.shape[0] - 1):
+        u, _, vt = np.linalg.svd(np.eye(3) / cnt[n] + Q)
+        assert np.abs(got[n] - u @ vt).max() < 20 * tol
