@@ -258,7 +258,7 @@ def test_von_mises_restatement_properties(dtype, method):
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_hexa_node_rotation_restatement(dtype):
     """HexahedronFEMForceField::getNodeRotation (.inl:946-974; PARITY UNPINNED by vectors): the mean starts from the identity, so
-    at rest every node gets polar((1 + n) / n * I) = I, and under a rigid rotation Q a node with n hexahedra gets polar(I / n + Q)."""
+    at rest every node gets polar((1 + n) / n * I) = I, and under a rigid rotation Q a node with n hexahedra gets polar(I / n + Q^T)."""
     pos, hexas = O.regular_grid((3, 3, 4), (0, 0, 0), (1, 1, 2))
     s = O.OracleScene(dtype, pos); s.set_hexas(hexas, "polar", 1000.0, 0.3)
     tol = 1e-5 if dtype == np.float32 else 1e-12
@@ -270,5 +270,5 @@ def test_hexa_node_rotation_restatement(dtype):
     cnt = np.zeros(pos.shape[0]); np.add.at(cnt, hexas.astype(np.int64).ravel(), 1)
     got = s.hex_get_rotations().astype(np.float64)
     for n in (0, 13, pos.shape[0] - 1):
-        u, _, vt = np.linalg.svd(np.eye(3) / cnt[n] + Q)
+        u, _, vt = np.linalg.svd(np.eye(3) / cnt[n] + Q.T)   # the class keeps R (world -> element frame), the transpose of the tetra class's
         assert np.abs(got[n] - u @ vt).max() < 20 * tol
