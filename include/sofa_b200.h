@@ -278,6 +278,11 @@ int sofab200_node_add_mbkdx(sofab200_node* node, void* out_dev, const void* init
 /* Replace the node's DiagonalMass vertexMass (n Reals, host).  Used by the multi-GPU host layer to give every rank the
  * global lumped mass of its nodes, zeroed where another rank adds the mass term of a shared node. */
 int sofab200_node_set_vertex_mass(sofab200_node* node, const void* vertex_mass_host);
+/* The node's mass component is a MeshMatrixMass (same real type and context; it must precede the force field in the scene): its addForce /
+ * addMDx terms run as their own kernels and become the per-node start values of the element passes, so f, b and A*p keep the reference's
+ * order of operations.  The CG loop of such a node is the multi-kernel one (the persistent kernel has no neighbour access to p).
+ * Not available in a distributed node. */
+int sofab200_node_set_mesh_mass(sofab200_node* node, sofab200_meshmass* mesh_mass);
 /* CGLinearSolver::solve [CG]:73-315 for the matrix-free system (m M + b B + k K), entirely on the
  * device: no host round trip per iteration.  x_dev: solution (initial guess when warm_start).
  * nb_iter_host: NULL = leave the result on the device (async); else (sync) receives "CG iterations". */

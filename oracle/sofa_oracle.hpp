@@ -1337,6 +1337,7 @@ template <class R> struct Scene {
     std::vector<Coord> x, x0;
     VecDeriv<R> v, f, dx;
     DiagonalMass<R> mass;
+    MeshMatrixMass<R> meshMass; bool hasMeshMass = false;   // when set, the node's mass component is a MeshMatrixMass instead
     bool hasMass = true;
     double massRayleighMass = 0;      // Mass::rayleighMass Data of the mass component (default 0)
     TetFEM<R> tet; bool hasTet = false;
@@ -1408,9 +1409,10 @@ template <class R> struct Scene {
     // Sofa/framework/Simulation/Core/src/sofa/simulation/MappingGraphMechanicalOperations.cpp:41-93
     void computeForce(VecDeriv<R>& F) {
         F.assign(x.size(), Coord());
-        if (massFirst && hasMass) mass.addForce(F, gravity);
+        auto massForce = [&]() { if (hasMeshMass) meshMass.addForce(F, gravity); else mass.addForce(F, gravity); };
+        if (massFirst && hasMass) massForce();
         femAddForce(F);
-        if (!massFirst && hasMass) mass.addForce(F, gravity);
+        if (!massFirst && hasMass) massForce();
         if (hasPlane) plane.addForce(F, x, v);
     }
     // addMBKdx over the node's force fields: BaseForceField::addMBKdx (BaseForceField.cpp:38-47) and
@@ -1419,7 +1421,7 @@ template <class R> struct Scene {
         auto massPart = [&]() {
             if (!hasMass) return;
             const double mf = m - b * massRayleighMass;
-            if (mf != 0.0) mass.addMDx(df, d, mf);
+            if (mf != 0.0) { if (hasMeshMass) meshMass.addMDx(df, d, mf); else mass.addMDx(df, d, mf); }
         };
         auto femPart = [&]() {
             const double kf = k + b * ffRayleighStiffness;

@@ -163,6 +163,14 @@ void orc_scene_set_mass(void* h, int kind, double value, size_t nelems, const ui
     });
 }
 // PlaneForceField of the node: prm as for orc_plane, + its rayleighStiffness
+// the node's mass becomes a MeshMatrixMass over the tetrahedra (massDensity, lumping)
+void orc_scene_set_mesh_mass(void* h, size_t T, const uint32_t* tets, double density, int lumping) {
+    DISPATCH(h, {
+        std::vector<uint32_t> t(tets, tets + 4 * T);
+        sc.hasMass = true; sc.hasMeshMass = true;
+        sc.meshMass.initFromMassDensityTets(R(density), sc.x0, t, lumping != 0);
+    });
+}
 void orc_scene_set_plane(void* h, const double* prm, double rayleigh) {
     DISPATCH(h, {
         sc.hasPlane = true; sc.planeRayleighStiffness = rayleigh;

@@ -111,6 +111,7 @@ SYMBOLS = {
     "sofab200_node_apply": (_I, [_P, _P, _P, _D, _D, _D]),
     "sofab200_node_add_mbkdx": (_I, [_P, _P, _P, _P, _D, _D, _D, _I, _D, _I]),
     "sofab200_node_set_vertex_mass": (_I, [_P, _P]),
+    "sofab200_node_set_mesh_mass": (_I, [_P, _P]),
     "sofab200_node_cg_solve": (_I, [_P, _P, _P, _D, _D, _D, C.POINTER(_I)]),
     "sofab200_node_step": (_I, [_P, _P, _P]),
     "sofab200_node_step_host": (_I, [_P, _P, _P]),

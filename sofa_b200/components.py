@@ -419,7 +419,7 @@ class SolverNode:
             d.hexfem = forcefield.h
         if isinstance(mass, UniformMass):
             d.uniform_mass, d.uniform_vertex_mass = 1, mass.vertexMass_value
-        elif mass is not None:
+        elif mass is not None and not isinstance(mass, MeshMatrixMass):
             d.vertex_mass_host = mass.vertexMass_host.ctypes.data_as(_P)
         if constraint is not None:
             d.n_fixed = len(constraint.indices_host)
@@ -431,6 +431,8 @@ class SolverNode:
             d.plane = C.pointer(plane.desc); d.plane_rayleigh_stiffness = plane.rayleighStiffness
         self.h = _P()
         check(self.ctx.L.sofab200_node_create(self.ctx.h, mstate.real, mstate.size, C.byref(d), C.byref(self.h)))
+        if isinstance(mass, MeshMatrixMass):
+            check(self.ctx.L.sofab200_node_set_mesh_mass(self.h, mass.h))
         self.params = dict(dt=dt, gravity=tuple(gravity), rayleighStiffness=rayleighStiffness, rayleighMass=rayleighMass, vdamping=vdamping,
                            firstOrder=firstOrder, trapezoidalScheme=trapezoidalScheme, iterations=iterations, tolerance=tolerance,
                            threshold=threshold, warmStart=warmStart)

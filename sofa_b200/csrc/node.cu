@@ -101,6 +101,7 @@ template <class R> struct Node : sofab200_node {
     sofab200_tetfem* tet = nullptr;
     sofab200_hexfem* hex = nullptr;
     bool has_mass = false, mass_first = true;
+    sofab200_meshmass* mesh_mass = nullptr;   // MeshMatrixMass instead of a diagonal mass: its terms run as their own kernels before the element pass (per-node start values)
     bool uniform_mass = false; double um = 0.0;   // UniformMass: every entry of `mass` holds Real(um)
     bool has_plane = false; PlaneDev<R> plane; double plane_stiffness = 0, plane_rayleigh = 0;   // PlaneForceField, last force field of the node
     DevBuf<unsigned char> plane_contacts;
@@ -237,7 +238,7 @@ template <class R> struct Node : sofab200_node {
         return ep;
     }
     void set_mass_term(NodeEpilogue<R>& ep, int kind, const R* src, double factor) {
-        if (!has_mass) return;
+        if (!has_mass || mesh_mass) return;
         if (kind == PRE_MDX && factor == 0.0) return;  // Mass::addMBKdx skips a null factor (Mass.inl:96-99)
         if (mass_first) ep.pre_kind = kind; else ep.post_kind = kind;
         ep.mdx_src = src; ep.mass_factor = R(factor); ep.mass_factor_is_one = (factor == 1.0);
@@ -250,6 +251,11 @@ template <class R> struct Node : sofab200_node {
         NodeEpilogue<R> ep = base_ep();
         ep.init_src = nullptr; ep.sign = +1; ep.out = f_out;
         set_mass_term(ep, PRE_GRAVITY, nullptr, 1.0);
+        if (mesh_mass) {   // f = 0; MeshMatrixMass::addForce(f); the element pass then starts every node from that value (same order as the reference's visitor)
+            LAUNCH(ctx, (vop_kernel<R, VOP_CLEAR>), vec_grid(3 * n, ctx->sm_count), kVecBlock, 3 * n, f_out, (const R*)nullptr, (const R*)nullptr, R(0));
+            SB_TRY(sofab200_meshmass_add_force(mesh_mass, f_out, prm.gravity));
+            ep.init_src = f_out;
+        }
         if (has_plane) { ep.plane_mode = 1; ep.plane = plane; ep.plane_v = v; ep.plane_contacts = plane_contacts.p; ep.plane_in = x; }
         SB_TRY(fem_run(false, x, R(0), ep));
         return halo_sum(f_out, nullptr);
@@ -263,6 +269,7 @@ template <class R> struct Node : sofab200_node {
         ep.has_scale = scale; ep.scale = R(s);
         ep.fixed = (project && has_fixed) ? fixed.p : nullptr;
         ep.dot_kind = dot_kind; ep.dot_with = d; ep.cg = cgp;
+        if (mesh_mass) ep.init_src = out;   // add_mbk has put init + m M d there
         if (has_plane) {   // BaseForceField::addMBKdx for the plane: skipped when its kFactor and bFactor are both zero
             const double kfp = k + bfac * plane_rayleigh;
             if (kfp != 0.0 || bfac != 0.0) {
@@ -275,6 +282,15 @@ template <class R> struct Node : sofab200_node {
     int add_mbk(R* out, const R* init, const R* d, double m, double bfac, double k, bool scale, double s, bool project, int dot_kind, CGDev* cgp, bool skip_gather = false) {
         NodeEpilogue<R> ep = make_mbk_ep(out, init, d, m, bfac, k, scale, s, project, dot_kind, cgp);
         const double kf = k + bfac * prm.ff_rayleigh_stiffness;       // MechanicalParams.h:62
+        if (mesh_mass) {
+            // Mass::addMBKdx (Mass.inl:93-105) for the MeshMatrixMass, as its own kernel: out = init (or 0) + M d * mFactor
+            if (!mass_first) return fail(SOFAB200_ERR_UNSUPPORTED, "a MeshMatrixMass must precede the force field in the node");
+            if (distributed()) return fail(SOFAB200_ERR_UNSUPPORTED, "MeshMatrixMass is not available in a distributed node");
+            if (init) { if (init != out) SB_CUDA(cudaMemcpyAsync(out, init, 3 * n * sizeof(R), cudaMemcpyDeviceToDevice, ctx->stream)); }
+            else LAUNCH(ctx, (vop_kernel<R, VOP_CLEAR>), vec_grid(3 * n, ctx->sm_count), kVecBlock, 3 * n, out, (const R*)nullptr, (const R*)nullptr, R(0));
+            const double mf = m - bfac * prm.mass_rayleigh_mass;
+            if (mf != 0.0) SB_TRY(sofab200_meshmass_add_mdx(mesh_mass, out, d, mf));
+        }
         if (kf != 0.0 || bfac != 0.0) return fem_run(true, d, R(kf), ep, skip_gather);   // BaseForceField::addMBKdx, BaseForceField.cpp:38-47
         if (dot_kind != DOT_NONE) return fail(SOFAB200_ERR_UNSUPPORTED, "system without a stiffness term is not supported in the CG loop");
         LAUNCH(ctx, (node_only_kernel<R>), vec_grid(n, ctx->sm_count), kVecBlock, n, ep);
@@ -288,6 +304,7 @@ template <class R> struct Node : sofab200_node {
     int cg_solve(R* x, const R* bvec, double m, double bfac, double k) {
         const size_t n3 = 3 * n;
         const int g = vec_grid(n3, ctx->sm_count);
+        if (mesh_mass) persistent = false;   // the persistent kernel keeps p of interior nodes in shared memory: no neighbour access for the edge terms
         CGBegin cb{prm.iterations, prm.tolerance, prm.threshold};
         LAUNCH(ctx, cg_begin_kernel, 1, 1, cg.p, cb);
         if (prm.warm_start) {
@@ -766,6 +783,12 @@ int sofab200_node_add_mbkdx(sofab200_node* node, void* out_dev, const void* init
     SB_CHECK(node && out_dev && d_dev && out_dev != d_dev, "null or aliased argument");
     return NODE_DISPATCH(node, NF(node)->add_mbk((float*)out_dev, (const float*)init_dev, (const float*)d_dev, m, b, k, scale != 0, sf, project != 0, DOT_NONE, nullptr),
                          ND(node)->add_mbk((double*)out_dev, (const double*)init_dev, (const double*)d_dev, m, b, k, scale != 0, sf, project != 0, DOT_NONE, nullptr));
+}
+int sofab200_node_set_mesh_mass(sofab200_node* node, sofab200_meshmass* mesh_mass) {
+    SB_CHECK(node && mesh_mass, "null argument");
+    if (node->real == SOFAB200_F32) { NF(node)->mesh_mass = mesh_mass; NF(node)->has_mass = true; }
+    else { ND(node)->mesh_mass = mesh_mass; ND(node)->has_mass = true; }
+    return SOFAB200_OK;
 }
 int sofab200_node_set_vertex_mass(sofab200_node* node, const void* vertex_mass_host) {
     SB_CHECK(node && vertex_mass_host, "null argument");

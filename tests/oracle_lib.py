@@ -144,6 +144,10 @@ class OracleScene:
                                   0 if lsf is None else len(lsf), _ptr(lsf))
         self.tets = t
 
+    def set_mesh_mass(self, tets, density=1.0, lumping=False):
+        t = np.ascontiguousarray(tets, np.uint32)
+        self.L.orc_scene_set_mesh_mass(self.h, C.c_size_t(t.shape[0]), _ptr(t), C.c_double(density), int(lumping))
+
     def set_plastic(self, max_threshold, yield_threshold=0.0001, creep=0.9):
         self.L.orc_scene_tet_set_plastic(self.h, C.c_double(max_threshold), C.c_double(yield_threshold), C.c_double(creep))
 

@@ -102,3 +102,48 @@ def test_device_mesh_matrix_mass_bit_exact(dtype, lumping, meshname):
     # run-to-run reproducible
     r1 = dev(r0); mm.addMDx(r1, dev(dx), 0.5); r2 = dev(r0); mm.addMDx(r2, dev(dx), 0.5)
     assert torch.equal(r1, r2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("lumping", [False, True])
+@pytest.mark.parametrize("cg_path", ["fused_tail", "multi_kernel"])
+def test_solver_node_with_mesh_matrix_mass(dtype, lumping, cg_path, monkeypatch):
+    """The device-resident solver node with a MeshMatrixMass as its mass component (sofab200_node_set_mesh_mass): force vector, A*p and
+    right-hand side BIT-IDENTICAL to the oracle scene with the same mass, CG iteration counts equal, solution within the vDot bounds."""
+    import sofa_b200 as sb
+    import gpu_common
+    from gpu_common import dev, rel_err
+    if cg_path == "multi_kernel":
+        monkeypatch.setenv("SOFAB200_FUSED_TAIL", "0")
+    c, pos, hexas, tets, fixed = gpu_common.mesh("C1")
+    ctx = sb.Context(0)
+    mo = sb.MechanicalObject(ctx, "B200Vec3f" if dtype == np.float32 else "B200Vec3d", position=pos)
+    ff = sb.TetrahedronFEMForceField(mo, tets, youngModulus=c["young"], poissonRatio=c["poisson"], method="large")
+    mass = sb.MeshMatrixMass(mo, tets, massDensity=c["density"], lumping=lumping)
+    node = sb.SolverNode(mo, ff, mass, sb.FixedProjectiveConstraint(mo, fixed), dt=c["dt"], gravity=c["gravity"], rayleighStiffness=c["rK"], rayleighMass=c["rM"],
+                         iterations=c["iterations"], tolerance=c["tolerance"], threshold=c["threshold"])
+    s = O.OracleScene(dtype, pos)
+    s.set_params(gravity=c["gravity"], dt=c["dt"], rayleighStiffness=c["rK"], rayleighMass=c["rM"], iterations=c["iterations"], tolerance=c["tolerance"],
+                 threshold=c["threshold"])
+    s.set_tets(tets, "large", c["young"], c["poisson"]); s.set_mesh_mass(tets, c["density"], lumping); s.set_fixed(fixed)
+    rng = np.random.default_rng(5)
+    x = (pos + 0.2 * rng.standard_normal(pos.shape)).astype(dtype)
+    s.set_x(x)
+    f_d = mo.new_vector(); node.computeForce(f_d, dev(mo, x))
+    assert f_d.cpu().numpy().tobytes() == s.compute_force().tobytes()
+    p = rng.standard_normal(x.shape).astype(dtype)
+    for (m, b, k) in ((1.001, -0.01, -0.0011), (1.0, 0.0, -0.01), (0.0, 0.0, 0.11)):
+        q_d = mo.new_vector(); node.apply(q_d, dev(mo, p), m, b, k)
+        assert q_d.cpu().numpy().tobytes() == s.apply(p, m, b, k).tobytes(), (m, b, k)
+    s.set_x(pos.astype(dtype))
+    for step in range(4):
+        import torch
+        mo.x.copy_(torch.from_numpy(s.get("x").astype(dtype))); mo.v.copy_(torch.from_numpy(s.get("v").astype(dtype)))
+        node.step()
+        it = node.last_solve()["iterations"]
+        it_ref = s.step()
+        assert node.get("f").tobytes() == s.get("f").tobytes(), step
+        assert node.get("b").tobytes() == s.get("b").tobytes(), step
+        assert abs(it - it_ref) <= 1, (step, it, it_ref)
+        assert rel_err(node.get("dx"), s.get("sol")) <= (1e-8 if dtype == np.float64 else 2e-4), step
