@@ -61,6 +61,9 @@ template <class T> struct DevBuf {
     }
 };
 
+// (mesh_mass.cu) what a solver node needs to know about a MeshMatrixMass handle
+void meshmass_info(const sofab200_meshmass* mm, int* real, size_t* n_nodes, const sofab200_ctx** ctx);
+
 }  // namespace sb
 
 struct sofab200_ctx {

@@ -64,6 +64,7 @@ struct sofab200_meshmass {
 };
 
 namespace sb {
+void meshmass_info(const sofab200_meshmass* mm, int* real, size_t* n_nodes, const sofab200_ctx** ctx) { *real = mm->real; *n_nodes = mm->n_nodes; *ctx = mm->ctx; }
 template <class R> struct MeshMass : sofab200_meshmass {
     DevBuf<R> vm;
     DevBuf<uint32_t> slice_base;

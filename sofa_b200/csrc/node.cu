@@ -786,6 +786,9 @@ int sofab200_node_add_mbkdx(sofab200_node* node, void* out_dev, const void* init
 }
 int sofab200_node_set_mesh_mass(sofab200_node* node, sofab200_meshmass* mesh_mass) {
     SB_CHECK(node && mesh_mass, "null argument");
+    int mreal = 0; size_t mn = 0; const sofab200_ctx* mctx = nullptr;
+    sb::meshmass_info(mesh_mass, &mreal, &mn, &mctx);
+    SB_CHECK(mreal == node->real && mn == node->n && mctx == node->ctx, "the MeshMatrixMass must have the node's real type, size and context");
     if (node->real == SOFAB200_F32) { NF(node)->mesh_mass = mesh_mass; NF(node)->has_mass = true; }
     else { ND(node)->mesh_mass = mesh_mass; ND(node)->has_mass = true; }
     return SOFAB200_OK;

@@ -75,3 +75,35 @@ def test_c2_steps_match_oracle(c2):
         assert node.get("b").tobytes() == s.get("b").tobytes()
         assert rel_err(node.get("dx"), s.get("sol")) <= 5e-3   # serial float vDot over 526k entries in the reference
     assert np.abs(mo.x.cpu().numpy().astype(np.float64) - s.get("x")).max() <= 1e-5
+
+
+def test_c2_per_node_outputs_and_mesh_mass_properties():
+    """Full size (983 040 tetrahedra), size-independent properties of the round's late additions: under a rigid motion getRotations gives
+    that rotation at every node and computeVonMisesStress gives zero (both strain measures); MeshMatrixMass applied to a constant field
+    conserves the total mass (sum of M*1 = rho * volume) and equals the lumped matrix row by row."""
+    import sofa_b200 as sb
+    import gpu_common
+    c, pos, hexas, tets, fixed = gpu_common.mesh("C2")
+    ctx = sb.Context(0)
+    mo = sb.MechanicalObject(ctx, "B200Vec3d", position=pos)
+    a = 0.3
+    Q = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    x = pos @ Q.T + np.array([0.5, -1.0, 2.0])
+    for how in (1, 2):
+        ff = sb.TetrahedronFEMForceField(mo, tets, youngModulus=c["young"], poissonRatio=c["poisson"], method="polar", computeVonMisesStress=how)
+        f = mo.new_vector()
+        ff.addForce(f, dev(mo, x))
+        assert float(f.abs().max()) < 1e-8                                    # no elastic force under a rigid motion
+        R = ff.getRotations().cpu().numpy()
+        assert np.abs(R - Q).max() < 1e-10
+        pe, pn = ff.computeVonMisesStress(dev(mo, x))
+        assert float(pe.max()) < 1e-7 and float(pn.max()) < 1e-7
+        del ff
+    mm = sb.MeshMatrixMass(mo, tets, massDensity=2.5)
+    lumped = sb.MeshMatrixMass(mo, tets, massDensity=2.5, lumping=True)
+    ones = dev(mo, np.ones_like(pos))
+    r1 = mo.new_vector(); mm.addMDx(r1, ones, 1.0)
+    r2 = mo.new_vector(); lumped.addMDx(r2, ones, 1.0)
+    total = 2.5 * 4.0 * 4.0 * 20.0                                             # density * volume of the beam
+    assert abs(float(r1[:, 0].sum()) - total) < 1e-8 * total
+    assert float((r1 - r2).abs().max()) < 1e-12                                # the lumped matrix is the row sum of the sparse one (2.5 x vertex mass)

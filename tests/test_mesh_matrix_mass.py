@@ -136,6 +136,10 @@ def test_solver_node_with_mesh_matrix_mass(dtype, lumping, cg_path, monkeypatch)
     for (m, b, k) in ((1.001, -0.01, -0.0011), (1.0, 0.0, -0.01), (0.0, 0.0, 0.11)):
         q_d = mo.new_vector(); node.apply(q_d, dev(mo, p), m, b, k)
         assert q_d.cpu().numpy().tobytes() == s.apply(p, m, b, k).tobytes(), (m, b, k)
+    # a mass of another size or real type is refused
+    other = sb.MechanicalObject(ctx, "B200Vec3d" if dtype == np.float32 else "B200Vec3f", position=pos)
+    with pytest.raises(sb.Sofab200Error):
+        check_node = sb.SolverNode(mo, ff, sb.MeshMatrixMass(other, tets), None)
     s.set_x(pos.astype(dtype))
     for step in range(4):
         import torch
