@@ -162,6 +162,9 @@ typedef struct sofab200_tetfem_desc {
     double plastic_max_threshold;   /* Data `plasticMaxThreshold` (2-norm of the strain); <= 0 = no plasticity (the default)   */
     double plastic_yield_threshold; /* Data `plasticYieldThreshold` (reference default 0.0001)                                  */
     double plastic_creep;           /* Data `plasticCreep` (reference default 0.9)                                              */
+    int update_stiffness_matrix;    /* Data `updateStiffnessMatrix`: addForce recomputes the strain-displacement terms from the deformed element every
+                                     * step ([TFF].inl:1063-1067,1174-1177).  polar / svd only: with `large` the reference rewrites 9 single entries of J
+                                     * ([TFF].inl:908-922), which the 12-cofactor layout cannot hold -> SOFAB200_ERR_UNSUPPORTED; ignored by `small` */
     int compute_von_mises;          /* Data `computeVonMisesStress` (0 = off, 1 = corotational strain, 2 = Green-Lagrange strain):
                                      * non-zero makes init keep the shape-function matrices and Lame coefficients ([TFF].inl:278-282,1521-1541) */
 } sofab200_tetfem_desc;

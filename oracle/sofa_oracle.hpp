@@ -483,6 +483,7 @@ template <class R> struct TetFEM {
     std::vector<Coord> X0;                // _rotatedInitialElements[e][0..3]
     std::vector<Mat3<R>> initialTransformation;  // _initialTransformation (svd: A0^-1)
     std::vector<uint32_t> rotationIdx;    // _rotationIdx
+    bool updateStiffnessMatrix = false;   // d_updateStiffnessMatrix (restated for polar / svd only; `large` rewrites single J entries, :908-922)
     std::vector<R> plasticStrains;        // _plasticStrains: 6 Voigt components per element
     R plastic[3] = {R(0), R(0.0001f), R(0.9f)};  // d_plasticMaxThreshold, d_plasticYieldThreshold, d_plasticCreep (defaults :51-53)
     R* plasticPtr(size_t e) { return plastic[0] > 0 ? &plasticStrains[6 * e] : nullptr; }
@@ -707,6 +708,7 @@ template <class R> struct TetFEM {
         const Coord* x0 = &X0[4 * e];
         R D[12];
         for (int n = 0; n < 4; ++n) for (int k = 0; k < 3; ++k) D[3 * n + k] = x0[n][k] - deforme[n][k];
+        if (updateStiffnessMatrix) computeStrainDisplacement(&J[12 * e], deforme[0], deforme[1], deforme[2], deforme[3]);   // :1063-1067 / :1174-1177
         R F[12];
         computeForce(F, D, &K[3 * e], &J[12 * e], false, 0, plasticPtr(e), plastic);
         for (int i = 0; i < 12; i += 3) f[index[i / 3]] += rotations[e] * Coord(F[i], F[i + 1], F[i + 2]);

@@ -168,7 +168,7 @@ class TetrahedronFEMForceField:
     (Real)0.0001f and (Real)0.9f, TetrahedronFEMForceField.inl:51-53)."""
 
     def __init__(self, mstate, tetrahedra, youngModulus=5000.0, poissonRatio=0.45, method="large", localStiffnessFactor=None,
-                 rayleighStiffness=0.0, tileElems=0, sharedNodes=None, plasticMaxThreshold=0.0, plasticYieldThreshold=float(np.float32(0.0001)), plasticCreep=float(np.float32(0.9)), computeVonMisesStress=0):
+                 rayleighStiffness=0.0, tileElems=0, sharedNodes=None, plasticMaxThreshold=0.0, plasticYieldThreshold=float(np.float32(0.0001)), plasticCreep=float(np.float32(0.9)), computeVonMisesStress=0, updateStiffnessMatrix=False):
         if method not in TET_METHODS:
             raise ValueError(f"method must be one of {list(TET_METHODS)}")
         self.mstate, self.ctx = mstate, mstate.ctx
@@ -181,6 +181,7 @@ class TetrahedronFEMForceField:
             l, lp = _darr(localStiffnessFactor); d.n_local_stiffness, d.local_stiffness = len(l), lp
         d.tile_elems = int(tileElems)
         d.compute_von_mises = int(computeVonMisesStress)
+        d.update_stiffness_matrix = int(bool(updateStiffnessMatrix))
         d.plastic_max_threshold, d.plastic_yield_threshold, d.plastic_creep = float(plasticMaxThreshold), float(plasticYieldThreshold), float(plasticCreep)
         if sharedNodes is not None:      # nodes that must take the staging path (partition interface of a multi-GPU run)
             self._shared = np.zeros(mstate.size, np.uint8); self._shared[np.asarray(sharedNodes, np.int64)] = 1

@@ -22,6 +22,7 @@ template <class R> struct TetFF : sofab200_tetfem {
     DevBuf<uint32_t> tile_node_off, tile_nodes, tile_nint, tile_nb, sh_nodes, sh_base;
     DevBuf<uint16_t> tile_val, tile_jds, sh_val;
     DevBuf<Quad<R>> stage;
+    bool update_j = false;   // updateStiffnessMatrix (polar / svd)
     DevBuf<R> vm_shf, vm_lambda, vm_mu, vm_rest, vm_elem; int von_mises = 0;   // computeVonMisesStress (uploaded at the first call)
     DevBuf<Quad<R>> pl0, pl1; double plastic[3] = {0, 0, 0};   // _plasticStrains in tile order (plasticMaxThreshold > 0 only)
     DevBuf<R> rot_export;
@@ -39,6 +40,7 @@ template <class R> struct TetFF : sofab200_tetfem {
         d.rk0 = rk0.p; d.rk1 = rk1.p; d.rk2 = rk2.p; d.j0 = j0.p; d.j1 = j1.p; d.j2 = j2.p;
         d.x0a = x0a.p; d.x0b = x0b.p; d.x0c = x0c.p; d.sv0 = sv0.p; d.sv1 = sv1.p; d.sv2 = sv2.p; d.sv3 = sv3.p; d.sv4 = sv4.p;
         d.k_factor = R(0);
+        d.j0w = update_j ? j0.p : nullptr; d.j1w = update_j ? j1.p : nullptr; d.j2w = update_j ? j2.p : nullptr;
         d.pl0 = pl0.p; d.pl1 = pl1.p; d.plastic_max = R(plastic[0]); d.plastic_yield = R(plastic[1]); d.plastic_creep = R(plastic[2]);
         return d;
     }
@@ -207,6 +209,7 @@ template <class R> static int tet_create(sofab200_ctx* ctx, size_t n_nodes, cons
     if (const char* env = getenv("SOFAB200_TILE_THREADS")) { const int v = atoi(env); if (v >= 64 && v <= 1024 && v % 32 == 0) ff->threads = v; }
     if (const char* env = getenv("SOFAB200_PREFETCH")) ff->prefetch = atoi(env) != 0;
     ff->von_mises = desc->compute_von_mises;
+    ff->update_j = desc->update_stiffness_matrix != 0 && (desc->method == SOFAB200_TET_POLAR || desc->method == SOFAB200_TET_SVD);
     ff->plastic[0] = desc->plastic_max_threshold; ff->plastic[1] = desc->plastic_yield_threshold; ff->plastic[2] = desc->plastic_creep;
     SB_TRY(tet_upload(*ff));
     *out = ff.release();
@@ -325,6 +328,8 @@ int sofab200_tetfem_create(sofab200_ctx* ctx, sofab200_real real, size_t n_nodes
                            const uint32_t* tets_host, const sofab200_tetfem_desc* desc, sofab200_tetfem** out) {
     SB_CHECK(ctx && out && desc && rest_position_host && (tets_host || n_tets == 0), "null argument");
     SB_CHECK(desc->method >= 0 && desc->method <= 3, "method must be small, large, polar or svd");
+    if (desc->update_stiffness_matrix && desc->method == SOFAB200_TET_LARGE)
+        return fail(SOFAB200_ERR_UNSUPPORTED, "updateStiffnessMatrix with method large rewrites single entries of the strain-displacement matrix (TetrahedronFEMForceField.inl:908-922), which the 12-cofactor element record cannot hold; use polar or svd");
     SB_CHECK(desc->compute_von_mises >= 0 && desc->compute_von_mises <= 2, "computeVonMisesStress must be 0, 1 or 2");
     SB_CHECK(desc->n_young > 0 && desc->young && desc->n_poisson > 0 && desc->poisson, "youngModulus / poissonRatio are required");
     SB_CHECK(n_nodes < 0xFFFFFFFFull && n_tets < 0x3FFFFFFFull, "mesh too large for 32-bit indices");

@@ -23,25 +23,7 @@ template <class R> struct HostTet {
     size_t smem_bytes = 0;
 };
 
-// peudo_determinant_for_coef, TetrahedronFEMForceField.inl:204-208
-template <class R> static inline R pdet(R m00, R m01, R m02, R m10, R m11, R m12) {
-    return m01 * m12 - m11 * m02 - m00 * m12 + m10 * m02 + m00 * m11 - m10 * m01;
-}
-// computeStrainDisplacement, :134-202 -- the 12 distinct cofactors
-template <class R> static void strain_displacement(R* j, const V3<R>& a, const V3<R>& b, const V3<R>& c, const V3<R>& d) {
-    j[0] = -pdet(b.y, c.y, d.y, b.z, c.z, d.z);
-    j[1] = pdet(b.x, c.x, d.x, b.z, c.z, d.z);
-    j[2] = -pdet(b.x, c.x, d.x, b.y, c.y, d.y);
-    j[3] = pdet(c.y, d.y, a.y, c.z, d.z, a.z);
-    j[4] = -pdet(c.x, d.x, a.x, c.z, d.z, a.z);
-    j[5] = pdet(c.x, d.x, a.x, c.y, d.y, a.y);
-    j[6] = -pdet(d.y, a.y, b.y, d.z, a.z, b.z);
-    j[7] = pdet(d.x, a.x, b.x, d.z, a.z, b.z);
-    j[8] = -pdet(d.x, a.x, b.x, d.y, a.y, b.y);
-    j[9] = pdet(a.y, b.y, c.y, a.z, b.z, c.z);
-    j[10] = -pdet(a.x, b.x, c.x, a.z, b.z, c.z);
-    j[11] = pdet(a.x, b.x, c.x, a.y, b.y, c.y);
-}
+template <class R> static void strain_displacement(R* j, const V3<R>& a, const V3<R>& b, const V3<R>& c, const V3<R>& d) { tet_strain_displacement(j, a, b, c, d); }   // tet_kernels.cuh
 
 // invertMatrix, general case (Sofa/framework/Type/src/sofa/type/Mat.h:1103-1166): Gauss-Jordan with full pivoting, S = 4
 template <class R> static bool invert4(R dest[4][4], const R from[4][4]) {

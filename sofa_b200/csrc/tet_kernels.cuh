@@ -14,12 +14,33 @@ namespace sb {
 
 enum TetMode { TM_DF_COROT = 0, TM_DF_SMALL = 1, TM_F_SMALL = 2, TM_F_LARGE = 3, TM_F_POLAR = 4, TM_F_SVD = 5 };
 
+// peudo_determinant_for_coef, TetrahedronFEMForceField.inl:204-208
+template <class R> HD R tet_pdet(R m00, R m01, R m02, R m10, R m11, R m12) {
+    return m01 * m12 - m11 * m02 - m00 * m12 + m10 * m02 + m00 * m11 - m10 * m01;
+}
+// computeStrainDisplacement, :134-202 -- the 12 distinct cofactors
+template <class R> HD void tet_strain_displacement(R* j, const V3<R>& a, const V3<R>& b, const V3<R>& c, const V3<R>& d) {
+    j[0] = -tet_pdet(b.y, c.y, d.y, b.z, c.z, d.z);
+    j[1] = tet_pdet(b.x, c.x, d.x, b.z, c.z, d.z);
+    j[2] = -tet_pdet(b.x, c.x, d.x, b.y, c.y, d.y);
+    j[3] = tet_pdet(c.y, d.y, a.y, c.z, d.z, a.z);
+    j[4] = -tet_pdet(c.x, d.x, a.x, c.z, d.z, a.z);
+    j[5] = tet_pdet(c.x, d.x, a.x, c.y, d.y, a.y);
+    j[6] = -tet_pdet(d.y, a.y, b.y, d.z, a.z, b.z);
+    j[7] = tet_pdet(d.x, a.x, b.x, d.z, a.z, b.z);
+    j[8] = -tet_pdet(d.x, a.x, b.x, d.y, a.y, b.y);
+    j[9] = tet_pdet(a.y, b.y, c.y, a.z, b.z, c.z);
+    j[10] = -tet_pdet(a.x, b.x, c.x, a.z, b.z, c.z);
+    j[11] = tet_pdet(a.x, b.x, c.x, a.y, b.y, c.y);
+}
+
 template <class R> struct TetDev {
     TileDev<R> t;
     const ushort4* lnode;      // [n_tiles*tile_e] local node index of the 4 corners (0xFFFF = padding element); read as one 64-bit word
     const uint4* slot;         // destination slot of each corner's contribution
     Quad<R>* rk0; Quad<R>* rk1; Quad<R>* rk2;            // rotations[e] (9, row-major) + {K00, K01, K33}
     const Quad<R>* j0; const Quad<R>* j1; const Quad<R>* j2;     // 12 strain-displacement cofactors
+    Quad<R>* j0w; Quad<R>* j1w; Quad<R>* j2w;                    // the same planes, writable: non-null when updateStiffnessMatrix is set (polar / svd addForce rewrites them)
     const Quad<R>* x0a; const Quad<R>* x0b; const Quad<R>* x0c;  // _rotatedInitialElements (small: rest positions)
     const Quad<R>* sv0; const Quad<R>* sv1; const Quad<R>* sv2; const Quad<R>* sv3; const Quad<R>* sv4;  // svd: A0^-1 (9) + R0^T (9)
     R k_factor;                // addDForce: (Real)kFactorIncludingRayleighDamping
@@ -95,7 +116,7 @@ template <class R> HD void tet_compute_force_addforce(const TetDev<R>& d, size_t
 template <class R, int MODE> HD void tet_element(const TetDev<R>& d, size_t es, const TetRec<R>& rec, const V3<R> P[4], V3<R> C[4]) {
     const Quad<R> q0 = rec.q0, q1 = rec.q1, q2 = rec.q2;
     const Quad<R> ja = rec.ja, jb = rec.jb, jc = rec.jc;
-    const R j[12] = {ja.a, ja.b, ja.c, ja.d, jb.a, jb.b, jb.c, jb.d, jc.a, jc.b, jc.c, jc.d};
+    R j[12] = {ja.a, ja.b, ja.c, ja.d, jb.a, jb.b, jb.c, jb.d, jc.a, jc.b, jc.c, jc.d};
     const R k0 = q2.b, k1 = q2.c, k2 = q2.d;
     R F[12];
     if (MODE == TM_DF_COROT) {
@@ -189,6 +210,10 @@ template <class R, int MODE> HD void tet_element(const TetDev<R>& d, size_t es, 
                 // :1047-1058 / :1160-1171
 #pragma unroll
                 for (int n = 0; n < 4; ++n) { D[3 * n] = X0[3 * n] - def[n].x; D[3 * n + 1] = X0[3 * n + 1] - def[n].y; D[3 * n + 2] = X0[3 * n + 2] - def[n].z; }
+                if (d.j0w) {   // d_updateStiffnessMatrix: shape functions from the deformed element, :1063-1067 / :1174-1177
+                    tet_strain_displacement(j, def[0], def[1], def[2], def[3]);
+                    d.j0w[es] = Quad<R>{j[0], j[1], j[2], j[3]}; d.j1w[es] = Quad<R>{j[4], j[5], j[6], j[7]}; d.j2w[es] = Quad<R>{j[8], j[9], j[10], j[11]};
+                }
             }
             tet_compute_force_addforce<R>(d, es, F, D, j, k0, k1, k2);
             // f[index[i/3]] += rotations[e] * Deriv(F[i],F[i+1],F[i+2]), :928-929

@@ -151,6 +151,9 @@ class OracleScene:
     def set_plastic(self, max_threshold, yield_threshold=0.0001, creep=0.9):
         self.L.orc_scene_tet_set_plastic(self.h, C.c_double(max_threshold), C.c_double(yield_threshold), C.c_double(creep))
 
+    def set_update_stiffness_matrix(self, on=True):
+        self.L.orc_scene_tet_set_update_stiffness(self.h, int(bool(on)))
+
     def tet_reset(self):
         self.L.orc_scene_tet_reset(self.h)
 

@@ -107,6 +107,39 @@ def test_plasticity_branch_bit_exact(dtype, method, plastic):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("method", ["polar", "svd", "small", "large"])
+def test_update_stiffness_matrix(dtype, method):
+    """Data updateStiffnessMatrix (TetrahedronFEMForceField.inl:1063-1067,1174-1177): polar / svd recompute the strain-displacement terms
+    from the deformed element in every addForce, and addDForce then uses them; `small` ignores the flag; `large` is refused (the reference
+    rewrites single entries of J there, :908-922)."""
+    import sofa_b200 as sb
+    c, pos, hexas, tets, fixed = gpu_common.mesh("C1")
+    ctx = sb.Context(0)
+    mo = sb.MechanicalObject(ctx, "B200Vec3f" if dtype == np.float32 else "B200Vec3d", position=pos)
+    if method == "large":
+        with pytest.raises(sb.Sofab200Error):
+            sb.TetrahedronFEMForceField(mo, tets, youngModulus=c["young"], poissonRatio=c["poisson"], method=method, updateStiffnessMatrix=True)
+        return
+    ff = sb.TetrahedronFEMForceField(mo, tets, youngModulus=c["young"], poissonRatio=c["poisson"], method=method, updateStiffnessMatrix=True)
+    s = oracle_scene("C1", dtype, method)
+    s.set_update_stiffness_matrix(True)
+    rng = np.random.default_rng(31)
+    f0 = rng.standard_normal(pos.shape).astype(dtype)
+    J0 = ff.get("strainDisplacements").copy()
+    for it in range(3):
+        x = (pos + 0.2 * rng.standard_normal(pos.shape)).astype(dtype)
+        f_d = dev(mo, f0)
+        ff.addForce(f_d, dev(mo, x))
+        assert f_d.cpu().numpy().tobytes() == s.fem_add_force(f0, x).tobytes(), it
+        dx = rng.standard_normal(pos.shape).astype(dtype)
+        df_d = dev(mo, f0)
+        ff.addDForce(df_d, dev(mo, dx), 0.11)
+        assert df_d.cpu().numpy().tobytes() == s.fem_add_dforce(f0, dx, 0.11).tobytes(), it
+    if method != "small":
+        assert np.abs(s.get("tet.J") - J0).max() > 0      # the oracle's J did change
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("method", ["small", "large", "polar", "svd"])
 @pytest.mark.parametrize("how", [1, 2])
 def test_von_mises_stress_bit_exact(dtype, method, how):
