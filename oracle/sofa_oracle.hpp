@@ -757,7 +757,7 @@ template <class R> struct TetFEM {
         const int S = 4;
         int r[S] = {0, 0, 0, 0}, c[S] = {0, 0, 0, 0}, row[S] = {0, 0, 0, 0}, col[S] = {0, 0, 0, 0};
         R m1[S][S], m2[S][S];
-        for (int i = 0; i < S; ++i) for (int j = 0; j < S; ++j) { m1[i][j] = from[i][j]; m2[i][j] = i == j ? R(1) : R(0); }
+        for (int i = 0; i < S; ++i) for (int j = 0; j < S; ++j) { m1[i][j] = from[i][j]; m2[i][j] = i == j ? R(1) : R(0); dest[i][j] = R(0); }
         for (int k = 0; k < S; k++) {
             R pivot = 0;
             for (int i = 0; i < S; i++) {
