@@ -165,6 +165,11 @@ typedef struct sofab200_tetfem_desc {
     int update_stiffness_matrix;    /* Data `updateStiffnessMatrix`: addForce recomputes the strain-displacement terms from the deformed element every
                                      * step ([TFF].inl:1063-1067,1174-1177).  polar / svd only: with `large` the reference rewrites 9 single entries of J
                                      * ([TFF].inl:908-922), which the 12-cofactor layout cannot hold -> SOFAB200_ERR_UNSUPPORTED; ignored by `small` */
+    int tetrahedral_corotational;   /* 1: the component is a TetrahedralCorotationalFEMForceField (…/fem/elastic/TetrahedralCorotationalFEMForceField.inl,
+                                     * what Demos/liver.scn uses): its init, accumulateForce{Small,Large,Polar}, applyStiffness* and computeForce
+                                     * (:356-398,400-602,604-743,840-1044,1046-1175) are statement for statement those of TetrahedronFEMForceField, so the
+                                     * same kernels serve it.  Differences: no svd, no plasticity; updateStiffnessMatrix works with `large` too (there all
+                                     * three copies of a cofactor are rewritten together, :920-937); its own computeVonMisesStress is not provided. */
     int compute_von_mises;          /* Data `computeVonMisesStress` (0 = off, 1 = corotational strain, 2 = Green-Lagrange strain):
                                      * non-zero makes init keep the shape-function matrices and Lame coefficients ([TFF].inl:278-282,1521-1541) */
 } sofab200_tetfem_desc;

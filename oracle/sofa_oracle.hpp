@@ -483,6 +483,8 @@ template <class R> struct TetFEM {
     std::vector<Coord> X0;                // _rotatedInitialElements[e][0..3]
     std::vector<Mat3<R>> initialTransformation;  // _initialTransformation (svd: A0^-1)
     std::vector<uint32_t> rotationIdx;    // _rotationIdx
+    bool tetrahedralCorotational = false; // the sibling class TetrahedralCorotationalFEMForceField (same statements, TetrahedralCorotationalFEMForceField.inl:356-1175): only its
+                                          // accumulateForceLarge differs, by rewriting all three copies of a cofactor under updateStiffnessMatrix (:920-937)
     bool updateStiffnessMatrix = false;   // d_updateStiffnessMatrix (restated for polar / svd only; `large` rewrites single J entries, :908-922)
     std::vector<R> plasticStrains;        // _plasticStrains: 6 Voigt components per element
     R plastic[3] = {R(0), R(0.0001f), R(0.9f)};  // d_plasticMaxThreshold, d_plasticYieldThreshold, d_plasticCreep (defaults :51-53)
@@ -684,6 +686,18 @@ template <class R> struct TetFEM {
         D[3] = x0[1][0] - deforme[1][0]; D[4] = 0; D[5] = 0;
         D[6] = x0[2][0] - deforme[2][0]; D[7] = x0[2][1] - deforme[2][1]; D[8] = 0;
         D[9] = x0[3][0] - deforme[3][0]; D[10] = x0[3][1] - deforme[3][1]; D[11] = x0[3][2] - deforme[3][2];
+        if (updateStiffnessMatrix && tetrahedralCorotational) {   // TetrahedralCorotationalFEMForceField.inl:920-937 (jx_n = j[3n], jy_n = j[3n+1], jz_n = j[3n+2])
+            R* j = &J[12 * e];
+            j[0] = ( - deforme[2][1]*deforme[3][2] );
+            j[1] = ( deforme[2][0]*deforme[3][2] - deforme[1][0]*deforme[3][2] );
+            j[2] = ( deforme[2][1]*deforme[3][0] - deforme[2][0]*deforme[3][1] + deforme[1][0]*deforme[3][1] - deforme[1][0]*deforme[2][1] );
+            j[3] = ( deforme[2][1]*deforme[3][2] );
+            j[4] = ( - deforme[2][0]*deforme[3][2] );
+            j[5] = ( - deforme[2][1]*deforme[3][0] + deforme[2][0]*deforme[3][1] );
+            j[7] = ( deforme[1][0]*deforme[3][2] );
+            j[8] = ( - deforme[1][0]*deforme[3][1] );
+            j[11] = ( deforme[1][0]*deforme[2][1] );
+        }
         R F[12];
         computeForce(F, D, &K[3 * e], &J[12 * e], false, 0, plasticPtr(e), plastic);
         for (int i = 0; i < 12; i += 3) f[index[i / 3]] += rotations[e] * Coord(F[i], F[i + 1], F[i + 2]);

@@ -320,6 +320,7 @@ void orc_scene_tet_set_plastic(void* h, double mx, double yield, double creep) {
     DISPATCH(h, { sc.tet.plastic[0] = R(mx); sc.tet.plastic[1] = R(yield); sc.tet.plastic[2] = R(creep); sc.tet.reset(); });
 }
 void orc_scene_tet_set_update_stiffness(void* h, int on) { DISPATCH(h, { sc.tet.updateStiffnessMatrix = on != 0; }); }
+void orc_scene_tet_set_sibling(void* h, int on) { DISPATCH(h, { sc.tet.tetrahedralCorotational = on != 0; }); }
 void orc_scene_tet_reset(void* h) { DISPATCH(h, { sc.tet.reset(); }); }
 // computeVonMisesStress at positions x (how = 1 or 2): per_element T Reals, per_node N Reals
 void orc_scene_tet_von_mises(void* h, const void* x, int how, void* per_element, void* per_node) {

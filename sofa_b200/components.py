@@ -182,6 +182,7 @@ class TetrahedronFEMForceField:
         d.tile_elems = int(tileElems)
         d.compute_von_mises = int(computeVonMisesStress)
         d.update_stiffness_matrix = int(bool(updateStiffnessMatrix))
+        d.tetrahedral_corotational = int(getattr(self, "_tetrahedral_corotational", False))
         d.plastic_max_threshold, d.plastic_yield_threshold, d.plastic_creep = float(plasticMaxThreshold), float(plasticYieldThreshold), float(plasticCreep)
         if sharedNodes is not None:      # nodes that must take the staging path (partition interface of a multi-GPU run)
             self._shared = np.zeros(mstate.size, np.uint8); self._shared[np.asarray(sharedNodes, np.int64)] = 1
@@ -236,6 +237,20 @@ class TetrahedronFEMForceField:
             self.ctx.L.sofab200_tetfem_destroy(self.h)
         except Exception:
             pass
+
+
+class TetrahedralCorotationalFEMForceField(TetrahedronFEMForceField):
+    """TetrahedralCorotationalFEMForceField<B200Vec3Types> (what Demos/liver.scn uses): methods small / large / polar, Data youngModulus,
+    poissonRatio, localStiffnessFactor, updateStiffnessMatrix.  Its arithmetic is statement for statement TetrahedronFEMForceField's
+    (TetrahedralCorotationalFEMForceField.inl:356-1175), so the same device object serves it (descriptor flag tetrahedral_corotational)."""
+    _tetrahedral_corotational = True
+
+    def __init__(self, mstate, tetrahedra, youngModulus=5000.0, poissonRatio=0.45, method="large", localStiffnessFactor=None, rayleighStiffness=0.0,
+                 updateStiffnessMatrix=False, tileElems=0):
+        if method == "svd":
+            raise ValueError("TetrahedralCorotationalFEMForceField has no svd method")
+        super().__init__(mstate, tetrahedra, youngModulus, poissonRatio, method, localStiffnessFactor, rayleighStiffness, tileElems,
+                         updateStiffnessMatrix=updateStiffnessMatrix)
 
 
 class HexahedronFEMForceField:

@@ -209,7 +209,7 @@ template <class R> static int tet_create(sofab200_ctx* ctx, size_t n_nodes, cons
     if (const char* env = getenv("SOFAB200_TILE_THREADS")) { const int v = atoi(env); if (v >= 64 && v <= 1024 && v % 32 == 0) ff->threads = v; }
     if (const char* env = getenv("SOFAB200_PREFETCH")) ff->prefetch = atoi(env) != 0;
     ff->von_mises = desc->compute_von_mises;
-    ff->update_j = desc->update_stiffness_matrix != 0 && (desc->method == SOFAB200_TET_POLAR || desc->method == SOFAB200_TET_SVD);
+    ff->update_j = desc->update_stiffness_matrix != 0 && (desc->method == SOFAB200_TET_POLAR || desc->method == SOFAB200_TET_SVD || (desc->method == SOFAB200_TET_LARGE && desc->tetrahedral_corotational));
     ff->plastic[0] = desc->plastic_max_threshold; ff->plastic[1] = desc->plastic_yield_threshold; ff->plastic[2] = desc->plastic_creep;
     SB_TRY(tet_upload(*ff));
     *out = ff.release();
@@ -328,7 +328,12 @@ int sofab200_tetfem_create(sofab200_ctx* ctx, sofab200_real real, size_t n_nodes
                            const uint32_t* tets_host, const sofab200_tetfem_desc* desc, sofab200_tetfem** out) {
     SB_CHECK(ctx && out && desc && rest_position_host && (tets_host || n_tets == 0), "null argument");
     SB_CHECK(desc->method >= 0 && desc->method <= 3, "method must be small, large, polar or svd");
-    if (desc->update_stiffness_matrix && desc->method == SOFAB200_TET_LARGE)
+    if (desc->tetrahedral_corotational) {
+        SB_CHECK(desc->method != SOFAB200_TET_SVD, "TetrahedralCorotationalFEMForceField has no svd method");
+        if (desc->plastic_max_threshold > 0 || desc->compute_von_mises)
+            return fail(SOFAB200_ERR_UNSUPPORTED, "plasticity and computeVonMisesStress belong to TetrahedronFEMForceField; TetrahedralCorotationalFEMForceField's own von Mises routine is not provided");
+    }
+    if (desc->update_stiffness_matrix && desc->method == SOFAB200_TET_LARGE && !desc->tetrahedral_corotational)
         return fail(SOFAB200_ERR_UNSUPPORTED, "updateStiffnessMatrix with method large rewrites single entries of the strain-displacement matrix (TetrahedronFEMForceField.inl:908-922), which the 12-cofactor element record cannot hold; use polar or svd");
     SB_CHECK(desc->compute_von_mises >= 0 && desc->compute_von_mises <= 2, "computeVonMisesStress must be 0, 1 or 2");
     SB_CHECK(desc->n_young > 0 && desc->young && desc->n_poisson > 0 && desc->poisson, "youngModulus / poissonRatio are required");

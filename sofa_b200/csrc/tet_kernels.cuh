@@ -206,6 +206,18 @@ template <class R, int MODE> HD void tet_element(const TetDev<R>& d, size_t es, 
                 D[3] = X0[3] - def[1].x; D[4] = 0; D[5] = 0;
                 D[6] = X0[6] - def[2].x; D[7] = X0[7] - def[2].y; D[8] = 0;
                 D[9] = X0[9] - def[3].x; D[10] = X0[10] - def[3].y; D[11] = X0[11] - def[3].z;
+                if (d.j0w) {   // TetrahedralCorotationalFEMForceField::accumulateForceLarge with d_updateStiffnessMatrix, TetrahedralCorotationalFEMForceField.inl:920-937
+                    j[0] = -def[2].y * def[3].z;
+                    j[1] = def[2].x * def[3].z - def[1].x * def[3].z;
+                    j[2] = def[2].y * def[3].x - def[2].x * def[3].y + def[1].x * def[3].y - def[1].x * def[2].y;
+                    j[3] = def[2].y * def[3].z;
+                    j[4] = -def[2].x * def[3].z;
+                    j[5] = -def[2].y * def[3].x + def[2].x * def[3].y;
+                    j[7] = def[1].x * def[3].z;
+                    j[8] = -def[1].x * def[3].y;
+                    j[11] = def[1].x * def[2].y;
+                    d.j0w[es] = Quad<R>{j[0], j[1], j[2], j[3]}; d.j1w[es] = Quad<R>{j[4], j[5], j[6], j[7]}; d.j2w[es] = Quad<R>{j[8], j[9], j[10], j[11]};
+                }
             } else {
                 // :1047-1058 / :1160-1171
 #pragma unroll

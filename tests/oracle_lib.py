@@ -154,6 +154,10 @@ class OracleScene:
     def set_update_stiffness_matrix(self, on=True):
         self.L.orc_scene_tet_set_update_stiffness(self.h, int(bool(on)))
 
+    def set_tetrahedral_corotational(self, on=True):
+        """The tetra force field is the sibling class TetrahedralCorotationalFEMForceField."""
+        self.L.orc_scene_tet_set_sibling(self.h, int(bool(on)))
+
     def tet_reset(self):
         self.L.orc_scene_tet_reset(self.h)
 

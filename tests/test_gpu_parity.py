@@ -107,6 +107,45 @@ def test_plasticity_branch_bit_exact(dtype, method, plastic):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("method", ["small", "large", "polar"])
+@pytest.mark.parametrize("update", [False, True], ids=["fixedJ", "updateStiffnessMatrix"])
+@pytest.mark.parametrize("meshname", ["C1", "liver"])
+def test_tetrahedral_corotational_fem_force_field(dtype, method, update, meshname):
+    """TetrahedralCorotationalFEMForceField (what Demos/liver.scn uses; the reference's own tests hold it to the SAME golden vectors as
+    TetrahedronFEMForceField, TetrahedralCorotationalFEMForceField_test.cpp:30-82): addForce / addDForce bit-identical to the oracle, also
+    with updateStiffnessMatrix (for `large` the class rewrites all three copies of a cofactor, .inl:920-937); without it the results equal
+    TetrahedronFEMForceField's bit for bit."""
+    import os
+    import sofa_b200 as sb
+    if meshname == "C1":
+        c, pos, hexas, tets, fixed = gpu_common.mesh("C1")
+        young, poisson, amp = c["young"], c["poisson"], 0.2
+    else:
+        z = np.load(os.path.join(os.path.dirname(__file__), "golden", "liver_mesh.npz"))
+        pos, tets, young, poisson, amp = z["positions"], z["tetrahedra"], 3000.0, 0.3, 0.05      # Demos/liver.scn:35
+    ctx = sb.Context(0)
+    mo = sb.MechanicalObject(ctx, "B200Vec3f" if dtype == np.float32 else "B200Vec3d", position=pos)
+    ff = sb.TetrahedralCorotationalFEMForceField(mo, tets, youngModulus=young, poissonRatio=poisson, method=method, updateStiffnessMatrix=update)
+    twin = sb.TetrahedronFEMForceField(mo, tets, youngModulus=young, poissonRatio=poisson, method=method)
+    s = O.OracleScene(dtype, pos); s.set_tets(tets, method, young, poisson)
+    s.set_tetrahedral_corotational(True); s.set_update_stiffness_matrix(update)
+    rng = np.random.default_rng(41)
+    f0 = rng.standard_normal(pos.shape).astype(dtype)
+    for it in range(3):
+        x = (pos + amp * rng.standard_normal(pos.shape)).astype(dtype)
+        f_d = dev(mo, f0); ff.addForce(f_d, dev(mo, x))
+        assert f_d.cpu().numpy().tobytes() == s.fem_add_force(f0, x).tobytes(), it
+        dx = rng.standard_normal(pos.shape).astype(dtype)
+        df_d = dev(mo, f0); ff.addDForce(df_d, dev(mo, dx), -0.0011)
+        assert df_d.cpu().numpy().tobytes() == s.fem_add_dforce(f0, dx, -0.0011).tobytes(), it
+        if not update:
+            t_d = dev(mo, f0); twin.addForce(t_d, dev(mo, x))
+            assert t_d.cpu().numpy().tobytes() == f_d.cpu().numpy().tobytes()
+    with pytest.raises((ValueError, sb.Sofab200Error)):
+        sb.TetrahedralCorotationalFEMForceField(mo, tets, method="svd")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("method", ["polar", "svd", "small", "large"])
 def test_update_stiffness_matrix(dtype, method):
     """Data updateStiffnessMatrix (TetrahedronFEMForceField.inl:1063-1067,1174-1177): polar / svd recompute the strain-displacement terms

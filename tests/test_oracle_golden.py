@@ -272,3 +272,25 @@ def test_hexa_node_rotation_restatement(dtype):
     for n in (0, 13, pos.shape[0] - 1):
         u, _, vt = np.linalg.svd(np.eye(3) / cnt[n] + Q.T)   # the class keeps R (world -> element frame), the transpose of the tetra class's
         assert np.abs(got[n] - u @ vt).max() < 20 * tol
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_tetrahedral_corotational_shares_the_golden_vectors(dtype):
+    """The reference holds TetrahedralCorotationalFEMForceField to the same expected values as TetrahedronFEMForceField
+    (tests/TetrahedralCorotationalFEMForceField_test.cpp:30-82 instantiates BaseTetrahedronFEMForceField_test for it): the single-tetra
+    init KAT with the sibling flag set, and updateStiffnessMatrix with method large changes the cofactors and the forces."""
+    x = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype)
+    s = O.OracleScene(dtype, x)
+    s.set_tets(np.array([[2, 3, 1, 0]], np.uint32), "large", 1000.0, 0.3)
+    s.set_tetrahedral_corotational(True)
+    exp_initPos = np.array([[0, 0, 0], [1.41421, 0, 0], [0.707107, 1.22474, 0], [0.707107, 0.408248, -0.57735]])
+    assert np.abs(s.get("tet.X0")[0] - exp_initPos).max() < TOL
+    J, K = s.tet_matrices(0)
+    assert abs(K[0, 0] - 224.359) < 1e-3 and abs(K[0, 1] - 96.1538) < 1e-3 and abs(K[3, 3] - 64.1026) < 1e-3
+    y = (x * np.array([1.2, 0.9, 1.1])).astype(dtype)
+    f_fixed = s.fem_add_force(np.zeros_like(x), y)
+    J0 = s.get("tet.J").copy()
+    s.set_update_stiffness_matrix(True)
+    f_upd = s.fem_add_force(np.zeros_like(x), y)
+    assert np.abs(s.get("tet.J") - J0).max() > 1e-3 and np.abs(f_upd - f_fixed).max() > 1e-3
+    assert np.abs(f_upd.sum(axis=0)).max() < (1e-2 if dtype == np.float32 else 1e-9)     # internal forces still balance
