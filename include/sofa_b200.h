@@ -169,7 +169,9 @@ typedef struct sofab200_tetfem_desc {
                                      * what Demos/liver.scn uses): its init, accumulateForce{Small,Large,Polar}, applyStiffness* and computeForce
                                      * (:356-398,400-602,604-743,840-1044,1046-1175) are statement for statement those of TetrahedronFEMForceField, so the
                                      * same kernels serve it.  Differences: no svd, no plasticity; updateStiffnessMatrix works with `large` too (there all
-                                     * three copies of a cofactor are rewritten together, :920-937); its own computeVonMisesStress is not provided. */
+                                     * three copies of a cofactor are rewritten together, :920-937); sofab200_tetfem_get_rotations follows the class's own getRotation
+                                     * (:779-820: mean of rotation * initialTransformation, Gram-Schmidt instead of a polar decomposition; large / polar);
+                                     * its own computeVonMisesStress is not provided. */
     int compute_von_mises;          /* Data `computeVonMisesStress` (0 = off, 1 = corotational strain, 2 = Green-Lagrange strain):
                                      * non-zero makes init keep the shape-function matrices and Lame coefficients ([TFF].inl:278-282,1521-1541) */
 } sofab200_tetfem_desc;

@@ -914,12 +914,34 @@ template <class R> struct TetFEM {
         Decompose<R>::polarDecomposition(Rn, Rmoy);
         Rn = Rmoy;
     }
+    // TetrahedralCorotationalFEMForceField::getRotation, TetrahedralCorotationalFEMForceField.inl:779-820 (large / polar)
+    void getRotationSibling(Mat3<R>& Rn, const std::vector<uint32_t>& liste) const {
+        const int numNeiTetra = int(liste.size());
+        Mat3<R> r;
+        for (int i = 0; i < numNeiTetra; i++) {
+            const uint32_t e = liste[i];
+            Mat3<R> r01;
+            if (method == POLAR) {   // initPolar :1046-1070: initialTransformation = A
+                r01.setRow(0, initialPoints[tets[4 * e + 1]] - initialPoints[tets[4 * e]]);
+                r01.setRow(1, initialPoints[tets[4 * e + 2]] - initialPoints[tets[4 * e]]);
+                r01.setRow(2, initialPoints[tets[4 * e + 3]] - initialPoints[tets[4 * e]]);
+            } else r01 = initialRotations[e].transposed();   // initLarge :840-881: initialTransformation = R_0_1
+            const Mat3<R> r21 = rotations[e] * r01;
+            for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) r.m[a][b] += r21.m[a][b];
+        }
+        Rn = r * R(1.0f / numNeiTetra);
+        Vec3<R> ex = Rn.row(0), ey = Rn.row(1);
+        ex.normalize(); ey.normalize();
+        Vec3<R> ez = cross(ex, ey); ez.normalize();
+        ey = cross(ez, ex); ey.normalize();
+        Rn.setRow(0, ex); Rn.setRow(1, ey); Rn.setRow(2, ez);
+    }
     // getRotations(VecReal&) :2033-2042: 9 Reals per node, row-major
     void getRotations(std::vector<Mat3<R>>& vecR, size_t nbdof) const {
         std::vector<std::vector<uint32_t>> around(nbdof);
         for (size_t t = 0; t < nbTets(); ++t) for (int k = 0; k < 4; ++k) around[tets[4 * t + k]].push_back(uint32_t(t));   // TetrahedronSetTopologyContainer::createTetrahedraAroundVertexArray
         vecR.assign(nbdof, Mat3<R>());
-        for (uint32_t i = 0; i < nbdof; ++i) getRotation(vecR[i], i, around);
+        for (uint32_t i = 0; i < nbdof; ++i) { if (tetrahedralCorotational) getRotationSibling(vecR[i], around[i]); else getRotation(vecR[i], i, around); }
     }
     // addDForce :1606-1636.  kFactor already includes the Rayleigh term
     // (MechanicalParams.h:62) and is narrowed to Real there (:1615).

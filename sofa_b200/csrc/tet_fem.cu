@@ -23,6 +23,7 @@ template <class R> struct TetFF : sofab200_tetfem {
     DevBuf<uint16_t> tile_val, tile_jds, sh_val;
     DevBuf<Quad<R>> stage;
     bool update_j = false;   // updateStiffnessMatrix (polar / svd)
+    bool sibling = false; DevBuf<R> a0_el;   // TetrahedralCorotationalFEMForceField (its getRotation differs)
     DevBuf<R> vm_shf, vm_lambda, vm_mu, vm_rest, vm_elem; int von_mises = 0;   // computeVonMisesStress (uploaded at the first call)
     DevBuf<Quad<R>> pl0, pl1; double plastic[3] = {0, 0, 0};   // _plasticStrains in tile order (plasticMaxThreshold > 0 only)
     DevBuf<R> rot_export;
@@ -209,6 +210,7 @@ template <class R> static int tet_create(sofab200_ctx* ctx, size_t n_nodes, cons
     if (const char* env = getenv("SOFAB200_TILE_THREADS")) { const int v = atoi(env); if (v >= 64 && v <= 1024 && v % 32 == 0) ff->threads = v; }
     if (const char* env = getenv("SOFAB200_PREFETCH")) ff->prefetch = atoi(env) != 0;
     ff->von_mises = desc->compute_von_mises;
+    ff->sibling = desc->tetrahedral_corotational != 0;
     ff->update_j = desc->update_stiffness_matrix != 0 && (desc->method == SOFAB200_TET_POLAR || desc->method == SOFAB200_TET_SVD || (desc->method == SOFAB200_TET_LARGE && desc->tetrahedral_corotational));
     ff->plastic[0] = desc->plastic_max_threshold; ff->plastic[1] = desc->plastic_yield_threshold; ff->plastic[2] = desc->plastic_creep;
     SB_TRY(tet_upload(*ff));
@@ -257,7 +259,7 @@ template <class R> static int tet_build_incidence(TetFF<R>& ff);
 // getRotations(VecReal&): 9 Reals per node into a device array
 template <class R> static int tet_node_rotations(TetFF<R>& ff, R* out_dev) {
     cudaStream_t s = ff.ctx->stream;
-    if (ff.method == SOFAB200_TET_SMALL) {   // :783-791: identity (and a warning) when no rotation is computed
+    if (ff.method == SOFAB200_TET_SMALL && !ff.sibling) {   // :783-791: identity (and a warning) when no rotation is computed
         std::vector<R> id(9 * ff.n_nodes, R(0));
         for (size_t n = 0; n < ff.n_nodes; ++n) id[9 * n] = id[9 * n + 4] = id[9 * n + 8] = R(1);
         SB_CUDA(cudaMemcpyAsync(out_dev, id.data(), id.size() * sizeof(R), cudaMemcpyHostToDevice, s));
@@ -265,7 +267,14 @@ template <class R> static int tet_node_rotations(TetFF<R>& ff, R* out_dev) {
         return SOFAB200_OK;
     }
     SB_TRY(tet_build_incidence(ff));
-    tet_node_rotations_kernel<R><<<unsigned((ff.n_nodes + 127) / 128), 128, 0, s>>>(ff.dev(), ff.inc_off.p, ff.inc_es.p, ff.inc_e.p, ff.r0t_el.p, ff.es_of_first, out_dev);
+    int sibling = 0;
+    if (ff.sibling) {
+        if (ff.method == SOFAB200_TET_SMALL) return fail(SOFAB200_ERR_UNSUPPORTED, "TetrahedralCorotationalFEMForceField keeps no rotations with method small");
+        sibling = ff.method == SOFAB200_TET_POLAR ? 2 : 1;
+        if (sibling == 2 && !ff.a0_el.p) { SB_TRY(ff.a0_el.upload(ff.h.h_A0, s)); SB_CUDA(cudaStreamSynchronize(s)); }
+    }
+    tet_node_rotations_kernel<R><<<unsigned((ff.n_nodes + 127) / 128), 128, 0, s>>>(ff.dev(), ff.inc_off.p, ff.inc_es.p, ff.inc_e.p, sibling == 2 ? ff.a0_el.p : ff.r0t_el.p, ff.es_of_first,
+                                                                                      out_dev, sibling);
     ff.ctx->launches++;
     SB_CUDA(cudaGetLastError());
     return SOFAB200_OK;

@@ -16,6 +16,7 @@ template <class R> struct HostTet {
     HostPlan plan;
     // element-ordered values, as the reference class keeps them
     std::vector<R> h_K, h_J, h_X0, h_R0t, h_A0inv;
+    std::vector<R> h_A0;   // TetrahedralCorotationalFEMForceField, polar: initialTransformation = the rest edge matrix (its getRotation multiplies by it)
     std::vector<R> h_shf, h_lambda, h_mu, h_rest;   // computeVonMisesStress != 0: elemShapeFun rows 1..3 (12 per element), elemLambda, elemMu, d_initialPoints
     // element planes in tile order
     std::vector<ushort4> lnode; std::vector<uint4> slot;
@@ -115,6 +116,7 @@ template <class R> static int tet_init_elements(HostTet<R>& ff, const R* x0, con
         } else {
             M3<R> A;
             set_row(A, 0, b - a); set_row(A, 1, c - a); set_row(A, 2, d - a);
+            if (desc->tetrahedral_corotational) { if (ff.h_A0.empty()) ff.h_A0.assign(9 * T, 0); for (int r = 0; r < 3; ++r) for (int cc = 0; cc < 3; ++cc) ff.h_A0[9 * i + 3 * r + cc] = A.m[r][cc]; }
             if (ff.method == SOFAB200_TET_SVD) {
                 M3<R> Ai;
                 std::memset(&Ai, 0, sizeof(Ai));

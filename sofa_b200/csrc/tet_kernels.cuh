@@ -501,10 +501,54 @@ template <class R> __global__ void tet_von_mises_nodes_kernel(size_t n, const ui
 // tetrahedra around it in ascending index, made orthogonal by polarDecomposition.  One thread per node; `inc` lists the tile-order slot
 // of the incident elements and `r0t` holds _initialRotations in ORIGINAL element order.  A node without tetrahedra takes element
 // _rotationIdx[node] = 0 (the array is zero-filled by resize, :1471).
+// sibling != 0: TetrahedralCorotationalFEMForceField::getRotation (TetrahedralCorotationalFEMForceField.inl:779-820) instead -- the sum of
+// rotation * initialTransformation (1: large, initialTransformation = R_0_1 = r0t transposed; 2: polar, = the rest edge matrix, r0t then holds it
+// as is), scaled by Real(1.0f / n), and made orthogonal by normalising rows 0 and 1 and two cross products (no polar decomposition).
 template <class R> __global__ void tet_node_rotations_kernel(TetDev<R> d, const uint32_t* __restrict__ inc_off, const uint32_t* __restrict__ inc_es,
-                                                             const uint32_t* __restrict__ inc_e, const R* __restrict__ r0t, uint32_t es_of_first, R* __restrict__ out) {
+                                                             const uint32_t* __restrict__ inc_e, const R* __restrict__ r0t, uint32_t es_of_first, R* __restrict__ out,
+                                                             int sibling = 0) {
     const size_t n = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (n >= size_t(d.t.n_nodes)) return;
+    if (sibling) {
+        M3<R> acc;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) acc.m[i][j] = R(0);
+        const uint32_t b = inc_off[n], e = inc_off[n + 1];
+        for (uint32_t k = b; k < e; ++k) {
+            const uint32_t es = inc_es[k];
+            const Quad<R> q0 = d.rk0[es], q1 = d.rk1[es], q2 = d.rk2[es];
+            M3<R> rot, r01;
+            rot.m[0][0] = q0.a; rot.m[0][1] = q0.b; rot.m[0][2] = q0.c; rot.m[1][0] = q0.d; rot.m[1][1] = q1.a; rot.m[1][2] = q1.b;
+            rot.m[2][0] = q1.c; rot.m[2][1] = q1.d; rot.m[2][2] = q2.a;
+            const R* p = r0t + 9 * size_t(inc_e[k]);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) r01.m[i][j] = sibling == 1 ? p[3 * j + i] : p[3 * i + j];
+            const M3<R> pr = mul(rot, r01);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) acc.m[i][j] += pr.m[i][j];
+        }
+        const R sc = R(1.0f / float(int(e - b)));
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) acc.m[i][j] = acc.m[i][j] * sc;
+        V3<R> ex = row(acc, 0), ey = row(acc, 1);
+        normalize3(ex);
+        normalize3(ey);
+        V3<R> ez = cross3(ex, ey);
+        normalize3(ez);
+        ey = cross3(ez, ex);
+        normalize3(ey);
+        R* o = out + 9 * n;
+        o[0] = ex.x; o[1] = ex.y; o[2] = ex.z; o[3] = ey.x; o[4] = ey.y; o[5] = ey.z; o[6] = ez.x; o[7] = ez.y; o[8] = ez.z;
+        return;
+    }
     auto elem_product = [&](uint32_t es, uint32_t e) {
         const Quad<R> q0 = d.rk0[es], q1 = d.rk1[es], q2 = d.rk2[es];
         M3<R> rot, r0;

@@ -141,6 +141,12 @@ def test_tetrahedral_corotational_fem_force_field(dtype, method, update, meshnam
         if not update:
             t_d = dev(mo, f0); twin.addForce(t_d, dev(mo, x))
             assert t_d.cpu().numpy().tobytes() == f_d.cpu().numpy().tobytes()
+        if method != "small":   # the class's own getRotation (.inl:779-820): rotation * initialTransformation averaged, Gram-Schmidt
+            f_d = dev(mo, f0); ff.addForce(f_d, dev(mo, x)); s.fem_add_force(f0, x)      # (addDForce does not touch the rotations; same state on both sides)
+            assert ff.getRotations().cpu().numpy().tobytes() == s.tet_get_rotations().tobytes(), it
+    if method == "small":
+        with pytest.raises(sb.Sofab200Error):
+            ff.getRotations()
     with pytest.raises((ValueError, sb.Sofab200Error)):
         sb.TetrahedralCorotationalFEMForceField(mo, tets, method="svd")
 
