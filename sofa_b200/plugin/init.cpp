@@ -9,6 +9,8 @@ namespace sofa::b200 {
 void registerMechanicalObject(sofa::core::ObjectFactory*);
 void registerTetrahedronFEMForceField(sofa::core::ObjectFactory*);
 void registerHexahedronFEMForceField(sofa::core::ObjectFactory*);
+void registerTetrahedralCorotationalFEMForceField(sofa::core::ObjectFactory*);
+void registerMeshMatrixMass(sofa::core::ObjectFactory*);
 void registerDiagonalMass(sofa::core::ObjectFactory*);
 void registerFixedProjectiveConstraint(sofa::core::ObjectFactory*);
 void registerCGLinearSolver(sofa::core::ObjectFactory*);
@@ -27,6 +29,8 @@ SOFA_EXPORT_DYNAMIC_LIBRARY void registerObjects(sofa::core::ObjectFactory* fact
     sofa::b200::registerMechanicalObject(factory);
     sofa::b200::registerTetrahedronFEMForceField(factory);
     sofa::b200::registerHexahedronFEMForceField(factory);
+    sofa::b200::registerTetrahedralCorotationalFEMForceField(factory);
+    sofa::b200::registerMeshMatrixMass(factory);
     sofa::b200::registerDiagonalMass(factory);
     sofa::b200::registerFixedProjectiveConstraint(factory);
     sofa::b200::registerCGLinearSolver(factory);
