@@ -61,11 +61,8 @@ template <class R> static int hex_upload(HexFF<R>& ff) {
 
 template <class R, int MODE> static int hex_launch_mode(HexFF<R>& ff, const HexDev<R>& d, const R* in, const NodeEpilogue<R>& ep) {
     auto kern = hex_tile_kernel<R, MODE>;
-    static thread_local size_t configured = 0;
-    if (ff.h.smem_bytes > 48 * 1024 && configured < ff.h.smem_bytes) {
-        SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ff.h.smem_bytes)));
-        configured = ff.h.smem_bytes;
-    }
+    // (per device and context, not per thread: set for the current device on every launch)
+    if (ff.h.smem_bytes > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ff.h.smem_bytes)));
     const int cls = MODE == HM_DF ? 0 : 2;
     ff.ctx->prof_start(cls);
     kern<<<ff.h.plan.n_tiles, 256, ff.h.smem_bytes, ff.ctx->stream>>>(d, in, ep, ff.h.plan.max_touched, ff.h.plan.max_slots);

@@ -120,6 +120,10 @@ template <class R> struct Node : sofab200_node {
     cudaStream_t side_stream = nullptr;    // step_host: the v copy runs here while addForce (which only needs x) runs on the main stream
     cudaEvent_t side_event = nullptr;
     bool use_graph = true;
+    // a captured step bakes in which mass / halo path the node takes: forget it whenever that changes
+    void invalidate_graphs() {
+        for (StepGraph* g : {&sg, &sg_rest}) { if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; } g->seen = 0; }
+    }
     ~Node() {
         if (sg.exec) cudaGraphExecDestroy(sg.exec);
         if (sg_rest.exec) cudaGraphExecDestroy(sg_rest.exec);
@@ -158,7 +162,7 @@ template <class R> struct Node : sofab200_node {
         if (!distributed() || halo.n_if == 0) return SOFAB200_OK;
         if (peer.ready && !cgp) {
             // over peer memory, one small kernel (the NCCL route below costs three launches and a send/recv group)
-            LAUNCH(ctx, (halo_peer_kernel<R>), 1, 1024, peer.dev, halo.n_if, (const uint32_t*)halo.if_idx.p, qv, peer.hcount, peer.buf_words, peer.fail_flag.p);
+            LAUNCH(ctx, (halo_peer_kernel<R>), 1, 1024, peer.dev, halo.n_if, (const uint32_t*)halo.if_idx.p, qv, peer.hcount, peer.buf_words, peer.fail_flag.p, cg.p);
             return SOFAB200_OK;
         }
         LAUNCH(ctx, (halo_pack_kernel<R>), vec_grid(halo.n_send, ctx->sm_count), kVecBlock, halo.n_send, (const uint32_t*)halo.send_idx.p, (const R*)qv, halo.sendbuf.p, cgp);
@@ -306,7 +310,7 @@ template <class R> struct Node : sofab200_node {
         const int g = vec_grid(n3, ctx->sm_count);
         if (mesh_mass) persistent = false;   // the persistent kernel keeps p of interior nodes in shared memory: no neighbour access for the edge terms
         CGBegin cb{prm.iterations, prm.tolerance, prm.threshold};
-        LAUNCH(ctx, cg_begin_kernel, 1, 1, cg.p, cb);
+        LAUNCH(ctx, cg_begin_kernel, 1, 1, cg.p, cb, (const int*)(peer.ready ? peer.fail_flag.p : nullptr));
         if (prm.warm_start) {
             SB_TRY(apply(r.p, x, m, bfac, k));                                             // r = A x
             LAUNCH(ctx, (vop_kernel<R, VOP_AVF>), g, kVecBlock, n3, r.p, bvec, (const R*)nullptr, R(-1.0));  // r = b + r*(-1)
@@ -636,6 +640,12 @@ int sofab200_comm_destroy(sofab200_comm* comm) {
 namespace sb {
 template <class R> static int node_set_distributed(Node<R>* nd, sofab200_comm* comm, const sofab200_halo_desc* h) {
     cudaStream_t s = nd->ctx->stream;
+    // every rank applies the per-node epilogue to its copy of an interface node and the copies are then summed over the sharers: only the
+    // DiagonalMass term is masked by ownership (the caller zeroes vertexMass on the non-owned copies).  PlaneForceField, UniformMass and
+    // MeshMatrixMass terms would be counted once per sharing rank.
+    if (nd->has_plane) return fail(SOFAB200_ERR_UNSUPPORTED, "a node with a PlaneForceField cannot be distributed (its term would be counted once per sharing rank on interface nodes)");
+    if (nd->uniform_mass) return fail(SOFAB200_ERR_UNSUPPORTED, "a node with a UniformMass cannot be distributed; use a DiagonalMass whose vertexMass is zero on non-owned interface nodes");
+    if (nd->mesh_mass) return fail(SOFAB200_ERR_UNSUPPORTED, "MeshMatrixMass is not available in a distributed node");
     auto& H = nd->halo;
     H.n_if = h->n_interface; H.max_sh = std::max(1, h->max_sharers);
     std::vector<unsigned char> owned(h->owned, h->owned + nd->n);
@@ -665,8 +675,7 @@ template <class R> static int node_set_distributed(Node<R>* nd, sofab200_comm* c
     SB_TRY(H.scal.alloc(2)); SB_TRY(H.scal.zero(s));
     SB_CUDA(cudaStreamSynchronize(s));
     H.comm = comm;
-    if (nd->sg.exec) { cudaGraphExecDestroy(nd->sg.exec); nd->sg.exec = nullptr; nd->sg.seen = 0; }
-    if (nd->sg_rest.exec) { cudaGraphExecDestroy(nd->sg_rest.exec); nd->sg_rest.exec = nullptr; nd->sg_rest.seen = 0; }
+    nd->invalidate_graphs();
     return SOFAB200_OK;
 }
 // mailbox layout (bytes): 64 all-reduce slots [2][kMaxPeers][2 words] | 320 epoch u64 | 328 halo-call counter u64 | 1024 three inbox
@@ -677,16 +686,15 @@ template <class R> static size_t node_peer_bytes(const Node<R>* nd, size_t rows)
     return kMailboxInbox + 3 * inbox_buf_words<R>(std::max(rows, nd->halo.n_send)) * sizeof(unsigned long long) + 256;
 }
 template <class R> static int node_set_peer(Node<R>* nd, const sofab200_peer_desc* d) {
-    if (!d->peer_base) { nd->peer.ready = false; if (nd->sg.exec) { cudaGraphExecDestroy(nd->sg.exec); nd->sg.exec = nullptr; nd->sg.seen = 0; }
-    if (nd->sg_rest.exec) { cudaGraphExecDestroy(nd->sg_rest.exec); nd->sg_rest.exec = nullptr; nd->sg_rest.seen = 0; } return SOFAB200_OK; }
+    if (!d->peer_base) { nd->peer.ready = false; nd->invalidate_graphs(); return SOFAB200_OK; }
     SB_CHECK(nd->distributed(), "sofab200_node_set_distributed must come first");
+    SB_CHECK(nd->tet != nullptr, "peer mode is implemented for the tetrahedral force field");
     {
         PersistCG<R> probe; std::memset(&probe, 0, sizeof(probe));
         const int rc = tet_cg_persistent<R>(nd->tet, R(1), probe, size_t(3) * 2048, true);
         if (rc == kPersistNotEligible) return fail(SOFAB200_ERR_UNSUPPORTED, "this partition does not fit the persistent CG kernel (more than two tiles per SM)");
         if (rc != SOFAB200_OK) return rc;
     }
-    SB_CHECK(nd->tet != nullptr, "peer mode is implemented for the tetrahedral force field");
     SB_CHECK(d->world >= 1 && d->world <= kMaxPeers && d->rank >= 0 && d->rank < d->world, "rank / world out of range (world <= 8)");
     auto& H = nd->halo;
     SB_CHECK(int(H.nb_rank.size()) <= kMaxPeers, "too many neighbours");
@@ -734,8 +742,7 @@ template <class R> static int node_set_peer(Node<R>* nd, const sofab200_peer_des
     P.sh_if_row = nd->peer.sh_if_row.p; P.if_send = nd->peer.if_send.p; P.src = H.src.p; P.owned = H.owned.p;
     P.enabled = 1;
     nd->peer.ready = true;
-    if (nd->sg.exec) { cudaGraphExecDestroy(nd->sg.exec); nd->sg.exec = nullptr; nd->sg.seen = 0; }
-    if (nd->sg_rest.exec) { cudaGraphExecDestroy(nd->sg_rest.exec); nd->sg_rest.exec = nullptr; nd->sg_rest.seen = 0; }
+    nd->invalidate_graphs();
     return SOFAB200_OK;
 }
 }  // namespace sb
@@ -789,15 +796,15 @@ int sofab200_node_set_mesh_mass(sofab200_node* node, sofab200_meshmass* mesh_mas
     int mreal = 0; size_t mn = 0; const sofab200_ctx* mctx = nullptr;
     sb::meshmass_info(mesh_mass, &mreal, &mn, &mctx);
     SB_CHECK(mreal == node->real && mn == node->n && mctx == node->ctx, "the MeshMatrixMass must have the node's real type, size and context");
-    if (node->real == SOFAB200_F32) { NF(node)->mesh_mass = mesh_mass; NF(node)->has_mass = true; }
-    else { ND(node)->mesh_mass = mesh_mass; ND(node)->has_mass = true; }
+    if (node->real == SOFAB200_F32) { SB_CHECK(!NF(node)->distributed(), "MeshMatrixMass is not available in a distributed node"); NF(node)->mesh_mass = mesh_mass; NF(node)->has_mass = true; NF(node)->invalidate_graphs(); }
+    else { SB_CHECK(!ND(node)->distributed(), "MeshMatrixMass is not available in a distributed node"); ND(node)->mesh_mass = mesh_mass; ND(node)->has_mass = true; ND(node)->invalidate_graphs(); }
     return SOFAB200_OK;
 }
 int sofab200_node_set_vertex_mass(sofab200_node* node, const void* vertex_mass_host) {
     SB_CHECK(node && vertex_mass_host, "null argument");
     cudaStream_t s = node->ctx->stream;
-    if (node->real == SOFAB200_F32) { auto* n = NF(node); if (!n->mass.p) SB_TRY(n->mass.alloc(n->n)); n->has_mass = true; SB_CUDA(cudaMemcpyAsync(n->mass.p, vertex_mass_host, n->n * 4, cudaMemcpyHostToDevice, s)); }
-    else { auto* n = ND(node); if (!n->mass.p) SB_TRY(n->mass.alloc(n->n)); n->has_mass = true; SB_CUDA(cudaMemcpyAsync(n->mass.p, vertex_mass_host, n->n * 8, cudaMemcpyHostToDevice, s)); }
+    if (node->real == SOFAB200_F32) { auto* n = NF(node); if (!n->mass.p) { SB_TRY(n->mass.alloc(n->n)); n->invalidate_graphs(); } if (!n->has_mass) n->invalidate_graphs(); n->has_mass = true; SB_CUDA(cudaMemcpyAsync(n->mass.p, vertex_mass_host, n->n * 4, cudaMemcpyHostToDevice, s)); }
+    else { auto* n = ND(node); if (!n->mass.p) { SB_TRY(n->mass.alloc(n->n)); n->invalidate_graphs(); } if (!n->has_mass) n->invalidate_graphs(); n->has_mass = true; SB_CUDA(cudaMemcpyAsync(n->mass.p, vertex_mass_host, n->n * 8, cudaMemcpyHostToDevice, s)); }
     SB_CUDA(cudaStreamSynchronize(s));
     return SOFAB200_OK;
 }

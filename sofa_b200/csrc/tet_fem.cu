@@ -74,12 +74,9 @@ template <class R> static int tet_upload(TetFF<R>& ff) {
 
 template <class R, int MODE, int MAXT, bool PF> static int tet_launch_variant(TetFF<R>& ff, const TetDev<R>& d, const R* in, const NodeEpilogue<R>& ep) {
     auto kern = tet_tile_kernel<R, MODE, MAXT, PF>;
-    static thread_local size_t configured = 0;
+    // (the attribute is per device and context, not per thread: set it for the current device on every launch -- a host-side table lookup)
     const size_t smem_total = ff.h.smem_bytes;
-    if (smem_total > 48 * 1024 && configured < smem_total) {
-        SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_total)));
-        configured = smem_total;
-    }
+    if (smem_total > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_total)));
     const int cls = (MODE == TM_DF_COROT || MODE == TM_DF_SMALL) ? 0 : 2;
     ff.ctx->prof_start(cls);
     kern<<<ff.h.plan.n_tiles, ((MODE == TM_DF_COROT || (MODE == TM_F_LARGE && MAXT > 256)) && sizeof(R) == 4) ? std::min(ff.threads, MAXT) : 256, smem_total, ff.ctx->stream>>>(d, in, ep, ff.h.plan.max_touched, ff.h.plan.max_slots);

@@ -251,7 +251,11 @@ template <class R> __global__ void __launch_bounds__(kVecBlock) mask_rows_kernel
 // sequence number, see cg_persist.cuh), then the rows are rebuilt from the own value and the neighbours' words in ascending rank
 // order.  Two inbox buffers alternate from call to call (a neighbour may start call k+1 before this rank has read call k).
 template <class R> __global__ void __launch_bounds__(1024) halo_peer_kernel(PeerDev<R> P, size_t n_if, const uint32_t* __restrict__ if_idx, R* q,
-                                                                             unsigned long long* hcount, size_t buf_words, int* fail_flag) {
+                                                                             unsigned long long* hcount, size_t buf_words, int* fail_flag, CGDev* cg) {
+    // a late or missing neighbour must not yield silently wrong rows: the flag is sticky, the step's solve is marked failed (end_cond 99),
+    // sofab200_node_last_solve / _step_host report it, and the call counter is not advanced past a failed exchange
+    __shared__ int s_fail;
+    if (threadIdx.x == 0) s_fail = 0;
     const unsigned long long c = *hcount + 1;
     const unsigned seq = unsigned(c);
     const size_t boff = (1 + (c & 1ull)) * buf_words;       // buffer 0 belongs to the CG kernel
@@ -276,14 +280,17 @@ template <class R> __global__ void __launch_bounds__(1024) halo_peer_kernel(Peer
                 const unsigned long long* w = P.inbox + boff + size_t(InboxWords<R>::N) * size_t(sj);
                 const unsigned long long t0 = globaltimer_ns();
                 while (!(inbox_get(w, 0, seq, c0) && inbox_get(w, 1, seq, c1) && inbox_get(w, 2, seq, c2)))
-                    if (globaltimer_ns() - t0 > kSyncTimeoutNs) { *fail_flag = 1; break; }
+                    if (globaltimer_ns() - t0 > kSyncTimeoutNs) { s_fail = 1; break; }
             }
             if (j == 0) { s0 = c0; s1 = c1; s2 = c2; } else { s0 += c0; s1 += c1; s2 += c2; }
         }
         q[g3] = s0; q[g3 + 1] = s1; q[g3 + 2] = s2;
     }
     __syncthreads();
-    if (threadIdx.x == 0) *hcount = c;
+    if (threadIdx.x == 0) {
+        if (s_fail) { *fail_flag = 1; if (cg) { cg->done = 1; cg->end_cond = 99; } }
+        else *hcount = c;
+    }
 }
 
 // the scalar bookkeeping of the CG after an all-reduced dot product
@@ -377,8 +384,10 @@ template <class R> __global__ void __launch_bounds__(kTailBlock) cg_tail_kernel(
 }
 
 struct CGBegin { unsigned max_iter; double tolerance, threshold; };
-__global__ void cg_begin_kernel(CGDev* cg, CGBegin b) {
+// fail: sticky flag of the peer-memory halo exchange (null outside peer mode); a solve whose inputs went through a failed exchange does not run
+__global__ void cg_begin_kernel(CGDev* cg, CGBegin b, const int* fail) {
     cg->done = 0; cg->nb_iter = 0; cg->end_cond = 0; cg->it = 0;
+    if (fail && *fail) { cg->done = 1; cg->end_cond = 99; }
     cg->max_iter = b.max_iter; cg->tolerance = b.tolerance; cg->threshold = b.threshold;
     cg->rho = 0; cg->rho_1 = 0; cg->den = 0; cg->alpha = 0; cg->normb = 0;
     cg->n_err = 1; cg->graph_error[0] = 1.0; cg->n_den = 0;
