@@ -92,6 +92,15 @@ __device__ __forceinline__ void trace_mark(unsigned long long* trace, int base, 
         if (i == 0) { unsigned sm; asm volatile("mov.u32 %0, %smid;" : "=r"(sm)); trace[base + blockIdx.x * kTraceWords + 7] = sm; }
     }
 }
+__device__ __forceinline__ void trace_mark_by(unsigned long long* trace, int base, int i, int who) {
+    if (trace && int(threadIdx.x) == who) {
+        unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        trace[base + blockIdx.x * kTraceWords + i] = t;
+    }
+}
+#else
+inline void trace_mark(unsigned long long*, int, int) {}
+inline void trace_mark_by(unsigned long long*, int, int, int) {}
 #endif
 
 template <class R> struct TileDev {
@@ -99,6 +108,7 @@ template <class R> struct TileDev {
     // per tile
     const uint32_t* tile_node_off;   // [n_tiles+1] into tile_nodes
     const uint32_t* tile_nodes;      // global node ids: interior (ranked by valence desc) then shared
+    const uint32_t* tile_shslot;     // aligned with tile_nodes: a shared node's index in sh_nodes (fused CG kernel: the owner's state arrays are indexed by it)
     const uint32_t* tile_nint;       // [n_tiles]
     const uint32_t* tile_nb;         // [n_tiles] leading elements of the tile that feed shared nodes (null: unknown)
     const uint16_t* tile_val;        // valence of each interior node, aligned with tile_nodes (shared entries unused)

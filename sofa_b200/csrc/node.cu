@@ -7,6 +7,7 @@
 #include <nccl.h>
 
 #include "vec_ops.cuh"
+#include "cg_fused.cuh"
 
 using namespace sb;
 
@@ -14,6 +15,8 @@ namespace sb {
 // implemented in tet_fem.cu / hex_fem.cu
 template <class R> int tet_run(sofab200_tetfem* ff, bool dforce, const R* in, R k_factor, NodeEpilogue<R> ep, bool skip_gather);
 template <class R> int tet_cg_persistent(sofab200_tetfem* ff, R k_factor, PersistCG<R> a, size_t part_capacity, bool dry_run);
+template <class R> int tet_cg_fused(sofab200_tetfem* ff, R k_factor, FusedCG<R> a, size_t sync_capacity, bool dry_run, int* info);
+size_t tet_shared_slot_count(sofab200_tetfem* ff);
 size_t tet_tile_node_count(sofab200_tetfem* ff);
 const std::vector<uint32_t>& tet_shared_node_table(sofab200_tetfem* ff);
 template <class R> TileDev<R> tet_tiledev(sofab200_tetfem* ff);
@@ -236,6 +239,29 @@ template <class R> struct Node : sofab200_node {
         if (rc == SOFAB200_OK) ctx->launches++;
         return rc;
     }
+    // second-generation kernel (cg_fused.cuh): one reduction per iteration, any number of tiles per CTA
+    bool fused = true;           // SOFAB200_CG_FUSED=0 selects the first-generation persistent kernel
+    DevBuf<typename SVec<R>::T> gP, xS, rS, pS, qS;
+    DevBuf<R> gQ;
+    DevBuf<NodeRec<R>> gNrec;
+    DevBuf<GRec<R>> shrec;
+    int fused_info[6] = {0, 0, 0, 0, 0, 0};
+    int launch_fused(R* x, const R* bvec, double m, double bfac, double k) {
+        if (!tet) return kPersistNotEligible;
+        const double kf = k + bfac * prm.ff_rayleigh_stiffness;
+        const size_t n_tile_nodes = tet_tile_node_count(tet), n_slots = tet_shared_slot_count(tet);
+        if (xt.n < n_tile_nodes) { SB_TRY(xt.alloc(n_tile_nodes)); SB_TRY(rt.alloc(n_tile_nodes)); }
+        if (gP.n < n_tile_nodes) { SB_TRY(gP.alloc(n_tile_nodes)); SB_TRY(gQ.alloc(3 * n_tile_nodes)); SB_TRY(gNrec.alloc(n_tile_nodes)); }
+        if (xS.n < n_slots) { SB_TRY(xS.alloc(n_slots)); SB_TRY(rS.alloc(n_slots)); SB_TRY(pS.alloc(n_slots)); SB_TRY(qS.alloc(n_slots)); SB_TRY(shrec.alloc(n_slots)); }
+        if (!sync_slots.p) SB_TRY(sync_slots.alloc(3 * 2048 + 8));
+        FusedCG<R> a;
+        a.ep = make_mbk_ep(q.p, nullptr, p.p, m, bfac, k, false, 1.0, true, DOT_STORE, cg.p);
+        a.x = x; a.r = r.p; a.b = bvec; a.xt = xt.p; a.rt = rt.p; a.gP = gP.p; a.gQ = gQ.p; a.gNrec = gNrec.p;
+        a.xS = xS.p; a.rS = rS.p; a.pS = pS.p; a.qS = qS.p; a.shrec = shrec.p; a.n3 = 3 * n; a.cg = cg.p; a.sync = sync_slots.p;
+        std::memset(&a.peer, 0, sizeof(a.peer));
+        SB_CUDA(cudaMemsetAsync(sync_slots.p, 0, sync_slots.n * sizeof(unsigned long long), ctx->stream));
+        return tet_cg_fused<R>(tet, R(kf), a, sync_slots.n, false, fused_info);
+    }
     NodeEpilogue<R> base_ep() {
         NodeEpilogue<R> ep{};
         ep.mass = mass.p; ep.partials = partials.p; ep.counter = counters.p; ep.cg = nullptr; ep.trace = ctx->trace.p;
@@ -344,6 +370,12 @@ template <class R> struct Node : sofab200_node {
             return SOFAB200_OK;
         }
         const double kf_chk = k + bfac * prm.ff_rayleigh_stiffness;
+        if (persistent && fused && tet && (kf_chk != 0.0 || bfac != 0.0)) {
+            const int rc = launch_fused(x, bvec, m, bfac, k);                   // (|b| and the first rho included)
+            if (rc == SOFAB200_OK) { LAUNCH(ctx, cg_end_kernel, 1, 1, cg.p); return SOFAB200_OK; }
+            if (rc != kPersistNotEligible) return rc;
+            fused = false;
+        }
         if (persistent && (kf_chk != 0.0 || bfac != 0.0)) {
             const int rc = launch_persistent(x, bvec, m, bfac, k, nullptr);     // (|b| and the first rho included)
             if (rc == SOFAB200_OK) { LAUNCH(ctx, cg_end_kernel, 1, 1, cg.p); return SOFAB200_OK; }
@@ -449,6 +481,7 @@ template <class R> static int node_create(sofab200_ctx* ctx, size_t n, const sof
     if (const char* env = getenv("SOFAB200_GRAPH")) nd->use_graph = atoi(env) != 0;
     if (const char* env = getenv("SOFAB200_FUSED_TAIL")) nd->fused_tail = atoi(env) != 0;
     if (const char* env = getenv("SOFAB200_CG_PERSISTENT")) nd->persistent = atoi(env) != 0;
+    if (const char* env = getenv("SOFAB200_CG_FUSED")) nd->fused = atoi(env) != 0;
     std::memset(&nd->prm, 0, sizeof(nd->prm));
     nd->prm.gravity[1] = -9.81; nd->prm.dt = 0.01; nd->prm.iterations = 25; nd->prm.tolerance = 1e-5; nd->prm.threshold = 1e-5;
     cudaStream_t s = ctx->stream;

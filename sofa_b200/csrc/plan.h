@@ -14,13 +14,14 @@ struct HostPlan {
     std::vector<uint32_t> order;          // [n_tiles*tile_e] element slot -> original element (0xFFFFFFFF = padding)
     std::vector<uint32_t> tile_node_off;  // [n_tiles+1]
     std::vector<uint32_t> tile_nodes;
+    std::vector<uint32_t> tile_shslot;    // aligned with tile_nodes: for a shared node, its index in sh_nodes (chunk * chunk_size + rank); 0xFFFFFFFF for interior entries
     std::vector<uint32_t> tile_nint;
     std::vector<uint32_t> tile_nb;        // [n_tiles] elements of the tile that feed at least one shared node, when they come FIRST in the tile (else 0xFFFFFFFF)
     std::vector<uint16_t> tile_val;
     std::vector<uint16_t> tile_jds;       // [n_tiles][maxval+1]
     std::vector<uint16_t> lnode;          // [n_tiles*tile_e*npe]
     std::vector<uint32_t> slot;           // [n_tiles*tile_e*npe]
-    int n_shared = 0, n_chunks = 0;
+    int n_shared = 0, n_chunks = 0, n_forced_shared = 0;
     std::vector<uint32_t> sh_nodes;       // [n_chunks*chunk]
     std::vector<uint16_t> sh_val;
     std::vector<uint32_t> sh_base;        // [n_chunks] first staging entry of the chunk's ELL block
@@ -220,7 +221,11 @@ inline std::string build_plan(HostPlan& P, int n_nodes, int n_elems, int npe, co
     // chunk c is staged at sh_base[c] + j*chunk + k: an ELL block per chunk, padded to the chunk's largest valence, so that
     // the staging address needs no index table and consecutive threads (k) read consecutive 16-byte entries.
     std::vector<uint32_t> shared;
-    for (int i = 0; i < n_nodes; ++i) if (interior_tile[i] < 0) shared.push_back(uint32_t(i));
+    // (nodes flagged in force_shared come first: in a multi-GPU run these are the partition-interface nodes, whose partial sums must
+    // leave for the other GPUs as early as possible in the shared-node phase)
+    if (force_shared) for (int i = 0; i < n_nodes; ++i) if (interior_tile[i] < 0 && force_shared[i] && inc_off[i + 1] > inc_off[i]) shared.push_back(uint32_t(i));
+    P.n_forced_shared = int(shared.size());
+    for (int i = 0; i < n_nodes; ++i) if (interior_tile[i] < 0 && !(force_shared && force_shared[i] && inc_off[i + 1] > inc_off[i])) shared.push_back(uint32_t(i));
     P.n_shared = int(shared.size());
     P.n_chunks = std::max(1, (P.n_shared + chunk - 1) / chunk);
     P.sh_nodes.assign(size_t(P.n_chunks) * chunk, 0xFFFFFFFFu);
@@ -245,6 +250,13 @@ inline std::string build_plan(HostPlan& P, int n_nodes, int n_elems, int npe, co
         stage += size_t(mv) * chunk;
     }
     P.stage_n = std::max<size_t>(stage, 1);
+    {
+        std::vector<uint32_t> slot_of(n_nodes, 0xFFFFFFFFu);
+        for (size_t i = 0; i < shared.size(); ++i) slot_of[shared[i]] = uint32_t(i);   // (chunks are consecutive runs of `chunk` shared nodes: index == chunk * chunk_size + rank)
+        P.tile_shslot.assign(P.tile_nodes.size(), 0xFFFFFFFFu);
+        for (int t = 0; t < P.n_tiles; ++t)
+            for (uint32_t i = P.tile_node_off[t] + P.tile_nint[t]; i < P.tile_node_off[t + 1]; ++i) P.tile_shslot[i] = slot_of[P.tile_nodes[i]];
+    }
 
     // ---- per element-slot destination table
     P.slot.assign(n_slots * npe, 0);

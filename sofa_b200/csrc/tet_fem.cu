@@ -19,7 +19,7 @@ template <class R> struct TetFF : sofab200_tetfem {
     HostTet<R> h;
     DevBuf<ushort4> lnode; DevBuf<uint4> slot; DevBuf<uint32_t> orig;
     DevBuf<Quad<R>> rk0, rk1, rk2, j0, j1, j2, x0a, x0b, x0c, sv0, sv1, sv2, sv3, sv4;
-    DevBuf<uint32_t> tile_node_off, tile_nodes, tile_nint, tile_nb, sh_nodes, sh_base;
+    DevBuf<uint32_t> tile_node_off, tile_nodes, tile_shslot, tile_nint, tile_nb, sh_nodes, sh_base;
     DevBuf<uint16_t> tile_val, tile_jds, sh_val;
     DevBuf<Quad<R>> stage;
     bool update_j = false;   // updateStiffnessMatrix (polar / svd)
@@ -34,7 +34,7 @@ template <class R> struct TetFF : sofab200_tetfem {
         const HostPlan& plan = h.plan;
         TetDev<R> d;
         d.t.n_nodes = int(n_nodes); d.t.n_elems = int(n_tets); d.t.n_tiles = plan.n_tiles; d.t.tile_e = plan.tile_e; d.t.maxval = plan.maxval;
-        d.t.tile_node_off = tile_node_off.p; d.t.tile_nodes = tile_nodes.p; d.t.tile_nint = tile_nint.p; d.t.tile_nb = tile_nb.p; d.t.tile_val = tile_val.p; d.t.tile_jds = tile_jds.p;
+        d.t.tile_node_off = tile_node_off.p; d.t.tile_nodes = tile_nodes.p; d.t.tile_shslot = tile_shslot.p; d.t.tile_nint = tile_nint.p; d.t.tile_nb = tile_nb.p; d.t.tile_val = tile_val.p; d.t.tile_jds = tile_jds.p;
         d.t.n_shared = plan.n_shared; d.t.n_chunks = plan.n_chunks; d.t.sh_nodes = sh_nodes.p; d.t.sh_val = sh_val.p; d.t.sh_base = sh_base.p;
         d.t.stage = stage.p; d.t.stage_n = plan.stage_n;
         d.lnode = lnode.p; d.slot = slot.p;
@@ -59,7 +59,7 @@ template <class R> static int tet_upload(TetFF<R>& ff) {
         SB_TRY(ff.sv0.upload(H.sv[0], s)); SB_TRY(ff.sv1.upload(H.sv[1], s)); SB_TRY(ff.sv2.upload(H.sv[2], s));
         SB_TRY(ff.sv3.upload(H.sv[3], s)); SB_TRY(ff.sv4.upload(H.sv[4], s));
     }
-    SB_TRY(ff.tile_node_off.upload(P.tile_node_off, s)); SB_TRY(ff.tile_nodes.upload(P.tile_nodes, s)); SB_TRY(ff.tile_nint.upload(P.tile_nint, s)); SB_TRY(ff.tile_nb.upload(P.tile_nb, s));
+    SB_TRY(ff.tile_node_off.upload(P.tile_node_off, s)); SB_TRY(ff.tile_nodes.upload(P.tile_nodes, s)); SB_TRY(ff.tile_shslot.upload(P.tile_shslot, s)); SB_TRY(ff.tile_nint.upload(P.tile_nint, s)); SB_TRY(ff.tile_nb.upload(P.tile_nb, s));
     SB_TRY(ff.tile_val.upload(P.tile_val, s)); SB_TRY(ff.tile_jds.upload(P.tile_jds, s));
     SB_TRY(ff.sh_nodes.upload(P.sh_nodes, s)); SB_TRY(ff.sh_val.upload(P.sh_val, s)); SB_TRY(ff.sh_base.upload(P.sh_base, s));
     SB_TRY(ff.stage.alloc(P.stage_n)); SB_TRY(ff.stage.zero(s));
@@ -142,6 +142,62 @@ template <class R> int tet_cg_persistent(sofab200_tetfem* base, R k_factor, Pers
 }
 template int tet_cg_persistent<float>(sofab200_tetfem*, float, PersistCG<float>, size_t, bool);
 template int tet_cg_persistent<double>(sofab200_tetfem*, double, PersistCG<double>, size_t, bool);
+
+// ---- fused persistent CG kernel (cg_fused.cuh): any number of tiles per CTA -----------------------------------------------------------
+// Returns SOFAB200_OK, an error, or kPersistNotEligible when not even the streamed layout fits.  info (optional): {grid, tiles per CTA,
+// cached, dynamic shared memory, element threads, gather threads}.
+template <class R, int MODE, bool PF, int ET, int GT> static int tet_fused_variant(TetFF<R>& ff, TetDev<R> d, FusedCG<R> a, size_t sync_capacity, bool dry_run, int* info) {
+    auto kern = fused_cg_kernel<R, TetPass<R, MODE, PF>, ET, GT>;
+    const HostPlan& P = ff.h.plan;
+    cudaFuncAttributes fa;
+    SB_CUDA(cudaFuncGetAttributes(&fa, kern));
+    int dev_smem_optin = 0;
+    SB_CUDA(cudaDeviceGetAttribute(&dev_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ff.ctx->device));
+    const int grid = std::max(1, std::min(ff.ctx->sm_count, P.n_tiles));
+    const int tiles_per_cta = (P.n_tiles + grid - 1) / grid;
+    const int n_units = P.n_chunks * (kGatherChunk / kUnit);
+    const int units_per_cta = (n_units + grid - 1) / grid;
+    // cached layout when the CTA's tiles fit next to the slots inside the 196 KB carve-out (a larger one throttles the element stream), else streamed
+    size_t cached_limit = 196 * 1024;
+    if (const char* env = getenv("SOFAB200_FUSED_CACHED_KB")) { const int v = atoi(env); if (v >= 0 && v <= 227) cached_limit = size_t(v) * 1024; }
+    FusedLayout L = fused_layout<R>(true, tiles_per_cta, units_per_cta, P.max_touched, P.max_slots, P.max_int, P.max_shtouch, P.maxval);
+    if (tiles_per_cta > 2 || L.total + fa.sharedSizeBytes + 1024 > cached_limit) L = fused_layout<R>(false, tiles_per_cta, units_per_cta, P.max_touched, P.max_slots, P.max_int, P.max_shtouch, P.maxval);
+    if (L.total + fa.sharedSizeBytes > size_t(dev_smem_optin) || tiles_per_cta > kMaxFusedTiles * 64) return kPersistNotEligible;
+    SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<unsigned>(L.total, 1024))));
+    int per_sm = 0;
+    SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ET + GT, L.total));
+    if (per_sm < 1) return kPersistNotEligible;
+    if (fused_sync_words(grid) > sync_capacity) return fail(SOFAB200_ERR_INVALID, "sync buffer too small for the fused CG kernel");
+    if (info) { info[0] = grid; info[1] = tiles_per_cta; info[2] = L.cached; info[3] = int(L.total); info[4] = ET; info[5] = GT; }
+    if (dry_run) return SOFAB200_OK;
+    a.lay = L;
+    void* args[] = {&d, &a};
+    ff.ctx->prof_start(4);
+    SB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(ET + GT), args, L.total, ff.ctx->stream));
+    ff.ctx->prof_stop(4);
+    ff.ctx->launches++;
+    return SOFAB200_OK;
+}
+template <class R> int tet_cg_fused(sofab200_tetfem* base, R k_factor, FusedCG<R> a, size_t sync_capacity, bool dry_run, int* info) {
+    TetFF<R>& ff = *static_cast<TetFF<R>*>(base);
+    TetDev<R> d = ff.dev();
+    d.k_factor = k_factor;
+    int gw = 4;   // dedicated gather warps
+    if (const char* env = getenv("SOFAB200_FUSED_GATHER_WARPS")) gw = atoi(env);
+    if (ff.method == SOFAB200_TET_SMALL) return tet_fused_variant<R, TM_DF_SMALL, false, 256, 0>(ff, d, a, sync_capacity, dry_run, info);
+    if (sizeof(R) == 8) return tet_fused_variant<R, TM_DF_COROT, false, 256, 0>(ff, d, a, sync_capacity, dry_run, info);
+    if (ff.threads > 256) {
+        if (gw >= 4) return tet_fused_variant<R, TM_DF_COROT, true, 512, 128>(ff, d, a, sync_capacity, dry_run, info);
+        return tet_fused_variant<R, TM_DF_COROT, true, 512, 0>(ff, d, a, sync_capacity, dry_run, info);
+    }
+    return tet_fused_variant<R, TM_DF_COROT, true, 256, 0>(ff, d, a, sync_capacity, dry_run, info);
+}
+template int tet_cg_fused<float>(sofab200_tetfem*, float, FusedCG<float>, size_t, bool, int*);
+template int tet_cg_fused<double>(sofab200_tetfem*, double, FusedCG<double>, size_t, bool, int*);
+size_t tet_shared_slot_count(sofab200_tetfem* base) {
+    if (base->real == SOFAB200_F32) return size_t(static_cast<TetFF<float>*>(base)->h.plan.n_chunks) * kGatherChunk;
+    return size_t(static_cast<TetFF<double>*>(base)->h.plan.n_chunks) * kGatherChunk;
+}
 
 // Element pass + boundary gather with a caller-provided epilogue (also used by the solver node).
 template <class R> TileDev<R> tet_tiledev(sofab200_tetfem* base) { return static_cast<TetFF<R>*>(base)->dev().t; }

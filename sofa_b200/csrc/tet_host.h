@@ -195,7 +195,8 @@ template <class R> static std::string tet_host_build(HostTet<R>& ff, size_t n_no
         // the persistent CG kernel gives CTA b the tiles b and b + ceil(n_tiles / 2) (or just b when there are at most sm_count):
         // the tile it processes last lists its elements that feed shared nodes first (see build_plan)
         const int n_tiles_guess = std::max(1, int((n_tets + size_t(tile_e) - 1) / size_t(tile_e)));
-        const int reorder_from = n_tiles_guess <= sm_count ? 0 : (n_tiles_guess <= 2 * sm_count ? (n_tiles_guess + 1) / 2 : 0x7fffffff);
+        // (tile b + c * grid goes to CTA b: the last tile of every CTA is among the final `sm_count` tiles)
+        const int reorder_from = n_tiles_guess <= sm_count ? 0 : (n_tiles_guess <= 2 * sm_count ? (n_tiles_guess + 1) / 2 : n_tiles_guess - sm_count);
         const std::string err = build_plan(ff.plan, int(n_nodes), int(n_tets), 4, tets, pos.data(), tile_e, chunk, kStageFlag, smem_limit, sizeof(SV), 3 * sizeof(R), desc->shared_nodes,
                                            reorder_from);
         ff.smem_bytes = tile_smem_bytes<R>(ff.plan.max_touched, ff.plan.max_slots);

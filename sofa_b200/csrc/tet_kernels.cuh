@@ -7,7 +7,7 @@
 // Arithmetic follows the reference statement by statement (file:line cited per function); compiled with
 // -fmad=false so no multiply-add is contracted.
 #pragma once
-#include "cg_persist.cuh"
+#include "cg_fused.cuh"
 #include "math3.cuh"
 
 namespace sb {
@@ -241,12 +241,16 @@ template <class R, int MODE> HD void tet_element(const TetDev<R>& d, size_t es, 
 // arrive_slots (persistent CG kernel, the CTA's last tile): once the elements [0, arrive_at) are done -- the plan puts the elements
 // that feed shared nodes first -- the CTA arrives at the "staged contributions complete" grid barrier and goes on with the
 // rest of the tile; arrive_at is a multiple of blockDim.x with arrive_at + blockDim.x <= tile_e (every thread passes there).
-template <class R, int MODE, bool PF>
+// NTHR: number of threads that share the tile (0: the whole CTA); on_boundary: called by every one of them, at the same trip count, once the
+// elements [0, arrive_at) are done (arrive_at < 0: never).
+struct NoBoundaryCall { __device__ __forceinline__ void operator()() const {} };
+template <class R, int MODE, bool PF, int NTHR = 0, class OnBoundary = NoBoundaryCall>
 __device__ __forceinline__ void tet_tile_elements(const TetDev<R>& d, int tile, const typename SVec<R>::T* s_in, R* s_slot, int max_slots,
-                                                  unsigned long long* arrive_slots = nullptr, int arrive_at = 0) {
+                                                  int arrive_at = -1, OnBoundary on_boundary = OnBoundary()) {
     typedef typename SVec<R>::T SV;
     const TileDev<R>& t = d.t;
     const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    const int nthr = NTHR > 0 ? NTHR : int(blockDim.x);
     int le = threadIdx.x;
     uint2 lnw = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); uint4 sl = make_uint4(0, 0, 0, 0);
     TetRec<R> rec;
@@ -255,11 +259,9 @@ __device__ __forceinline__ void tet_tile_elements(const TetDev<R>& d, int tile, 
         lnw = idx_load(reinterpret_cast<const uint2*>(d.lnode + es), pol_stream); sl = idx_load(d.slot + es, pol_stream); rec = tet_load_rec(d, es, pol_stream);
     }
     while (le < t.tile_e) {
-#ifdef __CUDA_ARCH__
-        if (arrive_slots && le - int(threadIdx.x) == arrive_at) grid_arrive(arrive_slots, 0u, blockDim.x - 32u);   // the last warp has the shortest tail of the tile
-#endif
+        if (le - int(threadIdx.x) == arrive_at) on_boundary();
         const size_t es = size_t(tile) * t.tile_e + le;
-        const int nle = le + blockDim.x;
+        const int nle = le + nthr;
         uint2 n_lnw = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); uint4 n_sl = make_uint4(0, 0, 0, 0);
         TetRec<R> n_rec;
         if (PF && nle < t.tile_e) {
@@ -364,7 +366,8 @@ __global__ void __launch_bounds__(MAXT) tet_cg_persistent_kernel(TetDev<R> d, Pe
                 const int nb_up = (int(t.tile_nb[tile]) + int(blockDim.x) - 1) / int(blockDim.x) * int(blockDim.x);
                 if (nb_up + int(blockDim.x) <= t.tile_e) arrive_at = nb_up;
             }
-            tet_tile_elements<R, MODE, PF>(d, tile, s_in + c * L.max_touched, s_slot, L.max_slots, arrive_at >= 0 ? a.sync : nullptr, arrive_at);
+            tet_tile_elements<R, MODE, PF>(d, tile, s_in + c * L.max_touched, s_slot, L.max_slots, arrive_at,
+                                           [&]() { grid_arrive(a.sync, 0u, blockDim.x - 32u); });   // the last warp has the shortest tail of the tile
             if (arrive_at >= 0) arrived = true;
             __syncthreads();
             if (c == 0) trace_mark(a.ep.trace, kTraceTail, 13);
@@ -377,6 +380,16 @@ __global__ void __launch_bounds__(MAXT) tet_cg_persistent_kernel(TetDev<R> d, Pe
     persist_finish<R>(t, a, st, smem_raw, s_grec);
     trace_mark(a.ep.trace, kTraceTail, 11);
 }
+
+// element policy of the fused CG kernel (cg_fused.cuh)
+template <class R, int MODE, bool PF> struct TetPass {
+    typedef TetDev<R> Dev;
+    static __device__ __forceinline__ const TileDev<R>& tiles(const Dev& d) { return d.t; }
+    template <int ET, class OnBoundary>
+    static __device__ __forceinline__ void elements(const Dev& d, int tile, const typename SVec<R>::T* s_in, R* s_slot, int max_slots, unsigned char*, int arrive_at, OnBoundary f) {
+        tet_tile_elements<R, MODE, PF, ET>(d, tile, s_in, s_slot, max_slots, arrive_at, f);
+    }
+};
 
 // rotations[e] back in ORIGINAL element order (getRotations-style accessors, parity checks)
 template <class R> __global__ void tet_export_rotations_kernel(TetDev<R> d, const uint32_t* __restrict__ orig, R* __restrict__ out) {

@@ -445,7 +445,12 @@ def test_node_compute_force_and_apply_bit_exact(dtype, method):
 
 # the three device implementations of CGLinearSolver::solve (node.cu: Node::cg_solve): ONE persistent cooperative kernel; element
 # pass + cooperative tail kernel per iteration; four plain kernels per iteration (the latter two serve meshes the first cannot hold)
-CG_PATHS = {"persistent": {}, "fused_tail": {"SOFAB200_CG_PERSISTENT": "0"}, "multi_kernel": {"SOFAB200_CG_PERSISTENT": "0", "SOFAB200_FUSED_TAIL": "0"}}
+# "fused" (default, cg_fused.cuh): ONE reduction per iteration -- alpha from the measured rho, beta from the one-step prediction
+# rho' = rho - 2 alpha r.q + alpha^2 q.q -- so its scalars are not bit-equal to a classical CG's; in Vec3f it stays closer to the
+# double-dot oracle than the reference's own serial-float dots do (tests/test_cg_fused_recurrence.py measures both).
+CG_PATHS = {"fused": {}, "fused_all_warps": {"SOFAB200_FUSED_GATHER_WARPS": "0"}, "fused_streamed": {"SOFAB200_FUSED_CACHED_KB": "0"},
+            "persistent_v1": {"SOFAB200_CG_FUSED": "0"}, "fused_tail": {"SOFAB200_CG_PERSISTENT": "0"},
+            "multi_kernel": {"SOFAB200_CG_PERSISTENT": "0", "SOFAB200_FUSED_TAIL": "0"}}
 
 
 @pytest.mark.parametrize("path", list(CG_PATHS))
@@ -474,9 +479,13 @@ def test_cg_solve_matches_oracle(dtype, path, monkeypatch):
             ge_ref = s.graph("Error")
             nmin = min(len(ge_ref), len(info["graph_error"]), 26 if not dd else 10 ** 6)
             rtol = 1e-7 if (dd or dtype == np.float64) else 2e-3
+            sol_tol = 1e-8 if (dd or dtype == np.float64) else 2e-3
+            if path.startswith("fused") and path != "fused_tail" and dtype == np.float32 and dd:
+                # (Vec3f: the predicted rho enters beta at ~1e-7 relative; near the Vec3f floor the residual histories of ANY two float CGs part)
+                rtol, sol_tol, nmin = 5e-6, 5e-6, min(nmin, 26)
             assert np.allclose(info["graph_error"][:nmin], ge_ref[:nmin], rtol=rtol, atol=1e-14), dd
             if it == it_ref:
-                assert rel_err(sol_d.cpu().numpy(), sol_ref) <= (1e-8 if (dd or dtype == np.float64) else 2e-3)
+                assert rel_err(sol_d.cpu().numpy(), sol_ref) <= sol_tol
                 assert info["end_condition"] == s.end_condition
     # b == 0: the reference returns at once with x = 0 (CGLinearSolver.inl:141-152)
     node.set_params(iterations=25, tolerance=1e-9, threshold=1e-9)

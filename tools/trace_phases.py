@@ -59,7 +59,22 @@ if s:
     # second CTA on the same SM (wave 2) starts when the first ends
     order = np.argsort(rel[:, 0])
     res["element_pass"]["first_wave_end_median"] = round(float(np.median(rel[order[:len(order) // 2], 4])), 2)
-s = summarize(tail, ["iter_start", "tiles_done", "barrier1", "shared_done", "barrier2", "xr_done", "barrier3"])
+fused = os.environ.get("SOFAB200_CG_FUSED", "1") != "0"
+if fused:
+    # second-generation kernel (cg_fused.cuh): marks of the 10th iteration of the solve (mark 12: start of the 11th)
+    tl = tail[tail[:, 0] > 0].astype(np.int64)
+    us = lambda a, b: round(float(np.median(tl[:, b] - tl[:, a])) / 1000.0, 2)
+    mx = lambda a, b: round(float(np.max(tl[:, b] - tl[:, a])) / 1000.0, 2)
+    res["cg_fused_last_iteration_us"] = {
+        "first tile: elements": us(0, 1), "first tile: interior sums": us(1, 2), "remaining tiles (elements + interior sums)": us(2, 3),
+        "iteration start -> S1 seen by the gather poller": us(0, 4), "S1 seen -> all units done (CTA barrier)": us(4, 5),
+        "element warps done -> all units done": us(3, 5), "S2 (post, wait, sum)": us(5, 6),
+        "iteration start -> S2 done (median / max CTA)": [us(0, 6), mx(0, 6)],
+        "S2 done -> update done": us(6, 13), "whole iteration (start -> next start), median / max CTA": [us(0, 12), mx(0, 12)]}
+    res["cg_fused_kernel_us"] = {"tables": us(8, 9), "kernel start -> end (median CTA)": us(8, 11), "last S2 -> end (update, x write-back)": us(6, 11)}
+    s = None
+else:
+    s = summarize(tail, ["iter_start", "tiles_done", "barrier1", "shared_done", "barrier2", "xr_done", "barrier3"])
 if s:
     res["cg_persistent_last_iteration"] = s[0]      # the persistent CG kernel (the multi-kernel tail uses other marks)
     tl = tail[tail[:, 0] > 0].astype(np.int64)
