@@ -97,6 +97,7 @@ template <class R> struct FusedScal {
     unsigned iter;                  // iterations started in this launch (sequence number of S1 / S2)
     unsigned vsync;                 // value syncs done (S2 and the prologue's)
     int failed;
+    int n_err, n_den;               // entries of CGDev::graph_error / graph_den so far (the lead thread records with plain stores, no read-modify-write)
 };
 
 template <class R> struct FusedAcc { double rr, pq, rq, qq; };
@@ -108,6 +109,7 @@ template <class R> __device__ __forceinline__ void acc_node(FusedAcc<R>& a, R r0
 }
 // fixed-order warp sum of the four accumulators (result in lane 0)
 template <class R> __device__ __forceinline__ void acc_warp_sum(FusedAcc<R>& a) {
+    __syncwarp();   // reconverge first: after a loop whose trip count differs between lanes the shuffles would take the per-shuffle WARPSYNC slow path (measured: 4.6 us for a 4 x 5 double tree)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         a.rr += __shfl_down_sync(0xffffffffu, a.rr, o); a.pq += __shfl_down_sync(0xffffffffu, a.pq, o);
@@ -123,13 +125,13 @@ template <class R> struct TileState {
     SV* P; R* Q; const NodeRec<R>* nrec; const uint32_t* tidx; const uint16_t* jds;
     uint32_t node_off; int n_touched, n_int;
 };
-template <class R> __device__ __forceinline__ TileState<R> tile_state(const TileDev<R>& t, const FusedCG<R>& a, unsigned char* smem_raw, int c, int tile) {
+template <class R, bool CACHED> __device__ __forceinline__ TileState<R> tile_state(const TileDev<R>& t, const FusedCG<R>& a, unsigned char* smem_raw, int c, int tile) {
     typedef typename SVec<R>::T SV;
     const FusedLayout& L = a.lay;
     TileState<R> s;
     s.node_off = t.tile_node_off[tile];
     s.n_touched = int(t.tile_node_off[tile + 1] - s.node_off); s.n_int = int(t.tile_nint[tile]);
-    if (L.cached) {
+    if constexpr (CACHED) {     // (compile-time: the pointers keep their shared-memory address space => LDS/STS, not generic accesses)
         s.P = reinterpret_cast<SV*>(smem_raw) + c * L.max_touched;
         s.Q = reinterpret_cast<R*>(smem_raw + L.off_q) + 3 * size_t(c * L.max_int);
         s.nrec = reinterpret_cast<const NodeRec<R>*>(smem_raw + L.off_nrec) + c * L.max_int;
@@ -146,37 +148,50 @@ template <class R> __device__ __forceinline__ TileState<R> tile_state(const Tile
 // ---- grid-wide sync that also sums kFusedDots doubles per CTA ------------------------------------------------------------------------
 // arrival: `v` (lane 0 of warp 0 holds the CTA's four sums) is posted, everything the CTA wrote before is released.  Must be called by
 // warp 0 after a CTA-wide barrier.
+// Wait until *counter >= target; every lane of the calling warp runs the loop (uniform control flow), ~4 s time-out.
+__device__ __forceinline__ bool poll_counter_warp(const unsigned* counter, unsigned target) {
+    const long long t0 = poll_clock();
+    bool ok = true;
+    for (;;) {
+        if (ld_acquire_u32(counter) >= target) break;
+        if (poll_clock() - t0 > kSyncTimeoutCycles) { ok = false; break; }
+    }
+    return ok;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void fused_arrive_values(unsigned long long* sync, unsigned vs, const double v[kFusedDots]) {
     const unsigned G = gridDim.x;
-    double* cur = reinterpret_cast<double*>(sync) + (size_t(vs % 3) * G + blockIdx.x) * kFusedDots;
+    double2* cur = reinterpret_cast<double2*>(reinterpret_cast<double*>(sync) + (size_t(vs % 3) * G + blockIdx.x) * kFusedDots);
     unsigned* counter = reinterpret_cast<unsigned*>(sync + size_t(3) * G * kFusedDots + 32);
     if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < kFusedDots; ++i) cur[i] = v[i];
-        __threadfence();
-        atomicAdd(counter, 1u);
+        __stcg(cur, make_double2(v[0], v[1])); __stcg(cur + 1, make_double2(v[2], v[3]));
+        red_release_gpu_add(counter, 1u);        // release: the CTA's writes (ordered before this thread by the CTA barrier) and the values above
     }
 }
-// wait (warp 0) + fixed-order sum over the CTAs; the totals are left in out[] (shared memory) for the CTA-wide barrier that follows
+// wait (warp 0) + fixed-order sum over the CTAs; the totals are left in out[] (shared memory) for the CTA-wide barrier that follows.
+// The values of up to 160 CTAs are requested at once (one L2 round trip), then added in a fixed order.
 __device__ __forceinline__ bool fused_wait_values(unsigned long long* sync, unsigned vs, double* out /* smem [kFusedDots] */) {
     const unsigned G = gridDim.x;
-    const double* cur = reinterpret_cast<const double*>(sync) + size_t(vs % 3) * G * kFusedDots;
+    const double2* cur = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(sync) + size_t(vs % 3) * G * kFusedDots);
     const unsigned* counter = reinterpret_cast<const unsigned*>(sync + size_t(3) * G * kFusedDots + 32);
-    bool ok = true;
-    if (threadIdx.x == 0) {
-        const unsigned target = (vs + 1) * G;
-        const unsigned long long t0 = globaltimer_ns();
-        while (ld_acquire_u32(counter) < target) { if (globaltimer_ns() - t0 > kSyncTimeoutNs) { ok = false; break; } }
-    }
-    ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
-    __syncwarp();
+    // (all 32 lanes poll together -- one transaction per trip, the same value for every lane: a loop run by lane 0 alone leaves that lane
+    // split from its warp for good on this compiler, and every later shuffle of the warp then takes the WARPSYNC slow path)
+    const bool ok = poll_counter_warp(counter, (vs + 1) * G);
     double v[kFusedDots];
 #pragma unroll
     for (int i = 0; i < kFusedDots; ++i) v[i] = 0.0;
-    for (unsigned c = threadIdx.x; c < G; c += 32) {
+    for (unsigned c0 = 0; c0 < G; c0 += 160u) {
+        double2 lo[5], hi[5];
 #pragma unroll
-        for (int i = 0; i < kFusedDots; ++i) v[i] += __ldcg(cur + size_t(c) * kFusedDots + i);
+        for (int u = 0; u < 5; ++u) {
+            const unsigned c = c0 + threadIdx.x + 32u * u;
+            lo[u] = make_double2(0.0, 0.0); hi[u] = lo[u];
+            if (c < G) { lo[u] = __ldcg(cur + 2 * size_t(c)); hi[u] = __ldcg(cur + 2 * size_t(c) + 1); }
+        }
+#pragma unroll
+        for (int u = 0; u < 5; ++u) { v[0] += lo[u].x; v[1] += lo[u].y; v[2] += hi[u].x; v[3] += hi[u].y; }
     }
+    __syncwarp();
 #pragma unroll
     for (int i = 0; i < kFusedDots; ++i) {
 #pragma unroll
@@ -188,22 +203,19 @@ __device__ __forceinline__ bool fused_wait_values(unsigned long long* sync, unsi
     }
     return ok;
 }
-// S1: "this CTA's staged contributions are complete" -- arrival only (the waiters are the gather threads)
+// S1: "this CTA's staged contributions are complete" -- arrival only (the waiters are the threads that sum shared nodes)
 __device__ __forceinline__ void fused_arrive_s1(unsigned long long* sync) {
     unsigned* counter = reinterpret_cast<unsigned*>(sync + size_t(3) * gridDim.x * kFusedDots);
-    __threadfence();
-    atomicAdd(counter, 1u);
+    red_release_gpu_add(counter, 1u);
 }
+// (called by all 32 lanes of one warp)
 __device__ __forceinline__ bool fused_poll_s1(const unsigned long long* sync, unsigned iter) {
     const unsigned* counter = reinterpret_cast<const unsigned*>(sync + size_t(3) * gridDim.x * kFusedDots);
-    const unsigned target = (iter + 1) * gridDim.x;
-    const unsigned long long t0 = globaltimer_ns();
-    while (ld_acquire_u32(counter) < target) { if (globaltimer_ns() - t0 > kSyncTimeoutNs) return false; }
-    return true;
+    return poll_counter_warp(counter, (iter + 1) * gridDim.x);
 }
 
 // ---- once per solve: static tables ------------------------------------------------------------------------------------------------
-template <class R, int NT> __device__ __forceinline__ void fused_load_tables(const TileDev<R>& t, const FusedCG<R>& a, unsigned char* smem_raw) {
+template <class R, int NT, bool CACHED> __device__ __forceinline__ void fused_load_tables(const TileDev<R>& t, const FusedCG<R>& a, unsigned char* smem_raw) {
     const FusedLayout& L = a.lay;
     const NodeEpilogue<R>& ep = a.ep;
     const int G = int(gridDim.x);
@@ -212,14 +224,14 @@ template <class R, int NT> __device__ __forceinline__ void fused_load_tables(con
         if (tile >= t.n_tiles) break;
         const uint32_t node_off = t.tile_node_off[tile];
         const int n_touched = int(t.tile_node_off[tile + 1] - node_off), n_int = int(t.tile_nint[tile]);
-        NodeRec<R>* nrec = L.cached ? reinterpret_cast<NodeRec<R>*>(smem_raw + L.off_nrec) + c * L.max_int : a.gNrec + node_off;
+        NodeRec<R>* nrec = CACHED ? reinterpret_cast<NodeRec<R>*>(smem_raw + L.off_nrec) + c * L.max_int : a.gNrec + node_off;
         for (int k = threadIdx.x; k < n_touched; k += NT) {
             if (k < n_int) {
                 const uint32_t g = t.tile_nodes[node_off + k];
                 nrec[k] = NodeRec<R>{g, unsigned(t.tile_val[node_off + k]) | ((ep.fixed && ep.fixed[g]) ? 0x10000u : 0u), ep.mass ? ep.mass[g] : R(0)};
-            } else if (L.cached) reinterpret_cast<uint32_t*>(smem_raw + L.off_tidx)[c * L.max_shtouch + (k - n_int)] = t.tile_shslot[node_off + k];
+            } else if (CACHED) reinterpret_cast<uint32_t*>(smem_raw + L.off_tidx)[c * L.max_shtouch + (k - n_int)] = t.tile_shslot[node_off + k];
         }
-        if (L.cached)
+        if (CACHED)
             for (int j = threadIdx.x; j <= t.maxval; j += NT) reinterpret_cast<uint16_t*>(smem_raw + L.off_jds)[c * (L.maxval + 1) + j] = t.tile_jds[size_t(tile) * (t.maxval + 1) + j];
     }
     // the shared nodes of this CTA's units
@@ -238,7 +250,7 @@ template <class R, int NT> __device__ __forceinline__ void fused_load_tables(con
 }
 
 // ---- start of the solve: |b|, rho_0 = r.r (CGLinearSolver.inl:130-180) and the initial state p = r of every copy --------------------
-template <class R, int NT> __device__ __forceinline__ bool fused_init(const TileDev<R>& t, const FusedCG<R>& a, FusedScal<R>* sc, unsigned char* smem_raw, double* s_wpart, double* s_tot) {
+template <class R, int NT, bool CACHED> __device__ __forceinline__ bool fused_init(const TileDev<R>& t, const FusedCG<R>& a, FusedScal<R>* sc, unsigned char* smem_raw, double* s_wpart, double* s_tot) {
     typedef typename SVec<R>::T SV;
     const FusedLayout& L = a.lay;
     const PeerDev<R>& P = a.peer;
@@ -252,6 +264,7 @@ template <class R, int NT> __device__ __forceinline__ bool fused_init(const Tile
         sb += double(b0) * double(b0) + double(b1) * double(b1) + double(b2) * double(b2);
         sr += double(r0) * double(r0) + double(r1) * double(r1) + double(r2) * double(r2);
     }
+    __syncwarp();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { sb += __shfl_down_sync(0xffffffffu, sb, o); sr += __shfl_down_sync(0xffffffffu, sr, o); }
     if ((threadIdx.x & 31) == 0) { s_wpart[(threadIdx.x >> 5) * kFusedDots] = sb; s_wpart[(threadIdx.x >> 5) * kFusedDots + 1] = sr; }
@@ -259,7 +272,7 @@ template <class R, int NT> __device__ __forceinline__ bool fused_init(const Tile
     for (int c = 0; c < L.tiles_per_cta; ++c) {
         const int tile = blockIdx.x + c * G;
         if (tile >= t.n_tiles) break;
-        const TileState<R> s = tile_state<R>(t, a, smem_raw, c, tile);
+        const TileState<R> s = tile_state<R, CACHED>(t, a, smem_raw, c, tile);
         for (int k = threadIdx.x; k < s.n_touched; k += NT) {
             const size_t g = t.tile_nodes[s.node_off + k];
             const SV rv = SVec<R>::make(a.r[3 * g], a.r[3 * g + 1], a.r[3 * g + 2]);
@@ -284,6 +297,7 @@ template <class R, int NT> __device__ __forceinline__ bool fused_init(const Tile
     if (threadIdx.x < 32) {
         double v[kFusedDots] = {0.0, 0.0, 0.0, 0.0};
         for (int w = threadIdx.x; w < NT / 32; w += 32) { v[0] += s_wpart[w * kFusedDots]; v[1] += s_wpart[w * kFusedDots + 1]; }
+        __syncwarp();
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { v[0] += __shfl_down_sync(0xffffffffu, v[0], o); v[1] += __shfl_down_sync(0xffffffffu, v[1], o); }
         fused_arrive_values(a.sync, 0u, v);
@@ -297,6 +311,7 @@ template <class R, int NT> __device__ __forceinline__ bool fused_init(const Tile
         sc->normb = sqrt(nb2); sc->rho = rho0; sc->it = 1;
         sc->tol = cg->tolerance; sc->thr = cg->threshold; sc->tsc = cg->time_step_count; sc->max_iter = cg->max_iter;
         sc->alpha = R(0); sc->malpha = R(0); sc->beta = R(0); sc->a_one = 0; sc->ma_one = 0;
+        sc->n_err = 2; sc->n_den = 0;       // (cg_begin_kernel: one entry; cg_after_rho(rho0) below: the second)
     }
     __syncthreads();
     if (sc->failed) { if (lead) { cg->done = 1; cg->end_cond = 99; } return false; }
@@ -350,41 +365,49 @@ template <class R, int ET> __device__ __forceinline__ void fused_interior(const 
 // ---- one unit of 32 shared nodes (one warp, lane = node) ---------------------------------------------------------------------------------
 // Applies the pending update of the previous iteration, sums the staged contributions in element order, publishes r and q for the tiles.
 template <class R> struct GatherBatch;
-template <> struct GatherBatch<float> { static constexpr int N = 8; };
+template <> struct GatherBatch<float> { static constexpr int N = 6; };
 template <> struct GatherBatch<double> { static constexpr int N = 4; };
-template <class R> __device__ __forceinline__ void fused_unit(const TileDev<R>& t, const FusedCG<R>& a, const FusedScal<R>* sc, int unit, double* upart /* smem [kFusedDots] */) {
+// what a unit needs that does not depend on S1: requested before the wait, so its L2 latency hides behind it
+template <class R> struct UnitPre { GRec<R> rec; typename SVec<R>::T pv, rv, xv, qo; };
+template <class R> __device__ __forceinline__ void fused_unit_preload(const FusedCG<R>& a, const FusedScal<R>* sc, int unit, UnitPre<R>& u) {
+    const size_t slot = size_t(unit) * kUnit + (threadIdx.x & 31);
+    u.rec = a.shrec[slot];
+    u.pv = sv_ldcg(a.pS + slot); u.rv = sv_ldcg(a.rS + slot);
+    if (!sc->first) { u.xv = sv_ldcg(a.xS + slot); u.qo = sv_ldcg(a.qS + slot); }
+    else { u.xv = u.pv; u.qo = u.pv; }
+}
+template <class R> __device__ __forceinline__ void fused_unit(const TileDev<R>& t, const FusedCG<R>& a, const FusedScal<R>* sc, int unit, const UnitPre<R>& pre, double* upart /* smem [kFusedDots] */) {
     typedef typename SVec<R>::T SV;
     constexpr int B = GatherBatch<R>::N;
     const NodeEpilogue<R>& ep = a.ep;
     const int lane = threadIdx.x & 31;
     const size_t slot = size_t(unit) * kUnit + lane;
     FusedAcc<R> acc{0.0, 0.0, 0.0, 0.0};
-    const GRec<R> rec = a.shrec[slot];
+    const GRec<R> rec = pre.rec;
     if (rec.g != 0xFFFFFFFFu) {
         const int val = int(rec.val_fixed & 0xFFFFu);
         const Quad<R>* stg = t.stage + rec.base;
         const uint64_t pol = l2_policy_evict_first();
         const Quad<R> zero{R(0), R(0), R(0), R(0)};
-        Quad<R> b0[B], b1[B];
-#pragma unroll
-        for (int u = 0; u < B; ++u) b0[u] = u < val ? stage_load(stg + size_t(u) * kGatherChunk, pol) : zero;
-#pragma unroll
-        for (int u = 0; u < B; ++u) b1[u] = B + u < val ? stage_load(stg + size_t(B + u) * kGatherChunk, pol) : zero;
-        SV pv = sv_ldcg(a.pS + slot), rv = sv_ldcg(a.rS + slot);
-        R p0 = R(pv.x), p1 = R(pv.y), p2 = R(pv.z), r0 = R(rv.x), r1 = R(rv.y), r2 = R(rv.z);
+        R p0 = R(pre.pv.x), p1 = R(pre.pv.y), p2 = R(pre.pv.z), r0 = R(pre.rv.x), r1 = R(pre.rv.y), r2 = R(pre.rv.z);
         if (!sc->first) {
-            // x += alpha p ; r -= alpha q ; p = p beta + r   of the previous iteration (cgstep_alpha, cgstep_beta)
-            const SV xv = sv_ldcg(a.xS + slot), qo = sv_ldcg(a.qS + slot);
-            R x0 = R(xv.x), x1 = R(xv.y), x2 = R(xv.z);
+            // x += alpha p ; r -= alpha q ; p = p beta + r   of the previous iteration (cgstep_alpha, cgstep_beta).  A dozen ALU operations on
+            // preloaded values: done before the staged contributions are requested so that x and the old q leave the registers first.
+            R x0 = R(pre.xv.x), x1 = R(pre.xv.y), x2 = R(pre.xv.z);
             const R alpha = sc->alpha, malpha = sc->malpha, beta = sc->beta;
             const bool a_one = sc->a_one != 0, ma_one = sc->ma_one != 0;
             x_one<R>(x0, p0, alpha, a_one); x_one<R>(x1, p1, alpha, a_one); x_one<R>(x2, p2, alpha, a_one);
-            r_one<R>(r0, R(qo.x), malpha, ma_one); r_one<R>(r1, R(qo.y), malpha, ma_one); r_one<R>(r2, R(qo.z), malpha, ma_one);
+            r_one<R>(r0, R(pre.qo.x), malpha, ma_one); r_one<R>(r1, R(pre.qo.y), malpha, ma_one); r_one<R>(r2, R(pre.qo.z), malpha, ma_one);
             p0 = p_update<R>(p0, beta, r0); p1 = p_update<R>(p1, beta, r1); p2 = p_update<R>(p2, beta, r2);
             stcg_sv(a.xS + slot, SVec<R>::make(x0, x1, x2));
             stcg_sv(a.rS + slot, SVec<R>::make(r0, r1, r2));
             stcg_sv(a.pS + slot, SVec<R>::make(p0, p1, p2));
         }
+        Quad<R> b0[B], b1[B];
+#pragma unroll
+        for (int u = 0; u < B; ++u) b0[u] = u < val ? stage_load(stg + size_t(u) * kGatherChunk, pol) : zero;
+#pragma unroll
+        for (int u = 0; u < B; ++u) b1[u] = B + u < val ? stage_load(stg + size_t(B + u) * kGatherChunk, pol) : zero;
         R q0 = R(0), q1 = R(0), q2 = R(0);
         node_mass_m(ep, ep.pre_kind, rec.mass, p0, p1, p2, q0, q1, q2);
         const bool plus = ep.sign > 0;
@@ -404,7 +427,7 @@ template <class R> __device__ __forceinline__ void fused_unit(const TileDev<R>& 
         }
         node_finish_m(ep, rec.g, rec.mass, (rec.val_fixed & 0x10000u) != 0, p0, p1, p2, q0, q1, q2);
         stcg_sv(a.qS + slot, SVec<R>::make(q0, q1, q2));
-        acc_node<R>(acc, r0, r1, r2, p0, p1, p2, q0, q1, q2);
+        if (!a.peer.enabled || a.peer.owned[rec.g]) acc_node<R>(acc, r0, r1, r2, p0, p1, p2, q0, q1, q2);
     }
     acc_warp_sum<R>(acc);
     if (lane == 0) { upart[0] = acc.rr; upart[1] = acc.pq; upart[2] = acc.rq; upart[3] = acc.qq; }
@@ -412,44 +435,50 @@ template <class R> __device__ __forceinline__ void fused_unit(const TileDev<R>& 
 
 // ---- after S2: x, r, p of every node the CTA's tiles touch ----------------------------------------------------------------------------------
 // with_p = false: the last iteration of the solve (only x matters; r is updated too so that the vector the caller sees is consistent)
-template <class R, int NT> __device__ __forceinline__ void fused_update(const TileDev<R>& t, const FusedCG<R>& a, const FusedScal<R>* sc, unsigned char* smem_raw, bool with_p) {
+template <class R, int NT, bool CACHED> __device__ __forceinline__ void fused_update(const TileDev<R>& t, const FusedCG<R>& a, const FusedScal<R>* sc, unsigned char* smem_raw, bool with_p) {
     typedef typename SVec<R>::T SV;
     const FusedLayout& L = a.lay;
     const int G = int(gridDim.x);
     const R alpha = sc->alpha, malpha = sc->malpha, beta = sc->beta;
     const bool a_one = sc->a_one != 0, ma_one = sc->ma_one != 0;
-    for (int c = 0; c < L.tiles_per_cta; ++c) {
-        const int tile = blockIdx.x + c * G;
-        if (tile >= t.n_tiles) break;
-        const TileState<R> s = tile_state<R>(t, a, smem_raw, c, tile);
-        constexpr int U = 2;        // rounds whose L2 requests are all issued before the first use
-        for (int k0 = threadIdx.x; k0 < s.n_touched; k0 += U * NT) {
-            SV va[U], vb[U];        // interior: x, r (private arrays) ; shared: r, q (the owner's published values)
+    constexpr int U = 2;            // rounds per tile whose L2 requests are all issued before the first use
+    // interior: x, r (private arrays) ; shared: r, q (the owner's published values)
+    auto request = [&](const TileState<R>& s, int k, SV& va, SV& vb) {
+        if (k < s.n_int) { va = sv_ldcg(a.xt + s.node_off + k); vb = sv_ldcg(a.rt + s.node_off + k); }
+        else if (k < s.n_touched) { const size_t slot = s.tidx[k - s.n_int]; va = sv_ldcg(a.rS + slot); vb = sv_ldcg(a.qS + slot); }
+    };
+    auto apply = [&](const TileState<R>& s, int k, const SV& va, const SV& vb) {
+        if (k >= s.n_touched) return;
+        const SV pv = s.P[k];
+        R p0 = R(pv.x), p1 = R(pv.y), p2 = R(pv.z), r0, r1, r2;
+        if (k < s.n_int) {
+            R x0 = R(va.x), x1 = R(va.y), x2 = R(va.z);
+            r0 = R(vb.x); r1 = R(vb.y); r2 = R(vb.z);
+            x_one<R>(x0, p0, alpha, a_one); x_one<R>(x1, p1, alpha, a_one); x_one<R>(x2, p2, alpha, a_one);
+            r_one<R>(r0, s.Q[3 * k], malpha, ma_one); r_one<R>(r1, s.Q[3 * k + 1], malpha, ma_one); r_one<R>(r2, s.Q[3 * k + 2], malpha, ma_one);
+            stcg_sv(a.xt + s.node_off + k, SVec<R>::make(x0, x1, x2));
+            stcg_sv(a.rt + s.node_off + k, SVec<R>::make(r0, r1, r2));
+        } else {
+            r0 = R(va.x); r1 = R(va.y); r2 = R(va.z);
+            r_one<R>(r0, R(vb.x), malpha, ma_one); r_one<R>(r1, R(vb.y), malpha, ma_one); r_one<R>(r2, R(vb.z), malpha, ma_one);
+        }
+        if (with_p) s.P[k] = SVec<R>::make(p_update<R>(p0, beta, r0), p_update<R>(p1, beta, r1), p_update<R>(p2, beta, r2));
+    };
+    // two tiles at a time: the requests of both are in flight together (one L2 round trip for a CTA with two ~900-node tiles)
+    for (int c = 0; c < L.tiles_per_cta; c += 2) {
+        const int tile0 = blockIdx.x + c * G, tile1 = tile0 + G;
+        if (tile0 >= t.n_tiles) break;
+        const bool two = c + 1 < L.tiles_per_cta && tile1 < t.n_tiles;
+        const TileState<R> s0 = tile_state<R, CACHED>(t, a, smem_raw, c, tile0);
+        TileState<R> s1 = s0;
+        if (two) s1 = tile_state<R, CACHED>(t, a, smem_raw, c + 1, tile1); else s1.n_touched = 0;
+        const int nmax = max(s0.n_touched, s1.n_touched);
+        for (int k0 = threadIdx.x; k0 < nmax; k0 += U * NT) {
+            SV va0[U], vb0[U], va1[U], vb1[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int k = k0 + u * NT;
-                if (k < s.n_int) { va[u] = sv_ldcg(a.xt + s.node_off + k); vb[u] = sv_ldcg(a.rt + s.node_off + k); }
-                else if (k < s.n_touched) { const size_t slot = s.tidx[k - s.n_int]; va[u] = sv_ldcg(a.rS + slot); vb[u] = sv_ldcg(a.qS + slot); }
-            }
+            for (int u = 0; u < U; ++u) { request(s0, k0 + u * NT, va0[u], vb0[u]); request(s1, k0 + u * NT, va1[u], vb1[u]); }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int k = k0 + u * NT;
-                if (k >= s.n_touched) continue;
-                const SV pv = s.P[k];
-                R p0 = R(pv.x), p1 = R(pv.y), p2 = R(pv.z), r0, r1, r2;
-                if (k < s.n_int) {
-                    R x0 = R(va[u].x), x1 = R(va[u].y), x2 = R(va[u].z);
-                    r0 = R(vb[u].x); r1 = R(vb[u].y); r2 = R(vb[u].z);
-                    x_one<R>(x0, p0, alpha, a_one); x_one<R>(x1, p1, alpha, a_one); x_one<R>(x2, p2, alpha, a_one);
-                    r_one<R>(r0, s.Q[3 * k], malpha, ma_one); r_one<R>(r1, s.Q[3 * k + 1], malpha, ma_one); r_one<R>(r2, s.Q[3 * k + 2], malpha, ma_one);
-                    stcg_sv(a.xt + s.node_off + k, SVec<R>::make(x0, x1, x2));
-                    stcg_sv(a.rt + s.node_off + k, SVec<R>::make(r0, r1, r2));
-                } else {
-                    r0 = R(va[u].x); r1 = R(va[u].y); r2 = R(va[u].z);
-                    r_one<R>(r0, R(vb[u].x), malpha, ma_one); r_one<R>(r1, R(vb[u].y), malpha, ma_one); r_one<R>(r2, R(vb[u].z), malpha, ma_one);
-                }
-                if (with_p) s.P[k] = SVec<R>::make(p_update<R>(p0, beta, r0), p_update<R>(p1, beta, r1), p_update<R>(p2, beta, r2));
-            }
+            for (int u = 0; u < U; ++u) { apply(s0, k0 + u * NT, va0[u], vb0[u]); apply(s1, k0 + u * NT, va1[u], vb1[u]); }
         }
     }
 }
@@ -497,17 +526,18 @@ template <class R, int NT> __device__ __forceinline__ void fused_finish(const Ti
 //   template <int ET, class OnBoundary> static void elements(const Dev&, int tile, const SV* s_in, R* s_slot, int max_slots, unsigned char* s_extra, int arrive_at, OnBoundary f)
 //       one pass over the tile's elements by the ET element threads; calls f() once (from every element thread, at the same trip count) when
 //       the elements [0, arrive_at) are done (arrive_at < 0: never).
-// ET element threads + GT dedicated gather threads (GT may be 0: everybody does everything).
+// ET element threads + GT dedicated gather threads (GT may be 0: everybody does everything).  The CTA's units of shared nodes are dealt
+// statically: the first `ded_units` to the dedicated warps, the others to the element warps (which take them once their tiles are done) --
+// a fixed assignment keeps every partial sum, hence every bit of the result, independent of timing.
 constexpr int kTrF = kTraceTail;     // trace records of the fused kernel: same area as the first-generation kernel's
-template <class R, class Pass, int ET, int GT>
-__global__ void __launch_bounds__(ET + GT, 1) fused_cg_kernel(typename Pass::Dev d, FusedCG<R> a) {
+template <class R, class Pass, int ET, int GT, bool CACHED>
+__global__ void __launch_bounds__(ET + GT, 1) fused_cg_kernel(typename Pass::Dev d, FusedCG<R> a, int ded_share_pct) {
     typedef typename SVec<R>::T SV;
     constexpr int NT = ET + GT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double s_wpart[(NT / 32) * kFusedDots];     // per element warp: running sums over the CTA's tiles
+    __shared__ double s_wpart[(NT / 32) * kFusedDots];     // per element warp: sums over the CTA's tiles
     __shared__ double s_tot[kFusedDots];
     __shared__ FusedScal<R> s_sc;
-    __shared__ unsigned s_flag1, s_next_unit;
     CGDev* cg = a.cg;
     if (cg->done) return;
     const TileDev<R>& t = Pass::tiles(d);
@@ -518,17 +548,20 @@ __global__ void __launch_bounds__(ET + GT, 1) fused_cg_kernel(typename Pass::Dev
     R* s_slot = reinterpret_cast<R*>(smem_raw + L.off_slot);
     double* s_upart = reinterpret_cast<double*>(smem_raw + L.off_upart);
     unsigned char* s_extra = smem_raw + L.off_extra;
-    if (threadIdx.x == 0) { s_flag1 = 0u; s_next_unit = 0u; }
     trace_mark(a.ep.trace, kTrF, 8);
-    fused_load_tables<R, NT>(t, a, smem_raw);
+    fused_load_tables<R, NT, CACHED>(t, a, smem_raw);
     __syncthreads();
     trace_mark(a.ep.trace, kTrF, 9);
     bool updated = false, pending = false;
-    if (fused_init<R, NT>(t, a, &s_sc, smem_raw, s_wpart, s_tot)) {
-        // units of this CTA: unit = lu * G + blockIdx.x
+    if (fused_init<R, NT, CACHED>(t, a, &s_sc, smem_raw, s_wpart, s_tot)) {
+        // units of this CTA: unit = lu * G + blockIdx.x, lu < n_my_units
         const int n_units_total = t.n_chunks * (kGatherChunk / kUnit);
         const int n_my_units = (n_units_total - int(blockIdx.x) + G - 1) / G;
+        const int ded_units = GT > 0 ? min(n_my_units, (n_my_units * ded_share_pct + 99) / 100) : 0;
         const bool elem_thread = threadIdx.x < ET;
+        const int warp = threadIdx.x >> 5;
+        // this warp's units: lu = lu0, lu0 + lu_step, ... < lu_end
+        const int lu0 = elem_thread ? ded_units + warp : (warp - ET / 32), lu_step = elem_thread ? ET / 32 : GT / 32, lu_end = elem_thread ? n_my_units : ded_units;
         for (;;) {
             const unsigned iter = s_sc.iter;
             // phase stamps of ONE iteration in the middle of the solve (the 10th of this launch; mark 12 = start of the 11th)
@@ -542,9 +575,9 @@ __global__ void __launch_bounds__(ET + GT, 1) fused_cg_kernel(typename Pass::Dev
                 for (int c = 0; c < L.tiles_per_cta; ++c) {
                     const int tile = blockIdx.x + c * G;
                     if (tile >= t.n_tiles) break;
-                    const TileState<R> s = tile_state<R>(t, a, smem_raw, c, tile);
+                    const TileState<R> s = tile_state<R, CACHED>(t, a, smem_raw, c, tile);
                     const SV* s_in = s.P;
-                    if (!L.cached) {
+                    if (!CACHED) {
                         for (int k = threadIdx.x; k < s.n_touched; k += ET) s_in0[k] = sv_ldcg(s.P + k);
                         uint16_t* jd = reinterpret_cast<uint16_t*>(smem_raw + L.off_jds);
                         for (int j = threadIdx.x; j <= t.maxval; j += ET) jd[j] = t.tile_jds[size_t(tile) * (t.maxval + 1) + j];
@@ -567,73 +600,90 @@ __global__ void __launch_bounds__(ET + GT, 1) fused_cg_kernel(typename Pass::Dev
                     if (last && !arrived) { if (threadIdx.x == ET - 32) fused_arrive_s1(a.sync); arrived = true; }
                     if (c == 0) trace_mark(tr, kTrF, 1);
                     TileState<R> s2 = s;
-                    if (!L.cached) s2.P = s_in0;        // (p of the tile's nodes is in shared memory right now)
+                    if (!CACHED) s2.P = s_in0;        // (p of the tile's nodes is in shared memory right now)
                     fused_interior<R, ET>(a, s2, s_slot, acc);
                     bar_first<ET>();                    // the slots are free for the next tile
                     if (c == 0) trace_mark(tr, kTrF, 2);
                 }
                 acc_warp_sum<R>(acc);
                 if ((threadIdx.x & 31) == 0) {
-                    double* w = s_wpart + (threadIdx.x >> 5) * kFusedDots;
+                    double* w = s_wpart + warp * kFusedDots;
                     w[0] = acc.rr; w[1] = acc.pq; w[2] = acc.rq; w[3] = acc.qq;
                 }
                 trace_mark(tr, kTrF, 3);
             }
-            // ---- shared nodes: wait for S1 (one poller per CTA), then take units until none is left
-            if (threadIdx.x == (GT > 0 ? ET : 0)) {
-                const bool ok = fused_poll_s1(a.sync, iter);
-                if (!ok) s_sc.failed = 1;
-                st_release_cta_shared(&s_flag1, iter + 1u);
+            // ---- shared nodes.  What the warp's first unit needs from the previous iteration is requested before the wait for S1.
+            UnitPre<R> pre;
+            if (lu0 < lu_end) fused_unit_preload<R>(a, &s_sc, lu0 * G + int(blockIdx.x), pre);
+            if (elem_thread) {
+                if (threadIdx.x < 32) { const bool ok = fused_poll_s1(a.sync, iter); if (!ok && threadIdx.x == 0) s_sc.failed = 1; }      // (normally complete long ago when GT > 0)
+                bar_first<ET>();
+                trace_mark(tr, kTrF, 4);
+            } else {
+                if (threadIdx.x < ET + 32) { const bool ok = fused_poll_s1(a.sync, iter); if (!ok && threadIdx.x == ET) s_sc.failed = 1; }
+                asm volatile("bar.sync 2, %0;" :: "n"(GT > 0 ? GT : 32) : "memory");
+                trace_mark_by(tr, kTrF, 14, ET);
             }
-            if ((threadIdx.x & 31) == 0) { while (ld_acquire_cta_shared(&s_flag1) != iter + 1u) { } }
-            __syncwarp();
-            trace_mark_by(tr, kTrF, 4, GT > 0 ? ET : 0);
-            for (;;) {
-                int lu = 0;
-                if ((threadIdx.x & 31) == 0) lu = int(atomicAdd(&s_next_unit, 1u));
-                lu = __shfl_sync(0xffffffffu, lu, 0);
-                if (lu >= n_my_units) break;
-                fused_unit<R>(t, a, &s_sc, lu * G + int(blockIdx.x), s_upart + size_t(lu) * kFusedDots);
+            for (int lu = lu0; lu < lu_end; lu += lu_step) {
+                if (lu != lu0) fused_unit_preload<R>(a, &s_sc, lu * G + int(blockIdx.x), pre);
+                fused_unit<R>(t, a, &s_sc, lu * G + int(blockIdx.x), pre, s_upart + size_t(lu) * kFusedDots);
             }
+            if (GT > 0 && !elem_thread) trace_mark_by(tr, kTrF, 15, ET);
             __syncthreads();
             pending = false;                        // (the units have applied the previous iteration's update of the shared nodes)
             trace_mark(tr, kTrF, 5);
             // ---- S2: the four dot products
             if (threadIdx.x < 32) {
                 double v[kFusedDots] = {0.0, 0.0, 0.0, 0.0};
-                for (int w = threadIdx.x; w < ET / 32; w += 32) {
+                // (uniform trip counts: a loop whose trip count differs between lanes can leave the warp split when it reaches the shuffles,
+                // which then take the per-shuffle WARPSYNC slow path)
+                for (int w0 = 0; w0 < ET / 32; w0 += 32) {
+                    const int w = w0 + int(threadIdx.x);
+                    if (w < ET / 32) {
 #pragma unroll
-                    for (int i = 0; i < kFusedDots; ++i) v[i] += s_wpart[w * kFusedDots + i];
+                        for (int i = 0; i < kFusedDots; ++i) v[i] += s_wpart[w * kFusedDots + i];
+                    }
                 }
-                for (int u = threadIdx.x; u < n_my_units; u += 32) {
+                for (int u0 = 0; u0 < n_my_units; u0 += 32) {
+                    const int u = u0 + int(threadIdx.x);
+                    if (u < n_my_units) {
 #pragma unroll
-                    for (int i = 0; i < kFusedDots; ++i) v[i] += s_upart[size_t(u) * kFusedDots + i];
+                        for (int i = 0; i < kFusedDots; ++i) v[i] += s_upart[size_t(u) * kFusedDots + i];
+                    }
                 }
+                __syncwarp();
 #pragma unroll
                 for (int i = 0; i < kFusedDots; ++i) {
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_down_sync(0xffffffffu, v[i], o);
                 }
+                trace_mark(tr, kTrF, 10);
                 fused_arrive_values(a.sync, s_sc.vsync, v);
+                if (GT == 0) trace_mark(tr, kTrF, 14);
                 const bool ok = fused_wait_values(a.sync, s_sc.vsync, s_tot);
+                if (GT == 0) trace_mark(tr, kTrF, 15);
                 if (threadIdx.x == 0) {
                     if (!ok) s_sc.failed = 1;
-                    s_sc.vsync += 1; s_sc.iter = iter + 1u; s_next_unit = 0u;
+                    s_sc.vsync += 1; s_sc.iter = iter + 1u;
                 }
             }
             __syncthreads();
             trace_mark(tr, kTrF, 6);
             if (s_sc.failed) { if (lead) { cg->done = 1; cg->end_cond = 99; } break; }
-            // ---- scalars (every thread of every CTA computes the same values from the same sums)
+            // ---- scalars (every thread of every CTA computes the same values from the same sums).  The lead thread records them in
+            // CGDev with plain stores -- no read-modify-write of global memory on anybody's path (cg_after_den / cg_after_rho semantics).
             const double rr = s_tot[0], den = s_tot[1], rq = s_tot[2], qq = s_tot[3];
             const double rho = rr;                  // the measured rho_k = r_k.r_k replaces last iteration's prediction
             const int it = s_sc.it;
+            const double normb = s_sc.normb;
             bool stop = false;
             if (den != 0.0) { if (fabs(den) <= s_sc.thr && !(it == 1 && s_sc.tsc == 0)) stop = true; } else stop = true;
+            int n_err = s_sc.n_err, n_den = s_sc.n_den;
             if (lead) {
-                cg->rho = rho;
-                if (cg->n_err > 0 && cg->n_err <= kMaxGraph) cg->graph_error[cg->n_err - 1] = sqrt(rho) / s_sc.normb;
-                cg_after_den(cg, den);
+                if (n_err >= 1 && n_err <= kMaxGraph) cg->graph_error[n_err - 1] = sqrt(rho) / normb;
+                if (n_den < kMaxGraph) { cg->graph_den[n_den] = den; ++n_den; cg->n_den = n_den; }
+                cg->den = den;
+                if (stop) { cg->rho = rho; cg->done = 1; cg->nb_iter = it; cg->end_cond = den != 0.0 ? 2 : 3; }
             }
             if (stop) break;
             const double alpha_d = rho / den;
@@ -644,16 +694,26 @@ __global__ void __launch_bounds__(ET + GT, 1) fused_cg_kernel(typename Pass::Dev
             if (!(rho_new > 0.0)) rho_new = 0.0;
             const int it2 = it + 1;
             bool stop2 = unsigned(it2) > s_sc.max_iter;
-            if (!stop2) { const double err = sqrt(rho_new) / s_sc.normb; if (err <= s_sc.tol && !(it2 == 1 && s_sc.tsc == 0)) stop2 = true; }
-            if (lead) cg_after_rho(cg, rho_new);
+            const double err2 = sqrt(rho_new) / normb;
+            const bool tol_hit = !stop2 && err2 <= s_sc.tol && !(it2 == 1 && s_sc.tsc == 0);
+            if (lead) {
+                cg->alpha = alpha_d; cg->rho_1 = rho; cg->rho = rho_new;
+                if (stop2) { cg->done = 1; cg->nb_iter = it2; cg->end_cond = 0; }
+                else {
+                    cg->it = it2;
+                    if (n_err < kMaxGraph) { cg->graph_error[n_err] = err2; ++n_err; cg->n_err = n_err; }
+                    if (tol_hit) { cg->done = 1; cg->nb_iter = it2; cg->end_cond = 1; }
+                }
+            }
+            stop2 = stop2 || tol_hit;
             __syncthreads();                        // everybody has read the scalars of the previous iteration
             if (threadIdx.x == 0) {
                 s_sc.alpha = alpha; s_sc.malpha = malpha; s_sc.a_one = alpha_d == 1.0 ? 1 : 0; s_sc.ma_one = -alpha_d == 1.0 ? 1 : 0;
-                s_sc.beta = R(rho_new / rho); s_sc.rho = rho_new; s_sc.it = it2; s_sc.first = 0;
+                s_sc.beta = R(rho_new / rho); s_sc.rho = rho_new; s_sc.it = it2; s_sc.first = 0; s_sc.n_err = n_err; s_sc.n_den = n_den;
             }
             __syncthreads();
             // ---- local update of x, r (and p unless the solve is over)
-            fused_update<R, NT>(t, a, &s_sc, smem_raw, !stop2);
+            fused_update<R, NT, CACHED>(t, a, &s_sc, smem_raw, !stop2);
             updated = true; pending = true;
             if (stop2) break;
             __syncthreads();

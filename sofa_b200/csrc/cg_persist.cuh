@@ -167,6 +167,7 @@ __device__ __forceinline__ double grid_wait_sum(unsigned long long* slots, unsig
     if (threadIdx.x < 32) {
         double v = 0.0;
         for (unsigned i = threadIdx.x; i < G; i += 32) v += __ldcg(cur + i);
+        __syncwarp();
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if (threadIdx.x == 0) *bcast = v;
@@ -201,6 +202,10 @@ __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsign
 }
 __device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 constexpr unsigned long long kSyncTimeoutNs = 4000000000ull;
+// Time-outs of the polling loops are taken on the SM's cycle counter: a read of %globaltimer inside a polling loop costs microseconds
+// per trip (measured: a grid sync with the timer in its loop took 7 us after the last arrival, 2 us without).
+constexpr long long kSyncTimeoutCycles = 8000000000ll;          // ~4 s at the 2 GHz boost clock
+__device__ __forceinline__ long long poll_clock() { return clock64(); }
 struct DistSeq { unsigned long long base; unsigned halo, ar; };
 __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) { asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
 __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
@@ -242,13 +247,14 @@ template <class R> __device__ __forceinline__ double dist_sync(const PersistCG<R
     if (threadIdx.x == 0) { cur[blockIdx.x] = cta_value; __threadfence(); atomicAdd(counter, 1u); }
     if (blockIdx.x == 0) {
         if (threadIdx.x == 0) {
-            const unsigned long long t0 = globaltimer_ns();
-            while (ld_acquire_u32(counter) < (s + 1) * G) { if (globaltimer_ns() - t0 > kSyncTimeoutNs) break; }
+            const long long t0 = poll_clock();
+            while (ld_acquire_u32(counter) < (s + 1) * G) { if (poll_clock() - t0 > kSyncTimeoutCycles) break; }
         }
         __syncthreads();
         if (threadIdx.x < 32) {
             double v = 0.0;
             for (unsigned i = threadIdx.x; i < G; i += 32) v += __ldcg(cur + i);
+            __syncwarp();
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
             if (threadIdx.x == 0) {
@@ -263,7 +269,7 @@ template <class R> __device__ __forceinline__ double dist_sync(const PersistCG<R
         }
     }
     if (threadIdx.x == 0) {
-        const unsigned long long t0 = globaltimer_ns();
+        const long long t0 = poll_clock();
         double tot = 0.0;
         bool fail = false;
         for (int r = 0; r < P.world && !fail; ++r) {
@@ -272,7 +278,7 @@ template <class R> __device__ __forceinline__ double dist_sync(const PersistCG<R
             for (;;) {
                 w0 = ld_relaxed_sys_u64(&src->w[0]); w1 = ld_relaxed_sys_u64(&src->w[1]);
                 if (unsigned(w0 >> 32) == aseq && unsigned(w1 >> 32) == aseq) break;
-                if (globaltimer_ns() - t0 > kSyncTimeoutNs) { fail = true; break; }
+                if (poll_clock() - t0 > kSyncTimeoutCycles) { fail = true; break; }
             }
             tot += __longlong_as_double((long long)((w0 & 0xFFFFFFFFull) | (w1 << 32)));      // rank order
         }
@@ -547,9 +553,9 @@ template <class R> __device__ __forceinline__ bool persist_rest(const TileDev<R>
                 // (the words were sent before the neighbour's contribution to den, so they have normally landed by now)
                 const unsigned long long* row = P.inbox + size_t(InboxWords<R>::N) * size_t(sj);
                 const unsigned hseq = unsigned(st.xs.base + st.xs.halo + 1);
-                const unsigned long long t0 = globaltimer_ns();
+                const long long t0 = poll_clock();
                 while (!(inbox_get(row, 0, hseq, c0) && inbox_get(row, 1, hseq, c1) && inbox_get(row, 2, hseq, c2)))
-                    if (globaltimer_ns() - t0 > kSyncTimeoutNs) { halo_timeout = true; break; }
+                    if (poll_clock() - t0 > kSyncTimeoutCycles) { halo_timeout = true; break; }
             }
             if (j == 0) { s0 = c0; s1 = c1; s2 = c2; } else { s0 += c0; s1 += c1; s2 += c2; }
         }

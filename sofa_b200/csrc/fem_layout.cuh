@@ -85,19 +85,19 @@ template <class R> struct NodeEpilogue {
 constexpr int kTraceWords = 16;          // words per CTA
 constexpr int kTraceTail = 4096 * kTraceWords;   // the CG tail kernel's records start here
 #ifdef __CUDA_ARCH__
-__device__ __forceinline__ void trace_mark(unsigned long long* trace, int base, int i) {
-    if (trace && threadIdx.x == 0) {
-        unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-        trace[base + blockIdx.x * kTraceWords + i] = t;
-        if (i == 0) { unsigned sm; asm volatile("mov.u32 %0, %smid;" : "=r"(sm)); trace[base + blockIdx.x * kTraceWords + 7] = sm; }
-    }
-}
+// The stamps are taken by ALL lanes of the marking thread's warp and stored by one: a branch taken by a single lane would split that lane
+// from its warp (measured: the warp's later shuffles then take the per-shuffle WARPSYNC slow path, microseconds per reduction tree).
 __device__ __forceinline__ void trace_mark_by(unsigned long long* trace, int base, int i, int who) {
-    if (trace && int(threadIdx.x) == who) {
+    if (trace && int(threadIdx.x >> 5) == (who >> 5)) {
         unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-        trace[base + blockIdx.x * kTraceWords + i] = t;
+        unsigned sm; asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+        if (int(threadIdx.x) == who) {
+            trace[base + blockIdx.x * kTraceWords + i] = t;
+            if (i == 0) trace[base + blockIdx.x * kTraceWords + 7] = sm;
+        }
     }
 }
+__device__ __forceinline__ void trace_mark(unsigned long long* trace, int base, int i) { trace_mark_by(trace, base, i, 0); }
 #else
 inline void trace_mark(unsigned long long*, int, int) {}
 inline void trace_mark_by(unsigned long long*, int, int, int) {}
@@ -303,6 +303,7 @@ template <class R> HD double node_post(const NodeEpilogue<R>& ep, uint32_t g, R 
 
 // block-wide sum in a fixed order: warp shuffles, then warp 0 over the per-warp partials
 __device__ __forceinline__ double block_sum(double v, double* warp_scratch /* >= 32 doubles of smem */) {
+    __syncwarp();   // (callers come out of loops with lane-dependent trip counts: without reconvergence every shuffle takes the WARPSYNC slow path)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -311,6 +312,7 @@ __device__ __forceinline__ double block_sum(double v, double* warp_scratch /* >=
     const int nw = (blockDim.x + 31) >> 5;
     v = (threadIdx.x < nw) ? warp_scratch[threadIdx.x] : 0.0;
     if (w == 0) {
+        __syncwarp();
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     }

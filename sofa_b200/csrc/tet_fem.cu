@@ -146,48 +146,58 @@ template int tet_cg_persistent<double>(sofab200_tetfem*, double, PersistCG<doubl
 // ---- fused persistent CG kernel (cg_fused.cuh): any number of tiles per CTA -----------------------------------------------------------
 // Returns SOFAB200_OK, an error, or kPersistNotEligible when not even the streamed layout fits.  info (optional): {grid, tiles per CTA,
 // cached, dynamic shared memory, element threads, gather threads}.
-template <class R, int MODE, bool PF, int ET, int GT> static int tet_fused_variant(TetFF<R>& ff, TetDev<R> d, FusedCG<R> a, size_t sync_capacity, bool dry_run, int* info) {
-    auto kern = fused_cg_kernel<R, TetPass<R, MODE, PF>, ET, GT>;
-    const HostPlan& P = ff.h.plan;
+template <class R, int MODE, bool PF, int ET, int GT, bool CACHED> static int tet_fused_launch(TetFF<R>& ff, TetDev<R> d, FusedCG<R> a, const FusedLayout& L, int grid, bool dry_run, int* info) {
+    auto kern = fused_cg_kernel<R, TetPass<R, MODE, PF>, ET, GT, CACHED>;
     cudaFuncAttributes fa;
     SB_CUDA(cudaFuncGetAttributes(&fa, kern));
     int dev_smem_optin = 0;
     SB_CUDA(cudaDeviceGetAttribute(&dev_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ff.ctx->device));
-    const int grid = std::max(1, std::min(ff.ctx->sm_count, P.n_tiles));
-    const int tiles_per_cta = (P.n_tiles + grid - 1) / grid;
-    const int n_units = P.n_chunks * (kGatherChunk / kUnit);
-    const int units_per_cta = (n_units + grid - 1) / grid;
-    // cached layout when the CTA's tiles fit next to the slots inside the 196 KB carve-out (a larger one throttles the element stream), else streamed
-    size_t cached_limit = 196 * 1024;
-    if (const char* env = getenv("SOFAB200_FUSED_CACHED_KB")) { const int v = atoi(env); if (v >= 0 && v <= 227) cached_limit = size_t(v) * 1024; }
-    FusedLayout L = fused_layout<R>(true, tiles_per_cta, units_per_cta, P.max_touched, P.max_slots, P.max_int, P.max_shtouch, P.maxval);
-    if (tiles_per_cta > 2 || L.total + fa.sharedSizeBytes + 1024 > cached_limit) L = fused_layout<R>(false, tiles_per_cta, units_per_cta, P.max_touched, P.max_slots, P.max_int, P.max_shtouch, P.maxval);
-    if (L.total + fa.sharedSizeBytes > size_t(dev_smem_optin) || tiles_per_cta > kMaxFusedTiles * 64) return kPersistNotEligible;
+    if (L.total + fa.sharedSizeBytes > size_t(dev_smem_optin)) return kPersistNotEligible;
     SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<unsigned>(L.total, 1024))));
     int per_sm = 0;
     SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ET + GT, L.total));
     if (per_sm < 1) return kPersistNotEligible;
-    if (fused_sync_words(grid) > sync_capacity) return fail(SOFAB200_ERR_INVALID, "sync buffer too small for the fused CG kernel");
-    if (info) { info[0] = grid; info[1] = tiles_per_cta; info[2] = L.cached; info[3] = int(L.total); info[4] = ET; info[5] = GT; }
+    if (info) { info[0] = grid; info[1] = L.tiles_per_cta; info[2] = L.cached; info[3] = int(L.total); info[4] = ET; info[5] = GT; }
     if (dry_run) return SOFAB200_OK;
     a.lay = L;
-    void* args[] = {&d, &a};
+    int ded_share = 50;       // per cent of the CTA's units of shared nodes that go to the dedicated warps
+    if (const char* env = getenv("SOFAB200_FUSED_GATHER_SHARE")) ded_share = std::max(0, std::min(100, atoi(env)));
+    void* args[] = {&d, &a, &ded_share};
     ff.ctx->prof_start(4);
     SB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(ET + GT), args, L.total, ff.ctx->stream));
     ff.ctx->prof_stop(4);
     ff.ctx->launches++;
     return SOFAB200_OK;
 }
+template <class R, int MODE, bool PF, int ET, int GT> static int tet_fused_variant(TetFF<R>& ff, TetDev<R> d, FusedCG<R> a, size_t sync_capacity, bool dry_run, int* info) {
+    const HostPlan& P = ff.h.plan;
+    const int grid = std::max(1, std::min(ff.ctx->sm_count, P.n_tiles));
+    const int tiles_per_cta = (P.n_tiles + grid - 1) / grid;
+    const int n_units = P.n_chunks * (kGatherChunk / kUnit);
+    const int units_per_cta = (n_units + grid - 1) / grid;
+    if (fused_sync_words(grid) > sync_capacity) return fail(SOFAB200_ERR_INVALID, "sync buffer too small for the fused CG kernel");
+    // cached layout when the CTA's tiles fit next to the slots inside the 196 KB carve-out (a larger one throttles the element stream), else streamed
+    size_t cached_limit = 196 * 1024;
+    if (const char* env = getenv("SOFAB200_FUSED_CACHED_KB")) { const int v = atoi(env); if (v >= 0 && v <= 227) cached_limit = size_t(v) * 1024; }
+    const FusedLayout Lc = fused_layout<R>(true, tiles_per_cta, units_per_cta, P.max_touched, P.max_slots, P.max_int, P.max_shtouch, P.maxval);
+    if (tiles_per_cta <= 2 && Lc.total + 2048 <= cached_limit) {
+        const int rc = tet_fused_launch<R, MODE, PF, ET, GT, true>(ff, d, a, Lc, grid, dry_run, info);
+        if (rc != kPersistNotEligible) return rc;
+    }
+    const FusedLayout Ls = fused_layout<R>(false, tiles_per_cta, units_per_cta, P.max_touched, P.max_slots, P.max_int, P.max_shtouch, P.maxval);
+    return tet_fused_launch<R, MODE, PF, ET, GT, false>(ff, d, a, Ls, grid, dry_run, info);
+}
 template <class R> int tet_cg_fused(sofab200_tetfem* base, R k_factor, FusedCG<R> a, size_t sync_capacity, bool dry_run, int* info) {
     TetFF<R>& ff = *static_cast<TetFF<R>*>(base);
     TetDev<R> d = ff.dev();
     d.k_factor = k_factor;
-    int gw = 4;   // dedicated gather warps
+    int gw = 0;   // dedicated gather warps
     if (const char* env = getenv("SOFAB200_FUSED_GATHER_WARPS")) gw = atoi(env);
     if (ff.method == SOFAB200_TET_SMALL) return tet_fused_variant<R, TM_DF_SMALL, false, 256, 0>(ff, d, a, sync_capacity, dry_run, info);
     if (sizeof(R) == 8) return tet_fused_variant<R, TM_DF_COROT, false, 256, 0>(ff, d, a, sync_capacity, dry_run, info);
     if (ff.threads > 256) {
         if (gw >= 4) return tet_fused_variant<R, TM_DF_COROT, true, 512, 128>(ff, d, a, sync_capacity, dry_run, info);
+        if (gw >= 2) return tet_fused_variant<R, TM_DF_COROT, true, 512, 64>(ff, d, a, sync_capacity, dry_run, info);
         return tet_fused_variant<R, TM_DF_COROT, true, 512, 0>(ff, d, a, sync_capacity, dry_run, info);
     }
     return tet_fused_variant<R, TM_DF_COROT, true, 256, 0>(ff, d, a, sync_capacity, dry_run, info);

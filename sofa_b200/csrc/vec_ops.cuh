@@ -278,9 +278,9 @@ template <class R> __global__ void __launch_bounds__(1024) halo_peer_kernel(Peer
             if (sj == -1) { c0 = q[g3]; c1 = q[g3 + 1]; c2 = q[g3 + 2]; }
             else if (sj >= 0) {
                 const unsigned long long* w = P.inbox + boff + size_t(InboxWords<R>::N) * size_t(sj);
-                const unsigned long long t0 = globaltimer_ns();
+                const long long t0 = poll_clock();
                 while (!(inbox_get(w, 0, seq, c0) && inbox_get(w, 1, seq, c1) && inbox_get(w, 2, seq, c2)))
-                    if (globaltimer_ns() - t0 > kSyncTimeoutNs) { s_fail = 1; break; }
+                    if (poll_clock() - t0 > kSyncTimeoutCycles) { s_fail = 1; break; }
             }
             if (j == 0) { s0 = c0; s1 = c1; s2 = c2; } else { s0 += c0; s1 += c1; s2 += c2; }
         }

@@ -65,13 +65,24 @@ if fused:
     tl = tail[tail[:, 0] > 0].astype(np.int64)
     us = lambda a, b: round(float(np.median(tl[:, b] - tl[:, a])) / 1000.0, 2)
     mx = lambda a, b: round(float(np.max(tl[:, b] - tl[:, a])) / 1000.0, 2)
-    res["cg_fused_last_iteration_us"] = {
+    t0 = tl[:, 0].min()
+    names = {0: "iteration start", 1: "tile 1 elements done", 2: "tile 1 interior sums done", 3: "all tiles done", 4: "S1 seen (element side)",
+             5: "all units done (CTA barrier)", 10: "S2: CTA sums ready", 14: "S2 arrival issued (GT>0: S1 seen by the dedicated warps)",
+             15: "S2 wait + sum done (GT>0: dedicated warps' units done)", 6: "S2 done", 13: "update done", 12: "next iteration start"}
+    dist = {"ctas": int(tl.shape[0])}
+    for i, nme in names.items():
+        c = tl[:, i]
+        if not np.all(c > 0):
+            continue
+        c = (c - t0) / 1000.0
+        dist[nme] = {"min": round(float(c.min()), 2), "p10": round(float(np.percentile(c, 10)), 2), "median": round(float(np.median(c)), 2),
+                     "p90": round(float(np.percentile(c, 90)), 2), "max": round(float(c.max()), 2), "argmax_cta": int(np.argmax(c))}
+    res["cg_fused_iteration_10_marks_us"] = dist
+    res["cg_fused_iteration_10_durations_us"] = {
         "first tile: elements": us(0, 1), "first tile: interior sums": us(1, 2), "remaining tiles (elements + interior sums)": us(2, 3),
-        "iteration start -> S1 seen by the gather poller": us(0, 4), "S1 seen -> all units done (CTA barrier)": us(4, 5),
-        "element warps done -> all units done": us(3, 5), "S2 (post, wait, sum)": us(5, 6),
-        "iteration start -> S2 done (median / max CTA)": [us(0, 6), mx(0, 6)],
+        "all tiles done -> S1 seen": us(3, 4), "S1 seen -> all units done (CTA barrier)": us(4, 5), "S2 (post, wait, sum)": us(5, 6),
         "S2 done -> update done": us(6, 13), "whole iteration (start -> next start), median / max CTA": [us(0, 12), mx(0, 12)]}
-    res["cg_fused_kernel_us"] = {"tables": us(8, 9), "kernel start -> end (median CTA)": us(8, 11), "last S2 -> end (update, x write-back)": us(6, 11)}
+    res["cg_fused_kernel_us"] = {"tables": us(8, 9), "kernel start -> end (median CTA)": us(8, 11)}
     s = None
 else:
     s = summarize(tail, ["iter_start", "tiles_done", "barrier1", "shared_done", "barrier2", "xr_done", "barrier3"])
