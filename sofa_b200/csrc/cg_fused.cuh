@@ -52,7 +52,7 @@ template <class R> inline FusedLayout fused_layout(bool cached, int tiles_per_ct
     L.off_nrec = unsigned(o); if (cached) o = up(o + sizeof(NodeRec<R>) * size_t(max_int) * tc);
     L.off_q = unsigned(o); if (cached) o = up(o + sizeof(R) * 3 * size_t(max_int) * tc);
     L.off_jds = unsigned(o); o = up(o + sizeof(uint16_t) * size_t(maxval + 1) * tc);
-    L.off_upart = unsigned(o); o = up(o + sizeof(double) * kFusedDots * size_t(std::max(units_per_cta, 1)));
+    L.off_upart = unsigned(o); o = up(o + sizeof(double) * kFusedDots * 2 * size_t(std::max(units_per_cta, 1)));   // [2][units]: second half = interface lanes (multi-GPU)
     L.off_extra = unsigned(o); o = up(o + extra_bytes);
     L.total = unsigned(o);
     return L;
@@ -72,6 +72,7 @@ template <class R> struct FusedCG {
     unsigned long long* sync;   // zero at launch: [3][grid][kFusedDots] doubles, then the S1 and S2 arrival counters (one 128-byte line each)
     FusedLayout lay;
     PeerDev<R> peer;
+    int n_if_units;         // multi-GPU: the partition-interface nodes are the first shared nodes; units [0, n_if_units) hold them
 };
 inline size_t fused_sync_words(int grid) { return size_t(3) * grid * kFusedDots + 64; }
 
@@ -97,6 +98,7 @@ template <class R> struct FusedScal {
     unsigned iter;                  // iterations started in this launch (sequence number of S1 / S2)
     unsigned vsync;                 // value syncs done (S2 and the prologue's)
     int failed;
+    unsigned long long seq_base;    // multi-GPU: sequence numbers of this launch start here (launches so far * 65536)
     int n_err, n_den;               // entries of CGDev::graph_error / graph_den so far (the lead thread records with plain stores, no read-modify-write)
 };
 
@@ -203,6 +205,69 @@ __device__ __forceinline__ bool fused_wait_values(unsigned long long* sync, unsi
     }
     return ok;
 }
+// ---- the same across the GPUs of one NVSwitch node (peer memory, see cg_persist.cuh) ---------------------------------------------------
+// Local arrival as above; CTA 0 is this GPU's leader: once the local CTAs have arrived it adds their values and stores the four sums into
+// slot [rank] of EVERY rank's table (lane r serves rank r: the W remote stores leave together), as 8-byte words carrying 32 bits of payload
+// and the 32-bit sequence number.  Warp 0 of every CTA then reads the W slots of its own GPU (lane r polls rank r) and adds them in rank
+// order: same operands, same order, same bits on every GPU.  The leader's own slot is stored last with release (it publishes this GPU's
+// CTAs' writes to the local pollers, which fence after seeing it).
+template <class R> __device__ __forceinline__ bool fused_sync_values_dist(const FusedCG<R>& a, unsigned vs, unsigned long long seq64, const double v[kFusedDots], double* out) {
+    const PeerDev<R>& P = a.peer;
+    const unsigned G = gridDim.x;
+    const unsigned seq = unsigned(seq64);
+    const int set = int(seq64 & 1ull), lane = int(threadIdx.x & 31);
+    fused_arrive_values(a.sync, vs, v);
+    bool ok = true;
+    if (blockIdx.x == 0) {
+        double tot[kFusedDots];
+        ok = fused_wait_values(a.sync, vs, out);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < kFusedDots; ++i) tot[i] = out[i];
+        __syncwarp();
+        if (lane < P.world) {
+            unsigned long long* dst = (lane == P.rank ? P.ar4 : P.peer_ar4[lane]) + (size_t(set) * kMaxPeers + P.rank) * 8;
+#pragma unroll
+            for (int i = 0; i < kFusedDots; ++i) {
+                const unsigned long long b = (unsigned long long)__double_as_longlong(tot[i]);
+                const unsigned long long w0 = (b & 0xFFFFFFFFull) | ((unsigned long long)seq << 32), w1 = (b >> 32) | ((unsigned long long)seq << 32);
+                if (lane == P.rank) { if (i < kFusedDots - 1) { dst[2 * i] = w0; dst[2 * i + 1] = w1; } else { dst[2 * i] = w0; st_release_gpu_u64(dst + 2 * i + 1, w1); } }
+                else { st_relaxed_sys_u64(dst + 2 * i, w0); st_relaxed_sys_u64(dst + 2 * i + 1, w1); }
+            }
+        }
+    }
+    __syncwarp();
+    double val[kFusedDots] = {0.0, 0.0, 0.0, 0.0};
+    if (lane < P.world) {
+        const unsigned long long* src = P.ar4 + (size_t(set) * kMaxPeers + lane) * 8;
+        const long long t0 = poll_clock();
+        for (;;) {
+            unsigned long long w[8];
+            bool all = true;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { w[i] = ld_relaxed_sys_u64(src + i); all = all && unsigned(w[i] >> 32) == seq; }
+            if (all) {
+#pragma unroll
+                for (int i = 0; i < kFusedDots; ++i) val[i] = __longlong_as_double((long long)((w[2 * i] & 0xFFFFFFFFull) | (w[2 * i + 1] << 32)));
+                break;
+            }
+            if (poll_clock() - t0 > kSyncTimeoutCycles) { ok = false; break; }
+        }
+    }
+    __syncwarp();
+    __threadfence();
+    ok = __all_sync(0xffffffffu, ok ? 1 : 0) != 0;
+    double tot[kFusedDots] = {0.0, 0.0, 0.0, 0.0};
+    for (int r = 0; r < P.world; ++r) {
+#pragma unroll
+        for (int i = 0; i < kFusedDots; ++i) tot[i] += __shfl_sync(0xffffffffu, val[i], r);      // rank order
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kFusedDots; ++i) out[i] = tot[i];
+    }
+    return ok;
+}
 // S1: "this CTA's staged contributions are complete" -- arrival only (the waiters are the threads that sum shared nodes)
 __device__ __forceinline__ void fused_arrive_s1(unsigned long long* sync) {
     unsigned* counter = reinterpret_cast<unsigned*>(sync + size_t(3) * gridDim.x * kFusedDots);
@@ -300,8 +365,8 @@ template <class R, int NT, bool CACHED> __device__ __forceinline__ bool fused_in
         __syncwarp();
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { v[0] += __shfl_down_sync(0xffffffffu, v[0], o); v[1] += __shfl_down_sync(0xffffffffu, v[1], o); }
-        fused_arrive_values(a.sync, 0u, v);
-        ok = fused_wait_values(a.sync, 0u, s_tot);
+        if (P.enabled) ok = fused_sync_values_dist<R>(a, 0u, (*P.epoch) * 65536ull + 1ull, v, s_tot);
+        else { fused_arrive_values(a.sync, 0u, v); ok = fused_wait_values(a.sync, 0u, s_tot); }
     }
     __syncthreads();
     const double nb2 = s_tot[0], rho0 = s_tot[1];
@@ -311,7 +376,8 @@ template <class R, int NT, bool CACHED> __device__ __forceinline__ bool fused_in
         sc->normb = sqrt(nb2); sc->rho = rho0; sc->it = 1;
         sc->tol = cg->tolerance; sc->thr = cg->threshold; sc->tsc = cg->time_step_count; sc->max_iter = cg->max_iter;
         sc->alpha = R(0); sc->malpha = R(0); sc->beta = R(0); sc->a_one = 0; sc->ma_one = 0;
-        sc->n_err = 2; sc->n_den = 0;       // (cg_begin_kernel: one entry; cg_after_rho(rho0) below: the second)
+        sc->n_err = 2; sc->n_den = 0;
+        sc->seq_base = P.enabled ? (*P.epoch) * 65536ull : 0ull;       // (cg_begin_kernel: one entry; cg_after_rho(rho0) below: the second)
     }
     __syncthreads();
     if (sc->failed) { if (lead) { cg->done = 1; cg->end_cond = 99; } return false; }
@@ -376,7 +442,7 @@ template <class R> __device__ __forceinline__ void fused_unit_preload(const Fuse
     if (!sc->first) { u.xv = sv_ldcg(a.xS + slot); u.qo = sv_ldcg(a.qS + slot); }
     else { u.xv = u.pv; u.qo = u.pv; }
 }
-template <class R> __device__ __forceinline__ void fused_unit(const TileDev<R>& t, const FusedCG<R>& a, const FusedScal<R>* sc, int unit, const UnitPre<R>& pre, double* upart /* smem [kFusedDots] */) {
+template <class R> __device__ __forceinline__ void fused_unit(const TileDev<R>& t, const FusedCG<R>& a, const FusedScal<R>* sc, int unit, const UnitPre<R>& pre, unsigned long long hseq64, double* upart /* smem [kFusedDots] */) {
     typedef typename SVec<R>::T SV;
     constexpr int B = GatherBatch<R>::N;
     const NodeEpilogue<R>& ep = a.ep;
@@ -427,10 +493,57 @@ template <class R> __device__ __forceinline__ void fused_unit(const TileDev<R>& 
         }
         node_finish_m(ep, rec.g, rec.mass, (rec.val_fixed & 0x10000u) != 0, p0, p1, p2, q0, q1, q2);
         stcg_sv(a.qS + slot, SVec<R>::make(q0, q1, q2));
-        if (!a.peer.enabled || a.peer.owned[rec.g]) acc_node<R>(acc, r0, r1, r2, p0, p1, p2, q0, q1, q2);
+        const PeerDev<R>& P = a.peer;
+        const int if_row = P.enabled ? P.sh_if_row[slot] : -1;
+        if (if_row >= 0) {
+            // multi-GPU, a node of the partition interface: (q) is this rank's PARTIAL sum.  Every other sharing rank gets it in its inbox now
+            // (NVLink stores); the node is finished in the second pass (fused_unit_interface), after the warp's other units.
+            const unsigned hseq = unsigned(hseq64);
+            for (int e = 0; e < P.max_sh - 1; ++e) {
+                const int2 to = P.if_send[if_row * (P.max_sh - 1) + e];
+                if (to.x >= 0) {
+                    unsigned long long* d = P.nb_inbox[to.x] + size_t(InboxWords<R>::N) * size_t(to.y);
+                    inbox_put(d, 0, q0, hseq); inbox_put(d, 1, q1, hseq); inbox_put(d, 2, q2, hseq);
+                }
+            }
+        } else acc_node<R>(acc, r0, r1, r2, p0, p1, p2, q0, q1, q2);
     }
     acc_warp_sum<R>(acc);
     if (lane == 0) { upart[0] = acc.rr; upart[1] = acc.pq; upart[2] = acc.rq; upart[3] = acc.qq; }
+}
+// second pass over a unit that holds interface nodes: q = the sharing ranks' partial sums in ascending rank order (own partial at its rank's
+// place) -- same operands, same order, same bits on every rank; the rank that owns the node counts it in the dot products.
+template <class R> __device__ __forceinline__ bool fused_unit_interface(const FusedCG<R>& a, int unit, unsigned long long hseq64, double* upart2 /* smem [kFusedDots] */) {
+    typedef typename SVec<R>::T SV;
+    const PeerDev<R>& P = a.peer;
+    const int lane = threadIdx.x & 31;
+    const size_t slot = size_t(unit) * kUnit + lane;
+    FusedAcc<R> acc{0.0, 0.0, 0.0, 0.0};
+    bool ok = true;
+    const GRec<R> rec = a.shrec[slot];
+    const int if_row = rec.g != 0xFFFFFFFFu ? P.sh_if_row[slot] : -1;
+    if (if_row >= 0) {
+        const SV pv = sv_ldcg(a.pS + slot), rv = sv_ldcg(a.rS + slot), qv = sv_ldcg(a.qS + slot);
+        const unsigned hseq = unsigned(hseq64);
+        R s0 = R(0), s1 = R(0), s2 = R(0);
+        for (int j = 0; j < P.max_sh; ++j) {
+            const int sj = P.src[if_row * P.max_sh + j];
+            R c0 = R(0), c1 = R(0), c2 = R(0);
+            if (sj == -1) { c0 = R(qv.x); c1 = R(qv.y); c2 = R(qv.z); }
+            else if (sj >= 0) {
+                const unsigned long long* row = P.inbox + size_t(InboxWords<R>::N) * size_t(sj);
+                const long long t0 = poll_clock();
+                while (!(inbox_get(row, 0, hseq, c0) && inbox_get(row, 1, hseq, c1) && inbox_get(row, 2, hseq, c2)))
+                    if (poll_clock() - t0 > kSyncTimeoutCycles) { ok = false; break; }
+            }
+            if (j == 0) { s0 = c0; s1 = c1; s2 = c2; } else { s0 += c0; s1 += c1; s2 += c2; }
+        }
+        stcg_sv(a.qS + slot, SVec<R>::make(s0, s1, s2));
+        if (P.owned[rec.g]) acc_node<R>(acc, R(rv.x), R(rv.y), R(rv.z), R(pv.x), R(pv.y), R(pv.z), s0, s1, s2);
+    }
+    acc_warp_sum<R>(acc);
+    if (lane == 0) { upart2[0] = acc.rr; upart2[1] = acc.pq; upart2[2] = acc.rq; upart2[3] = acc.qq; }
+    return __all_sync(0xffffffffu, ok ? 1 : 0) != 0;
 }
 
 // ---- after S2: x, r, p of every node the CTA's tiles touch ----------------------------------------------------------------------------------
@@ -557,6 +670,7 @@ __global__ void __launch_bounds__(ET + GT, 1) fused_cg_kernel(typename Pass::Dev
         // units of this CTA: unit = lu * G + blockIdx.x, lu < n_my_units
         const int n_units_total = t.n_chunks * (kGatherChunk / kUnit);
         const int n_my_units = (n_units_total - int(blockIdx.x) + G - 1) / G;
+        const int n_if_local = a.peer.enabled ? max(0, (a.n_if_units - int(blockIdx.x) + G - 1) / G) : 0;
         const int ded_units = GT > 0 ? min(n_my_units, (n_my_units * ded_share_pct + 99) / 100) : 0;
         const bool elem_thread = threadIdx.x < ET;
         const int warp = threadIdx.x >> 5;
@@ -626,7 +740,12 @@ __global__ void __launch_bounds__(ET + GT, 1) fused_cg_kernel(typename Pass::Dev
             }
             for (int lu = lu0; lu < lu_end; lu += lu_step) {
                 if (lu != lu0) fused_unit_preload<R>(a, &s_sc, lu * G + int(blockIdx.x), pre);
-                fused_unit<R>(t, a, &s_sc, lu * G + int(blockIdx.x), pre, s_upart + size_t(lu) * kFusedDots);
+                fused_unit<R>(t, a, &s_sc, lu * G + int(blockIdx.x), pre, s_sc.seq_base + iter + 1ull, s_upart + size_t(lu) * kFusedDots);
+            }
+            // multi-GPU: second pass over the warp's units that hold interface nodes (their partial sums left for the other GPUs in the first)
+            for (int lu = lu0; lu < lu_end && lu < n_if_local; lu += lu_step) {
+                const bool ok = fused_unit_interface<R>(a, lu * G + int(blockIdx.x), s_sc.seq_base + iter + 1ull, s_upart + (size_t(L.units_per_cta) + lu) * kFusedDots);
+                if (!ok && (threadIdx.x & 31) == 0) s_sc.failed = 1;
             }
             if (GT > 0 && !elem_thread) trace_mark_by(tr, kTrF, 15, ET);
             __syncthreads();
@@ -651,6 +770,13 @@ __global__ void __launch_bounds__(ET + GT, 1) fused_cg_kernel(typename Pass::Dev
                         for (int i = 0; i < kFusedDots; ++i) v[i] += s_upart[size_t(u) * kFusedDots + i];
                     }
                 }
+                for (int u0 = 0; u0 < n_if_local; u0 += 32) {
+                    const int u = u0 + int(threadIdx.x);
+                    if (u < n_if_local) {
+#pragma unroll
+                        for (int i = 0; i < kFusedDots; ++i) v[i] += s_upart[(size_t(L.units_per_cta) + u) * kFusedDots + i];
+                    }
+                }
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < kFusedDots; ++i) {
@@ -658,9 +784,13 @@ __global__ void __launch_bounds__(ET + GT, 1) fused_cg_kernel(typename Pass::Dev
                     for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_down_sync(0xffffffffu, v[i], o);
                 }
                 trace_mark(tr, kTrF, 10);
-                fused_arrive_values(a.sync, s_sc.vsync, v);
-                if (GT == 0) trace_mark(tr, kTrF, 14);
-                const bool ok = fused_wait_values(a.sync, s_sc.vsync, s_tot);
+                bool ok;
+                if (a.peer.enabled) ok = fused_sync_values_dist<R>(a, s_sc.vsync, s_sc.seq_base + s_sc.vsync + 1ull, v, s_tot);
+                else {
+                    fused_arrive_values(a.sync, s_sc.vsync, v);
+                    if (GT == 0) trace_mark(tr, kTrF, 14);
+                    ok = fused_wait_values(a.sync, s_sc.vsync, s_tot);
+                }
                 if (GT == 0) trace_mark(tr, kTrF, 15);
                 if (threadIdx.x == 0) {
                     if (!ok) s_sc.failed = 1;

@@ -95,6 +95,8 @@ template <class R> struct PeerDev {
     int nb_rank[kMaxPeers];
     ARSlot* ar;                                // local: [2][kMaxPeers] all-reduce slots (double-buffered by sequence parity)
     ARSlot* peer_ar[kMaxPeers];                // rank r's ar array (peer memory, own included)
+    unsigned long long* ar4;                   // local: [2][kMaxPeers][8 words] all-reduce slots of the fused kernel (four doubles per rank)
+    unsigned long long* peer_ar4[kMaxPeers];   // rank r's ar4 array
     unsigned long long* epoch;                 // local: launches done so far (sequence numbers are never reset)
     unsigned long long* inbox;                 // local: partial q of interface nodes received from the neighbours, kInboxWords<R> words per row
     unsigned long long* nb_inbox[kMaxPeers];   // neighbour k's inbox (peer memory)

@@ -246,7 +246,7 @@ template <class R> struct Node : sofab200_node {
     DevBuf<NodeRec<R>> gNrec;
     DevBuf<GRec<R>> shrec;
     int fused_info[6] = {0, 0, 0, 0, 0, 0};
-    int launch_fused(R* x, const R* bvec, double m, double bfac, double k) {
+    int launch_fused(R* x, const R* bvec, double m, double bfac, double k, const PeerDev<R>* pd = nullptr) {
         if (!tet) return kPersistNotEligible;
         const double kf = k + bfac * prm.ff_rayleigh_stiffness;
         const size_t n_tile_nodes = tet_tile_node_count(tet), n_slots = tet_shared_slot_count(tet);
@@ -258,7 +258,8 @@ template <class R> struct Node : sofab200_node {
         a.ep = make_mbk_ep(q.p, nullptr, p.p, m, bfac, k, false, 1.0, true, DOT_STORE, cg.p);
         a.x = x; a.r = r.p; a.b = bvec; a.xt = xt.p; a.rt = rt.p; a.gP = gP.p; a.gQ = gQ.p; a.gNrec = gNrec.p;
         a.xS = xS.p; a.rS = rS.p; a.pS = pS.p; a.qS = qS.p; a.shrec = shrec.p; a.n3 = 3 * n; a.cg = cg.p; a.sync = sync_slots.p;
-        std::memset(&a.peer, 0, sizeof(a.peer));
+        if (pd) a.peer = *pd; else std::memset(&a.peer, 0, sizeof(a.peer));
+        a.n_if_units = pd ? int((halo.n_if + kUnit - 1) / kUnit) : 0;
         SB_CUDA(cudaMemsetAsync(sync_slots.p, 0, sync_slots.n * sizeof(unsigned long long), ctx->stream));
         return tet_cg_fused<R>(tet, R(kf), a, sync_slots.n, false, fused_info);
     }
@@ -350,8 +351,8 @@ template <class R> struct Node : sofab200_node {
             // same loop, with the interface rows of q exchanged and the three dot products all-reduced over the ranks
             const double kf_d = k + bfac * prm.ff_rayleigh_stiffness;
             if (peer.ready && persistent && tet && (kf_d != 0.0 || bfac != 0.0)) {
-                // the loop in ONE persistent kernel per GPU; halo rows and dot products go through peer memory (cg_persist.cuh)
-                const int rc = launch_persistent(x, bvec, m, bfac, k, &peer.dev);
+                // the loop in ONE persistent kernel per GPU; halo rows and dot products go through peer memory (cg_fused.cuh / cg_persist.cuh)
+                const int rc = fused ? launch_fused(x, bvec, m, bfac, k, &peer.dev) : launch_persistent(x, bvec, m, bfac, k, &peer.dev);
                 if (rc == SOFAB200_OK) { LAUNCH(ctx, cg_end_kernel, 1, 1, cg.p); return SOFAB200_OK; }
                 if (rc != kPersistNotEligible) return rc;
                 peer.ready = false;      // (cannot happen after sofab200_node_set_peer's probe; kept for safety)
@@ -711,9 +712,10 @@ template <class R> static int node_set_distributed(Node<R>* nd, sofab200_comm* c
     nd->invalidate_graphs();
     return SOFAB200_OK;
 }
-// mailbox layout (bytes): 64 all-reduce slots [2][kMaxPeers][2 words] | 320 epoch u64 | 328 halo-call counter u64 | 1024 three inbox
-// buffers of inbox_rows rows each (the same inbox_rows on every rank, so that the offsets in a peer's mailbox are known)
-constexpr size_t kMailboxFlags = 0, kMailboxAr = 64, kMailboxEpoch = 320, kMailboxHcount = 328, kMailboxInbox = 1024;
+// mailbox layout (bytes): 64 all-reduce slots [2][kMaxPeers][2 words] (first-generation kernel) | 320 epoch u64 | 328 halo-call counter u64 |
+// 1024 all-reduce slots of the fused kernel [2][kMaxPeers][8 words] | 2048 three inbox buffers of inbox_rows rows each (the same
+// inbox_rows on every rank, so that the offsets in a peer's mailbox are known)
+constexpr size_t kMailboxFlags = 0, kMailboxAr = 64, kMailboxEpoch = 320, kMailboxHcount = 328, kMailboxAr4 = 1024, kMailboxInbox = 2048;
 template <class R> static size_t inbox_buf_words(size_t rows) { return (size_t(InboxWords<R>::N) * std::max<size_t>(rows, 1) + 31) & ~size_t(31); }
 template <class R> static size_t node_peer_bytes(const Node<R>* nd, size_t rows) {
     return kMailboxInbox + 3 * inbox_buf_words<R>(std::max(rows, nd->halo.n_send)) * sizeof(unsigned long long) + 256;
@@ -722,7 +724,12 @@ template <class R> static int node_set_peer(Node<R>* nd, const sofab200_peer_des
     if (!d->peer_base) { nd->peer.ready = false; nd->invalidate_graphs(); return SOFAB200_OK; }
     SB_CHECK(nd->distributed(), "sofab200_node_set_distributed must come first");
     SB_CHECK(nd->tet != nullptr, "peer mode is implemented for the tetrahedral force field");
-    {
+    if (nd->fused) {
+        FusedCG<R> probe; std::memset(&probe, 0, sizeof(probe));
+        const int rc = tet_cg_fused<R>(nd->tet, R(1), probe, size_t(3) * 2048 + 8, true, nullptr);
+        if (rc == kPersistNotEligible) return fail(SOFAB200_ERR_UNSUPPORTED, "this partition does not fit the fused CG kernel");
+        if (rc != SOFAB200_OK) return rc;
+    } else {
         PersistCG<R> probe; std::memset(&probe, 0, sizeof(probe));
         const int rc = tet_cg_persistent<R>(nd->tet, R(1), probe, size_t(3) * 2048, true);
         if (rc == kPersistNotEligible) return fail(SOFAB200_ERR_UNSUPPORTED, "this partition does not fit the persistent CG kernel (more than two tiles per SM)");
@@ -737,13 +744,15 @@ template <class R> static int node_set_peer(Node<R>* nd, const sofab200_peer_des
     P.rank = d->rank; P.world = d->world; P.n_nb = int(H.nb_rank.size()); P.max_sh = H.max_sh;
     unsigned char* mine = static_cast<unsigned char*>(d->peer_base[d->rank]);
     P.ar = reinterpret_cast<ARSlot*>(mine + kMailboxAr);
+    P.ar4 = reinterpret_cast<unsigned long long*>(mine + kMailboxAr4);
     P.epoch = reinterpret_cast<unsigned long long*>(mine + kMailboxEpoch);
     nd->peer.hcount = reinterpret_cast<unsigned long long*>(mine + kMailboxHcount);
     SB_CHECK(d->inbox_rows >= H.n_send, "inbox_rows must be the largest number of received rows over all ranks");
     nd->peer.buf_words = inbox_buf_words<R>(d->inbox_rows);
     SB_TRY(nd->peer.fail_flag.alloc(1)); SB_TRY(nd->peer.fail_flag.zero(s));
     P.inbox = reinterpret_cast<unsigned long long*>(mine + kMailboxInbox);
-    for (int r = 0; r < d->world; ++r) { SB_CHECK(d->peer_base[r] != nullptr, "peer_base entry is null"); P.peer_ar[r] = reinterpret_cast<ARSlot*>(static_cast<unsigned char*>(d->peer_base[r]) + kMailboxAr); }
+    for (int r = 0; r < d->world; ++r) { SB_CHECK(d->peer_base[r] != nullptr, "peer_base entry is null"); P.peer_ar[r] = reinterpret_cast<ARSlot*>(static_cast<unsigned char*>(d->peer_base[r]) + kMailboxAr);
+        P.peer_ar4[r] = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(d->peer_base[r]) + kMailboxAr4); }
     for (int k = 0; k < P.n_nb; ++k) {
         const int r = H.nb_rank[k];
         SB_CHECK(r >= 0 && r < d->world && r != d->rank, "neighbour rank out of range");

@@ -1,5 +1,5 @@
-"""Multi-GPU path on real devices (needs >= 2 GPUs; `gpurun --gpus 2`), against the single-domain oracle, in its three forms:
-"peer"  one persistent CG kernel per GPU exchanging over NVLink peer memory (sofab200_node_set_peer),
+"""Multi-GPU path on real devices (needs >= 2 GPUs; `gpurun --gpus 2` / `--gpus 8`), against the single-domain oracle, in its forms:
+"peer"  one persistent CG kernel per GPU (cg_fused.cuh) exchanging over NVLink peer memory (sofab200_node_set_peer); "peer_v1": the first-generation kernel,
 "nccl"  the library's multi-kernel loop with NCCL send/recv + allreduce (sofab200_node_set_distributed only),
 "torch" the host-driven loop of sofa_b200/parallel.py over torch.distributed (what tests/test_parallel_cpu.py runs on gloo)."""
 import os
@@ -24,7 +24,8 @@ def _worker(rank, world, port, cfg_name, dtype_name, mode, q_out):
     import sofa_b200 as sb
     import sofa_b200.parallel as PAR
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
-    os.environ["SOFAB200_PEER"] = "1" if mode == "peer" else "0"
+    os.environ["SOFAB200_PEER"] = "1" if mode.startswith("peer") else "0"
+    os.environ["SOFAB200_CG_FUSED"] = "0" if mode == "peer_v1" else "1"      # peer_v1: the first-generation persistent kernel (two cross-GPU syncs per iteration)
     native = mode != "torch"
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -51,13 +52,16 @@ def _worker(rank, world, port, cfg_name, dtype_name, mode, q_out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["peer", "nccl", "torch"])
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("mode", ["peer", "peer_v1", "nccl", "torch"])
 @pytest.mark.parametrize("dtype_name", ["f64", "f32"])
-def test_two_gpus_match_single_domain_oracle(dtype_name, mode):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+def test_n_gpus_match_single_domain_oracle(dtype_name, mode, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    if world > 2 and mode not in ("peer", "nccl"):
+        pytest.skip("the larger worlds exercise the two library loops")
     import torch.multiprocessing as mp
-    cfg, world = "C2_SMALL", 2
+    cfg = "C2_SMALL"
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -68,7 +72,7 @@ def test_two_gpus_match_single_domain_oracle(dtype_name, mode):
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    assert res["peer"] == (mode == "peer")     # the mode under test is the one that ran
+    assert res["peer"] == mode.startswith("peer")     # the mode under test is the one that ran
     dtype = np.float32 if dtype_name == "f32" else np.float64
     c, pos, hexas, tets, fixed = mesh(cfg)
     s = O.OracleScene(dtype, pos)
