@@ -302,6 +302,15 @@ int sofab200_node_step(sofab200_node* node, void* x_dev, void* v_dev);
 /* The same step for HOST state vectors (pinned or pageable): H2D of x,v, step, D2H of x,v; the upload of v overlaps addForce,
  * which only needs x. (sync) */
 int sofab200_node_step_host(sofab200_node* node, void* x_host, void* v_host);
+/* The step for a host-owned POSITION vector only: x goes up, the step runs on it and on the node's device-resident velocities, x comes back.
+ * The velocities never cross the bus unless asked: v_host_in (may be NULL) is uploaded first (initial velocities, or a host that changed
+ * them; they start at zero otherwise), v_host_out (may be NULL) receives the new ones.  This is what [EI]:83-341 needs per step when the state
+ * lives in a device-typed MechanicalObject: only a reader on the host (visual model, collision) makes x come back. (sync) */
+int sofab200_node_step_host_x(sofab200_node* node, void* x_host, const void* v_host_in, void* v_host_out);
+/* Which kernel the last CG solve of the node ran (diagnostics for the benchmark line): out = {grid, tiles per CTA, 1 = tile state cached in
+ * shared memory / 0 = streamed from HBM scratch, dynamic shared memory bytes, element threads, dedicated shared-node threads,
+ * 1 = fused single-reduction kernel enabled, 1 = a persistent kernel is enabled at all}; the first six are zero before the first fused solve. */
+int sofab200_node_cg_kernel_info(const sofab200_node* node, int out[8]);
 /* Results of the last solve (sync): nb_iter ("CG iterations" as the reference reports it), end condition
  * (0 iterations exhausted, 1 tolerance, 2 threshold, 3 den==0, 4 b==0; 99 = multi-GPU only: a wait on another GPU timed out
  * inside the CG kernel and the solve was abandoned), and the `graph` Data

@@ -1439,9 +1439,45 @@ template <class R> struct Scene {
         }
         for (auto& th : pool) th.join();
     }
+    // threads > 1: ParallelHexahedronFEMForceField::addDForce
+    // (applications/plugins/MultiThreading/src/MultiThreading/component/solidmechanics/fem/elastic/ParallelHexahedronFEMForceField.inl:201-268):
+    // pass 1, element ranges over threads: every hexahedron's 8 corner terms df_w = -(R^T F_w) kFactor into m_elementsDf; pass 2, vertex
+    // ranges over threads: df[v] += m_elementsDf[h][corner of v in h] over the hexahedra around v (m_around, ascending hexahedron index,
+    // built once as in the class's initStiffnessMatrices :147-172).  A TIMING variant for the CPU baseline.
+    std::vector<std::vector<uint32_t>> hexAround, hexAroundCorner;
+    std::vector<Coord> hexElementsDf;
+    void parallelHexAddDForce(VecDeriv<R>& df, const VecDeriv<R>& d, double kf) {
+        if (df.size() != d.size()) df.resize(d.size());
+        const size_t H = hex.nbHexas(), N = d.size();
+        const R kFactor = R(kf);
+        if (hexAround.size() != N) {
+            hexAround.assign(N, {}); hexAroundCorner.assign(N, {});
+            for (size_t h = 0; h < H; ++h) for (int w = 0; w < 8; ++w) { hexAround[hex.hexas[8 * h + w]].push_back(uint32_t(h)); hexAroundCorner[hex.hexas[8 * h + w]].push_back(uint32_t(w)); }
+        }
+        hexElementsDf.resize(8 * H);
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; ++t)
+            pool.emplace_back([&, t]() {
+                for (size_t i = H * t / threads; i < H * (t + 1) / threads; ++i) {
+                    const uint32_t* elem = &hex.hexas[8 * i];
+                    R X[24], F[24];
+                    for (int w = 0; w < 8; ++w) { const Coord x_2 = hex.rotations[i] * d[elem[w]]; X[3 * w] = x_2[0]; X[3 * w + 1] = x_2[1]; X[3 * w + 2] = x_2[2]; }
+                    HexaFEM<R>::computeForce(F, X, &hex.Ke[576 * i]);
+                    for (int w = 0; w < 8; ++w) hexElementsDf[8 * i + w] = -hex.rotations[i].multTranspose(Coord(F[3 * w], F[3 * w + 1], F[3 * w + 2])) * kFactor;
+                }
+            });
+        for (auto& th : pool) th.join();
+        pool.clear();
+        for (int t = 0; t < threads; ++t)
+            pool.emplace_back([&, t]() {
+                for (size_t v = N * t / threads; v < N * (t + 1) / threads; ++v)
+                    for (size_t a = 0; a < hexAround[v].size(); ++a) df[v] += hexElementsDf[8 * size_t(hexAround[v][a]) + hexAroundCorner[v][a]];
+            });
+        for (auto& th : pool) th.join();
+    }
     void femAddDForce(VecDeriv<R>& df, const VecDeriv<R>& d, double kf) {
         if (hasTet) { if (threads > 1) parallelTetAddDForce(df, d, kf); else tet.addDForce(df, d, kf); }
-        if (hasHex) hex.addDForce(df, d, kf);
+        if (hasHex) { if (threads > 1) parallelHexAddDForce(df, d, kf); else hex.addDForce(df, d, kf); }
     }
     // mop.computeForce: resetForce, accumulateForce (no external force), every force field's addForce in scene order
     // Sofa/framework/Simulation/Core/src/sofa/simulation/MappingGraphMechanicalOperations.cpp:41-93

@@ -115,6 +115,8 @@ SYMBOLS = {
     "sofab200_node_cg_solve": (_I, [_P, _P, _P, _D, _D, _D, C.POINTER(_I)]),
     "sofab200_node_step": (_I, [_P, _P, _P]),
     "sofab200_node_step_host": (_I, [_P, _P, _P]),
+    "sofab200_node_step_host_x": (_I, [_P, _P, _P, _P]),
+    "sofab200_node_cg_kernel_info": (_I, [_P, C.POINTER(C.c_int)]),
     "sofab200_node_last_solve": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_D), C.POINTER(_SZ), C.POINTER(_D), C.POINTER(_SZ), _SZ]),
     "sofab200_node_get": (_I, [_P, C.c_char_p, _P]),
     "sofab200_node_reset": (_I, [_P]),

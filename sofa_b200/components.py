@@ -542,6 +542,17 @@ class SolverNode:
         vp = v_host.ctypes.data_as(_P) if isinstance(v_host, np.ndarray) else C.c_void_p(v_host.data_ptr())
         check(self.ctx.L.sofab200_node_step_host(self.h, xp, vp))
 
+    def step_host_x(self, x_host, v_host_in=None, v_host_out=None):
+        """The step for a host-owned position array: x up, step on the device-resident velocities, x back (v only on request)."""
+        ptr = lambda a: None if a is None else (a.ctypes.data_as(_P) if isinstance(a, np.ndarray) else C.c_void_p(a.data_ptr()))
+        check(self.ctx.L.sofab200_node_step_host_x(self.h, ptr(x_host), ptr(v_host_in), ptr(v_host_out)))
+
+    def fused_info(self):
+        out = (C.c_int * 8)()
+        check(self.ctx.L.sofab200_node_cg_kernel_info(self.h, out))
+        return dict(zip(["grid", "tiles_per_cta", "tile_state_in_shared_memory", "dynamic_smem_bytes", "element_threads", "dedicated_shared_node_threads",
+                         "fused_enabled", "persistent_enabled"], list(out)))
+
     def last_solve(self):
         it, ec = C.c_int(), C.c_int()
         ne, nd = C.c_size_t(), C.c_size_t()

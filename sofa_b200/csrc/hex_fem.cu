@@ -21,7 +21,7 @@ template <class R> struct HexFF : sofab200_hexfem {
     DevBuf<uint32_t> orig, kidx, tile_kuniq;
     DevBuf<Quad<R>> r0, r1, r2, x0;
     DevBuf<R> ktab;
-    DevBuf<uint32_t> tile_node_off, tile_nodes, tile_nint, sh_nodes, sh_base;
+    DevBuf<uint32_t> tile_node_off, tile_nodes, tile_shslot, tile_nint, sh_nodes, sh_base;
     DevBuf<uint16_t> tile_val, tile_jds, sh_val;
     DevBuf<Quad<R>> stage;
     DevBuf<R> rot_export;
@@ -31,7 +31,7 @@ template <class R> struct HexFF : sofab200_hexfem {
         const HostPlan& plan = h.plan;
         HexDev<R> d;
         d.t.n_nodes = int(n_nodes); d.t.n_elems = int(n_hexas); d.t.n_tiles = plan.n_tiles; d.t.tile_e = plan.tile_e; d.t.maxval = plan.maxval;
-        d.t.tile_node_off = tile_node_off.p; d.t.tile_nodes = tile_nodes.p; d.t.tile_nint = tile_nint.p; d.t.tile_nb = nullptr; d.t.tile_val = tile_val.p; d.t.tile_jds = tile_jds.p;
+        d.t.tile_node_off = tile_node_off.p; d.t.tile_nodes = tile_nodes.p; d.t.tile_shslot = tile_shslot.p; d.t.tile_nint = tile_nint.p; d.t.tile_nb = nullptr; d.t.tile_val = tile_val.p; d.t.tile_jds = tile_jds.p;
         d.t.n_shared = plan.n_shared; d.t.n_chunks = plan.n_chunks; d.t.sh_nodes = sh_nodes.p; d.t.sh_val = sh_val.p; d.t.sh_base = sh_base.p;
         d.t.stage = stage.p; d.t.stage_n = plan.stage_n;
         d.lnode = lnode.p; d.slot_a = slot_a.p; d.slot_b = slot_b.p; d.r0 = r0.p; d.r1 = r1.p; d.r2 = r2.p;
@@ -48,7 +48,7 @@ template <class R> static int hex_upload(HexFF<R>& ff) {
     SB_TRY(ff.lnode.upload(H.lnode, s)); SB_TRY(ff.slot_a.upload(H.slot_a, s)); SB_TRY(ff.slot_b.upload(H.slot_b, s)); SB_TRY(ff.orig.upload(P.order, s));
     SB_TRY(ff.r0.upload(H.r0, s)); SB_TRY(ff.r1.upload(H.r1, s)); SB_TRY(ff.r2.upload(H.r2, s)); SB_TRY(ff.x0.upload(H.x0, s));
     SB_TRY(ff.kidx.upload(H.kidx, s)); SB_TRY(ff.tile_kuniq.upload(H.tile_kuniq, s)); SB_TRY(ff.ktab.upload(H.ktab, s));
-    SB_TRY(ff.tile_node_off.upload(P.tile_node_off, s)); SB_TRY(ff.tile_nodes.upload(P.tile_nodes, s)); SB_TRY(ff.tile_nint.upload(P.tile_nint, s));
+    SB_TRY(ff.tile_node_off.upload(P.tile_node_off, s)); SB_TRY(ff.tile_nodes.upload(P.tile_nodes, s)); SB_TRY(ff.tile_shslot.upload(P.tile_shslot, s)); SB_TRY(ff.tile_nint.upload(P.tile_nint, s));
     SB_TRY(ff.tile_val.upload(P.tile_val, s)); SB_TRY(ff.tile_jds.upload(P.tile_jds, s));
     SB_TRY(ff.sh_nodes.upload(P.sh_nodes, s)); SB_TRY(ff.sh_val.upload(P.sh_val, s)); SB_TRY(ff.sh_base.upload(P.sh_base, s));
     SB_TRY(ff.stage.alloc(P.stage_n)); SB_TRY(ff.stage.zero(s));
@@ -106,6 +106,57 @@ template <class R> int hex_cg_persistent(sofab200_hexfem* base, R k_factor, Pers
         return SOFAB200_OK;
     }
     return kPersistNotEligible;
+}
+// fused CG kernel (cg_fused.cuh) around the hexahedral element pass: cached when the CTA's tiles fit, else streamed (any number of tiles)
+template <class R, bool CACHED> static int hex_fused_launch(HexFF<R>& ff, HexDev<R> d, FusedCG<R> a, const FusedLayout& L, int grid, bool dry_run, int* info) {
+    auto kern = fused_cg_kernel<R, HexPass<R>, 256, 0, CACHED>;
+    cudaFuncAttributes fa;
+    SB_CUDA(cudaFuncGetAttributes(&fa, kern));
+    int dev_smem_optin = 0;
+    SB_CUDA(cudaDeviceGetAttribute(&dev_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ff.ctx->device));
+    if (L.total + fa.sharedSizeBytes > size_t(dev_smem_optin)) return kPersistNotEligible;
+    SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<unsigned>(L.total, 1024))));
+    int per_sm = 0;
+    SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, L.total));
+    if (per_sm < 1) return kPersistNotEligible;
+    if (info) { info[0] = grid; info[1] = L.tiles_per_cta; info[2] = L.cached; info[3] = int(L.total); info[4] = 256; info[5] = 0; }
+    if (dry_run) return SOFAB200_OK;
+    a.lay = L;
+    int ded_share = 0;
+    void* args[] = {&d, &a, &ded_share};
+    ff.ctx->prof_start(4);
+    SB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(256), args, L.total, ff.ctx->stream));
+    ff.ctx->prof_stop(4);
+    ff.ctx->launches++;
+    return SOFAB200_OK;
+}
+template <class R> int hex_cg_fused(sofab200_hexfem* base, R k_factor, FusedCG<R> a, size_t sync_capacity, bool dry_run, int* info) {
+    HexFF<R>& ff = *static_cast<HexFF<R>*>(base);
+    HexDev<R> d = ff.dev();
+    d.k_factor = k_factor;
+    const HostPlan& P = ff.h.plan;
+    const int grid = std::max(1, std::min(ff.ctx->sm_count, P.n_tiles));
+    const int tiles_per_cta = (P.n_tiles + grid - 1) / grid;
+    const int n_units = P.n_chunks * (kGatherChunk / kUnit);
+    const int units_per_cta = (n_units + grid - 1) / grid;
+    if (fused_sync_words(grid) > sync_capacity) return fail(SOFAB200_ERR_INVALID, "sync buffer too small for the fused CG kernel");
+    const size_t extra = sizeof(R) * 576 * kHexSmemMatrices;
+    const FusedLayout Lc = fused_layout<R>(true, tiles_per_cta, units_per_cta, P.max_touched, P.max_slots, P.max_int, P.max_shtouch, P.maxval, extra);
+    if (tiles_per_cta <= 2 && Lc.total + 2048 <= 200 * 1024) {
+        const int rc = hex_fused_launch<R, true>(ff, d, a, Lc, grid, dry_run, info);
+        if (rc != kPersistNotEligible) return rc;
+    }
+    // streamed tiles: measured on C3 (491 520 hexahedra, 4 tiles per CTA) the one-thread-per-hexahedron pass at 255 registers runs slower inside the
+    // persistent kernel (3.44 ms per step) than as plain tile launches (2.52 ms), so big hexahedral meshes keep the multi-kernel loop unless asked
+    if (!getenv("SOFAB200_HEX_FUSED_STREAMED")) return kPersistNotEligible;
+    const FusedLayout Ls = fused_layout<R>(false, tiles_per_cta, units_per_cta, P.max_touched, P.max_slots, P.max_int, P.max_shtouch, P.maxval, extra);
+    return hex_fused_launch<R, false>(ff, d, a, Ls, grid, dry_run, info);
+}
+template int hex_cg_fused<float>(sofab200_hexfem*, float, FusedCG<float>, size_t, bool, int*);
+template int hex_cg_fused<double>(sofab200_hexfem*, double, FusedCG<double>, size_t, bool, int*);
+size_t hex_shared_slot_count(sofab200_hexfem* base) {
+    if (base->real == SOFAB200_F32) return size_t(static_cast<HexFF<float>*>(base)->h.plan.n_chunks) * kGatherChunk;
+    return size_t(static_cast<HexFF<double>*>(base)->h.plan.n_chunks) * kGatherChunk;
 }
 template int hex_cg_persistent<float>(sofab200_hexfem*, float, PersistCG<float>, size_t, bool);
 template int hex_cg_persistent<double>(sofab200_hexfem*, double, PersistCG<double>, size_t, bool);

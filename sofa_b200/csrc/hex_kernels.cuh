@@ -5,7 +5,7 @@
 // bit-identical (all elements of a grid whose spacing is exactly representable) are stored once: the element record keeps
 // an index into a table of unique matrices, and a CTA whose tile refers to few matrices serves them from shared memory.
 #pragma once
-#include "cg_persist.cuh"
+#include "cg_fused.cuh"
 #include "math3.cuh"
 
 namespace sb {
@@ -107,16 +107,18 @@ template <class R> __host__ __device__ inline size_t hex_smem_bytes(int max_touc
 
 // phase 2 of a tile: one thread per hexahedron, 8 corner contributions scattered to their slots.  The tile's (few) distinct
 // element stiffness matrices are cached in shared memory first (s_k: kHexSmemMatrices x 576 Reals); ends with no barrier.
-template <class R, int MODE>
+// NTHR: number of threads that share the tile (0: the whole CTA, synchronised with __syncthreads; else the first NTHR threads, named barrier 1)
+template <class R, int MODE, int NTHR = 0>
 __device__ __forceinline__ void hex_tile_elements(const HexDev<R>& d, int tile, const typename SVec<R>::T* s_in, R* s_slot, int max_slots, R* s_k) {
     typedef typename SVec<R>::T SV;
     const TileDev<R>& t = d.t;
+    const int nthr = NTHR > 0 ? NTHR : int(blockDim.x);
     const uint32_t* ku = d.tile_kuniq + size_t(tile) * (kHexSmemMatrices + 1);
     const int n_ku = int(ku[0]);
-    for (int i = threadIdx.x; i < n_ku * 576; i += blockDim.x) s_k[i] = d.ktab[size_t(ku[1 + i / 576]) * 576 + i % 576];
-    __syncthreads();
+    for (int i = threadIdx.x; i < n_ku * 576; i += nthr) s_k[i] = d.ktab[size_t(ku[1 + i / 576]) * 576 + i % 576];
+    if (NTHR > 0) bar_first<(NTHR > 0 ? NTHR : 32)>(); else __syncthreads();
     const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
-    for (int le = threadIdx.x; le < t.tile_e; le += blockDim.x) {
+    for (int le = threadIdx.x; le < t.tile_e; le += nthr) {
         const size_t es = size_t(tile) * t.tile_e + le;
         const uint4 ln = idx_load(d.lnode + es, pol_stream);
         if ((ln.x & 0xFFFFu) == 0xFFFFu) continue;
@@ -134,6 +136,15 @@ __device__ __forceinline__ void hex_tile_elements(const HexDev<R>& d, int tile, 
         for (int w = 0; w < 8; ++w) tile_scatter<R>(t, s8[w], C[w].x, C[w].y, C[w].z, s_slot, max_slots, pol_keep);
     }
 }
+// element policy of the fused CG kernel (cg_fused.cuh); the plan does not order a tile's elements that feed shared nodes first (arrive_at < 0)
+template <class R> struct HexPass {
+    typedef HexDev<R> Dev;
+    static __device__ __forceinline__ const TileDev<R>& tiles(const Dev& d) { return d.t; }
+    template <int ET, class OnBoundary>
+    static __device__ __forceinline__ void elements(const Dev& d, int tile, const typename SVec<R>::T* s_in, R* s_slot, int max_slots, unsigned char* s_extra, int, OnBoundary) {
+        hex_tile_elements<R, HM_DF, ET>(d, tile, s_in, s_slot, max_slots, reinterpret_cast<R*>(s_extra));
+    }
+};
 
 template <class R, int MODE>
 __global__ void __launch_bounds__(256) hex_tile_kernel(HexDev<R> d, const R* __restrict__ in, NodeEpilogue<R> ep, int max_touched, int max_slots) {

@@ -17,6 +17,8 @@ template <class R> int tet_run(sofab200_tetfem* ff, bool dforce, const R* in, R 
 template <class R> int tet_cg_persistent(sofab200_tetfem* ff, R k_factor, PersistCG<R> a, size_t part_capacity, bool dry_run);
 template <class R> int tet_cg_fused(sofab200_tetfem* ff, R k_factor, FusedCG<R> a, size_t sync_capacity, bool dry_run, int* info);
 size_t tet_shared_slot_count(sofab200_tetfem* ff);
+template <class R> int hex_cg_fused(sofab200_hexfem* ff, R k_factor, FusedCG<R> a, size_t sync_capacity, bool dry_run, int* info);
+size_t hex_shared_slot_count(sofab200_hexfem* ff);
 size_t tet_tile_node_count(sofab200_tetfem* ff);
 const std::vector<uint32_t>& tet_shared_node_table(sofab200_tetfem* ff);
 template <class R> TileDev<R> tet_tiledev(sofab200_tetfem* ff);
@@ -247,9 +249,8 @@ template <class R> struct Node : sofab200_node {
     DevBuf<GRec<R>> shrec;
     int fused_info[6] = {0, 0, 0, 0, 0, 0};
     int launch_fused(R* x, const R* bvec, double m, double bfac, double k, const PeerDev<R>* pd = nullptr) {
-        if (!tet) return kPersistNotEligible;
         const double kf = k + bfac * prm.ff_rayleigh_stiffness;
-        const size_t n_tile_nodes = tet_tile_node_count(tet), n_slots = tet_shared_slot_count(tet);
+        const size_t n_tile_nodes = tet ? tet_tile_node_count(tet) : hex_tile_node_count(hex), n_slots = tet ? tet_shared_slot_count(tet) : hex_shared_slot_count(hex);
         if (xt.n < n_tile_nodes) { SB_TRY(xt.alloc(n_tile_nodes)); SB_TRY(rt.alloc(n_tile_nodes)); }
         if (gP.n < n_tile_nodes) { SB_TRY(gP.alloc(n_tile_nodes)); SB_TRY(gQ.alloc(3 * n_tile_nodes)); SB_TRY(gNrec.alloc(n_tile_nodes)); }
         if (xS.n < n_slots) { SB_TRY(xS.alloc(n_slots)); SB_TRY(rS.alloc(n_slots)); SB_TRY(pS.alloc(n_slots)); SB_TRY(qS.alloc(n_slots)); SB_TRY(shrec.alloc(n_slots)); }
@@ -261,7 +262,7 @@ template <class R> struct Node : sofab200_node {
         if (pd) a.peer = *pd; else std::memset(&a.peer, 0, sizeof(a.peer));
         a.n_if_units = pd ? int((halo.n_if + kUnit - 1) / kUnit) : 0;
         SB_CUDA(cudaMemsetAsync(sync_slots.p, 0, sync_slots.n * sizeof(unsigned long long), ctx->stream));
-        return tet_cg_fused<R>(tet, R(kf), a, sync_slots.n, false, fused_info);
+        return tet ? tet_cg_fused<R>(tet, R(kf), a, sync_slots.n, false, fused_info) : hex_cg_fused<R>(hex, R(kf), a, sync_slots.n, false, fused_info);
     }
     NodeEpilogue<R> base_ep() {
         NodeEpilogue<R> ep{};
@@ -371,7 +372,7 @@ template <class R> struct Node : sofab200_node {
             return SOFAB200_OK;
         }
         const double kf_chk = k + bfac * prm.ff_rayleigh_stiffness;
-        if (persistent && fused && tet && (kf_chk != 0.0 || bfac != 0.0)) {
+        if (persistent && fused && (kf_chk != 0.0 || bfac != 0.0)) {
             const int rc = launch_fused(x, bvec, m, bfac, k);                   // (|b| and the first rho included)
             if (rc == SOFAB200_OK) { LAUNCH(ctx, cg_end_kernel, 1, 1, cg.p); return SOFAB200_OK; }
             if (rc != kPersistNotEligible) return rc;
@@ -882,8 +883,25 @@ template <class R> static int node_step_host(Node<R>* n, void* x_host, void* v_h
     SB_CUDA(cudaStreamSynchronize(s));
     return SOFAB200_OK;
 }
+// x round trip only: the velocities stay resident in HBM between steps (what the reference's own loop does with a device-typed state)
+template <class R> static int node_step_host_x(Node<R>* n, void* x_host, const void* v_host_in, void* v_host_out) {
+    const size_t bytes = 3 * n->n * sizeof(R);
+    cudaStream_t s = n->ctx->stream;
+    if (!n->hx.p) { SB_TRY(n->hx.alloc(3 * n->n)); SB_TRY(n->hv.alloc(3 * n->n)); SB_TRY(n->hv.zero(s)); }
+    SB_CUDA(cudaMemcpyAsync(n->hx.p, x_host, bytes, cudaMemcpyHostToDevice, s));
+    if (v_host_in) SB_CUDA(cudaMemcpyAsync(n->hv.p, v_host_in, bytes, cudaMemcpyHostToDevice, s));
+    SB_TRY(n->step(n->hx.p, n->hv.p, false));
+    SB_CUDA(cudaMemcpyAsync(x_host, n->hx.p, bytes, cudaMemcpyDeviceToHost, s));
+    if (v_host_out) SB_CUDA(cudaMemcpyAsync(v_host_out, n->hv.p, bytes, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    return SOFAB200_OK;
+}
 }  // namespace sb
 extern "C" {
+int sofab200_node_step_host_x(sofab200_node* node, void* x_host, const void* v_host_in, void* v_host_out) {
+    SB_CHECK(node && x_host, "null argument");
+    return NODE_DISPATCH(node, sb::node_step_host_x<float>(NF(node), x_host, v_host_in, v_host_out), sb::node_step_host_x<double>(ND(node), x_host, v_host_in, v_host_out));
+}
 int sofab200_node_step_host(sofab200_node* node, void* x_host, void* v_host) {
     SB_CHECK(node && x_host && v_host, "null argument");
     return NODE_DISPATCH(node, sb::node_step_host<float>(NF(node), x_host, v_host), sb::node_step_host<double>(ND(node), x_host, v_host));
@@ -919,6 +937,15 @@ int sofab200_node_get(sofab200_node* node, const char* what, void* out_host) {
     SB_CHECK(src != nullptr, "unknown vector name");
     SB_CUDA(cudaMemcpyAsync(out_host, src, 3 * node->n * es, cudaMemcpyDeviceToHost, node->ctx->stream));
     SB_CUDA(cudaStreamSynchronize(node->ctx->stream));
+    return SOFAB200_OK;
+}
+int sofab200_node_cg_kernel_info(const sofab200_node* node, int out[8]) {
+    SB_CHECK(node && out, "null argument");
+    const int* fi = node->real == SOFAB200_F32 ? static_cast<const Node<float>*>(node)->fused_info : static_cast<const Node<double>*>(node)->fused_info;
+    const bool fused = node->real == SOFAB200_F32 ? static_cast<const Node<float>*>(node)->fused : static_cast<const Node<double>*>(node)->fused;
+    const bool persistent = node->real == SOFAB200_F32 ? static_cast<const Node<float>*>(node)->persistent : static_cast<const Node<double>*>(node)->persistent;
+    for (int i = 0; i < 6; ++i) out[i] = fi[i];
+    out[6] = fused ? 1 : 0; out[7] = persistent ? 1 : 0;
     return SOFAB200_OK;
 }
 int sofab200_node_reset(sofab200_node* node) {

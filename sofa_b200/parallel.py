@@ -2,8 +2,9 @@
 per-iteration halo exchange of the nodal A*p partial sums and an allreduce of the CG scalars.
 
 The reference has no distributed mode (no MPI/NCCL anywhere in the tree); this is the multi-GPU design
-north_star asks for.  Partition: CONTIGUOUS RANGES of the topology's element list, one per rank (on a RegularGridTopology
-beam these are z-slabs, so a rank has at most two neighbours).  A node touched by elements of several ranks is an
+north_star asks for.  Partition (`partition_elements`): contiguous ranges of the topology's element list, one per rank (on a
+RegularGridTopology beam these are z-slabs, so a rank has at most two neighbours), or recursive coordinate bisection of the element
+centroids for meshes whose numbering says nothing about space.  A node touched by elements of several ranks is an
 interface node; every sharing rank keeps it (ghost copy), the lowest sharing rank owns it.
 
 Per A*p:  each rank runs the fused element pass on its own elements (mass term of an interface node added by its owner
@@ -29,24 +30,74 @@ def element_ranges(n_elems, world):
     return [(lo[r], lo[r] + base + (1 if r < rem else 0)) for r in range(world)]
 
 
+def partition_rcb(positions, elems, world):
+    """Recursive coordinate bisection of the element CENTROIDS (the partitioner for meshes whose element numbering says
+    nothing about space): the current set is cut across its longest extent at the weighted median, the two halves get floor(w/2) and
+    ceil(w/2) of the ranks and element counts in the same proportion, recursively.  Deterministic (stable argsort, ties by element index).
+    Returns part[e] = rank of element e."""
+    elems = np.asarray(elems, np.int64)
+    cen = np.asarray(positions, np.float64)[elems].mean(axis=1)
+    part = np.zeros(elems.shape[0], np.int32)
+
+    def split(idx, r0, w):
+        if w == 1 or len(idx) == 0:
+            part[idx] = r0
+            return
+        c = cen[idx]
+        axis = int(np.argmax(c.max(axis=0) - c.min(axis=0))) if len(idx) else 0
+        order = idx[np.argsort(c[:, axis], kind="stable")]
+        wl = w // 2
+        nl = (len(idx) * wl + w // 2) // w
+        split(np.sort(order[:nl]), r0, wl)
+        split(np.sort(order[nl:]), r0 + wl, w - wl)
+
+    split(np.arange(elems.shape[0]), 0, world)
+    return part
+
+
+def partition_elements(positions, elems, world, method="slab"):
+    """part[e] = rank of element e.  "slab": contiguous ranges of the topology's element list (z-slabs of a RegularGridTopology beam, whose
+    hexahedra are numbered z-major: GridTopology.cpp:381-398); "rcb": recursive coordinate bisection, for any mesh."""
+    n = np.asarray(elems).shape[0]
+    if method in ("slab", "contiguous"):
+        part = np.zeros(n, np.int32)
+        for r, (a, b) in enumerate(element_ranges(n, world)):
+            part[a:b] = r
+        return part
+    if method == "rcb":
+        return partition_rcb(positions, elems, world)
+    raise ValueError(f"unknown partition method {method!r}")
+
+
+def interface_node_count(elems, part, world):
+    """Number of nodes touched by elements of more than one part (the quantity a partitioner minimises)."""
+    elems = np.asarray(elems, np.int64)
+    n_nodes = int(elems.max()) + 1 if elems.size else 0
+    cnt = np.zeros(n_nodes, np.int32)
+    for r in range(world):
+        ids = np.unique(elems[part == r])
+        cnt[ids] += 1
+    return int((cnt > 1).sum())
+
+
 class RankMesh:
     """What one rank needs: its elements in local numbering, its nodes (global ids), ownership and the halo plan."""
 
-    def __init__(self, positions, elems, rank, world):
+    def __init__(self, positions, elems, rank, world, partition="slab"):
         elems = np.asarray(elems, np.int64)
         n_nodes = positions.shape[0]
-        ranges = element_ranges(elems.shape[0], world)
-        self.rank, self.world, self.ranges = rank, world, ranges
-        lo, hi = ranges[rank]
-        mine = elems[lo:hi]
+        part = partition_elements(positions, elems, world, partition) if isinstance(partition, str) else np.asarray(partition, np.int32)
+        self.rank, self.world, self.part = rank, world, part
+        self.ranges = element_ranges(elems.shape[0], world) if isinstance(partition, str) and partition in ("slab", "contiguous") else None
+        mine = elems[part == rank]                                       # (original relative order of the rank's elements)
         self.global_ids = np.unique(mine)                               # sorted global node ids of the local nodes
         g2l = np.full(n_nodes, -1, np.int64); g2l[self.global_ids] = np.arange(len(self.global_ids))
         self.elems = g2l[mine].astype(np.uint32)                         # local numbering, original relative order
         self.positions = positions[self.global_ids]
         # which ranks touch each of MY nodes
         touch = np.zeros((len(self.global_ids), world), bool)
-        for r, (a, b) in enumerate(ranges):
-            ids = np.unique(elems[a:b])
+        for r in range(world):
+            ids = np.unique(elems[part == r])
             l = g2l[ids]; touch[l[l >= 0], r] = True
         self.sharers = touch
         nsh = touch.sum(1)
@@ -206,12 +257,12 @@ class DistributedSolverNode:
     CGLinearSolver.inl:73-315 with its scalars all-reduced (two small allreduces and one halo exchange per iteration)."""
 
     def __init__(self, positions, tets, fixed_global, massDensity, youngModulus, poissonRatio, method="large", group=None, ctx=None,
-                 template="B200Vec3f", backend_factory=None, native=True, dt=0.01, gravity=(0.0, -9.81, 0.0), rayleighStiffness=0.0, rayleighMass=0.0,
+                 template="B200Vec3f", backend_factory=None, native=True, partition="slab", dt=0.01, gravity=(0.0, -9.81, 0.0), rayleighStiffness=0.0, rayleighMass=0.0,
                  iterations=25, tolerance=1e-5, threshold=1e-5):
         from .topology import diagonal_mass
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.rm = rm = RankMesh(positions, tets, self.rank, self.world)
+        self.rm = rm = RankMesh(positions, tets, self.rank, self.world, partition)
         self.p = dict(dt=dt, gravity=tuple(gravity), rK=rayleighStiffness, rM=rayleighMass, iterations=iterations, tolerance=tolerance, threshold=threshold)
         ndtype = np.float32 if template.endswith("f") else np.float64
         # global lumped masses (identical on every sharing rank); the fused element pass of a rank adds the mass term of an

@@ -75,7 +75,7 @@ class OracleBackend:
         x += v * self.np_dtype(h)
 
 
-def _worker(rank, world, port, cfg_name, q_out):
+def _worker(rank, world, port, cfg_name, q_out, partition="slab"):
     import sofa_b200.parallel as PAR
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -87,7 +87,7 @@ def _worker(rank, world, port, cfg_name, q_out):
             be._fixed_global = fixed
             return be
         node = PAR.DistributedSolverNode(pos, tets, fixed, c["density"], c["young"], c["poisson"], "large", backend_factory=factory, template="B200Vec3d",
-                                         dt=c["dt"], gravity=c["gravity"], rayleighStiffness=c["rK"], rayleighMass=c["rM"], iterations=c["iterations"],
+                                         partition=partition, dt=c["dt"], gravity=c["gravity"], rayleighStiffness=c["rK"], rayleighMass=c["rM"], iterations=c["iterations"],
                                          tolerance=c["tolerance"], threshold=c["threshold"])
         rm = node.rm
         # (1) partition invariants
@@ -111,13 +111,13 @@ def _worker(rank, world, port, cfg_name, q_out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_distributed_apply_and_steps_match_single_domain(world):
+@pytest.mark.parametrize("world,partition", [(2, "slab"), (3, "slab"), (3, "rcb"), (4, "rcb")])
+def test_distributed_apply_and_steps_match_single_domain(world, partition):
     cfg = "C1"
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, cfg, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cfg, q, partition)) for r in range(world)]
     for p in procs:
         p.start()
     res = q.get(timeout=240)
@@ -155,3 +155,51 @@ def test_rank_mesh_and_halo_plan():
             assert np.array_equal(m.global_ids[nb["local"]], meshes[s].global_ids[other["local"]])
         assert np.array_equal(pos[m.global_ids], m.positions)
         assert np.array_equal(m.global_ids[m.elems.astype(np.int64)], tets[PAR.element_ranges(tets.shape[0], world)[r][0]:PAR.element_ranges(tets.shape[0], world)[r][1]])
+
+
+def _liver_replicated(k):
+    """The liver mesh (tests/golden/liver_mesh.npz) replicated k x k x k times with a random permutation of the element list: a mesh whose
+    element numbering says nothing about space (copies are disjoint: the partitioner must keep each copy's elements together to do well)."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "liver_mesh.npz"))
+    pos0, tets0 = z["positions"].astype(np.float64), z["tetrahedra"].astype(np.int64)
+    ext = pos0.max(0) - pos0.min(0)
+    pos, tets = [], []
+    for i in range(k):
+        for j in range(k):
+            for l in range(k):
+                tets.append(tets0 + len(pos) * pos0.shape[0])
+                pos.append(pos0 + np.array([i, j, l]) * ext * 0.97)      # (slightly overlapping boxes: centroids of neighbouring copies interleave)
+    pos, tets = np.concatenate(pos), np.concatenate(tets)
+    rng = np.random.default_rng(3)
+    return pos, tets[rng.permutation(tets.shape[0])]
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_rcb_partition_of_a_mesh_without_spatial_numbering(world):
+    import sofa_b200.parallel as PAR
+    pos, tets = _liver_replicated(4)          # 64 livers: 38 144 tetrahedra, shuffled
+    part = PAR.partition_elements(pos, tets, world, "rcb")
+    counts = np.bincount(part, minlength=world)
+    assert counts.sum() == tets.shape[0] and counts.max() - counts.min() <= world          # balanced
+    assert np.array_equal(part, PAR.partition_elements(pos, tets, world, "rcb"))            # deterministic
+    n_rcb = PAR.interface_node_count(tets, part, world)
+    n_slab = PAR.interface_node_count(tets, PAR.partition_elements(pos, tets, world, "slab"), world)
+    # contiguous ranges of a shuffled list put every node on the interface; bisection keeps it to the cut surfaces
+    assert n_slab > 0.5 * pos.shape[0]
+    assert n_rcb < 0.1 * pos.shape[0], (n_rcb, n_slab, pos.shape[0])
+    meshes = [PAR.RankMesh(pos, tets, r, world, "rcb") for r in range(world)]
+    assert sum(m.elems.shape[0] for m in meshes) == tets.shape[0]
+    assert sum(int(m.owned.sum()) for m in meshes) == np.unique(tets).shape[0]
+    for r, m in enumerate(meshes):
+        for s_, nb in m.neighbours.items():
+            other = meshes[s_].neighbours[r]
+            assert np.array_equal(m.global_ids[nb["local"]], meshes[s_].global_ids[other["local"]])     # symmetric interface lists, same order
+
+
+def test_rcb_on_a_grid_beam_is_as_good_as_slabs():
+    import sofa_b200.parallel as PAR
+    c, pos, hexas, tets, fixed = mesh("C2_SMALL")
+    for world in (2, 4):
+        n_rcb = PAR.interface_node_count(tets, PAR.partition_elements(pos, tets, world, "rcb"), world)
+        n_slab = PAR.interface_node_count(tets, PAR.partition_elements(pos, tets, world, "slab"), world)
+        assert n_rcb <= 1.25 * n_slab, (world, n_rcb, n_slab)
