@@ -535,6 +535,12 @@ def run_ours_distributed(args, rank, world, local):
     barrier()
     clocks = sampler.stop()
     launches = ctx.launch_count - launches0
+    # ---- per-kernel durations on every rank (plain launches with an event pair around each; all ranks must run the same steps)
+    ctx.profile_begin()
+    for _ in range(min(args.steps, 20)):
+        node.step()
+    prof = ctx.profile_end()
+    barrier()
     # ---- end-to-end arm: every rank's local x in pinned host memory, copied in and out every step; velocities resident
     xh = node.be.x.detach().cpu().pin_memory(); vh = node.be.v.detach().cpu().pin_memory()
     node.be.node.step_host_x(xh, vh)
@@ -585,7 +591,8 @@ def run_ours_distributed(args, rank, world, local):
                        "l2": "working set per CG iteration and GPU exceeds L2" if max_T * 120 > 126e6 else "per-GPU working set fits the 126 MB L2"},
             "parity_check": parity,
             "roofline": {"bound": "hbm", "achieved": cg_gbs, "peak": peak, "unit": "GB/s", "frac": cg_gbs / peak, "traffic": None,
-                         "kernel": "whole distributed step per GPU attributed to the CG iterations (algorithmic bytes of the largest partition)", "peak_source": peak_src},
+                         "kernel": "whole distributed step per GPU attributed to the CG iterations (algorithmic bytes of the largest partition)", "peak_source": peak_src,
+                         "kernel_ms_rank0": {k: v for k, v in prof.items()}},
             "e2e": {"value": it_step * e2e_steps * units / e2e_s, "unit": "cg_iters/s" if strong else "partition_cg_iters/s", "h2d_bytes_per_step": sum(int(a[1]) for a in all_sizes) * 3 * s,
                     "d2h_bytes_per_step": sum(int(a[1]) for a in all_sizes) * 3 * s, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                     "note": "every rank copies its partition's x from pinned host memory and back each step (sofab200_node_step_host_x), velocities resident; wall clock, max over ranks"},

@@ -255,7 +255,7 @@ template <class R> __device__ __forceinline__ bool fused_sync_values_dist(const 
         }
     }
     __syncwarp();
-    __threadfence();
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");       // acquire side of the leader's release (lighter than the sequentially consistent __threadfence)
     ok = __all_sync(0xffffffffu, ok ? 1 : 0) != 0;
     double tot[kFusedDots] = {0.0, 0.0, 0.0, 0.0};
     for (int r = 0; r < P.world; ++r) {

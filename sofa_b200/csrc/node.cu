@@ -279,7 +279,7 @@ template <class R> struct Node : sofab200_node {
         ep.gx = R(prm.gravity[0]); ep.gy = R(prm.gravity[1]); ep.gz = R(prm.gravity[2]);
     }
     // mop.computeForce
-    int compute_force(R* f_out, const R* x, const R* v = nullptr) {
+    int compute_force(R* f_out, const R* x, const R* v = nullptr, bool skip_halo = false) {
         NodeEpilogue<R> ep = base_ep();
         ep.init_src = nullptr; ep.sign = +1; ep.out = f_out;
         set_mass_term(ep, PRE_GRAVITY, nullptr, 1.0);
@@ -290,7 +290,7 @@ template <class R> struct Node : sofab200_node {
         }
         if (has_plane) { ep.plane_mode = 1; ep.plane = plane; ep.plane_v = v; ep.plane_contacts = plane_contacts.p; ep.plane_in = x; }
         SB_TRY(fem_run(false, x, R(0), ep));
-        return halo_sum(f_out, nullptr);
+        return skip_halo ? SOFAB200_OK : halo_sum(f_out, nullptr);     // (skip_halo: the caller keeps every rank's PARTIAL forces, see step_direct)
     }
     // df = init + (m M + b B + k K) d, optionally scaled and projected; dot(out, dot_with) optional
     NodeEpilogue<R> make_mbk_ep(R* out, const R* init, const R* d, double m, double bfac, double k, bool scale, double s, bool project, int dot_kind, CGDev* cgp) {
@@ -443,11 +443,14 @@ template <class R> struct Node : sofab200_node {
     int step_direct(R* x, R* v, bool skip_force = false) {
         const double h = prm.dt, tr = prm.trapezoidal ? 0.5 : 1.0;
         const bool fo = prm.first_order != 0;
-        if (!skip_force) SB_TRY(compute_force(f.p, x, v));
+        // Distributed: the right-hand side is linear in f, so every rank starts its partial b from its PARTIAL f (mass term on the owner only)
+        // and ONE exchange, of b, completes both -- the interface rows of f itself are left partial (nothing downstream reads them).
+        const bool partial_f = distributed() && halo.n_if && !fo && !skip_force;
+        if (!skip_force) SB_TRY(compute_force(f.p, x, v, partial_f));
         if (!fo) {
             // b = (f + (-rM M + (h tr + rK) K) v) * h, projected          EulerImplicitSolver.cpp:147-162
             const R* finit = f.p;
-            if (distributed() && halo.n_if) {   // the start value f of a shared node enters the distributed sum on its owner only
+            if (distributed() && halo.n_if && !partial_f) {   // f was completed over the ranks: its interface rows enter the distributed sum on their owner only
                 LAUNCH(ctx, (mask_rows_kernel<R>), vec_grid(n, ctx->sm_count), kVecBlock, n, (const unsigned char*)halo.owned.p, (const R*)f.p, p.p);
                 finit = p.p;
             }

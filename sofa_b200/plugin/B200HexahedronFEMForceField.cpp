@@ -2,11 +2,11 @@
 // Same pattern as B200TetrahedronFEMForceField.cpp: the class, its Data fields (youngModulus, poissonRatio, method,
 // rayleighStiffness) and init() are the reference's own template; reinit / addForce / addDForce forward to ONE entry point of
 // include/sofa_b200.h each.  Device state hangs off the HexahedronFEMForceFieldInternalData member the reference class
-// reserves (HexahedronFEMForceField.h:41-54,188-189).  Not compilable in this image (SOFA itself is not), see INTEGRATION.md.
+// reserves (HexahedronFEMForceField.h:41-54,188-189).  Syntax-checked against the reference headers by tools/plugin_syntax_check.sh.
 #include <sofa/component/solidmechanics/fem/elastic/HexahedronFEMForceField.inl>
 #include <sofa/core/ObjectFactory.h>
 
-#include "B200Types.h"
+#include "B200Handles.h"
 
 namespace sofa::component::solidmechanics::fem::elastic {
 using sofa::b200::B200Vec3Types;
@@ -14,6 +14,8 @@ using sofa::b200::B200Vec3Types;
 template <class TReal> class HexahedronFEMForceFieldInternalData<B200Vec3Types<TReal>> {
 public:
     sofab200_hexfem* ff = nullptr;
+    void initPtrData(HexahedronFEMForceField<B200Vec3Types<TReal>>*) {}
+    static sofab200_hexfem* handle(HexahedronFEMForceField<B200Vec3Types<TReal>>* m) { return m->data ? m->data->ff : nullptr; }   // (called by the class's constructor, HexahedronFEMForceField.inl:65)
     ~HexahedronFEMForceFieldInternalData() { if (ff) sofab200_hexfem_destroy(ff); }
 };
 
@@ -22,7 +24,7 @@ public:
         /* replaces reinit() .inl:155-192: material stiffness, rest rotations, rotated rest shapes and the 24x24 element           \
            stiffness matrices (computeElementStiffness .inl:306-536) are computed inside sofab200_hexfem_create */                   \
         if (this->d_componentState.getValue() == core::objectmodel::ComponentState::Invalid) return;                                \
-        setMethod(d_method.getValue()); /* "large" -> 0, "polar" -> 1, "small" -> 2 in both enums */                                \
+        { const std::string& m = d_method.getValue(); setMethod(m == "large" ? LARGE : (m == "polar" ? POLAR : SMALL)); } /* as init() does; LARGE=0, POLAR=1, SMALL=2 in both enums */ \
         const auto& rest = this->mstate->read(core::vec_id::read_access::restPosition)->getValue();                                 \
         const auto& hexas = this->l_topology->getHexahedra();                                                                        \
         std::vector<double> young(this->d_youngModulus.getValue().begin(), this->d_youngModulus.getValue().end());                 \
@@ -64,6 +66,12 @@ template class HexahedronFEMForceField<sofa::b200::B200Vec3dTypes>;
 }  // namespace sofa::component::solidmechanics::fem::elastic
 
 namespace sofa::b200 {
+sofab200_hexfem* hexfemHandle(sofa::component::solidmechanics::fem::elastic::HexahedronFEMForceField<B200Vec3fTypes>* ff) {
+    return sofa::component::solidmechanics::fem::elastic::HexahedronFEMForceFieldInternalData<B200Vec3fTypes>::handle(ff);
+}
+sofab200_hexfem* hexfemHandle(sofa::component::solidmechanics::fem::elastic::HexahedronFEMForceField<B200Vec3dTypes>* ff) {
+    return sofa::component::solidmechanics::fem::elastic::HexahedronFEMForceFieldInternalData<B200Vec3dTypes>::handle(ff);
+}
 void registerHexahedronFEMForceField(sofa::core::ObjectFactory* factory) {
     using namespace sofa::component::solidmechanics::fem::elastic;
     factory->registerObjects(sofa::core::ObjectRegistrationData("HexahedronFEMForceField on a B200 GPU (sofa_b200)")

@@ -1,9 +1,5 @@
-// SOFA-side glue: MechanicalObject<B200Vec3Types>::vOp / vMultiOp / vDot / resetForce, DiagonalMass<B200Vec3Types>
-// ::addMDx / addForce / accFromF and FixedProjectiveConstraint<B200Vec3Types>::projectResponse, each forwarding to one
-// C-ABI entry point (the set SofaCUDA specialises for the same scenes:
-// applications/plugins/SofaCUDA/Component/src/SofaCUDA/component/statecontainer/CudaMechanicalObject.h:133-142).
-#include <sofa/component/constraint/projective/FixedProjectiveConstraint.inl>
-#include <sofa/component/mass/DiagonalMass.inl>
+// SOFA-side glue: MechanicalObject<B200Vec3Types>::vOp / vMultiOp / vDot / resetForce, each forwarding to one C-ABI entry point (the set SofaCUDA
+// specialises for the same scenes: applications/plugins/SofaCUDA/Component/src/SofaCUDA/component/statecontainer/CudaMechanicalObject.h:133-142).
 #include <sofa/component/statecontainer/MechanicalObject.inl>
 #include <sofa/core/ObjectFactory.h>
 
@@ -12,27 +8,62 @@
 namespace sofa::component::statecontainer {
 using sofa::b200::B200Vec3Types;
 
+namespace {
+/// device pointer of the state vector `id` of `mo` (null id -> null pointer), for reading or for writing
+template <class MO> void* b200_vec(MO* mo, core::ConstVecId id, bool write) {
+    if (id.isNull()) return nullptr;
+    if (id.type == core::V_COORD) {
+        auto* d = mo->write(core::VecCoordId(id.index));
+        if (write) { void* p = sofa::b200::devWrite(*d->beginEdit()); d->endEdit(); return p; }
+        return const_cast<void*>(sofa::b200::devRead(d->getValue()));
+    }
+    auto* d = mo->write(core::VecDerivId(id.index));
+    if (write) { void* p = sofa::b200::devWrite(*d->beginEdit()); d->endEdit(); return p; }
+    return const_cast<void*>(sofa::b200::devRead(d->getValue()));
+}
+}  // namespace
+
 #define B200_MO(TReal)                                                                                                               \
     template <> void MechanicalObject<B200Vec3Types<TReal>>::vOp(const core::ExecParams*, core::VecId r, core::ConstVecId a,        \
                                                                  core::ConstVecId b, SReal k) {                                      \
         /* null ids become null pointers; the C ABI reproduces the dispatch of MechanicalObject.inl:2075-2203 */                     \
-        auto dptr = [&](core::ConstVecId id, bool write) -> void* {                                                                  \
-            if (id.isNull()) return nullptr;                                                                                         \
-            if (id.type == core::V_COORD) { auto* d = this->write(core::VecCoordId(id)); return write ? d->beginEdit()->deviceWrite() : const_cast<void*>(d->getValue().deviceRead()); } \
-            auto* d = this->write(core::VecDerivId(id)); return write ? d->beginEdit()->deviceWrite() : const_cast<void*>(d->getValue().deviceRead()); \
-        };                                                                                                                           \
-        void* pr = dptr(r, true);                                                                                                    \
-        const void* pa = a == r ? pr : dptr(a, false);                                                                               \
-        const void* pb = b == r ? pr : dptr(b, false);                                                                               \
+        if (r.isNull()) { msg_error() << "Invalid vOp operation: the result vector is null"; return; }                               \
+        void* pr = b200_vec(this, r, true);                                                                                          \
+        const void* pa = a == core::ConstVecId(r) ? pr : b200_vec(this, a, false);                                                   \
+        const void* pb = b == core::ConstVecId(r) ? pr : b200_vec(this, b, false);                                                   \
         if (sofab200_mo_vop(sofa::b200::threadContext(), B200Vec3Types<TReal>::abiReal, this->getSize(), pr, pa, pb, k) != SOFAB200_OK) \
             msg_error() << sofab200_last_error();                                                                                    \
     }                                                                                                                                \
     template <> SReal MechanicalObject<B200Vec3Types<TReal>>::vDot(const core::ExecParams*, core::ConstVecId a, core::ConstVecId b) { \
         double r = 0.0;                                                                                                              \
-        const void* pa = this->read(core::ConstVecDerivId(a))->getValue().deviceRead();                                              \
-        const void* pb = this->read(core::ConstVecDerivId(b))->getValue().deviceRead();                                              \
-        sofab200_mo_vdot(sofa::b200::threadContext(), B200Vec3Types<TReal>::abiReal, this->getSize(), pa, pb, &r);                   \
+        if (sofab200_mo_vdot(sofa::b200::threadContext(), B200Vec3Types<TReal>::abiReal, this->getSize(), b200_vec(this, a, false),  \
+                             b200_vec(this, b, false), &r) != SOFAB200_OK)                                                           \
+            msg_error() << sofab200_last_error();                                                                                    \
         return r;                                                                                                                    \
+    }                                                                                                                                \
+    template <> void MechanicalObject<B200Vec3Types<TReal>>::vMultiOp(const core::ExecParams* params, const VMultiOp& ops) {        \
+        /* the integration of EulerImplicitSolver (EulerImplicitSolver.cpp:259-284): v += a*f ; x += v*h -> ONE kernel; anything else   \
+           takes the reference's own fallback, a sequence of vOp (BaseMechanicalState.cpp:42-79) */                                  \
+        if (ops.size() == 2 && ops[0].second.size() == 2 && ops[1].second.size() == 2) {                                             \
+            const core::VecId v = ops[0].first.getId(this), x = ops[1].first.getId(this);                                            \
+            const core::ConstVecId v0 = ops[0].second[0].first.getId(this), a = ops[0].second[1].first.getId(this);                  \
+            const core::ConstVecId x0 = ops[1].second[0].first.getId(this), v1 = ops[1].second[1].first.getId(this);                 \
+            if (v0 == core::ConstVecId(v) && x0 == core::ConstVecId(x) && v1 == core::ConstVecId(v) && ops[0].second[0].second == 1.0 && \
+                ops[1].second[0].second == 1.0 && v.type == core::V_DERIV && x.type == core::V_COORD && a.type == core::V_DERIV) {   \
+                if (sofab200_mo_vmultiop_integrate(sofa::b200::threadContext(), B200Vec3Types<TReal>::abiReal, this->getSize(), b200_vec(this, v, true), \
+                                                   b200_vec(this, x, true), b200_vec(this, a, false), ops[0].second[1].second,      \
+                                                   ops[1].second[1].second) != SOFAB200_OK)                                          \
+                    msg_error() << sofab200_last_error();                                                                            \
+                return;                                                                                                              \
+            }                                                                                                                        \
+        }                                                                                                                            \
+        core::behavior::BaseMechanicalState::vMultiOp(params, ops);                                                                  \
+    }                                                                                                                                \
+    template <> void MechanicalObject<B200Vec3Types<TReal>>::resetForce(const core::ExecParams*, core::VecDerivId f) {              \
+        /* resetDataTypeVec of the force vector (MechanicalObject.inl:2497-2505) = vOp(f) with null operands */                      \
+        if (sofab200_mo_vop(sofa::b200::threadContext(), B200Vec3Types<TReal>::abiReal, this->getSize(), b200_vec(this, core::ConstVecId(f), true), \
+                            nullptr, nullptr, 0.0) != SOFAB200_OK)                                                                   \
+            msg_error() << sofab200_last_error();                                                                                    \
     }
 B200_MO(float)
 B200_MO(double)
@@ -40,36 +71,11 @@ template class MechanicalObject<sofa::b200::B200Vec3fTypes>;
 template class MechanicalObject<sofa::b200::B200Vec3dTypes>;
 }  // namespace sofa::component::statecontainer
 
-namespace sofa::component::mass {
-using sofa::b200::B200Vec3Types;
-#define B200_MASS(TReal)                                                                                                             \
-    template <> void DiagonalMass<B200Vec3Types<TReal>>::addMDx(const core::MechanicalParams*, DataVecDeriv& res, const DataVecDeriv& dx, SReal factor) { \
-        auto& r = *res.beginEdit();                                                                                                  \
-        sofab200_mass_add_mdx(sofa::b200::threadContext(), B200Vec3Types<TReal>::abiReal, r.size(), r.deviceWrite(), dx.getValue().deviceRead(), \
-                              d_vertexMass.getValue().deviceRead(), factor);                                                         \
-        res.endEdit();                                                                                                               \
-    }                                                                                                                                \
-    template <> void DiagonalMass<B200Vec3Types<TReal>>::addForce(const core::MechanicalParams*, DataVecDeriv& f, const DataVecCoord&, const DataVecDeriv&) { \
-        if (this->m_separateGravity.getValue()) return;                                                                              \
-        const sofa::type::Vec3d g(this->getContext()->getGravity());                                                                 \
-        auto& ff = *f.beginEdit();                                                                                                   \
-        sofab200_mass_add_force(sofa::b200::threadContext(), B200Vec3Types<TReal>::abiReal, ff.size(), ff.deviceWrite(), d_vertexMass.getValue().deviceRead(), g.ptr()); \
-        f.endEdit();                                                                                                                 \
-    }
-B200_MASS(float)
-B200_MASS(double)
-}  // namespace sofa::component::mass
-
-namespace sofa::component::constraint::projective {
-using sofa::b200::B200Vec3Types;
-#define B200_FIXED(TReal)                                                                                                            \
-    template <> void FixedProjectiveConstraint<B200Vec3Types<TReal>>::projectResponse(const core::MechanicalParams*, DataVecDeriv& resData) { \
-        auto& res = *resData.beginEdit();                                                                                            \
-        const auto& idx = d_indices.getValue(); /* uploaded once into data->indicesDevice by init(), omitted here */                 \
-        sofab200_fixed_project_response(sofa::b200::threadContext(), B200Vec3Types<TReal>::abiReal, res.size(), res.deviceWrite(), idx.size(), \
-                                        data->indicesDevice, d_fixAll.getValue());                                                   \
-        resData.endEdit();                                                                                                           \
-    }
-B200_FIXED(float)
-B200_FIXED(double)
-}  // namespace sofa::component::constraint::projective
+namespace sofa::b200 {
+void registerMechanicalObject(sofa::core::ObjectFactory* factory) {
+    using namespace sofa::component::statecontainer;
+    factory->registerObjects(sofa::core::ObjectRegistrationData("MechanicalObject whose state vectors live in B200 HBM (sofa_b200)")
+                                 .add<MechanicalObject<B200Vec3fTypes>>()
+                                 .add<MechanicalObject<B200Vec3dTypes>>());
+}
+}  // namespace sofa::b200

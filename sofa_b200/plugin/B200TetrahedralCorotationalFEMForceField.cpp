@@ -15,14 +15,14 @@ using sofa::b200::B200Vec3Types;
 
 namespace {
 std::mutex g_mutex;
-std::unordered_map<const void*, sofab200_tetfem*> g_handles;   // entries are dropped in the component's cleanup()
+std::unordered_map<const void*, sofab200_tetfem*> g_handles;   // entries are dropped by the component's destructor
 sofab200_tetfem*& handle(const void* self) { std::lock_guard<std::mutex> l(g_mutex); return g_handles[self]; }
 }  // namespace
 
 #define B200_TETCOROT(TReal)                                                                                                         \
     template <> void TetrahedralCorotationalFEMForceField<B200Vec3Types<TReal>>::reinit() {                                          \
         /* replaces reinit() .inl:122-160: the per-element precomputation runs inside sofab200_tetfem_create */                      \
-        setMethod(d_method.getValue());                                                                                              \
+        { const std::string& m = d_method.getValue(); setMethod(m == "small" ? SMALL : (m == "polar" ? POLAR : LARGE)); }   /* as init() does, .inl:135-147 */ \
         const auto& rest = this->mstate->read(core::vec_id::read_access::restPosition)->getValue();                                  \
         const auto& tetras = this->l_topology->getTetrahedra();                                                                      \
         std::vector<double> young(this->d_youngModulus.getValue().begin(), this->d_youngModulus.getValue().end());                  \
@@ -60,7 +60,8 @@ sofab200_tetfem*& handle(const void* self) { std::lock_guard<std::mutex> l(g_mut
         if (sofab200_tetfem_add_dforce(handle(this), df.deviceWrite(), dx.deviceRead(), k) != SOFAB200_OK) msg_error() << sofab200_last_error(); \
         d_df.endEdit();                                                                                                              \
     }                                                                                                                                \
-    template <> void TetrahedralCorotationalFEMForceField<B200Vec3Types<TReal>>::cleanup() {                                         \
+    /* (the class declares no cleanup(); its destructor is the one member that runs when the component goes away) */              \
+    template <> TetrahedralCorotationalFEMForceField<B200Vec3Types<TReal>>::~TetrahedralCorotationalFEMForceField() {               \
         std::lock_guard<std::mutex> l(g_mutex);                                                                                      \
         auto it = g_handles.find(this);                                                                                              \
         if (it != g_handles.end()) { if (it->second) sofab200_tetfem_destroy(it->second); g_handles.erase(it); }                     \

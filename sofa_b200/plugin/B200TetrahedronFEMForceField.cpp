@@ -6,7 +6,7 @@
 #include <sofa/component/solidmechanics/fem/elastic/TetrahedronFEMForceField.inl>
 #include <sofa/core/ObjectFactory.h>
 
-#include "B200Types.h"
+#include "B200Handles.h"
 
 namespace sofa::component::solidmechanics::fem::elastic {
 using sofa::b200::B200Vec3Types;
@@ -15,7 +15,9 @@ template <class TReal> class TetrahedronFEMForceFieldInternalData<B200Vec3Types<
 public:
     typedef TetrahedronFEMForceField<B200Vec3Types<TReal>> Main;
     sofab200_tetfem* ff = nullptr;
+    sofa::b200::B200Vector<TReal> vmElem, vmNode;   // device-side results of computeVonMisesStress (the Data of the class are host vectors)
     void initPtrData(Main*) {}
+    static sofab200_tetfem* handle(Main* m) { return m->data.ff; }
     ~TetrahedronFEMForceFieldInternalData() { if (ff) sofab200_tetfem_destroy(ff); }
 };
 
@@ -72,10 +74,12 @@ public:
     template <> void TetrahedronFEMForceField<B200Vec3Types<TReal>>::computeVonMisesStress() { /* .inl:2196-2372, values only */   \
         if (!data.ff || !isComputeVonMisesStressMethodSet()) return;                                                                 \
         const VecCoord& x = this->mstate->read(core::vec_id::read_access::position)->getValue();                                     \
-        auto& vME = *d_vonMisesPerElement.beginEdit(); auto& vMN = *d_vonMisesPerNode.beginEdit();                                   \
-        vME.resize(_indexedElements->size()); vMN.resize(x.size());                                                                  \
-        if (sofab200_tetfem_compute_von_mises(data.ff, x.deviceRead(), vME.deviceWrite(), vMN.deviceWrite()) != SOFAB200_OK)         \
+        data.vmElem.resize(_indexedElements->size()); data.vmNode.resize(x.size());                                                  \
+        if (sofab200_tetfem_compute_von_mises(data.ff, x.deviceRead(), data.vmElem.deviceWrite(), data.vmNode.deviceWrite()) != SOFAB200_OK) \
             msg_error() << sofab200_last_error();                                                                                    \
+        auto& vME = *d_vonMisesPerElement.beginEdit(); auto& vMN = *d_vonMisesPerNode.beginEdit();                                   \
+        vME.assign(data.vmElem.hostRead(), data.vmElem.hostRead() + data.vmElem.size());   /* D2H on demand (vector_device) */        \
+        vMN.assign(data.vmNode.hostRead(), data.vmNode.hostRead() + data.vmNode.size());                                             \
         d_vonMisesPerElement.endEdit(); d_vonMisesPerNode.endEdit();                                                                 \
         updateVonMisesStress = false;                                                                                                \
     }                                                                                                                                \
@@ -91,6 +95,9 @@ template class TetrahedronFEMForceField<sofa::b200::B200Vec3dTypes>;
 }  // namespace sofa::component::solidmechanics::fem::elastic
 
 namespace sofa::b200 {
+using namespace sofa::component::solidmechanics::fem::elastic;
+sofab200_tetfem* tetfemHandle(TetrahedronFEMForceField<B200Vec3fTypes>* ff) { return TetrahedronFEMForceFieldInternalData<B200Vec3fTypes>::handle(ff); }
+sofab200_tetfem* tetfemHandle(TetrahedronFEMForceField<B200Vec3dTypes>* ff) { return TetrahedronFEMForceFieldInternalData<B200Vec3dTypes>::handle(ff); }
 void registerTetrahedronFEMForceField(sofa::core::ObjectFactory* factory) {
     using namespace sofa::component::solidmechanics::fem::elastic;
     factory->registerObjects(sofa::core::ObjectRegistrationData("TetrahedronFEMForceField on a B200 GPU (sofa_b200)")

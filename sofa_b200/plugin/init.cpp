@@ -12,6 +12,10 @@ void registerHexahedronFEMForceField(sofa::core::ObjectFactory*);
 void registerTetrahedralCorotationalFEMForceField(sofa::core::ObjectFactory*);
 void registerMeshMatrixMass(sofa::core::ObjectFactory*);
 void registerDiagonalMass(sofa::core::ObjectFactory*);
+void registerUniformMass(sofa::core::ObjectFactory*);
+void registerPlaneForceField(sofa::core::ObjectFactory*);
+void registerEngines(sofa::core::ObjectFactory*);
+void registerIdentityMapping(sofa::core::ObjectFactory*);
 void registerFixedProjectiveConstraint(sofa::core::ObjectFactory*);
 void registerCGLinearSolver(sofa::core::ObjectFactory*);
 }  // namespace sofa::b200
@@ -32,6 +36,10 @@ SOFA_EXPORT_DYNAMIC_LIBRARY void registerObjects(sofa::core::ObjectFactory* fact
     sofa::b200::registerTetrahedralCorotationalFEMForceField(factory);
     sofa::b200::registerMeshMatrixMass(factory);
     sofa::b200::registerDiagonalMass(factory);
+    sofa::b200::registerUniformMass(factory);
+    sofa::b200::registerPlaneForceField(factory);
+    sofa::b200::registerEngines(factory);
+    sofa::b200::registerIdentityMapping(factory);
     sofa::b200::registerFixedProjectiveConstraint(factory);
     sofa::b200::registerCGLinearSolver(factory);
 }
