@@ -36,6 +36,69 @@ def test_c2_force_and_dforce_bit_exact(c2):
     assert df_d.cpu().numpy().tobytes() == s.fem_add_dforce(zero, dx, -0.0011).tobytes()
 
 
+@pytest.mark.parametrize("dtype,method", [(np.float32, "polar"), (np.float32, "svd"), (np.float64, "large"), (np.float64, "polar")])
+def test_c2_other_methods_and_vec3d_bit_exact_at_full_size(dtype, method):
+    """The same at full size for the rotation methods and the precision the headline does not use (Vec3d is SOFA's default build): addForce (with the
+    cached rotations) and addDForce bit-exact on 983 040 tetrahedra -- this also runs the tile counts / slot budgets big meshes get (Vec3d: 3 tiles per SM)."""
+    g = gpu_scene("C2", dtype, method)
+    s = oracle_scene("C2", dtype, method)
+    rng = np.random.default_rng(2)
+    z = g["pos"][:, 2:3]
+    x = (g["pos"] + np.hstack([0.02 * np.sin(z / 3.0), 0.05 * (z / 20.0) ** 2, 0 * z]) + 1e-3 * rng.standard_normal(g["pos"].shape)).astype(dtype)
+    zero = np.zeros_like(x)
+    f_d = dev(g["mo"], zero); g["ff"].addForce(f_d, dev(g["mo"], x))
+    assert f_d.cpu().numpy().tobytes() == s.fem_add_force(zero, x).tobytes()
+    assert g["ff"].get("rotations").tobytes() == s.get("tet.rotations").tobytes()
+    dx = (1e-3 * rng.standard_normal(x.shape)).astype(dtype)
+    df_d = dev(g["mo"], zero); g["ff"].addDForce(df_d, dev(g["mo"], dx), -0.0011)
+    assert df_d.cpu().numpy().tobytes() == s.fem_add_dforce(zero, dx, -0.0011).tobytes()
+    # one whole step from the rest state: f and b bit-identical, the CG kernel (streamed tiles in Vec3d) agrees with the oracle's double-dot CG
+    s.set_dot_double(True)
+    g["node"].step()
+    it = g["node"].last_solve()["iterations"]
+    it_ref = s.step()
+    assert abs(it - it_ref) <= 1
+    assert g["node"].get("f").tobytes() == s.get("f").tobytes()
+    assert g["node"].get("b").tobytes() == s.get("b").tobytes()
+    assert rel_err(g["node"].get("dx"), s.get("sol")) <= (1e-4 if dtype == np.float32 else 1e-9)
+
+
+def test_c3_hexahedra_at_full_size():
+    """BASELINE.json config 3 at full size: 65x65x121 grid, 491 520 hexahedra, method=polar, Vec3f -- addForce / addDForce bit-exact, one whole step with f and b
+    bit-identical and the same CG iteration count."""
+    import sofa_b200 as sb
+    from sofa_b200 import topology as T
+    import oracle_lib as O
+    pos, hexas = T.regular_grid((65, 65, 121), (0, 0, 0), (8, 8, 15))
+    fixed = T.box_roi(pos, (-1, -1, -1, 9, 9, 1e-6))
+    assert hexas.shape[0] == 491520
+    ctx = sb.Context(0)
+    mo = sb.MechanicalObject(ctx, "B200Vec3f", position=pos)
+    ff = sb.HexahedronFEMForceField(mo, hexas, youngModulus=1000.0, poissonRatio=0.3, method="polar")
+    node = sb.SolverNode(mo, ff, sb.DiagonalMass(mo, hexas, massDensity=1.0), sb.FixedProjectiveConstraint(mo, fixed), dt=0.01, gravity=(0.0, -9.0, 0.0),
+                         rayleighStiffness=0.1, rayleighMass=0.1, iterations=25, tolerance=1e-9, threshold=1e-9)
+    s = O.OracleScene(np.float32, pos)
+    s.set_params(gravity=(0.0, -9.0, 0.0), dt=0.01, rayleighStiffness=0.1, rayleighMass=0.1, iterations=25, tolerance=1e-9, threshold=1e-9)
+    s.set_mass_density(1.0, hexas); s.set_hexas(hexas, "polar", 1000.0, 0.3); s.set_fixed(fixed)
+    s.set_threads(8)      # (ParallelHexahedronFEMForceField-style addDForce: the same per-vertex summation order as the sequential class)
+    rng = np.random.default_rng(4)
+    z = pos[:, 2:3]
+    x = (pos + np.hstack([0.02 * np.sin(z / 3.0), 0.05 * (z / 15.0) ** 2, 0 * z]) + 1e-3 * rng.standard_normal(pos.shape)).astype(np.float32)
+    zero = np.zeros_like(x)
+    f_d = dev(mo, zero); ff.addForce(f_d, dev(mo, x))
+    assert f_d.cpu().numpy().tobytes() == s.fem_add_force(zero, x).tobytes()
+    dx = (1e-3 * rng.standard_normal(x.shape)).astype(np.float32)
+    df_d = dev(mo, zero); ff.addDForce(df_d, dev(mo, dx), -0.0011)
+    assert df_d.cpu().numpy().tobytes() == s.fem_add_dforce(zero, dx, -0.0011).tobytes()
+    s.set_dot_double(True)     # (the reference's serial float vDot over 1.5 M entries alone moves dx by 8e-3 here: measured)
+    node.step()
+    it, it_ref = node.last_solve()["iterations"], s.step()
+    assert abs(it - it_ref) <= 1
+    assert node.get("f").tobytes() == s.get("f").tobytes()
+    assert node.get("b").tobytes() == s.get("b").tobytes()
+    assert rel_err(node.get("dx"), s.get("sol")) <= 1e-4
+
+
 def test_c2_operator_properties(c2):
     g, _ = c2
     mo, node = g["mo"], g["node"]
@@ -75,6 +138,15 @@ def test_c2_steps_match_oracle(c2):
         assert node.get("b").tobytes() == s.get("b").tobytes()
         assert rel_err(node.get("dx"), s.get("sol")) <= 5e-3   # serial float vDot over 526k entries in the reference
     assert np.abs(mo.x.cpu().numpy().astype(np.float64) - s.get("x")).max() <= 1e-5
+    # ... and the device CG itself against the oracle with its dot products accumulated in double (the only difference left is the order of the
+    # double sums and the one-step rho prediction of the fused kernel): two more steps, each from that oracle's own state
+    s.set_dot_double(True)
+    for step in range(2):
+        mo.x.copy_(torch.from_numpy(s.get("x"))); mo.v.copy_(torch.from_numpy(s.get("v")))
+        node.step()
+        it_ref = s.step()
+        assert abs(node.last_solve()["iterations"] - it_ref) <= 1
+        assert rel_err(node.get("dx"), s.get("sol")) <= 2e-5, rel_err(node.get("dx"), s.get("sol"))
 
 
 def test_c2_per_node_outputs_and_mesh_mass_properties():
