@@ -636,7 +636,8 @@ template <class R, int NT> __device__ __forceinline__ void fused_finish(const Ti
 // ---- the kernel ----------------------------------------------------------------------------------------------------------------------------
 // Pass: the element type's policy --
 //   typedef Dev;  static const TileDev<R>& tiles(const Dev&);
-//   template <int ET, class OnBoundary> static void elements(const Dev&, int tile, const SV* s_in, R* s_slot, int max_slots, unsigned char* s_extra, int arrive_at, OnBoundary f)
+//   typedef First;  static void prefetch(const Dev&, int tile, First&)   requests what the thread needs for its first element of the tile
+//   template <int ET, class OnBoundary> static void elements(const Dev&, int tile, const SV* s_in, R* s_slot, int max_slots, unsigned char* s_extra, int arrive_at, OnBoundary f, const First&)
 //       one pass over the tile's elements by the ET element threads; calls f() once (from every element thread, at the same trip count) when
 //       the elements [0, arrive_at) are done (arrive_at < 0: never).
 // ET element threads + GT dedicated gather threads (GT may be 0: everybody does everything).  The CTA's units of shared nodes are dealt
@@ -675,6 +676,9 @@ __global__ void __launch_bounds__(ET + GT, 1) fused_cg_kernel(typename Pass::Dev
         const bool elem_thread = threadIdx.x < ET;
         const int warp = threadIdx.x >> 5;
         // this warp's units: lu = lu0, lu0 + lu_step, ... < lu_end
+        // the record of the thread's first element of the CTA's first tile is requested before the phase that precedes the tile
+        typename Pass::First first;
+        if (elem_thread) Pass::prefetch(d, int(blockIdx.x), first);
         const int lu0 = elem_thread ? ded_units + warp : (warp - ET / 32), lu_step = elem_thread ? ET / 32 : GT / 32, lu_end = elem_thread ? n_my_units : ded_units;
         for (;;) {
             const unsigned iter = s_sc.iter;
@@ -708,7 +712,8 @@ __global__ void __launch_bounds__(ET + GT, 1) fused_cg_kernel(typename Pass::Dev
                     Pass::template elements<ET>(d, tile, s_in, s_slot, L.max_slots, s_extra, arrive_at, [&]() {
                         bar_first<ET>();
                         if (threadIdx.x == ET - 32) fused_arrive_s1(a.sync);      // (the last element warp has the shortest tail of the tile)
-                    });
+                    }, first);
+                    if (c + 1 < L.tiles_per_cta && tile + G < t.n_tiles) Pass::prefetch(d, tile + G, first);     // the next tile's, under this tile's interior sums
                     if (arrive_at >= 0) arrived = true;
                     bar_first<ET>();
                     if (last && !arrived) { if (threadIdx.x == ET - 32) fused_arrive_s1(a.sync); arrived = true; }
@@ -842,7 +847,8 @@ __global__ void __launch_bounds__(ET + GT, 1) fused_cg_kernel(typename Pass::Dev
                 s_sc.beta = R(rho_new / rho); s_sc.rho = rho_new; s_sc.it = it2; s_sc.first = 0; s_sc.n_err = n_err; s_sc.n_den = n_den;
             }
             __syncthreads();
-            // ---- local update of x, r (and p unless the solve is over)
+            // ---- local update of x, r (and p unless the solve is over); the next iteration's first element record travels meanwhile
+            if (!stop2 && elem_thread) Pass::prefetch(d, int(blockIdx.x), first);
             fused_update<R, NT, CACHED>(t, a, &s_sc, smem_raw, !stop2);
             updated = true; pending = true;
             if (stop2) break;

@@ -140,8 +140,10 @@ __device__ __forceinline__ void hex_tile_elements(const HexDev<R>& d, int tile, 
 template <class R> struct HexPass {
     typedef HexDev<R> Dev;
     static __device__ __forceinline__ const TileDev<R>& tiles(const Dev& d) { return d.t; }
+    struct First {};
+    static __device__ __forceinline__ void prefetch(const Dev&, int, First&) {}
     template <int ET, class OnBoundary>
-    static __device__ __forceinline__ void elements(const Dev& d, int tile, const typename SVec<R>::T* s_in, R* s_slot, int max_slots, unsigned char* s_extra, int, OnBoundary) {
+    static __device__ __forceinline__ void elements(const Dev& d, int tile, const typename SVec<R>::T* s_in, R* s_slot, int max_slots, unsigned char* s_extra, int, OnBoundary, const First&) {
         hex_tile_elements<R, HM_DF, ET>(d, tile, s_in, s_slot, max_slots, reinterpret_cast<R*>(s_extra));
     }
 };

@@ -244,6 +244,20 @@ template <class R, int MODE> HD void tet_element(const TetDev<R>& d, size_t es, 
 // NTHR: number of threads that share the tile (0: the whole CTA); on_boundary: called by every one of them, at the same trip count, once the
 // elements [0, arrive_at) are done (arrive_at < 0: never).
 struct NoBoundaryCall { __device__ __forceinline__ void operator()() const {} };
+// The records of the FIRST round of a tile (one element per thread): the persistent CG kernel asks the L2 for them before the phase that precedes
+// the tile (interior sums of the previous tile, x/r/p update of the previous iteration), so that the stream does not start from an idle memory
+// system.  L2 prefetches only (no registers held across the phase; holding the record itself made ptxas spill it, which waits for the data).
+struct TetFirst {};
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+template <class R> __device__ __forceinline__ void tet_prefetch_first(const TetDev<R>& d, int tile) {
+    const TileDev<R>& t = d.t;
+    if (int(threadIdx.x) < t.tile_e && (threadIdx.x & 7) == 0) {      // one request per 128-byte line of the 16-byte planes
+        const size_t es = size_t(tile) * t.tile_e + threadIdx.x;
+        prefetch_l2(d.slot + es); prefetch_l2(d.rk0 + es); prefetch_l2(d.rk1 + es); prefetch_l2(d.rk2 + es);
+        prefetch_l2(d.j0 + es); prefetch_l2(d.j1 + es); prefetch_l2(d.j2 + es);
+        if ((threadIdx.x & 15) == 0) prefetch_l2(d.lnode + es);
+    }
+}
 template <class R, int MODE, bool PF, int NTHR = 0, class OnBoundary = NoBoundaryCall>
 __device__ __forceinline__ void tet_tile_elements(const TetDev<R>& d, int tile, const typename SVec<R>::T* s_in, R* s_slot, int max_slots,
                                                   int arrive_at = -1, OnBoundary on_boundary = OnBoundary()) {
@@ -385,8 +399,11 @@ __global__ void __launch_bounds__(MAXT) tet_cg_persistent_kernel(TetDev<R> d, Pe
 template <class R, int MODE, bool PF> struct TetPass {
     typedef TetDev<R> Dev;
     static __device__ __forceinline__ const TileDev<R>& tiles(const Dev& d) { return d.t; }
+    typedef TetFirst First;
+    static __device__ __forceinline__ void prefetch(const Dev& d, int tile, First&) { tet_prefetch_first<R>(d, tile); }
     template <int ET, class OnBoundary>
-    static __device__ __forceinline__ void elements(const Dev& d, int tile, const typename SVec<R>::T* s_in, R* s_slot, int max_slots, unsigned char*, int arrive_at, OnBoundary f) {
+    static __device__ __forceinline__ void elements(const Dev& d, int tile, const typename SVec<R>::T* s_in, R* s_slot, int max_slots, unsigned char*, int arrive_at, OnBoundary f,
+                                                    const First&) {
         tet_tile_elements<R, MODE, PF, ET>(d, tile, s_in, s_slot, max_slots, arrive_at, f);
     }
 };
