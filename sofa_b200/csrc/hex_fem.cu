@@ -19,6 +19,7 @@ template <class R> struct HexFF : sofab200_hexfem {
     HostHex<R> h;
     DevBuf<uint4> lnode, slot_a, slot_b;
     DevBuf<uint32_t> orig, kidx, tile_kuniq;
+    bool coop = true;      // addDForce: eight lanes per hexahedron
     DevBuf<Quad<R>> r0, r1, r2, x0;
     DevBuf<R> ktab;
     DevBuf<uint32_t> tile_node_off, tile_nodes, tile_shslot, tile_nint, sh_nodes, sh_base;
@@ -59,7 +60,19 @@ template <class R> static int hex_upload(HexFF<R>& ff) {
     return SOFAB200_OK;
 }
 
+// addDForce with eight lanes per hexahedron (hex_tile_df_coop_kernel); SOFAB200_HEX_COOP=0 selects the one-thread-per-hexahedron pass
+template <class R> static int hex_launch_df_coop(HexFF<R>& ff, const HexDev<R>& d, const R* in, const NodeEpilogue<R>& ep) {
+    auto kern = hex_tile_df_coop_kernel<R>;
+    if (ff.h.smem_bytes > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ff.h.smem_bytes)));
+    ff.ctx->prof_start(0);
+    kern<<<ff.h.plan.n_tiles, 256, ff.h.smem_bytes, ff.ctx->stream>>>(d, in, ep, ff.h.plan.max_touched, ff.h.plan.max_slots);
+    ff.ctx->prof_stop(0);
+    ff.ctx->launches++;
+    SB_CUDA(cudaGetLastError());
+    return SOFAB200_OK;
+}
 template <class R, int MODE> static int hex_launch_mode(HexFF<R>& ff, const HexDev<R>& d, const R* in, const NodeEpilogue<R>& ep) {
+    if (MODE == HM_DF && ff.coop && sizeof(R) == 4) return hex_launch_df_coop<R>(ff, d, in, ep);
     auto kern = hex_tile_kernel<R, MODE>;
     // (per device and context, not per thread: set for the current device on every launch)
     if (ff.h.smem_bytes > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ff.h.smem_bytes)));
@@ -109,7 +122,8 @@ template <class R> int hex_cg_persistent(sofab200_hexfem* base, R k_factor, Pers
 }
 // fused CG kernel (cg_fused.cuh) around the hexahedral element pass: cached when the CTA's tiles fit, else streamed (any number of tiles)
 template <class R, bool CACHED> static int hex_fused_launch(HexFF<R>& ff, HexDev<R> d, FusedCG<R> a, const FusedLayout& L, int grid, bool dry_run, int* info) {
-    auto kern = fused_cg_kernel<R, HexPass<R>, 256, 0, CACHED>;
+    constexpr int ET = sizeof(R) == 4 ? 512 : 256;     // eight lanes per hexahedron at <= 128 registers (Vec3f); Vec3d needs 255
+    auto kern = fused_cg_kernel<R, HexPass<R>, ET, 0, CACHED>;
     cudaFuncAttributes fa;
     SB_CUDA(cudaFuncGetAttributes(&fa, kern));
     int dev_smem_optin = 0;
@@ -117,15 +131,15 @@ template <class R, bool CACHED> static int hex_fused_launch(HexFF<R>& ff, HexDev
     if (L.total + fa.sharedSizeBytes > size_t(dev_smem_optin)) return kPersistNotEligible;
     SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<unsigned>(L.total, 1024))));
     int per_sm = 0;
-    SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, L.total));
+    SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ET, L.total));
     if (per_sm < 1) return kPersistNotEligible;
-    if (info) { info[0] = grid; info[1] = L.tiles_per_cta; info[2] = L.cached; info[3] = int(L.total); info[4] = 256; info[5] = 0; }
+    if (info) { info[0] = grid; info[1] = L.tiles_per_cta; info[2] = L.cached; info[3] = int(L.total); info[4] = ET; info[5] = 0; }
     if (dry_run) return SOFAB200_OK;
     a.lay = L;
     int ded_share = 0;
     void* args[] = {&d, &a, &ded_share};
     ff.ctx->prof_start(4);
-    SB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(256), args, L.total, ff.ctx->stream));
+    SB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(ET), args, L.total, ff.ctx->stream));
     ff.ctx->prof_stop(4);
     ff.ctx->launches++;
     return SOFAB200_OK;
@@ -140,15 +154,16 @@ template <class R> int hex_cg_fused(sofab200_hexfem* base, R k_factor, FusedCG<R
     const int n_units = P.n_chunks * (kGatherChunk / kUnit);
     const int units_per_cta = (n_units + grid - 1) / grid;
     if (fused_sync_words(grid) > sync_capacity) return fail(SOFAB200_ERR_INVALID, "sync buffer too small for the fused CG kernel");
-    const size_t extra = sizeof(R) * 576 * kHexSmemMatrices;
+    const size_t extra = sizeof(R) * kHexKPadded * kHexSmemMatrices;
     const FusedLayout Lc = fused_layout<R>(true, tiles_per_cta, units_per_cta, P.max_touched, P.max_slots, P.max_int, P.max_shtouch, P.maxval, extra);
     if (tiles_per_cta <= 2 && Lc.total + 2048 <= 200 * 1024) {
         const int rc = hex_fused_launch<R, true>(ff, d, a, Lc, grid, dry_run, info);
         if (rc != kPersistNotEligible) return rc;
     }
     // streamed tiles: measured on C3 (491 520 hexahedra, 4 tiles per CTA) the one-thread-per-hexahedron pass at 255 registers runs slower inside the
-    // persistent kernel (3.44 ms per step) than as plain tile launches (2.52 ms), so big hexahedral meshes keep the multi-kernel loop unless asked
-    if (!getenv("SOFAB200_HEX_FUSED_STREAMED")) return kPersistNotEligible;
+    // persistent kernel (3.44 ms per step; 4.62 ms with the eight-lane pass, which spills next to the kernel's other phases) than as plain tile launches
+    // (2.30 ms), so big hexahedral meshes keep the multi-kernel loop unless asked (SOFAB200_HEX_FUSED_STREAMED=1)
+    { const char* env = getenv("SOFAB200_HEX_FUSED_STREAMED"); if (!env || atoi(env) == 0) return kPersistNotEligible; }
     const FusedLayout Ls = fused_layout<R>(false, tiles_per_cta, units_per_cta, P.max_touched, P.max_slots, P.max_int, P.max_shtouch, P.maxval, extra);
     return hex_fused_launch<R, false>(ff, d, a, Ls, grid, dry_run, info);
 }
@@ -209,6 +224,7 @@ template <class R> static int hex_create(sofab200_ctx* ctx, size_t n_nodes, cons
                                          const sofab200_hexfem_desc* desc, sofab200_hexfem** out) {
     std::unique_ptr<HexFF<R>> ff(new HexFF<R>());
     ff->ctx = ctx; ff->real = sizeof(R) == 4 ? SOFAB200_F32 : SOFAB200_F64; ff->method = desc->method;
+    if (const char* env = getenv("SOFAB200_HEX_COOP")) ff->coop = atoi(env) != 0;
     ff->n_nodes = n_nodes; ff->n_hexas = n_hexas;
     const std::string err = hex_host_build(ff->h, n_nodes, static_cast<const R*>(rest), n_hexas, hexas, desc, kGatherChunk, ctx->sm_count);
     if (!err.empty()) return fail(SOFAB200_ERR_INVALID, err);

@@ -12,6 +12,9 @@ namespace sb {
 
 enum HexMode { HM_DF = 0, HM_F_SMALL = 1, HM_F_LARGE = 2, HM_F_POLAR = 3 };
 constexpr int kHexSmemMatrices = 4;   // unique K_e cached per CTA in shared memory
+constexpr int kHexKStride = 28;       // row stride of a cached K_e in the cooperative kernel: 24 padded to 28 floats, so that the eight lanes of a hexahedron
+                                      // (rows 3w..3w+2, 84w floats apart) hit eight different 16-byte bank groups
+constexpr int kHexKPadded = 24 * kHexKStride;
 
 template <class R> struct HexDev {
     TileDev<R> t;
@@ -102,7 +105,7 @@ template <class R, int MODE> HD void hex_element(const HexDev<R>& d, size_t es, 
 template <class R> __host__ __device__ inline size_t hex_smem_bytes(int max_touched, int max_slots) {
     size_t a = tile_smem_bytes<R>(max_touched, max_slots);
     a = (a + 15) & ~size_t(15);
-    return a + sizeof(R) * 576 * kHexSmemMatrices;
+    return a + sizeof(R) * kHexKPadded * kHexSmemMatrices;
 }
 
 // phase 2 of a tile: one thread per hexahedron, 8 corner contributions scattered to their slots.  The tile's (few) distinct
@@ -136,6 +139,7 @@ __device__ __forceinline__ void hex_tile_elements(const HexDev<R>& d, int tile, 
         for (int w = 0; w < 8; ++w) tile_scatter<R>(t, s8[w], C[w].x, C[w].y, C[w].z, s_slot, max_slots, pol_keep);
     }
 }
+template <class R, int NTHR> __device__ __forceinline__ void hex_coop_elements(const HexDev<R>& d, int tile, const typename SVec<R>::T* s_in, R* s_slot, int max_slots, R* s_k);
 // element policy of the fused CG kernel (cg_fused.cuh); the plan does not order a tile's elements that feed shared nodes first (arrive_at < 0)
 template <class R> struct HexPass {
     typedef HexDev<R> Dev;
@@ -144,7 +148,8 @@ template <class R> struct HexPass {
     static __device__ __forceinline__ void prefetch(const Dev&, int, First&) {}
     template <int ET, class OnBoundary>
     static __device__ __forceinline__ void elements(const Dev& d, int tile, const typename SVec<R>::T* s_in, R* s_slot, int max_slots, unsigned char* s_extra, int, OnBoundary, const First&) {
-        hex_tile_elements<R, HM_DF, ET>(d, tile, s_in, s_slot, max_slots, reinterpret_cast<R*>(s_extra));
+        if (sizeof(R) == 4) hex_coop_elements<R, ET>(d, tile, s_in, s_slot, max_slots, reinterpret_cast<R*>(s_extra));      // eight lanes per hexahedron
+        else hex_tile_elements<R, HM_DF, ET>(d, tile, s_in, s_slot, max_slots, reinterpret_cast<R*>(s_extra));           // Vec3d: one thread per hexahedron (the 24 + 72 doubles of the cooperative pass spill)
     }
 };
 
@@ -165,6 +170,120 @@ __global__ void __launch_bounds__(256) hex_tile_kernel(HexDev<R> d, const R* __r
     const int tile = blockIdx.x;
     tile_phase1<R>(t, tile, in, s_in, s_jds);   // ends with __syncthreads()
     hex_tile_elements<R, MODE>(d, tile, s_in, s_slot, max_slots, s_k);
+    __syncthreads();
+    const double part = tile_phase3<R>(t, tile, ep, s_in, s_slot, max_slots, s_jds);
+    if (ep.dot_kind != DOT_NONE) {
+        const double tot = block_sum(part, red);
+        finish_dot(ep, tot, red, false);
+    }
+}
+
+// phase 2 of a tile with eight lanes per hexahedron (see hex_tile_df_coop_kernel); NTHR as in hex_tile_elements.  s_k: kHexSmemMatrices padded matrices.
+template <class R, int NTHR>
+__device__ __forceinline__ void hex_coop_elements(const HexDev<R>& d, int tile, const typename SVec<R>::T* s_in, R* s_slot, int max_slots, R* s_k) {
+    typedef typename SVec<R>::T SV;
+    const TileDev<R>& t = d.t;
+    const int nthr = NTHR > 0 ? NTHR : int(blockDim.x);
+    const uint32_t* ku = d.tile_kuniq + size_t(tile) * (kHexSmemMatrices + 1);
+    const int n_ku = int(ku[0]);
+    for (int i = threadIdx.x; i < n_ku * 576; i += nthr) {
+        const int m = i / 576, rc = i % 576;
+        s_k[m * kHexKPadded + (rc / 24) * kHexKStride + rc % 24] = d.ktab[size_t(ku[1 + m]) * 576 + rc];
+    }
+    if (NTHR > 0) bar_first<(NTHR > 0 ? NTHR : 32)>(); else __syncthreads();
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    const int w = threadIdx.x & 7, grp = threadIdx.x >> 3, ngrp = nthr >> 3;
+    const int gbase = (threadIdx.x & 31) & ~7;           // first lane of the group inside its warp
+    // One element, lane w of its group.  KREG: the tile refers to ONE stiffness matrix (every tile of a regular grid) and the lane keeps its three
+    // rows in registers for the whole tile -- no shared-memory traffic for K_e at all; otherwise the rows come from the padded shared-memory copy
+    // (16-byte loads) or from HBM.
+    // what a lane reads from HBM for one element; requested one element ahead (the loop is bound by the latency of these loads otherwise: ncu showed
+    // long-scoreboard stalls of 4.5 per issue with 16 warps per SM)
+    struct Rec { unsigned lid, slot; Quad<R> q0, q1, q2; uint32_t ki; };
+    auto load = [&](int le) {
+        Rec r;
+        const size_t es = size_t(tile) * t.tile_e + le;
+        r.lid = reinterpret_cast<const uint16_t*>(d.lnode + es)[w];
+        r.slot = w < 4 ? reinterpret_cast<const uint32_t*>(d.slot_a + es)[w] : reinterpret_cast<const uint32_t*>(d.slot_b + es)[w - 4];
+        r.q0 = rec_load(d.r0 + es, pol_stream); r.q1 = rec_load(d.r1 + es, pol_stream); r.q2 = rec_load(d.r2 + es, pol_stream);
+        r.ki = d.kidx[es];
+        return r;
+    };
+    auto element = [&](const Rec& r, auto row_value) {
+        const bool valid = __shfl_sync(0xffffffffu, r.lid, gbase) != 0xFFFFu;       // (a padding element has 0xFFFF in its first corner)
+        M3<R> rot;
+        rot.m[0][0] = r.q0.a; rot.m[0][1] = r.q0.b; rot.m[0][2] = r.q0.c; rot.m[1][0] = r.q0.d; rot.m[1][1] = r.q1.a; rot.m[1][2] = r.q1.b;
+        rot.m[2][0] = r.q1.c; rot.m[2][1] = r.q1.d; rot.m[2][2] = r.q2.a;
+        SV pv = SVec<R>::make(R(0), R(0), R(0));
+        if (valid) pv = s_in[r.lid];
+        const V3<R> x2 = mul(rot, mk3<R>(pv.x, pv.y, pv.z));                      // const Coord x_2 = _rotations[i] * dx[elem[w]]
+        R D[24];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            D[3 * j] = __shfl_sync(0xffffffffu, x2.x, gbase + j); D[3 * j + 1] = __shfl_sync(0xffffffffu, x2.y, gbase + j); D[3 * j + 2] = __shfl_sync(0xffffffffu, x2.z, gbase + j);
+        }
+        R F[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            R s = row_value(c, 0) * D[0];
+#pragma unroll
+            for (int j = 1; j < 24; ++j) s += row_value(c, j) * D[j];
+            F[c] = s;
+        }
+        const V3<R> C = mul_t(rot, mk3<R>(F[0], F[1], F[2])) * d.k_factor;       // _rotations[i].multTranspose(F_w) * kFactor
+        if (valid) tile_scatter<R>(t, r.slot, C.x, C.y, C.z, s_slot, max_slots, pol_keep);
+    };
+    // tile_e is a multiple of 32 and a warp holds four consecutive groups: the loop condition is uniform inside a warp (full-mask shuffles are safe)
+    if (n_ku == 1) {
+        R kr[3][24];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int j = 0; j < 24; ++j) kr[c][j] = s_k[(3 * w + c) * kHexKStride + j];
+        int le = grp;
+        Rec cur;
+        if (le < t.tile_e) cur = load(le);
+        while (le < t.tile_e) {
+            const int nle = le + ngrp;
+            Rec nxt = cur;
+            if (nle < t.tile_e) nxt = load(nle);
+            element(cur, [&](int c, int j) { return kr[c][j]; });
+            cur = nxt; le = nle;
+        }
+    } else {
+        for (int le = grp; le < t.tile_e; le += ngrp) {
+            const Rec r = load(le);
+            int u_hit = -1;
+            for (int u = 0; u < n_ku; ++u) if (ku[1 + u] == r.ki) u_hit = u;
+            if (u_hit >= 0) { const R* Ks = s_k + kHexKPadded * u_hit + 3 * w * kHexKStride; element(r, [&](int c, int j) { return Ks[c * kHexKStride + j]; }); }
+            else { const R* Kg = d.ktab + size_t(r.ki) * 576 + 3 * w * 24; element(r, [&](int c, int j) { return Kg[c * 24 + j]; }); }
+        }
+    }
+}
+
+// ---- addDForce, eight lanes per hexahedron -------------------------------------------------------------------------------------------
+// The one-thread-per-hexahedron pass needs 255 registers (24 + 24 element values, 8 nodal vectors, the rotation), i.e. 8 warps per SM, and is
+// issue-bound at a third of the fp32 rate.  Here lane w of a group of eight owns node w: it rotates its nodal vector (D_w = R p_w), the group
+// exchanges the 24 values with shuffles, the lane forms rows 3w..3w+2 of F = K_e D -- each row the same left-to-right sum of 24 products as
+// HexahedronFEMForceField.inl:711-715, so every bit of the result is the reference's -- rotates back and scatters its own corner.  When the tile refers to ONE matrix (every tile of a regular grid) the lane keeps its three
+// rows of K_e in registers for the whole tile: two 256-thread CTAs per SM at ~128 registers (16 warps), no shared-memory traffic for K_e.  Otherwise
+// the rows are read from the padded shared-memory copy, or from HBM when the tile refers to more than kHexSmemMatrices distinct matrices.
+template <class R>
+__global__ void __launch_bounds__(256, sizeof(R) == 4 ? 2 : 1) hex_tile_df_coop_kernel(HexDev<R> d, const R* __restrict__ in, NodeEpilogue<R> ep, int max_touched, int max_slots) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[32];
+    __shared__ uint16_t s_jds[1024];
+    typedef typename SVec<R>::T SV;
+    if (ep.cg && ep.cg->done) return;
+    SV* s_in = reinterpret_cast<SV*>(smem_raw);
+    size_t off = (sizeof(SV) * size_t(max_touched) + 15) & ~size_t(15);
+    R* s_slot = reinterpret_cast<R*>(smem_raw + off);
+    off = (off + sizeof(R) * 3 * size_t(max_slots) + 15) & ~size_t(15);
+    R* s_k = reinterpret_cast<R*>(smem_raw + off);   // kHexSmemMatrices x 24 x kHexKStride
+    const TileDev<R>& t = d.t;
+    const int tile = blockIdx.x;
+    tile_phase1<R>(t, tile, in, s_in, s_jds);   // ends with __syncthreads()
+    hex_coop_elements<R, 0>(d, tile, s_in, s_slot, max_slots, s_k);
     __syncthreads();
     const double part = tile_phase3<R>(t, tile, ep, s_in, s_slot, max_slots, s_jds);
     if (ep.dot_kind != DOT_NONE) {
