@@ -163,8 +163,9 @@ typedef struct sofab200_tetfem_desc {
     double plastic_yield_threshold; /* Data `plasticYieldThreshold` (reference default 0.0001)                                  */
     double plastic_creep;           /* Data `plasticCreep` (reference default 0.9)                                              */
     int update_stiffness_matrix;    /* Data `updateStiffnessMatrix`: addForce recomputes the strain-displacement terms from the deformed element every
-                                     * step ([TFF].inl:1063-1067,1174-1177).  polar / svd only: with `large` the reference rewrites 9 single entries of J
-                                     * ([TFF].inl:908-922), which the 12-cofactor layout cannot hold -> SOFAB200_ERR_UNSUPPORTED; ignored by `small` */
+                                     * step ([TFF].inl:1063-1067,1174-1177).  With `large` the reference rewrites 9 single entries of J, all in its
+                                     * normal-strain columns ([TFF].inl:908-922): the element then carries a second set of 12 cofactors for the shear
+                                     * columns, and the CG loop runs as separate kernels (not the persistent one).  Ignored by `small`. */
     int tetrahedral_corotational;   /* 1: the component is a TetrahedralCorotationalFEMForceField (…/fem/elastic/TetrahedralCorotationalFEMForceField.inl,
                                      * what Demos/liver.scn uses): its init, accumulateForce{Small,Large,Polar}, applyStiffness* and computeForce
                                      * (:356-398,400-602,604-743,840-1044,1046-1175) are statement for statement those of TetrahedronFEMForceField, so the

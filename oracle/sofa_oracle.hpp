@@ -485,7 +485,10 @@ template <class R> struct TetFEM {
     std::vector<uint32_t> rotationIdx;    // _rotationIdx
     bool tetrahedralCorotational = false; // the sibling class TetrahedralCorotationalFEMForceField (same statements, TetrahedralCorotationalFEMForceField.inl:356-1175): only its
                                           // accumulateForceLarge differs, by rewriting all three copies of a cofactor under updateStiffnessMatrix (:920-937)
-    bool updateStiffnessMatrix = false;   // d_updateStiffnessMatrix (restated for polar / svd only; `large` rewrites single J entries, :908-922)
+    bool updateStiffnessMatrix = false;   // d_updateStiffnessMatrix: polar / svd recompute the whole strain-displacement matrix (:1063-1067, :1174-1177); `large` rewrites nine
+                                          // single entries, all in the normal-strain columns J(.,0..2) (:908-922), so the copies of the same cofactors in the shear columns
+                                          // J(.,3..5) keep their initial values: J holds the normal-column copies, Jsh the shear-column copies (equal until that happens)
+    std::vector<R> Jsh;
     std::vector<R> plasticStrains;        // _plasticStrains: 6 Voigt components per element
     R plastic[3] = {R(0), R(0.0001f), R(0.9f)};  // d_plasticMaxThreshold, d_plasticYieldThreshold, d_plasticCreep (defaults :51-53)
     R* plasticPtr(size_t e) { return plastic[0] > 0 ? &plasticStrains[6 * e] : nullptr; }
@@ -612,20 +615,21 @@ template <class R> struct TetFEM {
             case SVD:   initPolarLike(i, a, b, c, d, true); break;
             }
         }
+        Jsh = J;
     }
 
     // computeForce :293-415 (plasticity off) and :417-521 (with `fact`); useFact selects `KJtD *= fact`.
     // plasticStrain / plastic = {max, yield, creep}: the plasticity branch :357-371 (only when d_plasticMaxThreshold > 0)
-    static void computeForce(R F[12], const R D[12], const R* k, const R* j, bool useFact, SReal fact, R* plasticStrain = nullptr, const R* plastic = nullptr) {
-        // J(3n,0)=j[3n] J(3n+1,1)=j[3n+1] J(3n+2,2)=j[3n+2]; J(3n,3)=j[3n+1] J(3n+1,3)=j[3n];
-        // J(3n+1,4)=j[3n+2] J(3n+2,4)=j[3n+1]; J(3n,5)=j[3n+2] J(3n+2,5)=j[3n]
+    static void computeForce(R F[12], const R D[12], const R* k, const R* j, const R* js, bool useFact, SReal fact, R* plasticStrain = nullptr, const R* plastic = nullptr) {
+        // J(3n,0)=j[3n] J(3n+1,1)=j[3n+1] J(3n+2,2)=j[3n+2]; J(3n,3)=js[3n+1] J(3n+1,3)=js[3n];
+        // J(3n+1,4)=js[3n+2] J(3n+2,4)=js[3n+1]; J(3n,5)=js[3n+2] J(3n+2,5)=js[3n]
         R JtD[6];
         JtD[0] = j[0] * D[0] + j[3] * D[3] + j[6] * D[6] + j[9] * D[9];
         JtD[1] = j[1] * D[1] + j[4] * D[4] + j[7] * D[7] + j[10] * D[10];
         JtD[2] = j[2] * D[2] + j[5] * D[5] + j[8] * D[8] + j[11] * D[11];
-        JtD[3] = j[1] * D[0] + j[0] * D[1] + j[4] * D[3] + j[3] * D[4] + j[7] * D[6] + j[6] * D[7] + j[10] * D[9] + j[9] * D[10];
-        JtD[4] = j[2] * D[1] + j[1] * D[2] + j[5] * D[4] + j[4] * D[5] + j[8] * D[7] + j[7] * D[8] + j[11] * D[10] + j[10] * D[11];
-        JtD[5] = j[2] * D[0] + j[0] * D[2] + j[5] * D[3] + j[3] * D[5] + j[8] * D[6] + j[6] * D[8] + j[11] * D[9] + j[9] * D[11];
+        JtD[3] = js[1] * D[0] + js[0] * D[1] + js[4] * D[3] + js[3] * D[4] + js[7] * D[6] + js[6] * D[7] + js[10] * D[9] + js[9] * D[10];
+        JtD[4] = js[2] * D[1] + js[1] * D[2] + js[5] * D[4] + js[4] * D[5] + js[8] * D[7] + js[7] * D[8] + js[11] * D[10] + js[10] * D[11];
+        JtD[5] = js[2] * D[0] + js[0] * D[2] + js[5] * D[3] + js[3] * D[5] + js[8] * D[6] + js[6] * D[8] + js[11] * D[9] + js[9] * D[11];
         if (plasticStrain && plastic[0] > 0) {
             R elasticStrain[6];
             for (int i = 0; i < 6; ++i) elasticStrain[i] = JtD[i] - plasticStrain[i];           // VoigtTensor elasticStrain = JtD; elasticStrain -= plasticStrain
@@ -649,10 +653,10 @@ template <class R> struct TetFEM {
         KJtD[5] = k[2] * JtD[5];
         if (useFact) { const R f = R(fact); for (int i = 0; i < 6; ++i) KJtD[i] *= f; }
         for (int n = 0; n < 4; ++n) {
-            const R jx = j[3 * n], jy = j[3 * n + 1], jz = j[3 * n + 2];
-            F[3 * n + 0] = jx * KJtD[0] + jy * KJtD[3] + jz * KJtD[5];
-            F[3 * n + 1] = jy * KJtD[1] + jx * KJtD[3] + jz * KJtD[4];
-            F[3 * n + 2] = jz * KJtD[2] + jy * KJtD[4] + jx * KJtD[5];
+            const R jx = j[3 * n], jy = j[3 * n + 1], jz = j[3 * n + 2], sx = js[3 * n], sy = js[3 * n + 1], sz = js[3 * n + 2];
+            F[3 * n + 0] = jx * KJtD[0] + sy * KJtD[3] + sz * KJtD[5];
+            F[3 * n + 1] = jy * KJtD[1] + sx * KJtD[3] + sz * KJtD[4];
+            F[3 * n + 2] = jz * KJtD[2] + sy * KJtD[4] + sx * KJtD[5];
         }
     }
 
@@ -665,7 +669,7 @@ template <class R> struct TetFEM {
         for (int n = 0; n < 3; ++n) for (int k = 0; k < 3; ++k)
             D[3 * (n + 1) + k] = ip[idx[n]][k] - ip[a][k] - p[idx[n]][k] + p[a][k];
         R F[12];
-        computeForce(F, D, &K[3 * e], &J[12 * e], false, 0, plasticPtr(e), plastic);
+        computeForce(F, D, &K[3 * e], &J[12 * e], &Jsh[12 * e], false, 0, plasticPtr(e), plastic);
         f[a] += Coord(F[0], F[1], F[2]); f[b] += Coord(F[3], F[4], F[5]);
         f[c] += Coord(F[6], F[7], F[8]); f[d] += Coord(F[9], F[10], F[11]);
     }
@@ -686,7 +690,7 @@ template <class R> struct TetFEM {
         D[3] = x0[1][0] - deforme[1][0]; D[4] = 0; D[5] = 0;
         D[6] = x0[2][0] - deforme[2][0]; D[7] = x0[2][1] - deforme[2][1]; D[8] = 0;
         D[9] = x0[3][0] - deforme[3][0]; D[10] = x0[3][1] - deforme[3][1]; D[11] = x0[3][2] - deforme[3][2];
-        if (updateStiffnessMatrix && tetrahedralCorotational) {   // TetrahedralCorotationalFEMForceField.inl:920-937 (jx_n = j[3n], jy_n = j[3n+1], jz_n = j[3n+2])
+        if (updateStiffnessMatrix) {   // TetrahedronFEMForceField.inl:908-922: J(0,0) J(1,1) J(2,2) J(3,0) J(4,1) J(5,2) J(7,1) J(8,2) J(11,2) (jx_n = j[3n], jy_n = j[3n+1], jz_n = j[3n+2])
             R* j = &J[12 * e];
             j[0] = ( - deforme[2][1]*deforme[3][2] );
             j[1] = ( deforme[2][0]*deforme[3][2] - deforme[1][0]*deforme[3][2] );
@@ -697,9 +701,11 @@ template <class R> struct TetFEM {
             j[7] = ( deforme[1][0]*deforme[3][2] );
             j[8] = ( - deforme[1][0]*deforme[3][1] );
             j[11] = ( deforme[1][0]*deforme[2][1] );
+            if (tetrahedralCorotational)   // TetrahedralCorotationalFEMForceField.inl:920-937 assigns all three copies of each of the nine cofactors
+                for (int q : {0, 1, 2, 3, 4, 5, 7, 8, 11}) Jsh[12 * e + q] = j[q];
         }
         R F[12];
-        computeForce(F, D, &K[3 * e], &J[12 * e], false, 0, plasticPtr(e), plastic);
+        computeForce(F, D, &K[3 * e], &J[12 * e], &Jsh[12 * e], false, 0, plasticPtr(e), plastic);
         for (int i = 0; i < 12; i += 3) f[index[i / 3]] += rotations[e] * Coord(F[i], F[i + 1], F[i + 2]);
     }
     void accumulateForcePolarLike(VecDeriv<R>& f, const std::vector<Coord>& p, size_t e, bool svd) {  // :1025-1079, :1122-1185
@@ -722,9 +728,12 @@ template <class R> struct TetFEM {
         const Coord* x0 = &X0[4 * e];
         R D[12];
         for (int n = 0; n < 4; ++n) for (int k = 0; k < 3; ++k) D[3 * n + k] = x0[n][k] - deforme[n][k];
-        if (updateStiffnessMatrix) computeStrainDisplacement(&J[12 * e], deforme[0], deforme[1], deforme[2], deforme[3]);   // :1063-1067 / :1174-1177
+        if (updateStiffnessMatrix) {   // :1063-1067 / :1174-1177
+            computeStrainDisplacement(&J[12 * e], deforme[0], deforme[1], deforme[2], deforme[3]);
+            for (int q = 0; q < 12; ++q) Jsh[12 * e + q] = J[12 * e + q];
+        }
         R F[12];
-        computeForce(F, D, &K[3 * e], &J[12 * e], false, 0, plasticPtr(e), plastic);
+        computeForce(F, D, &K[3 * e], &J[12 * e], &Jsh[12 * e], false, 0, plasticPtr(e), plastic);
         for (int i = 0; i < 12; i += 3) f[index[i / 3]] += rotations[e] * Coord(F[i], F[i + 1], F[i + 2]);
     }
     // addForce :1547-1604
@@ -744,7 +753,7 @@ template <class R> struct TetFEM {
         const uint32_t* t = &tets[4 * i];
         R X[12], F[12];
         for (int n = 0; n < 4; ++n) for (int k = 0; k < 3; ++k) X[3 * n + k] = x[t[n]][k];
-        computeForce(F, X, &K[3 * i], &J[12 * i], true, fact);
+        computeForce(F, X, &K[3 * i], &J[12 * i], &Jsh[12 * i], true, fact);
         for (int n = 0; n < 4; ++n) f[t[n]] += Coord(-F[3 * n], -F[3 * n + 1], -F[3 * n + 2]);
     }
     void applyStiffnessCorotational(VecDeriv<R>& f, const VecDeriv<R>& x, size_t i, SReal fact) {  // :1192-1237
@@ -757,7 +766,7 @@ template <class R> struct TetFEM {
             X[3 * n + 1] = rot(0, 1) * xn[0] + rot(1, 1) * xn[1] + rot(2, 1) * xn[2];
             X[3 * n + 2] = rot(0, 2) * xn[0] + rot(1, 2) * xn[1] + rot(2, 2) * xn[2];
         }
-        computeForce(F, X, &K[3 * i], &J[12 * i], true, fact);
+        computeForce(F, X, &K[3 * i], &J[12 * i], &Jsh[12 * i], true, fact);
         for (int n = 0; n < 4; ++n) {
             Coord& fn = f[t[n]];
             fn[0] -= rot(0, 0) * F[3 * n] + rot(0, 1) * F[3 * n + 1] + rot(0, 2) * F[3 * n + 2];

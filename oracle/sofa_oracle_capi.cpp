@@ -266,7 +266,7 @@ size_t orc_scene_get(void* h, const char* what, void* out) {
         else if (w == "tet.initialTransformation") mats(sc.tet.initialTransformation);
         else if (w == "tet.plasticStrains") reals(sc.tet.plasticStrains);
         else if (w == "tet.elemShapeFun") reals(sc.tet.elemShapeFun);
-        else if (w == "tet.J") reals(sc.tet.J); else if (w == "tet.K") reals(sc.tet.K); else if (w == "tet.X0") vec3(sc.tet.X0);
+        else if (w == "tet.J") reals(sc.tet.J); else if (w == "tet.Jsh") reals(sc.tet.Jsh); else if (w == "tet.K") reals(sc.tet.K); else if (w == "tet.X0") vec3(sc.tet.X0);
         else if (w == "hex.rotations") mats(sc.hex.rotations); else if (w == "hex.initialRotations") mats(sc.hex.initialRotations);
         else if (w == "hex.Ke") reals(sc.hex.Ke); else if (w == "hex.X0") vec3(sc.hex.X0); else if (w == "hex.Kmat") reals(sc.hex.Kmat);
     });

@@ -18,11 +18,12 @@ namespace sb {
 template <class R> struct TetFF : sofab200_tetfem {
     HostTet<R> h;
     DevBuf<ushort4> lnode; DevBuf<uint4> slot; DevBuf<uint32_t> orig;
-    DevBuf<Quad<R>> rk0, rk1, rk2, j0, j1, j2, x0a, x0b, x0c, sv0, sv1, sv2, sv3, sv4;
+    DevBuf<Quad<R>> rk0, rk1, rk2, j0, j1, j2, js0, js1, js2, x0a, x0b, x0c, sv0, sv1, sv2, sv3, sv4;
     DevBuf<uint32_t> tile_node_off, tile_nodes, tile_shslot, tile_nint, tile_nb, sh_nodes, sh_base;
     DevBuf<uint16_t> tile_val, tile_jds, sh_val;
     DevBuf<Quad<R>> stage;
-    bool update_j = false;   // updateStiffnessMatrix (polar / svd)
+    bool update_j = false;   // updateStiffnessMatrix: addForce rewrites the cofactor planes
+    bool split_j = false;    // TetrahedronFEMForceField, method large, updateStiffnessMatrix: only the normal-strain copies are rewritten; js0..2 keep the shear copies (TM_*_JS)
     bool sibling = false; DevBuf<R> a0_el;   // TetrahedralCorotationalFEMForceField (its getRotation differs)
     DevBuf<R> vm_shf, vm_lambda, vm_mu, vm_rest, vm_elem; int von_mises = 0;   // computeVonMisesStress (uploaded at the first call)
     DevBuf<Quad<R>> pl0, pl1; double plastic[3] = {0, 0, 0};   // _plasticStrains in tile order (plasticMaxThreshold > 0 only)
@@ -41,6 +42,7 @@ template <class R> struct TetFF : sofab200_tetfem {
         d.rk0 = rk0.p; d.rk1 = rk1.p; d.rk2 = rk2.p; d.j0 = j0.p; d.j1 = j1.p; d.j2 = j2.p;
         d.x0a = x0a.p; d.x0b = x0b.p; d.x0c = x0c.p; d.sv0 = sv0.p; d.sv1 = sv1.p; d.sv2 = sv2.p; d.sv3 = sv3.p; d.sv4 = sv4.p;
         d.k_factor = R(0);
+        d.js0 = js0.p; d.js1 = js1.p; d.js2 = js2.p;
         d.j0w = update_j ? j0.p : nullptr; d.j1w = update_j ? j1.p : nullptr; d.j2w = update_j ? j2.p : nullptr;
         d.pl0 = pl0.p; d.pl1 = pl1.p; d.plastic_max = R(plastic[0]); d.plastic_yield = R(plastic[1]); d.plastic_creep = R(plastic[2]);
         return d;
@@ -54,6 +56,7 @@ template <class R> static int tet_upload(TetFF<R>& ff) {
     SB_TRY(ff.lnode.upload(H.lnode, s)); SB_TRY(ff.slot.upload(H.slot, s)); SB_TRY(ff.orig.upload(P.order, s));
     SB_TRY(ff.rk0.upload(H.rk0, s)); SB_TRY(ff.rk1.upload(H.rk1, s)); SB_TRY(ff.rk2.upload(H.rk2, s));
     SB_TRY(ff.j0.upload(H.j0, s)); SB_TRY(ff.j1.upload(H.j1, s)); SB_TRY(ff.j2.upload(H.j2, s));
+    if (ff.split_j) { SB_TRY(ff.js0.upload(H.j0, s)); SB_TRY(ff.js1.upload(H.j1, s)); SB_TRY(ff.js2.upload(H.j2, s)); }
     SB_TRY(ff.x0a.upload(H.x0a, s)); SB_TRY(ff.x0b.upload(H.x0b, s)); SB_TRY(ff.x0c.upload(H.x0c, s));
     if (H.method == SOFAB200_TET_SVD) {
         SB_TRY(ff.sv0.upload(H.sv[0], s)); SB_TRY(ff.sv1.upload(H.sv[1], s)); SB_TRY(ff.sv2.upload(H.sv[2], s));
@@ -77,7 +80,7 @@ template <class R, int MODE, int MAXT, bool PF> static int tet_launch_variant(Te
     // (the attribute is per device and context, not per thread: set it for the current device on every launch -- a host-side table lookup)
     const size_t smem_total = ff.h.smem_bytes;
     if (smem_total > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_total)));
-    const int cls = (MODE == TM_DF_COROT || MODE == TM_DF_SMALL) ? 0 : 2;
+    const int cls = (MODE == TM_DF_COROT || MODE == TM_DF_SMALL || MODE == TM_DF_COROT_JS) ? 0 : 2;
     ff.ctx->prof_start(cls);
     kern<<<ff.h.plan.n_tiles, ((MODE == TM_DF_COROT || (MODE == TM_F_LARGE && MAXT > 256)) && sizeof(R) == 4) ? std::min(ff.threads, MAXT) : 256, smem_total, ff.ctx->stream>>>(d, in, ep, ff.h.plan.max_touched, ff.h.plan.max_slots);
     ff.ctx->prof_stop(cls);
@@ -135,6 +138,7 @@ template <class R> int tet_cg_persistent(sofab200_tetfem* base, R k_factor, Pers
     TetFF<R>& ff = *static_cast<TetFF<R>*>(base);
     TetDev<R> d = ff.dev();
     d.k_factor = k_factor;
+    if (ff.split_j) return kPersistNotEligible;       // two cofactor sets per element: the multi-kernel loop serves it
     if (ff.method == SOFAB200_TET_SMALL) return tet_persist_variant<R, TM_DF_SMALL, 256, false>(ff, d, a, 256, sync_capacity, dry_run);
     if (sizeof(R) == 8) return tet_persist_variant<R, TM_DF_COROT, 256, false>(ff, d, a, 256, sync_capacity, dry_run);
     if (ff.threads > 256) return tet_persist_variant<R, TM_DF_COROT, 512, true>(ff, d, a, 512, sync_capacity, dry_run);
@@ -191,6 +195,7 @@ template <class R> int tet_cg_fused(sofab200_tetfem* base, R k_factor, FusedCG<R
     TetFF<R>& ff = *static_cast<TetFF<R>*>(base);
     TetDev<R> d = ff.dev();
     d.k_factor = k_factor;
+    if (ff.split_j) return kPersistNotEligible;       // two cofactor sets per element: the multi-kernel loop serves it
     int gw = 0;   // dedicated gather warps
     if (const char* env = getenv("SOFAB200_FUSED_GATHER_WARPS")) gw = atoi(env);
     if (ff.method == SOFAB200_TET_SMALL) return tet_fused_variant<R, TM_DF_SMALL, false, 256, 0>(ff, d, a, sync_capacity, dry_run, info);
@@ -225,11 +230,15 @@ template <class R> int tet_run(sofab200_tetfem* base, bool dforce, const R* in, 
     ep.partial_total = plan.n_tiles + plan.n_chunks;
     if (dforce) {
         if (ff.method == SOFAB200_TET_SMALL) SB_TRY((tet_launch_mode<R, TM_DF_SMALL>(ff, d, in, ep)));
+        else if (ff.split_j) SB_TRY((tet_launch_mode<R, TM_DF_COROT_JS>(ff, d, in, ep)));
         else SB_TRY((tet_launch_mode<R, TM_DF_COROT>(ff, d, in, ep)));
     } else {
         switch (ff.method) {
         case SOFAB200_TET_SMALL: SB_TRY((tet_launch_mode<R, TM_F_SMALL>(ff, d, in, ep))); break;
-        case SOFAB200_TET_LARGE: SB_TRY((tet_launch_mode<R, TM_F_LARGE>(ff, d, in, ep))); break;
+        case SOFAB200_TET_LARGE:
+            if (ff.split_j) SB_TRY((tet_launch_mode<R, TM_F_LARGE_JS>(ff, d, in, ep)));
+            else SB_TRY((tet_launch_mode<R, TM_F_LARGE>(ff, d, in, ep)));
+            break;
         case SOFAB200_TET_POLAR: SB_TRY((tet_launch_mode<R, TM_F_POLAR>(ff, d, in, ep))); break;
         default: SB_TRY((tet_launch_mode<R, TM_F_SVD>(ff, d, in, ep))); break;
         }
@@ -274,7 +283,8 @@ template <class R> static int tet_create(sofab200_ctx* ctx, size_t n_nodes, cons
     if (const char* env = getenv("SOFAB200_PREFETCH")) ff->prefetch = atoi(env) != 0;
     ff->von_mises = desc->compute_von_mises;
     ff->sibling = desc->tetrahedral_corotational != 0;
-    ff->update_j = desc->update_stiffness_matrix != 0 && (desc->method == SOFAB200_TET_POLAR || desc->method == SOFAB200_TET_SVD || (desc->method == SOFAB200_TET_LARGE && desc->tetrahedral_corotational));
+    ff->update_j = desc->update_stiffness_matrix != 0 && desc->method != SOFAB200_TET_SMALL;      // (accumulateForceSmall never reads the flag)
+    ff->split_j = ff->update_j && desc->method == SOFAB200_TET_LARGE && !desc->tetrahedral_corotational;
     ff->plastic[0] = desc->plastic_max_threshold; ff->plastic[1] = desc->plastic_yield_threshold; ff->plastic[2] = desc->plastic_creep;
     SB_TRY(tet_upload(*ff));
     *out = ff.release();
@@ -405,8 +415,6 @@ int sofab200_tetfem_create(sofab200_ctx* ctx, sofab200_real real, size_t n_nodes
         if (desc->plastic_max_threshold > 0 || desc->compute_von_mises)
             return fail(SOFAB200_ERR_UNSUPPORTED, "plasticity and computeVonMisesStress belong to TetrahedronFEMForceField; TetrahedralCorotationalFEMForceField's own von Mises routine is not provided");
     }
-    if (desc->update_stiffness_matrix && desc->method == SOFAB200_TET_LARGE && !desc->tetrahedral_corotational)
-        return fail(SOFAB200_ERR_UNSUPPORTED, "updateStiffnessMatrix with method large rewrites single entries of the strain-displacement matrix (TetrahedronFEMForceField.inl:908-922), which the 12-cofactor element record cannot hold; use polar or svd");
     SB_CHECK(desc->compute_von_mises >= 0 && desc->compute_von_mises <= 2, "computeVonMisesStress must be 0, 1 or 2");
     SB_CHECK(desc->n_young > 0 && desc->young && desc->n_poisson > 0 && desc->poisson, "youngModulus / poissonRatio are required");
     SB_CHECK(n_nodes < 0xFFFFFFFFull && n_tets < 0x3FFFFFFFull, "mesh too large for 32-bit indices");

@@ -12,7 +12,11 @@
 
 namespace sb {
 
-enum TetMode { TM_DF_COROT = 0, TM_DF_SMALL = 1, TM_F_SMALL = 2, TM_F_LARGE = 3, TM_F_POLAR = 4, TM_F_SVD = 5 };
+enum TetMode { TM_DF_COROT = 0, TM_DF_SMALL = 1, TM_F_SMALL = 2, TM_F_LARGE = 3, TM_F_POLAR = 4, TM_F_SVD = 5,
+               // TetrahedronFEMForceField, method large with updateStiffnessMatrix: addForce rewrites ONE of the three copies of nine cofactors
+               // (the normal-strain columns J(.,0..2), TetrahedronFEMForceField.inl:908-922); the shear columns J(.,3..5) keep their initial values,
+               // so the element carries a second set of 12 cofactors (planes js0..2) for them.
+               TM_DF_COROT_JS = 6, TM_F_LARGE_JS = 7 };
 
 // peudo_determinant_for_coef, TetrahedronFEMForceField.inl:204-208
 template <class R> HD R tet_pdet(R m00, R m01, R m02, R m10, R m11, R m12) {
@@ -40,6 +44,7 @@ template <class R> struct TetDev {
     const uint4* slot;         // destination slot of each corner's contribution
     Quad<R>* rk0; Quad<R>* rk1; Quad<R>* rk2;            // rotations[e] (9, row-major) + {K00, K01, K33}
     const Quad<R>* j0; const Quad<R>* j1; const Quad<R>* j2;     // 12 strain-displacement cofactors
+    const Quad<R>* js0; const Quad<R>* js1; const Quad<R>* js2;   // TM_*_JS: cofactors of the shear columns of J (initial values)
     Quad<R>* j0w; Quad<R>* j1w; Quad<R>* j2w;                    // the same planes, writable: non-null when updateStiffnessMatrix is set (polar / svd addForce rewrites them)
     const Quad<R>* x0a; const Quad<R>* x0b; const Quad<R>* x0c;  // _rotatedInitialElements (small: rest positions)
     const Quad<R>* sv0; const Quad<R>* sv1; const Quad<R>* sv2; const Quad<R>* sv3; const Quad<R>* sv4;  // svd: A0^-1 (9) + R0^T (9)
@@ -52,13 +57,14 @@ template <class R> struct TetDev {
 // j[3n..3n+2] = (jx,jy,jz) of node n: J(3n,0)=J(3n+1,3)=J(3n+2,5)=jx, J(3n,3)=J(3n+1,1)=J(3n+2,4)=jy,
 // J(3n,5)=J(3n+1,4)=J(3n+2,2)=jz; K has three distinct values k0=K(i,i) i<3, k1=K(i,j) i!=j<3, k2=K(i,i) i>=3.
 // `ps` (addForce with plasticMaxThreshold > 0): the element's plastic strain, updated as :357-371 do; pp = {max, yield, creep}.
-template <class R, bool USE_FACT, bool PLASTIC = false> HD void tet_compute_force(R F[12], const R D[12], const R j[12], R k0, R k1, R k2, R fact, R* ps = nullptr, const R* pp = nullptr) {
+template <class R, bool USE_FACT, bool PLASTIC = false> HD void tet_compute_force(R F[12], const R D[12], const R j[12], const R js[12], R k0, R k1, R k2, R fact, R* ps = nullptr, const R* pp = nullptr) {
+    // j: the copies of the cofactors in the normal-strain columns J(.,0..2); js: those in the shear columns J(.,3..5) (the same array unless TM_*_JS)
     R s0 = j[0] * D[0] + j[3] * D[3] + j[6] * D[6] + j[9] * D[9];
     R s1 = j[1] * D[1] + j[4] * D[4] + j[7] * D[7] + j[10] * D[10];
     R s2 = j[2] * D[2] + j[5] * D[5] + j[8] * D[8] + j[11] * D[11];
-    R s3 = j[1] * D[0] + j[0] * D[1] + j[4] * D[3] + j[3] * D[4] + j[7] * D[6] + j[6] * D[7] + j[10] * D[9] + j[9] * D[10];
-    R s4 = j[2] * D[1] + j[1] * D[2] + j[5] * D[4] + j[4] * D[5] + j[8] * D[7] + j[7] * D[8] + j[11] * D[10] + j[10] * D[11];
-    R s5 = j[2] * D[0] + j[0] * D[2] + j[5] * D[3] + j[3] * D[5] + j[8] * D[6] + j[6] * D[8] + j[11] * D[9] + j[9] * D[11];
+    R s3 = js[1] * D[0] + js[0] * D[1] + js[4] * D[3] + js[3] * D[4] + js[7] * D[6] + js[6] * D[7] + js[10] * D[9] + js[9] * D[10];
+    R s4 = js[2] * D[1] + js[1] * D[2] + js[5] * D[4] + js[4] * D[5] + js[8] * D[7] + js[7] * D[8] + js[11] * D[10] + js[10] * D[11];
+    R s5 = js[2] * D[0] + js[0] * D[2] + js[5] * D[3] + js[3] * D[5] + js[8] * D[6] + js[6] * D[8] + js[11] * D[9] + js[9] * D[11];
     if (PLASTIC) {
         // elasticStrain = JtD - plasticStrain; creep when |elastic|^2 > yield^2; clamp |plastic| to max; JtD -= plasticStrain
         const R el[6] = {s0 - ps[0], s1 - ps[1], s2 - ps[2], s3 - ps[3], s4 - ps[4], s5 - ps[5]};
@@ -86,10 +92,10 @@ template <class R, bool USE_FACT, bool PLASTIC = false> HD void tet_compute_forc
     if (USE_FACT) { t0 *= fact; t1 *= fact; t2 *= fact; t3 *= fact; t4 *= fact; t5 *= fact; }
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
-        const R jx = j[3 * n], jy = j[3 * n + 1], jz = j[3 * n + 2];
-        F[3 * n + 0] = jx * t0 + jy * t3 + jz * t5;
-        F[3 * n + 1] = jy * t1 + jx * t3 + jz * t4;
-        F[3 * n + 2] = jz * t2 + jy * t4 + jx * t5;
+        const R jx = j[3 * n], jy = j[3 * n + 1], jz = j[3 * n + 2], sx = js[3 * n], sy = js[3 * n + 1], sz = js[3 * n + 2];
+        F[3 * n + 0] = jx * t0 + sy * t3 + sz * t5;
+        F[3 * n + 1] = jy * t1 + sx * t3 + sz * t4;
+        F[3 * n + 2] = jz * t2 + sy * t4 + sx * t5;
     }
 }
 
@@ -104,22 +110,30 @@ template <class R> HD TetRec<R> tet_load_rec(const TetDev<R>& d, size_t es, uint
     return r;
 }
 // computeForce(F, D, _plasticStrains[e], K, J) as addForce calls it (:560,927,1071,1180)
-template <class R> HD void tet_compute_force_addforce(const TetDev<R>& d, size_t es, R F[12], const R D[12], const R j[12], R k0, R k1, R k2) {
+template <class R> HD void tet_compute_force_addforce(const TetDev<R>& d, size_t es, R F[12], const R D[12], const R j[12], const R js[12], R k0, R k1, R k2) {
     if (d.pl0) {
         const Quad<R> a = d.pl0[es], b = d.pl1[es];
         R ps[6] = {a.a, a.b, a.c, a.d, b.a, b.b};
         const R pp[3] = {d.plastic_max, d.plastic_yield, d.plastic_creep};
-        tet_compute_force<R, false, true>(F, D, j, k0, k1, k2, R(0), ps, pp);
+        tet_compute_force<R, false, true>(F, D, j, js, k0, k1, k2, R(0), ps, pp);
         d.pl0[es] = Quad<R>{ps[0], ps[1], ps[2], ps[3]}; d.pl1[es] = Quad<R>{ps[4], ps[5], R(0), R(0)};
-    } else tet_compute_force<R, false>(F, D, j, k0, k1, k2, R(0));
+    } else tet_compute_force<R, false>(F, D, j, js, k0, k1, k2, R(0));
 }
 template <class R, int MODE> HD void tet_element(const TetDev<R>& d, size_t es, const TetRec<R>& rec, const V3<R> P[4], V3<R> C[4]) {
     const Quad<R> q0 = rec.q0, q1 = rec.q1, q2 = rec.q2;
     const Quad<R> ja = rec.ja, jb = rec.jb, jc = rec.jc;
     R j[12] = {ja.a, ja.b, ja.c, ja.d, jb.a, jb.b, jb.c, jb.d, jc.a, jc.b, jc.c, jc.d};
     const R k0 = q2.b, k1 = q2.c, k2 = q2.d;
+    R js_own[12];
+    const R* js = j;
+    if (MODE == TM_DF_COROT_JS || MODE == TM_F_LARGE_JS) {
+        const Quad<R> sa = d.js0[es], sb = d.js1[es], sc = d.js2[es];
+        js_own[0] = sa.a; js_own[1] = sa.b; js_own[2] = sa.c; js_own[3] = sa.d; js_own[4] = sb.a; js_own[5] = sb.b; js_own[6] = sb.c; js_own[7] = sb.d;
+        js_own[8] = sc.a; js_own[9] = sc.b; js_own[10] = sc.c; js_own[11] = sc.d;
+        js = js_own;
+    }
     R F[12];
-    if (MODE == TM_DF_COROT) {
+    if (MODE == TM_DF_COROT || MODE == TM_DF_COROT_JS) {
         // applyStiffnessCorotational, TetrahedronFEMForceField.inl:1192-1237 (rot = rotations[e])
         const R r00 = q0.a, r01 = q0.b, r02 = q0.c, r10 = q0.d, r11 = q1.a, r12 = q1.b, r20 = q1.c, r21 = q1.d, r22 = q2.a;
         R X[12];
@@ -129,7 +143,7 @@ template <class R, int MODE> HD void tet_element(const TetDev<R>& d, size_t es, 
             X[3 * n + 1] = r01 * P[n].x + r11 * P[n].y + r21 * P[n].z;
             X[3 * n + 2] = r02 * P[n].x + r12 * P[n].y + r22 * P[n].z;
         }
-        tet_compute_force<R, true>(F, X, j, k0, k1, k2, d.k_factor);
+        tet_compute_force<R, true>(F, X, j, js, k0, k1, k2, d.k_factor);
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
             C[n].x = r00 * F[3 * n] + r01 * F[3 * n + 1] + r02 * F[3 * n + 2];
@@ -141,7 +155,7 @@ template <class R, int MODE> HD void tet_element(const TetDev<R>& d, size_t es, 
         R X[12];
 #pragma unroll
         for (int n = 0; n < 4; ++n) { X[3 * n] = P[n].x; X[3 * n + 1] = P[n].y; X[3 * n + 2] = P[n].z; }
-        tet_compute_force<R, true>(F, X, j, k0, k1, k2, d.k_factor);
+        tet_compute_force<R, true>(F, X, j, js, k0, k1, k2, d.k_factor);
 #pragma unroll
         for (int n = 0; n < 4; ++n) C[n] = mk3<R>(F[3 * n], F[3 * n + 1], F[3 * n + 2]);
     } else {
@@ -157,12 +171,12 @@ template <class R, int MODE> HD void tet_element(const TetDev<R>& d, size_t es, 
                 D[3 * n + 1] = X0[3 * n + 1] - X0[1] - P[n].y + P[0].y;
                 D[3 * n + 2] = X0[3 * n + 2] - X0[2] - P[n].z + P[0].z;
             }
-            tet_compute_force_addforce<R>(d, es, F, D, j, k0, k1, k2);
+            tet_compute_force_addforce<R>(d, es, F, D, j, js, k0, k1, k2);
 #pragma unroll
             for (int n = 0; n < 4; ++n) C[n] = mk3<R>(F[3 * n], F[3 * n + 1], F[3 * n + 2]);
         } else {
             M3<R> R02;  // R_0_2: rows = element frame axes
-            if (MODE == TM_F_LARGE) {
+            if (MODE == TM_F_LARGE || MODE == TM_F_LARGE_JS) {
                 // computeRotationLarge, :754-778
                 V3<R> ex = P[1] - P[0];
                 normalize3(ex);
@@ -196,7 +210,7 @@ template <class R, int MODE> HD void tet_element(const TetDev<R>& d, size_t es, 
             V3<R> def[4];
 #pragma unroll
             for (int n = 0; n < 4; ++n) def[n] = mul(R02, P[n]);
-            if (MODE == TM_F_LARGE) {
+            if (MODE == TM_F_LARGE || MODE == TM_F_LARGE_JS) {
                 // accumulateForceLarge, :870-905
                 def[1].x -= def[0].x;
                 def[2].x -= def[0].x;
@@ -206,7 +220,8 @@ template <class R, int MODE> HD void tet_element(const TetDev<R>& d, size_t es, 
                 D[3] = X0[3] - def[1].x; D[4] = 0; D[5] = 0;
                 D[6] = X0[6] - def[2].x; D[7] = X0[7] - def[2].y; D[8] = 0;
                 D[9] = X0[9] - def[3].x; D[10] = X0[10] - def[3].y; D[11] = X0[11] - def[3].z;
-                if (d.j0w) {   // TetrahedralCorotationalFEMForceField::accumulateForceLarge with d_updateStiffnessMatrix, TetrahedralCorotationalFEMForceField.inl:920-937
+                if (d.j0w) {   // d_updateStiffnessMatrix: TetrahedralCorotationalFEMForceField.inl:920-937 rewrites all three copies of the nine cofactors (TM_F_LARGE, one set);
+                               // TetrahedronFEMForceField.inl:908-922 only the copy in the normal-strain column (TM_F_LARGE_JS: `j` here, the shear copies stay in js)
                     j[0] = -def[2].y * def[3].z;
                     j[1] = def[2].x * def[3].z - def[1].x * def[3].z;
                     j[2] = def[2].y * def[3].x - def[2].x * def[3].y + def[1].x * def[3].y - def[1].x * def[2].y;
@@ -227,7 +242,7 @@ template <class R, int MODE> HD void tet_element(const TetDev<R>& d, size_t es, 
                     d.j0w[es] = Quad<R>{j[0], j[1], j[2], j[3]}; d.j1w[es] = Quad<R>{j[4], j[5], j[6], j[7]}; d.j2w[es] = Quad<R>{j[8], j[9], j[10], j[11]};
                 }
             }
-            tet_compute_force_addforce<R>(d, es, F, D, j, k0, k1, k2);
+            tet_compute_force_addforce<R>(d, es, F, D, j, js, k0, k1, k2);
             // f[index[i/3]] += rotations[e] * Deriv(F[i],F[i+1],F[i+2]), :928-929
 #pragma unroll
             for (int n = 0; n < 4; ++n) C[n] = mul(rot, mk3<R>(F[3 * n], F[3 * n + 1], F[3 * n + 2]));

@@ -20,7 +20,7 @@ template <class R> struct Emu {
         d.t.tile_val = P.tile_val.data(); d.t.tile_jds = P.tile_jds.data();
         d.t.n_shared = P.n_shared; d.t.n_chunks = P.n_chunks; d.t.sh_nodes = P.sh_nodes.data(); d.t.sh_val = P.sh_val.data();
         d.t.sh_base = P.sh_base.data(); d.t.stage = stage.data(); d.t.stage_n = P.stage_n;
-        d.lnode = h.lnode.data(); d.slot = h.slot.data();
+        d.lnode = h.lnode.data(); d.slot = h.slot.data(); d.js0 = nullptr; d.js1 = nullptr; d.js2 = nullptr;
         d.rk0 = h.rk0.data(); d.rk1 = h.rk1.data(); d.rk2 = h.rk2.data(); d.j0 = h.j0.data(); d.j1 = h.j1.data(); d.j2 = h.j2.data();
         d.x0a = h.x0a.data(); d.x0b = h.x0b.data(); d.x0c = h.x0c.data();
         d.sv0 = h.sv[0].data(); d.sv1 = h.sv[1].data(); d.sv2 = h.sv[2].data(); d.sv3 = h.sv[3].data(); d.sv4 = h.sv[4].data();

@@ -222,7 +222,7 @@ class OracleScene:
             return out.reshape(-1, 3)
         if what.endswith("otations") or what.endswith("Transformation"):
             return out.reshape(-1, 3, 3)
-        if what == "tet.J":
+        if what in ("tet.J", "tet.Jsh"):
             return out.reshape(-1, 4, 3)
         if what == "tet.plasticStrains":
             return out.reshape(-1, 6)

@@ -155,16 +155,12 @@ def test_tetrahedral_corotational_fem_force_field(dtype, method, update, meshnam
 @pytest.mark.parametrize("method", ["polar", "svd", "small", "large"])
 def test_update_stiffness_matrix(dtype, method):
     """Data updateStiffnessMatrix (TetrahedronFEMForceField.inl:1063-1067,1174-1177): polar / svd recompute the strain-displacement terms
-    from the deformed element in every addForce, and addDForce then uses them; `small` ignores the flag; `large` is refused (the reference
-    rewrites single entries of J there, :908-922)."""
+    from the deformed element in every addForce, and addDForce then uses them; `small` ignores the flag; `large` rewrites nine single entries
+    of J, all in its normal-strain columns (:908-922), so the copies of those cofactors in the shear columns keep their initial values."""
     import sofa_b200 as sb
     c, pos, hexas, tets, fixed = gpu_common.mesh("C1")
     ctx = sb.Context(0)
     mo = sb.MechanicalObject(ctx, "B200Vec3f" if dtype == np.float32 else "B200Vec3d", position=pos)
-    if method == "large":
-        with pytest.raises(sb.Sofab200Error):
-            sb.TetrahedronFEMForceField(mo, tets, youngModulus=c["young"], poissonRatio=c["poisson"], method=method, updateStiffnessMatrix=True)
-        return
     ff = sb.TetrahedronFEMForceField(mo, tets, youngModulus=c["young"], poissonRatio=c["poisson"], method=method, updateStiffnessMatrix=True)
     s = oracle_scene("C1", dtype, method)
     s.set_update_stiffness_matrix(True)
@@ -182,6 +178,33 @@ def test_update_stiffness_matrix(dtype, method):
         assert df_d.cpu().numpy().tobytes() == s.fem_add_dforce(f0, dx, 0.11).tobytes(), it
     if method != "small":
         assert np.abs(s.get("tet.J") - J0).max() > 0      # the oracle's J did change
+    if method == "large":
+        assert np.abs(s.get("tet.J") - s.get("tet.Jsh")).max() > 0      # ... and only its normal-strain columns
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_update_stiffness_matrix_large_steps(dtype):
+    """EulerImplicit + CG steps with method large and updateStiffnessMatrix (two cofactor sets per element: served by the multi-kernel CG loop)."""
+    import sofa_b200 as sb
+    c, pos, hexas, tets, fixed = gpu_common.mesh("C1")
+    ctx = sb.Context(0)
+    mo = sb.MechanicalObject(ctx, "B200Vec3f" if dtype == np.float32 else "B200Vec3d", position=pos)
+    ff = sb.TetrahedronFEMForceField(mo, tets, youngModulus=c["young"], poissonRatio=c["poisson"], method="large", updateStiffnessMatrix=True)
+    mass = sb.DiagonalMass(mo, tets, massDensity=c["density"])
+    node = sb.SolverNode(mo, ff, mass, sb.FixedProjectiveConstraint(mo, fixed), dt=c["dt"], gravity=c["gravity"], rayleighStiffness=c["rK"], rayleighMass=c["rM"],
+                         iterations=c["iterations"], tolerance=c["tolerance"], threshold=c["threshold"])
+    s = oracle_scene("C1", dtype, "large")
+    s.set_update_stiffness_matrix(True)
+    s.set_dot_double(True)
+    ref = oracle_scene("C1", dtype, "large"); ref.set_dot_double(True)      # without the flag: must differ
+    for it in range(4):
+        n_it = node.step(); s_it = s.step(); ref.step()
+        assert abs(node.last_solve()["iterations"] - s_it) <= 1
+        assert node.get("b").tobytes() == s.get("b").tobytes() or it > 0      # (first step: same state on both sides => bit-exact right-hand side)
+        # (the flag makes J, hence the operator, non-symmetric: CG amplifies the last-bit differences between the two dot-product orders about 20x per step --
+        #  measured 7e-13, 2e-9, 2e-8, 8e-8 in Vec3d; Vec3f with the oracle's dots in double comes out bit-identical)
+        assert np.abs(mo.x.cpu().numpy().astype(np.float64) - s.get("x")).max() <= (1e-6 if dtype == np.float64 else 2e-4)
+    assert np.abs(s.get("x") - ref.get("x")).max() > 1e-6
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

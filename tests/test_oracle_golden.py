@@ -294,3 +294,31 @@ def test_tetrahedral_corotational_shares_the_golden_vectors(dtype):
     f_upd = s.fem_add_force(np.zeros_like(x), y)
     assert np.abs(s.get("tet.J") - J0).max() > 1e-3 and np.abs(f_upd - f_fixed).max() > 1e-3
     assert np.abs(f_upd.sum(axis=0)).max() < (1e-2 if dtype == np.float32 else 1e-9)     # internal forces still balance
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_update_stiffness_matrix_large_rewrites_only_the_normal_strain_columns(dtype):
+    """TetrahedronFEMForceField.inl:908-922: with updateStiffnessMatrix, accumulateForceLarge assigns J(0,0) J(1,1) J(2,2) J(3,0) J(4,1) J(5,2) J(7,1)
+    J(8,2) J(11,2) -- one of the three places each cofactor occupies -- while the sibling class (TetrahedralCorotationalFEMForceField.inl:920-937)
+    assigns all three.  The oracle keeps the shear-column copies apart ("tet.Jsh")."""
+    x = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype)
+    y = (x * np.array([1.2, 0.9, 1.1])).astype(dtype)
+    res = {}
+    for sibling in (False, True):
+        s = O.OracleScene(dtype, x)
+        s.set_tets(np.array([[2, 3, 1, 0]], np.uint32), "large", 1000.0, 0.3)
+        s.set_tetrahedral_corotational(sibling)
+        J0 = s.get("tet.J").copy()
+        assert s.get("tet.Jsh").tobytes() == J0.tobytes()
+        s.set_update_stiffness_matrix(True)
+        f = s.fem_add_force(np.zeros_like(x), y)
+        J, Jsh = s.get("tet.J")[0].reshape(12), s.get("tet.Jsh")[0].reshape(12)
+        changed = [q for q in range(12) if J[q] != J0[0].reshape(12)[q]]
+        assert set(changed) <= {0, 1, 2, 3, 4, 5, 7, 8, 11} and len(changed) >= 6
+        if sibling:
+            assert Jsh.tobytes() == J.tobytes()
+        else:
+            assert Jsh.tobytes() == J0[0].tobytes()
+        df = s.fem_add_dforce(np.zeros_like(x), (0.01 * y).astype(dtype), 1.0)
+        res[sibling] = (f, df)
+    assert np.abs(res[False][0] - res[True][0]).max() > 1e-3 and np.abs(res[False][1] - res[True][1]).max() > 1e-5
