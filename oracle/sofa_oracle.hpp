@@ -1337,6 +1337,162 @@ template <class R> struct MeshMatrixMass {
 // (present in every SofaCUDA FEM benchmark scene).  setPlane :139-145, addForce :158-205, addDForce :208-226.
 // PARITY UNPINNED by reference vectors: the reference tree holds no numerical KAT for this class, only the behaviour test
 // MechanicalLoad/tests/PlaneForceField_test.cpp (reproduced in tests/test_oracle_golden.py).
+// ---------------------------------------------------------------------------
+// FastTetrahedralCorotationalForceField<DataTypes>   
+// Sofa/Component/SolidMechanics/FEM/Elastic/src/sofa/component/solidmechanics/fem/elastic/FastTetrahedralCorotationalForceField.{h,inl}
+// Per tetrahedron: four shape vectors, six 3x3 edge blocks of the linear stiffness (linearDfDx), the rest edge vectors and the rotation of the
+// last addForce; addDForce runs over the EDGES of the topology with one 3x3 matrix per edge, assembled from the tetrahedra at the first call after
+// each addForce.  Edge numbering: TetrahedronSetTopologyContainer::createEdgesInTetrahedronArray (see MeshMatrixMass::createEdgeSetArray above),
+// or the caller's edge list when the topology already holds one.
+// ---------------------------------------------------------------------------
+enum FastMethod { FAST_POLAR = 0, FAST_QR = 1, FAST_POLAR2 = 2, FAST_LINEAR = 3 };   // RotationDecompositionMethod, .h:70-76 (d_method "polar" / "qr","large" / "polar2" / "none","linear","small", .inl:191-203)
+template <class R> struct FastTetFEM {
+    typedef Vec3<R> Coord;
+    std::vector<uint32_t> tets;           // 4 * T
+    std::vector<uint32_t> edges;          // 2 * E  (l_topology->getEdges())
+    std::vector<uint32_t> edgesInTet;     // 6 * T  (getEdgesInTetrahedron)
+    std::vector<R> young, poisson;
+    int method = FAST_QR;
+    struct TetrahedronRestInformation {   // .h:83-106
+        Coord shapeVector[4]; R restVolume; Coord restEdgeVector[6]; Mat3<R> linearDfDxDiag[4]; Mat3<R> linearDfDx[6]; Mat3<R> rotation; Mat3<R> restRotation; R edgeOrientation[6];
+    };
+    std::vector<TetrahedronRestInformation> tetrahedronInfo;   // d_tetrahedronInfo
+    std::vector<Mat3<R>> edgeInfo;                             // d_edgeInfo
+    bool updateMatrix = true;
+    static constexpr int L[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};   // edgesInTetrahedronArray, core/topology/Topology.cpp:44
+
+    size_t nbTets() const { return tets.size() / 4; }
+    R youngIn(size_t e) const { return young.size() > e ? young[e] : young[0]; }      // BaseLinearElasticityFEMForceField.inl:112-137
+    R poissonIn(size_t e) const { return poisson.size() > e ? poisson[e] : poisson[0]; }
+
+    static void computeQRRotation(Mat3<R>& r, const Coord* dp) {   // .inl:272-294
+        const Coord edgex = dp[0].normalized();
+        Coord edgey = dp[1];
+        const Coord edgez = cross(edgex, edgey).normalized();
+        edgey = cross(edgez, edgex);
+        r.setRow(0, edgex); r.setRow(1, edgey); r.setRow(2, edgez);
+    }
+    void createTetrahedronRestInformation(size_t i, TetrahedronRestInformation& my_tinfo, const std::vector<Coord>& restPosition) {   // .inl:38-150
+        const R youngModulusElement = youngIn(i), poissonRatioElement = poissonIn(i);
+        // toLameParameters<3, Real>, impl/LameParameters.h:57-65
+        R mu = youngModulusElement / (2 * (1 + poissonRatioElement));
+        R lambda = youngModulusElement * poissonRatioElement / ((1 + poissonRatioElement) * (1 - (3 - 1) * poissonRatioElement));
+        Coord point[4];
+        const uint32_t* t = &tets[4 * i];
+        for (int j = 0; j < 4; ++j) point[j] = restPosition[t[j]];
+        // geometry::Tetrahedron::signedVolume, Geometry/src/sofa/geometry/Tetrahedron.h:73-83
+        const R tetrahedronVolume = -(dot(cross(point[1] - point[0], point[2] - point[0]), point[3] - point[0]) / R(6));
+        my_tinfo.restVolume = tetrahedronVolume;
+        mu *= std::fabs(tetrahedronVolume);
+        lambda *= std::fabs(tetrahedronVolume);
+        for (int j = 0; j < 4; ++j) {
+            const Coord c = cross(point[(j + 2) % 4] - point[(j + 1) % 4], point[(j + 3) % 4] - point[(j + 1) % 4]);
+            if ((j % 2) == 0) my_tinfo.shapeVector[j] = c / (tetrahedronVolume * 6);
+            else my_tinfo.shapeVector[j] = (-c) / (tetrahedronVolume * 6);
+        }
+        for (int j = 0; j < 4; ++j) {
+            const R val = mu * dot(my_tinfo.shapeVector[j], my_tinfo.shapeVector[j]);
+            for (int m = 0; m < 3; ++m)
+                for (int n = m; n < 3; ++n) {
+                    my_tinfo.linearDfDxDiag[j](m, n) = lambda * my_tinfo.shapeVector[j][n] * my_tinfo.shapeVector[j][m] + mu * my_tinfo.shapeVector[j][n] * my_tinfo.shapeVector[j][m];
+                    if (m == n) my_tinfo.linearDfDxDiag[j](m, m) += R(val);
+                    else my_tinfo.linearDfDxDiag[j](n, m) = my_tinfo.linearDfDxDiag[j](m, n);
+                }
+        }
+        for (int j = 0; j < 6; ++j) {
+            const int k = L[j][0], l = L[j][1];
+            my_tinfo.restEdgeVector[j] = point[l] - point[k];
+            const R val = mu * dot(my_tinfo.shapeVector[l], my_tinfo.shapeVector[k]);
+            for (int m = 0; m < 3; ++m)
+                for (int n = 0; n < 3; ++n) {
+                    my_tinfo.linearDfDx[j](m, n) = lambda * my_tinfo.shapeVector[k][n] * my_tinfo.shapeVector[l][m] + mu * my_tinfo.shapeVector[l][n] * my_tinfo.shapeVector[k][m];
+                    if (m == n) my_tinfo.linearDfDx[j](m, m) += R(val);
+                }
+        }
+        if (method == FAST_QR) computeQRRotation(my_tinfo.restRotation, my_tinfo.restEdgeVector);
+        else if (method == FAST_POLAR2) {
+            Mat3<R> Transformation;
+            Transformation.setRow(0, point[1] - point[0]); Transformation.setRow(1, point[2] - point[0]); Transformation.setRow(2, point[3] - point[0]);
+            Decompose<R>::polarDecomposition(Transformation, my_tinfo.restRotation);
+        }
+    }
+    // init :176-246 + updateTopologyInformation :249-270.  `givenEdges`: the topology's own edge list when it has one (TetrahedronSetTopologyContainer.cpp:163-205)
+    void init(const std::vector<Coord>& restPosition, const std::vector<uint32_t>* givenEdges = nullptr) {
+        const size_t T = nbTets();
+        if (givenEdges && !givenEdges->empty()) {
+            edges = *givenEdges;
+            std::map<std::pair<uint32_t, uint32_t>, uint32_t> idx;
+            for (size_t e = 0; e < edges.size() / 2; ++e) idx.emplace(std::minmax(edges[2 * e], edges[2 * e + 1]), uint32_t(e));
+            edgesInTet.assign(6 * T, 0);
+            for (size_t i = 0; i < T; ++i) for (int j = 0; j < 6; ++j) edgesInTet[6 * i + j] = idx.at(std::minmax(tets[4 * i + L[j][0]], tets[4 * i + L[j][1]]));
+        } else MeshMatrixMass<R>::createEdgeSetArray(tets, edges, edgesInTet);
+        edgeInfo.assign(edges.size() / 2, Mat3<R>());
+        tetrahedronInfo.assign(T, TetrahedronRestInformation());
+        for (size_t i = 0; i < T; ++i) createTetrahedronRestInformation(i, tetrahedronInfo[i], restPosition);
+        for (size_t i = 0; i < T; ++i)
+            for (int j = 0; j < 6; ++j)
+                tetrahedronInfo[i].edgeOrientation[j] = (tets[4 * i + L[j][0]] == edges[2 * edgesInTet[6 * i + j]]) ? R(1) : R(-1);
+        updateMatrix = true;
+    }
+    void addForce(VecDeriv<R>& f, const std::vector<Coord>& x) {   // .inl:296-399
+        for (size_t i = 0; i < nbTets(); ++i) {
+            TetrahedronRestInformation& tetraInfo = tetrahedronInfo[i];
+            const uint32_t* tetra = &tets[4 * i];
+            Coord tetraVertex[4], displ[6];
+            for (int j = 0; j < 4; ++j) tetraVertex[j] = x[tetra[j]];
+            for (int j = 0; j < 6; ++j) displ[j] = tetraVertex[L[j][1]] - tetraVertex[L[j][0]];
+            Mat3<R> deformationGradient, S, Rm;
+            if (method == FAST_POLAR) {
+                Coord sv = tetraInfo.shapeVector[1];
+                for (int k = 0; k < 3; ++k) for (int l = 0; l < 3; ++l) deformationGradient(k, l) = displ[0][k] * sv[l];
+                for (int j = 1; j < 3; ++j) {
+                    sv = tetraInfo.shapeVector[j + 1];
+                    for (int k = 0; k < 3; ++k) for (int l = 0; l < 3; ++l) deformationGradient(k, l) += displ[j][k] * sv[l];
+                }
+                Decompose<R>::polarDecomposition(deformationGradient, Rm);
+            } else if (method == FAST_QR) {
+                computeQRRotation(S, displ);
+                Rm = S.multTranspose(tetraInfo.restRotation);
+            } else if (method == FAST_POLAR2) {
+                S.setRow(0, displ[0]); S.setRow(1, displ[1]); S.setRow(2, displ[2]);
+                Decompose<R>::polarDecomposition(S, Rm);
+                Rm = Rm.transposed() * tetraInfo.restRotation;
+            } else Rm.identity();
+            tetraInfo.rotation = Rm.transposed();
+            Coord force[4];
+            for (int j = 0; j < 6; ++j) {
+                displ[j] = tetraInfo.rotation * displ[j] - tetraInfo.restEdgeVector[j];
+                force[L[j][1]] += tetraInfo.linearDfDx[j] * displ[j];
+                force[L[j][0]] -= tetraInfo.linearDfDx[j].multTranspose(displ[j]);
+            }
+            for (int j = 0; j < 4; ++j) f[tetra[j]] += Rm * force[j];
+        }
+        updateMatrix = true;
+    }
+    void assembleEdgeMatrices() {   // .inl:414-450
+        for (auto& m : edgeInfo) m = Mat3<R>();
+        for (size_t i = 0; i < nbTets(); ++i) {
+            const TetrahedronRestInformation& tetinfo = tetrahedronInfo[i];
+            for (int j = 0; j < 6; ++j) {
+                const uint32_t edgeID = edgesInTet[6 * i + j];
+                const Mat3<R> tmp = tetinfo.linearDfDx[j] * tetinfo.rotation;
+                const Mat3<R> add = tetinfo.edgeOrientation[j] == 1 ? tetinfo.rotation.multTranspose(tmp) : tmp.multTranspose(tetinfo.rotation);
+                edgeInfo[edgeID] = edgeInfo[edgeID] + add;
+            }
+        }
+    }
+    void addDForce(VecDeriv<R>& df, const VecDeriv<R>& dx, SReal kFactorIncludingRayleigh) {   // .inl:402-470
+        const R kFactor = R(kFactorIncludingRayleigh);
+        if (updateMatrix) { updateMatrix = false; assembleEdgeMatrices(); }
+        for (size_t i = 0; i < edges.size() / 2; ++i) {
+            const uint32_t e0 = edges[2 * i], e1 = edges[2 * i + 1];
+            const Coord deltax = (dx[e1] - dx[e0]) * kFactor;
+            df[e1] += edgeInfo[i] * deltax;
+            df[e0] -= edgeInfo[i].multTranspose(deltax);
+        }
+    }
+};
+
 template <class R> struct PlaneForceField {
     Vec3<R> planeNormal = Vec3<R>(0, 1, 0);
     R planeD = 0, stiffness = 500, damping = 5, maxForce = 0;
@@ -1389,6 +1545,7 @@ template <class R> struct Scene {
     double massRayleighMass = 0;      // Mass::rayleighMass Data of the mass component (default 0)
     TetFEM<R> tet; bool hasTet = false;
     HexaFEM<R> hex; bool hasHex = false;
+    FastTetFEM<R> fast; bool hasFast = false;
     double ffRayleighStiffness = 0;   // BaseForceField::rayleighStiffness of the FEM component (default 0)
     bool massFirst = true;            // scene order of the two force fields (mass before FEM in every reference scene)
     PlaneForceField<R> plane; bool hasPlane = false;   // last force field of the node (as in the SofaCUDA benchmark scenes)
@@ -1424,7 +1581,7 @@ template <class R> struct Scene {
     // MechanicalParams factors of the system being applied
     double mFact = 0, bFact = 0, kFact = 0;
 
-    void femAddForce(VecDeriv<R>& F) { if (hasTet) tet.addForce(F, x); if (hasHex) hex.addForce(F, x); }
+    void femAddForce(VecDeriv<R>& F) { if (hasTet) tet.addForce(F, x); if (hasHex) hex.addForce(F, x); if (hasFast) fast.addForce(F, x); }
     // threads > 1: the MultiThreading plugin's ParallelTetrahedronFEMForceField::addDForce
     // (applications/plugins/MultiThreading/src/MultiThreading/component/solidmechanics/fem/elastic/ParallelTetrahedronFEMForceField.inl:67-99):
     // element ranges over threads, thread-local df, merged under a mutex.  A TIMING variant for the CPU baseline
@@ -1487,6 +1644,7 @@ template <class R> struct Scene {
     void femAddDForce(VecDeriv<R>& df, const VecDeriv<R>& d, double kf) {
         if (hasTet) { if (threads > 1) parallelTetAddDForce(df, d, kf); else tet.addDForce(df, d, kf); }
         if (hasHex) { if (threads > 1) parallelHexAddDForce(df, d, kf); else hex.addDForce(df, d, kf); }
+        if (hasFast) fast.addDForce(df, d, kf);
     }
     // mop.computeForce: resetForce, accumulateForce (no external force), every force field's addForce in scene order
     // Sofa/framework/Simulation/Core/src/sofa/simulation/MappingGraphMechanicalOperations.cpp:41-93

@@ -138,6 +138,15 @@ void orc_scene_set_tets(void* h, size_t T, const uint32_t* tets, int method, int
         sc.tet.reinit(sc.x0);
     });
 }
+// FastTetrahedralCorotationalForceField: method 0 polar, 1 qr, 2 polar2, 3 none; E > 0: the topology's own edge list
+void orc_scene_set_fast_tets(void* h, size_t T, const uint32_t* tets, int method, int ny, const double* young, int np, const double* poisson, size_t E, const uint32_t* edges) {
+    DISPATCH(h, {
+        sc.hasFast = true; sc.fast.method = method; sc.fast.tets.assign(tets, tets + 4 * T);
+        fillReal(sc.fast.young, young, ny); fillReal(sc.fast.poisson, poisson, np);
+        std::vector<uint32_t> given; if (E > 0) given.assign(edges, edges + 2 * E);
+        sc.fast.init(sc.x0, E > 0 ? &given : nullptr);
+    });
+}
 // HexahedronFEMForceField: method 0 large, 1 polar, 2 small
 void orc_scene_set_hexas(void* h, size_t H, const uint32_t* hexas, int method, int ny, const double* young, int np, const double* poisson) {
     DISPATCH(h, {
@@ -267,6 +276,19 @@ size_t orc_scene_get(void* h, const char* what, void* out) {
         else if (w == "tet.plasticStrains") reals(sc.tet.plasticStrains);
         else if (w == "tet.elemShapeFun") reals(sc.tet.elemShapeFun);
         else if (w == "tet.J") reals(sc.tet.J); else if (w == "tet.Jsh") reals(sc.tet.Jsh); else if (w == "tet.K") reals(sc.tet.K); else if (w == "tet.X0") vec3(sc.tet.X0);
+        else if (w.rfind("fast.", 0) == 0) {
+            std::vector<Mat3<R>> m; std::vector<Vec3<R>> v; std::vector<R> r;
+            const auto& ti = sc.fast.tetrahedronInfo;
+            if (w == "fast.rotations") { for (auto& t : ti) m.push_back(t.rotation); mats(m); }
+            else if (w == "fast.restRotations") { for (auto& t : ti) m.push_back(t.restRotation); mats(m); }
+            else if (w == "fast.linearDfDx") { for (auto& t : ti) for (int j = 0; j < 6; ++j) m.push_back(t.linearDfDx[j]); mats(m); }
+            else if (w == "fast.linearDfDxDiag") { for (auto& t : ti) for (int j = 0; j < 4; ++j) m.push_back(t.linearDfDxDiag[j]); mats(m); }
+            else if (w == "fast.shapeVectors") { for (auto& t : ti) for (int j = 0; j < 4; ++j) v.push_back(t.shapeVector[j]); vec3(v); }
+            else if (w == "fast.restEdgeVectors") { for (auto& t : ti) for (int j = 0; j < 6; ++j) v.push_back(t.restEdgeVector[j]); vec3(v); }
+            else if (w == "fast.edgeOrientations") { for (auto& t : ti) for (int j = 0; j < 6; ++j) r.push_back(t.edgeOrientation[j]); reals(r); }
+            else if (w == "fast.edgeInfo") mats(sc.fast.edgeInfo);
+            else if (w == "fast.edges") { for (uint32_t e : sc.fast.edges) r.push_back(R(e)); reals(r); }
+        }
         else if (w == "hex.rotations") mats(sc.hex.rotations); else if (w == "hex.initialRotations") mats(sc.hex.initialRotations);
         else if (w == "hex.Ke") reals(sc.hex.Ke); else if (w == "hex.X0") vec3(sc.hex.X0); else if (w == "hex.Kmat") reals(sc.hex.Kmat);
     });

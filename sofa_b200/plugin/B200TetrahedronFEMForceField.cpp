@@ -39,7 +39,7 @@ public:
         desc.plastic_max_threshold = double(d_plasticMaxThreshold.getValue());     /* plasticity branch of computeForce, .inl:357-371 */ \
         desc.plastic_yield_threshold = double(d_plasticYieldThreshold.getValue());                                                  \
         desc.plastic_creep = double(d_plasticCreep.getValue());                                                                      \
-        desc.update_stiffness_matrix = d_updateStiffnessMatrix.getValue() ? 1 : 0;   /* polar / svd; refused with large (see include/sofa_b200.h) */ \
+        desc.update_stiffness_matrix = d_updateStiffnessMatrix.getValue() ? 1 : 0;   /* large / polar / svd (see include/sofa_b200.h) */                   \
         desc.compute_von_mises = isComputeVonMisesStressMethodSet() ? int(d_computeVonMisesStress.getValue()) : 0;                   \
         if (data.ff) { sofab200_tetfem_destroy(data.ff); data.ff = nullptr; }                                                        \
         const int rc = sofab200_tetfem_create(sofa::b200::threadContext(), B200Vec3Types<TReal>::abiReal, rest.size(), rest.hostRead(), \

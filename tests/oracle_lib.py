@@ -16,6 +16,7 @@ _ORACLE_SO = os.path.join(ORACLE_DIR, "libsofa_oracle.so")
 _REF_SO = os.path.join(ORACLE_DIR, "_ref", "libsofa_ref.so")
 
 TET_METHODS = {"small": 0, "large": 1, "polar": 2, "svd": 3}
+FAST_METHODS = {"polar": 0, "qr": 1, "large": 1, "polar2": 2, "none": 3, "linear": 3, "small": 3}
 HEX_METHODS = {"large": 0, "polar": 1, "small": 2}
 _P = C.c_void_p
 
@@ -144,6 +145,16 @@ class OracleScene:
                                   0 if lsf is None else len(lsf), _ptr(lsf))
         self.tets = t
 
+    def set_fast_tets(self, tets, method="qr", young=5000.0, poisson=0.45, edges=None):
+        """FastTetrahedralCorotationalForceField (d_method: "polar", "qr"/"large", "polar2", "none"/"linear"/"small")."""
+        t = np.ascontiguousarray(tets, np.uint32)
+        y = np.atleast_1d(np.asarray(young, np.float64))
+        p = np.atleast_1d(np.asarray(poisson, np.float64))
+        e = None if edges is None else np.ascontiguousarray(edges, np.uint32)
+        self.L.orc_scene_set_fast_tets(self.h, C.c_size_t(t.shape[0]), _ptr(t), FAST_METHODS[method], len(y), _ptr(y), len(p), _ptr(p),
+                                       C.c_size_t(0 if e is None else e.shape[0]), _ptr(e))
+        self.tets = t
+
     def set_mesh_mass(self, tets, density=1.0, lumping=False):
         t = np.ascontiguousarray(tets, np.uint32)
         self.L.orc_scene_set_mesh_mass(self.h, C.c_size_t(t.shape[0]), _ptr(t), C.c_double(density), int(lumping))
@@ -220,7 +231,7 @@ class OracleScene:
         self.L.orc_scene_get(self.h, what.encode(), _ptr(out))
         if what in ("x", "v", "f", "b", "sol", "x0"):
             return out.reshape(-1, 3)
-        if what.endswith("otations") or what.endswith("Transformation"):
+        if what.endswith("otations") or what.endswith("Transformation") or what in ("fast.linearDfDx", "fast.linearDfDxDiag", "fast.edgeInfo"):
             return out.reshape(-1, 3, 3)
         if what in ("tet.J", "tet.Jsh"):
             return out.reshape(-1, 4, 3)
@@ -228,6 +239,10 @@ class OracleScene:
             return out.reshape(-1, 6)
         if what == "tet.K":
             return out.reshape(-1, 3)
+        if what in ("fast.shapeVectors", "fast.restEdgeVectors"):
+            return out.reshape(-1, 3)
+        if what == "fast.edges":
+            return out.astype(np.int64).reshape(-1, 2)
         if what == "tet.X0":
             return out.reshape(-1, 4, 3)
         if what == "hex.X0":

@@ -322,3 +322,96 @@ def test_update_stiffness_matrix_large_rewrites_only_the_normal_strain_columns(d
         df = s.fem_add_dforce(np.zeros_like(x), (0.01 * y).astype(dtype), 1.0)
         res[sibling] = (f, df)
     assert np.abs(res[False][0] - res[True][0]).max() > 1e-3 and np.abs(res[False][1] - res[True][1]).max() > 1e-5
+
+
+# ---- FastTetrahedralCorotationalForceField: golden vectors of tests/FastTetrahedralCorotationalForceField_test.cpp:38-183 -------------------
+def _mat(rows):
+    return np.array(rows, np.float64)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_fast_tetrahedral_corotational_single_tetra_init(dtype):
+    """checkInit (:39-104): single tetra `2 3 1 0`, E=1000 nu=0.3, method "large" (= qr)."""
+    x = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype)
+    s = O.OracleScene(dtype, x)
+    s.set_fast_tets(np.array([[2, 3, 1, 0]], np.uint32), "large", 1000.0, 0.3)
+    exp_initRot = _mat([[0, 0.816497, 0.57735], [-0.707107, -0.408248, 0.57735], [0.707107, -0.408248, 0.57735]])
+    assert np.abs(s.get("fast.restRotations")[0].T - exp_initRot).max() < TOL          # "initRot.transpose(tetraInfo.restRotation)"
+    exp_shapeVector = _mat([[0, 1, 0], [0, 0, 1], [1, 0, 0], [-1, -1, -1]])
+    assert np.abs(s.get("fast.shapeVectors") - exp_shapeVector).max() < TOL
+    exp_diag = [_mat([[64.1026, 0, 0], [0, 224.359, 0], [0, 0, 64.1026]]), _mat([[64.1026, 0, 0], [0, 64.1026, 0], [0, 0, 224.359]]),
+                _mat([[224.359, 0, 0], [0, 64.1026, 0], [0, 0, 64.1026]]), _mat([[352.5641, 160.25641, 160.25641], [160.25641, 352.5641, 160.25641], [160.25641, 160.25641, 352.5641]])]
+    exp_dfdx = [_mat([[0, 0, 0], [0, 0, 64.1026], [0, 96.1538, 0]]), _mat([[0, 96.1538, 0], [64.1026, 0, 0], [0, 0, 0]]),
+                _mat([[-64.1026, -96.1538, 0], [-64.1026, -224.359, -64.1026], [0, -96.1538, -64.1026]]), _mat([[0, 0, 96.1538], [0, 0, 0], [64.1026, 0, 0]]),
+                _mat([[-64.1026, 0, -96.1538], [0, -64.1026, -96.1538], [-64.1026, -64.1026, -224.359]]), _mat([[-224.359, -64.1026, -64.1026], [-96.1538, -64.1026, 0], [-96.1538, 0, -64.1026]])]
+    # (the reference test compares 6 significant printed digits with 1e-4: the same 1e-3 allowance as for K above)
+    assert np.abs(s.get("fast.linearDfDxDiag") - np.array(exp_diag)).max() < 1e-3
+    assert np.abs(s.get("fast.linearDfDx") - np.array(exp_dfdx)).max() < 1e-3
+
+
+def _fast_grid_beam(dtype):
+    pos, hexas = O.regular_grid((4, 10, 4), (0, 0, 20), (10, 40, 30))
+    tets = O.hexas_to_tetras((4, 10, 4), 0)
+    s = O.OracleScene(dtype, pos)
+    s.set_params(gravity=(0, 10, 0), dt=0.01, iterations=20, tolerance=1e-5, threshold=1e-6)
+    s.set_mass_density(1.0, tets)
+    s.set_fast_tets(tets, "large", 600.0, 0.3)
+    s.set_fixed(O.box_roi(pos, (-1, -1, 0, 10, 1, 50)))
+    return s, pos
+
+
+def test_fast_tetrahedral_corotational_grid_beam_100_steps_double():
+    """checkFEMValues (:106-183): the 4x10x4 beam after 100 EulerImplicit + CG steps, element 100 -- pins init, addForce (qr), the per-edge
+    matrices of addDForce and the edge numbering (a wrong edge order or orientation moves node 159 away from the expected position)."""
+    s, pos = _fast_grid_beam(np.float64)
+    for _ in range(100):
+        s.step()
+    x = s.get("x")
+    assert np.abs(x[159] - [9.99985, 45.0487, 30.0011]).max() < TOL
+    e = 100
+    exp_initRot = _mat([[-1, 0, 0], [0, -0.8, -0.6], [0, -0.6, 0.8]])
+    assert np.abs(s.get("fast.restRotations")[e].T - exp_initRot).max() < TOL
+    exp_curRot = _mat([[0.99999985, 0.00032076406, -0.00043657642], [-0.00033142383, 0.99969634, -0.024639719], [0.00042854031, 0.024639861, 0.9996963]])
+    assert np.abs(s.get("fast.rotations")[e] - exp_curRot).max() < TOL
+    exp_shapeVector = _mat([[0.3, 0.224999, -0.3], [-0.3, 0, 0.3], [0, 0, -0.3], [0, -0.224999, 0.3]])
+    assert np.abs(s.get("fast.shapeVectors")[4 * e:4 * e + 4] - exp_shapeVector).max() < TOL
+    exp_diag = [_mat([[865.38462, 320.51282, -427.35043], [320.51282, 678.4188, -320.51282], [-427.35043, -320.51282, 865.38462]]),
+                _mat([[769.23077, 0, -427.35043], [0, 341.88034, 0], [-427.35043, 0, 769.23077]]),
+                _mat([[170.94017, 0, 0], [0, 170.94017, 0], [0, 0, 598.2906]]),
+                _mat([[267.09402, 0, 0], [0, 507.47863, -320.51282], [0, -320.51282, 694.44444]])]
+    exp_dfdx = [_mat([[-769.23077, -192.30769, 427.35043], [-128.20513, -341.88034, 128.20513], [427.35043, 192.30769, -769.23077]]),
+                _mat([[170.94017, 0, -170.94017], [0, 170.94017, -128.20513], [-256.41026, -192.30769, 598.2906]]),
+                _mat([[-267.09402, -128.20513, 170.94017], [-192.30769, -507.47863, 320.51282], [256.41026, 320.51282, -694.44444]]),
+                _mat([[-170.94017, 0, 170.94017], [0, -170.94017, 0], [256.41026, 0, -598.2906]]),
+                _mat([[170.94017, 128.20513, -170.94017], [192.30769, 170.94017, -192.30769], [-256.41026, -128.20513, 598.2906]]),
+                _mat([[-170.94017, 0, 0], [0, -170.94017, 192.30769], [0, 128.20513, -598.2906]])]
+    assert np.abs(s.get("fast.linearDfDxDiag")[4 * e:4 * e + 4] - np.array(exp_diag)).max() < 1e-3
+    # (the reference loop compares linearDfDx[id] for id < 4 only, :170-181; all six are printed in the expected values)
+    assert np.abs(s.get("fast.linearDfDx")[6 * e:6 * e + 6] - np.array(exp_dfdx)).max() < 1e-3
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("method", ["qr", "polar", "polar2", "none"])
+def test_fast_tetrahedral_corotational_dforce_is_force_derivative(dtype, method):
+    """ForceField_test's property (ForceFieldTestCreation.h:197-283) on the restatement: addDForce == d(addForce) for small dx, every rotation method,
+    and a rigid rotation of the rest shape gives no force (except `none`)."""
+    pos, hexas = O.regular_grid((3, 3, 4), (0, 0, 0), (1, 1, 2))
+    tets = O.hexas_to_tetras((3, 3, 4), 0)
+    s = O.OracleScene(dtype, pos)
+    s.set_fast_tets(tets, method, 1000.0, 0.3)
+    rng = np.random.default_rng(5)
+    x = (pos + 0.02 * rng.standard_normal(pos.shape)).astype(dtype)
+    eps = 1e-6 if dtype == np.float64 else 1e-3
+    dx = (eps * rng.standard_normal(pos.shape)).astype(dtype)
+    f0 = s.fem_add_force(np.zeros_like(x), x)
+    df = s.fem_add_dforce(np.zeros_like(x), dx, 1.0)       # (matrices assembled from the rotations of the addForce just before)
+    f1 = s.fem_add_force(np.zeros_like(x), (x + dx).astype(dtype))
+    num = (f1 - f0).astype(np.float64)
+    # the rotation's own derivative is not part of the corotational tangent: agreement to first order only
+    assert np.abs(num - df).max() <= 0.05 * np.abs(df).max() + (1e-9 if dtype == np.float64 else 2e-3)
+    if method != "none":
+        c, sn = np.cos(0.7), np.sin(0.7)
+        Rz = np.array([[c, -sn, 0], [sn, c, 0], [0, 0, 1]])
+        xr = (pos @ Rz.T + [0.3, -0.2, 0.1]).astype(dtype)
+        fr = s.fem_add_force(np.zeros_like(x), xr)
+        assert np.abs(fr).max() <= (1e-9 if dtype == np.float64 else 2e-2)
