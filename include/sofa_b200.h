@@ -48,7 +48,8 @@ extern "C" {
 typedef enum { SOFAB200_F32 = 0, SOFAB200_F64 = 1 } sofab200_real;
 
 /* TetrahedronFEMForceField `method` Data ([TFF].h:75-77, setMethod .inl) */
-typedef enum { SOFAB200_TET_SMALL = 0, SOFAB200_TET_LARGE = 1, SOFAB200_TET_POLAR = 2, SOFAB200_TET_SVD = 3 } sofab200_tet_method;
+typedef enum { SOFAB200_TET_SMALL = 0, SOFAB200_TET_LARGE = 1, SOFAB200_TET_POLAR = 2, SOFAB200_TET_SVD = 3,
+               SOFAB200_TET_POLAR2 = 4 /* FastTetrahedralCorotationalForceField only ("polar2") */ } sofab200_tet_method;
 /* HexahedronFEMForceField method numbering ([HFF].h setMethod: 0 large, 1 polar, 2 small) */
 typedef enum { SOFAB200_HEX_LARGE = 0, SOFAB200_HEX_POLAR = 1, SOFAB200_HEX_SMALL = 2 } sofab200_hex_method;
 
@@ -175,6 +176,14 @@ typedef struct sofab200_tetfem_desc {
                                      * its own computeVonMisesStress is not provided. */
     int compute_von_mises;          /* Data `computeVonMisesStress` (0 = off, 1 = corotational strain, 2 = Green-Lagrange strain):
                                      * non-zero makes init keep the shape-function matrices and Lame coefficients ([TFF].inl:278-282,1521-1541) */
+    int fast_corotational;          /* 1: the component is a FastTetrahedralCorotationalForceField (…/fem/elastic/FastTetrahedralCorotationalForceField.inl
+                                     * -- [FTC]): per tetrahedron six 3x3 edge blocks of the linear stiffness and a rotation ([FTC].inl:38-150, addForce
+                                     * :296-399); addDForce runs over the EDGES with one 3x3 matrix per edge, re-assembled from the tetrahedra after every
+                                     * addForce ([FTC].inl:402-470).  method: SOFAB200_TET_LARGE = "qr"/"large" (the class's default), _POLAR = "polar",
+                                     * _POLAR2 = "polar2", _SMALL = "none"/"linear"/"small".  No plasticity / von Mises / updateStiffnessMatrix /
+                                     * localStiffnessFactor Data; get_rotations / compute_von_mises / reset are not available; single GPU. */
+    size_t n_edges;                 /* fast_corotational: the topology's edge list (n_edges x 2) when it holds one; 0 = number the edges as            */
+    const uint32_t* edges;          /* TetrahedronSetTopologyContainer::createEdgesInTetrahedronArray does (first appearance, vertices sorted)        */
 } sofab200_tetfem_desc;
 
 /* init()+reinit() [TFF].inl:1257-1545: per-element material stiffness, rest rotation, rotated rest
@@ -194,7 +203,10 @@ int sofab200_tetfem_add_dforce(sofab200_tetfem* ff, void* df_dev, const void* dx
  *   "rotations" (T x 9, rotations[e] = R^T, [TFF].inl:880), "initialRotations" (T x 9),
  *   "strainDisplacements" (T x 12: the 12 distinct cofactors), "materialsStiffnesses" (T x 3: K00,K01,K33),
  *   "rotatedInitialElements" (T x 12), "initialTransformation" (T x 9, svd only),
- *   "plasticStrains" (T x 6, _plasticStrains; only with plastic_max_threshold > 0). */
+ *   "plasticStrains" (T x 6, _plasticStrains; only with plastic_max_threshold > 0).
+ * fast_corotational: "rotations" (T x 9, tetraInfo.rotation of the last addForce), "restRotations" (T x 9), "shapeVectors" (T x 4 x 3),
+ *   "linearDfDx" (T x 6 x 9), "linearDfDxDiag" (T x 4 x 9), "restEdgeVectors" (T x 6 x 3), "edgeOrientations" (T x 6),
+ *   "edgeInfo" (E x 9, d_edgeInfo as of the last addDForce), "edges" (E x 2 uint32), "n_edges" (one uint64). */
 int sofab200_tetfem_get(sofab200_tetfem* ff, const char* what, void* out_host);
 /* computeVonMisesStress() [TFF].inl:2196-2416 at positions x (the reference runs it on AnimateEndEvent): von Mises stress per element
  * (d_vonMisesPerElement, topology order) and per node (d_vonMisesPerNode: mean over the tetrahedra around the node, ascending index).

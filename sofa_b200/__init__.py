@@ -7,8 +7,9 @@ The computing is done by sofa_b200/lib/libsofa_b200.so (hand-written sm_100a CUD
 """
 from ._lib import F32, F64, Sofab200Error, load  # noqa: F401
 from .components import (Communicator, Context, DiagonalMass, MeshMatrixMass, UniformMass, PlaneForceField, FixedProjectiveConstraint, HexahedronFEMForceField,  # noqa: F401
-                         MechanicalObject, SolverNode, TetrahedralCorotationalFEMForceField, TetrahedronFEMForceField)
+                         MechanicalObject, SolverNode, TetrahedralCorotationalFEMForceField, TetrahedronFEMForceField,
+                         FastTetrahedralCorotationalForceField)
 from . import topology  # noqa: F401
 
-__all__ = ["Context", "Communicator", "MechanicalObject", "TetrahedronFEMForceField", "TetrahedralCorotationalFEMForceField", "HexahedronFEMForceField", "DiagonalMass", "MeshMatrixMass", "UniformMass", "PlaneForceField",
+__all__ = ["Context", "Communicator", "MechanicalObject", "TetrahedronFEMForceField", "TetrahedralCorotationalFEMForceField", "FastTetrahedralCorotationalForceField", "HexahedronFEMForceField", "DiagonalMass", "MeshMatrixMass", "UniformMass", "PlaneForceField",
            "FixedProjectiveConstraint", "SolverNode", "topology", "load", "Sofab200Error", "F32", "F64"]

@@ -22,7 +22,8 @@ class TetFemDesc(C.Structure):
     _fields_ = [("method", C.c_int), ("n_young", C.c_size_t), ("young", C.POINTER(C.c_double)), ("n_poisson", C.c_size_t),
                 ("poisson", C.POINTER(C.c_double)), ("n_local_stiffness", C.c_size_t), ("local_stiffness", C.POINTER(C.c_double)),
                 ("tile_elems", C.c_int), ("shared_nodes", C.POINTER(C.c_ubyte)),
-                ("plastic_max_threshold", C.c_double), ("plastic_yield_threshold", C.c_double), ("plastic_creep", C.c_double), ("update_stiffness_matrix", C.c_int), ("tetrahedral_corotational", C.c_int), ("compute_von_mises", C.c_int)]
+                ("plastic_max_threshold", C.c_double), ("plastic_yield_threshold", C.c_double), ("plastic_creep", C.c_double), ("update_stiffness_matrix", C.c_int), ("tetrahedral_corotational", C.c_int), ("compute_von_mises", C.c_int),
+                ("fast_corotational", C.c_int), ("n_edges", C.c_size_t), ("edges", C.POINTER(C.c_uint32))]
 
 
 class HexFemDesc(C.Structure):

@@ -253,6 +253,50 @@ class TetrahedralCorotationalFEMForceField(TetrahedronFEMForceField):
                          updateStiffnessMatrix=updateStiffnessMatrix)
 
 
+FAST_METHODS = {"qr": 1, "large": 1, "polar": 2, "polar2": 4, "none": 0, "linear": 0, "small": 0}      # d_method strings -> sofab200_tet_method
+
+
+class FastTetrahedralCorotationalForceField(TetrahedronFEMForceField):
+    """FastTetrahedralCorotationalForceField<B200Vec3Types> (FastTetrahedralCorotationalForceField.inl): Data youngModulus, poissonRatio, method
+    ("qr" -- the default --, "polar", "polar2", "none" and their synonyms).  addDForce runs over the topology's edges; `edges` is the topology's
+    own edge list when it has one, else the edges are numbered as TetrahedronSetTopologyContainer does.  Same handle type and calls as
+    TetrahedronFEMForceField, so a SolverNode takes it as its force field."""
+
+    def __init__(self, mstate, tetrahedra, youngModulus=5000.0, poissonRatio=0.45, method="qr", rayleighStiffness=0.0, edges=None, tileElems=0):
+        if method not in FAST_METHODS:
+            raise ValueError(f"method must be one of {list(FAST_METHODS)}")
+        self.mstate, self.ctx = mstate, mstate.ctx
+        self.method, self.rayleighStiffness = method, float(rayleighStiffness)
+        self.tetrahedra = np.ascontiguousarray(tetrahedra, np.uint32).reshape(-1, 4)
+        y, yp = _darr(youngModulus); p, pp = _darr(poissonRatio)
+        d = _lib.TetFemDesc(); d.method = FAST_METHODS[method]
+        d.n_young, d.young, d.n_poisson, d.poisson = len(y), yp, len(p), pp
+        d.tile_elems = int(tileElems)
+        d.fast_corotational = 1
+        if edges is not None:
+            self._edges = np.ascontiguousarray(edges, np.uint32).reshape(-1, 2)
+            d.n_edges, d.edges = self._edges.shape[0], self._edges.ctypes.data_as(C.POINTER(C.c_uint32))
+        self.h = _P()
+        rest = mstate.rest_position_host
+        check(self.ctx.L.sofab200_tetfem_create(self.ctx.h, mstate.real, mstate.size, rest.ctypes.data_as(_P), self.tetrahedra.shape[0],
+                                                self.tetrahedra.ctypes.data_as(_P), C.byref(d), C.byref(self.h)))
+
+    def get(self, what):
+        T = self.tetrahedra.shape[0]
+        if what in ("edges", "n_edges", "edgeInfo"):
+            n = np.zeros(1, np.uint64)
+            check(self.ctx.L.sofab200_tetfem_get(self.h, b"n_edges", n.ctypes.data_as(_P)))
+            if what == "n_edges":
+                return int(n[0])
+            out = np.empty((int(n[0]), 2), np.uint32) if what == "edges" else np.empty((int(n[0]), 3, 3), self.mstate.ndtype)
+        else:
+            shape = {"rotations": (T, 3, 3), "restRotations": (T, 3, 3), "shapeVectors": (T, 4, 3), "linearDfDx": (T, 6, 3, 3), "linearDfDxDiag": (T, 4, 3, 3),
+                     "restEdgeVectors": (T, 6, 3), "edgeOrientations": (T, 6)}[what]
+            out = np.empty(shape, self.mstate.ndtype)
+        check(self.ctx.L.sofab200_tetfem_get(self.h, what.encode(), out.ctypes.data_as(_P)))
+        return out
+
+
 class HexahedronFEMForceField:
     """HexahedronFEMForceField<B200Vec3Types>.  Data: youngModulus, poissonRatio, method (large | polar | small)."""
 

@@ -29,6 +29,7 @@ template <class R> int hex_cg_persistent(sofab200_hexfem* ff, R k_factor, Persis
 size_t hex_tile_node_count(sofab200_hexfem* ff);
 int hex_partial_count(sofab200_hexfem* ff);
 int tet_real(sofab200_tetfem* ff); size_t tet_nodes(sofab200_tetfem* ff);
+bool tet_is_fast(sofab200_tetfem* ff);
 int hex_real(sofab200_hexfem* ff); size_t hex_nodes(sofab200_hexfem* ff);
 }  // namespace sb
 
@@ -681,6 +682,7 @@ template <class R> static int node_set_distributed(Node<R>* nd, sofab200_comm* c
     // every rank applies the per-node epilogue to its copy of an interface node and the copies are then summed over the sharers: only the
     // DiagonalMass term is masked by ownership (the caller zeroes vertexMass on the non-owned copies).  PlaneForceField, UniformMass and
     // MeshMatrixMass terms would be counted once per sharing rank.
+    if (nd->tet && tet_is_fast(nd->tet)) return fail(SOFAB200_ERR_UNSUPPORTED, "FastTetrahedralCorotationalForceField is not partitioned over GPUs (its per-edge matrices sum over tetrahedra of several partitions)");
     if (nd->has_plane) return fail(SOFAB200_ERR_UNSUPPORTED, "a node with a PlaneForceField cannot be distributed (its term would be counted once per sharing rank on interface nodes)");
     if (nd->uniform_mass) return fail(SOFAB200_ERR_UNSUPPORTED, "a node with a UniformMass cannot be distributed; use a DiagonalMass whose vertexMass is zero on non-owned interface nodes");
     if (nd->mesh_mass) return fail(SOFAB200_ERR_UNSUPPORTED, "MeshMatrixMass is not available in a distributed node");

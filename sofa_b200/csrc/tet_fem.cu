@@ -6,12 +6,7 @@
 
 using namespace sb;
 
-struct sofab200_tetfem {
-    virtual ~sofab200_tetfem() {}
-    sofab200_ctx* ctx = nullptr;
-    int real = 0, method = 1;
-    size_t n_nodes = 0, n_tets = 0;
-};
+#include "tet_handle.h"
 
 namespace sb {
 
@@ -135,6 +130,7 @@ template <class R, int MODE, int MAXT, bool PF> static int tet_persist_variant(T
 }
 // dry_run: only tell whether the mesh fits the kernel (SOFAB200_OK) or not (kPersistNotEligible)
 template <class R> int tet_cg_persistent(sofab200_tetfem* base, R k_factor, PersistCG<R> a, size_t sync_capacity, bool dry_run) {
+    if (base->kind == 1) return kPersistNotEligible;      // FastTetrahedralCorotationalForceField: the multi-kernel loop
     TetFF<R>& ff = *static_cast<TetFF<R>*>(base);
     TetDev<R> d = ff.dev();
     d.k_factor = k_factor;
@@ -192,6 +188,7 @@ template <class R, int MODE, bool PF, int ET, int GT> static int tet_fused_varia
     return tet_fused_launch<R, MODE, PF, ET, GT, false>(ff, d, a, Ls, grid, dry_run, info);
 }
 template <class R> int tet_cg_fused(sofab200_tetfem* base, R k_factor, FusedCG<R> a, size_t sync_capacity, bool dry_run, int* info) {
+    if (base->kind == 1) return kPersistNotEligible;      // FastTetrahedralCorotationalForceField: the multi-kernel loop
     TetFF<R>& ff = *static_cast<TetFF<R>*>(base);
     TetDev<R> d = ff.dev();
     d.k_factor = k_factor;
@@ -210,17 +207,19 @@ template <class R> int tet_cg_fused(sofab200_tetfem* base, R k_factor, FusedCG<R
 template int tet_cg_fused<float>(sofab200_tetfem*, float, FusedCG<float>, size_t, bool, int*);
 template int tet_cg_fused<double>(sofab200_tetfem*, double, FusedCG<double>, size_t, bool, int*);
 size_t tet_shared_slot_count(sofab200_tetfem* base) {
+    if (base->kind == 1) return fast_shared_slot_count(base);
     if (base->real == SOFAB200_F32) return size_t(static_cast<TetFF<float>*>(base)->h.plan.n_chunks) * kGatherChunk;
     return size_t(static_cast<TetFF<double>*>(base)->h.plan.n_chunks) * kGatherChunk;
 }
 
 // Element pass + boundary gather with a caller-provided epilogue (also used by the solver node).
-template <class R> TileDev<R> tet_tiledev(sofab200_tetfem* base) { return static_cast<TetFF<R>*>(base)->dev().t; }
+template <class R> TileDev<R> tet_tiledev(sofab200_tetfem* base) { if (base->kind == 1) return fast_tiledev<R>(base); return static_cast<TetFF<R>*>(base)->dev().t; }
 template TileDev<float> tet_tiledev<float>(sofab200_tetfem*);
 template TileDev<double> tet_tiledev<double>(sofab200_tetfem*);
 
 // skip_gather: the caller sums the shared nodes itself (fused CG tail kernel)
 template <class R> int tet_run(sofab200_tetfem* base, bool dforce, const R* in, R k_factor, NodeEpilogue<R> ep, bool skip_gather) {
+    if (base->kind == 1) return fast_run<R>(base, dforce, in, k_factor, ep, skip_gather);
     TetFF<R>& ff = *static_cast<TetFF<R>*>(base);
     const HostPlan& plan = ff.h.plan;
     SB_CHECK((!ep.mdx_src || ep.mdx_src == in) && (!ep.dot_with || ep.dot_with == in) && (!ep.plane_mode || ep.plane_in == in), "mass / dot / plane operands must be the pass's input vector");
@@ -256,17 +255,22 @@ template int tet_run<float>(sofab200_tetfem*, bool, const float*, float, NodeEpi
 template int tet_run<double>(sofab200_tetfem*, bool, const double*, double, NodeEpilogue<double>, bool);
 
 int tet_real(sofab200_tetfem* ff) { return ff->real; }
+bool tet_is_fast(sofab200_tetfem* ff) { return ff->kind == 1; }
 // the plan's table of shared nodes (chunks of kGatherChunk, 0xFFFFFFFF = padding), for the multi-GPU set-up
 const std::vector<uint32_t>& tet_shared_node_table(sofab200_tetfem* base) {
+    static const std::vector<uint32_t> none;
+    if (base->kind == 1) return none;
     if (base->real == SOFAB200_F32) return static_cast<TetFF<float>*>(base)->h.plan.sh_nodes;
     return static_cast<TetFF<double>*>(base)->h.plan.sh_nodes;
 }
 size_t tet_tile_node_count(sofab200_tetfem* base) {
+    if (base->kind == 1) return fast_tile_node_count(base);
     if (base->real == SOFAB200_F32) return static_cast<TetFF<float>*>(base)->h.plan.tile_nodes.size();
     return static_cast<TetFF<double>*>(base)->h.plan.tile_nodes.size();
 }
 size_t tet_nodes(sofab200_tetfem* ff) { return ff->n_nodes; }
 int tet_partial_count(sofab200_tetfem* base) {
+    if (base->kind == 1) return fast_partial_count(base);
     if (base->real == SOFAB200_F32) { auto& ff = *static_cast<TetFF<float>*>(base); return ff.h.plan.n_tiles + ff.h.plan.n_chunks; }
     auto& ff = *static_cast<TetFF<double>*>(base); return ff.h.plan.n_tiles + ff.h.plan.n_chunks;
 }
@@ -409,6 +413,12 @@ extern "C" {
 int sofab200_tetfem_create(sofab200_ctx* ctx, sofab200_real real, size_t n_nodes, const void* rest_position_host, size_t n_tets,
                            const uint32_t* tets_host, const sofab200_tetfem_desc* desc, sofab200_tetfem** out) {
     SB_CHECK(ctx && out && desc && rest_position_host && (tets_host || n_tets == 0), "null argument");
+    if (desc->fast_corotational) {
+        SB_CHECK(desc->n_young > 0 && desc->young && desc->n_poisson > 0 && desc->poisson, "youngModulus / poissonRatio are required");
+        SB_CHECK(n_nodes < 0xFFFFFFFFull && n_tets < 0x0FFFFFFFull, "mesh too large for 32-bit indices");
+        SB_CUDA(cudaSetDevice(ctx->device));
+        return fast_create(ctx, int(real), n_nodes, rest_position_host, n_tets, tets_host, desc, out);
+    }
     SB_CHECK(desc->method >= 0 && desc->method <= 3, "method must be small, large, polar or svd");
     if (desc->tetrahedral_corotational) {
         SB_CHECK(desc->method != SOFAB200_TET_SVD, "TetrahedralCorotationalFEMForceField has no svd method");
@@ -445,27 +455,32 @@ int sofab200_tetfem_add_dforce(sofab200_tetfem* ff, void* df_dev, const void* dx
 }
 int sofab200_tetfem_get(sofab200_tetfem* ff, const char* what, void* out_host) {
     SB_CHECK(ff && what && out_host, "null argument");
+    if (ff->kind == 1) return fast_get(ff, what, out_host);
     if (ff->real == SOFAB200_F32) return tet_get(*static_cast<TetFF<float>*>(ff), what, out_host);
     return tet_get(*static_cast<TetFF<double>*>(ff), what, out_host);
 }
 int sofab200_tetfem_compute_von_mises(sofab200_tetfem* ff, const void* x_dev, void* per_element_dev, void* per_node_dev) {
     SB_CHECK(ff && x_dev, "null argument");
+    if (ff->kind == 1) return fail(SOFAB200_ERR_UNSUPPORTED, "FastTetrahedralCorotationalForceField has no computeVonMisesStress");
     if (ff->real == SOFAB200_F32) return tet_von_mises(*static_cast<TetFF<float>*>(ff), static_cast<const float*>(x_dev), static_cast<float*>(per_element_dev), static_cast<float*>(per_node_dev));
     return tet_von_mises(*static_cast<TetFF<double>*>(ff), static_cast<const double*>(x_dev), static_cast<double*>(per_element_dev), static_cast<double*>(per_node_dev));
 }
 int sofab200_tetfem_reset(sofab200_tetfem* ff) {
     SB_CHECK(ff, "null argument");
+    if (ff->kind == 1) return SOFAB200_OK;      // (no plastic strain to clear)
     if (ff->real == SOFAB200_F32) { auto* f = static_cast<TetFF<float>*>(ff); SB_TRY(f->pl0.zero(ff->ctx->stream)); SB_TRY(f->pl1.zero(ff->ctx->stream)); }
     else { auto* f = static_cast<TetFF<double>*>(ff); SB_TRY(f->pl0.zero(ff->ctx->stream)); SB_TRY(f->pl1.zero(ff->ctx->stream)); }
     return SOFAB200_OK;
 }
 int sofab200_tetfem_get_rotations(sofab200_tetfem* ff, void* vecR_dev) {
     SB_CHECK(ff && vecR_dev, "null argument");
+    if (ff->kind == 1) return fail(SOFAB200_ERR_UNSUPPORTED, "FastTetrahedralCorotationalForceField has no getRotations");
     if (ff->real == SOFAB200_F32) return tet_node_rotations(*static_cast<TetFF<float>*>(ff), static_cast<float*>(vecR_dev));
     return tet_node_rotations(*static_cast<TetFF<double>*>(ff), static_cast<double*>(vecR_dev));
 }
 int sofab200_tetfem_stats(const sofab200_tetfem* ff, uint64_t out[8]) {
     SB_CHECK(ff && out, "null argument");
+    if (ff->kind == 1) return fast_stats(ff, out);
     const HostPlan* P; size_t smem;
     if (ff->real == SOFAB200_F32) { auto* f = static_cast<const TetFF<float>*>(ff); P = &f->h.plan; smem = f->h.smem_bytes; }
     else { auto* f = static_cast<const TetFF<double>*>(ff); P = &f->h.plan; smem = f->h.smem_bytes; }
