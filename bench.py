@@ -38,6 +38,8 @@ WORKLOADS = {
     # liver.scn as written (Demos/liver.scn: 181 nodes, 596 tetrahedra, TetrahedralCorotationalFEMForceField), rotations by polar decomposition
     "C4": dict(kind="liver", method="polar", young=3000.0, poisson=0.3, density=1.0, gravity=(0.0, -9.81, 0.0), dt=0.02, rK=0.1, rM=0.1,
                iterations=CG_ITERS, tolerance=1e-9, threshold=1e-9),
+    # C2's mesh under FastTetrahedralCorotationalForceField (method "qr", the class's default): the CG loop runs over the EDGES
+    "C2_FAST": dict(kind="fast", n=(33, 33, 161), mn=(0, 0, 0), mx=(4, 4, 20), box=(-1, -1, -1, 5, 5, 1e-6), method="qr", **GRID),
     "C5": dict(kind="tet", n=(129, 129, 161), mn=(0, 0, 0), mx=(16, 16, 20), box=(-1, -1, -1, 17, 17, 1e-6), method="large", **GRID),
     "C1": dict(kind="tet", n=(5, 5, 20), mn=(-5, -5, 0), mx=(5, 5, 40), box=(-6, -6, -1, 50, 6, 0.1), method="large", **GRID),   # the reference's example scene (1824 tets): pure latency
     "SMALL": dict(kind="tet", n=(17, 17, 41), mn=(0, 0, 0), mx=(4, 4, 10), box=(-1, -1, -1, 5, 5, 1e-6), method="large", **GRID),
@@ -66,7 +68,8 @@ def build_mesh(name, stretch=1):
 def workload_string(name, n_elems, n_nodes, dtype):
     """The same string in both arms (the driver compares them)."""
     w = WORKLOADS[name]
-    what = {"tet": "tetrahedra, TetrahedronFEMForceField", "hex": "hexahedra, HexahedronFEMForceField", "liver": "tetrahedra (Demos/liver.scn mesh), TetrahedralCorotationalFEMForceField"}[w["kind"]]
+    what = {"tet": "tetrahedra, TetrahedronFEMForceField", "hex": "hexahedra, HexahedronFEMForceField", "liver": "tetrahedra (Demos/liver.scn mesh), TetrahedralCorotationalFEMForceField",
+            "fast": "tetrahedra, FastTetrahedralCorotationalForceField"}[w["kind"]]
     grid = f"RegularGridTopology {w['n']} cantilever, " if "n" in w else ""
     return (f"{name}: {grid}{n_elems} {what} method={w['method']} E={w['young']:g} nu={w['poisson']:g}, {n_nodes} nodes, Vec3{'f' if dtype == 'f32' else 'd'}, "
             f"DiagonalMass, FixedProjectiveConstraint, EulerImplicit rayleigh {w['rK']:g}/{w['rM']:g} dt={w['dt']:g}, CG {w['iterations']} it (tol {w['tolerance']:g})")
@@ -78,6 +81,8 @@ def algorithmic_bytes(kind, E, N, s):
     is E*(32+9s) (indices + rotation) + N*34s -- both are reported, the roofline uses the second."""
     if kind == "hex":
         return dict(cg_iteration=E * (32 + 9 * s) + N * 34 * s, cg_iteration_survey=E * (32 + 309 * s) + N * 34 * s)
+    if kind == "fast":      # E = number of EDGES: two indices + the edge's 3x3 matrix, plus the node streams
+        return dict(cg_iteration=E * (8 + 9 * s) + N * 34 * s)
     return dict(cg_iteration=E * (16 + 20 * s) + N * 34 * s)
 
 
@@ -213,6 +218,8 @@ def oracle_scene(workload, dtype, threads):
     s.set_mass_density(w["density"], elems)
     if w["kind"] == "hex":
         s.set_hexas(elems, w["method"], w["young"], w["poisson"])
+    elif w["kind"] == "fast":
+        s.set_fast_tets(elems, w["method"], w["young"], w["poisson"])
     else:
         s.set_tets(elems, w["method"], w["young"], w["poisson"])
         if w["kind"] == "liver":
@@ -231,7 +238,8 @@ def cpu_baseline(workload, dtype, steps, warmup, threads):
     for _ in range(steps):
         iters += min(s.step(), WORKLOADS[workload]["iterations"])
     dt = time.perf_counter() - t0
-    par = {"tet": "ParallelTetrahedronFEMForceField-style addDForce", "hex": "ParallelHexahedronFEMForceField-style addDForce", "liver": "ParallelTetrahedronFEMForceField-style addDForce"}[WORKLOADS[workload]["kind"]]
+    par = {"tet": "ParallelTetrahedronFEMForceField-style addDForce", "hex": "ParallelHexahedronFEMForceField-style addDForce", "liver": "ParallelTetrahedronFEMForceField-style addDForce",
+           "fast": "sequential addDForce (the MultiThreading plugin has no parallel FastTetrahedralCorotationalForceField)"}[WORKLOADS[workload]["kind"]]
     return dict(value=iters / dt, unit="cg_iters/s", cores=threads, kind="port", steps_per_s=steps / dt,
                 sample=f"{steps} EulerImplicit steps ({iters} CG iterations) of workload {workload} ({E} elements, Vec3{'f' if dtype == 'f32' else 'd'}) after {warmup} warm-up steps, "
                        f"oracle -O3 no-fma, {'sequential (the reference classes as they are)' if threads == 1 else par + f' on {threads} threads'}")
@@ -297,6 +305,8 @@ def build_node(ctx, workload, dtype, tile=0):
         ff = sb.HexahedronFEMForceField(mo, elems, youngModulus=w["young"], poissonRatio=w["poisson"], method=w["method"], tileElems=tile)
     elif w["kind"] == "liver":
         ff = sb.TetrahedralCorotationalFEMForceField(mo, elems, youngModulus=w["young"], poissonRatio=w["poisson"], method=w["method"])
+    elif w["kind"] == "fast":
+        ff = sb.FastTetrahedralCorotationalForceField(mo, elems, youngModulus=w["young"], poissonRatio=w["poisson"], method=w["method"])
     else:
         ff = sb.TetrahedronFEMForceField(mo, elems, youngModulus=w["young"], poissonRatio=w["poisson"], method=w["method"], tileElems=tile)
     mass = sb.DiagonalMass(mo, elems, massDensity=w["density"])
@@ -305,6 +315,8 @@ def build_node(ctx, workload, dtype, tile=0):
     import torch
     torch.cuda.synchronize()
     create_s = time.perf_counter() - t0
+    if w["kind"] == "fast":
+        return node, ff, dict(pos=pos, E=ff.get("n_edges"), N=pos.shape[0], kind="fast", create_s=create_s, mo=mo, n_tets=elems.shape[0])
     return node, ff, dict(pos=pos, E=elems.shape[0], N=pos.shape[0], kind="hex" if w["kind"] == "hex" else "tet", create_s=create_s, mo=mo)
 
 
@@ -341,9 +353,9 @@ def kernel_roofline(prof, ab, iters_per_step, kind, peak, peak_src):
     ep = prof["cg_persistent"] if fused else prof["element_pass_dforce"]
     k_ms = ep["ms"] / max(ep["launches"], 1)
     k_bytes = ab["cg_iteration"] * iters_per_step if fused else ab["cg_iteration"]
-    k_name = (f"fused_cg_kernel<{'Hex' if kind == 'hex' else 'Tet'}Pass> (the whole CGLinearSolver loop, {iters_per_step} iterations per launch: A*p element pass, "
+    k_name = (f"fused_cg_kernel<{'Hex' if kind == 'hex' else ('Edge' if kind == 'fast' else 'Tet')}Pass> (the whole CGLinearSolver loop, {iters_per_step} iterations per launch: A*p element pass, "
               "shared-node sums, x/r/p updates, one reduction of four dot products per iteration)") if fused else \
-             f"{'hex' if kind == 'hex' else 'tet'}_tile_kernel (A*p element pass of the multi-kernel loop)"
+             ("fast_edge_kernel (A*p over the edges of the multi-kernel loop)" if kind == "fast" else f"{'hex' if kind == 'hex' else 'tet'}_tile_kernel (A*p element pass of the multi-kernel loop)")
     achieved = k_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     return dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, kernel=k_name, algorithmic_bytes_per_launch=k_bytes,
                 avg_launch_ms=k_ms, launches_timed=ep["launches"], peak_source=peak_src), fused
@@ -360,10 +372,13 @@ def run_config(ctx, workload, dtype, steps, warmup, peak, peak_src, local=0):
     prof = profile_steps(ctx, node, min(steps, 10))
     ab = algorithmic_bytes(meta["kind"], meta["E"], meta["N"], s)
     roof, fused = kernel_roofline(prof, ab, it, meta["kind"], peak, peak_src)
-    out = {"workload": workload_string(workload, meta["E"], meta["N"], dtype), "dtype": dtype, "value": it * steps / (ms * 1e-3), "unit": "cg_iters/s",
+    out = {"workload": workload_string(workload, meta.get("n_tets", meta["E"]), meta["N"], dtype), "dtype": dtype, "value": it * steps / (ms * 1e-3), "unit": "cg_iters/s",
            "ms_per_step": ms / steps, "us_per_step": 1e3 * ms / steps, "steps_per_s": steps / (ms * 1e-3), "cg_iters_per_step": it, "steps": steps, "warmup": warmup,
            "create_s": meta["create_s"], "roofline": roof, "gpu_launches": launches, "layout": ff.stats(), "clocks": clocks,
            "algorithmic_bytes_per_cg_iteration": ab}
+    if meta["kind"] == "fast":
+        out["edges"] = int(meta["E"])
+        out["roofline"]["note"] = "addDForce of this class runs over the topology's edges (one 3x3 matrix per edge): algorithmic bytes = edges x (8 + 9s) + nodes x 34s"
     if meta["kind"] == "hex":
         out["roofline"]["note"] = ("issue-bound, not HBM-bound: 1152 FMUL + 1128 FADD per hexahedron (24x24 K_e row sums without FMA, the reference's rounding) "
                                    "= 2280 fp32 instructions per 68 bytes; the HBM fraction is reported for completeness")
@@ -433,7 +448,7 @@ def run_ours(args):
         "metric": "cg_iters_per_s", "value": value, "unit": unit_for(wl), "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if wl == "C5" else "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
         "steps_per_s": args.steps / (ms * 1e-3), "cg_iters_per_step": iters_per_step, "true_cg_iters_per_s": value, "create_s": meta["create_s"],
-        "config": {"workload": workload_string(wl, E, N, dtype), "partition": "single GPU: one partition = the whole mesh, so partition_cg_iters/s == CG iterations/s",
+        "config": {"workload": workload_string(wl, meta.get("n_tets", E), N, dtype), "partition": "single GPU: one partition = the whole mesh, so partition_cg_iters/s == CG iterations/s",
                    "l2": f"working set per CG iteration exceeds the 126 MB L2 ({(E * 120 + N * 34 * s) / 1e6:.0f} MB streamed)" if meta["kind"] == "tet" and E * 120 > 126e6 else
                          "working set per CG iteration fits the 126 MB L2 (inputs are not larger than L2; no flush between steps: the steady state of the simulation loop is what is measured)",
                    "layout": ff.stats()},
@@ -447,7 +462,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     if wl == "C2" and dtype == "f32" and not args.no_configs:
         cfgs = {}
-        for name, (w2, d2, st, wu) in {"C3_f32": ("C3", "f32", 20, 3), "C2_f64": ("C2", "f64", 30, 3), "C4_f32": ("C4", "f32", 200, 5)}.items():
+        for name, (w2, d2, st, wu) in {"C3_f32": ("C3", "f32", 20, 3), "C2_f64": ("C2", "f64", 30, 3), "C4_f32": ("C4", "f32", 200, 5), "C2_FAST_f32": ("C2_FAST", "f32", 20, 3)}.items():
             try:
                 cfgs[name] = run_config(ctx, w2, d2, st, wu, peak, peak_src, local)
             except Exception as e:  # a secondary configuration must not take the headline line down

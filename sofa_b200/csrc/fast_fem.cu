@@ -20,6 +20,7 @@
 #include <map>
 #include <memory>
 
+#include "cg_fused.cuh"
 #include "fem_layout.cuh"
 #include "math3.cuh"
 #include "plan.h"
@@ -230,6 +231,36 @@ __global__ void __launch_bounds__(256) fast_edge_kernel(FastDev<R> d, const R* _
         finish_dot(ep, tot, red, false);
     }
 }
+
+// element policy of the fused CG kernel (cg_fused.cuh): the whole CGLinearSolver loop in one persistent launch, A*p over the edges.
+// (The kernel's epilogue subtracts the contributions -- it computes q = (m M + b B + k K) p with the stiffness term as `df -= ...` -- hence
+// the signs of fast_edge_kernel's `minus` branch.)
+template <class R> struct EdgePass {
+    typedef FastDev<R> Dev;
+    static __device__ __forceinline__ const TileDev<R>& tiles(const Dev& d) { return d.t; }
+    struct First {};
+    static __device__ __forceinline__ void prefetch(const Dev&, int, First&) {}
+    template <int ET, class OnBoundary>
+    static __device__ __forceinline__ void elements(const Dev& d, int tile, const typename SVec<R>::T* s_in, R* s_slot, int max_slots, unsigned char*, int arrive_at, OnBoundary on_boundary,
+                                                    const First&) {
+        typedef typename SVec<R>::T SV;
+        const TileDev<R>& t = d.t;
+        const uint64_t pol_keep = l2_policy_evict_last();
+        for (int le = threadIdx.x; le < t.tile_e; le += ET) {
+            if (le - int(threadIdx.x) == arrive_at) on_boundary();
+            const size_t es = size_t(tile) * t.tile_e + le;
+            const ushort2 ln = d.elnode[es];
+            if (ln.x == 0xFFFFu) continue;
+            const uint2 sl = d.eslot[es];
+            const SV p0 = s_in[ln.x], p1 = s_in[ln.y];
+            const V3<R> deltax = (mk3<R>(p1.x, p1.y, p1.z) - mk3<R>(p0.x, p0.y, p0.z)) * d.k_factor;
+            const M3<R> M = fast_load_mat(d.emat, d.NSe, es);
+            const V3<R> c1 = mul(M, deltax), c0 = mul_t(M, deltax);
+            tile_scatter<R>(t, sl.x, c0.x, c0.y, c0.z, s_slot, max_slots, pol_keep);
+            tile_scatter<R>(t, sl.y, -c1.x, -c1.y, -c1.z, s_slot, max_slots, pol_keep);
+        }
+    }
+};
 
 // ---- host side ---------------------------------------------------------------------------------------------------------------------------------
 template <class R> struct PlanBufs {
@@ -480,13 +511,7 @@ template <class R> int fast_run(sofab200_tetfem* base, bool dforce, const R* in,
         }
         ff.update_matrix = true;          // "next time assemble the matrix", [FTC].inl:396
     } else {
-        if (ff.update_matrix) {
-            ff.update_matrix = false;
-            const size_t NSe = d.NSe;
-            fast_edge_assemble_kernel<R><<<unsigned((NSe + 127) / 128), 128, 0, ff.ctx->stream>>>(NSe, ff.eorder.p, ff.inc_off.p, ff.inc.p, ff.rec.p, d.NS, ff.rot.p, ff.emat.p);
-            ff.ctx->launches++;
-            SB_CUDA(cudaGetLastError());
-        }
+        SB_TRY(fast_assemble(ff));
         auto kern = fast_edge_kernel<R>;
         if (ff.esmem > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ff.esmem)));
         ff.ctx->prof_start(0);
@@ -506,6 +531,64 @@ template <class R> int fast_run(sofab200_tetfem* base, bool dforce, const R* in,
 }
 template int fast_run<float>(sofab200_tetfem*, bool, const float*, float, NodeEpilogue<float>, bool);
 template int fast_run<double>(sofab200_tetfem*, bool, const double*, double, NodeEpilogue<double>, bool);
+
+template <class R> static int fast_assemble(FastFF<R>& ff) {
+    if (!ff.update_matrix) return SOFAB200_OK;
+    ff.update_matrix = false;
+    const size_t NSe = size_t(ff.eplan.n_tiles) * ff.eplan.tile_e, NS = size_t(ff.tplan.n_tiles) * ff.tplan.tile_e;
+    fast_edge_assemble_kernel<R><<<unsigned((NSe + 127) / 128), 128, 0, ff.ctx->stream>>>(NSe, ff.eorder.p, ff.inc_off.p, ff.inc.p, ff.rec.p, NS, ff.rot.p, ff.emat.p);
+    ff.ctx->launches++;
+    SB_CUDA(cudaGetLastError());
+    return SOFAB200_OK;
+}
+
+// the whole CG loop in the fused persistent kernel, A*p over the edges: cached tile state when the CTA's (at most two) tiles fit, else streamed
+template <class R, bool CACHED> static int fast_fused_launch(FastFF<R>& ff, FastDev<R> d, FusedCG<R> a, const FusedLayout& L, int grid, bool dry_run, int* info) {
+    constexpr int ET = sizeof(R) == 4 ? 512 : 256;
+    auto kern = fused_cg_kernel<R, EdgePass<R>, ET, 0, CACHED>;
+    cudaFuncAttributes fa;
+    SB_CUDA(cudaFuncGetAttributes(&fa, kern));
+    int dev_smem_optin = 0;
+    SB_CUDA(cudaDeviceGetAttribute(&dev_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ff.ctx->device));
+    if (L.total + fa.sharedSizeBytes > size_t(dev_smem_optin)) return kPersistNotEligible;
+    SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<unsigned>(L.total, 1024))));
+    int per_sm = 0;
+    SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ET, L.total));
+    if (per_sm < 1) return kPersistNotEligible;
+    if (info) { info[0] = grid; info[1] = L.tiles_per_cta; info[2] = L.cached; info[3] = int(L.total); info[4] = ET; info[5] = 0; }
+    if (dry_run) return SOFAB200_OK;
+    SB_TRY(fast_assemble(ff));
+    a.lay = L;
+    int ded_share = 0;
+    void* args[] = {&d, &a, &ded_share};
+    ff.ctx->prof_start(4);
+    SB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(ET), args, L.total, ff.ctx->stream));
+    ff.ctx->prof_stop(4);
+    ff.ctx->launches++;
+    return SOFAB200_OK;
+}
+template <class R> int fast_cg_fused(sofab200_tetfem* base, R k_factor, FusedCG<R> a, size_t sync_capacity, bool dry_run, int* info) {
+    FastFF<R>& ff = *static_cast<FastFF<R>*>(base);
+    { const char* env = getenv("SOFAB200_FAST_FUSED"); if (env && atoi(env) == 0) return kPersistNotEligible; }
+    if (a.ep.sign >= 0) return kPersistNotEligible;      // (EdgePass writes the contributions for a subtracting epilogue)
+    FastDev<R> d = ff.dev(true);
+    d.k_factor = k_factor;
+    const HostPlan& P = ff.eplan;
+    const int grid = std::max(1, std::min(ff.ctx->sm_count, P.n_tiles));
+    const int tiles_per_cta = (P.n_tiles + grid - 1) / grid;
+    const int n_units = P.n_chunks * (kGatherChunk / kUnit);
+    const int units_per_cta = (n_units + grid - 1) / grid;
+    if (fused_sync_words(grid) > sync_capacity) return fail(SOFAB200_ERR_INVALID, "sync buffer too small for the fused CG kernel");
+    const FusedLayout Lc = fused_layout<R>(true, tiles_per_cta, units_per_cta, P.max_touched, P.max_slots, P.max_int, P.max_shtouch, P.maxval);
+    if (tiles_per_cta <= 2 && Lc.total + 2048 <= 196 * 1024) {
+        const int rc = fast_fused_launch<R, true>(ff, d, a, Lc, grid, dry_run, info);
+        if (rc != kPersistNotEligible) return rc;
+    }
+    const FusedLayout Ls = fused_layout<R>(false, tiles_per_cta, units_per_cta, P.max_touched, P.max_slots, P.max_int, P.max_shtouch, P.maxval);
+    return fast_fused_launch<R, false>(ff, d, a, Ls, grid, dry_run, info);
+}
+template int fast_cg_fused<float>(sofab200_tetfem*, float, FusedCG<float>, size_t, bool, int*);
+template int fast_cg_fused<double>(sofab200_tetfem*, double, FusedCG<double>, size_t, bool, int*);
 
 template <class R> TileDev<R> fast_tiledev(sofab200_tetfem* base) { FastFF<R>& ff = *static_cast<FastFF<R>*>(base); return ff.eb.dev(ff.eplan); }
 template TileDev<float> fast_tiledev<float>(sofab200_tetfem*);

@@ -188,7 +188,7 @@ template <class R, int MODE, bool PF, int ET, int GT> static int tet_fused_varia
     return tet_fused_launch<R, MODE, PF, ET, GT, false>(ff, d, a, Ls, grid, dry_run, info);
 }
 template <class R> int tet_cg_fused(sofab200_tetfem* base, R k_factor, FusedCG<R> a, size_t sync_capacity, bool dry_run, int* info) {
-    if (base->kind == 1) return kPersistNotEligible;      // FastTetrahedralCorotationalForceField: the multi-kernel loop
+    if (base->kind == 1) return fast_cg_fused<R>(base, k_factor, a, sync_capacity, dry_run, info);      // FastTetrahedralCorotationalForceField: A*p over the edges (fast_fem.cu)
     TetFF<R>& ff = *static_cast<TetFF<R>*>(base);
     TetDev<R> d = ff.dev();
     d.k_factor = k_factor;

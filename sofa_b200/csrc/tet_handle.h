@@ -14,9 +14,11 @@ struct sofab200_tetfem {
 namespace sb {
 template <class R> struct NodeEpilogue;
 template <class R> struct TileDev;
+template <class R> struct FusedCG;
 // fast_fem.cu
 int fast_create(sofab200_ctx* ctx, int real, size_t n_nodes, const void* rest, size_t n_tets, const uint32_t* tets, const sofab200_tetfem_desc* desc, sofab200_tetfem** out);
 template <class R> int fast_run(sofab200_tetfem* ff, bool dforce, const R* in, R k_factor, NodeEpilogue<R> ep, bool skip_gather);
+template <class R> int fast_cg_fused(sofab200_tetfem* ff, R k_factor, FusedCG<R> a, size_t sync_capacity, bool dry_run, int* info);
 template <class R> TileDev<R> fast_tiledev(sofab200_tetfem* ff);          // the plan of the addDForce pass (edges)
 int fast_partial_count(sofab200_tetfem* ff);
 size_t fast_tile_node_count(sofab200_tetfem* ff);

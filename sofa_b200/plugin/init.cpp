@@ -10,6 +10,7 @@ void registerMechanicalObject(sofa::core::ObjectFactory*);
 void registerTetrahedronFEMForceField(sofa::core::ObjectFactory*);
 void registerHexahedronFEMForceField(sofa::core::ObjectFactory*);
 void registerTetrahedralCorotationalFEMForceField(sofa::core::ObjectFactory*);
+void registerFastTetrahedralCorotationalForceField(sofa::core::ObjectFactory*);
 void registerMeshMatrixMass(sofa::core::ObjectFactory*);
 void registerDiagonalMass(sofa::core::ObjectFactory*);
 void registerUniformMass(sofa::core::ObjectFactory*);
@@ -34,6 +35,7 @@ SOFA_EXPORT_DYNAMIC_LIBRARY void registerObjects(sofa::core::ObjectFactory* fact
     sofa::b200::registerTetrahedronFEMForceField(factory);
     sofa::b200::registerHexahedronFEMForceField(factory);
     sofa::b200::registerTetrahedralCorotationalFEMForceField(factory);
+    sofa::b200::registerFastTetrahedralCorotationalForceField(factory);
     sofa::b200::registerMeshMatrixMass(factory);
     sofa::b200::registerDiagonalMass(factory);
     sofa::b200::registerUniformMass(factory);

@@ -89,10 +89,13 @@ def test_small_tiles_and_given_edge_list(dtype):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("method", ["qr", "polar"])
-def test_euler_implicit_cg_steps(dtype, method):
-    """The class inside EulerImplicitSolver + CGLinearSolver + DiagonalMass + FixedProjectiveConstraint (multi-kernel CG loop): right-hand side of
-    the first step bit for bit, iteration counts within one, positions within the Vec3f / Vec3d bands of the other force fields' step tests."""
+@pytest.mark.parametrize("path", ["fused", "multi_kernel"])
+def test_euler_implicit_cg_steps(dtype, method, path, monkeypatch):
+    """The class inside EulerImplicitSolver + CGLinearSolver + DiagonalMass + FixedProjectiveConstraint, with the CG loop in the fused persistent
+    kernel (A*p over the edges, EdgePass) and as separate kernels: right-hand side of the first step bit for bit, iteration counts within one,
+    positions within the Vec3f / Vec3d bands of the other force fields' step tests."""
     import sofa_b200 as sb
+    monkeypatch.setenv("SOFAB200_FAST_FUSED", "1" if path == "fused" else "0")
     c, pos, tets, fixed, mo, ff, s = _pair("C1", dtype, method)
     mass = sb.DiagonalMass(mo, tets, massDensity=c["density"])
     node = sb.SolverNode(mo, ff, mass, sb.FixedProjectiveConstraint(mo, fixed), dt=c["dt"], gravity=c["gravity"], rayleighStiffness=c["rK"], rayleighMass=c["rM"],
@@ -107,6 +110,7 @@ def test_euler_implicit_cg_steps(dtype, method):
         # (the two sides sum the CG dot products in different orders; measured 4e-9 after 5 steps in Vec3d)
         assert np.abs(mo.x.cpu().numpy().astype(np.float64) - s.get("x")).max() <= (1e-7 if dtype == np.float64 else 2e-4)
     assert np.abs(s.get("x") - pos).max() > 1e-3      # the beam did move
+    assert bool(node.fused_info()["fused_enabled"]) == (path == "fused")
 
 
 def test_refusals():
