@@ -18,9 +18,9 @@ shutil.copy(os.path.join(G, "ev2_ref_line.json"), os.path.join(P, "r02_reference
 shutil.copy(os.path.join(G, "ev2_trace.json"), os.path.join(P, "r02_trace_cg_iteration.json"))
 shutil.copy(os.path.join(G, "ev2_micro.txt"), os.path.join(P, "r02_micro_latencies.txt"))
 with open(os.path.join(P, "r02_sanitizer.log"), "w") as f:
-    f.write("# compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py -k cg_solve_matches_oracle  (fused, fused all warps, fused streamed, v1, tail, multi-kernel; Vec3f + Vec3d)\n")
+    f.write("# compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py tests/test_gpu_fast_tet.py -k 'cg_solve_matches_oracle or euler_implicit_cg_steps'  (fused, fused all warps, fused streamed, v1, tail, multi-kernel; the edge pass of FastTetrahedralCorotationalForceField fused and multi-kernel; Vec3f + Vec3d)\n")
     f.write("".join(open(os.path.join(G, "ev2_racecheck.log")).readlines()[-6:]))
-    f.write("\n# compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py tests/test_gpu_hexa.py -k 'cg_solve_matches_oracle or hexa_steps or hexa_add'\n")
+    f.write("\n# compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py tests/test_gpu_hexa.py tests/test_gpu_fast_tet.py -k 'cg_solve_matches_oracle or hexa_steps or hexa_add or update_stiffness or add_force_and_add_dforce or euler_implicit_cg_steps or small_tiles'\n")
     f.write("".join(open(os.path.join(G, "ev2_memcheck.log")).readlines()[-5:]))
     f.write("\n# python -m pytest tests -m gpu (1 GPU)\n" + open(os.path.join(G, "ev2_pytest.log")).read())
 # launch list
