@@ -408,7 +408,7 @@ template <class R, int ET> __device__ __forceinline__ void fused_interior(const 
         for (; jj + 4 <= val; jj += 4) {
             R cx[4], cy[4], cz[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { const int sl = s.jds[jj + u] + k; cx[u] = s_slot[sl]; cy[u] = s_slot[max_slots + sl]; cz[u] = s_slot[2 * max_slots + sl]; }
+            for (int u = 0; u < 4; ++u) { const int sl = s.jds[jj + u] + k; cx[u] = s_slot[3 * sl]; cy[u] = s_slot[3 * sl + 1]; cz[u] = s_slot[3 * sl + 2]; }
             if (plus) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) { ax += cx[u]; ay += cy[u]; az += cz[u]; }
@@ -419,8 +419,8 @@ template <class R, int ET> __device__ __forceinline__ void fused_interior(const 
         }
         for (; jj < val; ++jj) {
             const int sl = s.jds[jj] + k;
-            if (plus) { ax += s_slot[sl]; ay += s_slot[max_slots + sl]; az += s_slot[2 * max_slots + sl]; }
-            else { ax -= s_slot[sl]; ay -= s_slot[max_slots + sl]; az -= s_slot[2 * max_slots + sl]; }
+            if (plus) { ax += s_slot[3 * sl]; ay += s_slot[3 * sl + 1]; az += s_slot[3 * sl + 2]; }
+            else { ax -= s_slot[3 * sl]; ay -= s_slot[3 * sl + 1]; az -= s_slot[3 * sl + 2]; }
         }
         node_finish_m(ep, rec.g, rec.mass, (rec.val_fixed & 0x10000u) != 0, R(pv.x), R(pv.y), R(pv.z), ax, ay, az);
         s.Q[3 * k] = ax; s.Q[3 * k + 1] = ay; s.Q[3 * k + 2] = az;

@@ -457,7 +457,7 @@ template <class R> __device__ __forceinline__ double persist_phase3(const TileDe
         for (; jj + 4 <= val; jj += 4) {
             R cx[4], cy[4], cz[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { const int s = s_jds[jj + u] + k; cx[u] = s_slot[s]; cy[u] = s_slot[max_slots + s]; cz[u] = s_slot[2 * max_slots + s]; }
+            for (int u = 0; u < 4; ++u) { const int s = s_jds[jj + u] + k; cx[u] = s_slot[3 * s]; cy[u] = s_slot[3 * s + 1]; cz[u] = s_slot[3 * s + 2]; }
             if (plus) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) { ax += cx[u]; ay += cy[u]; az += cz[u]; }
@@ -468,8 +468,8 @@ template <class R> __device__ __forceinline__ double persist_phase3(const TileDe
         }
         for (; jj < val; ++jj) {
             const int s = s_jds[jj] + k;
-            if (plus) { ax += s_slot[s]; ay += s_slot[max_slots + s]; az += s_slot[2 * max_slots + s]; }
-            else { ax -= s_slot[s]; ay -= s_slot[max_slots + s]; az -= s_slot[2 * max_slots + s]; }
+            if (plus) { ax += s_slot[3 * s]; ay += s_slot[3 * s + 1]; az += s_slot[3 * s + 2]; }
+            else { ax -= s_slot[3 * s]; ay -= s_slot[3 * s + 1]; az -= s_slot[3 * s + 2]; }
         }
         part += node_finish_m(ep, rec.g, rec.mass, (rec.val_fixed & 0x10000u) != 0, R(pv.x), R(pv.y), R(pv.z), ax, ay, az);
         s_qr[3 * k] = ax; s_qr[3 * k + 1] = ay; s_qr[3 * k + 2] = az;

@@ -184,6 +184,14 @@ HD void stage_store(Quad<double>* p, double x, double y, double z, uint64_t pol)
     (void)pol; *p = Quad<double>{x, y, z, 0.0};
 #endif
 }
+// without a cache hint (no policy descriptor to move into uniform registers per store); the fourth word is padding and is never read as a value
+__device__ __forceinline__ void stage_store_plain(unsigned long long a, float x, float y, float z) {
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%3};" :: "l"(a), "f"(x), "f"(y), "f"(z) : "memory");
+}
+__device__ __forceinline__ void stage_store_plain(unsigned long long a, double x, double y, double z) {
+    asm volatile("st.global.v2.f64 [%0], {%1,%2};" :: "l"(a), "d"(x), "d"(y) : "memory");
+    asm volatile("st.global.v2.f64 [%0+16], {%1,%1};" :: "l"(a), "d"(z) : "memory");
+}
 HD Quad<float> stage_load(const Quad<float>* p, uint64_t pol) {
 #ifdef __CUDA_ARCH__
     const float4 v = ldg_hint(reinterpret_cast<const float4*>(p), pol);
@@ -400,10 +408,17 @@ template <class R> __device__ __forceinline__ void tile_phase1(const TileDev<R>&
     for (int j = threadIdx.x; j <= t.maxval; j += blockDim.x) s_jds[j] = t.tile_jds[size_t(tile) * (t.maxval + 1) + j];
     __syncthreads();
 }
-// phase 2 tail: one corner contribution to its slot (shared memory for interior nodes, L2-resident HBM stage for shared ones)
+// phase 2 tail: one corner contribution to its slot (shared memory for interior nodes, L2-resident HBM stage for shared ones).
+// Shared-memory slots are (x, y, z) triples at a stride of three Reals: one address per contribution, the other two stores at immediate
+// offsets, and the ordered sums (consecutive threads -> consecutive slots) stay conflict-free because 3 is odd.  The staging address is
+// one 32 x 32 -> 64-bit multiply-add.  (The scatter is ~20 % of the element loop's issue slots: measured, profiles/README.md.)
 template <class R> __device__ __forceinline__ void tile_scatter(const TileDev<R>& t, unsigned s, R cx, R cy, R cz, R* s_slot, int max_slots, uint64_t pol_keep) {
-    if (s & kStageFlag) stage_store(t.stage + (s & ~kStageFlag), cx, cy, cz, pol_keep);
-    else { s_slot[s] = cx; s_slot[max_slots + s] = cy; s_slot[2 * max_slots + s] = cz; }
+    (void)max_slots; (void)pol_keep;
+    if (s & kStageFlag) {
+        unsigned long long addr;
+        asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(s & ~kStageFlag), "r"(unsigned(sizeof(Quad<R>))), "l"(reinterpret_cast<unsigned long long>(t.stage)));
+        stage_store_plain(addr, cx, cy, cz);
+    } else { R* dst = s_slot + 3u * s; dst[0] = cx; dst[1] = cy; dst[2] = cz; }
 }
 // phase 3: interior nodes, sequential sum in element order + fused epilogue; returns the thread's share of the dot product.
 // mdx_src / dot_with are the kernel's own input vector whenever they are used (A*p: both are p), so the shared-memory
@@ -426,7 +441,7 @@ template <class R> __device__ __forceinline__ double tile_phase3(const TileDev<R
         for (; jj + 4 <= val; jj += 4) {
             R cx[4], cy[4], cz[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { const int s = s_jds[jj + u] + k; cx[u] = s_slot[s]; cy[u] = s_slot[max_slots + s]; cz[u] = s_slot[2 * max_slots + s]; }
+            for (int u = 0; u < 4; ++u) { const int s = s_jds[jj + u] + k; cx[u] = s_slot[3 * s]; cy[u] = s_slot[3 * s + 1]; cz[u] = s_slot[3 * s + 2]; }
             if (plus) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) { ax += cx[u]; ay += cy[u]; az += cz[u]; }
@@ -437,8 +452,8 @@ template <class R> __device__ __forceinline__ double tile_phase3(const TileDev<R
         }
         for (; jj < val; ++jj) {
             const int s = s_jds[jj] + k;
-            if (plus) { ax += s_slot[s]; ay += s_slot[max_slots + s]; az += s_slot[2 * max_slots + s]; }
-            else { ax -= s_slot[s]; ay -= s_slot[max_slots + s]; az -= s_slot[2 * max_slots + s]; }
+            if (plus) { ax += s_slot[3 * s]; ay += s_slot[3 * s + 1]; az += s_slot[3 * s + 2]; }
+            else { ax -= s_slot[3 * s]; ay -= s_slot[3 * s + 1]; az -= s_slot[3 * s + 2]; }
         }
         part += node_post_v(ep, g, R(pv.x), R(pv.y), R(pv.z), ax, ay, az);
     }
