@@ -179,3 +179,41 @@ def test_c2_per_node_outputs_and_mesh_mass_properties():
     total = 2.5 * 4.0 * 4.0 * 20.0                                             # density * volume of the beam
     assert abs(float(r1[:, 0].sum()) - total) < 1e-8 * total
     assert float((r1 - r2).abs().max()) < 1e-12                                # the lumped matrix is the row sum of the sparse one (2.5 x vertex mass)
+
+
+@pytest.mark.parametrize("dtype,method", [(np.float32, "qr"), (np.float64, "polar")])
+def test_c2_fast_tetrahedral_corotational_bit_exact_at_full_size(dtype, method):
+    """FastTetrahedralCorotationalForceField on C2's mesh (983 040 tetrahedra, 1 180 896 edges): addForce, the per-edge matrices and addDForce over
+    the edges bit-exact against the oracle's restatement, then one whole step (the fused CG kernel with the edge pass)."""
+    import sofa_b200 as sb
+    import oracle_lib as O
+    from gpu_common import mesh
+    c, pos, hexas, tets, fixed = mesh("C2")
+    ctx = sb.Context(0)
+    mo = sb.MechanicalObject(ctx, "B200Vec3f" if dtype == np.float32 else "B200Vec3d", position=pos)
+    ff = sb.FastTetrahedralCorotationalForceField(mo, tets, youngModulus=c["young"], poissonRatio=c["poisson"], method=method)
+    s = O.OracleScene(dtype, pos)
+    s.set_params(gravity=c["gravity"], dt=c["dt"], rayleighStiffness=c["rK"], rayleighMass=c["rM"], iterations=c["iterations"], tolerance=c["tolerance"], threshold=c["threshold"])
+    s.set_mass_density(c["density"], tets); s.set_fast_tets(tets, method, c["young"], c["poisson"]); s.set_fixed(fixed)
+    assert ff.get("n_edges") == 1180896 and ff.get("edges").astype(np.int64).tobytes() == s.get("fast.edges").tobytes()
+    rng = np.random.default_rng(3)
+    z = pos[:, 2:3]
+    x = (pos + np.hstack([0.02 * np.sin(z / 3.0), 0.05 * (z / 20.0) ** 2, 0 * z]) + 1e-3 * rng.standard_normal(pos.shape)).astype(dtype)
+    zero = np.zeros_like(x)
+    f_d = dev(mo, zero); ff.addForce(f_d, dev(mo, x))
+    assert f_d.cpu().numpy().tobytes() == s.fem_add_force(zero, x).tobytes()
+    assert ff.get("rotations").tobytes() == s.get("fast.rotations").tobytes()
+    dx = (1e-3 * rng.standard_normal(x.shape)).astype(dtype)
+    df_d = dev(mo, zero); ff.addDForce(df_d, dev(mo, dx), -0.0011)
+    assert df_d.cpu().numpy().tobytes() == s.fem_add_dforce(zero, dx, -0.0011).tobytes()
+    assert ff.get("edgeInfo").tobytes() == s.get("fast.edgeInfo").tobytes()
+    mass = sb.DiagonalMass(mo, tets, massDensity=c["density"])
+    node = sb.SolverNode(mo, ff, mass, sb.FixedProjectiveConstraint(mo, fixed), dt=c["dt"], gravity=c["gravity"], rayleighStiffness=c["rK"], rayleighMass=c["rM"],
+                         iterations=c["iterations"], tolerance=c["tolerance"], threshold=c["threshold"])
+    s.set_dot_double(True)
+    node.step()
+    it_ref = s.step()
+    assert node.get("b").tobytes() == s.get("b").tobytes()
+    assert abs(node.last_solve()["iterations"] - it_ref) <= 1
+    assert rel_err(node.get("dx"), s.get("sol")) <= (1e-9 if dtype == np.float64 else 1e-4)
+    assert bool(node.fused_info()["fused_enabled"])
