@@ -6,8 +6,9 @@
 //   * addForce      one tile pass over the tetrahedra (the plan of fem_layout.cuh with 4 corners per element): rotation, six edge forces,
 //                   four corner contributions summed per node in ascending tetrahedron index; the rotation (R^T, as the class stores it)
 //                   is written back per tetrahedron;
-//   * edge matrices one thread per edge: edgeDfDx[e] = sum over the tetrahedra around e, ascending index, of R^T (L R) or (L R)^T R
-//                   ([FTC].inl:414-450) -- run by the first addDForce after an addForce;
+//   * edge matrices the addForce pass also leaves, per tetrahedron, the six 3x3 blocks R^T (L_j R) / (L_j R)^T R it will add to its edges' matrices;
+//                   one thread per edge then sums the blocks of the tetrahedra around it in ascending index ([FTC].inl:414-450) -- run by the
+//                   first addDForce after an addForce;
 //   * addDForce     one tile pass over the EDGES (the same plan machinery with 2 corners per element): df[e1] += M dx, df[e0] -= M^T dx in
 //                   ascending edge index per node, the order of the reference's loop.
 // Both passes end in the shared fused epilogue (mass term, projection, dot product), so a solver node drives this class like the others.
@@ -37,6 +38,7 @@ constexpr int kFastDfDx = 18;        // linearDfDx[6], row-major     54
 constexpr int kFastRestRot = 72;     // restRotation                  9
 constexpr int kFastShape = 81;       // shapeVector[1..3]             9
 constexpr int kFastRec = 90;
+constexpr int kFastPmat = 56;        // six 3x3 matrices per tetrahedron, padded to a multiple of four Reals (written as 16-byte quads)
 // edgesInTetrahedronArray, core/topology/Topology.cpp:44: {0,1},{0,2},{0,3},{1,2},{1,3},{2,3}
 static const int kFastLh[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
 
@@ -45,6 +47,8 @@ template <class R> struct FastDev {
     const ushort4* lnode; const uint4* slot;        // tetrahedra: local node and destination of each corner
     const R* rec; size_t NS;      // rec[k * NS + es]
     R* rot;                       // rot[k * NS + es], k < 9: tetraInfo.rotation (the transposed rotation)
+    R* pmat;                      // pmat[es * kFastPmat + 9 j + k]: the element's contribution to the matrix of its j-th edge, R^T (L_j R) or its transpose
+    const unsigned char* orient;  // bit j: edgeOrientation[j] == 1
     const ushort2* elnode; const uint2* eslot;      // edges
     const R* emat; size_t NSe;    // emat[k * NSe + es], k < 9: edgeDfDx
     R k_factor;
@@ -116,6 +120,8 @@ template <class R, int METHOD> __device__ __forceinline__ void fast_tet_element(
     V3<R> force[4];
 #pragma unroll
     for (int n = 0; n < 4; ++n) force[n] = mk3<R>(R(0), R(0), R(0));
+    const unsigned orient = d.orient[es];
+    R pm[kFastPmat];
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
         const V3<R> rest_edge = mk3<R>(d.rec[size_t(kFastEdgeVec + 3 * j) * d.NS + es], d.rec[size_t(kFastEdgeVec + 3 * j + 1) * d.NS + es], d.rec[size_t(kFastEdgeVec + 3 * j + 2) * d.NS + es]);
@@ -123,6 +129,20 @@ template <class R, int METHOD> __device__ __forceinline__ void fast_tet_element(
         const M3<R> Lj = fast_load_mat(d.rec + size_t(kFastDfDx + 9 * j) * d.NS, d.NS, es);
         force[L1[j]] = force[L1[j]] + mul(Lj, dj);
         force[L0[j]] = force[L0[j]] - mul_t(Lj, dj);
+        // what this tetrahedron adds to the matrix of its j-th edge at the next addDForce ([FTC].inl:436-447): rotation^T (L_j rotation) when the
+        // edge runs the way the topology's edge does, (L_j rotation)^T rotation otherwise -- computed here, where both operands are in registers
+        const M3<R> tmp = mul(Lj, rot);
+        const M3<R> add = ((orient >> j) & 1u) ? mul_atb(rot, tmp) : mul_atb(tmp, rot);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) pm[9 * j + 3 * a + b] = add.m[a][b];
+    }
+    pm[54] = R(0); pm[55] = R(0);
+    {
+        Quad<R>* dst = reinterpret_cast<Quad<R>*>(d.pmat + es * size_t(kFastPmat));
+#pragma unroll
+        for (int q = 0; q < kFastPmat / 4; ++q) dst[q] = Quad<R>{pm[4 * q], pm[4 * q + 1], pm[4 * q + 2], pm[4 * q + 3]};
     }
 #pragma unroll
     for (int n = 0; n < 4; ++n) C[n] = mul(Rm, force[n]);
@@ -163,36 +183,26 @@ __global__ void __launch_bounds__(256) fast_tet_kernel(FastDev<R> d, const R* __
     }
 }
 
-// the per-edge matrices, [FTC].inl:414-450.  inc: (tetrahedron slot << 4) | (orientation == 1) << 3 | local edge, ascending tetrahedron index
+// the per-edge matrices, [FTC].inl:414-450: the sum, over the tetrahedra around the edge in ascending index, of the 3x3 blocks fast_tet_kernel left in
+// pmat.  inc: (tetrahedron slot << 4) | local edge.
 template <class R>
 __global__ void fast_edge_assemble_kernel(size_t NSe, const uint32_t* __restrict__ eorder, const uint32_t* __restrict__ inc_off, const uint32_t* __restrict__ inc,
-                                          const R* __restrict__ rec, size_t NS, const R* __restrict__ rot, R* __restrict__ emat) {
+                                          const R* __restrict__ pmat, R* __restrict__ emat) {
     const size_t s = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (s >= NSe) return;
     const uint32_t e = eorder[s];
     if (e == 0xFFFFFFFFu) return;
-    M3<R> M;
+    R M[9];
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) M.m[i][j] = R(0);
+    for (int k = 0; k < 9; ++k) M[k] = R(0);
     for (uint32_t q = inc_off[e]; q < inc_off[e + 1]; ++q) {
         const uint32_t w = inc[q];
-        const size_t est = w >> 4;
-        const int j = int(w & 7u);
-        const M3<R> rotation = fast_load_mat(rot, NS, est);
-        const M3<R> Lj = fast_load_mat(rec + size_t(kFastDfDx + 9 * j) * NS, NS, est);
-        const M3<R> tmp = mul(Lj, rotation);
-        const M3<R> add = (w & 8u) ? mul_atb(rotation, tmp) : mul_atb(tmp, rotation);
+        const R* src = pmat + size_t(w >> 4) * kFastPmat + 9 * (w & 7u);
 #pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int b = 0; b < 3; ++b) M.m[a][b] += add.m[a][b];
+        for (int k = 0; k < 9; ++k) M[k] += src[k];
     }
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) emat[size_t(3 * i + j) * NSe + s] = M.m[i][j];
+    for (int k = 0; k < 9; ++k) emat[size_t(k) * NSe + s] = M[k];
 }
 
 // addDForce over the edges, [FTC].inl:455-466.  The epilogue subtracts (sign -1, like the other force fields' addDForce): the corner of edge[1]
@@ -291,7 +301,8 @@ template <class R> struct FastFF : sofab200_tetfem {
     size_t n_edges = 0, tsmem = 0, esmem = 0;
     DevBuf<ushort4> lnode; DevBuf<uint4> slot;
     DevBuf<ushort2> elnode; DevBuf<uint2> eslot;
-    DevBuf<R> rec, rot, emat;
+    DevBuf<R> rec, rot, emat, pmat;
+    DevBuf<unsigned char> orient;
     DevBuf<uint32_t> eorder, inc_off, inc;
     bool update_matrix = true;
     // element-ordered host copies of what init computed (inspection / parity)
@@ -300,7 +311,7 @@ template <class R> struct FastFF : sofab200_tetfem {
     FastDev<R> dev(bool edges) const {
         FastDev<R> d;
         d.t = edges ? eb.dev(eplan) : tb.dev(tplan);
-        d.lnode = lnode.p; d.slot = slot.p; d.rec = rec.p; d.NS = size_t(tplan.n_tiles) * tplan.tile_e; d.rot = rot.p;
+        d.lnode = lnode.p; d.slot = slot.p; d.rec = rec.p; d.NS = size_t(tplan.n_tiles) * tplan.tile_e; d.rot = rot.p; d.pmat = pmat.p; d.orient = orient.p;
         d.elnode = elnode.p; d.eslot = eslot.p; d.emat = emat.p; d.NSe = size_t(eplan.n_tiles) * eplan.tile_e;
         d.k_factor = R(0);
         return d;
@@ -450,6 +461,16 @@ template <class R> static int fast_create_t(sofab200_ctx* ctx, size_t n_nodes, c
         }
         SB_TRY(ff->lnode.upload(ln, s)); SB_TRY(ff->slot.upload(sl, s)); SB_TRY(ff->rec.upload(rec, s));
         SB_TRY(ff->rot.alloc(9 * NS)); SB_TRY(ff->rot.zero(s));
+        SB_TRY(ff->pmat.alloc(size_t(kFastPmat) * NS)); SB_TRY(ff->pmat.zero(s));
+        {
+            std::vector<unsigned char> orient(NS, 0);
+            for (size_t es = 0; es < NS; ++es) {
+                const uint32_t e = TP.order[es];
+                if (e == 0xFFFFFFFFu) continue;
+                for (int j = 0; j < 6; ++j) if (ff->h_orient[6 * size_t(e) + j] == R(1)) orient[es] |= (unsigned char)(1u << j);
+            }
+            SB_TRY(ff->orient.upload(orient, s));
+        }
         // edges in tile order + the tetrahedra around each edge, ascending index (the order in which [FTC].inl:425-448 accumulates)
         std::vector<ushort2> eln(NSe, make_ushort2(0xFFFF, 0xFFFF)); std::vector<uint2> esl(NSe, make_uint2(0, 0));
         for (size_t es = 0; es < NSe; ++es) {
@@ -463,7 +484,7 @@ template <class R> static int fast_create_t(sofab200_ctx* ctx, size_t n_nodes, c
         std::vector<uint32_t> cur(inc_off.begin(), inc_off.end() - 1);
         for (size_t i = 0; i < n_tets; ++i)
             for (int j = 0; j < 6; ++j)
-                inc[cur[eit[6 * i + j]]++] = (slot_of_tet[i] << 4) | (ff->h_orient[6 * i + j] == R(1) ? 8u : 0u) | uint32_t(j);
+                inc[cur[eit[6 * i + j]]++] = (slot_of_tet[i] << 4) | uint32_t(j);
         SB_TRY(ff->elnode.upload(eln, s)); SB_TRY(ff->eslot.upload(esl, s)); SB_TRY(ff->eorder.upload(EP.order, s));
         SB_TRY(ff->inc_off.upload(inc_off, s)); SB_TRY(ff->inc.upload(inc, s));
         SB_TRY(ff->emat.alloc(9 * NSe)); SB_TRY(ff->emat.zero(s));
@@ -535,8 +556,8 @@ template int fast_run<double>(sofab200_tetfem*, bool, const double*, double, Nod
 template <class R> static int fast_assemble(FastFF<R>& ff) {
     if (!ff.update_matrix) return SOFAB200_OK;
     ff.update_matrix = false;
-    const size_t NSe = size_t(ff.eplan.n_tiles) * ff.eplan.tile_e, NS = size_t(ff.tplan.n_tiles) * ff.tplan.tile_e;
-    fast_edge_assemble_kernel<R><<<unsigned((NSe + 127) / 128), 128, 0, ff.ctx->stream>>>(NSe, ff.eorder.p, ff.inc_off.p, ff.inc.p, ff.rec.p, NS, ff.rot.p, ff.emat.p);
+    const size_t NSe = size_t(ff.eplan.n_tiles) * ff.eplan.tile_e;
+    fast_edge_assemble_kernel<R><<<unsigned((NSe + 127) / 128), 128, 0, ff.ctx->stream>>>(NSe, ff.eorder.p, ff.inc_off.p, ff.inc.p, ff.pmat.p, ff.emat.p);
     ff.ctx->launches++;
     SB_CUDA(cudaGetLastError());
     return SOFAB200_OK;
