@@ -9,7 +9,9 @@ EulerImplicitSolver rayleigh 0.1/0.1, CGLinearSolver 25 iterations forced by tol
 
 A "step" is one EulerImplicitSolver::solve: addForce + right-hand side + 25 CG iterations + integration.
 value    = CG iterations per second with x, v resident in HBM (CUDA events around K steps, max over ranks)
-e2e      = the same metric through the host-buffer entry point (sofab200_node_step_host_x: H2D of x and D2H of x inside every step)
+e2e      = the same metric through the host-buffer entry points, pinned host memory, H2D and D2H inside every step.  N=1: the coupling of a device-resident
+           state with a host loop (sofab200_node_step_pipelined: that step's external forces up, the new positions down on a copy stream under the next
+           step) with the synchronous round trip of x (sofab200_node_step_host_x) beside it; N>1: the synchronous round trip on every rank
 roofline = the CG kernel: algorithmic bytes per launch / event-timed launch duration vs the measured HBM peak
 configs  = (N=1, default workload) the other single-GPU configurations of BASELINE.json, each with its own numbers: C3 (hexahedra, polar),
            C2 in Vec3d, C4 (liver-sized mesh: latency)
@@ -421,7 +423,10 @@ def run_ours(args):
         n_sus = max(args.steps, int(args.sustain_s * 1e3 / (ms / args.steps)) + 1)
         ms_sus, _, clocks_sus = time_steps(ctx, node, n_sus, 1, local)
         sustained = {"seconds": ms_sus * 1e-3, "steps": n_sus, "value": iters_per_step * n_sus / (ms_sus * 1e-3), "unit": "cg_iters/s", "ms_per_step": ms_sus / n_sus, "clocks": clocks_sus}
-    # ---- end-to-end arm: the host owns x (pinned): H2D of x, step, D2H of x inside every step; v stays resident in HBM
+    # ---- end-to-end arms through the host-buffer entry points, pinned host memory, H2D and D2H inside every step:
+    # (a) synchronous round trip of the positions (sofab200_node_step_host_x): the host owns x;
+    # (b) the coupling of a device-resident state with a host loop (sofab200_node_step_pipelined): this step's external forces up, the new positions
+    #     down on a copy stream while the next step is already running (two alternating output buffers, flush inside the timed region).
     xh = torch.from_numpy(meta["pos"].astype(ndtype)).pin_memory()
     vh0 = torch.zeros_like(xh).pin_memory()
     node.step_host_x(xh, vh0)          # (initial velocities uploaded once)
@@ -433,7 +438,18 @@ def run_ours(args):
     for _ in range(e2e_steps):
         node.step_host_x(xh)
     torch.cuda.synchronize()
+    e2e_sync_s = time.perf_counter() - t0
+    ext_h = torch.zeros_like(xh).pin_memory()
+    xo = [torch.zeros_like(xh).pin_memory() for _ in range(2)]
+    for k in range(4):                 # (the external-force path captures its own step graph)
+        node.step_pipelined(ext_h, xo[k & 1])
+    node.flush()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        node.step_pipelined(ext_h, xo[k & 1])
+    node.flush()
     e2e_s = time.perf_counter() - t0
+    node.set_external_force(None)
 
     value = iters_per_step * args.steps / (ms * 1e-3)
     ab = algorithmic_bytes(meta["kind"], E, N, s)
@@ -455,7 +471,10 @@ def run_ours(args):
         "roofline": roof,
         "e2e": {"value": iters_per_step * e2e_steps / e2e_s, "unit": unit_for(wl), "h2d_bytes_per_step": N * 3 * s, "d2h_bytes_per_step": N * 3 * s,
                 "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                "note": "sofab200_node_step_host_x: x from pinned host memory and back every step (synchronous), velocities resident in HBM"},
+                "note": "sofab200_node_step_pipelined: device-resident x, v; every step uploads that step's external forces (n Vec3, pinned host memory) and "
+                        "downloads the new positions into one of two pinned buffers on a copy stream while the next step runs; the last download is inside the timed region",
+                "synchronous_round_trip": {"value": iters_per_step * e2e_steps / e2e_sync_s, "ms_per_step": 1e3 * e2e_sync_s / e2e_steps,
+                                           "note": "sofab200_node_step_host_x: the host owns x -- H2D of x, step, D2H of x, host sync, every step (velocities resident)"}},
         "sustained": sustained, "gpu_launches": launches, "clocks": clocks,
     }
     del node, ff

@@ -320,6 +320,17 @@ int sofab200_node_step_host(sofab200_node* node, void* x_host, void* v_host);
  * them; they start at zero otherwise), v_host_out (may be NULL) receives the new ones.  This is what [EI]:83-341 needs per step when the state
  * lives in a device-typed MechanicalObject: only a reader on the host (visual model, collision) makes x come back. (sync) */
 int sofab200_node_step_host_x(sofab200_node* node, void* x_host, const void* v_host_in, void* v_host_out);
+/* MechanicalObject's `externalForce` vector (Data `externalForce`, added to the freshly reset force by accumulateForce,
+ * Sofa/Component/StateContainer/src/sofa/component/statecontainer/MechanicalObject.inl:1356-1375, before any force field's addForce): n Vec3 of
+ * `real` in host memory, uploaded now; NULL removes it.  Not on a distributed node (interface nodes would count it once per sharing rank). (sync) */
+int sofab200_node_set_external_force(sofab200_node* node, const void* ext_host);
+/* One step of a DEVICE-RESIDENT state (x_dev, v_dev as for sofab200_node_step) coupled to a host loop: ext_host (may be NULL; pinned memory for
+ * the copy to be asynchronous) holds this step's external forces and is uploaded first; the new positions are copied into x_out_host on a second
+ * stream while the caller already submits the next step.  The call returns as soon as the PREVIOUS call's positions are complete on the host and
+ * this call's forces have been read from ext_host (which may then be refilled), so the caller alternates two output buffers; sofab200_node_flush waits for everything outstanding.  This is the coupling of a device-typed
+ * MechanicalObject with host-side readers (visual model, collision) and writers (interaction forces): nothing of the state crosses the bus twice. */
+int sofab200_node_step_pipelined(sofab200_node* node, void* x_dev, void* v_dev, const void* ext_host, void* x_out_host);
+int sofab200_node_flush(sofab200_node* node);
 /* Which kernel the last CG solve of the node ran (diagnostics for the benchmark line): out = {grid, tiles per CTA, 1 = tile state cached in
  * shared memory / 0 = streamed from HBM scratch, dynamic shared memory bytes, element threads, dedicated shared-node threads,
  * 1 = fused single-reduction kernel enabled, 1 = a persistent kernel is enabled at all}; the first six are zero before the first fused solve. */

@@ -1648,8 +1648,12 @@ template <class R> struct Scene {
     }
     // mop.computeForce: resetForce, accumulateForce (no external force), every force field's addForce in scene order
     // Sofa/framework/Simulation/Core/src/sofa/simulation/MappingGraphMechanicalOperations.cpp:41-93
+    VecDeriv<R> externalForce;   // MechanicalObject Data `externalForce` (empty = none)
     void computeForce(VecDeriv<R>& F) {
         F.assign(x.size(), Coord());
+        // MechanicalObject::accumulateForce, Sofa/Component/StateContainer/src/sofa/component/statecontainer/MechanicalObject.inl:1356-1375
+        for (size_t i = 0; i < externalForce.size(); ++i)
+            if (!(externalForce[i][0] == R(0) && externalForce[i][1] == R(0) && externalForce[i][2] == R(0))) F[i] += externalForce[i];
         auto massForce = [&]() { if (hasMeshMass) meshMass.addForce(F, gravity); else mass.addForce(F, gravity); };
         if (massFirst && hasMass) massForce();
         femAddForce(F);

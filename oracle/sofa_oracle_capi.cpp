@@ -124,6 +124,7 @@ void orc_scene_set_threads(void* h, int n) { DISPATCH(h, { sc.threads = n < 1 ? 
 void orc_scene_set_state(void* h, size_t n, const void* x, const void* v) {
     DISPATCH(h, { sc.x = toVec<R>(x, n); sc.x0 = sc.x; sc.v = toVec<R>(v, n); if (!v) sc.v.assign(n, Vec3<R>()); sc.f.assign(n, Vec3<R>()); sc.dx.assign(n, Vec3<R>()); });
 }
+void orc_scene_set_external_force(void* h, const void* f) { DISPATCH(h, { if (f) sc.externalForce = toVec<R>(f, sc.x.size()); else sc.externalForce.clear(); }); }
 void orc_scene_set_x(void* h, const void* x) { DISPATCH(h, { sc.x = toVec<R>(x, sc.x.size()); }); }
 void orc_scene_set_v(void* h, const void* v) { DISPATCH(h, { sc.v = toVec<R>(v, sc.v.size()); }); }
 

@@ -117,6 +117,9 @@ SYMBOLS = {
     "sofab200_node_step": (_I, [_P, _P, _P]),
     "sofab200_node_step_host": (_I, [_P, _P, _P]),
     "sofab200_node_step_host_x": (_I, [_P, _P, _P, _P]),
+    "sofab200_node_set_external_force": (_I, [_P, _P]),
+    "sofab200_node_step_pipelined": (_I, [_P, _P, _P, _P, _P]),
+    "sofab200_node_flush": (_I, [_P]),
     "sofab200_node_cg_kernel_info": (_I, [_P, C.POINTER(C.c_int)]),
     "sofab200_node_last_solve": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_D), C.POINTER(_SZ), C.POINTER(_D), C.POINTER(_SZ), _SZ]),
     "sofab200_node_get": (_I, [_P, C.c_char_p, _P]),

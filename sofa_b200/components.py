@@ -591,6 +591,23 @@ class SolverNode:
         ptr = lambda a: None if a is None else (a.ctypes.data_as(_P) if isinstance(a, np.ndarray) else C.c_void_p(a.data_ptr()))
         check(self.ctx.L.sofab200_node_step_host_x(self.h, ptr(x_host), ptr(v_host_in), ptr(v_host_out)))
 
+    def set_external_force(self, ext_host):
+        """MechanicalObject's externalForce (accumulateForce, MechanicalObject.inl:1356-1375): n x 3 host array, or None to remove it."""
+        if ext_host is not None:
+            ext_host = np.ascontiguousarray(ext_host, self.mstate.ndtype)
+        check(self.ctx.L.sofab200_node_set_external_force(self.h, None if ext_host is None else ext_host.ctypes.data_as(_P)))
+
+    def step_pipelined(self, ext_host, x_out_host, x=None, v=None):
+        """One step of the device-resident state: this step's external forces up from (pinned) host memory, the new positions down into
+        x_out_host on a copy stream while the next step is already being submitted (alternate two output buffers; flush() at the end)."""
+        ptr = lambda a: None if a is None else (a.ctypes.data_as(_P) if isinstance(a, np.ndarray) else C.c_void_p(a.data_ptr()))
+        x = self.mstate.x if x is None else x
+        v = self.mstate.v if v is None else v
+        check(self.ctx.L.sofab200_node_step_pipelined(self.h, _dptr(x), _dptr(v), ptr(ext_host), ptr(x_out_host)))
+
+    def flush(self):
+        check(self.ctx.L.sofab200_node_flush(self.h))
+
     def fused_info(self):
         out = (C.c_int * 8)()
         check(self.ctx.L.sofab200_node_cg_kernel_info(self.h, out))

@@ -125,6 +125,15 @@ template <class R> struct Node : sofab200_node {
     struct StepGraph { cudaGraphExec_t exec = nullptr; R* x = nullptr; R* v = nullptr; sofab200_solver_params prm; uint64_t launches = 0; int seen = 0; } sg, sg_rest;
     cudaStream_t side_stream = nullptr;    // step_host: the v copy runs here while addForce (which only needs x) runs on the main stream
     cudaEvent_t side_event = nullptr;
+    // MechanicalObject::externalForce (accumulateForce, MechanicalObject.inl:1356-1375): f starts from it instead of zero
+    DevBuf<R> ext; bool has_ext = false;
+    // pipelined host coupling (sofab200_node_step_pipelined): the positions of step k travel to the host on a copy stream while step k + 1 runs
+    cudaStream_t copy_stream = nullptr, up_stream = nullptr;
+    DevBuf<R> ext_stage; cudaEvent_t ev_ext_used = nullptr; bool ext_used_recorded = false;
+    cudaEvent_t ev_step[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr}, ev_h2d = nullptr;
+    bool copy_pending[2] = {false, false};
+    DevBuf<R> xout[2];
+    unsigned long long pipe_k = 0;
     bool use_graph = true;
     // a captured step bakes in which mass / halo path the node takes: forget it whenever that changes
     void invalidate_graphs() {
@@ -135,6 +144,11 @@ template <class R> struct Node : sofab200_node {
         if (sg_rest.exec) cudaGraphExecDestroy(sg_rest.exec);
         if (side_event) cudaEventDestroy(side_event);
         if (side_stream) cudaStreamDestroy(side_stream);
+        for (int i = 0; i < 2; ++i) { if (ev_step[i]) cudaEventDestroy(ev_step[i]); if (ev_copy[i]) cudaEventDestroy(ev_copy[i]); }
+        if (ev_h2d) cudaEventDestroy(ev_h2d);
+        if (ev_ext_used) cudaEventDestroy(ev_ext_used);
+        if (up_stream) cudaStreamDestroy(up_stream);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
     }
 
     // ---- multi-GPU state (sofab200_node_set_distributed) ------------------------------------------------
@@ -282,10 +296,11 @@ template <class R> struct Node : sofab200_node {
     // mop.computeForce
     int compute_force(R* f_out, const R* x, const R* v = nullptr, bool skip_halo = false) {
         NodeEpilogue<R> ep = base_ep();
-        ep.init_src = nullptr; ep.sign = +1; ep.out = f_out;
+        ep.init_src = has_ext ? ext.p : nullptr; ep.sign = +1; ep.out = f_out;     // resetForce + accumulateForce: f = 0 (+ externalForce)
         set_mass_term(ep, PRE_GRAVITY, nullptr, 1.0);
         if (mesh_mass) {   // f = 0; MeshMatrixMass::addForce(f); the element pass then starts every node from that value (same order as the reference's visitor)
-            LAUNCH(ctx, (vop_kernel<R, VOP_CLEAR>), vec_grid(3 * n, ctx->sm_count), kVecBlock, 3 * n, f_out, (const R*)nullptr, (const R*)nullptr, R(0));
+            if (has_ext) SB_CUDA(cudaMemcpyAsync(f_out, ext.p, 3 * n * sizeof(R), cudaMemcpyDeviceToDevice, ctx->stream));
+            else LAUNCH(ctx, (vop_kernel<R, VOP_CLEAR>), vec_grid(3 * n, ctx->sm_count), kVecBlock, 3 * n, f_out, (const R*)nullptr, (const R*)nullptr, R(0));
             SB_TRY(sofab200_meshmass_add_force(mesh_mass, f_out, prm.gravity));
             ep.init_src = f_out;
         }
@@ -888,6 +903,74 @@ template <class R> static int node_step_host(Node<R>* n, void* x_host, void* v_h
     SB_CUDA(cudaStreamSynchronize(s));
     return SOFAB200_OK;
 }
+// accumulateForce (MechanicalObject.inl:1356-1375): f[i] += externalForce[i] on a freshly reset f, i.e. every component becomes +0 + ext
+// (a negative zero does not survive; rows equal to Deriv() are skipped by the reference, which leaves the same +0)
+template <class R> __global__ void __launch_bounds__(kVecBlock) ext_accumulate_kernel(size_t n3, R* __restrict__ r) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n3; i += size_t(gridDim.x) * blockDim.x) r[i] = R(0) + r[i];
+}
+template <class R> static int node_upload_external_force(Node<R>* n, const void* ext_host, bool sync) {
+    if (n->distributed()) return fail(SOFAB200_ERR_UNSUPPORTED, "externalForce on a distributed node would be counted once per sharing rank on interface nodes");
+    cudaStream_t s = n->ctx->stream;
+    const bool on = ext_host != nullptr;
+    if (on != n->has_ext) { n->has_ext = on; n->invalidate_graphs(); }
+    if (!on) return SOFAB200_OK;
+    if (!n->ext.p) SB_TRY(n->ext.alloc(3 * n->n));
+    SB_CUDA(cudaMemcpyAsync(n->ext.p, ext_host, 3 * n->n * sizeof(R), cudaMemcpyHostToDevice, s));
+    LAUNCH(n->ctx, (ext_accumulate_kernel<R>), vec_grid(3 * n->n, n->ctx->sm_count), kVecBlock, 3 * n->n, n->ext.p);
+    if (sync) SB_CUDA(cudaStreamSynchronize(s));
+    return SOFAB200_OK;
+}
+// One step of a device-resident state coupled to a host loop: this step's external forces come up from (pinned) host memory, the new positions
+// go down on a copy stream into x_out_host while the caller already submits the next step; the call returns once the PREVIOUS step's positions
+// are complete on the host (so two output buffers must alternate), sofab200_node_flush waits for the last ones.
+template <class R> static int node_step_pipelined(Node<R>* n, R* x_dev, R* v_dev, const void* ext_host, void* x_out_host) {
+    const size_t bytes = 3 * n->n * sizeof(R);
+    cudaStream_t s = n->ctx->stream;
+    if (!n->copy_stream) {
+        SB_CUDA(cudaStreamCreateWithFlags(&n->copy_stream, cudaStreamNonBlocking));
+        SB_CUDA(cudaStreamCreateWithFlags(&n->up_stream, cudaStreamNonBlocking));
+        SB_CUDA(cudaEventCreateWithFlags(&n->ev_h2d, cudaEventDisableTiming));
+        SB_CUDA(cudaEventCreateWithFlags(&n->ev_ext_used, cudaEventDisableTiming));
+        SB_TRY(n->ext_stage.alloc(3 * n->n));
+        for (int i = 0; i < 2; ++i) {
+            SB_CUDA(cudaEventCreateWithFlags(&n->ev_step[i], cudaEventDisableTiming)); SB_CUDA(cudaEventCreateWithFlags(&n->ev_copy[i], cudaEventDisableTiming));
+            SB_TRY(n->xout[i].alloc(3 * n->n));
+        }
+    }
+    if (ext_host) {
+        // this step's forces go up on their own stream, under whatever step is still running; the main stream only moves them from the staging
+        // buffer into the vector the captured step reads (a device-to-device copy) once the previous step is through
+        if (n->distributed()) return fail(SOFAB200_ERR_UNSUPPORTED, "externalForce on a distributed node would be counted once per sharing rank on interface nodes");
+        if (!n->has_ext) { n->has_ext = true; n->invalidate_graphs(); }
+        if (!n->ext.p) SB_TRY(n->ext.alloc(3 * n->n));
+        if (n->ext_used_recorded) SB_CUDA(cudaStreamWaitEvent(n->up_stream, n->ev_ext_used, 0));    // (the staging buffer has been consumed)
+        SB_CUDA(cudaMemcpyAsync(n->ext_stage.p, ext_host, bytes, cudaMemcpyHostToDevice, n->up_stream));
+        SB_CUDA(cudaEventRecord(n->ev_h2d, n->up_stream));
+        SB_CUDA(cudaStreamWaitEvent(s, n->ev_h2d, 0));
+        SB_CUDA(cudaMemcpyAsync(n->ext.p, n->ext_stage.p, bytes, cudaMemcpyDeviceToDevice, s));
+        LAUNCH(n->ctx, (ext_accumulate_kernel<R>), vec_grid(3 * n->n, n->ctx->sm_count), kVecBlock, 3 * n->n, n->ext.p);
+        SB_CUDA(cudaEventRecord(n->ev_ext_used, s));
+        n->ext_used_recorded = true;
+    } else SB_TRY(node_upload_external_force(n, nullptr, false));
+    SB_TRY(n->step(x_dev, v_dev, false));
+    const int slot = int(n->pipe_k & 1ull);
+    if (n->copy_pending[slot]) SB_CUDA(cudaStreamWaitEvent(s, n->ev_copy[slot], 0));       // (the copy of two steps ago has left this staging buffer)
+    SB_CUDA(cudaMemcpyAsync(n->xout[slot].p, x_dev, bytes, cudaMemcpyDeviceToDevice, s));
+    SB_CUDA(cudaEventRecord(n->ev_step[slot], s));
+    SB_CUDA(cudaStreamWaitEvent(n->copy_stream, n->ev_step[slot], 0));
+    SB_CUDA(cudaMemcpyAsync(x_out_host, n->xout[slot].p, bytes, cudaMemcpyDeviceToHost, n->copy_stream));
+    SB_CUDA(cudaEventRecord(n->ev_copy[slot], n->copy_stream));
+    n->copy_pending[slot] = true;
+    if (n->copy_pending[slot ^ 1]) SB_CUDA(cudaEventSynchronize(n->ev_copy[slot ^ 1]));    // the previous step's positions are on the host now
+    if (ext_host) SB_CUDA(cudaEventSynchronize(n->ev_h2d));                                // ... and this step's forces have left ext_host (the caller may refill it)
+    ++n->pipe_k;
+    return SOFAB200_OK;
+}
+template <class R> static int node_flush(Node<R>* n) {
+    for (int i = 0; i < 2; ++i) if (n->copy_pending[i]) SB_CUDA(cudaEventSynchronize(n->ev_copy[i]));
+    SB_CUDA(cudaStreamSynchronize(n->ctx->stream));
+    return SOFAB200_OK;
+}
 // x round trip only: the velocities stay resident in HBM between steps (what the reference's own loop does with a device-typed state)
 template <class R> static int node_step_host_x(Node<R>* n, void* x_host, const void* v_host_in, void* v_host_out) {
     const size_t bytes = 3 * n->n * sizeof(R);
@@ -906,6 +989,19 @@ extern "C" {
 int sofab200_node_step_host_x(sofab200_node* node, void* x_host, const void* v_host_in, void* v_host_out) {
     SB_CHECK(node && x_host, "null argument");
     return NODE_DISPATCH(node, sb::node_step_host_x<float>(NF(node), x_host, v_host_in, v_host_out), sb::node_step_host_x<double>(ND(node), x_host, v_host_in, v_host_out));
+}
+int sofab200_node_set_external_force(sofab200_node* node, const void* ext_host) {
+    SB_CHECK(node != nullptr, "null argument");
+    return NODE_DISPATCH(node, sb::node_upload_external_force<float>(NF(node), ext_host, true), sb::node_upload_external_force<double>(ND(node), ext_host, true));
+}
+int sofab200_node_step_pipelined(sofab200_node* node, void* x_dev, void* v_dev, const void* ext_host, void* x_out_host) {
+    SB_CHECK(node && x_dev && v_dev && x_out_host, "null argument");
+    return NODE_DISPATCH(node, sb::node_step_pipelined<float>(NF(node), (float*)x_dev, (float*)v_dev, ext_host, x_out_host),
+                         sb::node_step_pipelined<double>(ND(node), (double*)x_dev, (double*)v_dev, ext_host, x_out_host));
+}
+int sofab200_node_flush(sofab200_node* node) {
+    SB_CHECK(node != nullptr, "null argument");
+    return NODE_DISPATCH(node, sb::node_flush<float>(NF(node)), sb::node_flush<double>(ND(node)));
 }
 int sofab200_node_step_host(sofab200_node* node, void* x_host, void* v_host) {
     SB_CHECK(node && x_host && v_host, "null argument");

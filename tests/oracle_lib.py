@@ -145,6 +145,11 @@ class OracleScene:
                                   0 if lsf is None else len(lsf), _ptr(lsf))
         self.tets = t
 
+    def set_external_force(self, f):
+        """MechanicalObject's externalForce vector (None removes it)."""
+        self._ext = None if f is None else np.ascontiguousarray(f, self.dtype)
+        self.L.orc_scene_set_external_force(self.h, _ptr(self._ext))
+
     def set_fast_tets(self, tets, method="qr", young=5000.0, poisson=0.45, edges=None):
         """FastTetrahedralCorotationalForceField (d_method: "polar", "qr"/"large", "polar2", "none"/"linear"/"small")."""
         t = np.ascontiguousarray(tets, np.uint32)
