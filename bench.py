@@ -575,16 +575,19 @@ def run_ours_distributed(args, rank, world, local):
         node.step()
     prof = ctx.profile_end()
     barrier()
-    # ---- end-to-end arm: every rank's local x in pinned host memory, copied in and out every step; velocities resident
-    xh = node.be.x.detach().cpu().pin_memory(); vh = node.be.v.detach().cpu().pin_memory()
-    node.be.node.step_host_x(xh, vh)
-    for _ in range(2):
-        node.be.node.step_host_x(xh)
+    # ---- end-to-end arm: every rank couples its partition's device-resident state to a host loop (sofab200_node_step_pipelined): that step's external
+    # forces of the rank's nodes up from pinned host memory, the new positions down into one of two pinned buffers under the next step
+    ext_h = torch.zeros_like(node.be.x).cpu().pin_memory()
+    xo = [torch.zeros_like(node.be.x).cpu().pin_memory() for _ in range(2)]
+    for k in range(4):
+        node.be.node.step_pipelined(ext_h, xo[k & 1], node.be.x, node.be.v)
+    node.be.node.flush()
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 50))
-    for _ in range(e2e_steps):
-        node.be.node.step_host_x(xh)
+    for k in range(e2e_steps):
+        node.be.node.step_pipelined(ext_h, xo[k & 1], node.be.x, node.be.v)
+    node.be.node.flush()
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e0.elapsed_time(e1), e2e_s], dtype=torch.float64, device=ctx.device)
@@ -629,7 +632,7 @@ def run_ours_distributed(args, rank, world, local):
                          "kernel_ms_rank0": {k: v for k, v in prof.items()}},
             "e2e": {"value": it_step * e2e_steps * units / e2e_s, "unit": "cg_iters/s" if strong else "partition_cg_iters/s", "h2d_bytes_per_step": sum(int(a[1]) for a in all_sizes) * 3 * s,
                     "d2h_bytes_per_step": sum(int(a[1]) for a in all_sizes) * 3 * s, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                    "note": "every rank copies its partition's x from pinned host memory and back each step (sofab200_node_step_host_x), velocities resident; wall clock, max over ranks"},
+                    "note": "sofab200_node_step_pipelined on every rank: the partition's state is device-resident, every step uploads that step's external forces of the rank's nodes (pinned host memory) and downloads the new positions into one of two pinned buffers under the next step; wall clock, max over ranks, last download inside the timed region"},
             "gpu_launches": launches, "clocks": clocks}
     print(json.dumps(line))
 

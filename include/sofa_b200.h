@@ -322,7 +322,8 @@ int sofab200_node_step_host(sofab200_node* node, void* x_host, void* v_host);
 int sofab200_node_step_host_x(sofab200_node* node, void* x_host, const void* v_host_in, void* v_host_out);
 /* MechanicalObject's `externalForce` vector (Data `externalForce`, added to the freshly reset force by accumulateForce,
  * Sofa/Component/StateContainer/src/sofa/component/statecontainer/MechanicalObject.inl:1356-1375, before any force field's addForce): n Vec3 of
- * `real` in host memory, uploaded now; NULL removes it.  Not on a distributed node (interface nodes would count it once per sharing rank). (sync) */
+ * `real` in host memory, uploaded now; NULL removes it.  On a distributed node every rank passes the rows of ITS nodes; only the owner's copy of an
+ * interface node keeps its row (the force sums over the sharing ranks would count it once per rank otherwise). (sync) */
 int sofab200_node_set_external_force(sofab200_node* node, const void* ext_host);
 /* One step of a DEVICE-RESIDENT state (x_dev, v_dev as for sofab200_node_step) coupled to a host loop: ext_host (may be NULL; pinned memory for
  * the copy to be asynchronous) holds this step's external forces and is uploaded first; the new positions are copied into x_out_host on a second

@@ -908,15 +908,21 @@ template <class R> static int node_step_host(Node<R>* n, void* x_host, void* v_h
 template <class R> __global__ void __launch_bounds__(kVecBlock) ext_accumulate_kernel(size_t n3, R* __restrict__ r) {
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n3; i += size_t(gridDim.x) * blockDim.x) r[i] = R(0) + r[i];
 }
+// (distributed node: every rank holds a copy of its interface nodes and their forces are summed over the sharing ranks, so only the owner's copy
+// carries the external force -- the same masking as for the DiagonalMass term)
+template <class R> static int node_finish_external_force(Node<R>* n) {
+    LAUNCH(n->ctx, (ext_accumulate_kernel<R>), vec_grid(3 * n->n, n->ctx->sm_count), kVecBlock, 3 * n->n, n->ext.p);
+    if (n->distributed()) LAUNCH(n->ctx, (mask_rows_kernel<R>), vec_grid(n->n, n->ctx->sm_count), kVecBlock, n->n, (const unsigned char*)n->halo.owned.p, (const R*)n->ext.p, n->ext.p);
+    return SOFAB200_OK;
+}
 template <class R> static int node_upload_external_force(Node<R>* n, const void* ext_host, bool sync) {
-    if (n->distributed()) return fail(SOFAB200_ERR_UNSUPPORTED, "externalForce on a distributed node would be counted once per sharing rank on interface nodes");
     cudaStream_t s = n->ctx->stream;
     const bool on = ext_host != nullptr;
     if (on != n->has_ext) { n->has_ext = on; n->invalidate_graphs(); }
     if (!on) return SOFAB200_OK;
     if (!n->ext.p) SB_TRY(n->ext.alloc(3 * n->n));
     SB_CUDA(cudaMemcpyAsync(n->ext.p, ext_host, 3 * n->n * sizeof(R), cudaMemcpyHostToDevice, s));
-    LAUNCH(n->ctx, (ext_accumulate_kernel<R>), vec_grid(3 * n->n, n->ctx->sm_count), kVecBlock, 3 * n->n, n->ext.p);
+    SB_TRY(node_finish_external_force(n));
     if (sync) SB_CUDA(cudaStreamSynchronize(s));
     return SOFAB200_OK;
 }
@@ -940,7 +946,6 @@ template <class R> static int node_step_pipelined(Node<R>* n, R* x_dev, R* v_dev
     if (ext_host) {
         // this step's forces go up on their own stream, under whatever step is still running; the main stream only moves them from the staging
         // buffer into the vector the captured step reads (a device-to-device copy) once the previous step is through
-        if (n->distributed()) return fail(SOFAB200_ERR_UNSUPPORTED, "externalForce on a distributed node would be counted once per sharing rank on interface nodes");
         if (!n->has_ext) { n->has_ext = true; n->invalidate_graphs(); }
         if (!n->ext.p) SB_TRY(n->ext.alloc(3 * n->n));
         if (n->ext_used_recorded) SB_CUDA(cudaStreamWaitEvent(n->up_stream, n->ev_ext_used, 0));    // (the staging buffer has been consumed)
@@ -948,7 +953,7 @@ template <class R> static int node_step_pipelined(Node<R>* n, R* x_dev, R* v_dev
         SB_CUDA(cudaEventRecord(n->ev_h2d, n->up_stream));
         SB_CUDA(cudaStreamWaitEvent(s, n->ev_h2d, 0));
         SB_CUDA(cudaMemcpyAsync(n->ext.p, n->ext_stage.p, bytes, cudaMemcpyDeviceToDevice, s));
-        LAUNCH(n->ctx, (ext_accumulate_kernel<R>), vec_grid(3 * n->n, n->ctx->sm_count), kVecBlock, 3 * n->n, n->ext.p);
+        SB_TRY(node_finish_external_force(n));
         SB_CUDA(cudaEventRecord(n->ev_ext_used, s));
         n->ext_used_recorded = true;
     } else SB_TRY(node_upload_external_force(n, nullptr, false));

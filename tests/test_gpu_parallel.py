@@ -42,6 +42,9 @@ def _worker(rank, world, port, cfg_name, dtype_name, mode, q_out):
         node.be.compute_force(node.f, node.be.x)      # rotations at rest
         q_loc = node.apply(node.be.new_vector(), p_loc, 1.001, -0.01, -0.0011)
         q_glob = node.gather_global(q_loc, pos.shape[0])
+        if native:      # MechanicalObject's externalForce on a partitioned node: every rank passes the rows of its nodes, the owner's copy of an interface node keeps them
+            ext_glob = (0.05 * np.random.default_rng(1).standard_normal(pos.shape)).astype(np.float32 if dtype_name == "f32" else np.float64)
+            node.be.node.set_external_force(ext_glob[rm.global_ids])
         its = [node.step() for _ in range(3)]
         if native:
             its = [node.be.node.last_solve()["iterations"]] * 3
@@ -84,6 +87,8 @@ def test_n_gpus_match_single_domain_oracle(dtype_name, mode, world):
     q_ref = s.apply(p_glob, 1.001, -0.01, -0.0011)
     err = np.linalg.norm(res["q"] - q_ref) / np.linalg.norm(q_ref)
     assert err <= (1e-14 if dtype == np.float64 else 1e-6), err      # only the interface sums are associated differently
+    if mode != "torch":
+        s.set_external_force((0.05 * np.random.default_rng(1).standard_normal(pos.shape)).astype(dtype))
     its_ref = [s.step() for _ in range(3)]
     assert all(abs(a - b) <= 1 for a, b in zip(res["its"], its_ref))
     assert np.abs(res["x"] - s.get("x")).max() <= (1e-7 if dtype == np.float64 else 1e-4)
