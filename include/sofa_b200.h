@@ -115,6 +115,9 @@ int sofab200_mo_vdot_dev(sofab200_ctx* ctx, sofab200_real real, size_t n, const 
 /* MechanicalObject::vMultiOp integration fast path [MO]:2208-2241: v += a*f_v_a ; x += v*f_x_v. */
 int sofab200_mo_vmultiop_integrate(sofab200_ctx* ctx, sofab200_real real, size_t n, void* v_dev, void* x_dev, const void* a_dev, double f_v_a, double f_x_v);
 
+/* MechanicalObject::accumulateForce [MO]:1356-1375: f[i] += externalForce[i] for every row of externalForce that differs from Deriv(). */
+int sofab200_mo_accumulate_force(sofab200_ctx* ctx, sofab200_real real, size_t n, void* f_dev, const void* ext_dev);
+
 /* ------------------------------------------------------------------------------------------------ */
 /* DiagonalMass / FixedProjectiveConstraint pieces of A*p and of the right-hand side                  */
 /* ------------------------------------------------------------------------------------------------ */

@@ -76,6 +76,7 @@ SYMBOLS = {
     "sofab200_mo_vdot": (_I, [_P, _I, _SZ, _P, _P, C.POINTER(_D)]),
     "sofab200_mo_vdot_dev": (_I, [_P, _I, _SZ, _P, _P, _P, _P]),
     "sofab200_mo_vmultiop_integrate": (_I, [_P, _I, _SZ, _P, _P, _P, _D, _D]),
+    "sofab200_mo_accumulate_force": (_I, [_P, _I, _SZ, _P, _P]),
     "sofab200_mass_add_mdx": (_I, [_P, _I, _SZ, _P, _P, _P, _D]),
     "sofab200_plane_add_force": (_I, [_P, _I, _SZ, _P, _P, _P, C.POINTER(PlaneDesc), _P]),
     "sofab200_plane_add_dforce": (_I, [_P, _I, _SZ, _P, _P, C.POINTER(PlaneDesc), _P, _D]),

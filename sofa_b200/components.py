@@ -161,6 +161,11 @@ class MechanicalObject:
     def resetForce(self, f=None):
         return self.vOp(self.f if f is None else f)
 
+    def accumulateForce(self, f, externalForce):
+        """MechanicalObject::accumulateForce (MechanicalObject.inl:1356-1375): f[i] += externalForce[i] for the rows that differ from Deriv()."""
+        check(self.ctx.L.sofab200_mo_accumulate_force(self.ctx.h, self.real, self.size, _dptr(f), _dptr(externalForce)))
+        return f
+
 
 class TetrahedronFEMForceField:
     """TetrahedronFEMForceField<B200Vec3Types>.  Data: youngModulus, poissonRatio, method, localStiffnessFactor,

@@ -571,6 +571,14 @@ int sofab200_mo_vmultiop_integrate(sofab200_ctx* ctx, sofab200_real real, size_t
     else LAUNCH(ctx, (integrate_kernel<double>), g, kVecBlock, n3, (double*)v_dev, (double*)x_dev, (const double*)a_dev, f_v_a, int(f_v_a == 1.0), f_x_v);
     return SOFAB200_OK;
 }
+int sofab200_mo_accumulate_force(sofab200_ctx* ctx, sofab200_real real, size_t n, void* f_dev, const void* ext_dev) {
+    SB_CHECK(ctx && f_dev && ext_dev, "null argument");
+    if (n == 0) return SOFAB200_OK;
+    const int g = vec_grid(n, ctx->sm_count);
+    if (real == SOFAB200_F32) LAUNCH(ctx, (accumulate_force_kernel<float>), g, kVecBlock, n, (float*)f_dev, (const float*)ext_dev);
+    else LAUNCH(ctx, (accumulate_force_kernel<double>), g, kVecBlock, n, (double*)f_dev, (const double*)ext_dev);
+    return SOFAB200_OK;
+}
 int sofab200_mass_add_mdx(sofab200_ctx* ctx, sofab200_real real, size_t n, void* res_dev, const void* dx_dev, const void* m_dev, double factor) {
     SB_CHECK(ctx && res_dev && dx_dev && m_dev, "null argument");
     if (n == 0) return SOFAB200_OK;

@@ -32,6 +32,14 @@ template <class R, int KIND> __global__ void __launch_bounds__(kVecBlock) vop_ke
     }
 }
 
+// MechanicalObject::accumulateForce, MechanicalObject.inl:1356-1375: f[i] += externalForce[i] for the rows that differ from Deriv()
+template <class R> __global__ void __launch_bounds__(kVecBlock) accumulate_force_kernel(size_t n, R* __restrict__ f, const R* __restrict__ ext) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        const R a = ext[3 * i], b = ext[3 * i + 1], c = ext[3 * i + 2];
+        if (!(a == R(0) && b == R(0) && c == R(0))) { f[3 * i] += a; f[3 * i + 1] += b; f[3 * i + 2] += c; }
+    }
+}
+
 // what the last CTA does with a finished dot product
 enum DotFinish { DF_STORE = 0, DF_CG_NORMB = 1, DF_CG_RHO = 2 };
 

@@ -1,4 +1,4 @@
-// SOFA-side glue: MechanicalObject<B200Vec3Types>::vOp / vMultiOp / vDot / resetForce, each forwarding to one C-ABI entry point (the set SofaCUDA
+// SOFA-side glue: MechanicalObject<B200Vec3Types>::vOp / vMultiOp / vDot / resetForce / accumulateForce, each forwarding to one C-ABI entry point (the set SofaCUDA
 // specialises for the same scenes: applications/plugins/SofaCUDA/Component/src/SofaCUDA/component/statecontainer/CudaMechanicalObject.h:133-142).
 #include <sofa/component/statecontainer/MechanicalObject.inl>
 #include <sofa/core/ObjectFactory.h>
@@ -63,6 +63,14 @@ template <class MO> void* b200_vec(MO* mo, core::ConstVecId id, bool write) {
         /* resetDataTypeVec of the force vector (MechanicalObject.inl:2497-2505) = vOp(f) with null operands */                      \
         if (sofab200_mo_vop(sofa::b200::threadContext(), B200Vec3Types<TReal>::abiReal, this->getSize(), b200_vec(this, core::ConstVecId(f), true), \
                             nullptr, nullptr, 0.0) != SOFAB200_OK)                                                                   \
+            msg_error() << sofab200_last_error();                                                                                    \
+    }                                                                                                                                \
+    template <> void MechanicalObject<B200Vec3Types<TReal>>::accumulateForce(const core::ExecParams*, core::VecDerivId f) {         \
+        /* MechanicalObject.inl:1356-1375: f += externalForce for the rows that differ from Deriv(), only when the Data is not empty */ \
+        const VecDeriv& ext = this->read(core::vec_id::read_access::externalForce)->getValue();                                      \
+        if (ext.empty()) return;                                                                                                     \
+        if (sofab200_mo_accumulate_force(sofa::b200::threadContext(), B200Vec3Types<TReal>::abiReal, ext.size(), b200_vec(this, core::ConstVecId(f), true), \
+                                         ext.deviceRead()) != SOFAB200_OK)                                                           \
             msg_error() << sofab200_last_error();                                                                                    \
     }
 B200_MO(float)

@@ -58,3 +58,23 @@ def test_pipelined_step_equals_synchronous_step(dtype):
     got.append(out[(K - 1) & 1].numpy().copy())
     for k in range(K):
         assert got[k].tobytes() == ref[k].tobytes(), k
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_mo_accumulate_force_per_operation(dtype):
+    """sofab200_mo_accumulate_force == MechanicalObject::accumulateForce: f[i] += ext[i] only for rows that differ from Deriv() (a row of zeros,
+    signed or not, leaves f untouched -- so a -0 in f survives there, and `-0 + ext` rounds as the reference's `+=` does elsewhere)."""
+    import sofa_b200 as sb
+    from gpu_common import dev, mesh
+    c, pos, hexas, tets, fixed = mesh("C1")
+    mo = sb.MechanicalObject(sb.Context(0), "B200Vec3f" if dtype == np.float32 else "B200Vec3d", position=pos)
+    rng = np.random.default_rng(23)
+    f = rng.standard_normal(pos.shape).astype(dtype); f[5] = -0.0
+    ext = rng.standard_normal(pos.shape).astype(dtype); ext[::2] = 0; ext[4, 1] = -0.0; ext[5] = -0.0
+    ref = f.copy()
+    for i in range(pos.shape[0]):
+        if not (ext[i] == 0).all():
+            ref[i] += ext[i]
+    f_d = dev(mo, f)
+    mo.accumulateForce(f_d, dev(mo, ext))
+    assert f_d.cpu().numpy().tobytes() == ref.tobytes()
